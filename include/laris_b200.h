@@ -1,0 +1,220 @@
+/*
+ * laris_b200.h - C ABI of the B200-native LARIS per-cell LR scoring path.
+ *
+ * The reference (genecell/LARIS) has no FFI/plugin interface: its boundary is
+ * the Python call surface laris.tl.prepareLRInteraction / laris.tl.runLARIS
+ * (reference laris/tools/__init__.py:29-34, :121-153) and it dispatches the
+ * arithmetic to compiled routines inside scikit-learn / scipy / numpy.  Each
+ * entry point below replaces one of those dispatches; the comment on each
+ * names the reference call site it stands in for.  INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless it says "host";
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     nothing synchronises the host unless the comment says so;
+ *   - return value: 0 = ok, <0 = error (LARIS_E_*); text via laris_last_error();
+ *   - scratch memory is taken from the stream-ordered allocator
+ *     (cudaMallocAsync/cudaFreeAsync on `stream`), never from the caller's buffers;
+ *   - row-major everywhere; "ld" is a row stride in ELEMENTS.
+ */
+#ifndef LARIS_B200_H
+#define LARIS_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define LARIS_API __attribute__((visibility("default")))
+#else
+#define LARIS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LARIS_OK 0
+#define LARIS_E_ARG (-1)     /* bad argument */
+#define LARIS_E_CUDA (-2)    /* CUDA runtime error */
+#define LARIS_E_LIMIT (-3)   /* size exceeds a compiled limit */
+
+#define LARIS_ABI_VERSION 1
+
+LARIS_API int laris_abi_version(void);
+/* Number of kernels this library has launched in the process so far (bench.py's gpu_launches). */
+LARIS_API int64_t laris_launch_count(void);
+/* Thread-local text of the last error returned on this thread (host pointer). */
+LARIS_API const char* laris_last_error(void);
+
+/* ---------------------------------------------------------------- K1 ----
+ * Exact Euclidean kNN graph on a uniform grid, rows ascending by distance.
+ * Replaces sklearn.neighbors.kneighbors_graph(mode='distance') at
+ * laris/tools/__init__.py:83-88 (include_self=1) and laris/tools/_utils.py:385-390,
+ * :847-852 (include_self=0: query k+1, drop the row's own index, or the first
+ * entry when the row id is absent).  d^2 = ((0+dx*dx)+dy*dy[+dz*dz]) in fp64
+ * without FMA, then IEEE sqrt; ties ordered by (d^2, index).
+ *   xy        [n*dim] fp64, dim in {2,3}
+ *   out_idx   [n*k]   int32 neighbour ids (the CSR 'indices'; indptr = i*k)
+ *   out_dist  [n*k]   fp64 distances (the CSR 'data' before the weight transform)
+ *   out_order [n]     int32 spatial processing order (grid-cell sorted), may be NULL
+ * Requires k(+1 if !include_self) <= 64 and n >= k+1.  Synchronises once
+ * (reads the bounding box back to size the grid).
+ */
+LARIS_API int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int include_self,
+                    int32_t* out_idx, double* out_dist, int32_t* out_order, void* stream);
+
+/* w = 1/exp(d/s), s = sigma if sigma > 0 else mean(all m distances)/2.
+ * Replaces the .data transforms at laris/tools/__init__.py:89 and
+ * laris/tools/_utils.py:392, :853.  Either output may be NULL.
+ * scale_out (device, 1 double, may be NULL) receives s. */
+LARIS_API int laris_decay_weights(const double* dist, int64_t m, double sigma, double* w64, float* w32,
+                        double* scale_out, void* stream);
+
+/* ------------------------------------------------------- gene selection --
+ * Restrict a CSR expression matrix to the genes the LR table uses and pack it
+ * for the diffusion kernel (part of the fancy-index gathers at
+ * laris/tools/__init__.py:100, :113-114).
+ *   indptr [n+1] int64, indices [nnz] int32, data [nnz] fp32
+ *   gene_map [G] int32: new column id in [0,G_u) or -1 to drop
+ * Phase 1 writes per-row kept counts to out_counts[n] (int64); the caller
+ * exclusive-scans them (laris_exclusive_scan_i64) into out_indptr[n+1];
+ * phase 2 writes packed entries {int32 col, fp32 val} as int64 words,
+ * dropping explicitly stored zeros.
+ */
+LARIS_API int laris_csr_select_count(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
+                           const int32_t* gene_map, int64_t* out_counts, void* stream);
+LARIS_API int laris_csr_select_fill(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
+                          const int32_t* gene_map, const int64_t* out_indptr, int64_t* out_packed,
+                          void* stream);
+/* out[0]=0, out[i+1]=sum(in[0..i]); in [n], out [n+1]; may alias in == out+1 is NOT allowed. */
+LARIS_API int laris_exclusive_scan_i64(const int64_t* in, int64_t n, int64_t* out, void* stream);
+
+/* ------------------------------------------------------------- K2+K3 ----
+ * Fused neighbour-aggregated expression + per-cell LR score:
+ *   D[i,g] = sum_j w[i,j] * Xu[idx[i,j], g]
+ *   S[i,p] = D[i,lig[p]] * D[i,rec[p]] * [Xu[i,lig[p]] != 0 || Xu[i,rec[p]] != 0]
+ * Replaces the SpGEMM at laris/tools/__init__.py:91-92, the row gathers and
+ * product at :100 and the expression mask at :110-117.  D is never written
+ * to HBM.
+ *   xu_indptr [n+1] int64, xu_packed [nnz] from laris_csr_select_fill
+ *   idx [n*k] int32, w [n*k] fp32 (K1 outputs; include_self graph)
+ *   order [n] int32 processing order or NULL
+ *   lig, rec [P] int32 in [0,G_u)
+ *   S [n*ldS] fp32 (ldS >= P, ldS % 4 == 0, base 16-byte aligned); columns [P,ldS) are zeroed
+ *   row_nnz [n] int64 number of non-zero scores per cell (scan it for the CSR indptr), may be NULL
+ */
+LARIS_API int laris_diffuse_lr_score(const int64_t* xu_indptr, const int64_t* xu_packed, int64_t n, int32_t G_u,
+                           const int32_t* idx, const float* w, int k, const int32_t* order,
+                           const int32_t* lig, const int32_t* rec, int32_t P,
+                           float* S, int64_t ldS, int64_t* row_nnz, void* stream);
+
+/* Dense S -> CSR (the reference's lr_adata.X, laris/tools/__init__.py:104,117):
+ * indptr [n+1] int64 = exclusive scan of row_nnz; writes column-sorted
+ * indices [nnz] int32 and data [nnz] fp32 holding exactly the non-zero scores. */
+LARIS_API int laris_csr_compact(const float* S, int64_t ldS, int64_t n, int32_t P, const int64_t* indptr,
+                      int32_t* out_indices, float* out_data, void* stream);
+/* CSR -> dense S (for a caller-supplied lr_adata.X); zero-fills then scatters. */
+LARIS_API int laris_csr_to_dense(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
+                       int32_t P, float* S, int64_t ldS, void* stream);
+
+/* ---------------------------------------------------------------- K4 ----
+ * Per-pair spatial statistics in ONE pass over S, T never materialised:
+ *   T[i,p] = sum_j w[i,j] * S[idx[i,j], p]   (/ sum_j w[i,j] if l1_normalise)
+ *   out[0,p]=sum_i S*T  out[1,p]=sum_i S^2  out[2,p]=sum_i T^2
+ *   out[3,p]=sum_i S    out[4,p]=#{i: S != 0}
+ * Replaces `genexcell @ cellxcell.T` + _rowwise_cosine_similarity at
+ * laris/tools/__init__.py:468-470 / laris/tools/_utils.py:81-101 (observed graph,
+ * l1_normalise=0) and normalize + SpMM + cosine at laris/tools/_utils.py:512-516
+ * (random graph, l1_normalise=1; duplicate (row,col) edges add, as in the
+ * reference's COO->CSR).  Sums 3-4 also feed n_cells_by_counts
+ * (laris/tools/__init__.py:493-504) and the (mean, variance) features of
+ * laris/tools/_utils.py:1081-1088.  Accumulation fp64, deterministic.
+ *   out [5*P] fp64
+ */
+LARIS_API int laris_spatial_stats(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* idx,
+                        const float* w, int k, int l1_normalise, const int32_t* order, double* out,
+                        void* stream);
+
+/* Random-neighbour graph of one null repeat, device RNG (Philox4x32-10 +
+ * Feistel permutation; spec in laris_b200/csrc/rng.cuh, CPU twin oracle/rng.py):
+ *   cols[e] uniform in [0,n),  wout[e] = w[perm(e)]  for e in [0, n*k)
+ * Replaces np.random.choice + np.random.shuffle at laris/tools/_utils.py:436-442. */
+LARIS_API int laris_null_graph_philox(int64_t n, int k, const float* w, int32_t repeat, uint64_t seed,
+                            int32_t* cols, float* wout, void* stream);
+/* wout[e] = w[perm[e]] for a host-replayed numpy permutation (rng="numpy"). */
+LARIS_API int laris_gather_f32(const float* w, const int64_t* perm, int64_t m, float* wout, void* stream);
+
+/* ---------------------------------------------------------------- K5 ----
+ * Neighbourhood composition N[i,a] = sum of w[i,j] over neighbours j of type a
+ * (cluster_mat @ cellxcell.T, laris/tools/_utils.py:839-856), cell-major.
+ *   labels [n] int32 in [0,C); Ncomp [n*C] fp32 */
+LARIS_API int laris_neighborhood_composition(const int32_t* labels, const int32_t* idx, const float* w, int64_t n,
+                                   int k, int32_t C, float* Ncomp, void* stream);
+
+/* Cell-type-pair contraction (the dense contraction over cells):
+ *   num[p, a*C+b] = sum_i S[i,p] * N[i,a] * N[i,b]
+ *   qnorm2[a*C+b] = sum_i (N[i,a]*N[i,b])^2
+ * Replaces _pairwise_row_multiply + sklearn cosine_similarity at
+ * laris/tools/_utils.py:859-866.  impl: 0 = tcgen05 tensor-core kernel
+ * (split-bf16 operands, fp32 TMEM accumulation), 1 = fp32 CUDA-core kernel.
+ *   num [P*C*C] fp64, qnorm2 [C*C] fp64 */
+LARIS_API int laris_celltype_pair_contract(const float* S, int64_t ldS, int64_t n, int32_t P, const float* Ncomp,
+                                 int32_t C, double* num, double* qnorm2, int impl, void* stream);
+
+/* cnt[c*P + p] = #{i : labels[i]==c and S[i,p] != 0}.  Replaces
+ * _compute_avg_expression on the binarised scores (laris/tools/_utils.py:1325-1337,
+ * :334-338); frac = cnt / n_c on the host.  counts [C*P] uint64.  C <= 100. */
+LARIS_API int laris_celltype_nonzero_count(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* labels,
+                                 int32_t C, uint64_t* counts, void* stream);
+/* One-hot contraction straight from a packed CSR (laris_csr_select_fill layout):
+ * sum[c*G_u+g] = sum of Xu over cells of type c, cnt = non-zero count, colsq[g] =
+ * sum_i Xu[i,g]^2.  These are the numerators / norms of the cosine between a
+ * gene and the one-hot group indicator in cosg.cosg (call site
+ * laris/tools/_utils.py:580-588) and its low-expression mask.  fp64 outputs. */
+LARIS_API int laris_onehot_contract_csr(const int64_t* indptr, const int64_t* packed, int64_t n, int32_t G_u,
+                              const int32_t* labels, int32_t C, double* sum, double* cnt, double* colsq,
+                              void* stream);
+
+/* ---------------------------------------------------------------- K6 ----
+ * Exceedance counts of the background-resampling null
+ * (laris/tools/_utils.py:1518-1596).  Row r = (group g, pair s), s over ALL pairs:
+ *   obs = table[g*ldt + s]; null_t = table[g*ldt + bg[s*nb + draw_t]]
+ *   ge[r] += #{t: null_t >= obs}, nz[r] += #{t: null_t > 0}, ge_nz[r] += #{both}
+ * (pairs outside the ranked list carry 0.0 in the table, reference :1563, and
+ * are skipped as rows through active[s] == 0).
+ * rng_mode 0: Philox draws keyed by (seed, global row id, t) with global row id
+ *   = (g0+g)*P_global + (slot_gid ? slot_gid[s] : s) and t in [t0, t0+n_perm) -
+ *   independent of how pairs / groups / permutations are sharded;
+ * rng_mode 1: draws [n_groups*n_slots*n_perm] uint8 supplied by the caller
+ *   (host replay of the reference's numpy stream).
+ *   table [n_groups*ldt] fp64, bg [n_slots*nb] int32, active [n_slots] uint8 or NULL
+ *   ge, nz, ge_nz [n_groups*n_slots] int32, accumulated into (zero them first)
+ */
+LARIS_API int laris_pvalue_counts(const double* table, int64_t ldt, int32_t n_groups, int32_t n_slots,
+                        const int32_t* bg, int32_t nb, const uint8_t* active, const int64_t* slot_gid,
+                        int64_t P_global, int32_t g0, int32_t t0, int32_t n_perm, int rng_mode,
+                        uint64_t seed, const uint8_t* draws, int32_t* ge, int32_t* nz, int32_t* ge_nz,
+                        void* stream);
+
+/* ---------------------------------------------------------------- K7 ----
+ * Benjamini-Hochberg per group (statsmodels multipletests 'fdr_bh' at
+ * laris/tools/_utils.py:1636-1646): p [n_groups*len] fp64, sel [n_groups*len]
+ * uint8 marks the tested rows; out fdr [n_groups*len] fp64 (1.0 where !sel). */
+LARIS_API int laris_bh_fdr(const double* p, const uint8_t* sel, int32_t n_groups, int32_t len, double* fdr,
+                 void* stream);
+
+/* ------------------------------------------------- laris.pp helpers ----
+ * Device versions of the three helpers the reference re-exports as laris.pp
+ * (laris/preprocessing/__init__.py:28-38).
+ * out[r] = <A_r,B_r>/(|A_r||B_r|), 0 when the denominator is 0
+ * (_rowwise_cosine_similarity, laris/tools/_utils.py:81-101); dense fp32 inputs. */
+LARIS_API int laris_rowwise_cosine(const float* A, const float* B, int64_t rows, int64_t cols, int64_t lda,
+                                   int64_t ldb, double* out, void* stream);
+/* out[(a*C+b)*n + i] = M[a*n+i] * M[b*n+i]  (_pairwise_row_multiply,
+ * laris/tools/_utils.py:208-245); M [C*n] fp32, out [C*C*n] fp32. */
+LARIS_API int laris_pairwise_row_multiply(const float* M, int32_t C, int64_t n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LARIS_B200_H */

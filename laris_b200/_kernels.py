@@ -1,0 +1,212 @@
+"""Torch-tensor carriers around the C ABI.  Tensors only provide device memory
+and the stream; every arithmetic step is a call into liblaris_b200.so."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError("expected a contiguous CUDA tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"expected {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("laris_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device(a, dtype):
+    """numpy -> device tensor of ``dtype`` (async when the source is pinned)."""
+    a = np.ascontiguousarray(a)
+    t = torch.from_numpy(a) if a.dtype != np.dtype(object) else None
+    if t is None:
+        raise TypeError("object arrays cannot be uploaded")
+    dev = require_cuda()
+    return t.to(dev, dtype=dtype, non_blocking=t.is_pinned())
+
+
+# ----------------------------------------------------------------- K1 ----
+def knn_graph(xy, k, include_self, want_order=True):
+    n, dim = xy.shape
+    dev = xy.device
+    idx = torch.empty((n, k), dtype=torch.int32, device=dev)
+    dist = torch.empty((n, k), dtype=torch.float64, device=dev)
+    order = torch.empty(n, dtype=torch.int32, device=dev) if want_order else None
+    check(lib.laris_knn_graph(_ptr(xy, torch.float64), n, dim, k, int(bool(include_self)), _ptr(idx), _ptr(dist),
+                              _ptr(order), _stream()), "laris_knn_graph")
+    return idx, dist, order
+
+
+def decay_weights(dist, sigma=None, want64=False):
+    m = dist.numel()
+    w32 = torch.empty(dist.shape, dtype=torch.float32, device=dist.device)
+    w64 = torch.empty(dist.shape, dtype=torch.float64, device=dist.device) if want64 else None
+    scale = torch.empty(1, dtype=torch.float64, device=dist.device)
+    check(lib.laris_decay_weights(_ptr(dist, torch.float64), m, float(sigma) if sigma else 0.0, _ptr(w64), _ptr(w32),
+                                  _ptr(scale), _stream()), "laris_decay_weights")
+    return w32, w64, scale
+
+
+# ------------------------------------------------------ gene selection ----
+def exclusive_scan(counts):
+    out = torch.empty(counts.numel() + 1, dtype=torch.int64, device=counts.device)
+    check(lib.laris_exclusive_scan_i64(_ptr(counts, torch.int64), counts.numel(), _ptr(out), _stream()),
+          "laris_exclusive_scan_i64")
+    return out
+
+
+def csr_select(indptr, indices, data, gene_map):
+    """(indptr_u int64[n+1], packed int64[nnz_u]) restricted to gene_map >= 0."""
+    n = indptr.numel() - 1
+    counts = torch.empty(n, dtype=torch.int64, device=indptr.device)
+    check(lib.laris_csr_select_count(_ptr(indptr, torch.int64), _ptr(indices, torch.int32), _ptr(data, torch.float32), n,
+                                     _ptr(gene_map, torch.int32), _ptr(counts), _stream()), "laris_csr_select_count")
+    out_indptr = exclusive_scan(counts)
+    nnz = int(out_indptr[-1].item())
+    packed = torch.empty(max(nnz, 1), dtype=torch.int64, device=indptr.device)
+    check(lib.laris_csr_select_fill(_ptr(indptr), _ptr(indices), _ptr(data), n, _ptr(gene_map), _ptr(out_indptr),
+                                    _ptr(packed), _stream()), "laris_csr_select_fill")
+    return out_indptr, packed[:nnz] if nnz else packed[:0]
+
+
+# -------------------------------------------------------------- K2+K3 ----
+def padded_ld(P):
+    return (P + 7) // 8 * 8
+
+
+def diffuse_lr_score(xu_indptr, xu_packed, G_u, idx, w, order, lig, rec, want_row_nnz=True):
+    n, k = idx.shape
+    P = lig.numel()
+    ld = padded_ld(P)
+    S = torch.empty((n, ld), dtype=torch.float32, device=idx.device)
+    row_nnz = torch.empty(n, dtype=torch.int64, device=idx.device) if want_row_nnz else None
+    packed_ptr = xu_packed.data_ptr() if xu_packed.numel() else _ptr(torch.zeros(1, dtype=torch.int64, device=idx.device))
+    check(lib.laris_diffuse_lr_score(_ptr(xu_indptr, torch.int64), packed_ptr, n, G_u, _ptr(idx, torch.int32),
+                                     _ptr(w, torch.float32), k, _ptr(order, torch.int32) if order is not None else None,
+                                     _ptr(lig, torch.int32), _ptr(rec, torch.int32), P, _ptr(S), ld, _ptr(row_nnz),
+                                     _stream()), "laris_diffuse_lr_score")
+    return S, row_nnz
+
+
+def csr_compact(S, P, row_nnz):
+    n, ld = S.shape
+    indptr = exclusive_scan(row_nnz)
+    nnz = int(indptr[-1].item())
+    indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=S.device)
+    data = torch.empty(max(nnz, 1), dtype=torch.float32, device=S.device)
+    check(lib.laris_csr_compact(_ptr(S, torch.float32), ld, n, P, _ptr(indptr), _ptr(indices), _ptr(data), _stream()),
+          "laris_csr_compact")
+    return indptr, indices[:nnz], data[:nnz]
+
+
+def csr_to_dense(indptr, indices, data, n, P):
+    ld = padded_ld(P)
+    S = torch.empty((n, ld), dtype=torch.float32, device=indptr.device)
+    check(lib.laris_csr_to_dense(_ptr(indptr, torch.int64), _ptr(indices, torch.int32) if indices.numel() else None,
+                                 _ptr(data, torch.float32) if data.numel() else None, n, P, _ptr(S), ld, _stream()),
+          "laris_csr_to_dense")
+    return S
+
+
+# ----------------------------------------------------------------- K4 ----
+def spatial_stats(S, P, idx, w, l1_normalise, order=None):
+    n, ld = S.shape
+    k = idx.shape[1]
+    out = torch.empty((5, P), dtype=torch.float64, device=S.device)
+    check(lib.laris_spatial_stats(_ptr(S, torch.float32), ld, n, P, _ptr(idx, torch.int32), _ptr(w, torch.float32), k,
+                                  int(bool(l1_normalise)), _ptr(order, torch.int32) if order is not None else None,
+                                  _ptr(out), _stream()), "laris_spatial_stats")
+    return out
+
+
+def null_graph_philox(n, k, w, repeat, seed):
+    cols = torch.empty((n, k), dtype=torch.int32, device=w.device)
+    wout = torch.empty((n, k), dtype=torch.float32, device=w.device)
+    check(lib.laris_null_graph_philox(n, k, _ptr(w, torch.float32), int(repeat), int(seed) & (2 ** 64 - 1), _ptr(cols),
+                                      _ptr(wout), _stream()), "laris_null_graph_philox")
+    return cols, wout
+
+
+def gather_f32(w, perm):
+    out = torch.empty(perm.shape, dtype=torch.float32, device=w.device)
+    check(lib.laris_gather_f32(_ptr(w, torch.float32), _ptr(perm, torch.int64), perm.numel(), _ptr(out), _stream()),
+          "laris_gather_f32")
+    return out
+
+
+# ----------------------------------------------------------------- K5 ----
+def neighborhood_composition(labels, idx, w, C):
+    n, k = idx.shape
+    N = torch.empty((n, C), dtype=torch.float32, device=idx.device)
+    check(lib.laris_neighborhood_composition(_ptr(labels, torch.int32), _ptr(idx, torch.int32), _ptr(w, torch.float32),
+                                             n, k, C, _ptr(N), _stream()), "laris_neighborhood_composition")
+    return N
+
+
+def celltype_pair_contract(S, P, N, impl=1):
+    n, ld = S.shape
+    C = N.shape[1]
+    num = torch.empty((P, C * C), dtype=torch.float64, device=S.device)
+    qn2 = torch.empty(C * C, dtype=torch.float64, device=S.device)
+    check(lib.laris_celltype_pair_contract(_ptr(S, torch.float32), ld, n, P, _ptr(N, torch.float32), C, _ptr(num),
+                                           _ptr(qn2), int(impl), _stream()), "laris_celltype_pair_contract")
+    return num, qn2
+
+
+def celltype_nonzero_count(S, P, labels, C):
+    n, ld = S.shape
+    cnt = torch.empty((C, P), dtype=torch.int64, device=S.device)
+    check(lib.laris_celltype_nonzero_count(_ptr(S, torch.float32), ld, n, P, _ptr(labels, torch.int32), C, _ptr(cnt),
+                                           _stream()), "laris_celltype_nonzero_count")
+    return cnt
+
+
+def onehot_contract_csr(xu_indptr, xu_packed, G_u, labels, C):
+    n = xu_indptr.numel() - 1
+    dev = xu_indptr.device
+    s = torch.empty((C, G_u), dtype=torch.float64, device=dev)
+    c = torch.empty((C, G_u), dtype=torch.float64, device=dev)
+    q = torch.empty(G_u, dtype=torch.float64, device=dev)
+    packed_ptr = xu_packed.data_ptr() if xu_packed.numel() else None
+    check(lib.laris_onehot_contract_csr(_ptr(xu_indptr, torch.int64), packed_ptr, n, G_u, _ptr(labels, torch.int32), C,
+                                        _ptr(s), _ptr(c), _ptr(q), _stream()), "laris_onehot_contract_csr")
+    return s, c, q
+
+
+# -------------------------------------------------------------- K6/K7 ----
+def pvalue_counts(table, bg, n_perm, *, active=None, seed=0, draws=None, slot_gid=None, P_global=None, g0=0, t0=0,
+                  out=None):
+    Gn, ldt = table.shape
+    P, nb = bg.shape
+    dev = table.device
+    if out is None:
+        out = tuple(torch.zeros((Gn, P), dtype=torch.int32, device=dev) for _ in range(3))
+    ge, nz, both = out
+    check(lib.laris_pvalue_counts(_ptr(table, torch.float64), ldt, Gn, P, _ptr(bg, torch.int32), nb,
+                                  _ptr(active, torch.uint8) if active is not None else None,
+                                  _ptr(slot_gid, torch.int64) if slot_gid is not None else None,
+                                  int(P if P_global is None else P_global), int(g0), int(t0), int(n_perm),
+                                  0 if draws is None else 1, int(seed) & (2 ** 64 - 1),
+                                  _ptr(draws, torch.uint8) if draws is not None else None,
+                                  _ptr(ge), _ptr(nz), _ptr(both), _stream()), "laris_pvalue_counts")
+    return ge, nz, both
+
+
+def bh_fdr(p, sel):
+    Gn, L = p.shape
+    out = torch.empty((Gn, L), dtype=torch.float64, device=p.device)
+    check(lib.laris_bh_fdr(_ptr(p, torch.float64), _ptr(sel, torch.uint8), Gn, L, _ptr(out), _stream()), "laris_bh_fdr")
+    return out

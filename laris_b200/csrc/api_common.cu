@@ -1,0 +1,89 @@
+// Error plumbing + small utility entry points of the C ABI.
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "scan.cuh"
+
+#include <atomic>
+
+namespace laris {
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+__global__ void gather_f32_kernel(const float* __restrict__ w, const int64_t* __restrict__ perm, int64_t m, float* __restrict__ out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < m) out[i] = w[perm[i]];
+}
+}  // namespace laris
+
+using namespace laris;
+
+extern "C" int laris_abi_version(void) { return LARIS_ABI_VERSION; }
+extern "C" int64_t laris_launch_count(void) { return (int64_t)g_launches.load(); }
+extern "C" const char* laris_last_error(void) { return g_err; }
+
+extern "C" int laris_exclusive_scan_i64(const int64_t* in, int64_t n, int64_t* out, void* stream) {
+    LARIS_CHECK_ARG(in && out && n >= 0, "laris_exclusive_scan_i64: bad arguments");
+    return exclusive_scan<int64_t>(in, n, out, (cudaStream_t)stream);
+}
+
+extern "C" int laris_gather_f32(const float* w, const int64_t* perm, int64_t m, float* wout, void* stream) {
+    LARIS_CHECK_ARG(w && perm && wout && m >= 0, "laris_gather_f32: bad arguments");
+    if (m == 0) return LARIS_OK;
+    gather_f32_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, (cudaStream_t)stream>>>(w, perm, m, wout);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
+// ---- generic helpers behind laris.pp (reference laris/preprocessing/__init__.py:28-38) ----
+namespace laris {
+__global__ void rowwise_cosine_kernel(const float* __restrict__ A, const float* __restrict__ B, int64_t rows, int64_t cols,
+                                      int64_t lda, int64_t ldb, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows) return;
+    double dot = 0.0, aa = 0.0, bb = 0.0;
+    for (int64_t c = lane; c < cols; c += 32) {
+        const double a = A[r * lda + c], b = B[r * ldb + c];
+        dot += a * b; aa += a * a; bb += b * b;
+    }
+    dot = warp_sum(dot); aa = warp_sum(aa); bb = warp_sum(bb);
+    if (lane == 0) {
+        const double den = sqrt(aa) * sqrt(bb);
+        out[r] = den != 0.0 ? dot / den : 0.0;
+    }
+}
+
+__global__ void pairwise_row_multiply_kernel(const float* __restrict__ M, int C, int64_t n, float* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int ab = blockIdx.y;
+    if (i >= n) return;
+    const int a = ab / C, b = ab - a * C;
+    out[(int64_t)ab * n + i] = M[(int64_t)a * n + i] * M[(int64_t)b * n + i];
+}
+}  // namespace laris
+
+extern "C" int laris_rowwise_cosine(const float* A, const float* B, int64_t rows, int64_t cols, int64_t lda, int64_t ldb,
+                                    double* out, void* stream) {
+    LARIS_CHECK_ARG(A && B && out && rows >= 0 && cols >= 0 && lda >= cols && ldb >= cols, "laris_rowwise_cosine: bad arguments");
+    if (rows == 0) return LARIS_OK;
+    rowwise_cosine_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(A, B, rows, cols, lda, ldb, out);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
+extern "C" int laris_pairwise_row_multiply(const float* M, int32_t C, int64_t n, float* out, void* stream) {
+    LARIS_CHECK_ARG(M && out && C >= 1 && C * C <= 65535 && n >= 0, "laris_pairwise_row_multiply: bad arguments");
+    if (n == 0) return LARIS_OK;
+    dim3 grid((unsigned)ceil_div(n, 256), (unsigned)(C * C));
+    pairwise_row_multiply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(M, C, n, out);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}

@@ -1,0 +1,232 @@
+// K5 family: cell-type contractions.
+//   neighborhood_composition  N[i,a] = sum of w over neighbours of type a
+//   celltype_nonzero_count    cnt[c,p] = #{i in c : S[i,p] != 0}            (-> frac)
+//   onehot_contract_csr       sum/cnt of Xu per (type, gene) + column sum of squares (-> COSG cosine)
+//   celltype_pair_contract    num[p,(a,b)] = sum_i S[i,p] N[i,a] N[i,b]   (fp32 CUDA-core tiles; the
+//                             tcgen05 variant lives in celltype_mma.cu)
+#include "common.cuh"
+
+namespace laris {
+
+__global__ void neighborhood_composition_kernel(const int32_t* __restrict__ labels, const int32_t* __restrict__ idx,
+                                                const float* __restrict__ w, int64_t n, int k, int C,
+                                                float* __restrict__ N) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float* row = N + i * C;                               // zeroed by the caller; this thread owns the row
+    for (int j = 0; j < k; ++j) row[labels[idx[i * k + j]]] += w[i * k + j];
+}
+
+// ---- counts of non-zero scores per (cell type, pair): thread owns 4 columns, CTA-private
+//      shared table [C][4][128] so increments never collide and never conflict on banks
+constexpr int kCcThreads = 128;
+
+__global__ void __launch_bounds__(kCcThreads)
+celltype_nonzero_count_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t n, int P,
+                              const int32_t* __restrict__ labels, int C, int nchunks,
+                              unsigned long long* __restrict__ counts /*[C][P]*/) {
+    extern __shared__ uint32_t tbl[];                      // [C][4][kCcThreads]
+    const int tid = threadIdx.x;
+    for (int q = tid; q < C * 4 * kCcThreads; q += kCcThreads) tbl[q] = 0;
+    __syncthreads();
+    const int64_t col4 = (int64_t)blockIdx.x * kCcThreads + tid;
+    if (col4 < ld4) {
+        for (int64_t i = blockIdx.y; i < n; i += nchunks) {
+            const float4 s = ld_stream_f4(S4 + i * ld4 + col4);
+            uint32_t* t = tbl + (size_t)labels[i] * 4 * kCcThreads + tid;
+            t[0] += s.x != 0.f;
+            t[kCcThreads] += s.y != 0.f;
+            t[2 * kCcThreads] += s.z != 0.f;
+            t[3 * kCcThreads] += s.w != 0.f;
+        }
+        for (int c = 0; c < C; ++c)
+            for (int u = 0; u < 4; ++u) {
+                const int64_t p = col4 * 4 + u;
+                const uint32_t v = tbl[((size_t)c * 4 + u) * kCcThreads + tid];
+                if (p < P && v) atomicAdd(&counts[(int64_t)c * P + p], (unsigned long long)v);
+            }
+    }
+}
+
+// ---- per (type, gene) sums straight from the packed CSR: warp per row
+__global__ void onehot_contract_csr_kernel(const int64_t* __restrict__ indptr, const int64_t* __restrict__ packed,
+                                           int64_t n, int G_u, const int32_t* __restrict__ labels,
+                                           double* __restrict__ sum, double* __restrict__ cnt, double* __restrict__ colsq) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    const int64_t base = (int64_t)labels[row] * G_u;
+    for (int64_t t = indptr[row] + lane; t < indptr[row + 1]; t += 32) {
+        const int64_t pk = packed[t];
+        const uint32_t g = (uint32_t)(pk & 0xffffffffll);
+        const double v = (double)__uint_as_float((uint32_t)((uint64_t)pk >> 32));
+        atomicAdd(&sum[base + g], v);
+        atomicAdd(&cnt[base + g], 1.0);
+        atomicAdd(&colsq[g], v * v);
+    }
+}
+
+// ---- ||Q_(ab)||^2 = sum_i (N[i,a] N[i,b])^2
+__global__ void pair_profile_norm_kernel(const float* __restrict__ N, int64_t n, int C, double* __restrict__ qnorm2) {
+    extern __shared__ float nt[];                          // [rows][C]
+    const int rows = 64;
+    const int64_t r0 = (int64_t)blockIdx.x * rows;
+    const int nr = (int)min((int64_t)rows, n - r0);
+    for (int q = threadIdx.x; q < nr * C; q += blockDim.x) nt[q] = N[r0 * C + q];
+    __syncthreads();
+    for (int ab = threadIdx.x; ab < C * C; ab += blockDim.x) {
+        const int a = ab / C, b = ab - a * C;
+        double s = 0.0;
+        for (int r = 0; r < nr; ++r) {
+            const float q = nt[r * C + a] * nt[r * C + b];
+            s += (double)(q * q);
+        }
+        if (s != 0.0) atomicAdd(&qnorm2[ab], s);
+    }
+}
+
+// ---- fp32 CUDA-core contraction: 64 (pairs) x 64 (type pairs) tile per CTA, 4x4 per thread,
+//      split over cells; partial sums are flushed to fp64 every kFlush cells
+constexpr int kCtTile = 64, kCtKc = 16, kCtThreads = 256, kCtFlush = 512;
+
+__global__ void __launch_bounds__(kCtThreads)
+celltype_pair_contract_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, int P, const float* __restrict__ N,
+                              int C, int64_t cells_per_split, double* __restrict__ num /*[P][C*C]*/) {
+    __shared__ float As[kCtKc][kCtTile + 4];               // [cell][pair]
+    __shared__ float Bs[kCtKc][kCtTile + 4];               // [cell][type pair]
+    extern __shared__ float Ns[];                          // [kCtKc][C]
+    const int CC = C * C;
+    const int p0 = blockIdx.x * kCtTile, q0 = blockIdx.y * kCtTile;
+    const int64_t i_beg = (int64_t)blockIdx.z * cells_per_split;
+    const int64_t i_end = min(n, i_beg + cells_per_split);
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;       // tx -> type-pair quad, ty -> pair quad
+    float acc[4][4] = {};
+    double dacc[4][4] = {};
+    int since_flush = 0;
+    for (int64_t i0 = i_beg; i0 < i_end; i0 += kCtKc) {
+        __syncthreads();
+        for (int q = tid; q < kCtKc * kCtTile; q += kCtThreads) {
+            const int r = q / kCtTile, c = q - r * kCtTile;
+            const int64_t i = i0 + r;
+            As[r][c] = (i < i_end && p0 + c < P) ? S[i * ldS + p0 + c] : 0.f;
+        }
+        for (int q = tid; q < kCtKc * C; q += kCtThreads) {
+            const int r = q / C;
+            const int64_t i = i0 + r;
+            Ns[q] = i < i_end ? N[i * C + (q - r * C)] : 0.f;
+        }
+        __syncthreads();
+        for (int q = tid; q < kCtKc * kCtTile; q += kCtThreads) {
+            const int r = q / kCtTile, c = q - r * kCtTile;
+            const int ab = q0 + c;
+            float v = 0.f;
+            if (ab < CC) { const int a = ab / C; v = Ns[r * C + a] * Ns[r * C + (ab - a * C)]; }
+            Bs[r][c] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kCtKc; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[r][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&Bs[r][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+        }
+        since_flush += kCtKc;
+        if (since_flush >= kCtFlush) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) { dacc[u][v] += (double)acc[u][v]; acc[u][v] = 0.f; }
+            since_flush = 0;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int p = p0 + ty * 4 + u, ab = q0 + tx * 4 + v;
+            const double val = dacc[u][v] + (double)acc[u][v];
+            if (p < P && ab < CC && val != 0.0) atomicAdd(&num[(int64_t)p * CC + ab], val);
+        }
+}
+
+}  // namespace laris
+
+using namespace laris;
+
+extern "C" int laris_neighborhood_composition(const int32_t* labels, const int32_t* idx, const float* w, int64_t n, int k,
+                                              int32_t C, float* Ncomp, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LARIS_CHECK_ARG(labels && idx && w && Ncomp && n > 0 && k >= 1 && C >= 1, "laris_neighborhood_composition: bad arguments");
+    LARIS_CUDA(cudaMemsetAsync(Ncomp, 0, (size_t)n * C * sizeof(float), st));
+    neighborhood_composition_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(labels, idx, w, n, k, C, Ncomp);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
+extern "C" int laris_celltype_nonzero_count(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* labels,
+                                            int32_t C, uint64_t* counts, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LARIS_CHECK_ARG(S && labels && counts && n > 0 && P >= 1 && C >= 1, "laris_celltype_nonzero_count: bad arguments");
+    LARIS_CHECK_ARG(ldS >= P && ldS % 4 == 0 && ((uintptr_t)S & 15) == 0, "laris_celltype_nonzero_count: S layout");
+    const size_t smem = (size_t)C * 4 * kCcThreads * sizeof(uint32_t);
+    if (smem > 200 * 1024) { set_error("laris_celltype_nonzero_count: C=%d exceeds the shared-memory table (limit 100)", C); return LARIS_E_LIMIT; }
+    LARIS_CUDA(cudaFuncSetAttribute(celltype_nonzero_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARIS_CUDA(cudaMemsetAsync(counts, 0, (size_t)C * P * sizeof(uint64_t), st));
+    const int64_t ld4 = ldS / 4;
+    const int slabs = (int)ceil_div(ld4, kCcThreads);
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    int64_t nchunks = ceil_div((int64_t)kNumSMs * per_sm, slabs);
+    if (nchunks > n) nchunks = n;
+    if (nchunks > 65535) nchunks = 65535;
+    dim3 grid((unsigned)slabs, (unsigned)nchunks);
+    celltype_nonzero_count_kernel<<<grid, kCcThreads, smem, st>>>((const float4*)S, ld4, n, P, labels, C, (int)nchunks,
+                                                                  (unsigned long long*)counts);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
+extern "C" int laris_onehot_contract_csr(const int64_t* indptr, const int64_t* packed, int64_t n, int32_t G_u,
+                                         const int32_t* labels, int32_t C, double* sum, double* cnt, double* colsq,
+                                         void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LARIS_CHECK_ARG(indptr && labels && sum && cnt && colsq && n > 0 && G_u >= 1 && C >= 1, "laris_onehot_contract_csr: bad arguments");
+    LARIS_CUDA(cudaMemsetAsync(sum, 0, (size_t)C * G_u * sizeof(double), st));
+    LARIS_CUDA(cudaMemsetAsync(cnt, 0, (size_t)C * G_u * sizeof(double), st));
+    LARIS_CUDA(cudaMemsetAsync(colsq, 0, (size_t)G_u * sizeof(double), st));
+    onehot_contract_csr_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(indptr, packed, n, G_u, labels, sum, cnt, colsq);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
+namespace laris {
+int celltype_pair_contract_mma(const float* S, int64_t ldS, int64_t n, int32_t P, const float* Ncomp, int32_t C,
+                               double* num, cudaStream_t st);   // celltype_mma.cu
+}
+
+extern "C" int laris_celltype_pair_contract(const float* S, int64_t ldS, int64_t n, int32_t P, const float* Ncomp,
+                                            int32_t C, double* num, double* qnorm2, int impl, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LARIS_CHECK_ARG(S && Ncomp && num && qnorm2 && n > 0 && P >= 1 && C >= 1 && ldS >= P, "laris_celltype_pair_contract: bad arguments");
+    LARIS_CHECK_ARG(impl == 0 || impl == 1, "laris_celltype_pair_contract: impl must be 0 (tcgen05) or 1 (fp32 CUDA cores)");
+    const int CC = C * C;
+    LARIS_CUDA(cudaMemsetAsync(num, 0, (size_t)P * CC * sizeof(double), st));
+    LARIS_CUDA(cudaMemsetAsync(qnorm2, 0, (size_t)CC * sizeof(double), st));
+    pair_profile_norm_kernel<<<(unsigned)ceil_div(n, 64), 256, 64 * C * sizeof(float), st>>>(Ncomp, n, C, qnorm2);
+    LARIS_LAUNCH_CHECK();
+    if (impl == 0) return celltype_pair_contract_mma(S, ldS, n, P, Ncomp, C, num, st);
+    const int tm = (int)ceil_div(P, kCtTile), tn = (int)ceil_div(CC, kCtTile);
+    int64_t splits = ceil_div((int64_t)kNumSMs * 4, (int64_t)tm * tn);
+    int64_t per = ceil_div(ceil_div(n, splits), kCtKc) * kCtKc;
+    if (per < kCtKc) per = kCtKc;
+    splits = ceil_div(n, per);
+    if (splits > 65535) { splits = 65535; per = ceil_div(ceil_div(n, splits), kCtKc) * kCtKc; splits = ceil_div(n, per); }
+    dim3 grid((unsigned)tm, (unsigned)tn, (unsigned)splits);
+    celltype_pair_contract_kernel<<<grid, kCtThreads, (size_t)kCtKc * C * sizeof(float), st>>>(S, ldS, n, P, Ncomp, C, per, num);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}

@@ -1,0 +1,373 @@
+// K1: exact Euclidean kNN on a uniform grid, emitted directly as fixed-degree CSR
+// (+ the distance-decay weight transform).  See include/laris_b200.h for the
+// reference call sites this replaces.
+//
+// Layout: points are binned into a uniform grid (~2.5 points per cell), a
+// counting sort gives the cell-ordered point list (which is also the spatial
+// processing order handed to the downstream kernels), and one thread per query
+// walks Chebyshev rings of cells until the k-th best distance is provably
+// smaller than anything outside the visited block.  Distances follow sklearn's
+// KD-tree arithmetic bit for bit: d2 = ((0 + dx*dx) + dy*dy [+ dz*dz]) with
+// separate fp64 multiply/add roundings (no FMA), then IEEE sqrt.
+#include <float.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace laris {
+
+struct GridSpec {
+    double lo[3];
+    double inv_h;
+    double h;
+    int g[3];
+    int dim;
+};
+
+// ------------------------------------------------------------------ bbox --
+__global__ void bbox_partial_kernel(const double* __restrict__ xy, int64_t n, int dim, double* __restrict__ part) {
+    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        for (int a = 0; a < dim; ++a) {
+            double v = xy[i * dim + a];
+            mn[a] = fmin(mn[a], v);
+            mx[a] = fmax(mx[a], v);
+        }
+    }
+    __shared__ double sm[6][32];
+    for (int a = 0; a < 3; ++a) {
+        double lo = mn[a], hi = mx[a];
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            sm[a][threadIdx.x >> 5] = lo;
+            sm[3 + a][threadIdx.x >> 5] = hi;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        int nw = blockDim.x >> 5;
+        double v = sm[threadIdx.x][0];
+        for (int w = 1; w < nw; ++w) v = threadIdx.x < 3 ? fmin(v, sm[threadIdx.x][w]) : fmax(v, sm[threadIdx.x][w]);
+        part[blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
+__global__ void bbox_final_kernel(const double* __restrict__ part, int nblocks, double* __restrict__ out) {
+    int t = threadIdx.x;
+    if (t < 6) {
+        double v = part[t];
+        for (int b = 1; b < nblocks; ++b) v = t < 3 ? fmin(v, part[b * 6 + t]) : fmax(v, part[b * 6 + t]);
+        out[t] = v;
+    }
+}
+
+// --------------------------------------------------------------- binning --
+__device__ __forceinline__ int cell_coord(double v, double lo, double inv_h, int g) {
+    int c = (int)floor((v - lo) * inv_h);
+    return min(max(c, 0), g - 1);
+}
+
+__global__ void cell_count_kernel(const double* __restrict__ xy, int64_t n, GridSpec gs, int32_t* __restrict__ cell_of,
+                                  int32_t* __restrict__ counts) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = 0, stride = 1;
+    for (int a = 0; a < gs.dim; ++a) {
+        c += cell_coord(xy[i * gs.dim + a], gs.lo[a], gs.inv_h, gs.g[a]) * stride;
+        stride *= gs.g[a];
+    }
+    cell_of[i] = c;
+    atomicAdd(&counts[c], 1);
+}
+
+__global__ void cell_scatter_kernel(const int32_t* __restrict__ cell_of, int64_t n, const int32_t* __restrict__ cell_start,
+                                    int32_t* __restrict__ fill, int32_t* __restrict__ sorted_id) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = cell_of[i];
+    sorted_id[cell_start[c] + atomicAdd(&fill[c], 1)] = (int32_t)i;
+}
+
+// order inside a cell came from atomics: sort each (tiny) cell segment by point id
+// so that the emitted processing order is deterministic
+__global__ void cell_sort_kernel(const int32_t* __restrict__ cell_start, int64_t ncell, int32_t* __restrict__ sorted_id) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    int s = cell_start[c], e = cell_start[c + 1];
+    for (int a = s + 1; a < e; ++a) {
+        int v = sorted_id[a], b = a - 1;
+        while (b >= s && sorted_id[b] > v) { sorted_id[b + 1] = sorted_id[b]; --b; }
+        sorted_id[b + 1] = v;
+    }
+}
+
+__global__ void gather_sorted_kernel(const double* __restrict__ xy, int64_t n, int dim, const int32_t* __restrict__ sorted_id,
+                                     const int32_t* __restrict__ cell_of, double* __restrict__ sx, double* __restrict__ sy,
+                                     double* __restrict__ sz, int32_t* __restrict__ sorted_cell) {
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    int64_t i = sorted_id[q];
+    sx[q] = xy[i * dim];
+    sy[q] = xy[i * dim + 1];
+    if (dim == 3) sz[q] = xy[i * dim + 2];
+    sorted_cell[q] = cell_of[i];
+}
+
+// ---------------------------------------------------------------- search --
+template <int KMAX>
+struct TopK {
+    double d2[KMAX];
+    int32_t id[KMAX];
+    int count;
+    int K;
+    __device__ __forceinline__ void init(int k) { count = 0; K = k; }
+    __device__ __forceinline__ bool full() const { return count == K; }
+    __device__ __forceinline__ double worst() const { return d2[count - 1]; }
+    __device__ __forceinline__ void offer(double v, int32_t pid) {
+        if (count == K) {
+            double wv = d2[K - 1];
+            if (v > wv || (v == wv && pid > id[K - 1])) return;
+        }
+        int pos = count < K ? count : K - 1;
+        while (pos > 0 && (d2[pos - 1] > v || (d2[pos - 1] == v && id[pos - 1] > pid))) {
+            d2[pos] = d2[pos - 1];
+            id[pos] = id[pos - 1];
+            --pos;
+        }
+        d2[pos] = v;
+        id[pos] = pid;
+        if (count < K) ++count;
+    }
+};
+
+template <int KMAX, int DIM>
+__global__ void __launch_bounds__(128)
+knn_search_kernel(int64_t n, GridSpec gs, int kq, int k, int include_self, const int32_t* __restrict__ cell_start,
+                  const int32_t* __restrict__ sorted_id, const int32_t* __restrict__ sorted_cell,
+                  const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
+                  int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const double qx = sx[q], qy = sy[q], qz = DIM == 3 ? sz[q] : 0.0;
+    const int32_t self = sorted_id[q];
+    int c = sorted_cell[q];
+    const int cx = c % gs.g[0];
+    const int cy = (c / gs.g[0]) % gs.g[1];
+    const int cz = DIM == 3 ? c / (gs.g[0] * gs.g[1]) : 0;
+    const int gx = gs.g[0], gy = gs.g[1], gz = DIM == 3 ? gs.g[2] : 1;
+
+    TopK<KMAX> top;
+    top.init(kq);
+    const int rmax = max(max(max(cx, gx - 1 - cx), max(cy, gy - 1 - cy)), max(cz, gz - 1 - cz));
+    for (int r = 0; r <= rmax; ++r) {
+        const int z0 = DIM == 3 ? max(cz - r, 0) : 0, z1 = DIM == 3 ? min(cz + r, gz - 1) : 0;
+        for (int z = z0; z <= z1; ++z) {
+            const bool zface = DIM == 3 && (z == cz - r || z == cz + r);
+            const int y0 = max(cy - r, 0), y1 = min(cy + r, gy - 1);
+            for (int y = y0; y <= y1; ++y) {
+                const bool full_row = zface || y == cy - r || y == cy + r;
+                const int nseg = (full_row || r == 0) ? 1 : 2;
+                for (int seg = 0; seg < nseg; ++seg) {
+                    int xa, xb;
+                    if (full_row || r == 0) { xa = max(cx - r, 0); xb = min(cx + r, gx - 1); }
+                    else if (seg == 0) { xa = xb = cx - r; if (xa < 0) continue; }
+                    else { xa = xb = cx + r; if (xa > gx - 1) continue; }
+                    const int64_t base = ((int64_t)z * gy + y) * gx;
+                    const int ps = cell_start[base + xa], pe = cell_start[base + xb + 1];
+                    for (int p = ps; p < pe; ++p) {
+                        const double dx = qx - sx[p], dy = qy - sy[p];
+                        double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                        if (DIM == 3) { const double dz = qz - sz[p]; d2 = __dadd_rn(d2, __dmul_rn(dz, dz)); }
+                        top.offer(d2, sorted_id[p]);
+                    }
+                }
+            }
+        }
+        if (top.full()) {
+            // smallest possible distance to any point outside the visited block
+            double bound = DBL_MAX;
+            if (cx - r > 0) bound = fmin(bound, qx - (gs.lo[0] + (cx - r) * gs.h));
+            if (cx + r < gx - 1) bound = fmin(bound, (gs.lo[0] + (cx + r + 1) * gs.h) - qx);
+            if (cy - r > 0) bound = fmin(bound, qy - (gs.lo[1] + (cy - r) * gs.h));
+            if (cy + r < gy - 1) bound = fmin(bound, (gs.lo[1] + (cy + r + 1) * gs.h) - qy);
+            if (DIM == 3) {
+                if (cz - r > 0) bound = fmin(bound, qz - (gs.lo[2] + (cz - r) * gs.h));
+                if (cz + r < gz - 1) bound = fmin(bound, (gs.lo[2] + (cz + r + 1) * gs.h) - qz);
+            }
+            if (bound == DBL_MAX) break;
+            bound -= gs.h * 1e-9;                      // slack for rounding in the cell assignment
+            if (bound > 0.0 && top.worst() < bound * bound) break;
+        }
+    }
+
+    int32_t* oi = out_idx + (int64_t)self * k;
+    double* od = out_dist + (int64_t)self * k;
+    if (include_self) {
+        for (int j = 0; j < k; ++j) { oi[j] = top.id[j]; od[j] = __dsqrt_rn(top.d2[j]); }
+    } else {
+        int drop = 0;                                  // sklearn: drop own index, else the first entry
+        for (int j = 0; j < kq; ++j) if (top.id[j] == self) { drop = j; break; }
+        int o = 0;
+        for (int j = 0; j < kq; ++j) {
+            if (j == drop) continue;
+            oi[o] = top.id[j];
+            od[o] = __dsqrt_rn(top.d2[j]);
+            ++o;
+        }
+    }
+}
+
+// --------------------------------------------------------------- weights --
+constexpr int kSumBlocks = 592, kSumThreads = 256;
+
+__global__ void sum_partial_kernel(const double* __restrict__ v, int64_t m, double* __restrict__ part) {
+    double s = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) s += v[i];
+    __shared__ double sm[32];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) t += sm[w];
+        part[blockIdx.x] = t;
+    }
+}
+
+__global__ void scale_final_kernel(const double* __restrict__ part, int nb, int64_t m, double sigma, double* __restrict__ scale) {
+    if (threadIdx.x == 0) {
+        if (sigma > 0.0) { *scale = sigma; return; }
+        double t = 0.0;
+        for (int b = 0; b < nb; ++b) t += part[b];
+        *scale = (t / (double)m) / 2.0;
+    }
+}
+
+__global__ void decay_weights_kernel(const double* __restrict__ dist, int64_t m, const double* __restrict__ scale,
+                                     double* __restrict__ w64, float* __restrict__ w32) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    double w = 1.0 / exp(dist[i] / *scale);
+    if (w64) w64[i] = w;
+    if (w32) w32[i] = (float)w;
+}
+
+}  // namespace laris
+
+using namespace laris;
+
+extern "C" int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int include_self, int32_t* out_idx,
+                               double* out_dist, int32_t* out_order, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    LARIS_CHECK_ARG(xy && out_idx && out_dist, "laris_knn_graph: null pointer");
+    LARIS_CHECK_ARG(dim == 2 || dim == 3, "laris_knn_graph: dim must be 2 or 3 (got %d)", dim);
+    const int kq = include_self ? k : k + 1;
+    LARIS_CHECK_ARG(k >= 1 && kq <= 64, "laris_knn_graph: k out of range (k=%d, limit 64 incl. self)", k);
+    LARIS_CHECK_ARG(n >= kq && n < (int64_t)INT32_MAX, "laris_knn_graph: need k+1 <= n < 2^31 (n=%lld)", (long long)n);
+
+    // bounding box (one host sync: the grid shape depends on it)
+    const int nb = kNumSMs * 2;
+    Scratch<double> part(st), box_d(st);
+    LARIS_CUDA(part.alloc(nb * 6));
+    LARIS_CUDA(box_d.alloc(6));
+    bbox_partial_kernel<<<nb, 256, 0, st>>>(xy, n, dim, part.p);
+    LARIS_LAUNCH_CHECK();
+    bbox_final_kernel<<<1, 32, 0, st>>>(part.p, nb, box_d.p);
+    LARIS_LAUNCH_CHECK();
+    double box[6];
+    LARIS_CUDA(cudaMemcpyAsync(box, box_d.p, sizeof(box), cudaMemcpyDeviceToHost, st));
+    LARIS_CUDA(cudaStreamSynchronize(st));
+
+    GridSpec gs;
+    gs.dim = dim;
+    double ext[3] = {0, 0, 0}, vol = 1.0;
+    int nz_dims = 0;
+    for (int a = 0; a < dim; ++a) {
+        LARIS_CHECK_ARG(isfinite(box[a]) && isfinite(box[3 + a]), "laris_knn_graph: non-finite coordinates");
+        gs.lo[a] = box[a];
+        ext[a] = box[3 + a] - box[a];
+        if (ext[a] > 0) { vol *= ext[a]; ++nz_dims; }
+    }
+    for (int a = dim; a < 3; ++a) { gs.lo[a] = 0; gs.g[a] = 1; }
+    const double per_cell = 2.5;
+    double h = nz_dims ? pow(vol * per_cell / (double)n, 1.0 / nz_dims) : 1.0;
+    if (!(h > 0) || !isfinite(h)) h = 1.0;
+    int64_t ncell;
+    for (;;) {                                         // keep the grid within int32 / memory limits
+        ncell = 1;
+        for (int a = 0; a < dim; ++a) {
+            double g = floor(ext[a] / h) + 1.0;
+            if (g > 1e9) g = 1e9;
+            gs.g[a] = (int)g;
+            ncell *= gs.g[a];
+        }
+        if (ncell <= 4 * n + 1024) break;
+        h *= 1.5;
+    }
+    gs.h = h;
+    gs.inv_h = 1.0 / h;
+
+    Scratch<int32_t> cell_of(st), counts(st), cell_start(st), fill(st), sorted_id(st), sorted_cell(st);
+    Scratch<double> sx(st), sy(st), sz(st);
+    LARIS_CUDA(cell_of.alloc(n));
+    LARIS_CUDA(counts.alloc(ncell));
+    LARIS_CUDA(cell_start.alloc(ncell + 1));
+    LARIS_CUDA(fill.alloc(ncell));
+    LARIS_CUDA(sorted_id.alloc(n));
+    LARIS_CUDA(sorted_cell.alloc(n));
+    LARIS_CUDA(sx.alloc(n));
+    LARIS_CUDA(sy.alloc(n));
+    LARIS_CUDA(sz.alloc(dim == 3 ? n : 1));
+    LARIS_CUDA(cudaMemsetAsync(counts.p, 0, ncell * sizeof(int32_t), st));
+    LARIS_CUDA(cudaMemsetAsync(fill.p, 0, ncell * sizeof(int32_t), st));
+    const int T = 256;
+    const unsigned gn = (unsigned)ceil_div(n, T), gc = (unsigned)ceil_div(ncell, T);
+    cell_count_kernel<<<gn, T, 0, st>>>(xy, n, gs, cell_of.p, counts.p);
+    LARIS_LAUNCH_CHECK();
+    int rc = exclusive_scan<int32_t>(counts.p, ncell, cell_start.p, st);
+    if (rc) return rc;
+    cell_scatter_kernel<<<gn, T, 0, st>>>(cell_of.p, n, cell_start.p, fill.p, sorted_id.p);
+    LARIS_LAUNCH_CHECK();
+    cell_sort_kernel<<<gc, T, 0, st>>>(cell_start.p, ncell, sorted_id.p);
+    LARIS_LAUNCH_CHECK();
+    gather_sorted_kernel<<<gn, T, 0, st>>>(xy, n, dim, sorted_id.p, cell_of.p, sx.p, sy.p, sz.p, sorted_cell.p);
+    LARIS_LAUNCH_CHECK();
+
+    const unsigned gq = (unsigned)ceil_div(n, 128);
+#define LARIS_KNN_LAUNCH(KMAX, DIM)                                                                          \
+    knn_search_kernel<KMAX, DIM><<<gq, 128, 0, st>>>(n, gs, kq, k, include_self, cell_start.p, sorted_id.p,  \
+                                                     sorted_cell.p, sx.p, sy.p, sz.p, out_idx, out_dist)
+    if (dim == 2) {
+        if (kq <= 16) LARIS_KNN_LAUNCH(16, 2); else if (kq <= 32) LARIS_KNN_LAUNCH(32, 2); else LARIS_KNN_LAUNCH(64, 2);
+    } else {
+        if (kq <= 16) LARIS_KNN_LAUNCH(16, 3); else if (kq <= 32) LARIS_KNN_LAUNCH(32, 3); else LARIS_KNN_LAUNCH(64, 3);
+    }
+#undef LARIS_KNN_LAUNCH
+    LARIS_LAUNCH_CHECK();
+    if (out_order)
+        LARIS_CUDA(cudaMemcpyAsync(out_order, sorted_id.p, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return LARIS_OK;
+}
+
+extern "C" int laris_decay_weights(const double* dist, int64_t m, double sigma, double* w64, float* w32,
+                                   double* scale_out, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    LARIS_CHECK_ARG(dist && m > 0, "laris_decay_weights: empty input");
+    Scratch<double> part(st), scale(st);
+    LARIS_CUDA(part.alloc(kSumBlocks));
+    LARIS_CUDA(scale.alloc(1));
+    if (!(sigma > 0.0)) {
+        sum_partial_kernel<<<kSumBlocks, kSumThreads, 0, st>>>(dist, m, part.p);
+        LARIS_LAUNCH_CHECK();
+    }
+    scale_final_kernel<<<1, 32, 0, st>>>(part.p, kSumBlocks, m, sigma, scale.p);
+    LARIS_LAUNCH_CHECK();
+    decay_weights_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(dist, m, scale.p, w64, w32);
+    LARIS_LAUNCH_CHECK();
+    if (scale_out) LARIS_CUDA(cudaMemcpyAsync(scale_out, scale.p, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return LARIS_OK;
+}

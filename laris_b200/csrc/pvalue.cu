@@ -1,0 +1,157 @@
+// K6: exceedance counts of the background-resampling null, K7: per-group
+// Benjamini-Hochberg.  See include/laris_b200.h for the reference call sites.
+//
+// K6: one warp per (group, pair) row.  The nb candidate null values of the row
+// (scores of the pair's background pairs inside the same sender-receiver group)
+// are staged once in shared memory; each lane then turns Philox outputs into
+// draws (4 per call) and compares.  The score table (C^2 x P fp64) is read once
+// per row and stays L2-resident; the kernel is integer-ALU bound.
+#include <math.h>
+
+#include "common.cuh"
+#include "rng.cuh"
+
+namespace laris {
+
+constexpr int kPvWarps = 8;
+constexpr int kPvMaxNb = 256;
+
+__global__ void __launch_bounds__(kPvWarps * 32)
+pvalue_counts_kernel(const double* __restrict__ table, int64_t ldt, int n_groups, int n_slots,
+                     const int32_t* __restrict__ bg, int nb, const uint8_t* __restrict__ active,
+                     const int64_t* __restrict__ slot_gid, int64_t P_global, int g0, int t0, int n_perm, int rng_mode,
+                     uint64_t seed, const uint8_t* __restrict__ draws, int32_t* __restrict__ ge, int32_t* __restrict__ nz,
+                     int32_t* __restrict__ ge_nz) {
+    __shared__ double nullv[kPvWarps][kPvMaxNb];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nrows = (int64_t)n_groups * n_slots;
+    for (int64_t r = (int64_t)blockIdx.x * kPvWarps + warp; r < nrows; r += (int64_t)gridDim.x * kPvWarps) {
+        const int g = (int)(r / n_slots), s = (int)(r - (int64_t)g * n_slots);
+        if (active && !active[s]) continue;                         // warp-uniform
+        const double* trow = table + (int64_t)g * ldt;
+        const double obs = trow[s];
+        __syncwarp();
+        for (int m = lane; m < nb; m += 32) nullv[warp][m] = trow[bg[(int64_t)s * nb + m]];
+        __syncwarp();
+        int c_ge = 0, c_nz = 0, c_both = 0;
+        if (rng_mode == 0) {
+            const uint64_t grow = (uint64_t)(g0 + g) * (uint64_t)P_global + (uint64_t)(slot_gid ? slot_gid[s] : s);
+            const int q_beg = t0 >> 2, q_end = (t0 + n_perm + 3) >> 2;
+            for (int q = q_beg + lane; q < q_end; q += 32) {
+                const u32x4 o = philox4x32_10((uint32_t)q, (uint32_t)grow, (uint32_t)(grow >> 32), kStreamPval, seed);
+                const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = q * 4 + u;
+                    if (t >= t0 && t < t0 + n_perm) {
+                        const double v = nullv[warp][__umulhi(ov[u], (uint32_t)nb)];
+                        const bool a = v >= obs, b = v > 0.0;
+                        c_ge += a; c_nz += b; c_both += a && b;
+                    }
+                }
+            }
+        } else {
+            const uint8_t* d = draws + r * (int64_t)n_perm;
+            for (int t = lane; t < n_perm; t += 32) {
+                const double v = nullv[warp][d[t]];
+                const bool a = v >= obs, b = v > 0.0;
+                c_ge += a; c_nz += b; c_both += a && b;
+            }
+        }
+        c_ge = warp_sum(c_ge); c_nz = warp_sum(c_nz); c_both = warp_sum(c_both);
+        if (lane == 0) {
+            ge[r] += c_ge;                                          // one warp per row: plain RMW
+            nz[r] += c_nz;
+            ge_nz[r] += c_both;
+        }
+    }
+}
+
+// ---- BH per group: bitonic sort of (p, index) in shared memory, rank scaling, suffix minimum
+__global__ void bh_fdr_kernel(const double* __restrict__ p, const uint8_t* __restrict__ sel, int len, int cap,
+                              double* __restrict__ fdr) {
+    extern __shared__ unsigned char raw[];
+    double* key = reinterpret_cast<double*>(raw);                   // [cap]
+    int32_t* id = reinterpret_cast<int32_t*>(key + cap);            // [cap]
+    __shared__ int m_sel;
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const double* pg = p + (int64_t)g * len;
+    const uint8_t* sg = sel + (int64_t)g * len;
+    double* fg = fdr + (int64_t)g * len;
+    if (tid == 0) m_sel = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = tid; i < cap; i += blockDim.x) {
+        const bool on = i < len && sg[i];
+        key[i] = on ? pg[i] : INFINITY;
+        id[i] = i;
+        local += on;
+        if (i < len && !on) fg[i] = 1.0;
+    }
+    atomicAdd(&m_sel, local);
+    __syncthreads();
+    const int m = m_sel;
+    for (int kk = 2; kk <= cap; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < cap; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & kk) == 0;
+                    const double a = key[i], b = key[l];
+                    const int ia = id[i], ib = id[l];
+                    const bool gt = a > b || (a == b && ia > ib);
+                    if (gt == up) { key[i] = b; key[l] = a; id[i] = ib; id[l] = ia; }
+                }
+            }
+            __syncthreads();
+        }
+    // scaled values p_(i) * m / i for the m selected (sorted first), +inf elsewhere
+    for (int i = tid; i < cap; i += blockDim.x) key[i] = i < m ? key[i] * (double)m / (double)(i + 1) : INFINITY;
+    __syncthreads();
+    // suffix minimum (Hillis-Steele)
+    for (int off = 1; off < cap; off <<= 1) {
+        double v[8];
+        int cnt = 0;
+        for (int i = tid; i < cap; i += blockDim.x) { v[cnt++] = i + off < cap ? fmin(key[i], key[i + off]) : key[i]; }
+        __syncthreads();
+        cnt = 0;
+        for (int i = tid; i < cap; i += blockDim.x) key[i] = v[cnt++];
+        __syncthreads();
+    }
+    for (int i = tid; i < m; i += blockDim.x) fg[id[i]] = fmin(key[i], 1.0);
+}
+
+}  // namespace laris
+
+using namespace laris;
+
+extern "C" int laris_pvalue_counts(const double* table, int64_t ldt, int32_t n_groups, int32_t n_slots, const int32_t* bg,
+                                   int32_t nb, const uint8_t* active, const int64_t* slot_gid, int64_t P_global,
+                                   int32_t g0, int32_t t0, int32_t n_perm, int rng_mode, uint64_t seed,
+                                   const uint8_t* draws, int32_t* ge, int32_t* nz, int32_t* ge_nz, void* stream) {
+    LARIS_CHECK_ARG(table && bg && ge && nz && ge_nz, "laris_pvalue_counts: null pointer");
+    LARIS_CHECK_ARG(n_groups >= 1 && n_slots >= 1 && ldt >= n_slots && n_perm >= 0, "laris_pvalue_counts: bad sizes");
+    LARIS_CHECK_ARG(nb >= 1 && nb <= kPvMaxNb, "laris_pvalue_counts: nb must be in [1,%d] (got %d)", kPvMaxNb, nb);
+    LARIS_CHECK_ARG(rng_mode == 0 || (rng_mode == 1 && draws), "laris_pvalue_counts: rng_mode 1 needs host draws");
+    if (n_perm == 0) return LARIS_OK;
+    const int64_t nrows = (int64_t)n_groups * n_slots;
+    int64_t grid = ceil_div(nrows, kPvWarps);
+    if (grid > (int64_t)kNumSMs * 16) grid = (int64_t)kNumSMs * 16;
+    pvalue_counts_kernel<<<(unsigned)grid, kPvWarps * 32, 0, (cudaStream_t)stream>>>(
+        table, ldt, n_groups, n_slots, bg, nb, active, slot_gid, P_global, g0, t0, n_perm, rng_mode, seed, draws, ge, nz, ge_nz);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
+extern "C" int laris_bh_fdr(const double* p, const uint8_t* sel, int32_t n_groups, int32_t len, double* fdr, void* stream) {
+    LARIS_CHECK_ARG(p && sel && fdr && n_groups >= 1 && len >= 1, "laris_bh_fdr: bad arguments");
+    int cap = 32;
+    while (cap < len) cap <<= 1;
+    if (cap > 8192) { set_error("laris_bh_fdr: group length %d exceeds the shared-memory sort (limit 8192)", len); return LARIS_E_LIMIT; }
+    const size_t smem = (size_t)cap * 12;
+    LARIS_CUDA(cudaFuncSetAttribute(bh_fdr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int threads = cap >= 1024 ? 1024 : cap;
+    bh_fdr_kernel<<<(unsigned)n_groups, threads, smem, (cudaStream_t)stream>>>(p, sel, len, cap, fdr);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}

@@ -1,0 +1,220 @@
+"""Device pipeline of the LR scoring path.
+
+Every function here is host orchestration only: it moves AnnData arrays to
+the GPU (torch tensors as the carrier), calls the C-ABI kernels in
+``liblaris_b200.so`` and brings small per-pair / per-group tables back.  The
+reference functions each stage replaces are cited on the kernels
+(include/laris_b200.h) and on the public wrappers in ``laris_b200.tools``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from . import _kernels as K
+from . import _rng_compat
+
+
+# ---------------------------------------------------------------- graph ----
+@dataclass
+class SpatialGraph:
+    idx: torch.Tensor      # [n,k] int32 neighbour ids (CSR indices, indptr = i*k)
+    dist: torch.Tensor     # [n,k] fp64 distances
+    w: torch.Tensor        # [n,k] fp32 decay weights
+    w64: torch.Tensor      # [n,k] fp64 decay weights (the reference's CSR data)
+    order: torch.Tensor    # [n] int32 spatial processing order
+    scale: torch.Tensor    # [1] fp64 decay scale s
+    include_self: bool
+
+    @property
+    def n(self):
+        return self.idx.shape[0]
+
+    @property
+    def k(self):
+        return self.idx.shape[1]
+
+    def to_scipy(self):
+        """The reference's ``cellxcell`` (n x n CSR, fp64 weights, int64 indices)."""
+        n, k = self.idx.shape
+        return sp.csr_matrix((self.w64.cpu().numpy().ravel(), self.idx.cpu().numpy().astype(np.int64).ravel(),
+                              np.arange(0, n * k + 1, k, dtype=np.int64)), shape=(n, n))
+
+
+def build_graph(xy, k, include_self, sigma=None) -> SpatialGraph:
+    """kNN graph + decay weights (K1).  ``sigma=None`` -> s = mean(d)/2."""
+    xy_d = xy if torch.is_tensor(xy) else K.to_device(np.asarray(xy, dtype=np.float64), torch.float64)
+    if xy_d.dim() != 2 or xy_d.shape[1] not in (2, 3):
+        raise ValueError(f"spatial coordinates must be n x 2 or n x 3, got {tuple(xy_d.shape)}")
+    idx, dist, order = K.knn_graph(xy_d.contiguous(), int(k), include_self)
+    w32, w64, scale = K.decay_weights(dist, sigma, want64=True)
+    return SpatialGraph(idx, dist, w32, w64, order, scale, bool(include_self))
+
+
+# ----------------------------------------------------------- expression ----
+@dataclass
+class ExpressionU:
+    indptr: torch.Tensor   # [n+1] int64
+    packed: torch.Tensor   # [nnz] int64 {col:int32, val:fp32}
+    genes: np.ndarray      # [G_u] global gene column of each packed column
+    n: int
+
+    @property
+    def G_u(self):
+        return len(self.genes)
+
+
+def upload_csr(X):
+    """scipy sparse -> (indptr int64, indices int32, data fp32) on the device."""
+    if not sp.issparse(X):
+        raise TypeError("adata.X must be a scipy sparse matrix (as in the reference, laris/tools/__init__.py:100)")
+    X = X.tocsr()
+    return (K.to_device(X.indptr, torch.int64), K.to_device(X.indices, torch.int32), K.to_device(X.data, torch.float32))
+
+
+def select_genes(X, genes, csr_dev=None) -> ExpressionU:
+    """Restrict X (n x G CSR) to ``genes`` (unique global columns) on the device."""
+    n, G = X.shape
+    genes = np.asarray(genes, dtype=np.int64)
+    gene_map = np.full(G, -1, dtype=np.int32)
+    gene_map[genes] = np.arange(len(genes), dtype=np.int32)
+    indptr, indices, data = csr_dev if csr_dev is not None else upload_csr(X)
+    out_indptr, packed = K.csr_select(indptr, indices, data, K.to_device(gene_map, torch.int32))
+    return ExpressionU(out_indptr, packed, genes, n)
+
+
+# --------------------------------------------------------------- scores ----
+@dataclass
+class ScoreMatrix:
+    S: torch.Tensor                    # [n, ld] fp32 dense, columns >= P are zero
+    P: int
+    row_nnz: torch.Tensor | None = None
+    cache: dict = field(default_factory=dict)
+
+    @property
+    def n(self):
+        return self.S.shape[0]
+
+
+def lr_scores(xu: ExpressionU, graph: SpatialGraph, lig_u, rec_u) -> ScoreMatrix:
+    """Fused diffusion + LR score (K2+K3)."""
+    lig_d = K.to_device(np.asarray(lig_u, dtype=np.int32), torch.int32)
+    rec_d = K.to_device(np.asarray(rec_u, dtype=np.int32), torch.int32)
+    S, row_nnz = K.diffuse_lr_score(xu.indptr, xu.packed, xu.G_u, graph.idx, graph.w, graph.order, lig_d, rec_d)
+    return ScoreMatrix(S, len(lig_u), row_nnz)
+
+
+def scores_to_csr(sm: ScoreMatrix, dtype=np.float32) -> sp.csr_matrix:
+    if sm.row_nnz is None:
+        raise ValueError("score matrix has no row counts")
+    indptr, indices, data = K.csr_compact(sm.S, sm.P, sm.row_nnz)
+    X = sp.csr_matrix((data.cpu().numpy().astype(dtype, copy=False), indices.cpu().numpy(), indptr.cpu().numpy()),
+                      shape=(sm.n, sm.P))
+    X.has_sorted_indices = True
+    return X
+
+
+def scores_from_csr(X) -> ScoreMatrix:
+    indptr, indices, data = upload_csr(X)
+    return ScoreMatrix(K.csr_to_dense(indptr, indices, data, X.shape[0], X.shape[1]), X.shape[1])
+
+
+# --------------------------------------------------- spatial specificity ----
+def _cosine(stats):
+    dot, ss, tt = stats[0], stats[1], stats[2]
+    den = np.sqrt(ss) * np.sqrt(tt)
+    out = np.zeros_like(dot)
+    np.divide(dot, den, out=out, where=den != 0)
+    return out
+
+
+def observed_stats(sm: ScoreMatrix, graph: SpatialGraph):
+    """[5,P] fp64 host array: dot, sum S^2, sum T^2, sum S, nnz (observed graph, K4)."""
+    return K.spatial_stats(sm.S, sm.P, graph.idx, graph.w, False, graph.order).cpu().numpy()
+
+
+def null_cosines(sm: ScoreMatrix, graph: SpatialGraph, n_repeats, random_seed, rng="numpy"):
+    """Per-repeat cosine of the random-graph null (K4b).  Returns ([R,P], rng_state)."""
+    n, k = graph.n, graph.k
+    out, state = [], None
+    if rng == "numpy":
+        seeds = _rng_compat.repeat_seeds(random_seed, n_repeats)
+        for s in seeds:
+            cols, perm, state = _rng_compat.null_graph(n, k, s)
+            cols_d = K.to_device(cols.astype(np.int32), torch.int32).view(n, k)
+            wperm = K.gather_f32(graph.w.view(-1), K.to_device(perm, torch.int64)).view(n, k)
+            out.append(_cosine(K.spatial_stats(sm.S, sm.P, cols_d, wperm, True, None).cpu().numpy()))
+    elif rng == "philox":
+        for r in range(n_repeats):
+            cols_d, wperm = K.null_graph_philox(n, k, graph.w, r, random_seed)
+            out.append(_cosine(K.spatial_stats(sm.S, sm.P, cols_d, wperm, True, None).cpu().numpy()))
+    else:
+        raise ValueError(f"rng must be 'numpy' or 'philox', got {rng!r}")
+    return np.asarray(out).reshape(n_repeats, sm.P), state
+
+
+# ------------------------------------------------------------ cell types ----
+def celltype_fraction(sm: ScoreMatrix, labels_d, C, n_c):
+    """frac[p,c] = #{i in c: S_ip != 0} / n_c (K5b)."""
+    cnt = K.celltype_nonzero_count(sm.S, sm.P, labels_d, C).cpu().numpy().astype(np.float64)
+    return (cnt / n_c[:, None]).T
+
+
+def cosg_regularise(cos, mu):
+    """lambda*cos; lambda = cos^2/((1-mu)cos^2 + mu*sum_groups cos^2) (reference _utils.py:869-880)."""
+    sq = cos * cos
+    tot = sq.sum(1, keepdims=True)
+    den = tot if mu == 1 else (1 - mu) * sq + mu * tot
+    out = np.zeros_like(cos)
+    np.divide(sq, den, out=out, where=cos != 0)
+    return out * cos
+
+
+def neighborhood_specificity(sm: ScoreMatrix, labels_d, C, graph: SpatialGraph, mu, ss=None, impl=1):
+    """Raw P x C^2 co-localisation table (reference _utils.py:839-880), K5."""
+    N = K.neighborhood_composition(labels_d, graph.idx, graph.w, C)
+    num, qn2 = K.celltype_pair_contract(sm.S, sm.P, N, impl)
+    num, qn2 = num.cpu().numpy(), qn2.cpu().numpy()
+    if ss is None:
+        ss = observed_stats(sm, graph)[1]
+    den = np.sqrt(ss)[:, None] * np.sqrt(qn2)[None, :]
+    cos = np.zeros_like(num)
+    np.divide(num, den, out=cos, where=den != 0)
+    return cosg_regularise(cos, mu), cos
+
+
+def cosg_gene_scores(xu: ExpressionU, labels_d, C, n_c, mu, expressed_pct, remove_lowly_expressed):
+    """COSG gene x group score of the packed expression (cosg.cosg semantics)."""
+    s, c, q = K.onehot_contract_csr(xu.indptr, xu.packed, xu.G_u, labels_d, C)
+    s, c, q = s.cpu().numpy(), c.cpu().numpy(), q.cpu().numpy()
+    den = np.sqrt(q)[:, None] * np.sqrt(n_c.astype(np.float64))[None, :]
+    cos = np.zeros((xu.G_u, C))
+    np.divide(s.T, den, out=cos, where=den != 0)
+    score = cosg_regularise(cos, mu)
+    if remove_lowly_expressed:
+        score[c.T < n_c[None, :] * expressed_pct] = -1.0
+    return score
+
+
+# --------------------------------------------------------------- p-values ----
+def pvalue_counts(table, bg, active, n_perm, *, rng="philox", seed=0, draws=None):
+    """Exceedance counts (K6).  ``table`` [groups,P] fp64 host, ``bg`` [P,nb] host."""
+    t = K.to_device(np.ascontiguousarray(table, dtype=np.float64), torch.float64)
+    b = K.to_device(np.ascontiguousarray(bg, dtype=np.int32), torch.int32)
+    a = K.to_device(np.ascontiguousarray(active, dtype=np.uint8), torch.uint8) if active is not None else None
+    d = None
+    if rng == "numpy":
+        if draws is None:
+            raise ValueError("rng='numpy' needs host draws")
+        d = K.to_device(np.ascontiguousarray(draws, dtype=np.uint8), torch.uint8)
+    ge, nz, both = K.pvalue_counts(t, b, n_perm, active=a, seed=seed, draws=d)
+    return ge.cpu().numpy(), nz.cpu().numpy(), both.cpu().numpy()
+
+
+def bh_fdr(p, sel):
+    out = K.bh_fdr(K.to_device(np.ascontiguousarray(p, dtype=np.float64), torch.float64),
+                   K.to_device(np.ascontiguousarray(sel, dtype=np.uint8), torch.uint8))
+    return out.cpu().numpy()

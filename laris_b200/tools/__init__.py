@@ -1,0 +1,142 @@
+"""laris_b200.tl - drop-in for the reference's ``laris.tl`` scoring path.
+
+``prepareLRInteraction`` and ``runLARIS`` keep the reference's signatures,
+defaults, error behaviour and AnnData layouts
+(reference laris/tools/__init__.py:29-119 and :121-593); the arithmetic runs in
+hand-written sm_100a kernels behind the C ABI of include/laris_b200.h.
+Extra keyword-only arguments (``rng``, ``verbose``, ``dtype``, ``contract_impl``)
+default to the reference's behaviour.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import scipy.sparse as sp
+import torch
+
+from .. import _kernels as K
+from .. import _rng_compat, engine
+from .._anndata import make_anndata
+from . import _utils
+from ._utils import _log
+
+
+def _lr_gene_indices(adata, lr_df):
+    """Gene columns of every ligand / receptor.  The reference's
+    argsort/searchsorted lookup (laris/tools/__init__.py:95-97) silently maps a
+    missing name to its lexicographic successor; here a missing gene raises."""
+    return _utils._gene_columns(adata, lr_df["ligand"].astype(str)), _utils._gene_columns(adata, lr_df["receptor"].astype(str))
+
+
+def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_rep_spatial: str = "X_spatial", *,
+                         dtype=np.float32):
+    """Per-cell diffused ligand-receptor scores as a new AnnData (cells x LR pairs).
+
+    Reference laris/tools/__init__.py:29-119: kNN graph incl. self with
+    w = 1/exp(d/(mean(d)/2)); D = W X; S[i,p] = D[i,l_p] D[i,r_p] masked to cells
+    expressing the ligand or the receptor.  Returns a new AnnData with ``.X`` the
+    sparse n x P score matrix (exact zeros pruned), ``obs``/``obsm`` copied and
+    ``var_names`` = "ligand::receptor".  The dense scores stay resident on the GPU
+    for a following ``runLARIS`` call.
+    """
+    xy = _utils._coords(adata, use_rep_spatial)
+    lig_g, rec_g = _lr_gene_indices(adata, lr_df)
+    genes, inv = np.unique(np.concatenate([lig_g, rec_g]), return_inverse=True)
+    P = len(lig_g)
+    graph = engine.build_graph(xy, number_nearest_neighbors, True, None)
+    xu = engine.select_genes(adata.X, genes)
+    sm = engine.lr_scores(xu, graph, inv[:P], inv[P:])
+    X = engine.scores_to_csr(sm, dtype)
+    lr_names = (lr_df["ligand"].astype(str) + "::" + lr_df["receptor"].astype(str)).to_numpy(dtype=object)
+    lr_adata = make_anndata(X, obs=adata.obs.copy(), var=pd.DataFrame(index=pd.Index(lr_names, dtype=object)),
+                            obsm={k: np.array(v, copy=True) for k, v in adata.obsm.items()})
+    _utils._remember_scores(lr_adata.X, sm)
+    return lr_adata
+
+
+def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbors: int = 10, random_seed: int = 27,
+             n_repeats: int = 3, mu: float = 1, sigma: float = 100, remove_lowly_expressed: bool = True,
+             expressed_pct: float = 0.1, n_cells_expressed_threshold: int = 100, n_top_lr: int = 4000,
+             by_celltype: bool = True, groupby: str = "CellTypes", use_rep_spatial: str = "X_spatial",
+             number_nearest_neighbors: int = 10, mu_celltype: float = 100, expressed_pct_celltype: float = 0.1,
+             remove_lowly_expressed_celltype: bool = True, mask_threshold: float = 1e-6, calculate_pvalues: bool = True,
+             layer_celltype=None, n_neighbors_permutation: int = 30, n_permutations: int = 1000, chunk_size: int = 50000,
+             prefilter_fdr: bool = True, prefilter_threshold: float = 0.0, score_threshold: float = 1e-6,
+             spatial_weight: float = 1.0, use_conditional_pvalue: bool = False, *, rng: str = "numpy",
+             verbose: bool = True, contract_impl: int = 1):
+    """Spatially-specific LR pairs and (optionally) the cell-type interaction table.
+
+    Reference laris/tools/__init__.py:121-593, same arguments and returns
+    (``laris_lr`` or ``(laris_lr, celltype_results)``), same in-place writes to
+    ``lr_adata.var`` / ``lr_adata.uns['cosg_lr']``.  ``n_top_lr`` is clamped to the
+    number of LR pairs (the reference raises for P < 4000);
+    ``remove_lowly_expressed``/``expressed_pct`` are accepted and unused, as in the
+    reference body.  ``rng='numpy'`` replays the reference's random stream
+    bit-exactly; ``rng='philox'`` generates the nulls on the device.
+    """
+    if by_celltype and adata is None:
+        raise ValueError("Parameter 'adata' must be provided when by_celltype=True. "
+                         "adata should contain gene expression and cell type annotations.")
+    if use_rep not in lr_adata.obsm:
+        raise KeyError(f"Representation '{use_rep}' not found in lr_adata.obsm. "
+                       f"Available keys: {list(lr_adata.obsm.keys())}")
+    _log(verbose, "\n" + "=" * 70 + "\nLARIS ANALYSIS\n" + "=" * 70)
+    _log(verbose, f"\nInput data: {lr_adata.shape[0]} cells x {lr_adata.shape[1]} LR pairs")
+
+    # ---- step 1: spatial specificity (reference :459-490) ----
+    _log(verbose, "\n--- Step 1: Calculating spatial specificity scores ---")
+    sm = _utils._scores_of(lr_adata)
+    graph = engine.build_graph(_utils._coords(lr_adata, use_rep), n_nearest_neighbors, False, sigma)
+    st = engine.observed_stats(sm, graph)
+    sm.cache.update(ss=st[1], sum=st[3], nnz=st[4])
+    gsp = engine._cosine(st)
+    rand_each, rng_state = engine.null_cosines(sm, graph, n_repeats, random_seed, rng)
+    random_gsp = np.mean(rand_each, axis=0)
+    gsp_score = gsp - mu * random_gsp
+    lr_adata.var["LRSS_Target"] = gsp
+    lr_adata.var["LRSS_Random"] = random_gsp
+    lr_adata.var["LR_SpatialSpecificity"] = gsp_score
+    # the QC column the ranking consumes (reference :493-504 via scanpy) + its cheap siblings
+    n = lr_adata.shape[0]
+    lr_adata.var["n_cells_by_counts"] = st[4].astype(np.int64)
+    lr_adata.var["mean_counts"] = st[3] / n
+    lr_adata.var["pct_dropout_by_counts"] = 100.0 * (1.0 - st[4] / n)
+    lr_adata.var["total_counts"] = st[3]
+
+    # ---- ranking (reference :499-526) ----
+    lr_var = lr_adata.var.sort_values(by="LR_SpatialSpecificity", ascending=False).copy()
+    n_cells_expressed = lr_var["n_cells_by_counts"].to_numpy()
+    ranking = lr_var["LR_SpatialSpecificity"].to_numpy().copy()
+    ranking[n_cells_expressed < n_cells_expressed_threshold] = np.min(ranking) - 0.001
+    top = _utils._select_top_n(ranking, min(int(n_top_lr), len(ranking)))
+    names = lr_var.index.to_numpy(dtype=object)[top]
+    ligs = [nm.split("::")[0] for nm in names]
+    recs = [nm.split("::")[1] for nm in names]
+    laris_lr = pd.DataFrame({"ligand": ligs, "receptor": recs, "score": ranking[top]})
+    laris_lr.index = pd.Index([f"{l}::{r}" for l, r in zip(ligs, recs)], dtype=object)
+    laris_lr["Rank"] = np.arange(len(laris_lr))
+    _log(verbose, f"  Identified {len(laris_lr)} top spatially-specific LR pairs")
+
+    if not by_celltype:
+        if rng_state is not None:
+            _rng_compat.sync_global(rng_state)
+        return laris_lr
+
+    # ---- step 2: cell-type table (reference :536-572) ----
+    if groupby not in adata.obs:
+        raise ValueError(f"Cell type column '{groupby}' not found in adata.obs. "
+                         f"Available columns: {list(adata.obs.columns)}")
+    celltype_results = _utils._calculate_laris_score_by_celltype(
+        adata=adata, lr_adata=lr_adata, laris_lr=laris_lr, groupby=groupby, use_rep_spatial=use_rep_spatial,
+        number_nearest_neighbors=number_nearest_neighbors, mu=mu_celltype, expressed_pct=expressed_pct_celltype,
+        remove_lowly_expressed=remove_lowly_expressed_celltype, mask_threshold=mask_threshold,
+        calculate_pvalues=calculate_pvalues, layer=layer_celltype, n_nearest_neighbors=n_neighbors_permutation,
+        n_permutations=n_permutations, chunk_size=chunk_size, prefilter_fdr=prefilter_fdr,
+        prefilter_threshold=prefilter_threshold, score_threshold=score_threshold, spatial_weight=spatial_weight,
+        use_conditional_pvalue=use_conditional_pvalue, rng=rng, random_seed=random_seed, rng_state=rng_state,
+        verbose=verbose, contract_impl=contract_impl)
+    _log(verbose, f"\nResults: {len(laris_lr)} LR pairs, {len(celltype_results):,} cell type combinations")
+    return laris_lr, celltype_results
+
+
+__all__ = ["prepareLRInteraction", "runLARIS"]

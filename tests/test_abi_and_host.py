@@ -1,0 +1,117 @@
+"""CPU tier: the C-ABI library loads and exports every symbol the header
+declares; host-side logic (carrier, generators, table reshaping, argument
+errors) behaves like the reference's."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "laris_b200.h")).read()
+    declared = set(re.findall(r"LARIS_API[\s\w\*]+?\b(laris_\w+)\s*\(", hdr))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(os.path.join(ROOT, "laris_b200", "liblaris_b200.so"))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    from laris_b200 import _lib
+    assert declared - {"laris_last_error", "laris_launch_count"} == set(_lib.SIGNATURES), "ctypes table out of sync with the header"
+    assert _lib.lib.laris_abi_version() == 1
+
+
+def test_sass_is_sm100a():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "laris_b200", "liblaris_b200.so")],
+                         capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cuda_means_loud_failure(tiny):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import laris_b200 as la
+    a, lr, _ = tiny
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        la.tl.prepareLRInteraction(a, lr)
+
+
+def test_product_never_imports_the_oracle():
+    for d, _, files in os.walk(os.path.join(ROOT, "laris_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "/root/reference" not in src, f
+
+
+def test_argument_errors_match_reference(tiny):
+    import laris_b200 as la
+    a, lr, _ = tiny
+    lr_adata = a[:, :5]
+    with pytest.raises(ValueError, match="must be provided when by_celltype=True"):
+        la.tl.runLARIS(lr_adata, None, by_celltype=True)                       # reference tools/__init__.py:424-428
+    with pytest.raises(KeyError, match="not found in lr_adata.obsm"):
+        la.tl.runLARIS(lr_adata, a, use_rep="nope")                            # :430-434
+    with pytest.raises(ValueError, match="same shape"):
+        la.pp._rowwise_cosine_similarity(np.zeros((2, 3)), np.zeros((3, 2)))   # _utils.py:81-82
+    with pytest.raises(ValueError, match="must match number of rows"):
+        la.pp._pairwise_row_multiply(sp.csr_matrix(np.eye(3)), ["a", "b"])     # _utils.py:211-212
+    with pytest.raises(ValueError):
+        la.pp._select_top_n(np.arange(5.0), 9)                                 # argpartition kth out of bounds
+    bad = pd.DataFrame({"ligand": ["g00001", "nope"], "receptor": ["g00002", "g00003"]})
+    with pytest.raises(KeyError, match="nope"):
+        la.tl._lr_gene_indices(a, bad)                                         # FIX of the silent mis-map (:95-97)
+
+
+def test_select_top_n_docstring():
+    import laris_b200 as la
+    assert list(la.pp._select_top_n(np.array([0.1, 0.9, 0.3, 0.7, 0.5]), 3)) == [1, 3, 4]
+
+
+def test_anndata_carrier(tiny):
+    a, _, c = tiny
+    assert a.shape == (c.n, c.G) and a.n_obs == c.n and a.n_vars == c.G
+    b = a[:, ["g00003", "g00001"]]
+    assert b.shape == (c.n, 2) and list(b.var_names) == ["g00003", "g00001"]
+    assert (b.X != sp.csr_matrix(a.X)[:, [3, 1]]).nnz == 0
+    m = (a.obs["CellTypes"] == "ct01").to_numpy()
+    assert a[m, :].n_obs == m.sum()
+    d = a.copy()
+    d.obsm["X_spatial"][0, 0] = -1
+    assert a.obsm["X_spatial"][0, 0] != -1
+
+
+def test_synthetic_configs():
+    from laris_b200.synth import CONFIGS, make_dataset
+    assert set(CONFIGS) == {1, 2, 3, 4, 5}
+    a, lr, c = make_dataset(3, n=2000, G=200, G_u=120, P=90)
+    assert lr.shape == (90, 2) and not lr.duplicated().any()
+    assert lr["ligand"].value_counts().max() >= 2          # complexes expanded to several rows per ligand
+    xy = a.obsm["X_spatial"]
+    assert len(np.unique(xy, axis=0)) == len(xy)
+    b, _, _ = make_dataset(3, n=2000, G=200, G_u=120, P=90)
+    assert np.array_equal(b.obsm["X_spatial"], xy) and (b.X != a.X).nnz == 0
+
+
+def test_ranked_frame_roundtrip():
+    from laris_b200 import cosg_compat
+    rng = np.random.default_rng(0)
+    sc = rng.random((7, 3))
+    sc[2, 1] = -1.0
+    names = np.array([f"n{i}" for i in range(7)], dtype=object)
+    frame, order = cosg_compat.ranked_frame(names, sc, ["a", "b", "c"], "@@")
+    assert list(frame.columns[:3]) == ["names@@a", "names@@b", "names@@c"]
+    assert (np.diff(frame["scores@@a"].to_numpy()) <= 0).all()
+    back = cosg_compat.index_by_gene(frame, set_nan_to_zero=True, convert_negative_one_to_zero=True).loc[names]
+    expect = sc.copy()
+    expect[2, 1] = 0.0
+    assert np.allclose(back.to_numpy(), expect)
+    norm = cosg_compat.iqr_log_normalize(back)
+    assert norm.shape == back.shape and (norm.to_numpy() >= 0).all() and norm.to_numpy()[2, 1] == 0

@@ -1,0 +1,484 @@
+"""GPU tier: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs and against the committed reference fixtures.
+
+Bar: bit-exact for neighbour indices, distances, CSR structure, permutation
+counts; rtol 1e-5 for floating-point scores / statistics / p-values
+(BASELINE.json north_star)."""
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse as sp
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    import laris_b200._lib  # noqa: F401  (fails loudly if the library is missing)
+    return torch.device("cuda:0")
+
+
+def _coords(kind, n, seed=0, dim=2):
+    rng = np.random.default_rng(seed)
+    if kind == "uniform":
+        return rng.random((n, dim)) * 10.0 * np.sqrt(n)
+    if kind == "hex":
+        side = int(np.ceil(np.sqrt(n)))
+        ii, jj = np.divmod(np.arange(n), side)
+        return np.stack([(jj + 0.5 * (ii & 1)) * 100.0, ii * 86.60254037844386], 1) + rng.normal(0, 1, (n, 2))
+    if kind == "bins":
+        side = int(np.ceil(np.sqrt(n)))
+        ii, jj = np.divmod(np.arange(n), side)
+        return np.stack([jj, ii], 1).astype(np.float64) + rng.uniform(-0.01, 0.01, (n, 2))
+    if kind == "clustered":            # strongly non-uniform density + far outliers
+        c = rng.normal(0, 1, (n, dim)) * rng.choice([0.01, 1.0, 50.0], (n, 1))
+        c[:5] += 1e4
+        return c
+    if kind == "line":                 # degenerate extent in y
+        return np.stack([rng.random(n) * 1000.0, np.zeros(n)], 1)
+    raise ValueError(kind)
+
+
+# ------------------------------------------------------------------ K1 ----
+@pytest.mark.parametrize("kind,n,dim", [("uniform", 20000, 2), ("hex", 10000, 2), ("bins", 10000, 2),
+                                        ("clustered", 6000, 2), ("uniform", 8000, 3), ("line", 3000, 2),
+                                        ("uniform", 12, 2)])
+@pytest.mark.parametrize("k,include_self", [(10, True), (10, False), (1, False), (31, True)])
+def test_knn_bit_exact(dev, kind, n, dim, k, include_self):
+    from laris_b200 import engine
+    from oracle import restate as R
+    if k + (0 if include_self else 1) > n:
+        pytest.skip("k too large for n")
+    xy = _coords(kind, n, seed=n + k, dim=dim)
+    g = engine.build_graph(xy, k, include_self, sigma=100.0)
+    ind, dist = R.knn_graph(xy, k, include_self)
+    got_i, got_d = g.idx.cpu().numpy(), g.dist.cpu().numpy()
+    assert np.array_equal(got_d, dist), "distances must be bit-identical to sklearn's"
+    same = got_i == ind
+    if not same.all():                  # only exact distance ties may be ordered differently
+        rows = np.unique(np.nonzero(~same)[0])
+        for r in rows:
+            assert np.array_equal(np.sort(got_i[r]), np.sort(ind[r])) or len(np.unique(dist[r])) < k, r
+        assert len(rows) <= max(1, n // 1000)
+    order = g.order.cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(n))
+
+
+def test_knn_matches_reference_fixture(dev, golden):
+    from laris_b200 import engine
+    g = engine.build_graph(golden["xy"], 8, True)
+    assert np.array_equal(g.idx.cpu().numpy(), golden["knn_self_idx"])
+    assert np.array_equal(g.dist.cpu().numpy(), golden["knn_self_dist"])
+    g2 = engine.build_graph(golden["xy"], 8, False, sigma=100.0)
+    assert np.array_equal(g2.idx.cpu().numpy(), golden["knn_noself_idx"])
+    assert np.allclose(g2.w64.cpu().numpy(), golden["knn_noself_w"], rtol=1e-12)
+    A = g2.to_scipy()
+    assert A.shape == (1500, 1500) and A.indices.dtype == np.int64 and (np.diff(A.indptr) == 8).all()
+
+
+def test_knn_argument_errors(dev):
+    from laris_b200 import engine
+    from laris_b200._lib import LarisError
+    xy = _coords("uniform", 50)
+    with pytest.raises(LarisError, match="k out of range"):
+        engine.build_graph(xy, 64, False)
+    with pytest.raises(LarisError, match="need k"):
+        engine.build_graph(xy[:5], 10, True)
+    with pytest.raises(ValueError):
+        engine.build_graph(np.zeros((10, 4)), 3, True)
+
+
+def test_decay_weights(dev):
+    from laris_b200 import engine
+    from oracle import restate as R
+    xy = _coords("uniform", 5000, 3)
+    g = engine.build_graph(xy, 10, True)
+    _, dist = R.knn_graph(xy, 10, True)
+    assert np.allclose(g.w64.cpu().numpy(), R.decay_weights(dist), rtol=1e-12)
+    assert np.allclose(g.scale.item(), dist.mean() / 2, rtol=1e-13)
+    assert np.allclose(g.w.cpu().numpy(), R.decay_weights(dist), rtol=1e-6)
+    assert (g.w64.cpu().numpy()[:, 0] == 1.0).all()          # self weight exp(0)
+
+
+@pytest.mark.parametrize("n", [1, 5, 2047, 2048, 2049, 300001, 5_000_003])
+def test_exclusive_scan(dev, n):
+    from laris_b200 import _kernels as K
+    v = np.random.default_rng(n).integers(0, 1000, n)
+    out = K.exclusive_scan(torch.from_numpy(v).to(dev)).cpu().numpy()
+    assert out[0] == 0 and np.array_equal(out[1:], np.cumsum(v))
+
+
+# --------------------------------------------------------------- K2+K3 ----
+def _prepare_both(a, lr, k):
+    import laris_b200 as la
+    from oracle import restate as R
+    out = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=k)
+    li = R.gene_index(a.var_names, lr["ligand"])
+    ri = R.gene_index(a.var_names, lr["receptor"])
+    ind, dist = R.knn_graph(a.obsm["X_spatial"], k, True)
+    S = R.lr_scores(a.X, ind, R.decay_weights(dist), li, ri)
+    X = sp.csr_matrix(out.X)
+    X.sort_indices()
+    return out, X, S
+
+
+def _assert_csr_equal(X, S):
+    assert X.shape == S.shape
+    assert np.array_equal(X.indptr, S.indptr), "CSR row pointers differ"
+    assert np.array_equal(X.indices, S.indices), "CSR column indices differ"
+    assert np.allclose(X.data, S.data, rtol=RTOL, atol=0)
+
+
+def test_prepare_matches_reference_fixture(dev, golden, tiny):
+    import laris_b200 as la
+    a, lr, _ = tiny
+    out = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=8)
+    X = sp.csr_matrix(out.X)
+    X.sort_indices()
+    assert np.array_equal(X.indptr, golden["S_indptr"]) and np.array_equal(X.indices, golden["S_indices"])
+    assert np.allclose(X.data, golden["S_data"], rtol=RTOL, atol=0)
+    assert list(out.var_names[:2]) == [f"{l}::{r}" for l, r in zip(lr["ligand"][:2], lr["receptor"][:2])]
+    assert out.obs.equals(a.obs) and np.array_equal(out.obsm["X_spatial"], a.obsm["X_spatial"])
+    assert out.obsm["X_spatial"] is not a.obsm["X_spatial"]
+
+
+@pytest.mark.parametrize("cfg,n,over", [
+    (1, 10000, {}),                                              # BASELINE configs[0], full size
+    (2, 20000, {}),
+    (3, 6000, dict(G=2500, G_u=1500, P=1001)),                   # TC=16 tile, P not a multiple of 8
+    (3, 3000, dict(G=4000, G_u=3500, P=300)),                    # TC=8 tile
+    (1, 777, dict(G=64, G_u=40, P=7)),                           # ragged tile tail, tiny P
+])
+def test_prepare_vs_oracle(dev, cfg, n, over):
+    from laris_b200.synth import make_dataset
+    a, lr, c = make_dataset(cfg, n=n, **over)
+    _, X, S = _prepare_both(a, lr, c.k)
+    _assert_csr_equal(X, S)
+
+
+def test_prepare_edge_cases(dev):
+    """Empty cells, unexpressed genes, ligand == receptor, duplicate pairs, k=1, k=33, explicit zeros, float64 X."""
+    from laris_b200.synth import make_dataset
+    a, lr, c = make_dataset(1, n=1200, G=80, G_u=50, P=30)
+    X = sp.lil_matrix(a.X.astype(np.float64))
+    X[5:40, :] = 0                     # cells with no expression at all
+    X[:, 3] = 0                        # a gene nobody expresses
+    X = X.tocsr()
+    X.data[::17] = 0.0                 # explicitly stored zeros must not count as expressed
+    a.X = X
+    lr = pd.concat([lr, pd.DataFrame({"ligand": ["g00003", "g00007", lr["ligand"][0]],
+                                      "receptor": ["g00004", "g00007", lr["receptor"][0]]})], ignore_index=True)
+    for k in (1, 10, 33):
+        _, Xg, S = _prepare_both(a, lr, k)
+        _assert_csr_equal(Xg, S)
+    assert Xg[5:40].nnz == 0
+
+
+def test_prepare_requires_sparse_and_known_genes(dev, tiny):
+    import laris_b200 as la
+    a, lr, _ = tiny
+    bad = lr.copy()
+    bad.loc[0, "ligand"] = "not_a_gene"
+    with pytest.raises(KeyError, match="not_a_gene"):
+        la.tl.prepareLRInteraction(a, bad)
+    d = a.copy()
+    d._X = np.asarray(a.X.todense())
+    with pytest.raises(TypeError, match="sparse"):
+        la.tl.prepareLRInteraction(d, lr)
+    with pytest.raises(KeyError, match="X_nope"):
+        la.tl.prepareLRInteraction(a, lr, use_rep_spatial="X_nope")
+
+
+# ------------------------------------------------------------------ K4 ----
+def test_spatial_stats_and_nulls(dev, golden, tiny):
+    from laris_b200 import engine
+    from oracle import restate as R
+    n, P = 1500, 120
+    S = sp.csr_matrix((golden["S_data"], golden["S_indices"], golden["S_indptr"]), shape=(n, P))
+    sm = engine.scores_from_csr(S)
+    g = engine.build_graph(golden["xy"], 8, False, sigma=100.0)
+    st = engine.observed_stats(sm, g)
+    assert np.allclose(engine._cosine(st), golden["gsp"], rtol=RTOL, atol=1e-9)
+    assert np.array_equal(st[4].astype(np.int64), golden["nnz"])
+    assert np.allclose(st[3], np.asarray(S.sum(0)).ravel(), rtol=1e-6)
+    assert np.allclose(st[1], np.asarray(S.multiply(S).sum(0)).ravel(), rtol=1e-6)
+    # numpy-stream null == the reference's own random background
+    cos, state = engine.null_cosines(sm, g, 3, 27, "numpy")
+    assert np.allclose(cos, golden["rand_each"], rtol=RTOL, atol=1e-9)
+    assert state is not None
+    # philox null == oracle fed the CPU twin's draws
+    cos_p, _ = engine.null_cosines(sm, g, 3, 27, "philox")
+    ind, dist = R.knn_graph(golden["xy"], 8, False)
+    w = R.decay_weights(dist, 100.0)
+    ref = [R.null_cosine(S, 8, c, wp.astype(np.float32).astype(np.float64))
+           for c, wp in R.null_graphs(n, 8, w.astype(np.float32), 3, 27, "philox")]
+    assert np.allclose(cos_p, ref, rtol=RTOL, atol=1e-9)
+
+
+def test_null_graph_philox_bit_exact(dev):
+    from laris_b200 import _kernels as K
+    from oracle import rng as orng
+    n, k = 30011, 7
+    w = torch.rand((n, k), device=dev)
+    for rep in (0, 2):
+        cols, wout = K.null_graph_philox(n, k, w, rep, 27)
+        assert np.array_equal(cols.cpu().numpy().ravel(), orng.philox_null_cols(n, n * k, rep, 27))
+        perm = orng.feistel_permutation(n * k, rep, 27)
+        assert np.array_equal(wout.cpu().numpy().ravel(), w.cpu().numpy().ravel()[perm])
+
+
+def test_stats_column_tail_and_large_k(dev):
+    """P not a multiple of 4/128, k not a multiple of 4, order=None vs spatial order."""
+    from laris_b200 import _kernels as K, engine
+    from oracle import restate as R
+    rng = np.random.default_rng(5)
+    n, P, k = 3001, 131, 13
+    S = sp.random(n, P, 0.2, random_state=3, format="csr", dtype=np.float32)
+    xy = _coords("uniform", n, 9)
+    sm = engine.scores_from_csr(S)
+    g = engine.build_graph(xy, k, False, sigma=50.0)
+    a = K.spatial_stats(sm.S, P, g.idx, g.w, False, g.order).cpu().numpy()
+    b = K.spatial_stats(sm.S, P, g.idx, g.w, False, None).cpu().numpy()
+    assert np.allclose(a, b, rtol=1e-12)                         # order only changes fp64 summation order
+    ind, dist = R.knn_graph(xy, k, False)
+    ref = R.observed_cosine(S.astype(np.float64), ind, R.decay_weights(dist, 50.0))
+    assert np.allclose(engine._cosine(a), ref, rtol=RTOL, atol=1e-9)
+    del rng
+
+
+# ------------------------------------------------------------------ K5 ----
+def test_celltype_contractions(dev, golden, tiny):
+    from laris_b200 import _kernels as K, engine
+    from oracle import restate as R
+    a, _, c = tiny
+    n, P, C = 1500, 120, c.C
+    labels = golden["labels"].astype(np.int32)
+    S = sp.csr_matrix((golden["S_data"], golden["S_indices"], golden["S_indptr"]), shape=(n, P))
+    sm = engine.scores_from_csr(S)
+    lab_d = torch.from_numpy(labels).to(dev)
+    n_c = np.bincount(labels, minlength=C).astype(np.float64)
+    assert np.allclose(engine.celltype_fraction(sm, lab_d, C, n_c), R.celltype_fraction(S, labels, C), rtol=1e-12)
+    g = engine.build_graph(golden["xy"], 8, False, None)
+    ind, dist = R.knn_graph(golden["xy"], 8, False)
+    N_ref = R.neighborhood_composition(labels, ind, R.decay_weights(dist), C)
+    N = K.neighborhood_composition(lab_d, g.idx, g.w, C).cpu().numpy()
+    assert np.allclose(N.T, N_ref, rtol=1e-5, atol=1e-7)
+    raw, cos = engine.neighborhood_specificity(sm, lab_d, C, g, 100.0, impl=1)
+    assert np.allclose(cos, R.celltype_pair_cosine(S, N_ref), rtol=RTOL, atol=1e-8)
+    assert np.allclose(raw, golden["ctc_raw"], rtol=2e-5, atol=1e-10)       # the reference's own table
+    # COSG gene scores
+    X = sp.csr_matrix(a.X)
+    genes = np.unique(np.concatenate([golden["lig_idx"], golden["rec_idx"]]))
+    xu = engine.select_genes(X, genes)
+    got = engine.cosg_gene_scores(xu, lab_d, C, n_c.astype(np.int64), 100.0, 0.1, True)
+    ref = R.cosg_scores(X[:, genes], labels, C, 100.0, 0.1, True)
+    assert np.array_equal(got == -1, ref == -1)
+    assert np.allclose(got, ref, rtol=RTOL, atol=1e-9)
+
+
+# --------------------------------------------------------------- K6/K7 ----
+def test_pvalue_counts_exact(dev):
+    from laris_b200 import engine
+    from oracle import restate as R
+    from oracle import rng as orng
+    rng = np.random.default_rng(11)
+    Gn, P, nb, N = 9, 57, 30, 1003
+    table = rng.random((Gn, P)) * (rng.random((Gn, P)) < 0.4)
+    active = (rng.random(P) < 0.8).astype(np.uint8)
+    table[:, active == 0] = 0.0
+    bg = np.stack([rng.permutation(P)[:nb] for _ in range(P)]).astype(np.int32)
+    # philox: the oracle is fed the CPU twin's draws
+    ge, nz, both = engine.pvalue_counts(table, bg, active, N, rng="philox", seed=27)
+    rge, rnz, rboth = R.pvalue_counts(table, active.astype(bool), bg,
+                                      lambda g, pidx: orng.philox_pvalue_draws(g * P + pidx, N, nb, 27))
+    m = active.astype(bool)
+    assert np.array_equal(ge[:, m], rge[:, m]) and np.array_equal(nz[:, m], rnz[:, m])
+    assert np.array_equal(both[:, m], rboth[:, m])
+    assert (ge[:, ~m] == 0).all()
+    # host-supplied (numpy-stream) draws
+    draws = rng.integers(0, nb, (Gn, P, N)).astype(np.uint8)
+    ge2, nz2, both2 = engine.pvalue_counts(table, bg, active, N, rng="numpy", draws=draws)
+    rge2, _, rboth2 = R.pvalue_counts(table, m, bg, lambda g, pidx: draws[g][pidx].astype(np.int64))
+    assert np.array_equal(ge2[:, m], rge2[:, m]) and np.array_equal(both2[:, m], rboth2[:, m])
+
+
+def test_pvalue_counts_shard_invariance(dev):
+    """Permutation shards and pair shards add up to the unsharded counts (multi-GPU contract)."""
+    from laris_b200 import _kernels as K
+    rng = np.random.default_rng(3)
+    Gn, P, nb, N = 4, 40, 30, 1000
+    table = torch.from_numpy(rng.random((Gn, P))).to(dev)
+    bg = torch.from_numpy(np.stack([rng.permutation(P)[:nb] for _ in range(P)]).astype(np.int32)).to(dev)
+    full = K.pvalue_counts(table, bg, N, seed=5)[0].cpu().numpy()
+    acc = None
+    for t0, cnt in ((0, 333), (333, 334), (667, 333)):
+        acc = K.pvalue_counts(table, bg, cnt, seed=5, t0=t0, out=acc)
+    assert np.array_equal(acc[0].cpu().numpy(), full)
+
+
+def test_bh_fdr(dev):
+    from laris_b200 import engine
+    from oracle import restate as R
+    rng = np.random.default_rng(2)
+    for L in (1, 5, 33, 500, 2000):
+        p = np.round(rng.random((6, L)) ** 2, 6)
+        p[0, : L // 2] = p[0, 0]                      # heavy ties
+        sel = rng.random((6, L)) < 0.7
+        sel[1] = False
+        got = engine.bh_fdr(p, sel.astype(np.uint8))
+        for g in range(6):
+            exp = np.ones(L)
+            if sel[g].any():
+                exp[sel[g]] = R.bh_fdr(p[g, sel[g]])
+            assert np.allclose(got[g], exp, rtol=1e-12), (L, g)
+
+
+# ------------------------------------------------------- whole path ----
+def _keyed(res, lr_names, cats):
+    C = len(cats)
+    pid = pd.Index(lr_names).get_indexer(res["interaction_name"].to_numpy())
+    key = (pid * C + pd.Index(cats).get_indexer(res["sender"])) * C + pd.Index(cats).get_indexer(res["receiver"])
+    return key, np.argsort(key)
+
+
+def test_runlaris_matches_reference_fixture(dev, golden, tiny):
+    """prepare -> runLARIS(rng='numpy') against the unmodified reference's outputs."""
+    import laris_b200 as la
+    a, lr, c = tiny
+    lr_adata = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=8)
+    np.random.seed(999)
+    laris_lr, res = la.tl.runLARIS(lr_adata, a, n_nearest_neighbors=8, random_seed=27, n_repeats=3, mu=1, sigma=100,
+                                   n_cells_expressed_threshold=20, n_top_lr=4000, number_nearest_neighbors=8,
+                                   mu_celltype=100, n_neighbors_permutation=30, n_permutations=200, rng="numpy",
+                                   verbose=False)
+    assert np.allclose(lr_adata.var["LRSS_Target"], golden["gsp"], rtol=RTOL, atol=1e-9)
+    assert np.allclose(lr_adata.var["LRSS_Random"], golden["rand"], rtol=RTOL, atol=1e-9)
+    assert np.array_equal(lr_adata.var["n_cells_by_counts"], golden["nnz"])
+    lr_names = np.asarray(lr_adata.var_names)
+    assert list(laris_lr.columns) == ["ligand", "receptor", "score", "Rank"]
+    assert np.array_equal(laris_lr.index.to_numpy(), lr_names[golden["rank_order"]])     # permutation-derived ranks
+    assert np.allclose(laris_lr["score"], golden["rank_score"], rtol=RTOL, atol=1e-8)
+    assert list(res.columns) == ["sender", "receiver", "interaction_score", "ligand", "receptor", "interaction_name",
+                                 "p_value", "p_value_fdr", "nlog10_p_value_fdr"]
+    assert (np.diff(res["interaction_score"].to_numpy()) <= 0).all()
+    key, o = _keyed(res, lr_names, list(a.obs["CellTypes"].cat.categories))
+    assert np.array_equal(key[o], golden["tbl_key"])
+    sc = res["interaction_score"].to_numpy()[o]
+    assert np.array_equal(sc == 0, golden["tbl_score"] == 0)
+    assert np.allclose(sc, golden["tbl_score"], rtol=5e-5, atol=1e-12)
+    assert np.allclose(res["p_value"].to_numpy()[o], golden["tbl_p"], rtol=1e-12), "p-values are count-derived: exact"
+    assert np.allclose(res["p_value_fdr"].to_numpy()[o], golden["tbl_fdr"], rtol=1e-9)
+    assert np.allclose(res["nlog10_p_value_fdr"].to_numpy()[o], golden["tbl_nlog"], rtol=1e-9, atol=1e-12)
+    u = lr_adata.uns["cosg_lr"]
+    assert set(u) >= {"params", "COSG", "names", "scores"} and u["params"]["method"] == "COSG"
+    assert u["COSG"].shape == (120, 2 * c.C * c.C) and u["scores"].dtype[0] == np.float32
+    # the reference leaves np.random advanced exactly like this
+    from oracle import rng as orng
+    rs = orng.numpy_null_graph(1500, 8, orng.numpy_repeat_seeds(27, 3)[-1])[2]
+    for _ in range(c.C * c.C):
+        rs.randint(0, 30, size=(120, 200))
+    assert np.random.randint(0, 1 << 30) == rs.randint(0, 1 << 30)
+
+
+def test_runlaris_spatial_only_and_uploaded_scores(dev, golden, tiny):
+    """by_celltype=False returns one frame; a caller-built lr_adata (no device cache) gives the same numbers."""
+    import laris_b200 as la
+    from laris_b200._anndata import AnnDataLite
+    a, lr, _ = tiny
+    S = sp.csr_matrix((golden["S_data"], golden["S_indices"], golden["S_indptr"]), shape=(1500, 120))
+    names = (lr["ligand"] + "::" + lr["receptor"]).to_numpy(dtype=object)
+    lr_adata = AnnDataLite(S, obs=a.obs.copy(), var=pd.DataFrame(index=pd.Index(names, dtype=object)),
+                           obsm={"X_spatial": a.obsm["X_spatial"]})
+    out = la.tl.runLARIS(lr_adata, None, n_nearest_neighbors=8, by_celltype=False, n_cells_expressed_threshold=20,
+                         verbose=False)
+    assert isinstance(out, pd.DataFrame) and len(out) == 120
+    assert np.allclose(lr_adata.var["LRSS_Target"], golden["gsp"], rtol=RTOL, atol=1e-9)
+    assert np.array_equal(out.index.to_numpy(), names[golden["rank_order"]])
+    out_p = la.tl.runLARIS(lr_adata, None, n_nearest_neighbors=8, by_celltype=False, n_cells_expressed_threshold=20,
+                           rng="philox", verbose=False)
+    assert len(out_p) == 120 and np.isfinite(out_p["score"]).all()
+
+
+def test_runlaris_philox_conditional(dev, tiny):
+    """Device RNG end to end, conditional p-values, no prefilter: well-formed and reproducible."""
+    import laris_b200 as la
+    a, lr, c = tiny
+    lr_adata = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=8)
+    kw = dict(n_nearest_neighbors=8, n_cells_expressed_threshold=20, number_nearest_neighbors=8, n_permutations=300,
+              rng="philox", use_conditional_pvalue=True, prefilter_fdr=False, verbose=False)
+    _, r1 = la.tl.runLARIS(lr_adata, a, **kw)
+    _, r2 = la.tl.runLARIS(lr_adata, a, **kw)
+    assert r1.equals(r2)
+    assert len(r1) == 120 * c.C * c.C
+    p = r1["p_value"].to_numpy()
+    assert ((p > 0) & (p <= 1)).all() and (p[r1["interaction_score"].to_numpy() == 0] == 1).all()
+    assert ((r1["p_value_fdr"] >= r1["p_value"].round(6) - 1e-12) & (r1["p_value_fdr"] <= 1)).all()
+
+
+def test_pp_helpers(dev):
+    import laris_b200 as la
+    rng = np.random.default_rng(0)
+    A, B = rng.random((40, 300)), rng.random((40, 300))
+    A[3] = 0
+    ref = np.einsum("ij,ij->i", A, B) / np.maximum(np.linalg.norm(A, axis=1) * np.linalg.norm(B, axis=1), 1e-300)
+    ref[3] = 0
+    assert np.allclose(la.pp._rowwise_cosine_similarity(A, B), ref, rtol=RTOL)
+    assert np.allclose(la.pp._rowwise_cosine_similarity(sp.csr_matrix(A), sp.csr_matrix(B)), ref, rtol=RTOL)
+    m = sp.csr_matrix(np.array([[1., 0, 2, 0, 1], [0, 1, 1, 0, 2], [2, 0, 0, 1, 1]]))
+    prod, names = la.pp._pairwise_row_multiply(m, ["TypeA", "TypeB", "TypeC"])
+    assert prod.shape == (9, 5) and list(names[:3]) == ["TypeA::TypeA", "TypeA::TypeB", "TypeA::TypeC"]
+    d = m.toarray()
+    assert np.array_equal(prod.toarray(), (d[:, None, :] * d[None, :, :]).reshape(9, 5))
+
+
+def test_utils_wrappers(dev, golden, tiny):
+    from laris_b200.tools import _utils as U
+    a, _, _ = tiny
+    A = U._build_adjacency_matrix(a, n_nearest_neighbors=8, sigma=100)
+    assert np.array_equal(A.indices.reshape(1500, 8), golden["knn_noself_idx"])
+    S = sp.csr_matrix((golden["S_data"], golden["S_indices"], golden["S_indptr"]), shape=(1500, 120))
+    bgl = U._generate_random_background(a, A, S.T.tocsr(), n_nearest_neighbors=8, n_repeats=3, random_seed=27)
+    assert np.allclose(np.asarray(bgl), golden["rand_each"], rtol=RTOL, atol=1e-9)
+    R_ = U._build_random_adjacency_matrix(a, A, n_nearest_neighbors=8, random_seed=5)
+    assert R_.shape == A.shape and np.isclose(R_.sum(), A.sum())
+
+
+# ------------------------------------------- full-size properties ----
+def test_full_size_properties_config2(dev):
+    """BASELINE configs[1] at full size: size-independent invariants instead of an O(n) oracle run."""
+    import laris_b200 as la
+    from laris_b200 import engine
+    from laris_b200.synth import make_dataset
+    from laris_b200.tools import _utils as U
+    a, lr, c = make_dataset(2)
+    out = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=c.k)
+    X = out.X
+    assert X.shape == (c.n, c.P) and X.has_sorted_indices and (X.data != 0).all()
+    sm = U._scores_of(out)
+    g = engine.build_graph(a.obsm["X_spatial"], c.k, False, sigma=100.0)
+    st = engine.observed_stats(sm, g)
+    # checksum of checksums: device column sums == host sums of the materialised CSR
+    assert np.allclose(st[3], np.asarray(X.sum(0)).ravel(), rtol=1e-5)
+    assert np.array_equal(st[4].astype(np.int64), np.asarray(X.getnnz(0)).ravel())
+    # mask property: a score is non-zero only where the ligand or receptor is expressed in that cell
+    li = pd.Index(a.var_names).get_indexer(lr["ligand"])
+    ri = pd.Index(a.var_names).get_indexer(lr["receptor"])
+    Xc = sp.csc_matrix(a.X)
+    rows = slice(0, 5000)
+    expr = ((Xc[rows][:, li] != 0) + (Xc[rows][:, ri] != 0)).toarray()
+    assert not (X[rows].toarray() != 0)[~expr].any()
+    # linearity of the diffusion: scaling X by 2 scales every score by 4
+    b = a.copy()
+    b.X = a.X * 2.0
+    X2 = la.tl.prepareLRInteraction(b, lr, number_nearest_neighbors=c.k).X
+    assert np.array_equal(X2.indices, X.indices) and np.allclose(X2.data, 4.0 * X.data, rtol=1e-6)
+    # cosines are bounded and the null is reproducible
+    cos = engine._cosine(st)
+    assert (np.abs(cos) <= 1 + 1e-9).all()
+    n1, _ = engine.null_cosines(sm, g, 2, 27, "philox")
+    n2, _ = engine.null_cosines(sm, g, 2, 27, "philox")
+    assert np.array_equal(n1, n2) and (np.abs(n1) <= 1 + 1e-9).all()

@@ -1,0 +1,50 @@
+"""CPU tier: the CPU twin of the device RNG (oracle/rng.py) against published
+Philox known answers and numpy's legacy stream."""
+import numpy as np
+
+from oracle import rng
+
+
+def test_philox4x32_10_random123_kat():
+    M = 0xFFFFFFFF
+    assert [int(x) for x in rng.philox4x32(0, 0, 0, 0, 0)] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert [int(x) for x in rng.philox4x32(M, M, M, M, (M << 32) | M)] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    got = rng.philox4x32(0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344, (0x299F31D0 << 32) | 0xA4093822)
+    assert [int(x) for x in got] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_mulhi64_exact():
+    a = np.array([2 ** 64 - 1, 12345678901234567, 0, 1 << 63], dtype=np.uint64)
+    for b in (1, 1000003, 2 ** 40 + 7):
+        assert [int(x) for x in rng.mulhi64(a, b)] == [(int(x) * b) >> 64 for x in a]
+
+
+def test_feistel_is_a_bijection():
+    for m in (1, 2, 3, 17, 1000, 4096, 100003):
+        p = rng.feistel_permutation(m, 2, 27)
+        assert np.array_equal(np.sort(p), np.arange(m))
+    assert not np.array_equal(rng.feistel_permutation(1000, 0, 27), rng.feistel_permutation(1000, 1, 27))
+
+
+def test_null_cols_in_range_and_uniform():
+    c = rng.philox_null_cols(1000, 200000, 0, 27)
+    assert c.min() >= 0 and c.max() < 1000
+    assert abs(np.bincount(c, minlength=1000).std() / 200 - 1 / np.sqrt(200)) < 0.02
+
+
+def test_pvalue_draws_sharding_invariant():
+    full = rng.philox_pvalue_draws(np.arange(50), 101, 30, 27)
+    part = rng.philox_pvalue_draws(np.arange(20, 30), 101, 30, 27)
+    assert np.array_equal(full[20:30], part) and full.max() < 30 and full.min() >= 0
+
+
+def test_numpy_replay_known_answers():
+    # seed(27); choice(1902772, 3, replace=False)
+    assert list(rng.numpy_repeat_seeds(27, 3)) == [1076532, 128070, 219018]
+    cols, perm, rs = rng.numpy_null_graph(50, 3, 5)
+    np.random.seed(5)
+    c2 = np.random.choice(np.arange(50), 150, replace=True)
+    x = np.arange(150) * 1.5
+    np.random.shuffle(x)
+    assert np.array_equal(cols, c2) and np.array_equal(x, (np.arange(150) * 1.5)[perm])
+    assert np.array_equal(rs.randint(0, 30, size=(4, 7)), np.random.randint(0, 30, size=(4, 7)))
