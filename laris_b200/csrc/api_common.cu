@@ -9,6 +9,19 @@
 namespace laris {
 static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<unsigned long long> g_pool_ready{0};          // bit d = device d configured
+void retain_pool_memory() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+    const unsigned long long bit = 1ull << dev;
+    if (g_pool_ready.load(std::memory_order_relaxed) & bit) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    g_pool_ready.fetch_or(bit, std::memory_order_relaxed);
+}
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
     va_list ap;

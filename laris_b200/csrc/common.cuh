@@ -42,13 +42,20 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// keep freed scratch cached in the device's default memory pool instead of handing it back to the
+// driver at every synchronisation (the pool's default release threshold is 0)
+void retain_pool_memory();
+
 // stream-ordered scratch; freed on the same stream (no host sync)
 template <typename T>
 struct Scratch {
     T* p = nullptr;
     cudaStream_t s;
     explicit Scratch(cudaStream_t st) : s(st) {}
-    cudaError_t alloc(size_t count) { return cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), s); }
+    cudaError_t alloc(size_t count) {
+        retain_pool_memory();
+        return cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), s);
+    }
     ~Scratch() { if (p) cudaFreeAsync(p, s); }
     Scratch(const Scratch&) = delete;
     Scratch& operator=(const Scratch&) = delete;
