@@ -57,12 +57,15 @@ __global__ void bbox_partial_kernel(const double* __restrict__ xy, int64_t n, in
 }
 
 __global__ void bbox_final_kernel(const double* __restrict__ part, int nblocks, double* __restrict__ out) {
-    int t = threadIdx.x;
-    if (t < 6) {
-        double v = part[t];
-        for (int b = 1; b < nblocks; ++b) v = t < 3 ? fmin(v, part[b * 6 + t]) : fmax(v, part[b * 6 + t]);
-        out[t] = v;
+    // one warp per output component, lanes stride over the block partials
+    const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double v = t < 3 ? DBL_MAX : -DBL_MAX;
+    for (int b = lane; b < nblocks; b += 32) v = t < 3 ? fmin(v, part[b * 6 + t]) : fmax(v, part[b * 6 + t]);
+    for (int o = 16; o > 0; o >>= 1) {
+        const double u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = t < 3 ? fmin(v, u) : fmax(v, u);
     }
+    if (lane == 0) out[t] = v;
 }
 
 // --------------------------------------------------------------- binning --
@@ -239,12 +242,12 @@ __global__ void sum_partial_kernel(const double* __restrict__ v, int64_t m, doub
 }
 
 __global__ void scale_final_kernel(const double* __restrict__ part, int nb, int64_t m, double sigma, double* __restrict__ scale) {
-    if (threadIdx.x == 0) {
-        if (sigma > 0.0) { *scale = sigma; return; }
-        double t = 0.0;
-        for (int b = 0; b < nb; ++b) t += part[b];
-        *scale = (t / (double)m) / 2.0;
-    }
+    // one warp; fixed lane-strided order + butterfly, so the sum is deterministic
+    if (sigma > 0.0) { if (threadIdx.x == 0) *scale = sigma; return; }
+    double t = 0.0;
+    for (int b = threadIdx.x; b < nb; b += 32) t += part[b];
+    t = warp_sum(t);
+    if (threadIdx.x == 0) *scale = (t / (double)m) / 2.0;
 }
 
 __global__ void decay_weights_kernel(const double* __restrict__ dist, int64_t m, const double* __restrict__ scale,
@@ -276,7 +279,7 @@ extern "C" int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int 
     LARIS_CUDA(box_d.alloc(6));
     bbox_partial_kernel<<<nb, 256, 0, st>>>(xy, n, dim, part.p);
     LARIS_LAUNCH_CHECK();
-    bbox_final_kernel<<<1, 32, 0, st>>>(part.p, nb, box_d.p);
+    bbox_final_kernel<<<1, 192, 0, st>>>(part.p, nb, box_d.p);
     LARIS_LAUNCH_CHECK();
     double box[6];
     LARIS_CUDA(cudaMemcpyAsync(box, box_d.p, sizeof(box), cudaMemcpyDeviceToHost, st));
