@@ -168,8 +168,6 @@ def run_ours(args):
     xy_d = K.to_device(a.obsm["X_spatial"], torch.float64)
     csr_d = engine.upload_csr(a.X)
     lig_g, rec_g = la.tl._lr_gene_indices(a, lr)
-    genes, inv = np.unique(np.concatenate([lig_g, rec_g]), return_inverse=True)
-    lig_u, rec_u = inv[:P].astype(np.int32), inv[P:].astype(np.int32)
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # > 126 MB L2
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -179,9 +177,9 @@ def run_ours(args):
         e0, e1, e2, e3 = ev(), ev(), ev(), ev()
         e0.record()
         graph = engine.build_graph(xy_d, k, True, None)
-        xu = engine.select_genes(a.X, genes, csr_dev=csr_d)
+        xu, lig_c, rec_c = engine.select_lr_genes(a.X, lig_g, rec_g, csr_dev=csr_d)
         e1.record()
-        sm = engine.lr_scores(xu, graph, lig_u, rec_u)
+        sm = engine.lr_scores(xu, graph, lig_c, rec_c)
         e2.record()
         e3.record()
         state.update(graph=graph, xu=xu, sm=sm)

@@ -108,6 +108,16 @@ LARIS_API int laris_diffuse_lr_score(const int64_t* xu_indptr, const int64_t* xu
                            const int32_t* lig, const int32_t* rec, int32_t P,
                            float* S, int64_t ldS, int64_t* row_nnz, void* stream);
 
+/* HOST helper (all pointers are host memory, no device work): number the Xu columns so that
+ * laris_diffuse_lr_score's 32-lane gathers of D[lig[p]] / D[rec[p]] are free of shared-memory
+ * bank conflicts.  lig, rec [P] are gene indices in [0,G_u); column_of [G_u] receives the column
+ * of each gene (injective), *n_columns the column range (a multiple of 32, >= G_u).  Feed
+ * column_of through gene_map of laris_csr_select_* and use column_of[lig], column_of[rec] and
+ * G_u = *n_columns in laris_diffuse_lr_score.  Any injective numbering is CORRECT; this one is
+ * the fast one. */
+LARIS_API int laris_lr_column_layout(const int32_t* lig, const int32_t* rec, int32_t P, int32_t G_u,
+                           int32_t* column_of, int32_t* n_columns);
+
 /* Dense S -> CSR (the reference's lr_adata.X, laris/tools/__init__.py:104,117):
  * indptr [n+1] int64 = exclusive scan of row_nnz; writes column-sorted
  * indices [nnz] int32 and data [nnz] fp32 holding exactly the non-zero scores. */

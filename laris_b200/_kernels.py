@@ -38,6 +38,21 @@ def to_device(a, dtype):
     return t.to(dev, dtype=dtype, non_blocking=t.is_pinned())
 
 
+def to_host(*tensors):
+    """Device tensors -> numpy arrays through page-locked staging (one stream sync for all).
+
+    The arrays are views of torch pinned-host tensors: torch's caching host allocator
+    recycles the pages once the arrays are garbage collected, so steady-state calls pay
+    neither page-locking nor page-fault cost and the copies run at PCIe speed."""
+    outs = []
+    for t in tensors:
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        outs.append(h)
+    torch.cuda.current_stream().synchronize()
+    return tuple(h.numpy() for h in outs) if len(outs) != 1 else outs[0].numpy()
+
+
 # ----------------------------------------------------------------- K1 ----
 def knn_graph(xy, k, include_self, want_order=True):
     n, dim = xy.shape
@@ -83,6 +98,16 @@ def csr_select(indptr, indices, data, gene_map):
 
 
 # -------------------------------------------------------------- K2+K3 ----
+def lr_column_layout(lig_u, rec_u, n_genes):
+    """Host call: (column_of [n_genes] int32, n_columns)."""
+    import ctypes
+    cols = np.empty(n_genes, dtype=np.int32)
+    ncol = ctypes.c_int32(0)
+    check(lib.laris_lr_column_layout(lig_u.ctypes.data, rec_u.ctypes.data, len(lig_u), n_genes, cols.ctypes.data,
+                                     ctypes.addressof(ncol)), "laris_lr_column_layout")
+    return cols, int(ncol.value)
+
+
 def padded_ld(P):
     return (P + 7) // 8 * 8
 

@@ -2,24 +2,29 @@
 // gene-selection and CSR (de)compaction kernels either side of it.
 //
 // Data layout in HBM
-//   Xu      packed CSR over the G_u genes the LR table uses: indptr int64[n+1],
+//   Xu      packed CSR over the columns the LR table uses: indptr int64[n+1],
 //           entries int64 = {lo: int32 column in [0,G_u), hi: fp32 bits}
 //   graph   idx int32[n*k], w fp32[n*k]  (K1 output, fixed degree)
 //   S       dense fp32 [n][ldS], cell-major (a row = all pair scores of a cell,
 //           which is the unit every downstream kernel gathers)
 //
-// Kernel shape (diffuse_score_kernel): a CTA owns a tile of TC spatially
-// adjacent cells (consecutive entries of the K1 processing order).
-//   phase 1  each warp owns some of the tile's cells and streams the packed
-//            sparse rows of that cell's k neighbours (64-bit coalesced loads,
-//            software-prefetched one neighbour ahead) into a shared-memory
-//            tile D[g][cell] (row stride TC+1 so both phases are conflict-light)
-//   phase 2  lane = cell: for each LR pair both operands D[lig][cell],
-//            D[rec][cell] are conflict-free shared loads, the expression mask is
-//            a broadcast word per gene (bit per cell); each lane emits 8
-//            consecutive pairs of its cell as two 128-bit streaming stores.
+// Kernel shape (diffuse_score_kernel): ONE WARP OWNS ONE CELL, no CTA barrier in
+// the loop.  The warp keeps the cell's neighbour-aggregated expression row
+// D[0..G_u) in a private slab of shared memory.
+//   phase 1  the k neighbour rows are streamed as a flat list of 32-entry
+//            chunks (64-bit coalesced ld.global.nc, 4 chunks in flight per
+//            lane); each lane adds w*x into D[column] (columns of one row are
+//            distinct, so the read-modify-write needs no atomics)
+//   flags    the cell's own row marks "expressed" in the SIGN BIT of D (all
+//            contributions non-negative, the normal case), else in a bitmap
+//   phase 2  lane owns 4 consecutive pairs: two shared loads per score, and
+//            the warp writes 512 contiguous bytes of the cell's S row per step
 // D never touches HBM.  Algorithmic bytes: 8*nnz(Xu) + 8*n*k + 4*n*P.
+// Shared-memory bank conflicts: phase 2 reads D[lig[p]] for 32 different pairs
+// at once; laris_lr_column_layout() numbers the columns so that those land in
+// 32 different banks (graph colouring of the LR table).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace laris {
 
@@ -61,36 +66,10 @@ __global__ void csr_select_fill_kernel(const int64_t* __restrict__ indptr, const
 }
 
 // ---------------------------------------------------------------- K2+K3 --
-// Shared-memory layout of one CTA (all regions 16-byte aligned):
-//   D      [(G_u+1)][TC+1] fp32   neighbour-aggregated expression of the tile, gene-major;
-//                                 row G_u is a zero "dummy gene" that padding pairs point at
-//   flags  [G_u+1]         u32    bit c set <=> cell c of the tile expresses the gene
-//   pairs  [P8]            u32    lig | rec << 16  (padding: dummy | dummy << 16)
-//   nb_ptr [TC][KC] i64, nb_len [TC][KC] i32, nb_w [TC][KC] f32   neighbour rows of the tile
-//   self_ptr [TC] i64, self_len [TC] i32, cell_row [TC] i32, cell_cnt [TC] i32
-constexpr int kDsKC = 16;                          // neighbours staged per pass (k > 16 takes several passes)
-
-struct DsLayout {
-    int d_words, f_words, p_words;
-    size_t off_flags, off_pairs, off_nbptr, off_nblen, off_nbw, off_selfptr, off_selflen, off_row, off_cnt, total;
-    __host__ __device__ DsLayout(int G_u, int64_t ldS, int TC) {
-        d_words = ((G_u + 1) * (TC + 1) + 3) & ~3;
-        f_words = (G_u + 1 + 3) & ~3;
-        p_words = (int)((ldS + 7) / 8) * 8;
-        size_t o = (size_t)d_words * 4;
-        off_flags = o; o += (size_t)f_words * 4;
-        off_pairs = o; o += (size_t)p_words * 4;
-        o = (o + 7) & ~(size_t)7;
-        off_nbptr = o; o += (size_t)TC * kDsKC * 8;
-        off_selfptr = o; o += (size_t)TC * 8;
-        off_nblen = o; o += (size_t)TC * kDsKC * 4;
-        off_nbw = o; o += (size_t)TC * kDsKC * 4;
-        off_selflen = o; o += (size_t)TC * 4;
-        off_row = o; o += (size_t)TC * 4;
-        off_cnt = o; o += (size_t)TC * 4;
-        total = (o + 15) & ~(size_t)15;
-    }
-};
+// Shared memory of one CTA:  pairs [p_words] u32 (lig | rec << 16, shared by the warps), then per
+// warp  D [dw_words] fp32 (slot G_u = always-zero column of the padding pairs, slot G_u+1 = write
+// sink of idle lanes)  and  B [bw_words] u32 (expression bitmap, only used for signed data).
+constexpr int kDsDepth = 4;                        // entry chunks in flight per warp
 
 __device__ __forceinline__ int2 ld_entry(const int2* p) {
     int2 r;
@@ -98,136 +77,155 @@ __device__ __forceinline__ int2 ld_entry(const int2* p) {
     return r;
 }
 
-template <int TC, int NT>
+struct DsLayout {
+    int dw_words, bw_words;
+    size_t total;
+    __host__ __device__ DsLayout(int G_u, int p_words, int nw) {
+        dw_words = (G_u + 2 + 3) & ~3;
+        bw_words = ((G_u + 2 + 31) / 32 + 3) & ~3;
+        total = ((size_t)p_words + (size_t)nw * (dw_words + bw_words)) * 4;
+    }
+};
+
+template <int NT>
 __global__ void __launch_bounds__(NT)
 diffuse_score_kernel(const int64_t* __restrict__ xu_indptr, const int64_t* __restrict__ xu_packed, int64_t n, int G_u,
                      const int32_t* __restrict__ idx, const float* __restrict__ w, int k,
-                     const int32_t* __restrict__ order, const int32_t* __restrict__ lig, const int32_t* __restrict__ rec,
-                     int P, float* __restrict__ S, int64_t ldS, int64_t* __restrict__ row_nnz) {
-    constexpr int STRIDE = TC + 1;
-    constexpr int SUB = 32 / TC;                   // pair groups handled side by side by one warp
+                     const int32_t* __restrict__ order, const uint32_t* __restrict__ pairs, int p_words,
+                     float* __restrict__ S, int64_t ldS, int64_t* __restrict__ row_nnz) {
     constexpr int NW = NT / 32;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const DsLayout L(G_u, ldS, TC);
-    float* D = reinterpret_cast<float*>(smem_raw);
-    uint32_t* flags = reinterpret_cast<uint32_t*>(smem_raw + L.off_flags);
-    uint32_t* pairs = reinterpret_cast<uint32_t*>(smem_raw + L.off_pairs);
-    int64_t* nb_ptr = reinterpret_cast<int64_t*>(smem_raw + L.off_nbptr);
-    int32_t* nb_len = reinterpret_cast<int32_t*>(smem_raw + L.off_nblen);
-    float* nb_w = reinterpret_cast<float*>(smem_raw + L.off_nbw);
-    int64_t* self_ptr = reinterpret_cast<int64_t*>(smem_raw + L.off_selfptr);
-    int32_t* self_len = reinterpret_cast<int32_t*>(smem_raw + L.off_selflen);
-    int32_t* cell_row = reinterpret_cast<int32_t*>(smem_raw + L.off_row);
-    int32_t* cell_cnt = reinterpret_cast<int32_t*>(smem_raw + L.off_cnt);
-
+    const DsLayout L(G_u, p_words, NW);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t pad_pair = (uint32_t)G_u | ((uint32_t)G_u << 16);
-    for (int p = tid; p < L.p_words; p += NT)
-        pairs[p] = p < P ? ((uint32_t)lig[p] | ((uint32_t)rec[p] << 16)) : pad_pair;
+    uint32_t* pairs_s = reinterpret_cast<uint32_t*>(smem_raw);
+    float* Dw = reinterpret_cast<float*>(pairs_s + p_words) + (size_t)warp * (L.dw_words + L.bw_words);
+    uint32_t* Bw = reinterpret_cast<uint32_t*>(Dw + L.dw_words);
+    for (int p = tid; p < p_words; p += NT) pairs_s[p] = pairs[p];
+    __syncthreads();
     const int2* __restrict__ entries = reinterpret_cast<const int2*>(xu_packed);
+    const int sink = G_u + 1;
 
-    const int64_t ntiles = (n + TC - 1) / TC;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        __syncthreads();                                            // previous tile fully consumed
-        {   // zero the D tile and the flag words (adjacent regions, 128-bit stores)
-            float4* z = reinterpret_cast<float4*>(D);
-            const int nz4 = (L.d_words + L.f_words) / 4;
-            for (int q = tid; q < nz4; q += NT) z[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (tid < TC) {
-            const int64_t q = tile * TC + tid;
-            const int32_t i = q < n ? (order ? order[q] : (int32_t)q) : -1;
-            cell_row[tid] = i;
-            cell_cnt[tid] = 0;
-            int64_t s = 0, e = 0;
-            if (i >= 0) { s = xu_indptr[i]; e = xu_indptr[i + 1]; }
-            self_ptr[tid] = s;
-            self_len[tid] = (int)(e - s);
-        }
-        __syncthreads();
-
-        // ---------------- phase 1: D[g][c] = sum_j w[c,j] * Xu[nb(c,j), g] ----------------
-        for (int j0 = 0; j0 < k; j0 += kDsKC) {
-            const int kc = min(kDsKC, k - j0);
-            if (j0) __syncthreads();
-            for (int e = tid; e < TC * kc; e += NT) {                // neighbour table of this pass
-                const int c = e / kc, j = e - c * kc;
-                const int64_t i = cell_row[c];
-                int64_t s = 0;
-                int len = 0;
-                float wj = 0.f;
-                if (i >= 0) {
-                    const int64_t nb = idx[i * k + j0 + j];
-                    wj = w[i * k + j0 + j];
-                    s = xu_indptr[nb];
-                    len = (int)(xu_indptr[nb + 1] - s);
-                }
-                nb_ptr[c * kDsKC + j] = s;
-                nb_len[c * kDsKC + j] = len;
-                nb_w[c * kDsKC + j] = wj;
-            }
-            __syncthreads();
-            for (int c = warp; c < TC; c += NW) {
-                float* Dc = D + c;
-                if (j0 == 0) {                                       // expression flags of the cell itself
-                    const int2* row = entries + self_ptr[c];
-                    const int len = self_len[c];
-                    for (int t = lane; t < len; t += 32) atomicOr(&flags[ld_entry(row + t).x], 1u << c);
-                }
-                for (int j = 0; j < kc; ++j) {
-                    const int2* row = entries + nb_ptr[c * kDsKC + j];
-                    const int len = nb_len[c * kDsKC + j];
-                    const float wj = nb_w[c * kDsKC + j];
-                    for (int t = lane; t < len; t += 128) {          // 4 independent 64-bit loads in flight per lane
-                        const bool v1 = t + 32 < len, v2 = t + 64 < len, v3 = t + 96 < len;
-                        const int2 e0 = ld_entry(row + t);
-                        int2 e1 = make_int2(0, 0), e2 = make_int2(0, 0), e3 = make_int2(0, 0);
-                        if (v1) e1 = ld_entry(row + t + 32);
-                        if (v2) e2 = ld_entry(row + t + 64);
-                        if (v3) e3 = ld_entry(row + t + 96);
-                        { float* d = Dc + e0.x * STRIDE; *d = fmaf(wj, __int_as_float(e0.y), *d); }
-                        if (v1) { float* d = Dc + e1.x * STRIDE; *d = fmaf(wj, __int_as_float(e1.y), *d); }
-                        if (v2) { float* d = Dc + e2.x * STRIDE; *d = fmaf(wj, __int_as_float(e2.y), *d); }
-                        if (v3) { float* d = Dc + e3.x * STRIDE; *d = fmaf(wj, __int_as_float(e3.y), *d); }
-                    }
-                    __syncwarp();                                    // the next neighbour may hit the same genes
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---------------- phase 2: S[c][p] = D[l][c] * D[r][c] * (flag_l | flag_r)[c] ----------------
-        {
-            const int c = lane % TC, sub = lane / TC;
-            const int64_t i = cell_row[c];
-            const float* Dc = D + c;
-            float* srow = S + (i >= 0 ? i : 0) * ldS;
-            int cnt = 0;
-            for (int p0 = (warp * SUB + sub) * 8; p0 < L.p_words; p0 += NW * SUB * 8) {
-                const uint4 pa = *reinterpret_cast<const uint4*>(pairs + p0);
-                const uint4 pb = *reinterpret_cast<const uint4*>(pairs + p0 + 4);
-                const uint32_t pr[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-                float v[8];
+    const int64_t nwarps = (int64_t)gridDim.x * NW;
+    for (int64_t q = (int64_t)blockIdx.x * NW + warp; q < n; q += nwarps) {
+        const int64_t i = order ? (int64_t)order[q] : q;
+        for (int t = lane * 4; t < L.dw_words; t += 128) *reinterpret_cast<float4*>(Dw + t) = make_float4(0.f, 0.f, 0.f, 0.f);
+        // the cell's own row: its first 128 columns are fetched now and consumed after phase 1
+        const int64_t self_s = xu_indptr[i];
+        const int self_len = (int)(xu_indptr[i + 1] - self_s);
+        int selfcol[4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int l = (int)(pr[u] & 0xffffu), r = (int)(pr[u] >> 16);
-                    const float prod = Dc[l * STRIDE] * Dc[r * STRIDE];
-                    const uint32_t m = ((flags[l] | flags[r]) >> c) & 1u;
+        for (int u = 0; u < 4; ++u) selfcol[u] = lane + 32 * u < self_len ? ld_entry(entries + self_s + lane + 32 * u).x : sink;
+        __syncwarp();
+
+        // ---------------- phase 1: D[g] = sum_j w[j] * Xu[nb(j), g] ----------------
+        uint32_t signs = 0;                                          // sign bit set <=> some contribution was negative
+        for (int j0 = 0; j0 < k; j0 += 32) {
+            const int kc = min(32, k - j0);
+            int64_t rs = 0;
+            int len = 0;
+            float wv = 0.f;
+            if (lane < kc) {
+                const int64_t nb = idx[i * k + j0 + lane];
+                wv = w[i * k + j0 + lane];
+                rs = xu_indptr[nb];
+                len = (int)(xu_indptr[nb + 1] - rs);
+            }
+            const int nchunk = warp_sum(lane < kc ? max(1, (len + 31) >> 5) : 0);
+            int pj = 0, pt = 0;                                      // producer cursor: neighbour, offset in its row
+            int64_t prs = __shfl_sync(FULL, rs, 0);
+            int plen = __shfl_sync(FULL, len, 0);
+            float pw = __shfl_sync(FULL, wv, 0);
+            int2 eb[kDsDepth];
+            float wb[kDsDepth];
+            for (int c0 = 0; c0 < nchunk + kDsDepth; c0 += kDsDepth) {
+#pragma unroll
+                for (int d = 0; d < kDsDepth; ++d) {
+                    const int ci = c0 + d;
+                    if (ci >= kDsDepth && ci - kDsDepth < nchunk) {  // consume the chunk loaded kDsDepth steps ago
+                        float* dp = Dw + eb[d].x;
+                        *dp = fmaf(wb[d], __int_as_float(eb[d].y), *dp);
+                        signs |= __float_as_uint(wb[d]) ^ (uint32_t)eb[d].y;
+                        __syncwarp();                                // the next chunk may belong to another row
+                    }
+                    if (ci < nchunk) {                               // issue the next chunk
+                        const int t = pt + lane;
+                        eb[d] = t < plen ? ld_entry(entries + prs + t) : make_int2(sink, 0);
+                        wb[d] = pw;
+                        pt += 32;
+                        if (pt >= plen) {
+                            ++pj;
+                            pt = 0;
+                            prs = __shfl_sync(FULL, rs, pj & 31);
+                            plen = __shfl_sync(FULL, len, pj & 31);
+                            pw = __shfl_sync(FULL, wv, pj & 31);
+                        }
+                    }
+                }
+            }
+        }
+        const bool signed_data = __any_sync(FULL, (signs >> 31) != 0u);
+
+        // ---------------- expression flags of the cell itself ----------------
+        if (!signed_data) {                                          // D >= 0: the sign bit is free to carry the flag
+#pragma unroll
+            for (int u = 0; u < 4; ++u) Dw[selfcol[u]] = -fabsf(Dw[selfcol[u]]);
+            for (int t = 128 + lane; t < self_len; t += 32) { float* dp = Dw + ld_entry(entries + self_s + t).x; *dp = -fabsf(*dp); }
+        } else {
+            for (int t = lane * 4; t < L.bw_words; t += 128) *reinterpret_cast<uint4*>(Bw + t) = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+            for (int t = lane; t < self_len; t += 32) {
+                const int g = ld_entry(entries + self_s + t).x;
+                atomicOr(&Bw[g >> 5], 1u << (g & 31));
+            }
+        }
+        __syncwarp();
+
+        // ---------------- phase 2: S[p] = D[l] * D[r] * (flag_l | flag_r) ----------------
+        float* srow = S + i * ldS;
+        int cnt = 0;
+        if (!signed_data) {
+            for (int p0 = lane * 4; p0 < (int)ldS; p0 += 128) {
+                const uint4 pr4 = *reinterpret_cast<const uint4*>(pairs_s + p0);
+                const uint32_t pr[4] = {pr4.x, pr4.y, pr4.z, pr4.w};
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float a = Dw[pr[u] & 0xffffu], b = Dw[pr[u] >> 16];
+                    const bool m = (int)(__float_as_uint(a) | __float_as_uint(b)) < 0;
+                    v[u] = m ? fabsf(a * b) : 0.f;
+                    cnt += v[u] != 0.f;
+                }
+                st_stream_f4(reinterpret_cast<float4*>(srow + p0), make_float4(v[0], v[1], v[2], v[3]));
+            }
+        } else {
+            for (int p0 = lane * 4; p0 < (int)ldS; p0 += 128) {
+                const uint4 pr4 = *reinterpret_cast<const uint4*>(pairs_s + p0);
+                const uint32_t pr[4] = {pr4.x, pr4.y, pr4.z, pr4.w};
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t l = pr[u] & 0xffffu, r = pr[u] >> 16;
+                    const uint32_t m = ((Bw[l >> 5] >> (l & 31)) | (Bw[r >> 5] >> (r & 31))) & 1u;
+                    const float prod = Dw[l] * Dw[r];
                     v[u] = m ? prod : 0.f;
                     cnt += v[u] != 0.f;
                 }
-                if (i >= 0) {
-                    if (p0 + 4 <= ldS) st_stream_f4(reinterpret_cast<float4*>(srow + p0), make_float4(v[0], v[1], v[2], v[3]));
-                    if (p0 + 8 <= ldS) st_stream_f4(reinterpret_cast<float4*>(srow + p0 + 4), make_float4(v[4], v[5], v[6], v[7]));
-                }
+                st_stream_f4(reinterpret_cast<float4*>(srow + p0), make_float4(v[0], v[1], v[2], v[3]));
             }
-            if (row_nnz) atomicAdd(&cell_cnt[c], cnt);
         }
         if (row_nnz) {
-            __syncthreads();
-            if (tid < TC && cell_row[tid] >= 0) row_nnz[cell_row[tid]] = cell_cnt[tid];
+            cnt = warp_sum(cnt);
+            if (lane == 0) row_nnz[i] = cnt;
         }
+        __syncwarp();                                                // D is re-zeroed for the next cell
     }
+}
+
+__global__ void pack_pairs_kernel(const int32_t* __restrict__ lig, const int32_t* __restrict__ rec, int P, int G_u,
+                                  int p_words, uint32_t* __restrict__ pairs) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < p_words) pairs[p] = p < P ? ((uint32_t)lig[p] | ((uint32_t)rec[p] << 16)) : ((uint32_t)G_u | ((uint32_t)G_u << 16));
 }
 
 // --------------------------------------------------------- CSR <-> dense --
@@ -258,26 +256,6 @@ __global__ void csr_scatter_kernel(const int64_t* __restrict__ indptr, const int
     const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (row >= n) return;
     for (int64_t t = indptr[row] + lane; t < indptr[row + 1]; t += 32) S[row * ldS + indices[t]] = data[t];
-}
-
-template <int TC, int NT>
-static int launch_diffuse(const int64_t* xu_indptr, const int64_t* xu_packed, int64_t n, int G_u, const int32_t* idx,
-                          const float* w, int k, const int32_t* order, const int32_t* lig, const int32_t* rec, int P,
-                          float* S, int64_t ldS, int64_t* row_nnz, size_t smem, int per_sm, cudaStream_t st) {
-    auto kern = diffuse_score_kernel<TC, NT>;
-    LARIS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 1;
-    LARIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
-    if (occ < 1) occ = 1;
-    if (occ < per_sm) per_sm = occ;
-    int dev = 0, sms = kNumSMs;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t ntiles = (n + TC - 1) / TC;
-    const int64_t grid = ntiles < (int64_t)sms * per_sm ? ntiles : (int64_t)sms * per_sm;
-    kern<<<(unsigned)grid, NT, smem, st>>>(xu_indptr, xu_packed, n, G_u, idx, w, k, order, lig, rec, P, S, ldS, row_nnz);
-    LARIS_LAUNCH_CHECK();
-    return LARIS_OK;
 }
 
 }  // namespace laris
@@ -312,32 +290,36 @@ extern "C" int laris_diffuse_lr_score(const int64_t* xu_indptr, const int64_t* x
     cudaStream_t st = (cudaStream_t)stream;
     LARIS_CHECK_ARG(xu_indptr && idx && w && lig && rec && S, "laris_diffuse_lr_score: null pointer");
     LARIS_CHECK_ARG(n > 0 && k >= 1 && P >= 1, "laris_diffuse_lr_score: empty problem");
-    LARIS_CHECK_ARG(G_u >= 1 && G_u <= 65535, "laris_diffuse_lr_score: G_u must be in [1, 65535] (got %d)", G_u);
+    LARIS_CHECK_ARG(G_u >= 1 && G_u <= 65533, "laris_diffuse_lr_score: G_u must be in [1, 65533] (got %d)", G_u);
     LARIS_CHECK_ARG(ldS >= P && ldS % 4 == 0 && ((uintptr_t)S & 15) == 0,
                     "laris_diffuse_lr_score: S needs ldS >= P, ldS %% 4 == 0 and 16-byte alignment");
-    // tile shape: the largest tile that still leaves >= 6 CTAs (48 warps) per SM; when the gene
-    // set is too large for that, the largest tile with >= 2 CTAs and 512-thread CTAs to keep warps up
-    const size_t smem_sm = 227 * 1024;
-    auto need = [&](int tc) { return DsLayout(G_u, ldS, tc).total; };
-    int tc = 0, nt = 256, per_sm = 1;
-    for (int cand : {32, 16, 8}) if ((need(cand) + 1024) * 6 <= smem_sm) { tc = cand; per_sm = (int)(smem_sm / (need(cand) + 1024)); break; }
-    if (!tc) for (int cand : {32, 16, 8}) if ((need(cand) + 1024) * 2 <= smem_sm) { tc = cand; nt = 512; per_sm = (int)(smem_sm / (need(cand) + 1024)); break; }
-    if (!tc) for (int cand : {16, 8}) if (need(cand) + 1024 <= smem_sm) { tc = cand; nt = 512; per_sm = 1; break; }
-    if (!tc) {
-        set_error("laris_diffuse_lr_score: G_u=%d, P=%d do not fit the shared-memory tile (limit ~6000 genes)", G_u, P);
+    // pack the pair table once: lig | rec << 16, padded with the zero "dummy gene" G_u
+    const int p_words = (int)((ldS + 7) / 8) * 8;
+    Scratch<uint32_t> pairs(st);
+    LARIS_CUDA(pairs.alloc((size_t)p_words));
+    pack_pairs_kernel<<<(unsigned)ceil_div(p_words, 256), 256, 0, st>>>(lig, rec, P, G_u, p_words, pairs.p);
+    LARIS_LAUNCH_CHECK();
+    // 8 warps per CTA, each with a private D slab; persistent grid = SMs x resident CTAs
+    constexpr int NT = 256;
+    const DsLayout L(G_u, p_words, NT / 32);
+    if (L.total + 1024 > (size_t)227 * 1024) {
+        set_error("laris_diffuse_lr_score: G_u=%d, P=%d do not fit shared memory (limit ~6500 columns)", G_u, P);
         return LARIS_E_LIMIT;
     }
-    if (per_sm > 8) per_sm = 8;
-#define ARGS xu_indptr, xu_packed, n, G_u, idx, w, k, order, lig, rec, P, S, ldS, row_nnz, need(tc), per_sm, st
-    if (nt == 256) {
-        if (tc == 32) return launch_diffuse<32, 256>(ARGS);
-        if (tc == 16) return launch_diffuse<16, 256>(ARGS);
-        return launch_diffuse<8, 256>(ARGS);
-    }
-    if (tc == 32) return launch_diffuse<32, 512>(ARGS);
-    if (tc == 16) return launch_diffuse<16, 512>(ARGS);
-    return launch_diffuse<8, 512>(ARGS);
-#undef ARGS
+    auto kern = diffuse_score_kernel<NT>;
+    LARIS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    int occ = 1;
+    LARIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, L.total));
+    if (occ < 1) occ = 1;
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t want = ceil_div(n, NT / 32);
+    const int64_t grid = want < (int64_t)sms * occ ? want : (int64_t)sms * occ;
+    kern<<<(unsigned)grid, NT, L.total, st>>>(xu_indptr, xu_packed, n, G_u, idx, w, k, order, pairs.p, p_words, S, ldS,
+                                              row_nnz);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
 }
 
 extern "C" int laris_csr_compact(const float* S, int64_t ldS, int64_t n, int32_t P, const int64_t* indptr,

@@ -59,12 +59,15 @@ def build_graph(xy, k, include_self, sigma=None) -> SpatialGraph:
 class ExpressionU:
     indptr: torch.Tensor   # [n+1] int64
     packed: torch.Tensor   # [nnz] int64 {col:int32, val:fp32}
-    genes: np.ndarray      # [G_u] global gene column of each packed column
+    genes: np.ndarray      # [n_genes] global gene column of each selected gene
     n: int
+    columns: np.ndarray | None = None   # [n_genes] packed column of each selected gene (None: 0..n_genes-1)
+    n_columns: int | None = None
 
     @property
     def G_u(self):
-        return len(self.genes)
+        """Column range of the packed matrix (>= number of selected genes when a layout leaves holes)."""
+        return len(self.genes) if self.n_columns is None else self.n_columns
 
 
 def upload_csr(X):
@@ -72,18 +75,42 @@ def upload_csr(X):
     if not sp.issparse(X):
         raise TypeError("adata.X must be a scipy sparse matrix (as in the reference, laris/tools/__init__.py:100)")
     X = X.tocsr()
+    if not X.has_canonical_format:                  # the kernels assume one entry per (row, column)
+        X = X.copy()
+        X.sum_duplicates()
     return (K.to_device(X.indptr, torch.int64), K.to_device(X.indices, torch.int32), K.to_device(X.data, torch.float32))
 
 
-def select_genes(X, genes, csr_dev=None) -> ExpressionU:
-    """Restrict X (n x G CSR) to ``genes`` (unique global columns) on the device."""
+def select_genes(X, genes, csr_dev=None, columns=None, n_columns=None) -> ExpressionU:
+    """Restrict X (n x G CSR) to ``genes`` (unique global columns) on the device.
+    ``columns`` optionally gives the packed column of each gene (see ``lr_column_layout``)."""
     n, G = X.shape
     genes = np.asarray(genes, dtype=np.int64)
     gene_map = np.full(G, -1, dtype=np.int32)
-    gene_map[genes] = np.arange(len(genes), dtype=np.int32)
+    gene_map[genes] = np.arange(len(genes), dtype=np.int32) if columns is None else np.asarray(columns, dtype=np.int32)
     indptr, indices, data = csr_dev if csr_dev is not None else upload_csr(X)
     out_indptr, packed = K.csr_select(indptr, indices, data, K.to_device(gene_map, torch.int32))
-    return ExpressionU(out_indptr, packed, genes, n)
+    return ExpressionU(out_indptr, packed, genes, n, None if columns is None else np.asarray(columns, dtype=np.int32),
+                       n_columns)
+
+
+def lr_column_layout(lig_u, rec_u, n_genes):
+    """Bank-conflict-free numbering of the packed columns for the score kernel
+    (host-side graph colouring of the LR table, ``laris_lr_column_layout``)."""
+    lig_u = np.ascontiguousarray(lig_u, dtype=np.int32)
+    rec_u = np.ascontiguousarray(rec_u, dtype=np.int32)
+    return K.lr_column_layout(lig_u, rec_u, int(n_genes))
+
+
+def select_lr_genes(X, lig_g, rec_g, csr_dev=None):
+    """Gene selection for an LR table given as global gene columns.
+    Returns (ExpressionU, ligand packed columns [P], receptor packed columns [P])."""
+    P = len(lig_g)
+    genes, inv = np.unique(np.concatenate([np.asarray(lig_g), np.asarray(rec_g)]), return_inverse=True)
+    lig_u, rec_u = inv[:P].astype(np.int32), inv[P:].astype(np.int32)
+    columns, n_columns = lr_column_layout(lig_u, rec_u, len(genes))
+    xu = select_genes(X, genes, csr_dev=csr_dev, columns=columns, n_columns=n_columns)
+    return xu, columns[lig_u], columns[rec_u]
 
 
 # --------------------------------------------------------------- scores ----
@@ -110,10 +137,17 @@ def lr_scores(xu: ExpressionU, graph: SpatialGraph, lig_u, rec_u) -> ScoreMatrix
 def scores_to_csr(sm: ScoreMatrix, dtype=np.float32) -> sp.csr_matrix:
     if sm.row_nnz is None:
         raise ValueError("score matrix has no row counts")
-    indptr, indices, data = K.csr_compact(sm.S, sm.P, sm.row_nnz)
-    X = sp.csr_matrix((data.cpu().numpy().astype(dtype, copy=False), indices.cpu().numpy(), indptr.cpu().numpy()),
-                      shape=(sm.n, sm.P))
+    indptr, indices, data = K.to_host(*K.csr_compact(sm.S, sm.P, sm.row_nnz))
+    # built without scipy's O(nnz) validation passes (check_format / index-dtype scans): the device
+    # kernel guarantees a canonical CSR (sorted, duplicate-free, no explicit zeros)
+    X = sp.csr_matrix((sm.n, sm.P), dtype=np.dtype(dtype))
+    if len(data) < 2 ** 31 - 1:
+        indptr = indptr.astype(np.int32)             # scipy's own choice of index dtype for this size
+    else:
+        indices = indices.astype(np.int64)
+    X.data, X.indices, X.indptr = data.astype(dtype, copy=False), indices, indptr
     X.has_sorted_indices = True
+    X.has_canonical_format = True
     return X
 
 

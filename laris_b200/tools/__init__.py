@@ -41,11 +41,9 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     """
     xy = _utils._coords(adata, use_rep_spatial)
     lig_g, rec_g = _lr_gene_indices(adata, lr_df)
-    genes, inv = np.unique(np.concatenate([lig_g, rec_g]), return_inverse=True)
-    P = len(lig_g)
     graph = engine.build_graph(xy, number_nearest_neighbors, True, None)
-    xu = engine.select_genes(adata.X, genes)
-    sm = engine.lr_scores(xu, graph, inv[:P], inv[P:])
+    xu, lig_c, rec_c = engine.select_lr_genes(adata.X, lig_g, rec_g)
+    sm = engine.lr_scores(xu, graph, lig_c, rec_c)
     X = engine.scores_to_csr(sm, dtype)
     lr_names = (lr_df["ligand"].astype(str) + "::" + lr_df["receptor"].astype(str)).to_numpy(dtype=object)
     lr_adata = make_anndata(X, obs=adata.obs.copy(), var=pd.DataFrame(index=pd.Index(lr_names, dtype=object)),

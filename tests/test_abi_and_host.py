@@ -115,3 +115,25 @@ def test_ranked_frame_roundtrip():
     assert np.allclose(back.to_numpy(), expect)
     norm = cosg_compat.iqr_log_normalize(back)
     assert norm.shape == back.shape and (norm.to_numpy() >= 0).all() and norm.to_numpy()[2, 1] == 0
+
+
+def test_lr_column_layout_is_injective_and_conflict_free():
+    """Host helper laris_lr_column_layout: an injective column numbering under which the score
+    kernel's 32-lane gathers (pairs 128b + 4t + u, t = lane) hit 32 distinct banks."""
+    from laris_b200 import engine
+    rng = np.random.default_rng(3)
+    for G_u, P in ((40, 64), (334, 500), (1346, 2000), (7, 300)):
+        lig = rng.integers(0, G_u, P).astype(np.int32)
+        rec = rng.integers(0, G_u, P).astype(np.int32)
+        cols, ncol = engine.lr_column_layout(lig, rec, G_u)
+        assert cols.shape == (G_u,) and len(np.unique(cols)) == G_u and cols.min() >= 0 and cols.max() < ncol
+        assert ncol % 32 == 0 and ncol <= G_u + 96
+        got = ident = groups = 0
+        for a in (lig, rec):
+            for b0 in range(0, P, 128):
+                for u in range(4):
+                    g = np.unique(a[b0 + u:b0 + 128:4])
+                    got += np.bincount(cols[g] % 32).max()          # wavefronts of that gather
+                    ident += np.bincount(g % 32).max()
+                    groups += 1
+        assert got <= ident and (G_u < 64 or got <= 0.7 * ident), (got, ident, groups)

@@ -14,9 +14,11 @@ xy = K.to_device(a.obsm["X_spatial"], torch.float64)
 csr = engine.upload_csr(a.X)
 lg, rg = la.tl._lr_gene_indices(a, lr)
 genes, inv = np.unique(np.concatenate([lg, rg]), return_inverse=True)
-gm = np.full(a.shape[1], -1, np.int32); gm[genes] = np.arange(len(genes), dtype=np.int32)
+layout = os.environ.get("LARIS_LAYOUT", "1") == "1"
+cols, ncols = engine.lr_column_layout(inv[:P], inv[P:], len(genes)) if layout else (np.arange(len(genes), dtype=np.int32), len(genes))
+gm = np.full(a.shape[1], -1, np.int32); gm[genes] = cols
 gm_d = K.to_device(gm, torch.int32)
-lig = K.to_device(inv[:P].astype(np.int32), torch.int32); rec = K.to_device(inv[P:].astype(np.int32), torch.int32)
+lig = K.to_device(cols[inv[:P]].astype(np.int32), torch.int32); rec = K.to_device(cols[inv[P:]].astype(np.int32), torch.int32)
 labels = K.to_device(a.obs["CellTypes"].cat.codes.to_numpy().astype(np.int32), torch.int32)
 
 def T(name, fn, reps=5):
@@ -34,8 +36,8 @@ idx, dist, order = T("knn_graph(incl self)", lambda: K.knn_graph(xy, k, True))
 w32, w64, sc = T("decay_weights", lambda: K.decay_weights(dist, None, True))
 xu_indptr, xu_packed = T("csr_select", lambda: K.csr_select(*csr, gm_d))
 print("  nnz_u =", xu_packed.numel())
-S, row_nnz = T("diffuse_lr_score", lambda: K.diffuse_lr_score(xu_indptr, xu_packed, len(genes), idx, w32, order, lig, rec))
-T("diffuse_lr_score(order=None)", lambda: K.diffuse_lr_score(xu_indptr, xu_packed, len(genes), idx, w32, None, lig, rec))
+S, row_nnz = T("diffuse_lr_score", lambda: K.diffuse_lr_score(xu_indptr, xu_packed, ncols, idx, w32, order, lig, rec))
+T("diffuse_lr_score(order=None)", lambda: K.diffuse_lr_score(xu_indptr, xu_packed, ncols, idx, w32, None, lig, rec))
 T("csr_compact", lambda: K.csr_compact(S, P, row_nnz))
 idx2, dist2, order2 = T("knn_graph(excl self)", lambda: K.knn_graph(xy, k, False))
 w2, _, _ = K.decay_weights(dist2, 100.0)
