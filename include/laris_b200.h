@@ -108,6 +108,25 @@ LARIS_API int laris_diffuse_lr_score(const int64_t* xu_indptr, const int64_t* xu
                            const int32_t* lig, const int32_t* rec, int32_t P,
                            float* S, int64_t ldS, int64_t* row_nnz, void* stream);
 
+/* Dense-panel variant of the same fused path, for expression panels dense enough (>= ~8 % non-zeros
+ * over the LR genes) that dense fp32 rows are cheaper to gather than packed sparse rows.  Same
+ * reference lines as above (laris/tools/__init__.py:91-92, :100, :110-117).
+ *
+ * laris_csr_select_dense: restrict the CSR matrix to the LR genes and write them as dense rows
+ *   Xd [n*ldX] fp32, ldX % 128 == 0, ldX > (largest column id in gene_map); slots without a gene
+ *   are zero.  neg_flag [1] int32 (may be NULL) is set to 1 if any kept value is negative.
+ * laris_diffuse_lr_score_dense: one warp owns min(3, 32/k) consecutive cells of `order`, loads each
+ *   distinct neighbour row once (128-bit loads) and accumulates D for all of them in registers.
+ *   neg_flag from the call above (NULL = unknown: the slower bitmap path is taken); the other
+ *   arguments as in laris_diffuse_lr_score.  Result: identical structure, values equal up to the
+ *   fp32 summation order over neighbours. */
+LARIS_API int laris_csr_select_dense(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
+                           const int32_t* gene_map, float* Xd, int64_t ldX, int32_t* neg_flag, void* stream);
+LARIS_API int laris_diffuse_lr_score_dense(const float* Xd, int64_t ldX, const int32_t* neg_flag, int64_t n,
+                                 int32_t G_u, const int32_t* idx, const float* w, int k, const int32_t* order,
+                                 const int32_t* lig, const int32_t* rec, int32_t P,
+                                 float* S, int64_t ldS, int64_t* row_nnz, void* stream);
+
 /* HOST helper (all pointers are host memory, no device work): number the Xu columns so that
  * laris_diffuse_lr_score's 32-lane gathers of D[lig[p]] / D[rec[p]] are free of shared-memory
  * bank conflicts.  lig, rec [P] are gene indices in [0,G_u); column_of [G_u] receives the column

@@ -126,6 +126,32 @@ def diffuse_lr_score(xu_indptr, xu_packed, G_u, idx, w, order, lig, rec, want_ro
     return S, row_nnz
 
 
+def csr_select_dense(indptr, indices, data, gene_map, n_columns):
+    """(Xd fp32 [n, ldX] dense over the packed columns, neg_flag int32[1]); ldX = 128-multiple > n_columns."""
+    n = indptr.numel() - 1
+    ldX = (int(n_columns) + 1 + 127) // 128 * 128
+    Xd = torch.empty((n, ldX), dtype=torch.float32, device=indptr.device)
+    neg = torch.empty(1, dtype=torch.int32, device=indptr.device)
+    check(lib.laris_csr_select_dense(_ptr(indptr, torch.int64), _ptr(indices, torch.int32), _ptr(data, torch.float32), n,
+                                     _ptr(gene_map, torch.int32), _ptr(Xd), ldX, _ptr(neg), _stream()),
+          "laris_csr_select_dense")
+    return Xd, neg
+
+
+def diffuse_lr_score_dense(Xd, neg_flag, G_u, idx, w, order, lig, rec, want_row_nnz=True):
+    n, k = idx.shape
+    P = lig.numel()
+    ld = padded_ld(P)
+    S = torch.empty((n, ld), dtype=torch.float32, device=idx.device)
+    row_nnz = torch.empty(n, dtype=torch.int64, device=idx.device) if want_row_nnz else None
+    check(lib.laris_diffuse_lr_score_dense(_ptr(Xd, torch.float32), Xd.shape[1], _ptr(neg_flag, torch.int32) if neg_flag is not None else None,
+                                           n, G_u, _ptr(idx, torch.int32), _ptr(w, torch.float32), k,
+                                           _ptr(order, torch.int32) if order is not None else None,
+                                           _ptr(lig, torch.int32), _ptr(rec, torch.int32), P, _ptr(S), ld, _ptr(row_nnz),
+                                           _stream()), "laris_diffuse_lr_score_dense")
+    return S, row_nnz
+
+
 def csr_compact(S, P, row_nnz):
     n, ld = S.shape
     indptr = exclusive_scan(row_nnz)

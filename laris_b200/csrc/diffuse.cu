@@ -66,11 +66,9 @@ __global__ void csr_select_fill_kernel(const int64_t* __restrict__ indptr, const
 }
 
 // ---------------------------------------------------------------- K2+K3 --
-// Shared memory of one CTA:  pairs [p_words] u32 (lig | rec << 16, shared by the warps), then per
-// warp  D [dw_words] fp32 (slot G_u = always-zero column of the padding pairs, slot G_u+1 = write
-// sink of idle lanes)  and  B [bw_words] u32 (expression bitmap, only used for signed data).
-constexpr int kDsDepth = 4;                        // entry chunks in flight per warp
-
+// Shared memory of one CTA:  [pair table p_words u32, only when the table does not fit registers]
+// then per warp  D [dw_words] fp32 (slot G_u = always-zero column of the padding pairs)  and
+// B [bw_words] u32 (expression bitmap, only touched for signed data).
 __device__ __forceinline__ int2 ld_entry(const int2* p) {
     int2 r;
     asm volatile("ld.global.nc.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
@@ -80,14 +78,66 @@ __device__ __forceinline__ int2 ld_entry(const int2* p) {
 struct DsLayout {
     int dw_words, bw_words;
     size_t total;
-    __host__ __device__ DsLayout(int G_u, int p_words, int nw) {
-        dw_words = (G_u + 2 + 3) & ~3;
-        bw_words = ((G_u + 2 + 31) / 32 + 3) & ~3;
-        total = ((size_t)p_words + (size_t)nw * (dw_words + bw_words)) * 4;
+    __host__ __device__ DsLayout(int G_u, int table_words, int nw) {
+        dw_words = (G_u + 1 + 3) & ~3;
+        bw_words = ((G_u + 1 + 31) / 32 + 3) & ~3;
+        total = ((size_t)table_words + (size_t)nw * (dw_words + bw_words)) * 4;
     }
 };
 
-template <int NT>
+// One neighbour row in flight: CH chunks of 32 packed entries (lane-strided), its weight, and the
+// number of entries left counted from this lane (chunk c holds a valid entry iff 32c < rem).
+template <int CH>
+struct RowBuf {
+    int2 e[CH];
+    float w;
+    int rem;
+};
+
+template <int CH>
+__device__ __forceinline__ void row_load(RowBuf<CH>& b, const int2* rowp, int len, float wv, int j, int lane) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int2* p = reinterpret_cast<const int2*>(__shfl_sync(FULL, (unsigned long long)rowp, j)) + lane;
+    b.rem = __shfl_sync(FULL, len, j) - lane;
+    b.w = __shfl_sync(FULL, wv, j);
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+        if (32 * c < b.rem) b.e[c] = ld_entry(p + 32 * c);
+}
+
+// D[col] += w * x for the row's entries.  Columns of one row are distinct, so the chunks of a row need
+// no ordering among themselves; the trailing __syncwarp orders this row against the next one.
+template <int CH>
+__device__ __forceinline__ void row_accumulate(const RowBuf<CH>& b, float* Dw, uint32_t& signs) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+        if (32 * c < b.rem) {
+            float* dp = Dw + b.e[c].x;
+            *dp = fmaf(b.w, __int_as_float(b.e[c].y), *dp);
+            signs |= (uint32_t)b.e[c].y;
+        }
+    __syncwarp();
+}
+
+// one score: D[l]*D[r] gated by "ligand or receptor expressed in this cell"
+template <bool SIGNED>
+__device__ __forceinline__ float lr_score1(const float* Dw, const uint32_t* Bw, uint32_t pr, int& cnt) {
+    const uint32_t l = pr & 0xffffu, r = pr >> 16;
+    const float a = Dw[l], b = Dw[r];
+    float v;
+    if (SIGNED) {
+        const uint32_t m = ((Bw[l >> 5] >> (l & 31)) | (Bw[r >> 5] >> (r & 31))) & 1u;
+        v = m ? a * b : 0.f;
+    } else {                                                         // flag = sign bit of D (D >= 0)
+        const bool m = (int)(__float_as_uint(a) | __float_as_uint(b)) < 0;
+        v = m ? fabsf(a * b) : 0.f;
+    }
+    cnt += v != 0.f;
+    return v;
+}
+
+// NT threads, CH entry chunks per row pass, PPL LR pairs per lane held in registers (0: table in smem)
+template <int NT, int CH, int PPL>
 __global__ void __launch_bounds__(NT)
 diffuse_score_kernel(const int64_t* __restrict__ xu_indptr, const int64_t* __restrict__ xu_packed, int64_t n, int G_u,
                      const int32_t* __restrict__ idx, const float* __restrict__ w, int k,
@@ -96,71 +146,75 @@ diffuse_score_kernel(const int64_t* __restrict__ xu_indptr, const int64_t* __res
     constexpr int NW = NT / 32;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const DsLayout L(G_u, p_words, NW);
+    const int table_words = PPL ? 0 : p_words;
+    const DsLayout L(G_u, table_words, NW);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* pairs_s = reinterpret_cast<uint32_t*>(smem_raw);
-    float* Dw = reinterpret_cast<float*>(pairs_s + p_words) + (size_t)warp * (L.dw_words + L.bw_words);
+    float* Dw = reinterpret_cast<float*>(pairs_s + table_words) + (size_t)warp * (L.dw_words + L.bw_words);
     uint32_t* Bw = reinterpret_cast<uint32_t*>(Dw + L.dw_words);
-    for (int p = tid; p < p_words; p += NT) pairs_s[p] = pairs[p];
-    __syncthreads();
+    uint32_t pr[PPL ? PPL : 1];
+    if (PPL) {                                                       // this lane's pairs never change: registers
+#pragma unroll
+        for (int g = 0; g < PPL / 4; ++g) {
+            const uint4 t = *reinterpret_cast<const uint4*>(pairs + 128 * g + 4 * lane);   // table padded to 32*PPL
+            pr[4 * g] = t.x; pr[4 * g + 1] = t.y; pr[4 * g + 2] = t.z; pr[4 * g + 3] = t.w;
+        }
+    } else {
+        for (int p = tid; p < p_words; p += NT) pairs_s[p] = pairs[p];
+        __syncthreads();
+    }
     const int2* __restrict__ entries = reinterpret_cast<const int2*>(xu_packed);
-    const int sink = G_u + 1;
 
     const int64_t nwarps = (int64_t)gridDim.x * NW;
     for (int64_t q = (int64_t)blockIdx.x * NW + warp; q < n; q += nwarps) {
         const int64_t i = order ? (int64_t)order[q] : q;
         for (int t = lane * 4; t < L.dw_words; t += 128) *reinterpret_cast<float4*>(Dw + t) = make_float4(0.f, 0.f, 0.f, 0.f);
-        // the cell's own row: its first 128 columns are fetched now and consumed after phase 1
+        // the cell's own row: its first 32*CH columns are fetched now and consumed after phase 1
         const int64_t self_s = xu_indptr[i];
         const int self_len = (int)(xu_indptr[i + 1] - self_s);
-        int selfcol[4];
+        int selfcol[CH];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) selfcol[u] = lane + 32 * u < self_len ? ld_entry(entries + self_s + lane + 32 * u).x : sink;
+        for (int c = 0; c < CH; ++c)
+            if (lane + 32 * c < self_len) selfcol[c] = ld_entry(entries + self_s + lane + 32 * c).x;
         __syncwarp();
 
         // ---------------- phase 1: D[g] = sum_j w[j] * Xu[nb(j), g] ----------------
-        uint32_t signs = 0;                                          // sign bit set <=> some contribution was negative
+        // Rows are consumed in neighbour order; the loads of row j+1 are in flight while row j is added.
+        uint32_t signs = 0;                                          // sign bit set <=> a negative value or weight was seen
         for (int j0 = 0; j0 < k; j0 += 32) {
             const int kc = min(32, k - j0);
-            int64_t rs = 0;
+            const int2* rowp = entries;
             int len = 0;
             float wv = 0.f;
             if (lane < kc) {
                 const int64_t nb = idx[i * k + j0 + lane];
                 wv = w[i * k + j0 + lane];
-                rs = xu_indptr[nb];
+                const int64_t rs = xu_indptr[nb];
                 len = (int)(xu_indptr[nb + 1] - rs);
+                rowp = entries + rs;
             }
-            const int nchunk = warp_sum(lane < kc ? max(1, (len + 31) >> 5) : 0);
-            int pj = 0, pt = 0;                                      // producer cursor: neighbour, offset in its row
-            int64_t prs = __shfl_sync(FULL, rs, 0);
-            int plen = __shfl_sync(FULL, len, 0);
-            float pw = __shfl_sync(FULL, wv, 0);
-            int2 eb[kDsDepth];
-            float wb[kDsDepth];
-            for (int c0 = 0; c0 < nchunk + kDsDepth; c0 += kDsDepth) {
-#pragma unroll
-                for (int d = 0; d < kDsDepth; ++d) {
-                    const int ci = c0 + d;
-                    if (ci >= kDsDepth && ci - kDsDepth < nchunk) {  // consume the chunk loaded kDsDepth steps ago
-                        float* dp = Dw + eb[d].x;
-                        *dp = fmaf(wb[d], __int_as_float(eb[d].y), *dp);
-                        signs |= __float_as_uint(wb[d]) ^ (uint32_t)eb[d].y;
-                        __syncwarp();                                // the next chunk may belong to another row
+            signs |= __float_as_uint(wv);
+            RowBuf<CH> A, B;
+            row_load(A, rowp, len, wv, 0, lane);
+            for (int j = 0; j < kc; j += 2) {
+                if (j + 1 < kc) row_load(B, rowp, len, wv, j + 1, lane);
+                row_accumulate(A, Dw, signs);
+                if (j + 2 < kc) row_load(A, rowp, len, wv, j + 2, lane);
+                if (j + 1 < kc) row_accumulate(B, Dw, signs);
+            }
+            if (__any_sync(FULL, len > 32 * CH)) {                   // rare: rows longer than one pass
+                for (int j = 0; j < kc; ++j) {
+                    const int lj = __shfl_sync(FULL, len, j);
+                    if (lj <= 32 * CH) continue;
+                    const int2* p = reinterpret_cast<const int2*>(__shfl_sync(FULL, (unsigned long long)rowp, j));
+                    const float wj = __shfl_sync(FULL, wv, j);
+                    for (int t = 32 * CH + lane; t < lj; t += 32) {
+                        const int2 e = ld_entry(p + t);
+                        float* dp = Dw + e.x;
+                        *dp = fmaf(wj, __int_as_float(e.y), *dp);
+                        signs |= (uint32_t)e.y;
                     }
-                    if (ci < nchunk) {                               // issue the next chunk
-                        const int t = pt + lane;
-                        eb[d] = t < plen ? ld_entry(entries + prs + t) : make_int2(sink, 0);
-                        wb[d] = pw;
-                        pt += 32;
-                        if (pt >= plen) {
-                            ++pj;
-                            pt = 0;
-                            prs = __shfl_sync(FULL, rs, pj & 31);
-                            plen = __shfl_sync(FULL, len, pj & 31);
-                            pw = __shfl_sync(FULL, wv, pj & 31);
-                        }
-                    }
+                    __syncwarp();
                 }
             }
         }
@@ -169,8 +223,9 @@ diffuse_score_kernel(const int64_t* __restrict__ xu_indptr, const int64_t* __res
         // ---------------- expression flags of the cell itself ----------------
         if (!signed_data) {                                          // D >= 0: the sign bit is free to carry the flag
 #pragma unroll
-            for (int u = 0; u < 4; ++u) Dw[selfcol[u]] = -fabsf(Dw[selfcol[u]]);
-            for (int t = 128 + lane; t < self_len; t += 32) { float* dp = Dw + ld_entry(entries + self_s + t).x; *dp = -fabsf(*dp); }
+            for (int c = 0; c < CH; ++c)
+                if (lane + 32 * c < self_len) Dw[selfcol[c]] = -fabsf(Dw[selfcol[c]]);
+            for (int t = 32 * CH + lane; t < self_len; t += 32) { float* dp = Dw + ld_entry(entries + self_s + t).x; *dp = -fabsf(*dp); }
         } else {
             for (int t = lane * 4; t < L.bw_words; t += 128) *reinterpret_cast<uint4*>(Bw + t) = make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
@@ -182,40 +237,40 @@ diffuse_score_kernel(const int64_t* __restrict__ xu_indptr, const int64_t* __res
         __syncwarp();
 
         // ---------------- phase 2: S[p] = D[l] * D[r] * (flag_l | flag_r) ----------------
+        // lane owns 4 consecutive pairs of every 128: the warp stores 512 contiguous bytes per step
         float* srow = S + i * ldS;
         int cnt = 0;
-        if (!signed_data) {
-            for (int p0 = lane * 4; p0 < (int)ldS; p0 += 128) {
-                const uint4 pr4 = *reinterpret_cast<const uint4*>(pairs_s + p0);
-                const uint32_t pr[4] = {pr4.x, pr4.y, pr4.z, pr4.w};
-                float v[4];
+        if (PPL) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float a = Dw[pr[u] & 0xffffu], b = Dw[pr[u] >> 16];
-                    const bool m = (int)(__float_as_uint(a) | __float_as_uint(b)) < 0;
-                    v[u] = m ? fabsf(a * b) : 0.f;
-                    cnt += v[u] != 0.f;
+            for (int g = 0; g < PPL / 4; ++g) {
+                float v[4];
+                if (!signed_data) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = lr_score1<false>(Dw, Bw, pr[4 * g + u], cnt);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = lr_score1<true>(Dw, Bw, pr[4 * g + u], cnt);
                 }
-                st_stream_f4(reinterpret_cast<float4*>(srow + p0), make_float4(v[0], v[1], v[2], v[3]));
+                const int p0 = 128 * g + 4 * lane;
+                if (p0 < (int)ldS) st_stream_f4(reinterpret_cast<float4*>(srow + p0), make_float4(v[0], v[1], v[2], v[3]));
             }
         } else {
             for (int p0 = lane * 4; p0 < (int)ldS; p0 += 128) {
                 const uint4 pr4 = *reinterpret_cast<const uint4*>(pairs_s + p0);
-                const uint32_t pr[4] = {pr4.x, pr4.y, pr4.z, pr4.w};
+                const uint32_t q4[4] = {pr4.x, pr4.y, pr4.z, pr4.w};
                 float v[4];
+                if (!signed_data) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t l = pr[u] & 0xffffu, r = pr[u] >> 16;
-                    const uint32_t m = ((Bw[l >> 5] >> (l & 31)) | (Bw[r >> 5] >> (r & 31))) & 1u;
-                    const float prod = Dw[l] * Dw[r];
-                    v[u] = m ? prod : 0.f;
-                    cnt += v[u] != 0.f;
+                    for (int u = 0; u < 4; ++u) v[u] = lr_score1<false>(Dw, Bw, q4[u], cnt);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) v[u] = lr_score1<true>(Dw, Bw, q4[u], cnt);
                 }
                 st_stream_f4(reinterpret_cast<float4*>(srow + p0), make_float4(v[0], v[1], v[2], v[3]));
             }
         }
         if (row_nnz) {
-            cnt = warp_sum(cnt);
+            cnt = __reduce_add_sync(FULL, cnt);
             if (lane == 0) row_nnz[i] = cnt;
         }
         __syncwarp();                                                // D is re-zeroed for the next cell
@@ -293,20 +348,28 @@ extern "C" int laris_diffuse_lr_score(const int64_t* xu_indptr, const int64_t* x
     LARIS_CHECK_ARG(G_u >= 1 && G_u <= 65533, "laris_diffuse_lr_score: G_u must be in [1, 65533] (got %d)", G_u);
     LARIS_CHECK_ARG(ldS >= P && ldS % 4 == 0 && ((uintptr_t)S & 15) == 0,
                     "laris_diffuse_lr_score: S needs ldS >= P, ldS %% 4 == 0 and 16-byte alignment");
-    // pack the pair table once: lig | rec << 16, padded with the zero "dummy gene" G_u
-    const int p_words = (int)((ldS + 7) / 8) * 8;
+    // pack the pair table once: lig | rec << 16, padded to whole 128-pair groups with the zero "dummy gene" G_u
+    const int p_words = (int)((ldS + 127) / 128) * 128;
     Scratch<uint32_t> pairs(st);
     LARIS_CUDA(pairs.alloc((size_t)p_words));
     pack_pairs_kernel<<<(unsigned)ceil_div(p_words, 256), 256, 0, st>>>(lig, rec, P, G_u, p_words, pairs.p);
     LARIS_LAUNCH_CHECK();
-    // 8 warps per CTA, each with a private D slab; persistent grid = SMs x resident CTAs
+    // 8 warps per CTA, each with a private D slab; persistent grid = SMs x resident CTAs.
+    // CH: entry chunks per row pass; large gene panels have longer rows.
     constexpr int NT = 256;
-    const DsLayout L(G_u, p_words, NT / 32);
+    const int ppl = 0;   // register-resident pair tables cost too many registers next to the row pipeline
+    const int ch = G_u > 1024 ? 8 : 4;
+    const DsLayout L(G_u, ppl ? 0 : p_words, NT / 32);
     if (L.total + 1024 > (size_t)227 * 1024) {
         set_error("laris_diffuse_lr_score: G_u=%d, P=%d do not fit shared memory (limit ~6500 columns)", G_u, P);
         return LARIS_E_LIMIT;
     }
-    auto kern = diffuse_score_kernel<NT>;
+    using Kern = void (*)(const int64_t*, const int64_t*, int64_t, int, const int32_t*, const float*, int, const int32_t*,
+                          const uint32_t*, int, float*, int64_t, int64_t*);
+    Kern kern = nullptr;
+#define DS_PICK(CH_, PPL_) if (ch == CH_ && ppl == PPL_) kern = diffuse_score_kernel<NT, CH_, PPL_>;
+    DS_PICK(4, 0) DS_PICK(8, 0)
+#undef DS_PICK
     LARIS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     int occ = 1;
     LARIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, L.total));

@@ -120,6 +120,39 @@ __global__ void gather_sorted_kernel(const double* __restrict__ xy, int64_t n, i
     sorted_cell[q] = cell_of[i];
 }
 
+// ------------------------------------------------------ processing order --
+// The order handed to the downstream gather kernels walks the grid in horizontal strips of
+// kStripH cells, column by column, boustrophedon in both directions: consecutive cells are
+// spatial neighbours and the set of "recently visited" cells is a compact patch, so a kernel
+// that lets one SM walk a contiguous range of the order finds most neighbour rows in its L1.
+constexpr int kStripH = 8;
+
+__device__ __forceinline__ int64_t strip_slot(int c, const GridSpec& gs) {
+    const int gx = gs.g[0], gy = gs.g[1];
+    const int cx = c % gx, cy = (c / gx) % gy, cz = c / (gx * gy);
+    const int s = cy / kStripH, yl = cy - s * kStripH;
+    const int xi = (s & 1) ? gx - 1 - cx : cx;
+    const int yi = (xi & 1) ? kStripH - 1 - yl : yl;
+    const int64_t nstrip = (gy + kStripH - 1) / kStripH;
+    return ((int64_t)cz * nstrip + s) * ((int64_t)kStripH * gx) + (int64_t)xi * kStripH + yi;
+}
+
+__global__ void strip_count_kernel(const int32_t* __restrict__ cell_start, int64_t ncell, GridSpec gs,
+                                   int32_t* __restrict__ slot_count) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    slot_count[strip_slot((int)c, gs)] = cell_start[c + 1] - cell_start[c];
+}
+
+__global__ void strip_order_kernel(const int32_t* __restrict__ cell_start, const int32_t* __restrict__ sorted_id,
+                                   const int32_t* __restrict__ sorted_cell, int64_t n, GridSpec gs,
+                                   const int32_t* __restrict__ slot_start, int32_t* __restrict__ order) {
+    int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int c = sorted_cell[q];
+    order[slot_start[strip_slot(c, gs)] + (int)(q - cell_start[c])] = sorted_id[q];
+}
+
 // ---------------------------------------------------------------- search --
 template <int KMAX>
 struct TopK {
@@ -351,8 +384,20 @@ extern "C" int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int 
     }
 #undef LARIS_KNN_LAUNCH
     LARIS_LAUNCH_CHECK();
-    if (out_order)
-        LARIS_CUDA(cudaMemcpyAsync(out_order, sorted_id.p, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    if (out_order) {                                   // cell segments re-dealt in strip order
+        const int64_t nstrip = ceil_div(gs.g[1], kStripH);
+        const int64_t nslot = (int64_t)gs.g[2] * nstrip * kStripH * gs.g[0];
+        Scratch<int32_t> slot_count(st), slot_start(st);
+        LARIS_CUDA(slot_count.alloc(nslot));
+        LARIS_CUDA(slot_start.alloc(nslot + 1));
+        LARIS_CUDA(cudaMemsetAsync(slot_count.p, 0, nslot * sizeof(int32_t), st));
+        strip_count_kernel<<<gc, T, 0, st>>>(cell_start.p, ncell, gs, slot_count.p);
+        LARIS_LAUNCH_CHECK();
+        rc = exclusive_scan<int32_t>(slot_count.p, nslot, slot_start.p, st);
+        if (rc) return rc;
+        strip_order_kernel<<<gn, T, 0, st>>>(cell_start.p, sorted_id.p, sorted_cell.p, n, gs, slot_start.p, out_order);
+        LARIS_LAUNCH_CHECK();
+    }
     return LARIS_OK;
 }
 

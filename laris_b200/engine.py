@@ -57,12 +57,16 @@ def build_graph(xy, k, include_self, sigma=None) -> SpatialGraph:
 # ----------------------------------------------------------- expression ----
 @dataclass
 class ExpressionU:
-    indptr: torch.Tensor   # [n+1] int64
-    packed: torch.Tensor   # [nnz] int64 {col:int32, val:fp32}
+    """Expression restricted to the LR genes, in one of the two device layouts of K2+K3:
+    packed sparse rows (``indptr``/``packed``) or dense fp32 rows (``dense``/``neg_flag``)."""
+    indptr: torch.Tensor | None   # [n+1] int64
+    packed: torch.Tensor | None   # [nnz] int64 {col:int32, val:fp32}
     genes: np.ndarray      # [n_genes] global gene column of each selected gene
     n: int
     columns: np.ndarray | None = None   # [n_genes] packed column of each selected gene (None: 0..n_genes-1)
     n_columns: int | None = None
+    dense: torch.Tensor | None = None     # [n, ldX] fp32
+    neg_flag: torch.Tensor | None = None  # [1] int32: a negative value was seen
 
     @property
     def G_u(self):
@@ -81,7 +85,21 @@ def upload_csr(X):
     return (K.to_device(X.indptr, torch.int64), K.to_device(X.indices, torch.int32), K.to_device(X.data, torch.float32))
 
 
-def select_genes(X, genes, csr_dev=None, columns=None, n_columns=None) -> ExpressionU:
+DENSE_PANEL_MIN_DENSITY = 0.15     # below this the packed sparse rows are the faster layout (measured, profiles/)
+
+
+def choose_layout(X, layout="auto"):
+    """'dense' or 'sparse' device layout of the LR-gene expression for K2+K3.  The fraction of
+    non-zeros of the whole matrix stands in for that of the LR genes (no pass over the data)."""
+    if layout in ("dense", "sparse"):
+        return layout
+    if layout != "auto":
+        raise ValueError(f"layout must be 'auto', 'dense' or 'sparse', got {layout!r}")
+    n, G = X.shape
+    return "dense" if X.nnz >= DENSE_PANEL_MIN_DENSITY * float(n) * float(G) else "sparse"
+
+
+def select_genes(X, genes, csr_dev=None, columns=None, n_columns=None, layout="sparse") -> ExpressionU:
     """Restrict X (n x G CSR) to ``genes`` (unique global columns) on the device.
     ``columns`` optionally gives the packed column of each gene (see ``lr_column_layout``)."""
     n, G = X.shape
@@ -89,9 +107,13 @@ def select_genes(X, genes, csr_dev=None, columns=None, n_columns=None) -> Expres
     gene_map = np.full(G, -1, dtype=np.int32)
     gene_map[genes] = np.arange(len(genes), dtype=np.int32) if columns is None else np.asarray(columns, dtype=np.int32)
     indptr, indices, data = csr_dev if csr_dev is not None else upload_csr(X)
+    cols = None if columns is None else np.asarray(columns, dtype=np.int32)
+    if layout == "dense":
+        ncol = len(genes) if n_columns is None else int(n_columns)
+        Xd, neg = K.csr_select_dense(indptr, indices, data, K.to_device(gene_map, torch.int32), ncol)
+        return ExpressionU(None, None, genes, n, cols, n_columns, Xd, neg)
     out_indptr, packed = K.csr_select(indptr, indices, data, K.to_device(gene_map, torch.int32))
-    return ExpressionU(out_indptr, packed, genes, n, None if columns is None else np.asarray(columns, dtype=np.int32),
-                       n_columns)
+    return ExpressionU(out_indptr, packed, genes, n, cols, n_columns)
 
 
 def lr_column_layout(lig_u, rec_u, n_genes):
@@ -102,15 +124,64 @@ def lr_column_layout(lig_u, rec_u, n_genes):
     return K.lr_column_layout(lig_u, rec_u, int(n_genes))
 
 
-def select_lr_genes(X, lig_g, rec_g, csr_dev=None):
-    """Gene selection for an LR table given as global gene columns.
-    Returns (ExpressionU, ligand packed columns [P], receptor packed columns [P])."""
+@dataclass
+class LRPlan:
+    """Everything about an LR table that does not depend on the cells: the distinct genes, their
+    packed (bank-conflict-free) columns and the per-pair column indices, already on the device."""
+    genes: np.ndarray
+    columns: np.ndarray
+    n_columns: int
+    lig_c: np.ndarray
+    rec_c: np.ndarray
+    gene_map_d: torch.Tensor
+    lig_d: torch.Tensor
+    rec_d: torch.Tensor
+
+
+_PLAN_CACHE: dict = {}
+
+
+def plan_lr_table(lig_g, rec_g, G) -> LRPlan:
+    """Plan of an LR table (cached: the same table is usually scored on many samples)."""
+    lig_g = np.ascontiguousarray(lig_g, dtype=np.int64)
+    rec_g = np.ascontiguousarray(rec_g, dtype=np.int64)
+    key = (int(G), torch.cuda.current_device(), hash(lig_g.tobytes()), hash(rec_g.tobytes()), len(lig_g))
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        if len(_PLAN_CACHE) >= 8:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+        plan = _PLAN_CACHE[key] = _plan_lr_table(lig_g, rec_g, G)
+    return plan
+
+
+def _plan_lr_table(lig_g, rec_g, G) -> LRPlan:
     P = len(lig_g)
     genes, inv = np.unique(np.concatenate([np.asarray(lig_g), np.asarray(rec_g)]), return_inverse=True)
     lig_u, rec_u = inv[:P].astype(np.int32), inv[P:].astype(np.int32)
     columns, n_columns = lr_column_layout(lig_u, rec_u, len(genes))
-    xu = select_genes(X, genes, csr_dev=csr_dev, columns=columns, n_columns=n_columns)
-    return xu, columns[lig_u], columns[rec_u]
+    gene_map = np.full(G, -1, dtype=np.int32)
+    gene_map[genes] = columns
+    lig_c, rec_c = columns[lig_u], columns[rec_u]
+    return LRPlan(genes, columns, n_columns, lig_c, rec_c, K.to_device(gene_map, torch.int32),
+                  K.to_device(lig_c.astype(np.int32), torch.int32), K.to_device(rec_c.astype(np.int32), torch.int32))
+
+
+def select_planned(plan: LRPlan, csr_dev, n, layout) -> ExpressionU:
+    """Device-only gene selection for a planned LR table (no host work, no host sync in the dense layout)."""
+    indptr, indices, data = csr_dev
+    if layout == "dense":
+        Xd, neg = K.csr_select_dense(indptr, indices, data, plan.gene_map_d, plan.n_columns)
+        return ExpressionU(None, None, plan.genes, n, plan.columns, plan.n_columns, Xd, neg)
+    out_indptr, packed = K.csr_select(indptr, indices, data, plan.gene_map_d)
+    return ExpressionU(out_indptr, packed, plan.genes, n, plan.columns, plan.n_columns)
+
+
+def select_lr_genes(X, lig_g, rec_g, csr_dev=None, layout="auto"):
+    """Gene selection for an LR table given as global gene columns.
+    Returns (ExpressionU, ligand packed columns [P], receptor packed columns [P]) - the columns as device tensors."""
+    plan = plan_lr_table(lig_g, rec_g, X.shape[1])
+    xu = select_planned(plan, csr_dev if csr_dev is not None else upload_csr(X), X.shape[0], choose_layout(X, layout))
+    return xu, plan.lig_d, plan.rec_d
 
 
 # --------------------------------------------------------------- scores ----
@@ -128,9 +199,12 @@ class ScoreMatrix:
 
 def lr_scores(xu: ExpressionU, graph: SpatialGraph, lig_u, rec_u) -> ScoreMatrix:
     """Fused diffusion + LR score (K2+K3)."""
-    lig_d = K.to_device(np.asarray(lig_u, dtype=np.int32), torch.int32)
-    rec_d = K.to_device(np.asarray(rec_u, dtype=np.int32), torch.int32)
-    S, row_nnz = K.diffuse_lr_score(xu.indptr, xu.packed, xu.G_u, graph.idx, graph.w, graph.order, lig_d, rec_d)
+    lig_d = lig_u if torch.is_tensor(lig_u) else K.to_device(np.asarray(lig_u, dtype=np.int32), torch.int32)
+    rec_d = rec_u if torch.is_tensor(rec_u) else K.to_device(np.asarray(rec_u, dtype=np.int32), torch.int32)
+    if xu.dense is not None:
+        S, row_nnz = K.diffuse_lr_score_dense(xu.dense, xu.neg_flag, xu.G_u, graph.idx, graph.w, graph.order, lig_d, rec_d)
+    else:
+        S, row_nnz = K.diffuse_lr_score(xu.indptr, xu.packed, xu.G_u, graph.idx, graph.w, graph.order, lig_d, rec_d)
     return ScoreMatrix(S, len(lig_u), row_nnz)
 
 

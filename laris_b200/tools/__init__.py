@@ -29,7 +29,7 @@ def _lr_gene_indices(adata, lr_df):
 
 
 def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_rep_spatial: str = "X_spatial", *,
-                         dtype=np.float32):
+                         dtype=np.float32, layout: str = "auto"):
     """Per-cell diffused ligand-receptor scores as a new AnnData (cells x LR pairs).
 
     Reference laris/tools/__init__.py:29-119: kNN graph incl. self with
@@ -37,12 +37,14 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     expressing the ligand or the receptor.  Returns a new AnnData with ``.X`` the
     sparse n x P score matrix (exact zeros pruned), ``obs``/``obsm`` copied and
     ``var_names`` = "ligand::receptor".  The dense scores stay resident on the GPU
-    for a following ``runLARIS`` call.
+    for a following ``runLARIS`` call.  ``layout`` picks the device layout of the LR-gene
+    expression ('dense' rows, packed 'sparse' rows, or 'auto' by the fraction of non-zeros);
+    both give the same result.
     """
     xy = _utils._coords(adata, use_rep_spatial)
     lig_g, rec_g = _lr_gene_indices(adata, lr_df)
     graph = engine.build_graph(xy, number_nearest_neighbors, True, None)
-    xu, lig_c, rec_c = engine.select_lr_genes(adata.X, lig_g, rec_g)
+    xu, lig_c, rec_c = engine.select_lr_genes(adata.X, lig_g, rec_g, layout=layout)
     sm = engine.lr_scores(xu, graph, lig_c, rec_c)
     X = engine.scores_to_csr(sm, dtype)
     lr_names = (lr_df["ligand"].astype(str) + "::" + lr_df["receptor"].astype(str)).to_numpy(dtype=object)

@@ -118,10 +118,13 @@ def test_exclusive_scan(dev, n):
 
 
 # --------------------------------------------------------------- K2+K3 ----
-def _prepare_both(a, lr, k):
+LAYOUTS = ("dense", "sparse")
+
+
+def _prepare_both(a, lr, k, layout="auto"):
     import laris_b200 as la
     from oracle import restate as R
-    out = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=k)
+    out = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=k, layout=layout)
     li = R.gene_index(a.var_names, lr["ligand"])
     ri = R.gene_index(a.var_names, lr["receptor"])
     ind, dist = R.knn_graph(a.obsm["X_spatial"], k, True)
@@ -138,10 +141,11 @@ def _assert_csr_equal(X, S):
     assert np.allclose(X.data, S.data, rtol=RTOL, atol=0)
 
 
-def test_prepare_matches_reference_fixture(dev, golden, tiny):
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_prepare_matches_reference_fixture(dev, golden, tiny, layout):
     import laris_b200 as la
     a, lr, _ = tiny
-    out = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=8)
+    out = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=8, layout=layout)
     X = sp.csr_matrix(out.X)
     X.sort_indices()
     assert np.array_equal(X.indptr, golden["S_indptr"]) and np.array_equal(X.indices, golden["S_indices"])
@@ -154,15 +158,43 @@ def test_prepare_matches_reference_fixture(dev, golden, tiny):
 @pytest.mark.parametrize("cfg,n,over", [
     (1, 10000, {}),                                              # BASELINE configs[0], full size
     (2, 20000, {}),
-    (3, 6000, dict(G=2500, G_u=1500, P=1001)),                   # TC=16 tile, P not a multiple of 8
-    (3, 3000, dict(G=4000, G_u=3500, P=300)),                    # TC=8 tile
-    (1, 777, dict(G=64, G_u=40, P=7)),                           # ragged tile tail, tiny P
+    (3, 6000, dict(G=2500, G_u=1500, P=1001)),                   # several column passes, P not a multiple of 8, smem pair table
+    (3, 3000, dict(G=4000, G_u=3500, P=300)),                    # wide panel
+    (1, 777, dict(G=64, G_u=40, P=7)),                           # ragged group tail, tiny P
+    (2, 5001, dict(G=300, G_u=200, P=130)),                      # two 128-pair groups in registers
 ])
-def test_prepare_vs_oracle(dev, cfg, n, over):
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_prepare_vs_oracle(dev, cfg, n, over, layout):
     from laris_b200.synth import make_dataset
     a, lr, c = make_dataset(cfg, n=n, **over)
-    _, X, S = _prepare_both(a, lr, c.k)
+    _, X, S = _prepare_both(a, lr, c.k, layout)
     _assert_csr_equal(X, S)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_prepare_signed_expression(dev, layout):
+    """Centred (negative) expression values: the expression flag cannot ride in the sign bit."""
+    from laris_b200.synth import make_dataset
+    a, lr, c = make_dataset(1, n=3000, G=200, G_u=150, P=90)
+    X = a.X.tocsr().astype(np.float32)
+    X.data -= 0.7
+    a.X = X
+    _, Xg, S = _prepare_both(a, lr, c.k, layout)
+    assert (S.data < 0).any()
+    assert Xg.shape == S.shape and np.array_equal(Xg.indptr, S.indptr) and np.array_equal(Xg.indices, S.indices)
+    # products of cancelling sums: compare on the scale of the row, not per element
+    assert np.allclose(Xg.data, S.data, rtol=1e-4, atol=1e-5 * np.abs(S.data).max())
+
+
+def test_prepare_auto_layout(dev):
+    from laris_b200 import engine
+    from laris_b200.synth import make_dataset
+    a, _, _ = make_dataset(2, n=2000)
+    assert engine.choose_layout(a.X) == "dense"
+    thin = sp.random(2000, 500, density=0.01, format="csr", dtype=np.float32, random_state=1)
+    assert engine.choose_layout(thin) == "sparse"
+    with pytest.raises(ValueError):
+        engine.choose_layout(thin, "blocked")
 
 
 def test_prepare_edge_cases(dev):
@@ -178,10 +210,11 @@ def test_prepare_edge_cases(dev):
     a.X = X
     lr = pd.concat([lr, pd.DataFrame({"ligand": ["g00003", "g00007", lr["ligand"][0]],
                                       "receptor": ["g00004", "g00007", lr["receptor"][0]]})], ignore_index=True)
-    for k in (2, 10, 33):
-        _, Xg, S = _prepare_both(a, lr, k)
-        _assert_csr_equal(Xg, S)
-    assert Xg[5:40].nnz == 0
+    for layout in LAYOUTS:
+        for k in (2, 10, 16, 33, 40):
+            _, Xg, S = _prepare_both(a, lr, k, layout)
+            _assert_csr_equal(Xg, S)
+        assert Xg[5:40].nnz == 0
 
 
 def test_prepare_requires_sparse_and_known_genes(dev, tiny):

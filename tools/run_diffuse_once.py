@@ -18,10 +18,15 @@ cols, ncols = engine.lr_column_layout(inv[:P], inv[P:], len(genes)) if layout el
 gm = np.full(a.shape[1], -1, np.int32); gm[genes] = cols
 gm_d = K.to_device(gm, torch.int32)
 lig = K.to_device(cols[inv[:P]].astype(np.int32), torch.int32); rec = K.to_device(cols[inv[P:]].astype(np.int32), torch.int32)
+dense = os.environ.get("LARIS_DENSE", "1") == "1"
 for _ in range(reps):
     idx, dist, order = K.knn_graph(xy, k, True)
     w32, _, _ = K.decay_weights(dist, None, False)
-    xu_indptr, xu_packed = K.csr_select(*csr, gm_d)
-    S, rn = K.diffuse_lr_score(xu_indptr, xu_packed, ncols, idx, w32, order, lig, rec)
+    if dense:
+        Xd, neg = K.csr_select_dense(*csr, gm_d, ncols)
+        S, rn = K.diffuse_lr_score_dense(Xd, neg, ncols, idx, w32, order, lig, rec)
+    else:
+        xu_indptr, xu_packed = K.csr_select(*csr, gm_d)
+        S, rn = K.diffuse_lr_score(xu_indptr, xu_packed, ncols, idx, w32, order, lig, rec)
 torch.cuda.synchronize()
 print("ok", float(S.sum()))

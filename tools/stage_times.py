@@ -38,6 +38,11 @@ xu_indptr, xu_packed = T("csr_select", lambda: K.csr_select(*csr, gm_d))
 print("  nnz_u =", xu_packed.numel())
 S, row_nnz = T("diffuse_lr_score", lambda: K.diffuse_lr_score(xu_indptr, xu_packed, ncols, idx, w32, order, lig, rec))
 T("diffuse_lr_score(order=None)", lambda: K.diffuse_lr_score(xu_indptr, xu_packed, ncols, idx, w32, None, lig, rec))
+Xd, neg = T("csr_select_dense", lambda: K.csr_select_dense(*csr, gm_d, ncols))
+Sd, rnd = T("diffuse_lr_score_dense", lambda: K.diffuse_lr_score_dense(Xd, neg, ncols, idx, w32, order, lig, rec))
+T("diffuse_lr_score_dense(order=None)", lambda: K.diffuse_lr_score_dense(Xd, neg, ncols, idx, w32, None, lig, rec))
+print("  dense == sparse structure:", bool(((Sd != 0) == (S != 0)).all().item()), " max rel diff:",
+      float(((Sd - S).abs() / S.abs().clamp_min(1e-30)).max().item()), " ldX =", Xd.shape[1])
 T("csr_compact", lambda: K.csr_compact(S, P, row_nnz))
 idx2, dist2, order2 = T("knn_graph(excl self)", lambda: K.knn_graph(xy, k, False))
 w2, _, _ = K.decay_weights(dist2, 100.0)
