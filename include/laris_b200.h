@@ -185,10 +185,14 @@ LARIS_API int laris_neighborhood_composition(const int32_t* labels, const int32_
  *   qnorm2[a*C+b] = sum_i (N[i,a]*N[i,b])^2
  * Replaces _pairwise_row_multiply + sklearn cosine_similarity at
  * laris/tools/_utils.py:859-866.  impl: 0 = tcgen05 tensor-core kernel
- * (split-bf16 operands, fp32 TMEM accumulation), 1 = fp32 CUDA-core kernel.
+ * (fp32 inputs split into bf16 hi/lo, three MMAs per K step, fp32 TMEM accumulation in 256-cell
+ * chunks, fp64 combine; needs 8 <= C <= ~44), 1 = fp32 CUDA-core kernel (any C).
+ *   order [n] int32 or NULL: cell processing order for impl=0 (a spatially coherent order lets the
+ *   operand builder skip the all-zero cell-type blocks); the result does not depend on it beyond
+ *   fp32 summation order.
  *   num [P*C*C] fp64, qnorm2 [C*C] fp64 */
 LARIS_API int laris_celltype_pair_contract(const float* S, int64_t ldS, int64_t n, int32_t P, const float* Ncomp,
-                                 int32_t C, double* num, double* qnorm2, int impl, void* stream);
+                                 int32_t C, const int32_t* order, double* num, double* qnorm2, int impl, void* stream);
 
 /* cnt[c*P + p] = #{i : labels[i]==c and S[i,p] != 0}.  Replaces
  * _compute_avg_expression on the binarised scores (laris/tools/_utils.py:1325-1337,

@@ -207,12 +207,19 @@ def neighborhood_composition(labels, idx, w, C):
     return N
 
 
-def celltype_pair_contract(S, P, N, impl=1):
+MMA_MIN_C, MMA_MAX_C = 1, 64      # cell-type counts the tcgen05 contraction handles (N row = two values per lane)
+
+
+def celltype_pair_contract(S, P, N, impl=None, order=None):
+    """impl: 0 tcgen05 tensor cores, 1 fp32 CUDA cores, None = 0 whenever the number of cell types allows it."""
     n, ld = S.shape
     C = N.shape[1]
+    if impl is None:
+        impl = 0 if MMA_MIN_C <= C <= MMA_MAX_C else 1
     num = torch.empty((P, C * C), dtype=torch.float64, device=S.device)
     qn2 = torch.empty(C * C, dtype=torch.float64, device=S.device)
-    check(lib.laris_celltype_pair_contract(_ptr(S, torch.float32), ld, n, P, _ptr(N, torch.float32), C, _ptr(num),
+    check(lib.laris_celltype_pair_contract(_ptr(S, torch.float32), ld, n, P, _ptr(N, torch.float32), C,
+                                           _ptr(order, torch.int32) if order is not None else None, _ptr(num),
                                            _ptr(qn2), int(impl), _stream()), "laris_celltype_pair_contract")
     return num, qn2
 

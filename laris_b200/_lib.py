@@ -39,7 +39,7 @@ SIGNATURES = {
     "laris_null_graph_philox": [_i64, _i, _p, _i, _u64, _p, _p, _p],
     "laris_gather_f32": [_p, _p, _i64, _p, _p],
     "laris_neighborhood_composition": [_p, _p, _p, _i64, _i, _i, _p, _p],
-    "laris_celltype_pair_contract": [_p, _i64, _i64, _i, _p, _i, _p, _p, _i, _p],
+    "laris_celltype_pair_contract": [_p, _i64, _i64, _i, _p, _i, _p, _p, _p, _i, _p],
     "laris_celltype_nonzero_count": [_p, _i64, _i64, _i, _p, _i, _p, _p],
     "laris_onehot_contract_csr": [_p, _p, _i64, _i, _p, _i, _p, _p, _p, _p],
     "laris_pvalue_counts": [_p, _i64, _i, _i, _p, _i, _p, _p, _i64, _i, _i, _i, _i, _u64, _p, _p, _p, _p, _p],

@@ -205,11 +205,12 @@ extern "C" int laris_onehot_contract_csr(const int64_t* indptr, const int64_t* p
 
 namespace laris {
 int celltype_pair_contract_mma(const float* S, int64_t ldS, int64_t n, int32_t P, const float* Ncomp, int32_t C,
-                               double* num, cudaStream_t st);   // celltype_mma.cu
+                               const int32_t* order, double* num, cudaStream_t st);   // celltype_mma.cu
 }
 
 extern "C" int laris_celltype_pair_contract(const float* S, int64_t ldS, int64_t n, int32_t P, const float* Ncomp,
-                                            int32_t C, double* num, double* qnorm2, int impl, void* stream) {
+                                            int32_t C, const int32_t* order, double* num, double* qnorm2, int impl,
+                                            void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LARIS_CHECK_ARG(S && Ncomp && num && qnorm2 && n > 0 && P >= 1 && C >= 1 && ldS >= P, "laris_celltype_pair_contract: bad arguments");
     LARIS_CHECK_ARG(impl == 0 || impl == 1, "laris_celltype_pair_contract: impl must be 0 (tcgen05) or 1 (fp32 CUDA cores)");
@@ -218,7 +219,7 @@ extern "C" int laris_celltype_pair_contract(const float* S, int64_t ldS, int64_t
     LARIS_CUDA(cudaMemsetAsync(qnorm2, 0, (size_t)CC * sizeof(double), st));
     pair_profile_norm_kernel<<<(unsigned)ceil_div(n, 64), 256, 64 * C * sizeof(float), st>>>(Ncomp, n, C, qnorm2);
     LARIS_LAUNCH_CHECK();
-    if (impl == 0) return celltype_pair_contract_mma(S, ldS, n, P, Ncomp, C, num, st);
+    if (impl == 0) return celltype_pair_contract_mma(S, ldS, n, P, Ncomp, C, order, num, st);
     const int tm = (int)ceil_div(P, kCtTile), tn = (int)ceil_div(CC, kCtTile);
     int64_t splits = ceil_div((int64_t)kNumSMs * 4, (int64_t)tm * tn);
     int64_t per = ceil_div(ceil_div(n, splits), kCtKc) * kCtKc;

@@ -4,20 +4,28 @@
 // GEMM view: D[M = pairs][N = type pairs] = A * B^T with the contraction over cells,
 //   A[p][i] = S[i][p]                 (S is cell-major, so A is "MN-major": p is the contiguous index)
 //   B[(a,b)][i] = N[i][a] * N[i][b]   (built on the fly from the C values of each cell)
-// fp32 inputs are split into bf16 hi + bf16 lo; three tcgen05.mma (lo*hi, hi*lo, hi*hi) accumulate in
-// fp32 in TMEM, which restores ~16 mantissa bits per operand.  Tensor-core accumulation truncates, so a
-// TMEM accumulator only ever sums 256 cells (48 MMAs); the epilogue warps add each such chunk into fp32
+// fp32 inputs are split into bf16 hi + bf16 lo (x = hi + lo to 2^-18 relative); four tcgen05.mma
+// (lo*lo, lo*hi, hi*lo, hi*hi) accumulate in fp32 in TMEM, so a product is exact to 2^-17 relative.
+// Tensor-core accumulation truncates (measured: bias grows linearly with the number of accumulated MMAs), so a
+// TMEM accumulator only ever sums 256 cells (64 MMAs); the epilogue warps add each such chunk into fp32
 // running sums in registers (round-to-nearest), and the K-split partials are combined in fp64.
 //
-// CTA = one 128 x 128 output tile x one range of cells; 16 warps, one CTA per SM:
+// Two kernels:
+//  split_scores_kernel   one pass over S: fp32 -> bf16 hi / lo, written tile by tile in exactly the shared-memory
+//                        operand layout (canonical no-swizzle MN-major: 16-byte slots [cell/8][pair/8][cell%8][8 pairs]),
+//                        cells taken in the spatial processing order when one is given; also gathers the N rows
+//                        in that order.  Cost: S read once, the same number of bytes written.
+//  pair_contract_mma_kernel   CTA = one 128 x 128 output tile x one range of cells; 16 warps, one CTA per SM:
 //   warps 0-7   epilogue: tcgen05.ld the finished TMEM chunk (two accumulator buffers, so the next chunk
 //               is being multiplied meanwhile) and add it to the running sums; at the end write the partial
 //   warp  8     one elected thread issues the MMAs and commits them to mbarriers
-//   warps 9-15  producers: read S (fp32, 32-byte pieces of 8 cell rows per quarter-warp) and N, split,
-//               and store the bf16 operand tiles of a 64-cell stage in the canonical no-swizzle
-//               MN-major layout (16-byte slots, conflict-free), then fence.proxy.async + mbarrier arrive
-// Shared memory: 2 operand stages (A_hi, A_lo, B_hi, B_lo, 16 KB each), 2 raw fp32 S tiles and 3 raw N blocks
-// in flight by cp.async.
+//   warps 9-15  producers: one thread issues the two 16 KB bulk copies (cp.async.bulk -> mbarrier complete_tx)
+//               that bring the stage's A_hi / A_lo tiles straight into their operand slots; all of them build
+//               B = N[i,a]*N[i,b] (split hi/lo) for the stage's 64 cells from the N rows (cp.async, one stage
+//               ahead).  N is mostly zeros (a neighbourhood holds few cell types), so a unit whose N[i,a] is
+//               zero is stored as zeros without touching the b side; with spatially ordered cells whole warps
+//               take that path.  Then fence.proxy.async + mbarrier arrive.
+// Shared memory: 3 operand stages (A_hi, A_lo, B_hi, B_lo, 16 KB each) and 2 raw N blocks in flight.
 #include "common.cuh"
 
 #include <cuda_bf16.h>
@@ -90,18 +98,36 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-constexpr int RAW_A_BYTES = SK * TM * 4;               // fp32 S tile of a stage as it arrives by cp.async (32 KB)
-constexpr int RAW_A_SLOTS = 2, RAW_N_SLOTS = 3;
+constexpr uint32_t A_TX_BYTES = 2 * OPER_BYTES;
+
+constexpr int LIST_CAP = 384;                          // non-zero B elements a warp remembers per stage buffer
+constexpr int CELLS_PER_WARP = (SK + N_PROD - 1) / N_PROD;      // 10
+constexpr int MAX_C = 64;                              // N row of a cell = two values per lane
 
 struct Smem {
-    // dynamic layout (1024-byte aligned): [nstages][STAGE_BYTES] bf16 operand tiles, [2][RAW_A_BYTES] fp32 S tiles in
-    // flight, [3][SK*C] fp32 N rows in flight, the (a,b) table of the tile's 128 columns, barriers, TMEM base address
-    static __host__ __device__ size_t n_slot_bytes(int C) { return ((size_t)SK * C * 4 + 15) & ~(size_t)15; }
-    static __host__ __device__ size_t bytes(int nstages, int C) {
-        return (size_t)nstages * STAGE_BYTES + (size_t)RAW_A_SLOTS * RAW_A_BYTES + RAW_N_SLOTS * n_slot_bytes(C) + TN * 2 +
-               16 * 8 + 16 + 1024;
+    // dynamic layout (1024-byte aligned): [nstages][STAGE_BYTES] bf16 operand tiles, [nstages][N_PROD][LIST_CAP] u16
+    // offsets of the non-zero B elements each producer warp wrote into each stage buffer, control words, barriers
+    static __host__ __device__ size_t bytes(int nstages) {
+        return (size_t)nstages * STAGE_BYTES + (size_t)nstages * N_PROD * LIST_CAP * 2 + 256 + 16 * 8 + 1024;
     }
 };
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {      // long waits: do not burn issue slots
+    uint32_t ok;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(128);
+    }
+}
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -110,19 +136,111 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// S (fp32, cell-major) -> A_hi / A_lo tiles in operand layout: block (sg, tm) = cells [64 sg, 64 sg + 64) of the
+// processing order x pairs [128 tm, 128 tm + 128), hi tile then lo tile, 16 KB each.  One thread per 16-byte slot.
+__global__ void __launch_bounds__(256)
+split_scores_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, int P, const int32_t* __restrict__ order,
+                    int tiles_m, unsigned char* __restrict__ Asplit) {
+    const int64_t blk = blockIdx.x >> 2;                             // 4 CTAs of 256 slots per tile
+    const int u = ((blockIdx.x & 3) << 8) + threadIdx.x;
+    const int64_t sg = blk / tiles_m;
+    const int tm = (int)(blk - sg * tiles_m);
+    const int r = u & 7, g = (u >> 3) & 15, kg = u >> 7;
+    const int64_t q = sg * SK + kg * 8 + r;
+    const int pc = tm * TM + 8 * g;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = 0.f;
+    if (q < n) {
+        const int64_t i = order ? (int64_t)order[q] : q;
+        const float* row = S + i * ldS + pc;
+        if (pc + 8 <= ldS) {                                          // columns [P, ldS) hold zeros
+            const float4 v0 = ld_stream_f4(reinterpret_cast<const float4*>(row));
+            const float4 v1 = ld_stream_f4(reinterpret_cast<const float4*>(row + 4));
+            x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (pc + j < P) x[j] = row[j];
+        }
+    }
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    unsigned char* dst = Asplit + blk * (int64_t)(2 * OPER_BYTES) + 16 * u;
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + OPER_BYTES) = lo;
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ N, int64_t n, int C, const int32_t* __restrict__ order,
+                                   float* __restrict__ out) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n * C) return;
+    const int64_t q = e / C;
+    out[e] = N[(int64_t)order[q] * C + (e - q * C)];
+}
+
+// which cell types occur (N != 0) in each 64-cell stage: one warp per stage, 64-bit mask
+__global__ void stage_type_mask_kernel(const float* __restrict__ N, int64_t n, int C, int64_t nsg,
+                                       unsigned long long* __restrict__ mask) {
+    const int lane = threadIdx.x & 31;
+    const int64_t sg = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (sg >= nsg) return;
+    unsigned long long m = 0ull;
+    for (int r = lane; r < SK; r += 32) {
+        const int64_t i = sg * SK + r;
+        if (i >= n) break;
+        const float* row = N + i * C;
+        for (int a = 0; a < C; ++a)
+            if (row[a] != 0.f) m |= 1ull << a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+    if (lane == 0) mask[sg] = m;
+}
+
+// per column tile: the ascending list of stages in which one of the tile's cell types a occurs (a superset of the
+// stages with a non-zero B tile; the others contribute nothing and are never visited).  One CTA per tile.
+__global__ void __launch_bounds__(1024)
+active_stage_list_kernel(const unsigned long long* __restrict__ mask, int64_t nsg, int C, int32_t* __restrict__ list /*[tiles_n][nsg]*/,
+                         int32_t* __restrict__ count /*[tiles_n]*/) {
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t running;
+    const int tn = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int a_lo = tn * TN / C, a_hi = min(C - 1, (tn * TN + TN - 1) / C);
+    unsigned long long am = 0ull;
+    for (int a = a_lo; a <= a_hi; ++a) am |= 1ull << a;
+    if (tid == 0) running = 0;
+    __syncthreads();
+    int32_t* out = list + (int64_t)tn * nsg;
+    for (int64_t s0 = 0; s0 < nsg; s0 += 1024) {
+        const int64_t sg = s0 + tid;
+        const bool act = sg < nsg && (mask[sg] & am) != 0ull;
+        const unsigned bm = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) warp_tot[w] = __popc(bm);
+        __syncthreads();
+        int32_t before = running;
+        for (int q = 0; q < w; ++q) before += warp_tot[q];
+        if (act) out[before + __popc(bm & ((1u << lane) - 1u))] = (int32_t)sg;
+        __syncthreads();
+        if (tid == 0) { int32_t t = 0; for (int q = 0; q < 32; ++q) t += warp_tot[q]; running += t; }
+        __syncthreads();
+    }
+    if (tid == 0) count[tn] = running;
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
-pair_contract_mma_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, int P, const float* __restrict__ Ncomp, int C,
-                         int tiles_n, int tiles_mn, int64_t cells_per_split, int nstages,
-                         float* __restrict__ partial /*[splits][P][C*C]*/) {
+pair_contract_mma_kernel(const unsigned char* __restrict__ Asplit, int tiles_m, int64_t n, int P,
+                         const float* __restrict__ Ncomp, int C, int tiles_n, int tiles_mn, int splits,
+                         const int32_t* __restrict__ alist, const int32_t* __restrict__ acount, int64_t nsg,
+                         int nstages, float* __restrict__ partial /*[splits][P][C*C]*/) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     const int CC = C * C;
-    unsigned char* rawA = base + (size_t)nstages * STAGE_BYTES;
-    unsigned char* rawN = rawA + (size_t)RAW_A_SLOTS * RAW_A_BYTES;
-    const size_t n_slot = Smem::n_slot_bytes(C);
-    uint16_t* ab_s = reinterpret_cast<uint16_t*>(rawN + RAW_N_SLOTS * n_slot);
-    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(ab_s + TN) + 7) & ~(uintptr_t)7);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint16_t* blist = reinterpret_cast<uint16_t*>(base + (size_t)nstages * STAGE_BYTES);   // [nstages][N_PROD][LIST_CAP]
+    // control words: [4..7] non-zero count of the stage being built, [8..11] stage-skip flag, [12..13]
+    // accumulator-holds-data flag, [14] TMEM base address, [16 + 8*stage + warp] per-warp list lengths
+    uint32_t* ctrl = reinterpret_cast<uint32_t*>(blist + (size_t)nstages * N_PROD * LIST_CAP);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ctrl + 64);
+    uint32_t* tmem_slot = ctrl + 14;
     // barriers: full[0..3], empty[4..7], acc_full[8..9], acc_empty[10..11]
     const uint32_t bar0 = smem_u32(bars);
     auto BAR = [&](int i) { return bar0 + 8u * i; };
@@ -131,17 +249,20 @@ pair_contract_mma_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, in
     const int tile = blockIdx.x % tiles_mn, split = blockIdx.x / tiles_mn;
     const int tn = tile % tiles_n, tm = tile / tiles_n;
     const int p0 = tm * TM, n0 = tn * TN;
-    const int64_t i_beg = (int64_t)split * cells_per_split;
-    const int64_t i_end = min(n, i_beg + cells_per_split);
-    const int nst = (int)((i_end - i_beg + SK - 1) / SK);
+    // this CTA's share of the tile's active stages
+    const int n_act = acount[tn];
+    const int s_lo = (int)((int64_t)n_act * split / splits), s_hi = (int)((int64_t)n_act * (split + 1) / splits);
+    const int32_t* my_stages = alist + (int64_t)tn * nsg + s_lo;
+    const int nst = s_hi - s_lo;
     const int nchunk = (nst + FLUSH_STAGES - 1) / FLUSH_STAGES;
 
-    for (int c = tid; c < TN; c += THREADS) {
-        const int ab = n0 + c;
-        ab_s[c] = ab < CC ? (uint16_t)((ab / C) | ((ab % C) << 8)) : (uint16_t)0xffffu;
-    }
+    if (tid < 64) ctrl[tid] = 0u;
+    for (int q = tid; q < nstages * (2 * OPER_BYTES / 16); q += THREADS)        // B tiles start as zeros
+        *reinterpret_cast<uint4*>(base + (size_t)(q / (2 * OPER_BYTES / 16)) * STAGE_BYTES + 2 * OPER_BYTES +
+                                  16 * (q % (2 * OPER_BYTES / 16))) = make_uint4(0u, 0u, 0u, 0u);
+    fence_async_smem();
     if (tid == 0) {
-        for (int s = 0; s < nstages; ++s) { mbar_init(BAR(s), N_PROD); mbar_init(BAR(4 + s), 1); }
+        for (int s = 0; s < nstages; ++s) { mbar_init(BAR(s), N_PROD + 1); mbar_init(BAR(4 + s), 1); }
         mbar_init(BAR(8), 1); mbar_init(BAR(9), 1);
         mbar_init(BAR(10), N_EPI); mbar_init(BAR(11), N_EPI);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -163,10 +284,12 @@ pair_contract_mma_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, in
         for (int j = 0; j < 64; ++j) sums[j] = 0.f;
         for (int c = 0; c < nchunk; ++c) {
             const int acc = c & 1;
-            mbar_wait(BAR(8 + acc), (uint32_t)((c >> 1) & 1));
+            mbar_wait_sleep(BAR(8 + acc), (uint32_t)((c >> 1) & 1));
             tc_fence_after();
+            const bool has_data = *reinterpret_cast<volatile uint32_t*>(ctrl + 12 + acc) != 0u;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
+                if (!has_data) break;                                // every stage of this chunk was skipped
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(acc * TN + 64 * half + 32 * h);
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -195,97 +318,154 @@ pair_contract_mma_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, in
     } else if (warp == N_EPI) {
         // ================= MMA issuer: one elected thread =================
         if (lane == 0) {
+            bool chunk_data = false;
             for (int s = 0; s < nst; ++s) {
                 const int stage = s % nstages;
                 const uint32_t ph = (uint32_t)((s / nstages) & 1);
                 const int c = s / FLUSH_STAGES, acc = c & 1;
-                const bool first = (s % FLUSH_STAGES) == 0;
-                if (first) { mbar_wait(BAR(10 + acc), (uint32_t)(((c >> 1) & 1) ^ 1)); tc_fence_after(); }
+                if ((s % FLUSH_STAGES) == 0) {
+                    mbar_wait(BAR(10 + acc), (uint32_t)(((c >> 1) & 1) ^ 1));
+                    tc_fence_after();
+                    chunk_data = false;
+                }
                 mbar_wait(BAR(stage), ph);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(base + (size_t)stage * STAGE_BYTES);
-                const uint32_t tacc = tmem_base + (uint32_t)(acc * TN);
+                if (*reinterpret_cast<volatile uint32_t*>(ctrl + 8 + stage) == 0u) {      // B of this stage is not all zeros
+                    const uint32_t sa = smem_u32(base + (size_t)stage * STAGE_BYTES);
+                    const uint32_t tacc = tmem_base + (uint32_t)(acc * TN);
 #pragma unroll
-                for (int kk = 0; kk < SK / 16; ++kk) {
-                    const uint32_t off = (uint32_t)kk * 2u * LBO;
-                    const uint64_t a_hi = make_desc(sa + off), a_lo = make_desc(sa + OPER_BYTES + off);
-                    const uint64_t b_hi = make_desc(sa + 2 * OPER_BYTES + off), b_lo = make_desc(sa + 3 * OPER_BYTES + off);
-                    umma(tacc, a_lo, b_hi, (first && kk == 0) ? 0u : 1u);
-                    umma(tacc, a_hi, b_lo, 1u);
-                    umma(tacc, a_hi, b_hi, 1u);
+                    for (int kk = 0; kk < SK / 16; ++kk) {
+                        const uint32_t off = (uint32_t)kk * 2u * LBO;
+                        const uint64_t a_hi = make_desc(sa + off), a_lo = make_desc(sa + OPER_BYTES + off);
+                        const uint64_t b_hi = make_desc(sa + 2 * OPER_BYTES + off), b_lo = make_desc(sa + 3 * OPER_BYTES + off);
+                        umma(tacc, a_lo, b_lo, (!chunk_data && kk == 0) ? 0u : 1u);     // smallest terms first
+                        umma(tacc, a_lo, b_hi, 1u);
+                        umma(tacc, a_hi, b_lo, 1u);
+                        umma(tacc, a_hi, b_hi, 1u);
+                    }
+                    chunk_data = true;
                 }
                 umma_commit(BAR(4 + stage));                         // smem stage is free once these MMAs retire
-                if ((s % FLUSH_STAGES) == FLUSH_STAGES - 1 || s == nst - 1) umma_commit(BAR(8 + acc));
+                if ((s % FLUSH_STAGES) == FLUSH_STAGES - 1 || s == nst - 1) {
+                    ctrl[12 + acc] = chunk_data ? 1u : 0u;
+                    __threadfence_block();
+                    umma_commit(BAR(8 + acc));
+                }
             }
         }
     } else {
-        // ================= producers: fp32 -> split bf16 operand tiles =================
-        // The raw fp32 inputs of stage s+1 are in flight (cp.async, no registers) while stage s is converted.
-        // An S unit is fetched and consumed by the same thread, so only the N rows need a producer barrier.
-        const int ptid = tid - (N_EPI + 1) * 32;
-        const int n_chunks16 = (int)(n_slot / 16);
-        auto prefetch = [&](int s) {
-            const int64_t i0 = i_beg + (int64_t)s * SK;
-            const uint32_t ra = smem_u32(rawA + (size_t)(s % RAW_A_SLOTS) * RAW_A_BYTES);
-            for (int u = ptid; u < UNITS; u += PROD_THREADS) {
-                const int r = u & 7, g = (u >> 3) & 15, kg = u >> 7;
-                const int64_t i = i0 + kg * 8 + r;
-                const int pc = p0 + 8 * g;
-                const bool row = i < i_end;
-                const float* src = S + (row ? i : 0) * ldS;
-                const bool in0 = row && pc + 4 <= ldS, in1 = row && pc + 8 <= ldS;   // columns [P,ldS) hold zeros
-                cp_async16(ra + 16 * u, in0 ? src + pc : S, in0 ? 16u : 0u);
-                cp_async16(ra + UNITS * 16 + 16 * u, in1 ? src + pc + 4 : S, in1 ? 16u : 0u);
+        // ================= producers: A tiles by bulk copy, B tiles scattered from the non-zeros of N =================
+        // B[(a,b)][i] = N[i,a] N[i,b] is non-zero only where both types occur in cell i's neighbourhood: a handful of
+        // elements per cell.  A stage buffer's B tiles are kept all-zero except for the elements its lists name;
+        // re-using the buffer clears exactly those, then scatters the new ones.  Each producer warp owns every 7th
+        // cell of a stage: it prefetches those cells' N rows into registers a stage ahead (lane = cell type), finds
+        // the non-zero types by ballot and lets the lanes write the products.  A stage whose B stays empty is flagged:
+        // no A copy is issued and the MMA thread skips it.
+        const int pw = warp - (N_EPI + 1);
+        const int a_lo = n0 / C, a_hi = min(C - 1, (n0 + TN - 1) / C);
+        const unsigned a_mask_lo = a_lo < 32 ? (a_hi >= 31 ? 0xffffffffu : ((1u << (a_hi + 1)) - 1u)) & ~((1u << a_lo) - 1u) : 0u;
+        const unsigned a_mask_hi = a_hi >= 32 ? ((a_hi - 32 >= 31 ? 0xffffffffu : ((1u << (a_hi - 31)) - 1u)) &
+                                                ~(a_lo > 32 ? ((1u << (a_lo - 32)) - 1u) : 0u)) : 0u;
+        // N rows of this warp's cells: stage s in cv*, s+1 in nv*, s+2 in fv* (two stages of loads in flight)
+        float nv0[CELLS_PER_WARP], nv1[CELLS_PER_WARP], fv0[CELLS_PER_WARP], fv1[CELLS_PER_WARP];
+        auto load_n = [&](int s, float (&v0)[CELLS_PER_WARP], float (&v1)[CELLS_PER_WARP]) {
+            const int64_t i0 = s < nst ? (int64_t)my_stages[s] * SK : n;
+#pragma unroll
+            for (int j = 0; j < CELLS_PER_WARP; ++j) {
+                const int cell = pw + N_PROD * j;
+                const int64_t i = i0 + cell;
+                const bool ok = cell < SK && i < n;
+                v0[j] = ok && lane < C ? Ncomp[i * C + lane] : 0.f;
+                v1[j] = ok && lane + 32 < C ? Ncomp[i * C + lane + 32] : 0.f;
             }
-            const uint32_t rn = smem_u32(rawN + (size_t)(s % RAW_N_SLOTS) * n_slot);
-            const int64_t f0 = i0 * C, fend = i_end * C;             // the stage's N rows are one contiguous block
-            for (int q = ptid; q < n_chunks16; q += PROD_THREADS) {
-                const int64_t f = f0 + 4 * q;
-                const int64_t left = fend - f;
-                const uint32_t nb = left >= 4 ? 16u : left > 0 ? (uint32_t)(4 * left) : 0u;
-                cp_async16(rn + 16 * q, nb ? Ncomp + f : Ncomp, nb);
-            }
-            cp_async_commit();
         };
-        if (nst > 0) prefetch(0);
+        load_n(0, nv0, nv1);
+        load_n(1, fv0, fv1);
         for (int s = 0; s < nst; ++s) {
             const int stage = s % nstages;
             const uint32_t ph = (uint32_t)((s / nstages) & 1);
-            if (s + 1 < nst) { prefetch(s + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
-            if (lane == 0) mbar_wait(BAR(4 + stage), ph ^ 1u);
+            float cv0[CELLS_PER_WARP], cv1[CELLS_PER_WARP];
+#pragma unroll
+            for (int j = 0; j < CELLS_PER_WARP; ++j) { cv0[j] = nv0[j]; cv1[j] = nv1[j]; nv0[j] = fv0[j]; nv1[j] = fv1[j]; }
+            load_n(s + 2, fv0, fv1);
+            const int64_t sg = my_stages[s];
+            if (lane == 0) mbar_wait(BAR(4 + stage), ph ^ 1u);       // the MMAs that read this buffer have retired
             __syncwarp();
             unsigned char* st = base + (size_t)stage * STAGE_BYTES;
-            const unsigned char* ra = rawA + (size_t)(s % RAW_A_SLOTS) * RAW_A_BYTES;
-            // A: unit u = 16-byte slot ((cell/8)*16 + colgroup)*8 + cell%8  <-  S[i0+cell][p0 + 8*colgroup ..+7]
-            for (int u = ptid; u < UNITS; u += PROD_THREADS) {
-                const float4 v0 = *reinterpret_cast<const float4*>(ra + 16 * u);
-                const float4 v1 = *reinterpret_cast<const float4*>(ra + UNITS * 16 + 16 * u);
-                const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                uint4 hi, lo;
-                split8(x, hi, lo);
-                *reinterpret_cast<uint4*>(st + 16 * u) = hi;
-                *reinterpret_cast<uint4*>(st + OPER_BYTES + 16 * u) = lo;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS) : "memory");     // every thread's N chunks of this stage landed
-            const float* nsr = reinterpret_cast<const float*>(rawN + (size_t)(s % RAW_N_SLOTS) * n_slot);
-            // B: same slot numbering with type-pair columns  <-  N[i][a] * N[i][b]
-            for (int u = ptid; u < UNITS; u += PROD_THREADS) {
-                const int r = u & 7, g = (u >> 3) & 15, kg = u >> 7;
-                const float* nrow = nsr + (kg * 8 + r) * C;
-                const uint4 abv = *reinterpret_cast<const uint4*>(ab_s + 8 * g);
-                const uint32_t abw[4] = {abv.x, abv.y, abv.z, abv.w};
-                float x[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const uint32_t ab = (abw[j >> 1] >> (16 * (j & 1))) & 0xffffu;
-                    x[j] = ab == 0xffffu ? 0.f : nrow[ab & 0xffu] * nrow[ab >> 8];
+            unsigned char* bh = st + 2 * OPER_BYTES;
+            uint16_t* lst = blist + ((size_t)stage * N_PROD + pw) * LIST_CAP;
+            uint32_t* my_len = ctrl + 16 + 8 * stage + pw;
+            // -- clear what this warp wrote into the buffer last time
+            const uint32_t old = *my_len;
+            if (old > LIST_CAP) {                                    // list overflowed: zero all columns of this warp's cells
+                for (int q = lane; q < CELLS_PER_WARP * (TN / 8); q += 32) {
+                    const int cell = pw + N_PROD * (q / (TN / 8));
+                    if (cell < SK) {
+                        const uint32_t off = (uint32_t)(cell >> 3) * LBO + (uint32_t)(cell & 7) * 16u + (uint32_t)(q % (TN / 8)) * SBO;
+                        *reinterpret_cast<uint4*>(bh + off) = make_uint4(0u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4*>(bh + OPER_BYTES + off) = make_uint4(0u, 0u, 0u, 0u);
+                    }
                 }
-                uint4 hi, lo;
-                split8(x, hi, lo);
-                *reinterpret_cast<uint4*>(st + 2 * OPER_BYTES + 16 * u) = hi;
-                *reinterpret_cast<uint4*>(st + 3 * OPER_BYTES + 16 * u) = lo;
+            } else {
+                for (uint32_t q = lane; q < old; q += 32) {
+                    const uint32_t off = 2u * lst[q];
+                    *reinterpret_cast<uint16_t*>(bh + off) = 0;
+                    *reinterpret_cast<uint16_t*>(bh + OPER_BYTES + off) = 0;
+                }
+            }
+            __syncwarp();
+            // -- scatter the non-zeros of this warp's cells
+            uint32_t len = 0;
+#pragma unroll
+            for (int j = 0; j < CELLS_PER_WARP; ++j) {
+                const int cell = pw + N_PROD * j;
+                const unsigned nz0 = __ballot_sync(0xffffffffu, cv0[j] != 0.f), nz1 = __ballot_sync(0xffffffffu, cv1[j] != 0.f);
+                unsigned am0 = nz0 & a_mask_lo, am1 = nz1 & a_mask_hi;
+                const uint32_t koff = (uint32_t)(cell >> 3) * LBO + (uint32_t)(cell & 7) * 16u;
+                while (am0 | am1) {                                  // each non-zero type a of this tile's column range
+                    int a;
+                    float va;
+                    if (am0) { a = __ffs(am0) - 1; am0 &= am0 - 1; va = __shfl_sync(0xffffffffu, cv0[j], a); }
+                    else { a = 32 + __ffs(am1) - 1; am1 &= am1 - 1; va = __shfl_sync(0xffffffffu, cv1[j], a - 32); }
+#pragma unroll
+                    for (int hb = 0; hb < 2; ++hb) {                 // lane = cell type b (two halves)
+                        const int b = lane + 32 * hb;
+                        const float q = va * (hb ? cv1[j] : cv0[j]);
+                        const int nl = a * C + b - n0;
+                        const bool hit = q != 0.f && b < C && nl >= 0 && nl < TN;
+                        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+                        if (hit) {
+                            const uint32_t off = koff + (uint32_t)(nl >> 3) * SBO + (uint32_t)(nl & 7) * 2u;
+                            const __nv_bfloat16 h = __float2bfloat16_rn(q);
+                            const __nv_bfloat16 l = __float2bfloat16_rn(q - __bfloat162float(h));
+                            *reinterpret_cast<__nv_bfloat16*>(bh + off) = h;
+                            *reinterpret_cast<__nv_bfloat16*>(bh + OPER_BYTES + off) = l;
+                            const uint32_t pos = len + __popc(hm & ((1u << lane) - 1u));
+                            if (pos < LIST_CAP) lst[pos] = (uint16_t)(off >> 1);
+                        }
+                        len += __popc(hm);
+                    }
+                }
+            }
+            if (lane == 0) {
+                *my_len = len;                                       // > LIST_CAP means "overflowed" to the next user of the buffer
+                if (len) atomicAdd(ctrl + 4 + stage, len);
             }
             fence_async_smem();                                      // generic-proxy writes -> visible to the tensor core
+            asm volatile("bar.sync 1, %0;" ::"n"(PROD_THREADS) : "memory");     // the stage's count is final
+            if (pw == 0 && lane == 0) {
+                const uint32_t cnt = ctrl[4 + stage];
+                ctrl[4 + stage] = 0u;
+                ctrl[8 + stage] = cnt == 0u ? 1u : 0u;
+                if (cnt) {                                           // A_hi | A_lo of this stage: one contiguous 32 KB block
+                    mbar_expect_tx(BAR(stage), A_TX_BYTES);
+                    const unsigned char* src = Asplit + (sg * tiles_m + tm) * (int64_t)A_TX_BYTES;
+                    bulk_g2s(smem_u32(st), src, OPER_BYTES, BAR(stage));
+                    bulk_g2s(smem_u32(st + OPER_BYTES), src + OPER_BYTES, OPER_BYTES, BAR(stage));
+                } else {
+                    mbar_arrive(BAR(stage));
+                }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(BAR(stage));
         }
@@ -309,39 +489,52 @@ __global__ void partial_reduce_kernel(const float* __restrict__ partial, int spl
 }  // namespace mma
 
 int celltype_pair_contract_mma(const float* S, int64_t ldS, int64_t n, int32_t P, const float* Ncomp, int32_t C,
-                               double* num, cudaStream_t st) {
+                               const int32_t* order, double* num, cudaStream_t st) {
     using namespace mma;
-    if (C > 255 || ldS % 4 != 0 || ((uintptr_t)S & 15) != 0) {
-        set_error("laris_celltype_pair_contract(impl=0): needs C <= 255, ldS %% 4 == 0 and a 16-byte aligned S");
+    if (C < 1 || C > MAX_C || ldS % 4 != 0 || ((uintptr_t)S & 15) != 0) {
+        set_error("laris_celltype_pair_contract(impl=0): needs C <= %d, ldS %% 4 == 0 and a 16-byte aligned S", MAX_C);
         return LARIS_E_LIMIT;
     }
-    int nstages = 2;
-    if (Smem::bytes(nstages, C) > (size_t)227 * 1024) {
-        set_error("laris_celltype_pair_contract(impl=0): C=%d does not fit shared memory", C);
-        return LARIS_E_LIMIT;
-    }
+    const int nstages = 3;
     const int CC = C * C;
     const int tiles_m = (int)ceil_div(P, TM), tiles_n = (int)ceil_div(CC, TN), tiles = tiles_m * tiles_n;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // K split: enough CTAs for whole waves of the SMs, at least 16 stages of work each
-    const int64_t max_splits = ceil_div(n, (int64_t)16 * SK) < 1 ? 1 : ceil_div(n, (int64_t)16 * SK);
-    int best = 1;
-    double best_eff = 0.0;
-    for (int s = 1; s <= 64 && s <= max_splits; ++s) {
-        const double ctas = (double)tiles * s;
-        const double eff = ctas / (ceil(ctas / sms) * sms);
-        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    // K split: the active stages of a column tile are dealt evenly to `splits` CTAs; aim at >= 4 waves of CTAs so
+    // the hardware scheduler evens out tiles with few / many active stages
+    const int64_t nsg = ceil_div(n, SK);
+    int splits = (int)ceil_div((int64_t)sms * 4, tiles);
+    if (splits > nsg / 8) splits = (int)(nsg / 8);
+    if (splits < 1) splits = 1;
+    // pass 1: split S once (and put the N rows in the same cell order); active stages of every column tile
+    Scratch<unsigned char> asplit(st);
+    Scratch<float> nsorted(st), partial(st);
+    Scratch<unsigned long long> smask(st);
+    Scratch<int32_t> alist(st), acount(st);
+    LARIS_CUDA(asplit.alloc((size_t)nsg * tiles_m * A_TX_BYTES));
+    split_scores_kernel<<<(unsigned)(nsg * tiles_m * 4), 256, 0, st>>>(S, ldS, n, P, order, tiles_m, asplit.p);
+    LARIS_LAUNCH_CHECK();
+    const float* nrows = Ncomp;
+    if (order) {
+        LARIS_CUDA(nsorted.alloc((size_t)n * C));
+        gather_rows_kernel<<<(unsigned)ceil_div(n * C, 256), 256, 0, st>>>(Ncomp, n, C, order, nsorted.p);
+        LARIS_LAUNCH_CHECK();
+        nrows = nsorted.p;
     }
-    int64_t per = ceil_div(ceil_div(n, (int64_t)best), (int64_t)SK) * SK;
-    const int splits = (int)ceil_div(n, per);
-    Scratch<float> partial(st);
+    LARIS_CUDA(smask.alloc((size_t)nsg));
+    LARIS_CUDA(alist.alloc((size_t)tiles_n * nsg));
+    LARIS_CUDA(acount.alloc((size_t)tiles_n));
+    stage_type_mask_kernel<<<(unsigned)ceil_div(nsg * 32, 256), 256, 0, st>>>(nrows, n, C, nsg, smask.p);
+    LARIS_LAUNCH_CHECK();
+    active_stage_list_kernel<<<(unsigned)tiles_n, 1024, 0, st>>>(smask.p, nsg, C, alist.p, acount.p);
+    LARIS_LAUNCH_CHECK();
+    // pass 2: the contraction
     LARIS_CUDA(partial.alloc((size_t)splits * P * CC));
-    const size_t smem = Smem::bytes(nstages, C);
+    const size_t smem = Smem::bytes(nstages);
     LARIS_CUDA(cudaFuncSetAttribute(pair_contract_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pair_contract_mma_kernel<<<(unsigned)(tiles * splits), THREADS, smem, st>>>(S, ldS, n, P, Ncomp, C, tiles_n, tiles, per, nstages,
-                                                                               partial.p);
+    pair_contract_mma_kernel<<<(unsigned)(tiles * splits), THREADS, smem, st>>>(asplit.p, tiles_m, n, P, nrows, C, tiles_n, tiles,
+                                                                               splits, alist.p, acount.p, nsg, nstages, partial.p);
     LARIS_LAUNCH_CHECK();
     const int64_t total = (int64_t)P * CC;
     partial_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(partial.p, splits, total, num);

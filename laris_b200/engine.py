@@ -281,10 +281,10 @@ def cosg_regularise(cos, mu):
     return out * cos
 
 
-def neighborhood_specificity(sm: ScoreMatrix, labels_d, C, graph: SpatialGraph, mu, ss=None, impl=1):
+def neighborhood_specificity(sm: ScoreMatrix, labels_d, C, graph: SpatialGraph, mu, ss=None, impl=None):
     """Raw P x C^2 co-localisation table (reference _utils.py:839-880), K5."""
     N = K.neighborhood_composition(labels_d, graph.idx, graph.w, C)
-    num, qn2 = K.celltype_pair_contract(sm.S, sm.P, N, impl)
+    num, qn2 = K.celltype_pair_contract(sm.S, sm.P, N, impl, order=graph.order)
     num, qn2 = num.cpu().numpy(), qn2.cpu().numpy()
     if ss is None:
         ss = observed_stats(sm, graph)[1]

@@ -63,7 +63,7 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
              layer_celltype=None, n_neighbors_permutation: int = 30, n_permutations: int = 1000, chunk_size: int = 50000,
              prefilter_fdr: bool = True, prefilter_threshold: float = 0.0, score_threshold: float = 1e-6,
              spatial_weight: float = 1.0, use_conditional_pvalue: bool = False, *, rng: str = "numpy",
-             verbose: bool = True, contract_impl: int = 1):
+             verbose: bool = True, contract_impl=None):
     """Spatially-specific LR pairs and (optionally) the cell-type interaction table.
 
     Reference laris/tools/__init__.py:121-593, same arguments and returns

@@ -212,7 +212,7 @@ def _calculate_specificity_in_spatial_neighborhood(adata, lr_adata, groupby: str
                                                    number_nearest_neighbors: int = 10, mu: float = 100,
                                                    expressed_pct: float = 0.1, remove_lowly_expressed: bool = True,
                                                    return_by_group: bool = True, key_added=None,
-                                                   column_delimiter: str = "@@", contract_impl: int = 1):
+                                                   column_delimiter: str = "@@", contract_impl=None):
     """Specificity of every LR pair for every sender::receiver neighbourhood profile.
 
     Reference :726-977.  Stores ``lr_adata.uns[key_added]`` with the reference's
@@ -278,7 +278,7 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_r
                                        prefilter_threshold: float = 0.0, score_threshold: float = 1e-6,
                                        spatial_weight: float = 1.0, use_conditional_pvalue: bool = False, *,
                                        rng: str = "numpy", random_seed: int = 27, rng_state=None, verbose: bool = True,
-                                       contract_impl: int = 1):
+                                       contract_impl=None):
     """Sender/receiver cell-type table with permutation p-values and BH-FDR.
 
     Reference laris/tools/_utils.py:1113-1688; same arguments (``mask_threshold`` and

@@ -42,6 +42,32 @@ def run(n, P, C, dens=0.3, seed=0, timing=False):
 if __name__ == "__main__":
     mode = sys.argv[1] if len(sys.argv) > 1 else "small"
     if mode == "small":
-        run(300, 40, 5); run(1000, 128, 8); run(5000, 200, 12); run(4097, 500, 20); run(20000, 131, 40, timing=True)
-    else:
+        run(300, 40, 8); run(1000, 128, 9); run(5000, 200, 12); run(4097, 500, 20); run(20000, 131, 40, timing=True)
+    elif mode == "big":
         run(100000, 500, 20, timing=True); run(1000000, 2000, 40, dens=0.2, timing=True)
+    else:                                   # the synthetic configs: real score matrix, real neighbourhood composition
+        from laris_b200 import engine
+        from laris_b200.synth import make_dataset
+        import laris_b200 as la
+        for cfg in (2, 3):
+            a, lr, c = make_dataset(cfg)
+            lg, rg = la.tl._lr_gene_indices(a, lr)
+            g1 = engine.build_graph(a.obsm["X_spatial"], c.k, True, None)
+            xu, lc, rc = engine.select_lr_genes(a.X, lg, rg)
+            sm = engine.lr_scores(xu, g1, lc, rc)
+            g2 = engine.build_graph(a.obsm["X_spatial"], c.k, False, None)
+            lab = K.to_device(a.obs["CellTypes"].cat.codes.to_numpy().astype(np.int32), torch.int32)
+            N_ = K.neighborhood_composition(lab, g2.idx, g2.w, c.C)
+            print(f"config {cfg}: n={c.n} P={c.P} C={c.C}  nonzero fraction of N = {float((N_ != 0).float().mean()):.3f}", flush=True)
+            ref, _ = K.celltype_pair_contract(sm.S, c.P, N_, 1)
+            for name, order in (("natural order", None), ("spatial order", g2.order)):
+                num, _ = K.celltype_pair_contract(sm.S, c.P, N_, 0, order=order)
+                r, x = ref.cpu().numpy(), num.cpu().numpy()
+                m = np.abs(r) > 1e-3 * np.abs(r).max()
+                ts = []
+                for _ in range(3):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); K.celltype_pair_contract(sm.S, c.P, N_, 0, order=order); e1.record(); torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                print(f"   tcgen05 {name}: max rel {np.abs(x - r)[m].max() and (np.abs(x - r)[m] / np.abs(r)[m]).max():.2e}  {min(ts):.3f} ms"
+                      f" -> {2.0*c.n*c.P*c.C*c.C/min(ts)/1e9:.1f} TFLOP/s algorithmic", flush=True)

@@ -19,12 +19,14 @@ for l in txt[start + 1:]:
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/", l)
     if m:
         addr2line[int(m.group(1), 16)] = line
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+kflt = ["--kernel-name", "regex:" + os.environ["NCU_KERNEL"]] if os.environ.get("NCU_KERNEL") else []
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + kflt, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 h = rows[hi]
 ai, ie, smp = h.index("Address"), h.index("Instructions Executed"), h.index("# Samples")
-ws, wsi = h.index("L1 Wavefronts Shared"), h.index("L1 Wavefronts Shared Ideal")
+ws = h.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in h else smp
+wsi = h.index("L1 Wavefronts Shared Ideal") if "L1 Wavefronts Shared Ideal" in h else smp
 per, pers, pw, pwi = (collections.Counter() for _ in range(4))
 base, tot, ts, tw = None, 0, 0, 0
 for r in rows[hi + 1:]:
