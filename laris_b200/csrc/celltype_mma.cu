@@ -4,14 +4,16 @@
 // GEMM view: D[M = pairs][N = type pairs] = A * B^T with the contraction over cells,
 //   A[p][i] = S[i][p]                 (S is cell-major, so A is "MN-major": p is the contiguous index)
 //   B[(a,b)][i] = N[i][a] * N[i][b]   (built on the fly from the C values of each cell)
-// fp32 inputs are split into bf16 hi + bf16 lo (x = hi + lo to 2^-18 relative); four tcgen05.mma
-// (lo*lo, lo*hi, hi*lo, hi*hi) accumulate in fp32 in TMEM, so a product is exact to 2^-17 relative.
+// fp32 inputs are split three ways into bf16 hi + mid + lo (x = hi + mid + lo to 2^-24 relative: a two-way
+// split only reaches 2^-17 per operand in the worst case, which breaks the 1e-5 bar on sums of a few terms);
+// six tcgen05.mma (mid*mid, lo*hi, hi*lo, mid*hi, hi*mid, hi*hi; the dropped products are < 2^-23) accumulate
+// in fp32 in TMEM.
 // Tensor-core accumulation truncates (measured: bias grows linearly with the number of accumulated MMAs), so a
 // TMEM accumulator only ever sums 256 cells (64 MMAs); the epilogue warps add each such chunk into fp32
 // running sums in registers (round-to-nearest), and the K-split partials are combined in fp64.
 //
 // Two kernels:
-//  split_scores_kernel   one pass over S: fp32 -> bf16 hi / lo, written tile by tile in exactly the shared-memory
+//  split_scores_kernel   one pass over S: fp32 -> bf16 hi / mid / lo, written tile by tile in exactly the shared-memory
 //                        operand layout (canonical no-swizzle MN-major: 16-byte slots [cell/8][pair/8][cell%8][8 pairs]),
 //                        cells taken in the spatial processing order when one is given; also gathers the N rows
 //                        in that order.  Cost: S read once, the same number of bytes written.
@@ -19,13 +21,13 @@
 //   warps 0-7   epilogue: tcgen05.ld the finished TMEM chunk (two accumulator buffers, so the next chunk
 //               is being multiplied meanwhile) and add it to the running sums; at the end write the partial
 //   warp  8     one elected thread issues the MMAs and commits them to mbarriers
-//   warps 9-15  producers: one thread issues the two 16 KB bulk copies (cp.async.bulk -> mbarrier complete_tx)
-//               that bring the stage's A_hi / A_lo tiles straight into their operand slots; all of them build
-//               B = N[i,a]*N[i,b] (split hi/lo) for the stage's 64 cells from the N rows (cp.async, one stage
+//   warps 9-15  producers: one thread issues the bulk copies (cp.async.bulk -> mbarrier complete_tx)
+//               that bring the stage's A_hi / A_mid / A_lo tiles straight into their operand slots; all of them build
+//               B = N[i,a]*N[i,b] (split hi/mid/lo) for the stage's 64 cells from the N rows (cp.async, one stage
 //               ahead).  N is mostly zeros (a neighbourhood holds few cell types), so a unit whose N[i,a] is
 //               zero is stored as zeros without touching the b side; with spatially ordered cells whole warps
 //               take that path.  Then fence.proxy.async + mbarrier arrive.
-// Shared memory: 3 operand stages (A_hi, A_lo, B_hi, B_lo, 16 KB each) and 2 raw N blocks in flight.
+// Shared memory: NSTAGES operand stages of six tiles (A_hi, A_mid, A_lo, B_hi, B_mid, B_lo; SK*256 bytes each).
 #include "common.cuh"
 
 #include <cuda_bf16.h>
@@ -33,13 +35,18 @@
 namespace laris {
 namespace mma {
 
-constexpr int TM = 128, TN = 128, SK = 64;
-constexpr int FLUSH_STAGES = 4;                        // 256 cells per TMEM accumulation chunk
+#ifndef LARIS_MMA_SK
+#define LARIS_MMA_SK 64
+#endif
+constexpr int TM = 128, TN = 128, SK = LARIS_MMA_SK;  // SK = cells per pipeline stage (32 or 64)
+constexpr int NSTAGES = SK == 64 ? 2 : 4;              // 192 KB of operand tiles either way
+constexpr int FLUSH_STAGES = 256 / SK;                 // 256 cells per TMEM accumulation chunk
 constexpr int N_EPI = 8, N_PROD = 7;
 constexpr int THREADS = (N_EPI + 1 + N_PROD) * 32;     // 512
 constexpr int PROD_THREADS = N_PROD * 32;
 constexpr int OPER_BYTES = SK * TM * 2;                // 16 KB
-constexpr int STAGE_BYTES = 4 * OPER_BYTES;
+constexpr int NSPLIT = 3;                              // bf16 terms per fp32 operand
+constexpr int STAGE_BYTES = 2 * NSPLIT * OPER_BYTES;
 constexpr int UNITS = SK * TM / 8;                     // 16-byte slots per operand tile (1024)
 constexpr uint32_t IDESC = (1u << 4)      // D format fp32
                          | (1u << 7)      // A format bf16
@@ -83,22 +90,25 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-// 8 fp32 -> 8 bf16 "hi" and 8 bf16 "lo" (x ~ hi + lo to ~16 mantissa bits)
-__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
-    uint32_t h[4], l[4];
+// 8 fp32 -> 8 bf16 "hi", "mid" and "lo": x = hi + mid + lo to 24 mantissa bits (each remainder is exact in fp32)
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& mid, uint4& lo) {
+    uint32_t h[4], m[4], l[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const __nv_bfloat162 hb = __floats2bfloat162_rn(x[2 * q], x[2 * q + 1]);
         h[q] = *reinterpret_cast<const uint32_t*>(&hb);
-        const float h0 = __uint_as_float(h[q] << 16), h1 = __uint_as_float(h[q] & 0xffff0000u);
-        const __nv_bfloat162 lb = __floats2bfloat162_rn(x[2 * q] - h0, x[2 * q + 1] - h1);
+        const float r0 = x[2 * q] - __uint_as_float(h[q] << 16), r1 = x[2 * q + 1] - __uint_as_float(h[q] & 0xffff0000u);
+        const __nv_bfloat162 mb = __floats2bfloat162_rn(r0, r1);
+        m[q] = *reinterpret_cast<const uint32_t*>(&mb);
+        const __nv_bfloat162 lb = __floats2bfloat162_rn(r0 - __uint_as_float(m[q] << 16), r1 - __uint_as_float(m[q] & 0xffff0000u));
         l[q] = *reinterpret_cast<const uint32_t*>(&lb);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
+    mid = make_uint4(m[0], m[1], m[2], m[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-constexpr uint32_t A_TX_BYTES = 2 * OPER_BYTES;
+constexpr uint32_t A_TX_BYTES = NSPLIT * OPER_BYTES;
 
 constexpr int LIST_CAP = 384;                          // non-zero B elements a warp remembers per stage buffer
 constexpr int CELLS_PER_WARP = (SK + N_PROD - 1) / N_PROD;      // 10
@@ -136,13 +146,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// S (fp32, cell-major) -> A_hi / A_lo tiles in operand layout: block (sg, tm) = cells [64 sg, 64 sg + 64) of the
-// processing order x pairs [128 tm, 128 tm + 128), hi tile then lo tile, 16 KB each.  One thread per 16-byte slot.
+// S (fp32, cell-major) -> A_hi / A_mid / A_lo tiles in operand layout: block (sg, tm) = cells [SK sg, SK sg + SK) of the
+// processing order x pairs [128 tm, 128 tm + 128), hi tile, mid tile, lo tile.  One thread per 16-byte slot.
 __global__ void __launch_bounds__(256)
 split_scores_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, int P, const int32_t* __restrict__ order,
                     int tiles_m, unsigned char* __restrict__ Asplit) {
-    const int64_t blk = blockIdx.x >> 2;                             // 4 CTAs of 256 slots per tile
-    const int u = ((blockIdx.x & 3) << 8) + threadIdx.x;
+    constexpr int CTAS_PER_TILE = UNITS / 256;
+    const int64_t blk = blockIdx.x / CTAS_PER_TILE;
+    const int u = (int)(blockIdx.x % CTAS_PER_TILE) * 256 + threadIdx.x;
     const int64_t sg = blk / tiles_m;
     const int tm = (int)(blk - sg * tiles_m);
     const int r = u & 7, g = (u >> 3) & 15, kg = u >> 7;
@@ -163,11 +174,12 @@ split_scores_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, int P, 
             for (int j = 0; j < 8; ++j) if (pc + j < P) x[j] = row[j];
         }
     }
-    uint4 hi, lo;
-    split8(x, hi, lo);
-    unsigned char* dst = Asplit + blk * (int64_t)(2 * OPER_BYTES) + 16 * u;
+    uint4 hi, mid, lo;
+    split8(x, hi, mid, lo);
+    unsigned char* dst = Asplit + blk * (int64_t)A_TX_BYTES + 16 * u;
     *reinterpret_cast<uint4*>(dst) = hi;
-    *reinterpret_cast<uint4*>(dst + OPER_BYTES) = lo;
+    *reinterpret_cast<uint4*>(dst + OPER_BYTES) = mid;
+    *reinterpret_cast<uint4*>(dst + 2 * OPER_BYTES) = lo;
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ N, int64_t n, int C, const int32_t* __restrict__ order,
@@ -257,9 +269,9 @@ pair_contract_mma_kernel(const unsigned char* __restrict__ Asplit, int tiles_m, 
     const int nchunk = (nst + FLUSH_STAGES - 1) / FLUSH_STAGES;
 
     if (tid < 64) ctrl[tid] = 0u;
-    for (int q = tid; q < nstages * (2 * OPER_BYTES / 16); q += THREADS)        // B tiles start as zeros
-        *reinterpret_cast<uint4*>(base + (size_t)(q / (2 * OPER_BYTES / 16)) * STAGE_BYTES + 2 * OPER_BYTES +
-                                  16 * (q % (2 * OPER_BYTES / 16))) = make_uint4(0u, 0u, 0u, 0u);
+    for (int q = tid; q < nstages * (NSPLIT * OPER_BYTES / 16); q += THREADS)   // B tiles start as zeros
+        *reinterpret_cast<uint4*>(base + (size_t)(q / (NSPLIT * OPER_BYTES / 16)) * STAGE_BYTES + NSPLIT * OPER_BYTES +
+                                  16 * (q % (NSPLIT * OPER_BYTES / 16))) = make_uint4(0u, 0u, 0u, 0u);
     fence_async_smem();
     if (tid == 0) {
         for (int s = 0; s < nstages; ++s) { mbar_init(BAR(s), N_PROD + 1); mbar_init(BAR(4 + s), 1); }
@@ -336,11 +348,15 @@ pair_contract_mma_kernel(const unsigned char* __restrict__ Asplit, int tiles_m, 
 #pragma unroll
                     for (int kk = 0; kk < SK / 16; ++kk) {
                         const uint32_t off = (uint32_t)kk * 2u * LBO;
-                        const uint64_t a_hi = make_desc(sa + off), a_lo = make_desc(sa + OPER_BYTES + off);
-                        const uint64_t b_hi = make_desc(sa + 2 * OPER_BYTES + off), b_lo = make_desc(sa + 3 * OPER_BYTES + off);
-                        umma(tacc, a_lo, b_lo, (!chunk_data && kk == 0) ? 0u : 1u);     // smallest terms first
+                        const uint64_t a_hi = make_desc(sa + off), a_mi = make_desc(sa + OPER_BYTES + off),
+                                       a_lo = make_desc(sa + 2 * OPER_BYTES + off);
+                        const uint64_t b_hi = make_desc(sa + 3 * OPER_BYTES + off), b_mi = make_desc(sa + 4 * OPER_BYTES + off),
+                                       b_lo = make_desc(sa + 5 * OPER_BYTES + off);
+                        umma(tacc, a_mi, b_mi, (!chunk_data && kk == 0) ? 0u : 1u);     // smallest terms first
                         umma(tacc, a_lo, b_hi, 1u);
                         umma(tacc, a_hi, b_lo, 1u);
+                        umma(tacc, a_mi, b_hi, 1u);
+                        umma(tacc, a_hi, b_mi, 1u);
                         umma(tacc, a_hi, b_hi, 1u);
                     }
                     chunk_data = true;
@@ -392,7 +408,7 @@ pair_contract_mma_kernel(const unsigned char* __restrict__ Asplit, int tiles_m, 
             if (lane == 0) mbar_wait(BAR(4 + stage), ph ^ 1u);       // the MMAs that read this buffer have retired
             __syncwarp();
             unsigned char* st = base + (size_t)stage * STAGE_BYTES;
-            unsigned char* bh = st + 2 * OPER_BYTES;
+            unsigned char* bh = st + NSPLIT * OPER_BYTES;
             uint16_t* lst = blist + ((size_t)stage * N_PROD + pw) * LIST_CAP;
             uint32_t* my_len = ctrl + 16 + 8 * stage + pw;
             // -- clear what this warp wrote into the buffer last time
@@ -404,6 +420,7 @@ pair_contract_mma_kernel(const unsigned char* __restrict__ Asplit, int tiles_m, 
                         const uint32_t off = (uint32_t)(cell >> 3) * LBO + (uint32_t)(cell & 7) * 16u + (uint32_t)(q % (TN / 8)) * SBO;
                         *reinterpret_cast<uint4*>(bh + off) = make_uint4(0u, 0u, 0u, 0u);
                         *reinterpret_cast<uint4*>(bh + OPER_BYTES + off) = make_uint4(0u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4*>(bh + 2 * OPER_BYTES + off) = make_uint4(0u, 0u, 0u, 0u);
                     }
                 }
             } else {
@@ -411,6 +428,7 @@ pair_contract_mma_kernel(const unsigned char* __restrict__ Asplit, int tiles_m, 
                     const uint32_t off = 2u * lst[q];
                     *reinterpret_cast<uint16_t*>(bh + off) = 0;
                     *reinterpret_cast<uint16_t*>(bh + OPER_BYTES + off) = 0;
+                    *reinterpret_cast<uint16_t*>(bh + 2 * OPER_BYTES + off) = 0;
                 }
             }
             __syncwarp();
@@ -437,9 +455,12 @@ pair_contract_mma_kernel(const unsigned char* __restrict__ Asplit, int tiles_m, 
                         if (hit) {
                             const uint32_t off = koff + (uint32_t)(nl >> 3) * SBO + (uint32_t)(nl & 7) * 2u;
                             const __nv_bfloat16 h = __float2bfloat16_rn(q);
-                            const __nv_bfloat16 l = __float2bfloat16_rn(q - __bfloat162float(h));
+                            const float r1 = q - __bfloat162float(h);
+                            const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+                            const __nv_bfloat16 l = __float2bfloat16_rn(r1 - __bfloat162float(m));
                             *reinterpret_cast<__nv_bfloat16*>(bh + off) = h;
-                            *reinterpret_cast<__nv_bfloat16*>(bh + OPER_BYTES + off) = l;
+                            *reinterpret_cast<__nv_bfloat16*>(bh + OPER_BYTES + off) = m;
+                            *reinterpret_cast<__nv_bfloat16*>(bh + 2 * OPER_BYTES + off) = l;
                             const uint32_t pos = len + __popc(hm & ((1u << lane) - 1u));
                             if (pos < LIST_CAP) lst[pos] = (uint16_t)(off >> 1);
                         }
@@ -457,11 +478,12 @@ pair_contract_mma_kernel(const unsigned char* __restrict__ Asplit, int tiles_m, 
                 const uint32_t cnt = ctrl[4 + stage];
                 ctrl[4 + stage] = 0u;
                 ctrl[8 + stage] = cnt == 0u ? 1u : 0u;
-                if (cnt) {                                           // A_hi | A_lo of this stage: one contiguous 32 KB block
+                if (cnt) {                                           // A_hi | A_mid | A_lo of this stage: one contiguous block
                     mbar_expect_tx(BAR(stage), A_TX_BYTES);
                     const unsigned char* src = Asplit + (sg * tiles_m + tm) * (int64_t)A_TX_BYTES;
-                    bulk_g2s(smem_u32(st), src, OPER_BYTES, BAR(stage));
-                    bulk_g2s(smem_u32(st + OPER_BYTES), src + OPER_BYTES, OPER_BYTES, BAR(stage));
+#pragma unroll
+                    for (int t = 0; t < NSPLIT; ++t)
+                        bulk_g2s(smem_u32(st + t * OPER_BYTES), src + t * OPER_BYTES, OPER_BYTES, BAR(stage));
                 } else {
                     mbar_arrive(BAR(stage));
                 }
@@ -495,7 +517,7 @@ int celltype_pair_contract_mma(const float* S, int64_t ldS, int64_t n, int32_t P
         set_error("laris_celltype_pair_contract(impl=0): needs C <= %d, ldS %% 4 == 0 and a 16-byte aligned S", MAX_C);
         return LARIS_E_LIMIT;
     }
-    const int nstages = 3;
+    const int nstages = NSTAGES;
     const int CC = C * C;
     const int tiles_m = (int)ceil_div(P, TM), tiles_n = (int)ceil_div(CC, TN), tiles = tiles_m * tiles_n;
     int dev = 0, sms = kNumSMs;
@@ -513,7 +535,7 @@ int celltype_pair_contract_mma(const float* S, int64_t ldS, int64_t n, int32_t P
     Scratch<unsigned long long> smask(st);
     Scratch<int32_t> alist(st), acount(st);
     LARIS_CUDA(asplit.alloc((size_t)nsg * tiles_m * A_TX_BYTES));
-    split_scores_kernel<<<(unsigned)(nsg * tiles_m * 4), 256, 0, st>>>(S, ldS, n, P, order, tiles_m, asplit.p);
+    split_scores_kernel<<<(unsigned)(nsg * tiles_m * (UNITS / 256)), 256, 0, st>>>(S, ldS, n, P, order, tiles_m, asplit.p);
     LARIS_LAUNCH_CHECK();
     const float* nrows = Ncomp;
     if (order) {

@@ -105,14 +105,24 @@ spatial_stats_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t n, cons
     }
 }
 
-__global__ void stats_reduce_kernel(const double* __restrict__ partial, int nchunks, int64_t Ppad, int P,
-                                    double* __restrict__ out) {
-    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;     // over 5*P
-    if (e >= 5ll * P) return;
-    const int q = (int)(e / P), p = (int)(e - (int64_t)q * P);
+// partial [nchunks][5][Ppad] -> out [5][P].  CTA (32 columns x 8 chunk lanes): coalesced reads, the 8 chunk lanes
+// are combined in a fixed order, so the result is deterministic.
+__global__ void __launch_bounds__(256)
+stats_reduce_kernel(const double* __restrict__ partial, int nchunks, int64_t Ppad, int P, double* __restrict__ out) {
+    __shared__ double red[8][33];
+    const int cx = threadIdx.x & 31, cy = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + cx, q = blockIdx.y;
     double s = 0.0;
-    for (int c = 0; c < nchunks; ++c) s += partial[((int64_t)c * 5 + q) * Ppad + p];
-    out[e] = s;
+    if (p < P)
+        for (int c = cy; c < nchunks; c += 8) s += partial[((int64_t)c * 5 + q) * Ppad + p];
+    red[cy][cx] = s;
+    __syncthreads();
+    if (cy == 0 && p < P) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += red[r][cx];
+        out[(int64_t)q * P + p] = t;
+    }
 }
 
 __global__ void null_graph_kernel(int64_t n, int64_t m, const float* __restrict__ w, uint32_t repeat, uint64_t seed,
@@ -153,7 +163,7 @@ extern "C" int laris_spatial_stats(const float* S, int64_t ldS, int64_t n, int32
     else
         spatial_stats_kernel<false><<<grid, kStThreads, 0, st>>>((const float4*)S, ld4, n, idx, w, k, order, (int)nchunks, partial.p);
     LARIS_LAUNCH_CHECK();
-    stats_reduce_kernel<<<(unsigned)ceil_div(5ll * P, 256), 256, 0, st>>>(partial.p, (int)nchunks, ld4 * 4, P, out);
+    stats_reduce_kernel<<<dim3((unsigned)ceil_div(P, 32), 5), 256, 0, st>>>(partial.p, (int)nchunks, ld4 * 4, P, out);
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
 }

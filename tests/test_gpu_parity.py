@@ -306,9 +306,10 @@ def test_celltype_contractions(dev, golden, tiny):
     N_ref = R.neighborhood_composition(labels, ind, R.decay_weights(dist), C)
     N = K.neighborhood_composition(lab_d, g.idx, g.w, C).cpu().numpy()
     assert np.allclose(N.T, N_ref, rtol=1e-5, atol=1e-7)
-    raw, cos = engine.neighborhood_specificity(sm, lab_d, C, g, 100.0, impl=1)
-    assert np.allclose(cos, R.celltype_pair_cosine(S, N_ref), rtol=RTOL, atol=1e-8)
-    assert np.allclose(raw, golden["ctc_raw"], rtol=2e-5, atol=1e-10)       # the reference's own table
+    for impl in (0, 1):                                             # tcgen05 tensor cores / fp32 CUDA cores
+        raw, cos = engine.neighborhood_specificity(sm, lab_d, C, g, 100.0, impl=impl)
+        assert np.allclose(cos, R.celltype_pair_cosine(S, N_ref), rtol=RTOL, atol=1e-8), impl
+        assert np.allclose(raw, golden["ctc_raw"], rtol=2e-5, atol=1e-10), impl   # the reference's own table
     # COSG gene scores
     X = sp.csr_matrix(a.X)
     genes = np.unique(np.concatenate([golden["lig_idx"], golden["rec_idx"]]))
@@ -317,6 +318,53 @@ def test_celltype_contractions(dev, golden, tiny):
     ref = R.cosg_scores(X[:, genes], labels, C, 100.0, 0.1, True)
     assert np.array_equal(got == -1, ref == -1)
     assert np.allclose(got, ref, rtol=RTOL, atol=1e-9)
+
+
+@pytest.mark.parametrize("n,P,C,perm", [
+    (300, 40, 8, False),          # one tile, ragged everything
+    (1000, 128, 9, True),         # P exactly one tile; C*C < 128
+    (4097, 500, 20, True),        # several row/column tiles, n % 64 != 0
+    (9000, 131, 40, False),       # column tiles straddling cell types
+    (2500, 70, 64, True),         # largest supported number of cell types
+    (3000, 33, 1, False),         # single cell type
+])
+def test_pair_contract_tensor_cores(dev, n, P, C, perm):
+    """tcgen05 contraction (impl=0) against a float64 contraction and against the fp32 CUDA-core kernel."""
+    from laris_b200 import _kernels as K
+    rng = np.random.default_rng(n + P + C)
+    ld = K.padded_ld(P)
+    S = np.zeros((n, ld), np.float32)
+    S[:, :P] = (rng.random((n, P)) < 0.3) * rng.gamma(2.0, 1.0, (n, P)).astype(np.float32)
+    N = np.zeros((n, C), np.float32)
+    for _ in range(3):
+        N[np.arange(n), rng.integers(0, C, n)] += rng.random(n).astype(np.float32)
+    N[::50] = 0.0                                                    # cells with an empty neighbourhood profile
+    Sd, Nd = torch.from_numpy(S).to(dev), torch.from_numpy(N).to(dev)
+    order = torch.from_numpy(rng.permutation(n).astype(np.int32)).to(dev) if perm else None
+    num0, q0 = K.celltype_pair_contract(Sd, P, Nd, 0, order=order)
+    num1, q1 = K.celltype_pair_contract(Sd, P, Nd, 1)
+    Q = (N[:, :, None].astype(np.float64) * N[:, None, :]).reshape(n, C * C)
+    ref = S[:, :P].astype(np.float64).T @ Q
+    a0, a1 = num0.cpu().numpy(), num1.cpu().numpy()
+    assert np.array_equal(a0 == 0, ref == 0)                         # exact zeros stay exact
+    # split-bf16 operands: every product is exact to 2^-17, sums of positive terms inherit that bound
+    assert np.allclose(a0, ref, rtol=RTOL, atol=0)
+    assert np.allclose(a1, ref, rtol=1e-6, atol=0)
+    assert np.allclose(q0.cpu().numpy(), (Q * Q).sum(0), rtol=1e-6)
+    if perm:                                                         # the cell order only changes fp32 summation order
+        num2, _ = K.celltype_pair_contract(Sd, P, Nd, 0)
+        assert np.allclose(num2.cpu().numpy(), a0, rtol=2e-6, atol=0)
+
+
+def test_pair_contract_argument_errors(dev):
+    from laris_b200 import _kernels as K
+    from laris_b200._lib import LarisError
+    S = torch.zeros((64, 8), device=dev)
+    N = torch.zeros((64, 65), device=dev)
+    with pytest.raises(LarisError, match="C <= 64"):
+        K.celltype_pair_contract(S, 8, N, 0)
+    num, _ = K.celltype_pair_contract(S, 8, N)                        # auto: falls to the CUDA-core kernel
+    assert float(num.abs().sum()) == 0.0
 
 
 # --------------------------------------------------------------- K6/K7 ----

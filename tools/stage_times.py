@@ -52,7 +52,8 @@ cols, wperm = T("null_graph_philox", lambda: K.null_graph_philox(c.n, k, w2, 0, 
 T("spatial_stats(null)", lambda: K.spatial_stats(S, P, cols, wperm, True, None))
 T("celltype_nonzero_count", lambda: K.celltype_nonzero_count(S, P, labels, c.C))
 N_ = T("neighborhood_composition", lambda: K.neighborhood_composition(labels, idx2, w2, c.C))
-T("celltype_pair_contract(fp32)", lambda: K.celltype_pair_contract(S, P, N_, 1), reps=3)
+T("celltype_pair_contract(tcgen05)", lambda: K.celltype_pair_contract(S, P, N_, 0, order=order2), reps=3)
+T("celltype_pair_contract(fp32)", lambda: K.celltype_pair_contract(S, P, N_, 1), reps=2)
 T("onehot_contract_csr", lambda: K.onehot_contract_csr(xu_indptr, xu_packed, len(genes), labels, c.C))
 rng = np.random.default_rng(0)
 table = K.to_device(rng.random((c.C * c.C, P)), torch.float64)
