@@ -222,10 +222,11 @@ def run_ours(args):
         a_h.X = Xh
         a_h.obsm["X_spatial"] = pin(a.obsm["X_spatial"])
         h2d = Xh.data.nbytes + Xh.indices.nbytes + Xh.indptr.nbytes + a_h.obsm["X_spatial"].nbytes
-        la.tl.prepareLRInteraction(a_h, lr, number_nearest_neighbors=k)
+        out = None
+        for _ in range(max(args.warmup, 3)):        # warm-up: page-locked staging buffers of both result generations
+            out = la.tl.prepareLRInteraction(a_h, lr, number_nearest_neighbors=k)
         barrier()
         e2e_t = []
-        out = None
         for _ in range(args.steps):
             flush.fill_(1.0)
             torch.cuda.synchronize()
@@ -283,7 +284,7 @@ def run_ours(args):
                        "sharding": f"LR pairs: {P} per GPU x {world} GPUs, graph replicated, no collective",
                        "l2": "512 MiB buffer written between timed iterations (outside the event bracket)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "ms_per_step": 1e3 * t_e2e / args.steps, "ms_each": [round(1e3 * t, 3) for t in e2e_t],
                     "call": "laris_b200.tl.prepareLRInteraction(adata, lr_df) -> AnnData with scipy CSR on the host"},
             "gpu_launches": int(launches), "wall_s_timed_region": wall, "clocks": clocks.summary(),
             "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
@@ -327,7 +328,7 @@ def extra_metrics(torch, a, c, state, engine, K):
     N_ = K.neighborhood_composition(lab_d, g2.idx, g2.w, C)
     ms, _ = timed(lambda: K.celltype_pair_contract(sm.S, P, N_, 0, order=g2.order), reps=3)
     out["celltype_contract_ms"] = ms
-    out["celltype_contract_impl"] = "tcgen05 (split bf16 x4, fp32 TMEM accumulation)"
+    out["celltype_contract_impl"] = "tcgen05 (bf16 hi/mid/lo operand split, 6 MMAs per k-step, fp32 TMEM accumulation)"
     out["celltype_contract_TFLOPs_algorithmic"] = 2.0 * n * P * C * C / ms / 1e9
     ms1, _ = timed(lambda: K.celltype_pair_contract(sm.S, P, N_, 1), reps=2)
     out["celltype_contract_cuda_core_ms"] = ms1

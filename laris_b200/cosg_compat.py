@@ -68,12 +68,14 @@ def index_by_gene(df, gene_key="names", score_key="scores", set_nan_to_zero=Fals
                                 column_delimiter=column_delimiter)
     prefix = f"{gene_key}{column_delimiter}"
     groups = [c[len(prefix):] for c in df.columns if str(c).startswith(prefix)]
-    all_names = pd.unique(np.concatenate([df[f"{prefix}{g}"].to_numpy(dtype=object) for g in groups]))
-    out = pd.DataFrame(np.nan, index=pd.Index(all_names), columns=groups, dtype=np.float64)
-    for g in groups:
-        nm = df[f"{prefix}{g}"].to_numpy(dtype=object)
-        sc = df[f"{score_key}{column_delimiter}{g}"].to_numpy(dtype=np.float64)
-        out.loc[nm, g] = sc
+    ng = len(groups)
+    nm = np.concatenate([df[f"{prefix}{g}"].to_numpy(dtype=object) for g in groups]) if ng else np.empty(0, object)
+    codes, all_names = pd.factorize(nm)                  # first-appearance order, one hash pass for all groups
+    vals = np.full((len(all_names), ng), np.nan)
+    rows = len(df)
+    for j, g in enumerate(groups):
+        vals[codes[j * rows:(j + 1) * rows], j] = df[f"{score_key}{column_delimiter}{g}"].to_numpy(dtype=np.float64)
+    out = pd.DataFrame(vals, index=pd.Index(all_names, dtype=object), columns=groups)
     if convert_negative_one_to_zero:
         out = out.mask(out == -1, 0.0)
     if set_nan_to_zero:

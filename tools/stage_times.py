@@ -22,6 +22,7 @@ lig = K.to_device(cols[inv[:P]].astype(np.int32), torch.int32); rec = K.to_devic
 labels = K.to_device(a.obs["CellTypes"].cat.codes.to_numpy().astype(np.int32), torch.int32)
 
 def T(name, fn, reps=5):
+    reps = int(os.environ.get("LARIS_REPS", reps))
     ev, wl = [], []
     for _ in range(reps):
         torch.cuda.synchronize()
