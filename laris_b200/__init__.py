@@ -14,4 +14,6 @@ def __getattr__(name):
         return importlib.import_module(".tools", __name__)
     if name in ("pp", "preprocessing"):
         return importlib.import_module(".preprocessing", __name__)
+    if name in ("dist", "engine", "synth"):
+        return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

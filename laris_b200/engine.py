@@ -308,7 +308,7 @@ def cosg_gene_scores(xu: ExpressionU, labels_d, C, n_c, mu, expressed_pct, remov
 
 
 # --------------------------------------------------------------- p-values ----
-def pvalue_counts(table, bg, active, n_perm, *, rng="philox", seed=0, draws=None):
+def pvalue_counts(table, bg, active, n_perm, *, rng="philox", seed=0, draws=None, t0=0):
     """Exceedance counts (K6).  ``table`` [groups,P] fp64 host, ``bg`` [P,nb] host."""
     t = K.to_device(np.ascontiguousarray(table, dtype=np.float64), torch.float64)
     b = K.to_device(np.ascontiguousarray(bg, dtype=np.int32), torch.int32)
@@ -318,7 +318,10 @@ def pvalue_counts(table, bg, active, n_perm, *, rng="philox", seed=0, draws=None
         if draws is None:
             raise ValueError("rng='numpy' needs host draws")
         d = K.to_device(np.ascontiguousarray(draws, dtype=np.uint8), torch.uint8)
-    ge, nz, both = K.pvalue_counts(t, b, n_perm, active=a, seed=seed, draws=d)
+    if n_perm == 0:
+        z = np.zeros(t.shape, dtype=np.int32)
+        return z, z.copy(), z.copy()
+    ge, nz, both = K.pvalue_counts(t, b, n_perm, active=a, seed=seed, draws=d, t0=t0)
     return ge.cpu().numpy(), nz.cpu().numpy(), both.cpu().numpy()
 
 

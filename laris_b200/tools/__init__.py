@@ -16,6 +16,7 @@ import torch
 
 from .. import _kernels as K
 from .. import _rng_compat, engine
+from .. import dist as _dist
 from .._anndata import make_anndata
 from . import _utils
 from ._utils import _log
@@ -85,26 +86,37 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
 
     # ---- step 1: spatial specificity (reference :459-490) ----
     _log(verbose, "\n--- Step 1: Calculating spatial specificity scores ---")
+    # multi-GPU: this rank holds a block of LR pairs (laris_b200.dist.prepare_sharded); per-pair results are
+    # all-gathered in global pair order, so everything from the ranking on is identical on every rank
+    shard = _dist.shard_of(lr_adata)
+    gather = (lambda x, axis=-1: x) if shard is None else (lambda x, axis=-1: _dist.all_gather_pairs(x, shard, axis))
+    own = slice(None) if shard is None else slice(shard.start, shard.stop)
     sm = _utils._scores_of(lr_adata)
     graph = engine.build_graph(_utils._coords(lr_adata, use_rep), n_nearest_neighbors, False, sigma)
     st = engine.observed_stats(sm, graph)
     sm.cache.update(ss=st[1], sum=st[3], nnz=st[4])
-    gsp = engine._cosine(st)
     rand_each, rng_state = engine.null_cosines(sm, graph, n_repeats, random_seed, rng)
+    st, rand_each = gather(st), gather(rand_each)
+    gsp = engine._cosine(st)
     random_gsp = np.mean(rand_each, axis=0)
     gsp_score = gsp - mu * random_gsp
-    lr_adata.var["LRSS_Target"] = gsp
-    lr_adata.var["LRSS_Random"] = random_gsp
-    lr_adata.var["LR_SpatialSpecificity"] = gsp_score
+    lr_adata.var["LRSS_Target"] = gsp[own]
+    lr_adata.var["LRSS_Random"] = random_gsp[own]
+    lr_adata.var["LR_SpatialSpecificity"] = gsp_score[own]
     # the QC column the ranking consumes (reference :493-504 via scanpy) + its cheap siblings
     n = lr_adata.shape[0]
-    lr_adata.var["n_cells_by_counts"] = st[4].astype(np.int64)
-    lr_adata.var["mean_counts"] = st[3] / n
-    lr_adata.var["pct_dropout_by_counts"] = 100.0 * (1.0 - st[4] / n)
-    lr_adata.var["total_counts"] = st[3]
+    lr_adata.var["n_cells_by_counts"] = st[4][own].astype(np.int64)
+    lr_adata.var["mean_counts"] = st[3][own] / n
+    lr_adata.var["pct_dropout_by_counts"] = 100.0 * (1.0 - st[4][own] / n)
+    lr_adata.var["total_counts"] = st[3][own]
 
     # ---- ranking (reference :499-526) ----
-    lr_var = lr_adata.var.sort_values(by="LR_SpatialSpecificity", ascending=False).copy()
+    if shard is None:
+        lr_var = lr_adata.var
+    else:
+        lr_var = pd.DataFrame({"LR_SpatialSpecificity": gsp_score, "n_cells_by_counts": st[4].astype(np.int64)},
+                              index=pd.Index(shard.names_global, dtype=object))
+    lr_var = lr_var.sort_values(by="LR_SpatialSpecificity", ascending=False).copy()
     n_cells_expressed = lr_var["n_cells_by_counts"].to_numpy()
     ranking = lr_var["LR_SpatialSpecificity"].to_numpy().copy()
     ranking[n_cells_expressed < n_cells_expressed_threshold] = np.min(ranking) - 0.001
@@ -134,7 +146,7 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
         n_permutations=n_permutations, chunk_size=chunk_size, prefilter_fdr=prefilter_fdr,
         prefilter_threshold=prefilter_threshold, score_threshold=score_threshold, spatial_weight=spatial_weight,
         use_conditional_pvalue=use_conditional_pvalue, rng=rng, random_seed=random_seed, rng_state=rng_state,
-        verbose=verbose, contract_impl=contract_impl)
+        verbose=verbose, contract_impl=contract_impl, shard=shard)
     _log(verbose, f"\nResults: {len(laris_lr)} LR pairs, {len(celltype_results):,} cell type combinations")
     return laris_lr, celltype_results
 

@@ -16,6 +16,7 @@ import torch
 
 from .. import _kernels as K
 from .. import _rng_compat, cosg_compat, engine
+from .. import dist as _dist
 
 # ---------------------------------------------------------------------------
 # device-resident score cache: prepareLRInteraction leaves S on the GPU so that
@@ -212,7 +213,7 @@ def _calculate_specificity_in_spatial_neighborhood(adata, lr_adata, groupby: str
                                                    number_nearest_neighbors: int = 10, mu: float = 100,
                                                    expressed_pct: float = 0.1, remove_lowly_expressed: bool = True,
                                                    return_by_group: bool = True, key_added=None,
-                                                   column_delimiter: str = "@@", contract_impl=None):
+                                                   column_delimiter: str = "@@", contract_impl=None, shard=None):
     """Specificity of every LR pair for every sender::receiver neighbourhood profile.
 
     Reference :726-977.  Stores ``lr_adata.uns[key_added]`` with the reference's
@@ -230,16 +231,21 @@ def _calculate_specificity_in_spatial_neighborhood(adata, lr_adata, groupby: str
     if ss is None:
         ss = engine.observed_stats(sm, graph)[1]
         sm.cache["ss"] = ss
-    raw, _ = engine.neighborhood_specificity(sm, K.to_device(codes, torch.int32), C, graph, mu, ss, contract_impl)
+    if shard is None:
+        raw, _ = engine.neighborhood_specificity(sm, K.to_device(codes, torch.int32), C, graph, mu, ss, contract_impl)
+        lr_names = np.asarray(lr_adata.var_names, dtype=object)
+    else:                       # cosines of this rank's pairs, gathered; the regularisation runs over a pair's C^2 row
+        _, cos = engine.neighborhood_specificity(sm, K.to_device(codes, torch.int32), C, graph, mu, ss, contract_impl)
+        raw = engine.cosg_regularise(_dist.all_gather_pairs(cos, shard, axis=0), mu)
+        lr_names = np.asarray(shard.names_global, dtype=object)
     pair_names = [f"{a}::{b}" for a in cats for b in cats]
     if key_added is None:
         key_added = "cosg"
-    frame, order = cosg_compat.ranked_frame(np.asarray(lr_adata.var_names, dtype=object), raw, pair_names,
-                                            column_delimiter)
+    frame, order = cosg_compat.ranked_frame(lr_names, raw, pair_names, column_delimiter)
     lr_adata.uns[key_added] = {"params": dict(groupby=groupby, method="COSG", mu=mu)}
     if return_by_group:
         lr_adata.uns[key_added]["COSG"] = frame
-    names_rec = np.rec.fromarrays([np.asarray(lr_adata.var_names, dtype=object)[order[:, j]] for j in range(C * C)],
+    names_rec = np.rec.fromarrays([lr_names[order[:, j]] for j in range(C * C)],
                                   dtype=[(nm, "O") for nm in pair_names])
     scores_rec = np.rec.fromarrays([raw[order[:, j], j].astype(np.float32) for j in range(C * C)],
                                    dtype=[(nm, "float32") for nm in pair_names])
@@ -249,7 +255,7 @@ def _calculate_specificity_in_spatial_neighborhood(adata, lr_adata, groupby: str
     return cosg_compat.iqr_log_normalize(table)
 
 
-def _prepare_background_interactions(lr_adata, n_nearest_neighbors: int = 30, leaf_size: int = 40):
+def _prepare_background_interactions(lr_adata, n_nearest_neighbors: int = 30, leaf_size: int = 40, shard=None):
     """30-NN of every LR pair in (mean, variance) space (reference :1013-1109).
 
     The column moments come from the device pass over S; the neighbour search
@@ -263,11 +269,15 @@ def _prepare_background_interactions(lr_adata, n_nearest_neighbors: int = 30, le
         st = engine.observed_stats(sm, graph)
         sm.cache.update(ss=st[1], sum=st[3], nnz=st[4])
     n = sm.n
-    mean = sm.cache["sum"] / n
-    var = sm.cache["ss"] / n - mean ** 2
+    csum, css, names = sm.cache["sum"], sm.cache["ss"], lr_adata.var_names
+    if shard is not None:
+        csum, css = _dist.all_gather_pairs(csum, shard), _dist.all_gather_pairs(css, shard)
+        names = pd.Index(shard.names_global, dtype=object)
+    mean = csum / n
+    var = css / n - mean ** 2
     feats = np.column_stack([mean, var])
     _, idx = KDTree(feats, leaf_size=leaf_size, metric="euclidean").query(feats, k=n_nearest_neighbors + 1)
-    return pd.DataFrame(idx[:, 1:], index=lr_adata.var_names, columns=range(n_nearest_neighbors))
+    return pd.DataFrame(idx[:, 1:], index=names, columns=range(n_nearest_neighbors))
 
 
 def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_rep_spatial: str = "X_spatial",
@@ -278,7 +288,7 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_r
                                        prefilter_threshold: float = 0.0, score_threshold: float = 1e-6,
                                        spatial_weight: float = 1.0, use_conditional_pvalue: bool = False, *,
                                        rng: str = "numpy", random_seed: int = 27, rng_state=None, verbose: bool = True,
-                                       contract_impl=None):
+                                       contract_impl=None, shard=None):
     """Sender/receiver cell-type table with permutation p-values and BH-FDR.
 
     Reference laris/tools/_utils.py:1113-1688; same arguments (``mask_threshold`` and
@@ -293,7 +303,7 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_r
     cats_arr = np.asarray(cats, dtype=object)
     n_c = np.bincount(codes, minlength=C)
     labels_d = K.to_device(codes, torch.int32)
-    lr_names = np.asarray(lr_adata.var_names, dtype=object)
+    lr_names = np.asarray(lr_adata.var_names if shard is None else shard.names_global, dtype=object)
     P = len(lr_names)
 
     # ---- step 1: ligand / receptor specificity (reference :1306) ----
@@ -309,6 +319,8 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_r
     sm = _scores_of(lr_adata)
     with np.errstate(invalid="ignore", divide="ignore"):
         frac_all = engine.celltype_fraction(sm, labels_d, C, n_c.astype(np.float64))          # [P, C]
+    if shard is not None:
+        frac_all = _dist.all_gather_pairs(frac_all, shard, axis=0)
 
     # ---- step 3: interaction scores, pair-major / receiver-major / sender fastest (:1351-1406) ----
     _log(verbose, f"\n--- Step 3: Computing interaction scores (spatial_weight={spatial_weight}) ---")
@@ -347,7 +359,7 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_r
     ctc = _calculate_specificity_in_spatial_neighborhood(
         adata, lr_adata, groupby=groupby, use_rep_spatial=use_rep_spatial,
         number_nearest_neighbors=number_nearest_neighbors, mu=mu, return_by_group=True, key_added="cosg_lr",
-        column_delimiter="@@", contract_impl=contract_impl)
+        column_delimiter="@@", contract_impl=contract_impl, shard=shard)
     ctc_cols = [f"{a}::{b}" for a in cats for b in cats]
     ctc_m = ctc.loc[lr_names[pair_id], ctc_cols].to_numpy(dtype=np.float64).reshape(npair, C, C)
     flat = flat * ctc_m[row_pair, row_send, row_recv]
@@ -370,7 +382,7 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_r
 
     # ---- step 5.1: background sets (:1507) ----
     _log(verbose, "\n--- Step 5.1: Preparing background interaction sets ---")
-    bg = _prepare_background_interactions(lr_adata, n_nearest_neighbors=n_nearest_neighbors).to_numpy()
+    bg = _prepare_background_interactions(lr_adata, n_nearest_neighbors=n_nearest_neighbors, shard=shard).to_numpy()
     nb = bg.shape[1]
 
     # ---- step 5.2: permutation p-values (:1518-1596) ----
@@ -394,7 +406,14 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_r
         _rng_compat.sync_global(rs)
     elif rng != "philox":
         raise ValueError(f"rng must be 'numpy' or 'philox', got {rng!r}")
-    ge, nz, both = engine.pvalue_counts(table, bg, active, n_permutations, rng=rng, seed=random_seed, draws=draws)
+    if shard is None:
+        ge, nz, both = engine.pvalue_counts(table, bg, active, n_permutations, rng=rng, seed=random_seed, draws=draws)
+    else:                       # permutations [t0, t1) on this rank; exceedance counts are integers, so the sum is exact
+        pb = _dist.perm_bounds(n_permutations, shard.world)
+        t0, t1 = int(pb[shard.rank]), int(pb[shard.rank + 1])
+        part = engine.pvalue_counts(table, bg, active, t1 - t0, rng=rng, seed=random_seed, t0=t0,
+                                    draws=None if draws is None else np.ascontiguousarray(draws[:, :, t0:t1]))
+        ge, nz, both = _dist.all_reduce_sum(np.stack(part).astype(np.int64))
     if use_conditional_pvalue:
         p_tab = np.ones_like(table)
         pos = table > 0
