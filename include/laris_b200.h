@@ -63,6 +63,25 @@ LARIS_API const char* laris_last_error(void);
 LARIS_API int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int include_self,
                     int32_t* out_idx, double* out_dist, int32_t* out_order, void* stream);
 
+/* ---------------------------------------------------------------- K1r ---
+ * Radius graph (north-star item 1; EXTENSION - the reference only ever calls kneighbors_graph,
+ * laris/tools/__init__.py:83, laris/tools/_utils.py:385,847).  Oracle:
+ * sklearn.neighbors.radius_neighbors_graph(mode='distance', include_self=...): every j with
+ * d^2(i,j) <= radius^2 (d^2 accumulated as in laris_knn_graph), self kept only when include_self.
+ * Two passes over the same uniform grid (cell edge >= radius):
+ *   count: counts [n] int64 row degrees (+ optional spatial processing order [n] int32);
+ *          the caller scans them into indptr (laris_exclusive_scan_i64)
+ *   fill:  indices [nnz] int32 column-sorted within a row (canonical CSR), dist [nnz] fp64
+ * Each pass synchronises once (bounding box). */
+LARIS_API int laris_radius_graph_count(const double* xy, int64_t n, int dim, double radius, int include_self,
+                                       int64_t* counts, int32_t* out_order, void* stream);
+LARIS_API int laris_radius_graph_fill(const double* xy, int64_t n, int dim, double radius, int include_self,
+                                      const int64_t* indptr, int32_t* indices, double* dist, void* stream);
+/* Variable-degree CSR rows -> fixed-degree rows idx/w_out [n*kmax] (kmax >= max degree): padding edges point
+ * at the row itself with weight 0, so every weighted neighbour sum downstream is unchanged. */
+LARIS_API int laris_csr_pad_rows(const int64_t* indptr, const int32_t* indices, const float* w, int64_t n, int kmax,
+                                 int32_t* idx, float* w_out, void* stream);
+
 /* w = 1/exp(d/s), s = sigma if sigma > 0 else mean(all m distances)/2.
  * Replaces the .data transforms at laris/tools/__init__.py:89 and
  * laris/tools/_utils.py:392, :853.  Either output may be NULL.

@@ -75,6 +75,33 @@ def decay_weights(dist, sigma=None, want64=False):
     return w32, w64, scale
 
 
+def radius_graph(xy, radius, include_self, want_order=True):
+    """K1r: (indptr int64[n+1], indices int32[nnz] column-sorted, dist fp64[nnz], order int32[n])."""
+    n, dim = xy.shape
+    dev = xy.device
+    counts = torch.empty(n, dtype=torch.int64, device=dev)
+    order = torch.empty(n, dtype=torch.int32, device=dev) if want_order else None
+    check(lib.laris_radius_graph_count(_ptr(xy, torch.float64), n, dim, float(radius), int(bool(include_self)), _ptr(counts),
+                                       _ptr(order), _stream()), "laris_radius_graph_count")
+    indptr = exclusive_scan(counts)
+    nnz = int(indptr[-1].item())
+    indices = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    dist = torch.empty(max(nnz, 1), dtype=torch.float64, device=dev)
+    check(lib.laris_radius_graph_fill(_ptr(xy, torch.float64), n, dim, float(radius), int(bool(include_self)), _ptr(indptr),
+                                      _ptr(indices), _ptr(dist), _stream()), "laris_radius_graph_fill")
+    return indptr, indices[:nnz], dist[:nnz], order
+
+
+def csr_pad_rows(indptr, indices, w, kmax):
+    """Fixed-degree rows (idx int32 [n,kmax], w fp32 [n,kmax]); padding = (own row, weight 0)."""
+    n = indptr.numel() - 1
+    idx = torch.empty((n, kmax), dtype=torch.int32, device=indptr.device)
+    wout = torch.empty((n, kmax), dtype=torch.float32, device=indptr.device)
+    check(lib.laris_csr_pad_rows(_ptr(indptr, torch.int64), indices.data_ptr(), w.data_ptr(), n, int(kmax), _ptr(idx),
+                                 _ptr(wout), _stream()), "laris_csr_pad_rows")
+    return idx, wout
+
+
 # ------------------------------------------------------ gene selection ----
 def exclusive_scan(counts):
     out = torch.empty(counts.numel() + 1, dtype=torch.int64, device=counts.device)

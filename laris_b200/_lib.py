@@ -26,6 +26,9 @@ SIGNATURES = {
     "laris_abi_version": [],
     "laris_knn_graph": [_p, _i64, _i, _i, _i, _p, _p, _p, _p],
     "laris_decay_weights": [_p, _i64, _d, _p, _p, _p, _p],
+    "laris_radius_graph_count": [_p, _i64, _i, _d, _i, _p, _p, _p],
+    "laris_radius_graph_fill": [_p, _i64, _i, _d, _i, _p, _p, _p, _p],
+    "laris_csr_pad_rows": [_p, _p, _p, _i64, _i, _p, _p, _p],
     "laris_csr_select_count": [_p, _p, _p, _i64, _p, _p, _p],
     "laris_csr_select_fill": [_p, _p, _p, _i64, _p, _p, _p, _p],
     "laris_exclusive_scan_i64": [_p, _i64, _p, _p],

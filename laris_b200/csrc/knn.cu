@@ -257,6 +257,70 @@ knn_search_kernel(int64_t n, GridSpec gs, int kq, int k, int include_self, const
     }
 }
 
+
+// ---------------------------------------------------------- radius graph --
+// K1r (extension; oracle: sklearn.neighbors.radius_neighbors_graph(mode='distance')): every point within
+// `radius` of the query, d^2 <= radius^2 with d^2 accumulated exactly as in the kNN search (sklearn compares
+// reduced distances, sklearn/neighbors/_binary_tree.pxi.tp query_radius).  The grid's cell edge is >= radius,
+// so the 3^dim block around the query's cell holds every candidate.  MODE 0 counts, MODE 1 writes the row
+// (column-sorted: a canonical CSR) at its indptr offset.
+template <int DIM, int MODE>
+__global__ void __launch_bounds__(128)
+radius_search_kernel(int64_t n, GridSpec gs, double r2, int include_self, const int32_t* __restrict__ cell_start,
+                     const int32_t* __restrict__ sorted_id, const int32_t* __restrict__ sorted_cell,
+                     const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
+                     int64_t* __restrict__ counts, const int64_t* __restrict__ indptr, int32_t* __restrict__ indices,
+                     double* __restrict__ dist) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const double qx = sx[q], qy = sy[q], qz = DIM == 3 ? sz[q] : 0.0;
+    const int32_t self = sorted_id[q];
+    const int c = sorted_cell[q];
+    const int gx = gs.g[0], gy = gs.g[1], gz = DIM == 3 ? gs.g[2] : 1;
+    const int cx = c % gx, cy = (c / gx) % gy, cz = DIM == 3 ? c / (gx * gy) : 0;
+    int64_t cnt = 0;
+    const int64_t base_out = MODE ? indptr[self] : 0;
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, gz - 1); ++z)
+        for (int y = max(cy - 1, 0); y <= min(cy + 1, gy - 1); ++y) {
+            const int64_t base = ((int64_t)z * gy + y) * gx;
+            const int ps = cell_start[base + max(cx - 1, 0)], pe = cell_start[base + min(cx + 1, gx - 1) + 1];
+            for (int p = ps; p < pe; ++p) {
+                const double dx = qx - sx[p], dy = qy - sy[p];
+                double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                if (DIM == 3) { const double dz = qz - sz[p]; d2 = __dadd_rn(d2, __dmul_rn(dz, dz)); }
+                const int32_t id = sorted_id[p];
+                if (d2 <= r2 && (include_self || id != self)) {
+                    if (MODE) {                                  // insertion by column id into the row written so far
+                        int64_t pos = base_out + cnt;
+                        while (pos > base_out && indices[pos - 1] > id) {
+                            indices[pos] = indices[pos - 1];
+                            dist[pos] = dist[pos - 1];
+                            --pos;
+                        }
+                        indices[pos] = id;
+                        dist[pos] = __dsqrt_rn(d2);
+                    }
+                    ++cnt;
+                }
+            }
+        }
+    if (!MODE) counts[self] = cnt;
+}
+
+// variable-degree CSR rows -> fixed-degree (ELL) rows for the gather kernels: padding edges point at the row itself
+// with weight 0, which adds nothing to any weighted sum
+__global__ void csr_pad_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                    const float* __restrict__ w, int64_t n, int kmax, int32_t* __restrict__ idx,
+                                    float* __restrict__ wout) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n * kmax) return;
+    const int64_t i = e / kmax;
+    const int j = (int)(e - i * kmax);
+    const int64_t s = indptr[i], deg = indptr[i + 1] - s;
+    idx[e] = j < deg ? indices[s + j] : (int32_t)i;
+    wout[e] = j < deg ? w[s + j] : 0.f;
+}
+
 // --------------------------------------------------------------- weights --
 constexpr int kSumBlocks = 592, kSumThreads = 256;
 
@@ -296,16 +360,21 @@ __global__ void decay_weights_kernel(const double* __restrict__ dist, int64_t m,
 
 using namespace laris;
 
-extern "C" int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int include_self, int32_t* out_idx,
-                               double* out_dist, int32_t* out_order, void* stream_) {
-    cudaStream_t st = (cudaStream_t)stream_;
-    LARIS_CHECK_ARG(xy && out_idx && out_dist, "laris_knn_graph: null pointer");
-    LARIS_CHECK_ARG(dim == 2 || dim == 3, "laris_knn_graph: dim must be 2 or 3 (got %d)", dim);
-    const int kq = include_self ? k : k + 1;
-    LARIS_CHECK_ARG(k >= 1 && kq <= 64, "laris_knn_graph: k out of range (k=%d, limit 64 incl. self)", k);
-    LARIS_CHECK_ARG(n >= kq && n < (int64_t)INT32_MAX, "laris_knn_graph: need k+1 <= n < 2^31 (n=%lld)", (long long)n);
+// ------------------------------------------------------------ point grid --
+// Everything the searches need: the grid shape and the cell-sorted copies of the points.
+struct PointGrid {
+    GridSpec gs;
+    int64_t ncell = 0;
+    Scratch<int32_t> cell_of, counts, cell_start, fill, sorted_id, sorted_cell;
+    Scratch<double> sx, sy, sz;
+    explicit PointGrid(cudaStream_t st)
+        : cell_of(st), counts(st), cell_start(st), fill(st), sorted_id(st), sorted_cell(st), sx(st), sy(st), sz(st) {}
+};
 
-    // bounding box (one host sync: the grid shape depends on it)
+// Bins the points on a uniform grid of about `per_cell` points per cell whose cell edge is at least `min_h`
+// (one host sync: the grid shape depends on the bounding box).
+static int build_point_grid(const double* xy, int64_t n, int dim, double per_cell, double min_h, cudaStream_t st,
+                            PointGrid& G, const char* who) {
     const int nb = kNumSMs * 2;
     Scratch<double> part(st), box_d(st);
     LARIS_CUDA(part.alloc(nb * 6));
@@ -318,20 +387,20 @@ extern "C" int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int 
     LARIS_CUDA(cudaMemcpyAsync(box, box_d.p, sizeof(box), cudaMemcpyDeviceToHost, st));
     LARIS_CUDA(cudaStreamSynchronize(st));
 
-    GridSpec gs;
+    GridSpec& gs = G.gs;
     gs.dim = dim;
     double ext[3] = {0, 0, 0}, vol = 1.0;
     int nz_dims = 0;
     for (int a = 0; a < dim; ++a) {
-        LARIS_CHECK_ARG(isfinite(box[a]) && isfinite(box[3 + a]), "laris_knn_graph: non-finite coordinates");
+        LARIS_CHECK_ARG(isfinite(box[a]) && isfinite(box[3 + a]), "%s: non-finite coordinates", who);
         gs.lo[a] = box[a];
         ext[a] = box[3 + a] - box[a];
         if (ext[a] > 0) { vol *= ext[a]; ++nz_dims; }
     }
     for (int a = dim; a < 3; ++a) { gs.lo[a] = 0; gs.g[a] = 1; }
-    const double per_cell = 2.5;
     double h = nz_dims ? pow(vol * per_cell / (double)n, 1.0 / nz_dims) : 1.0;
     if (!(h > 0) || !isfinite(h)) h = 1.0;
+    if (h < min_h) h = min_h;
     int64_t ncell;
     for (;;) {                                         // keep the grid within int32 / memory limits
         ncell = 1;
@@ -346,32 +415,69 @@ extern "C" int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int 
     }
     gs.h = h;
     gs.inv_h = 1.0 / h;
+    G.ncell = ncell;
 
-    Scratch<int32_t> cell_of(st), counts(st), cell_start(st), fill(st), sorted_id(st), sorted_cell(st);
-    Scratch<double> sx(st), sy(st), sz(st);
-    LARIS_CUDA(cell_of.alloc(n));
-    LARIS_CUDA(counts.alloc(ncell));
-    LARIS_CUDA(cell_start.alloc(ncell + 1));
-    LARIS_CUDA(fill.alloc(ncell));
-    LARIS_CUDA(sorted_id.alloc(n));
-    LARIS_CUDA(sorted_cell.alloc(n));
-    LARIS_CUDA(sx.alloc(n));
-    LARIS_CUDA(sy.alloc(n));
-    LARIS_CUDA(sz.alloc(dim == 3 ? n : 1));
-    LARIS_CUDA(cudaMemsetAsync(counts.p, 0, ncell * sizeof(int32_t), st));
-    LARIS_CUDA(cudaMemsetAsync(fill.p, 0, ncell * sizeof(int32_t), st));
+    LARIS_CUDA(G.cell_of.alloc(n));
+    LARIS_CUDA(G.counts.alloc(ncell));
+    LARIS_CUDA(G.cell_start.alloc(ncell + 1));
+    LARIS_CUDA(G.fill.alloc(ncell));
+    LARIS_CUDA(G.sorted_id.alloc(n));
+    LARIS_CUDA(G.sorted_cell.alloc(n));
+    LARIS_CUDA(G.sx.alloc(n));
+    LARIS_CUDA(G.sy.alloc(n));
+    LARIS_CUDA(G.sz.alloc(dim == 3 ? n : 1));
+    LARIS_CUDA(cudaMemsetAsync(G.counts.p, 0, ncell * sizeof(int32_t), st));
+    LARIS_CUDA(cudaMemsetAsync(G.fill.p, 0, ncell * sizeof(int32_t), st));
     const int T = 256;
     const unsigned gn = (unsigned)ceil_div(n, T), gc = (unsigned)ceil_div(ncell, T);
-    cell_count_kernel<<<gn, T, 0, st>>>(xy, n, gs, cell_of.p, counts.p);
+    cell_count_kernel<<<gn, T, 0, st>>>(xy, n, gs, G.cell_of.p, G.counts.p);
     LARIS_LAUNCH_CHECK();
-    int rc = exclusive_scan<int32_t>(counts.p, ncell, cell_start.p, st);
+    int rc = exclusive_scan<int32_t>(G.counts.p, ncell, G.cell_start.p, st);
     if (rc) return rc;
-    cell_scatter_kernel<<<gn, T, 0, st>>>(cell_of.p, n, cell_start.p, fill.p, sorted_id.p);
+    cell_scatter_kernel<<<gn, T, 0, st>>>(G.cell_of.p, n, G.cell_start.p, G.fill.p, G.sorted_id.p);
     LARIS_LAUNCH_CHECK();
-    cell_sort_kernel<<<gc, T, 0, st>>>(cell_start.p, ncell, sorted_id.p);
+    cell_sort_kernel<<<gc, T, 0, st>>>(G.cell_start.p, ncell, G.sorted_id.p);
     LARIS_LAUNCH_CHECK();
-    gather_sorted_kernel<<<gn, T, 0, st>>>(xy, n, dim, sorted_id.p, cell_of.p, sx.p, sy.p, sz.p, sorted_cell.p);
+    gather_sorted_kernel<<<gn, T, 0, st>>>(xy, n, dim, G.sorted_id.p, G.cell_of.p, G.sx.p, G.sy.p, G.sz.p, G.sorted_cell.p);
     LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
+// cell segments re-dealt in strip order -> the processing order handed to the gather kernels
+static int emit_strip_order(const PointGrid& G, int64_t n, int32_t* out_order, cudaStream_t st) {
+    const GridSpec& gs = G.gs;
+    const int T = 256;
+    const unsigned gn = (unsigned)ceil_div(n, T), gc = (unsigned)ceil_div(G.ncell, T);
+    const int64_t nstrip = ceil_div(gs.g[1], kStripH);
+    const int64_t nslot = (int64_t)gs.g[2] * nstrip * kStripH * gs.g[0];
+    Scratch<int32_t> slot_count(st), slot_start(st);
+    LARIS_CUDA(slot_count.alloc(nslot));
+    LARIS_CUDA(slot_start.alloc(nslot + 1));
+    LARIS_CUDA(cudaMemsetAsync(slot_count.p, 0, nslot * sizeof(int32_t), st));
+    strip_count_kernel<<<gc, T, 0, st>>>(G.cell_start.p, G.ncell, gs, slot_count.p);
+    LARIS_LAUNCH_CHECK();
+    int rc = exclusive_scan<int32_t>(slot_count.p, nslot, slot_start.p, st);
+    if (rc) return rc;
+    strip_order_kernel<<<gn, T, 0, st>>>(G.cell_start.p, G.sorted_id.p, G.sorted_cell.p, n, gs, slot_start.p, out_order);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
+extern "C" int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int include_self, int32_t* out_idx,
+                               double* out_dist, int32_t* out_order, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    LARIS_CHECK_ARG(xy && out_idx && out_dist, "laris_knn_graph: null pointer");
+    LARIS_CHECK_ARG(dim == 2 || dim == 3, "laris_knn_graph: dim must be 2 or 3 (got %d)", dim);
+    const int kq = include_self ? k : k + 1;
+    LARIS_CHECK_ARG(k >= 1 && kq <= 64, "laris_knn_graph: k out of range (k=%d, limit 64 incl. self)", k);
+    LARIS_CHECK_ARG(n >= kq && n < (int64_t)INT32_MAX, "laris_knn_graph: need k+1 <= n < 2^31 (n=%lld)", (long long)n);
+
+    PointGrid G(st);
+    int rc = build_point_grid(xy, n, dim, 2.5, 0.0, st, G, "laris_knn_graph");
+    if (rc) return rc;
+    const GridSpec gs = G.gs;
+    Scratch<int32_t>&cell_start = G.cell_start, &sorted_id = G.sorted_id, &sorted_cell = G.sorted_cell;
+    Scratch<double>&sx = G.sx, &sy = G.sy, &sz = G.sz;
 
     const unsigned gq = (unsigned)ceil_div(n, 128);
 #define LARIS_KNN_LAUNCH(KMAX, DIM)                                                                          \
@@ -384,20 +490,61 @@ extern "C" int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int 
     }
 #undef LARIS_KNN_LAUNCH
     LARIS_LAUNCH_CHECK();
-    if (out_order) {                                   // cell segments re-dealt in strip order
-        const int64_t nstrip = ceil_div(gs.g[1], kStripH);
-        const int64_t nslot = (int64_t)gs.g[2] * nstrip * kStripH * gs.g[0];
-        Scratch<int32_t> slot_count(st), slot_start(st);
-        LARIS_CUDA(slot_count.alloc(nslot));
-        LARIS_CUDA(slot_start.alloc(nslot + 1));
-        LARIS_CUDA(cudaMemsetAsync(slot_count.p, 0, nslot * sizeof(int32_t), st));
-        strip_count_kernel<<<gc, T, 0, st>>>(cell_start.p, ncell, gs, slot_count.p);
-        LARIS_LAUNCH_CHECK();
-        rc = exclusive_scan<int32_t>(slot_count.p, nslot, slot_start.p, st);
+    if (out_order) {
+        rc = emit_strip_order(G, n, out_order, st);
         if (rc) return rc;
-        strip_order_kernel<<<gn, T, 0, st>>>(cell_start.p, sorted_id.p, sorted_cell.p, n, gs, slot_start.p, out_order);
-        LARIS_LAUNCH_CHECK();
     }
+    return LARIS_OK;
+}
+
+
+static int radius_graph_pass(const double* xy, int64_t n, int dim, double radius, int include_self, int mode,
+                             int64_t* counts, const int64_t* indptr, int32_t* indices, double* dist, int32_t* out_order,
+                             cudaStream_t st, const char* who) {
+    LARIS_CHECK_ARG(xy && n >= 1 && n < (int64_t)INT32_MAX, "%s: bad arguments (n=%lld)", who, (long long)n);
+    LARIS_CHECK_ARG(dim == 2 || dim == 3, "%s: dim must be 2 or 3 (got %d)", who, dim);
+    LARIS_CHECK_ARG(radius > 0.0 && isfinite(radius), "%s: radius must be positive and finite", who);
+    PointGrid G(st);
+    // cell edge >= radius (plus rounding slack in the cell assignment) so that one ring of cells is enough
+    int rc = build_point_grid(xy, n, dim, 2.5, radius * (1.0 + 1e-9), st, G, who);
+    if (rc) return rc;
+    const unsigned gq = (unsigned)ceil_div(n, 128);
+    const double r2 = radius * radius;
+#define LARIS_RADIUS_LAUNCH(DIM, MODE)                                                                              \
+    radius_search_kernel<DIM, MODE><<<gq, 128, 0, st>>>(n, G.gs, r2, include_self, G.cell_start.p, G.sorted_id.p,   \
+                                                        G.sorted_cell.p, G.sx.p, G.sy.p, G.sz.p, counts, indptr,    \
+                                                        indices, dist)
+    if (dim == 2) { if (mode) LARIS_RADIUS_LAUNCH(2, 1); else LARIS_RADIUS_LAUNCH(2, 0); }
+    else { if (mode) LARIS_RADIUS_LAUNCH(3, 1); else LARIS_RADIUS_LAUNCH(3, 0); }
+#undef LARIS_RADIUS_LAUNCH
+    LARIS_LAUNCH_CHECK();
+    if (out_order) {
+        rc = emit_strip_order(G, n, out_order, st);
+        if (rc) return rc;
+    }
+    return LARIS_OK;
+}
+
+extern "C" int laris_radius_graph_count(const double* xy, int64_t n, int dim, double radius, int include_self,
+                                        int64_t* counts, int32_t* out_order, void* stream) {
+    LARIS_CHECK_ARG(counts, "laris_radius_graph_count: null pointer");
+    return radius_graph_pass(xy, n, dim, radius, include_self, 0, counts, nullptr, nullptr, nullptr, out_order,
+                             (cudaStream_t)stream, "laris_radius_graph_count");
+}
+
+extern "C" int laris_radius_graph_fill(const double* xy, int64_t n, int dim, double radius, int include_self,
+                                       const int64_t* indptr, int32_t* indices, double* dist, void* stream) {
+    LARIS_CHECK_ARG(indptr && indices && dist, "laris_radius_graph_fill: null pointer");
+    return radius_graph_pass(xy, n, dim, radius, include_self, 1, nullptr, indptr, indices, dist, nullptr,
+                             (cudaStream_t)stream, "laris_radius_graph_fill");
+}
+
+extern "C" int laris_csr_pad_rows(const int64_t* indptr, const int32_t* indices, const float* w, int64_t n, int kmax,
+                                  int32_t* idx, float* w_out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LARIS_CHECK_ARG(indptr && indices && w && idx && w_out && n >= 1 && kmax >= 1, "laris_csr_pad_rows: bad arguments");
+    csr_pad_rows_kernel<<<(unsigned)ceil_div(n * kmax, 256), 256, 0, st>>>(indptr, indices, w, n, kmax, idx, w_out);
+    LARIS_LAUNCH_CHECK();
     return LARIS_OK;
 }
 

@@ -37,9 +37,15 @@ class SpatialGraph:
     def k(self):
         return self.idx.shape[1]
 
+    csr: tuple | None = None   # radius graphs: (indptr int64, indices int32, dist fp64, w64 fp64) on the device
+
     def to_scipy(self):
         """The reference's ``cellxcell`` (n x n CSR, fp64 weights, int64 indices)."""
         n, k = self.idx.shape
+        if self.csr is not None:
+            indptr, indices, _, w64 = self.csr
+            return sp.csr_matrix((w64.cpu().numpy(), indices.cpu().numpy().astype(np.int64), indptr.cpu().numpy()),
+                                 shape=(n, n))
         return sp.csr_matrix((self.w64.cpu().numpy().ravel(), self.idx.cpu().numpy().astype(np.int64).ravel(),
                               np.arange(0, n * k + 1, k, dtype=np.int64)), shape=(n, n))
 
@@ -52,6 +58,24 @@ def build_graph(xy, k, include_self, sigma=None) -> SpatialGraph:
     idx, dist, order = K.knn_graph(xy_d.contiguous(), int(k), include_self)
     w32, w64, scale = K.decay_weights(dist, sigma, want64=True)
     return SpatialGraph(idx, dist, w32, w64, order, scale, bool(include_self))
+
+
+def build_radius_graph(xy, radius, include_self, sigma=None) -> SpatialGraph:
+    """Radius graph + decay weights (K1r; extension, oracle sklearn.neighbors.radius_neighbors_graph).
+
+    The variable-degree CSR is kept in ``csr``; ``idx``/``w`` hold the same rows padded to the maximum degree with
+    (own row, weight 0) edges, which is the fixed-degree layout every gather kernel takes.  ``sigma=None`` uses
+    s = mean(stored distances)/2, the reference's rule for its kNN graphs."""
+    xy_d = xy if torch.is_tensor(xy) else K.to_device(np.asarray(xy, dtype=np.float64), torch.float64)
+    if xy_d.dim() != 2 or xy_d.shape[1] not in (2, 3):
+        raise ValueError(f"spatial coordinates must be n x 2 or n x 3, got {tuple(xy_d.shape)}")
+    indptr, indices, dist, order = K.radius_graph(xy_d.contiguous(), float(radius), include_self)
+    if dist.numel() == 0:
+        raise ValueError(f"radius={radius} leaves every cell without a neighbour")
+    w32, w64, scale = K.decay_weights(dist, sigma, want64=True)
+    kmax = max(int((indptr[1:] - indptr[:-1]).max().item()), 1)
+    idx, w = K.csr_pad_rows(indptr, indices, w32, kmax)
+    return SpatialGraph(idx, None, w, None, order, scale, bool(include_self), (indptr, indices, dist, w64))
 
 
 # ----------------------------------------------------------- expression ----

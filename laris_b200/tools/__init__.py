@@ -30,7 +30,7 @@ def _lr_gene_indices(adata, lr_df):
 
 
 def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_rep_spatial: str = "X_spatial", *,
-                         dtype=np.float32, layout: str = "auto"):
+                         dtype=np.float32, layout: str = "auto", radius=None):
     """Per-cell diffused ligand-receptor scores as a new AnnData (cells x LR pairs).
 
     Reference laris/tools/__init__.py:29-119: kNN graph incl. self with
@@ -40,11 +40,16 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     ``var_names`` = "ligand::receptor".  The dense scores stay resident on the GPU
     for a following ``runLARIS`` call.  ``layout`` picks the device layout of the LR-gene
     expression ('dense' rows, packed 'sparse' rows, or 'auto' by the fraction of non-zeros);
-    both give the same result.
+    both give the same result.  ``radius`` (extension, not in the reference): use the radius graph
+    {j: |x_i - x_j| <= radius}, self included, instead of the kNN graph; weights follow the same
+    1/exp(d/(mean(d)/2)) rule over the stored distances.
     """
     xy = _utils._coords(adata, use_rep_spatial)
     lig_g, rec_g = _lr_gene_indices(adata, lr_df)
-    graph = engine.build_graph(xy, number_nearest_neighbors, True, None)
+    if radius is None:
+        graph = engine.build_graph(xy, number_nearest_neighbors, True, None)
+    else:
+        graph = engine.build_radius_graph(xy, radius, True, None)
     xu, lig_c, rec_c = engine.select_lr_genes(adata.X, lig_g, rec_g, layout=layout)
     sm = engine.lr_scores(xu, graph, lig_c, rec_c)
     X = engine.scores_to_csr(sm, dtype)

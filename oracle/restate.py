@@ -75,6 +75,28 @@ def knn_bruteforce(xy, k, include_self, block=2048):
     return ind[keep].reshape(n, k), dist[keep].reshape(n, k)
 
 
+def radius_graph(xy, radius, include_self):
+    """EXTENSION oracle (north-star item 1; the reference has no radius graph, SURVEY.md "gaps"):
+    ``sklearn.neighbors.radius_neighbors_graph(mode='distance')`` as canonical CSR (column-sorted, explicit
+    zero distance on the diagonal when ``include_self``).  Returns ``(indptr, indices, dist)``."""
+    from sklearn.neighbors import radius_neighbors_graph
+    A = sp.csr_matrix(radius_neighbors_graph(np.asarray(xy, dtype=np.float64), radius, mode="distance",
+                                             include_self=bool(include_self)))
+    A.sort_indices()
+    return A.indptr.astype(np.int64), A.indices.astype(np.int64), A.data.astype(np.float64)
+
+
+def lr_scores_csr_graph(X, W, lig_idx, rec_idx):
+    """``lr_scores`` for an arbitrary n x n CSR weight matrix W (same arithmetic, laris/tools/__init__.py:91-117)."""
+    D = (W @ sp.csr_matrix(X)).tocsc()
+    Xc = sp.csc_matrix(X)
+    mask = (Xc[:, lig_idx] != 0).maximum(Xc[:, rec_idx] != 0)
+    S = D[:, lig_idx].multiply(D[:, rec_idx]).multiply(mask).tocsr()
+    S.eliminate_zeros()
+    S.sort_indices()
+    return S
+
+
 def decay_weights(dist, sigma=None):
     """w = 1/exp(d/s); s = mean(all stored d)/2 or the constant ``sigma``.
 

@@ -572,3 +572,67 @@ def test_full_size_properties_config2(dev):
     n1, _ = engine.null_cosines(sm, g, 2, 27, "philox")
     n2, _ = engine.null_cosines(sm, g, 2, 27, "philox")
     assert np.array_equal(n1, n2) and (np.abs(n1) <= 1 + 1e-9).all()
+
+
+# ----------------------------------------------------------------- K1r ----
+@pytest.mark.parametrize("kind,n,dim,radius", [("uniform", 20000, 2, 18.0), ("hex", 10000, 2, 105.0), ("bins", 10000, 2, 1.05),
+                                               ("clustered", 6000, 2, 0.5), ("uniform", 6000, 3, 60.0),
+                                               ("line", 3000, 2, 1.0), ("uniform", 40, 2, 1e-3)])
+@pytest.mark.parametrize("include_self", [True, False])
+def test_radius_graph_bit_exact(dev, kind, n, dim, radius, include_self):
+    """K1r against sklearn.radius_neighbors_graph: identical CSR structure and bit-identical distances."""
+    from laris_b200 import _kernels as K
+    from oracle import restate as R
+    xy = _coords(kind, n, seed=n + 7, dim=dim)
+    indptr, indices, dist, order = K.radius_graph(K.to_device(xy, torch.float64), radius, include_self)
+    r_indptr, r_indices, r_dist = R.radius_graph(xy, radius, include_self)
+    assert np.array_equal(indptr.cpu().numpy(), r_indptr)
+    assert np.array_equal(indices.cpu().numpy(), r_indices)
+    assert np.array_equal(dist.cpu().numpy(), r_dist)
+    assert np.array_equal(np.sort(order.cpu().numpy()), np.arange(n))
+
+
+def test_radius_graph_scores_match_oracle(dev):
+    """prepareLRInteraction(radius=...) == W X gather-product-mask with the sklearn radius graph as W."""
+    import laris_b200 as la
+    from laris_b200 import engine
+    from laris_b200.synth import make_dataset
+    from oracle import restate as R
+    a, lr, c = make_dataset(5, n=6000, G=200, G_u=120, P=90, C=4)        # bin lattice, pitch 1
+    radius = 1.5                                                           # 8-neighbourhood + self, ragged at the border
+    xy = a.obsm["X_spatial"]
+    g = engine.build_radius_graph(xy, radius, True)
+    indptr, indices, dist = R.radius_graph(xy, radius, True)
+    w = R.decay_weights(dist)                                              # s = mean(stored d)/2, zeros on the diagonal included
+    deg = np.diff(indptr)
+    assert g.k == deg.max() and deg.min() < deg.max()
+    A = g.to_scipy()
+    assert np.array_equal(A.indptr, indptr) and np.array_equal(A.indices, indices) and np.allclose(A.data, w, rtol=1e-12)
+    # padded rows: own row with weight 0
+    gi, gw = g.idx.cpu().numpy(), g.w.cpu().numpy()
+    short = np.flatnonzero(deg < deg.max())[:50]
+    for i in short:
+        assert (gi[i, deg[i]:] == i).all() and (gw[i, deg[i]:] == 0).all()
+    out = la.tl.prepareLRInteraction(a, lr, radius=radius)
+    W = sp.csr_matrix((w, indices, indptr), shape=(c.n, c.n))
+    S = R.lr_scores_csr_graph(a.X, W, R.gene_index(a.var_names, lr["ligand"]), R.gene_index(a.var_names, lr["receptor"]))
+    X = sp.csr_matrix(out.X)
+    X.sort_indices()
+    assert np.array_equal(X.indptr, S.indptr) and np.array_equal(X.indices, S.indices)
+    assert np.allclose(X.data, S.data, rtol=RTOL, atol=0)
+    # the neighbourhood composition takes the same padded rows
+    labels = a.obs["CellTypes"].cat.codes.to_numpy().astype(np.int32)
+    from laris_b200 import _kernels as K
+    N = K.neighborhood_composition(K.to_device(labels, torch.int32), g.idx, g.w, c.C).cpu().numpy()
+    onehot = sp.csr_matrix((np.ones(c.n), (labels, np.arange(c.n))), shape=(c.C, c.n))
+    assert np.allclose(N.T, (onehot @ W.T).toarray(), rtol=1e-5, atol=1e-7)
+
+
+def test_radius_graph_argument_errors(dev):
+    from laris_b200 import engine
+    from laris_b200._lib import LarisError
+    xy = _coords("uniform", 100)
+    with pytest.raises(LarisError, match="radius must be positive"):
+        engine.build_radius_graph(xy, 0.0, True)
+    with pytest.raises(ValueError, match="without a neighbour"):
+        engine.build_radius_graph(xy, 1e-9, False)

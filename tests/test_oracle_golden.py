@@ -119,3 +119,19 @@ def test_philox_mode_null_is_a_valid_null(golden):
     _, rand_p, _ = R.spatial_specificity(S, ind, w, 3, 27, 1.0, "philox")
     assert np.isfinite(rand_p).all() and (np.abs(rand_p) <= 1 + 1e-12).all()
     assert abs(rand_p.mean() - golden["rand"].mean()) < 0.02
+
+
+def test_radius_graph_oracle_is_the_plain_definition():
+    """Extension oracle (K1r): sklearn's radius graph equals the brute-force definition d <= r on tie-free points."""
+    from oracle import restate as R
+    rng = np.random.default_rng(5)
+    xy = rng.random((400, 2)) * 50.0
+    for include_self in (True, False):
+        indptr, indices, dist = R.radius_graph(xy, 6.0, include_self)
+        d = np.sqrt(((xy[:, None, :] - xy[None, :, :]) ** 2).sum(-1))
+        adj = d <= 6.0
+        if not include_self:
+            np.fill_diagonal(adj, False)
+        assert np.array_equal(np.diff(indptr), adj.sum(1))
+        rows = np.repeat(np.arange(400), np.diff(indptr))
+        assert adj[rows, indices].all() and np.allclose(dist, d[rows, indices], rtol=1e-12, atol=1e-12)
