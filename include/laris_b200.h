@@ -146,6 +146,23 @@ LARIS_API int laris_diffuse_lr_score_dense(const float* Xd, int64_t ldX, const i
                                  const int32_t* lig, const int32_t* rec, int32_t P,
                                  float* S, int64_t ldS, int64_t* row_nnz, void* stream);
 
+/* Multi-subunit complexes (north-star item 3; EXTENSION - the reference has no complex handling and scores
+ * one LR row per subunit pair, docs/notebooks/04_LARIS_tutorial.html:743,767).  Same kernels and arguments as
+ * laris_diffuse_lr_score / laris_diffuse_lr_score_dense, plus a complex table: complex c owns the packed
+ * column cx_vcol[c] (a column no gene maps to) and is aggregated from the subunit columns
+ * cx_cols[cx_ptr[c] .. cx_ptr[c+1]) after the diffusion: rule 0 = min over subunits, rule 1 = geometric mean
+ * of max(v,0); it is "expressed" in a cell only if every subunit is.  lig/rec may name virtual columns. */
+LARIS_API int laris_diffuse_lr_score_complex(const int64_t* xu_indptr, const int64_t* xu_packed, int64_t n, int32_t G_u,
+                           const int32_t* idx, const float* w, int k, const int32_t* order,
+                           const int32_t* lig, const int32_t* rec, int32_t P,
+                           float* S, int64_t ldS, int64_t* row_nnz, const int32_t* cx_ptr, const int32_t* cx_cols,
+                           const int32_t* cx_vcol, int32_t n_complex, int32_t rule, void* stream);
+LARIS_API int laris_diffuse_lr_score_dense_complex(const float* Xd, int64_t ldX, const int32_t* neg_flag, int64_t n,
+                           int32_t G_u, const int32_t* idx, const float* w, int k, const int32_t* order,
+                           const int32_t* lig, const int32_t* rec, int32_t P, float* S, int64_t ldS, int64_t* row_nnz,
+                           const int32_t* cx_ptr, const int32_t* cx_cols, const int32_t* cx_vcol, int32_t n_complex,
+                           int32_t rule, void* stream);
+
 /* HOST helper (all pointers are host memory, no device work): number the Xu columns so that
  * laris_diffuse_lr_score's 32-lane gathers of D[lig[p]] / D[rec[p]] are free of shared-memory
  * bank conflicts.  lig, rec [P] are gene indices in [0,G_u); column_of [G_u] receives the column

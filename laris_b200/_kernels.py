@@ -139,17 +139,25 @@ def padded_ld(P):
     return (P + 7) // 8 * 8
 
 
-def diffuse_lr_score(xu_indptr, xu_packed, G_u, idx, w, order, lig, rec, want_row_nnz=True):
+def _cx_args(cx):
+    """(ptr, cols, vcol, n_complex, rule) C arguments of a complex table (device int32 tensors) or five nulls."""
+    if cx is None:
+        return None, None, None, 0, 0
+    ptr, cols, vcol, rule = cx
+    return _ptr(ptr, torch.int32), _ptr(cols, torch.int32), _ptr(vcol, torch.int32), int(vcol.numel()), int(rule)
+
+
+def diffuse_lr_score(xu_indptr, xu_packed, G_u, idx, w, order, lig, rec, want_row_nnz=True, cx=None):
     n, k = idx.shape
     P = lig.numel()
     ld = padded_ld(P)
     S = torch.empty((n, ld), dtype=torch.float32, device=idx.device)
     row_nnz = torch.empty(n, dtype=torch.int64, device=idx.device) if want_row_nnz else None
     packed_ptr = xu_packed.data_ptr() if xu_packed.numel() else _ptr(torch.zeros(1, dtype=torch.int64, device=idx.device))
-    check(lib.laris_diffuse_lr_score(_ptr(xu_indptr, torch.int64), packed_ptr, n, G_u, _ptr(idx, torch.int32),
-                                     _ptr(w, torch.float32), k, _ptr(order, torch.int32) if order is not None else None,
-                                     _ptr(lig, torch.int32), _ptr(rec, torch.int32), P, _ptr(S), ld, _ptr(row_nnz),
-                                     _stream()), "laris_diffuse_lr_score")
+    check(lib.laris_diffuse_lr_score_complex(_ptr(xu_indptr, torch.int64), packed_ptr, n, G_u, _ptr(idx, torch.int32),
+                                             _ptr(w, torch.float32), k, _ptr(order, torch.int32) if order is not None else None,
+                                             _ptr(lig, torch.int32), _ptr(rec, torch.int32), P, _ptr(S), ld, _ptr(row_nnz),
+                                             *_cx_args(cx), _stream()), "laris_diffuse_lr_score")
     return S, row_nnz
 
 
@@ -165,17 +173,17 @@ def csr_select_dense(indptr, indices, data, gene_map, n_columns):
     return Xd, neg
 
 
-def diffuse_lr_score_dense(Xd, neg_flag, G_u, idx, w, order, lig, rec, want_row_nnz=True):
+def diffuse_lr_score_dense(Xd, neg_flag, G_u, idx, w, order, lig, rec, want_row_nnz=True, cx=None):
     n, k = idx.shape
     P = lig.numel()
     ld = padded_ld(P)
     S = torch.empty((n, ld), dtype=torch.float32, device=idx.device)
     row_nnz = torch.empty(n, dtype=torch.int64, device=idx.device) if want_row_nnz else None
-    check(lib.laris_diffuse_lr_score_dense(_ptr(Xd, torch.float32), Xd.shape[1], _ptr(neg_flag, torch.int32) if neg_flag is not None else None,
-                                           n, G_u, _ptr(idx, torch.int32), _ptr(w, torch.float32), k,
-                                           _ptr(order, torch.int32) if order is not None else None,
-                                           _ptr(lig, torch.int32), _ptr(rec, torch.int32), P, _ptr(S), ld, _ptr(row_nnz),
-                                           _stream()), "laris_diffuse_lr_score_dense")
+    check(lib.laris_diffuse_lr_score_dense_complex(
+        _ptr(Xd, torch.float32), Xd.shape[1], _ptr(neg_flag, torch.int32) if neg_flag is not None else None,
+        n, G_u, _ptr(idx, torch.int32), _ptr(w, torch.float32), k, _ptr(order, torch.int32) if order is not None else None,
+        _ptr(lig, torch.int32), _ptr(rec, torch.int32), P, _ptr(S), ld, _ptr(row_nnz), *_cx_args(cx), _stream()),
+        "laris_diffuse_lr_score_dense")
     return S, row_nnz
 
 

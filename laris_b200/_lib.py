@@ -33,6 +33,9 @@ SIGNATURES = {
     "laris_csr_select_fill": [_p, _p, _p, _i64, _p, _p, _p, _p],
     "laris_exclusive_scan_i64": [_p, _i64, _p, _p],
     "laris_diffuse_lr_score": [_p, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i64, _p, _p],
+    "laris_diffuse_lr_score_complex": [_p, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i64, _p, _p, _p, _p, _i, _i, _p],
+    "laris_diffuse_lr_score_dense_complex": [_p, _i64, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i64, _p, _p, _p, _p,
+                                             _i, _i, _p],
     "laris_csr_select_dense": [_p, _p, _p, _i64, _p, _p, _i64, _p, _p],
     "laris_diffuse_lr_score_dense": [_p, _i64, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i64, _p, _p],
     "laris_lr_column_layout": [_p, _p, _i, _i, _p, _p],

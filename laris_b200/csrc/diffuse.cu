@@ -24,6 +24,7 @@
 // at once; laris_lr_column_layout() numbers the columns so that those land in
 // 32 different banks (graph colouring of the LR table).
 #include "common.cuh"
+#include "complex.cuh"
 #include <stdlib.h>
 
 namespace laris {
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(NT)
 diffuse_score_kernel(const int64_t* __restrict__ xu_indptr, const int64_t* __restrict__ xu_packed, int64_t n, int G_u,
                      const int32_t* __restrict__ idx, const float* __restrict__ w, int k,
                      const int32_t* __restrict__ order, const uint32_t* __restrict__ pairs, int p_words,
-                     float* __restrict__ S, int64_t ldS, int64_t* __restrict__ row_nnz) {
+                     float* __restrict__ S, int64_t ldS, int64_t* __restrict__ row_nnz, ComplexTable cx) {
     constexpr int NW = NT / 32;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -235,6 +236,10 @@ diffuse_score_kernel(const int64_t* __restrict__ xu_indptr, const int64_t* __res
             }
         }
         __syncwarp();
+        if (cx.nc) {                                                 // multi-subunit complexes -> their virtual columns
+            if (signed_data) complex_pass<true>(cx, Dw, Bw, lane); else complex_pass<false>(cx, Dw, Bw, lane);
+            __syncwarp();
+        }
 
         // ---------------- phase 2: S[p] = D[l] * D[r] * (flag_l | flag_r) ----------------
         // lane owns 4 consecutive pairs of every 128: the warp stores 512 contiguous bytes per step
@@ -338,11 +343,10 @@ extern "C" int laris_csr_select_fill(const int64_t* indptr, const int32_t* indic
     return LARIS_OK;
 }
 
-extern "C" int laris_diffuse_lr_score(const int64_t* xu_indptr, const int64_t* xu_packed, int64_t n, int32_t G_u,
-                                      const int32_t* idx, const float* w, int k, const int32_t* order,
-                                      const int32_t* lig, const int32_t* rec, int32_t P, float* S, int64_t ldS,
-                                      int64_t* row_nnz, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+static int diffuse_lr_score_impl(const int64_t* xu_indptr, const int64_t* xu_packed, int64_t n, int32_t G_u,
+                                 const int32_t* idx, const float* w, int k, const int32_t* order,
+                                 const int32_t* lig, const int32_t* rec, int32_t P, float* S, int64_t ldS,
+                                 int64_t* row_nnz, ComplexTable cx, cudaStream_t st) {
     LARIS_CHECK_ARG(xu_indptr && idx && w && lig && rec && S, "laris_diffuse_lr_score: null pointer");
     LARIS_CHECK_ARG(n > 0 && k >= 1 && P >= 1, "laris_diffuse_lr_score: empty problem");
     LARIS_CHECK_ARG(G_u >= 1 && G_u <= 65533, "laris_diffuse_lr_score: G_u must be in [1, 65533] (got %d)", G_u);
@@ -365,7 +369,7 @@ extern "C" int laris_diffuse_lr_score(const int64_t* xu_indptr, const int64_t* x
         return LARIS_E_LIMIT;
     }
     using Kern = void (*)(const int64_t*, const int64_t*, int64_t, int, const int32_t*, const float*, int, const int32_t*,
-                          const uint32_t*, int, float*, int64_t, int64_t*);
+                          const uint32_t*, int, float*, int64_t, int64_t*, ComplexTable);
     Kern kern = nullptr;
 #define DS_PICK(CH_, PPL_) if (ch == CH_ && ppl == PPL_) kern = diffuse_score_kernel<NT, CH_, PPL_>;
     DS_PICK(4, 0) DS_PICK(8, 0)
@@ -380,9 +384,30 @@ extern "C" int laris_diffuse_lr_score(const int64_t* xu_indptr, const int64_t* x
     const int64_t want = ceil_div(n, NT / 32);
     const int64_t grid = want < (int64_t)sms * occ ? want : (int64_t)sms * occ;
     kern<<<(unsigned)grid, NT, L.total, st>>>(xu_indptr, xu_packed, n, G_u, idx, w, k, order, pairs.p, p_words, S, ldS,
-                                              row_nnz);
+                                              row_nnz, cx);
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
+}
+
+extern "C" int laris_diffuse_lr_score(const int64_t* xu_indptr, const int64_t* xu_packed, int64_t n, int32_t G_u,
+                                      const int32_t* idx, const float* w, int k, const int32_t* order,
+                                      const int32_t* lig, const int32_t* rec, int32_t P, float* S, int64_t ldS,
+                                      int64_t* row_nnz, void* stream) {
+    return diffuse_lr_score_impl(xu_indptr, xu_packed, n, G_u, idx, w, k, order, lig, rec, P, S, ldS, row_nnz,
+                                 ComplexTable(), (cudaStream_t)stream);
+}
+
+extern "C" int laris_diffuse_lr_score_complex(const int64_t* xu_indptr, const int64_t* xu_packed, int64_t n, int32_t G_u,
+                                              const int32_t* idx, const float* w, int k, const int32_t* order,
+                                              const int32_t* lig, const int32_t* rec, int32_t P, float* S, int64_t ldS,
+                                              int64_t* row_nnz, const int32_t* cx_ptr, const int32_t* cx_cols,
+                                              const int32_t* cx_vcol, int32_t n_complex, int32_t rule, void* stream) {
+    LARIS_CHECK_ARG(n_complex >= 0 && (n_complex == 0 || (cx_ptr && cx_cols && cx_vcol)) && (rule == 0 || rule == 1),
+                    "laris_diffuse_lr_score_complex: bad complex table (n_complex=%d, rule=%d)", n_complex, rule);
+    ComplexTable cx;
+    cx.ptr = cx_ptr; cx.cols = cx_cols; cx.vcol = cx_vcol; cx.nc = n_complex; cx.rule = rule;
+    return diffuse_lr_score_impl(xu_indptr, xu_packed, n, G_u, idx, w, k, order, lig, rec, P, S, ldS, row_nnz, cx,
+                                 (cudaStream_t)stream);
 }
 
 extern "C" int laris_csr_compact(const float* S, int64_t ldS, int64_t n, int32_t P, const int64_t* indptr,

@@ -22,6 +22,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "complex.cuh"
 
 namespace laris {
 
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(NT, NBT >= 1 && NBT <= 3 ? 4 : 3)
 diffuse_dense_kernel(const float* __restrict__ Xd, int64_t ldX, const int32_t* __restrict__ neg_flag, int64_t n,
                      const int32_t* __restrict__ idx, const float* __restrict__ w, int k, int R, int nreg,
                      const int32_t* __restrict__ order, const uint32_t* __restrict__ pairs, int p_words,
-                     float* __restrict__ S, int64_t ldS, int64_t* __restrict__ row_nnz) {
+                     float* __restrict__ S, int64_t ldS, int64_t* __restrict__ row_nnz, ComplexTable cx) {
     constexpr int NW = NT / 32;
     constexpr int RM = kDenseRMax;
     constexpr int NBS = NBT ? NBT : 4;
@@ -298,6 +299,13 @@ diffuse_dense_kernel(const float* __restrict__ Xd, int64_t ldX, const int32_t* _
         }
         const bool signed_data = panel_signed || wneg;
         __syncwarp();
+        if (cx.nc) {                                                 // multi-subunit complexes -> their virtual columns
+            for (int r = 0; r < Rg; ++r) {
+                if (signed_data) complex_pass<true>(cx, slab + r * slab_words, Bw + r * bw_words, lane);
+                else complex_pass<false>(cx, slab + r * slab_words, Bw + r * bw_words, lane);
+            }
+            __syncwarp();
+        }
         // ---------------- phase 2: S[p] = D[l] * D[r] * (flag_l | flag_r) ----------------
         // the lane's pairs are scored for all cells of the group at once: one address per operand, RM gathers
         int cnt[RM];
@@ -382,11 +390,10 @@ extern "C" int laris_csr_select_dense(const int64_t* indptr, const int32_t* indi
     return LARIS_OK;
 }
 
-extern "C" int laris_diffuse_lr_score_dense(const float* Xd, int64_t ldX, const int32_t* neg_flag, int64_t n, int32_t G_u,
-                                            const int32_t* idx, const float* w, int k, const int32_t* order,
-                                            const int32_t* lig, const int32_t* rec, int32_t P, float* S, int64_t ldS,
-                                            int64_t* row_nnz, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+static int diffuse_lr_score_dense_impl(const float* Xd, int64_t ldX, const int32_t* neg_flag, int64_t n, int32_t G_u,
+                                       const int32_t* idx, const float* w, int k, const int32_t* order,
+                                       const int32_t* lig, const int32_t* rec, int32_t P, float* S, int64_t ldS,
+                                       int64_t* row_nnz, ComplexTable cx, cudaStream_t st) {
     LARIS_CHECK_ARG(Xd && idx && w && lig && rec && S, "laris_diffuse_lr_score_dense: null pointer");
     LARIS_CHECK_ARG(n > 0 && k >= 1 && P >= 1, "laris_diffuse_lr_score_dense: empty problem");
     LARIS_CHECK_ARG(G_u >= 1 && ldX > G_u && ldX % 128 == 0 && ldX <= 65536 && ((uintptr_t)Xd & 15) == 0,
@@ -407,7 +414,7 @@ extern "C" int laris_diffuse_lr_score_dense(const float* Xd, int64_t ldX, const 
         return LARIS_E_LIMIT;
     }
     using Kern = void (*)(const float*, int64_t, const int32_t*, int64_t, const int32_t*, const float*, int, int, int,
-                          const int32_t*, const uint32_t*, int, float*, int64_t, int64_t*);
+                          const int32_t*, const uint32_t*, int, float*, int64_t, int64_t*, ComplexTable);
     const int NB = (int)(ldX / 128);
     const int nbt = NB <= 4 ? NB : 0;
     Kern kern = nbt == 1 ? diffuse_dense_kernel<NT, 1> : nbt == 2 ? diffuse_dense_kernel<NT, 2>
@@ -426,7 +433,29 @@ extern "C" int laris_diffuse_lr_score_dense(const float* Xd, int64_t ldX, const 
     if (nsub > occ) nsub = occ;
     if (nsub < 1) nsub = 1;
     kern<<<(unsigned)(nreg * nsub), NT, L.total, st>>>(Xd, ldX, neg_flag, n, idx, w, k, R, nreg, order, pairs.p, p_words, S,
-                                                       ldS, row_nnz);
+                                                       ldS, row_nnz, cx);
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
+}
+
+extern "C" int laris_diffuse_lr_score_dense(const float* Xd, int64_t ldX, const int32_t* neg_flag, int64_t n, int32_t G_u,
+                                            const int32_t* idx, const float* w, int k, const int32_t* order,
+                                            const int32_t* lig, const int32_t* rec, int32_t P, float* S, int64_t ldS,
+                                            int64_t* row_nnz, void* stream) {
+    return diffuse_lr_score_dense_impl(Xd, ldX, neg_flag, n, G_u, idx, w, k, order, lig, rec, P, S, ldS, row_nnz,
+                                       ComplexTable(), (cudaStream_t)stream);
+}
+
+extern "C" int laris_diffuse_lr_score_dense_complex(const float* Xd, int64_t ldX, const int32_t* neg_flag, int64_t n,
+                                                    int32_t G_u, const int32_t* idx, const float* w, int k,
+                                                    const int32_t* order, const int32_t* lig, const int32_t* rec,
+                                                    int32_t P, float* S, int64_t ldS, int64_t* row_nnz,
+                                                    const int32_t* cx_ptr, const int32_t* cx_cols, const int32_t* cx_vcol,
+                                                    int32_t n_complex, int32_t rule, void* stream) {
+    LARIS_CHECK_ARG(n_complex >= 0 && (n_complex == 0 || (cx_ptr && cx_cols && cx_vcol)) && (rule == 0 || rule == 1),
+                    "laris_diffuse_lr_score_dense_complex: bad complex table (n_complex=%d, rule=%d)", n_complex, rule);
+    ComplexTable cx;
+    cx.ptr = cx_ptr; cx.cols = cx_cols; cx.vcol = cx_vcol; cx.nc = n_complex; cx.rule = rule;
+    return diffuse_lr_score_dense_impl(Xd, ldX, neg_flag, n, G_u, idx, w, k, order, lig, rec, P, S, ldS, row_nnz, cx,
+                                       (cudaStream_t)stream);
 }

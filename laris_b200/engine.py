@@ -91,6 +91,7 @@ class ExpressionU:
     n_columns: int | None = None
     dense: torch.Tensor | None = None     # [n, ldX] fp32
     neg_flag: torch.Tensor | None = None  # [1] int32: a negative value was seen
+    cx: tuple | None = None               # complex table (ptr, cols, vcol int32 device tensors, rule) or None
 
     @property
     def G_u(self):
@@ -160,34 +161,60 @@ class LRPlan:
     gene_map_d: torch.Tensor
     lig_d: torch.Tensor
     rec_d: torch.Tensor
+    cx: tuple | None = None
 
 
 _PLAN_CACHE: dict = {}
 
 
-def plan_lr_table(lig_g, rec_g, G) -> LRPlan:
-    """Plan of an LR table (cached: the same table is usually scored on many samples)."""
+COMPLEX_RULES = {"min": 0, "gmean": 1}
+
+
+def plan_lr_table(lig_g, rec_g, G, complexes=None, rule="min") -> LRPlan:
+    """Plan of an LR table (cached: the same table is usually scored on many samples).
+
+    ``lig_g`` / ``rec_g`` hold gene columns in [0, G); an entry ``G + c`` names the multi-subunit complex
+    ``complexes[c]`` (an array of gene columns), aggregated with ``rule`` ('min' | 'gmean') in the kernel."""
     lig_g = np.ascontiguousarray(lig_g, dtype=np.int64)
     rec_g = np.ascontiguousarray(rec_g, dtype=np.int64)
-    key = (int(G), torch.cuda.current_device(), hash(lig_g.tobytes()), hash(rec_g.tobytes()), len(lig_g))
+    if rule not in COMPLEX_RULES:
+        raise ValueError(f"complex_rule must be one of {sorted(COMPLEX_RULES)}, got {rule!r}")
+    cx_key = None if not complexes else (rule, tuple(tuple(int(g) for g in c) for c in complexes))
+    key = (int(G), torch.cuda.current_device(), hash(lig_g.tobytes()), hash(rec_g.tobytes()), len(lig_g), hash(cx_key))
     plan = _PLAN_CACHE.get(key)
     if plan is None:
         if len(_PLAN_CACHE) >= 8:
             _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
-        plan = _PLAN_CACHE[key] = _plan_lr_table(lig_g, rec_g, G)
+        plan = _PLAN_CACHE[key] = _plan_lr_table(lig_g, rec_g, G, complexes or [], rule)
     return plan
 
 
-def _plan_lr_table(lig_g, rec_g, G) -> LRPlan:
+def _plan_lr_table(lig_g, rec_g, G, complexes=(), rule="min") -> LRPlan:
     P = len(lig_g)
-    genes, inv = np.unique(np.concatenate([np.asarray(lig_g), np.asarray(rec_g)]), return_inverse=True)
-    lig_u, rec_u = inv[:P].astype(np.int32), inv[P:].astype(np.int32)
-    columns, n_columns = lr_column_layout(lig_u, rec_u, len(genes))
+    sub = np.concatenate([np.asarray(c, dtype=np.int64) for c in complexes]) if len(complexes) else np.empty(0, np.int64)
+    if len(complexes) and (min(len(c) for c in complexes) < 1 or sub.min() < 0 or sub.max() >= G):
+        raise ValueError("every complex needs at least one subunit gene in [0, G)")
+    # units = genes and complexes (pseudo ids >= G); every unit gets a packed column of the D slab
+    units, inv = np.unique(np.concatenate([np.asarray(lig_g), np.asarray(rec_g), sub]), return_inverse=True)
+    if units[-1] >= G + len(complexes):
+        raise ValueError("LR table names a complex that is not in `complexes`")
+    lig_u, rec_u = inv[:P].astype(np.int32), inv[P:2 * P].astype(np.int32)
+    columns, n_columns = lr_column_layout(lig_u, rec_u, len(units))
+    is_gene = units < G
+    genes, gene_cols = units[is_gene], columns[is_gene]
     gene_map = np.full(G, -1, dtype=np.int32)
-    gene_map[genes] = columns
+    gene_map[genes] = gene_cols
     lig_c, rec_c = columns[lig_u], columns[rec_u]
-    return LRPlan(genes, columns, n_columns, lig_c, rec_c, K.to_device(gene_map, torch.int32),
-                  K.to_device(lig_c.astype(np.int32), torch.int32), K.to_device(rec_c.astype(np.int32), torch.int32))
+    cx = None
+    used = units[~is_gene] - G                                    # complexes some pair names
+    if len(used):
+        ptr = np.concatenate([[0], np.cumsum([len(complexes[c]) for c in used])]).astype(np.int32)
+        cols = np.concatenate([gene_map[np.asarray(complexes[c], dtype=np.int64)] for c in used]).astype(np.int32)
+        vcol = columns[~is_gene].astype(np.int32)
+        cx = (K.to_device(ptr, torch.int32), K.to_device(cols, torch.int32), K.to_device(vcol, torch.int32),
+              COMPLEX_RULES[rule])
+    return LRPlan(genes, gene_cols, n_columns, lig_c, rec_c, K.to_device(gene_map, torch.int32),
+                  K.to_device(lig_c.astype(np.int32), torch.int32), K.to_device(rec_c.astype(np.int32), torch.int32), cx)
 
 
 def select_planned(plan: LRPlan, csr_dev, n, layout) -> ExpressionU:
@@ -195,15 +222,15 @@ def select_planned(plan: LRPlan, csr_dev, n, layout) -> ExpressionU:
     indptr, indices, data = csr_dev
     if layout == "dense":
         Xd, neg = K.csr_select_dense(indptr, indices, data, plan.gene_map_d, plan.n_columns)
-        return ExpressionU(None, None, plan.genes, n, plan.columns, plan.n_columns, Xd, neg)
+        return ExpressionU(None, None, plan.genes, n, plan.columns, plan.n_columns, Xd, neg, plan.cx)
     out_indptr, packed = K.csr_select(indptr, indices, data, plan.gene_map_d)
-    return ExpressionU(out_indptr, packed, plan.genes, n, plan.columns, plan.n_columns)
+    return ExpressionU(out_indptr, packed, plan.genes, n, plan.columns, plan.n_columns, cx=plan.cx)
 
 
-def select_lr_genes(X, lig_g, rec_g, csr_dev=None, layout="auto"):
-    """Gene selection for an LR table given as global gene columns.
+def select_lr_genes(X, lig_g, rec_g, csr_dev=None, layout="auto", complexes=None, rule="min"):
+    """Gene selection for an LR table given as global gene columns (entries >= G name ``complexes``).
     Returns (ExpressionU, ligand packed columns [P], receptor packed columns [P]) - the columns as device tensors."""
-    plan = plan_lr_table(lig_g, rec_g, X.shape[1])
+    plan = plan_lr_table(lig_g, rec_g, X.shape[1], complexes, rule)
     xu = select_planned(plan, csr_dev if csr_dev is not None else upload_csr(X), X.shape[0], choose_layout(X, layout))
     return xu, plan.lig_d, plan.rec_d
 
@@ -226,9 +253,11 @@ def lr_scores(xu: ExpressionU, graph: SpatialGraph, lig_u, rec_u) -> ScoreMatrix
     lig_d = lig_u if torch.is_tensor(lig_u) else K.to_device(np.asarray(lig_u, dtype=np.int32), torch.int32)
     rec_d = rec_u if torch.is_tensor(rec_u) else K.to_device(np.asarray(rec_u, dtype=np.int32), torch.int32)
     if xu.dense is not None:
-        S, row_nnz = K.diffuse_lr_score_dense(xu.dense, xu.neg_flag, xu.G_u, graph.idx, graph.w, graph.order, lig_d, rec_d)
+        S, row_nnz = K.diffuse_lr_score_dense(xu.dense, xu.neg_flag, xu.G_u, graph.idx, graph.w, graph.order, lig_d, rec_d,
+                                              cx=xu.cx)
     else:
-        S, row_nnz = K.diffuse_lr_score(xu.indptr, xu.packed, xu.G_u, graph.idx, graph.w, graph.order, lig_d, rec_d)
+        S, row_nnz = K.diffuse_lr_score(xu.indptr, xu.packed, xu.G_u, graph.idx, graph.w, graph.order, lig_d, rec_d,
+                                        cx=xu.cx)
     return ScoreMatrix(S, len(lig_u), row_nnz)
 
 

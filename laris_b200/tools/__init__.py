@@ -22,6 +22,23 @@ from . import _utils
 from ._utils import _log
 
 
+def _lr_units(adata, lr_df, complex_sep):
+    """Like ``_lr_gene_indices`` for tables whose names may be multi-subunit complexes ``A{sep}B{sep}...``:
+    returns (ligand ids, receptor ids, complexes) where an id >= n_genes names ``complexes[id - n_genes]``."""
+    G = adata.shape[1]
+    lig_n, rec_n = lr_df["ligand"].astype(str).to_numpy(), lr_df["receptor"].astype(str).to_numpy()
+    names = pd.unique(np.concatenate([lig_n, rec_n]))
+    parts = {nm: [s for s in nm.split(complex_sep) if s] for nm in names}
+    cx_names = [nm for nm in names if len(parts[nm]) > 1]           # "A+" is just gene A
+    cx_id = {nm: G + c for c, nm in enumerate(cx_names)}
+    complexes = [_utils._gene_columns(adata, parts[nm]) for nm in cx_names]
+    plain = [nm for nm in names if len(parts[nm]) <= 1]
+    simple = {nm: g for nm, g in zip(plain, _utils._gene_columns(adata, [(parts[nm] or [nm])[0] for nm in plain]))}
+    ids = {**simple, **cx_id}
+    return (np.array([ids[nm] for nm in lig_n], dtype=np.int64), np.array([ids[nm] for nm in rec_n], dtype=np.int64),
+            complexes)
+
+
 def _lr_gene_indices(adata, lr_df):
     """Gene columns of every ligand / receptor.  The reference's
     argsort/searchsorted lookup (laris/tools/__init__.py:95-97) silently maps a
@@ -30,7 +47,8 @@ def _lr_gene_indices(adata, lr_df):
 
 
 def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_rep_spatial: str = "X_spatial", *,
-                         dtype=np.float32, layout: str = "auto", radius=None):
+                         dtype=np.float32, layout: str = "auto", radius=None, complex_sep=None,
+                         complex_rule: str = "min"):
     """Per-cell diffused ligand-receptor scores as a new AnnData (cells x LR pairs).
 
     Reference laris/tools/__init__.py:29-119: kNN graph incl. self with
@@ -42,15 +60,23 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     expression ('dense' rows, packed 'sparse' rows, or 'auto' by the fraction of non-zeros);
     both give the same result.  ``radius`` (extension, not in the reference): use the radius graph
     {j: |x_i - x_j| <= radius}, self included, instead of the kNN graph; weights follow the same
-    1/exp(d/(mean(d)/2)) rule over the stored distances.
+    1/exp(d/(mean(d)/2)) rule over the stored distances.  ``complex_sep`` (extension): a ligand/receptor
+    name containing this separator (e.g. ``"TGFBR1+TGFBR2"`` with ``complex_sep="+"``) is a multi-subunit
+    complex; its diffused expression is the ``complex_rule`` ('min' | 'gmean') of its subunits' and it counts as
+    expressed in a cell only if every subunit is.  Without it, complexes are pre-expanded rows as in the
+    reference's tutorial.
     """
     xy = _utils._coords(adata, use_rep_spatial)
-    lig_g, rec_g = _lr_gene_indices(adata, lr_df)
+    complexes = None
+    if complex_sep:
+        lig_g, rec_g, complexes = _lr_units(adata, lr_df, complex_sep)
+    else:
+        lig_g, rec_g = _lr_gene_indices(adata, lr_df)
     if radius is None:
         graph = engine.build_graph(xy, number_nearest_neighbors, True, None)
     else:
         graph = engine.build_radius_graph(xy, radius, True, None)
-    xu, lig_c, rec_c = engine.select_lr_genes(adata.X, lig_g, rec_g, layout=layout)
+    xu, lig_c, rec_c = engine.select_lr_genes(adata.X, lig_g, rec_g, layout=layout, complexes=complexes, rule=complex_rule)
     sm = engine.lr_scores(xu, graph, lig_c, rec_c)
     X = engine.scores_to_csr(sm, dtype)
     lr_names = (lr_df["ligand"].astype(str) + "::" + lr_df["receptor"].astype(str)).to_numpy(dtype=object)

@@ -97,6 +97,37 @@ def lr_scores_csr_graph(X, W, lig_idx, rec_idx):
     return S
 
 
+def lr_scores_complex(X, W, lig_sets, rec_sets, rule="min"):
+    """EXTENSION oracle (north-star item 3; no reference behaviour, SURVEY.md "gaps"): LR scores where a ligand /
+    receptor may be a multi-subunit complex (a list of gene columns).  D = W X as in the reference
+    (laris/tools/__init__.py:91-92); a unit's diffused expression is the min ('min') or the geometric mean of
+    max(v,0) ('gmean') of its subunits' D; a unit is expressed in a cell iff every subunit has X != 0; the score is
+    D_L * D_R masked to cells expressing the ligand unit or the receptor unit (:100, :110-117 for single genes)."""
+    Xd = np.asarray(sp.csr_matrix(X).todense(), dtype=np.float64)
+    D = np.asarray((sp.csr_matrix(W) @ sp.csr_matrix(X)).todense(), dtype=np.float64)
+
+    def unit(cols):
+        v = D[:, cols]
+        if len(cols) == 1:                 # a single gene is never aggregated: the reference's own arithmetic
+            a = v[:, 0]
+        elif rule == "min":
+            a = v.min(1)
+        else:
+            v = np.maximum(v, 0.0)
+            with np.errstate(divide="ignore"):
+                a = np.where((v > 0).all(1), np.exp(np.log(np.where(v > 0, v, 1.0)).mean(1)), 0.0)
+        return a, (Xd[:, cols] != 0).all(1)
+
+    out = np.zeros((X.shape[0], len(lig_sets)))
+    for p, (ls, rs) in enumerate(zip(lig_sets, rec_sets)):
+        (a, fa), (b, fb) = unit(list(ls)), unit(list(rs))
+        out[:, p] = a * b * (fa | fb)
+    S = sp.csr_matrix(out)
+    S.eliminate_zeros()
+    S.sort_indices()
+    return S
+
+
 def decay_weights(dist, sigma=None):
     """w = 1/exp(d/s); s = mean(all stored d)/2 or the constant ``sigma``.
 

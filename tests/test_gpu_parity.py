@@ -636,3 +636,61 @@ def test_radius_graph_argument_errors(dev):
         engine.build_radius_graph(xy, 0.0, True)
     with pytest.raises(ValueError, match="without a neighbour"):
         engine.build_radius_graph(xy, 1e-9, False)
+
+
+# ------------------------------------------------ multi-subunit complexes ----
+@pytest.mark.parametrize("layout", ["sparse", "dense"])
+@pytest.mark.parametrize("rule", ["min", "gmean"])
+@pytest.mark.parametrize("signed", [False, True])
+def test_complex_aggregation_matches_oracle(dev, layout, rule, signed):
+    """In-kernel subunit aggregation (extension) against the numpy oracle; single-gene rows stay the reference's."""
+    import laris_b200 as la
+    from laris_b200.synth import make_dataset
+    from oracle import restate as R
+    a, lr, c = make_dataset(2, n=3000, G=120, G_u=80, P=40, C=4, density=0.35)
+    if signed:                                                     # negative expression -> bitmap flag path
+        X = a.X.copy().astype(np.float32)
+        X.data[::7] *= -1.0
+        a.X = X
+    rng = np.random.default_rng(9)
+    names = np.asarray(a.var_names, dtype=object)
+    lig, rec, lsets, rsets = list(lr["ligand"]), list(lr["receptor"]), [], []
+    col = {nm: i for i, nm in enumerate(names)}
+    for p in range(len(lig)):                                      # every third row gets a 2-3 subunit receptor / ligand
+        ls, rs = [col[lig[p]]], [col[rec[p]]]
+        if p % 3 == 0:
+            rs = list(rng.choice(80, int(rng.integers(2, 4)), replace=False))
+            rec[p] = "+".join(names[rs])
+        if p % 5 == 0:
+            ls = list(rng.choice(80, 2, replace=False))
+            lig[p] = "+".join(names[ls])
+        lsets.append(ls)
+        rsets.append(rs)
+    lr2 = pd.DataFrame({"ligand": lig, "receptor": rec})
+    out = la.tl.prepareLRInteraction(a, lr2, number_nearest_neighbors=8, complex_sep="+", complex_rule=rule, layout=layout)
+    ind, dist = R.knn_graph(a.obsm["X_spatial"], 8, True)
+    S = R.lr_scores_complex(a.X, R.graph_csr(ind, R.decay_weights(dist), c.n), lsets, rsets, rule)
+    X = sp.csr_matrix(out.X)
+    X.sort_indices()
+    assert list(out.var_names) == [f"{l}::{r}" for l, r in zip(lig, rec)]
+    if not signed:
+        assert np.array_equal(X.indptr, S.indptr) and np.array_equal(X.indices, S.indices)
+        assert np.allclose(X.data, S.data, rtol=RTOL, atol=0)
+    else:                                  # mixed signs: sums may cancel to ~0, compare values with an absolute floor
+        assert np.allclose(X.toarray(), S.toarray(), rtol=1e-4, atol=1e-5)
+    # rows without a complex are exactly the single-gene path
+    plain = [p for p in range(len(lig)) if "+" not in lig[p] and "+" not in rec[p]]
+    ref = la.tl.prepareLRInteraction(a, lr.iloc[plain].reset_index(drop=True), number_nearest_neighbors=8, layout=layout)
+    assert np.array_equal(sp.csr_matrix(out.X)[:, plain].toarray(), sp.csr_matrix(ref.X).toarray())
+
+
+def test_complex_argument_errors(dev):
+    import laris_b200 as la
+    from laris_b200.synth import make_dataset
+    a, lr, c = make_dataset(2, n=500, G=60, G_u=40, P=10, C=3)
+    bad = lr.copy()
+    bad.loc[0, "receptor"] = "g00001+nope"
+    with pytest.raises(KeyError):
+        la.tl.prepareLRInteraction(a, bad, complex_sep="+")
+    with pytest.raises(ValueError, match="complex_rule"):
+        la.tl.prepareLRInteraction(a, lr, complex_sep="+", complex_rule="max")
