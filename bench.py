@@ -266,6 +266,8 @@ def run_ours(args):
     extra = {}
     if not args.no_extra and rank == 0:
         extra = extra_metrics(torch, a, c, state, engine, K)
+        if not args.no_cpu_baseline:
+            extra.update(cpu_permutation_baselines(a, c, out.X, extra))
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -340,6 +342,42 @@ def extra_metrics(torch, a, c, state, engine, K):
         out["pvalue_null_ms"] = ms
         out["pvalue_permutations_per_sec"] = c.N / (ms * 1e-3)
         out["pvalue_draws_per_sec"] = C * C * P * c.N / (ms * 1e-3)
+    return out
+
+
+def cpu_permutation_baselines(a, c, S_host, gpu):
+    """The permutation half of the metric on the host cores (oracle port, 1 core - scipy.sparse / numpy are serial):
+    one random-graph null repeat on the full score matrix, and the p-value resampling on a bounded sample of
+    sender-receiver groups (its cost is linear in the number of groups)."""
+    from oracle import restate as R
+    import scipy.sparse as sp
+    out = {}
+    n, k, P, C = c.n, c.k, c.P, c.C
+    S = sp.csr_matrix(S_host).astype(np.float64)
+    ind, dist = R.knn_graph(a.obsm["X_spatial"], k, False)
+    w = R.decay_weights(dist, 100.0)
+    t0 = time.perf_counter()
+    cols, wperm = next(iter(R.null_graphs(n, k, w, 1, 27, "numpy")))
+    R.null_cosine(S, k, cols, wperm)
+    t = time.perf_counter() - t0
+    out["cpu_null_repeats_per_sec"] = 1.0 / t
+    out["cpu_null_repeat_sample"] = f"1 repeat, full {n} x {P} score matrix ({t:.2f} s), oracle port, 1 core"
+    if "null_repeats_per_sec" in gpu:
+        out["null_repeats_speedup_vs_cpu"] = gpu["null_repeats_per_sec"] / out["cpu_null_repeats_per_sec"]
+    if c.N > 0:
+        rng = np.random.default_rng(0)
+        groups = min(C * C, 40)                                    # bounded sample: 40 of the C^2 groups
+        table = rng.random((groups, P))
+        bg = np.stack([rng.permutation(P)[:30] for _ in range(P)]).astype(np.int64)
+        rs = np.random.RandomState(27)
+        t0 = time.perf_counter()
+        R.pvalue_counts(table, np.ones(P, bool), bg, lambda g, pidx: rs.randint(0, 30, (len(pidx), c.N)))
+        t = (time.perf_counter() - t0) * (C * C / groups)          # linear in the number of groups
+        out["cpu_pvalue_permutations_per_sec"] = c.N / t
+        out["cpu_pvalue_draws_per_sec"] = C * C * P * c.N / t
+        out["cpu_pvalue_sample"] = f"{groups} of {C * C} groups x {P} pairs x {c.N} permutations, scaled linearly, oracle port, 1 core"
+        if "pvalue_permutations_per_sec" in gpu:
+            out["pvalue_permutations_speedup_vs_cpu"] = gpu["pvalue_permutations_per_sec"] / out["cpu_pvalue_permutations_per_sec"]
     return out
 
 

@@ -272,6 +272,14 @@ LARIS_API int laris_pvalue_counts(const double* table, int64_t ldt, int32_t n_gr
 LARIS_API int laris_bh_fdr(const double* p, const uint8_t* sel, int32_t n_groups, int32_t len, double* fdr,
                  void* stream);
 
+/* ------------------------------------------------------- per-cell QC ----
+ * Per-cell metrics of the score matrix that scanpy.pp.calculate_qc_metrics writes to lr_adata.obs at
+ * laris/tools/__init__.py:493-496: total[i] = sum_p S[i,p], nnz[i] = #{p: S[i,p] != 0} and, for each N of
+ * top_n (HOST array, n_top <= 4), top_sum[i*n_top + t] = sum of the N largest scores of the cell
+ * (= total when N >= P); pct_counts_in_top_N_genes = 100 * top_sum / total. */
+LARIS_API int laris_row_qc(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* top_n, int32_t n_top,
+                           double* total, int64_t* nnz, double* top_sum, void* stream);
+
 /* ------------------------------------------------- laris.pp helpers ----
  * Device versions of the three helpers the reference re-exports as laris.pp
  * (laris/preprocessing/__init__.py:28-38).

@@ -279,6 +279,18 @@ def onehot_contract_csr(xu_indptr, xu_packed, G_u, labels, C):
     return s, c, q
 
 
+def row_qc(S, P, top_n=()):
+    """Per-cell (total fp64 [n], nnz int64 [n], top_sum fp64 [n, len(top_n)]) of the score matrix."""
+    n, ld = S.shape
+    tops = np.ascontiguousarray(top_n, dtype=np.int32)
+    total = torch.empty(n, dtype=torch.float64, device=S.device)
+    nnz = torch.empty(n, dtype=torch.int64, device=S.device)
+    top = torch.empty((n, max(len(tops), 1)), dtype=torch.float64, device=S.device)
+    check(lib.laris_row_qc(_ptr(S, torch.float32), ld, n, P, tops.ctypes.data if len(tops) else None, len(tops),
+                           _ptr(total), _ptr(nnz), _ptr(top), _stream()), "laris_row_qc")
+    return total, nnz, top[:, :len(tops)]
+
+
 # -------------------------------------------------------------- K6/K7 ----
 def pvalue_counts(table, bg, n_perm, *, active=None, seed=0, draws=None, slot_gid=None, P_global=None, g0=0, t0=0,
                   out=None):

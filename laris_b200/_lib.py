@@ -50,6 +50,7 @@ SIGNATURES = {
     "laris_onehot_contract_csr": [_p, _p, _i64, _i, _p, _i, _p, _p, _p, _p],
     "laris_pvalue_counts": [_p, _i64, _i, _i, _p, _i, _p, _p, _i64, _i, _i, _i, _i, _u64, _p, _p, _p, _p, _p],
     "laris_bh_fdr": [_p, _p, _i, _i, _p, _p],
+    "laris_row_qc": [_p, _i64, _i64, _i, _p, _i, _p, _p, _p, _p],
     "laris_rowwise_cosine": [_p, _p, _i64, _i64, _i64, _i64, _p, _p],
     "laris_pairwise_row_multiply": [_p, _i, _i64, _p, _p],
 }

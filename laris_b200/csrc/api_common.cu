@@ -83,6 +83,92 @@ __global__ void pairwise_row_multiply_kernel(const float* __restrict__ M, int C,
 }
 }  // namespace laris
 
+// ---- per-cell QC metrics of the score matrix (scanpy.pp.calculate_qc_metrics at laris/tools/__init__.py:493-496) ----
+namespace laris {
+struct TopList { int n[4]; int count; };
+
+// order-preserving map float -> uint32 (larger value <=> larger key)
+__device__ __forceinline__ uint32_t order_key(float v) {
+    const uint32_t b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// warp per row: the row is staged in shared memory; total / non-zero count in one pass, then for every N of the list
+// the N-th largest value by a 32-step radix select on the ordered keys, and the sum of the N largest from it
+__global__ void __launch_bounds__(256)
+row_qc_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, int P, TopList tops, double* __restrict__ total,
+              int64_t* __restrict__ nnz, double* __restrict__ top_sum) {
+    extern __shared__ float qc_rows[];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* row = qc_rows + (size_t)warp * P;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; i < n; i += nwarps) {
+        double s = 0.0;
+        int c = 0;
+        for (int p = lane; p < P; p += 32) {
+            const float v = S[i * ldS + p];
+            row[p] = v;
+            s += (double)v;
+            c += v != 0.f;
+        }
+        s = warp_sum(s);
+        c = __reduce_add_sync(FULL, c);
+        __syncwarp();
+        if (lane == 0) { total[i] = s; nnz[i] = c; }
+        for (int t = 0; t < tops.count; ++t) {
+            const int N = tops.n[t];
+            double ts = s;
+            if (N < P) {
+                uint32_t key = 0u;                                  // largest key with #{key(v) >= key} >= N
+                for (int bit = 31; bit >= 0; --bit) {
+                    const uint32_t cand = key | (1u << bit);
+                    int cnt = 0;
+                    for (int p = lane; p < P; p += 32) cnt += order_key(row[p]) >= cand;
+                    if (__reduce_add_sync(FULL, cnt) >= N) key = cand;
+                }
+                double sg = 0.0;
+                int cg = 0;
+                float vN = 0.f;
+                for (int p = lane; p < P; p += 32) {
+                    const float v = row[p];
+                    const uint32_t kv = order_key(v);
+                    if (kv > key) { sg += (double)v; ++cg; }
+                    if (kv == key) vN = v;
+                }
+                sg = warp_sum(sg);
+                cg = __reduce_add_sync(FULL, cg);
+                const unsigned has = __ballot_sync(FULL, order_key(vN) == key);
+                vN = __shfl_sync(FULL, vN, has ? __ffs(has) - 1 : 0);
+                ts = sg + (double)(N - cg) * (double)vN;
+            }
+            if (lane == 0) top_sum[i * tops.count + t] = ts;
+        }
+        __syncwarp();
+    }
+}
+}  // namespace laris
+
+extern "C" int laris_row_qc(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* top_n, int32_t n_top,
+                            double* total, int64_t* nnz, double* top_sum, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LARIS_CHECK_ARG(S && total && nnz && n >= 0 && P >= 1 && ldS >= P, "laris_row_qc: bad arguments");
+    LARIS_CHECK_ARG(n_top >= 0 && n_top <= 4 && (n_top == 0 || (top_n && top_sum)), "laris_row_qc: at most 4 top-N sizes");
+    LARIS_CHECK_ARG((size_t)P * 8 * sizeof(float) <= (size_t)200 * 1024, "laris_row_qc: P=%d does not fit shared memory", P);
+    if (n == 0) return LARIS_OK;
+    TopList tl;
+    tl.count = n_top;
+    for (int t = 0; t < 4; ++t) tl.n[t] = t < n_top ? top_n[t] : 0;          // top_n is HOST memory
+    for (int t = 0; t < n_top; ++t) LARIS_CHECK_ARG(tl.n[t] >= 1, "laris_row_qc: top sizes must be >= 1");
+    const size_t smem = (size_t)P * 8 * sizeof(float);
+    LARIS_CUDA(cudaFuncSetAttribute(row_qc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t want = ceil_div(n, 8);
+    const int64_t grid = want < (int64_t)kNumSMs * 4 ? want : (int64_t)kNumSMs * 4;
+    row_qc_kernel<<<(unsigned)grid, 256, smem, st>>>(S, ldS, n, P, tl, total, nnz, top_sum);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
 extern "C" int laris_rowwise_cosine(const float* A, const float* B, int64_t rows, int64_t cols, int64_t lda, int64_t ldb,
                                     double* out, void* stream) {
     LARIS_CHECK_ARG(A && B && out && rows >= 0 && cols >= 0 && lda >= cols && ldb >= cols, "laris_rowwise_cosine: bad arguments");

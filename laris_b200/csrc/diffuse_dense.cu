@@ -81,12 +81,19 @@ __device__ __forceinline__ float dense_score1(float a, float b, uint32_t m, int&
         if (nz) ++cnt;
         return nz ? t : 0.f;
     }
-    nz = (int)(__float_as_uint(a) | __float_as_uint(b)) < 0 && t != 0.f;   // flag = sign bit of D (D >= 0)
-    if (nz) ++cnt;
-    return nz ? fabsf(t) : 0.f;
+    const int fm = (int)(__float_as_uint(a) | __float_as_uint(b)) >> 31;   // flag = sign bit of D (D >= 0): all ones / zero
+    const uint32_t vb = __float_as_uint(t) & 0x7fffffffu & (uint32_t)fm;
+    cnt += vb != 0u;
+    return __uint_as_float(vb);
 }
 
-constexpr int kDenseDepth = 3;                                       // distinct neighbour rows in flight per warp
+#ifndef LARIS_DENSE_DEPTH
+#define LARIS_DENSE_DEPTH 2
+#endif
+#ifndef LARIS_DENSE_MINB
+#define LARIS_DENSE_MINB 5
+#endif
+constexpr int kDenseDepth = LARIS_DENSE_DEPTH;                                       // distinct neighbour rows in flight per warp
 
 // Per-warp shared memory: kDenseRMax cell slabs [slab_words] fp32 and their flag bitmaps [slab_words/32]
 // (bitmaps are only touched for signed data).
@@ -134,10 +141,11 @@ __device__ __forceinline__ void dense_row_accumulate(const DenseRow<NBS>& row, f
         if (b0 + b < NB) {
 #pragma unroll
             for (int r = 0; r < kDenseRMax; ++r) {
-                D[r][b].x = fmaf(row.w[r], row.x[b].x, D[r][b].x);
-                D[r][b].y = fmaf(row.w[r], row.x[b].y, D[r][b].y);
-                D[r][b].z = fmaf(row.w[r], row.x[b].z, D[r][b].z);
-                D[r][b].w = fmaf(row.w[r], row.x[b].w, D[r][b].w);
+                // packed fp32 FMA (FFMA2, sm_100): two columns per instruction, same rounding as two fmaf
+                const float2 w2 = make_float2(row.w[r], row.w[r]);
+                const float2 lo = __ffma2_rn(w2, make_float2(row.x[b].x, row.x[b].y), make_float2(D[r][b].x, D[r][b].y));
+                const float2 hi = __ffma2_rn(w2, make_float2(row.x[b].z, row.x[b].w), make_float2(D[r][b].z, D[r][b].w));
+                D[r][b] = make_float4(lo.x, lo.y, hi.x, hi.y);
             }
         }
     if (row.self) {                                                  // the own row of a cell carries its expression flags
@@ -159,7 +167,7 @@ __device__ __forceinline__ void dense_row_accumulate(const DenseRow<NBS>& row, f
 // range of the spatial order with all its warps interleaved, so the neighbour rows the next groups
 // need are the ones the previous groups left in that SM's L1.
 template <int NT, int NBT>
-__global__ void __launch_bounds__(NT, NBT >= 1 && NBT <= 3 ? 4 : 3)
+__global__ void __launch_bounds__(NT, NBT >= 1 && NBT <= 3 ? LARIS_DENSE_MINB : 3)
 diffuse_dense_kernel(const float* __restrict__ Xd, int64_t ldX, const int32_t* __restrict__ neg_flag, int64_t n,
                      const int32_t* __restrict__ idx, const float* __restrict__ w, int k, int R, int nreg,
                      const int32_t* __restrict__ order, const uint32_t* __restrict__ pairs, int p_words,
@@ -186,11 +194,40 @@ diffuse_dense_kernel(const float* __restrict__ Xd, int64_t ldX, const int32_t* _
     const int region = blockIdx.x % nreg, sub = blockIdx.x / nreg, nsub = gridDim.x / nreg;
     const int64_t per_region = (ngroups + nreg - 1) / nreg;
     const int64_t g_begin = (int64_t)region * per_region, g_end = min(ngroups, g_begin + per_region);
-    for (int64_t grp = g_begin + sub * NW + warp; grp < g_end; grp += (int64_t)nsub * NW) {
+    // Software pipeline over the warp's groups: the cell ids of group g+2 and the first 32 graph edges of group g+1
+    // are loaded while group g is processed, so the order -> idx/w -> row dependent-load chain of a group is off
+    // its critical path.
+    const int64_t gstride = (int64_t)nsub * NW;
+    auto load_cells = [&](int64_t grp) -> int {                      // the group's cells live in lanes 0..Rg-1
+        const int64_t q0 = grp * R;
+        if (grp >= g_end || lane >= (int)min((int64_t)R, n - q0)) return -1;
+        return order ? order[q0 + lane] : (int)(q0 + lane);
+    };
+    auto load_edges = [&](int cq_, int64_t grp, int& eid, float& ew) {   // one graph edge per lane: (cell e/k, edge e%k)
+        const int Rg_ = grp < g_end ? (int)min((int64_t)R, n - grp * R) : 0;
+        const int er = lane / k;
+        const bool valid = lane < nedge && er < Rg_;
+        const int c = __shfl_sync(FULL, cq_, valid ? er : 0);
+        eid = -1 - lane;                                             // idle lanes never match anything
+        ew = 0.f;
+        if (valid) {
+            eid = idx[(int64_t)c * k + (lane - er * k)];
+            ew = w[(int64_t)c * k + (lane - er * k)];
+        }
+    };
+    const int64_t grp0 = g_begin + sub * NW + warp;
+    int cq_next = load_cells(grp0), eid_next;
+    float ew_next;
+    load_edges(cq_next, grp0, eid_next, ew_next);
+    int cq_next2 = load_cells(grp0 + gstride);
+    for (int64_t grp = grp0; grp < g_end; grp += gstride) {
         const int64_t q0 = grp * R;
         const int Rg = (int)min((int64_t)R, n - q0);
-        int cq = -1;                                                 // the group's cells live in lanes 0..Rg-1
-        if (lane < Rg) cq = order ? order[q0 + lane] : (int)(q0 + lane);
+        const int cq = cq_next, eid_first = eid_next;
+        const float ew_first = ew_next;
+        cq_next = cq_next2;
+        load_edges(cq_next, grp + gstride, eid_next, ew_next);
+        cq_next2 = load_cells(grp + 2 * gstride);
         bool wneg = false;
 
         for (int b0 = 0; b0 < NB; b0 += NBS) {                       // passes over the column blocks (1 pass when NB <= 4)
@@ -212,7 +249,10 @@ diffuse_dense_kernel(const float* __restrict__ Xd, int64_t ldX, const int32_t* _
                 int eid = -1 - lane;                                 // idle lanes never match anything
                 float ew = 0.f;
                 const int c = __shfl_sync(FULL, cq, valid ? er : 0);
-                if (valid) {
+                if (e0 == 0) {                                       // prefetched with the previous group
+                    eid = eid_first;
+                    ew = ew_first;
+                } else if (valid) {
                     eid = idx[(int64_t)c * k + (e - er * k)];
                     ew = w[(int64_t)c * k + (e - er * k)];
                 }

@@ -140,6 +140,9 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     lr_adata.var["mean_counts"] = st[3][own] / n
     lr_adata.var["pct_dropout_by_counts"] = 100.0 * (1.0 - st[4][own] / n)
     lr_adata.var["total_counts"] = st[3][own]
+    lr_adata.var["log1p_mean_counts"] = np.log1p(st[3][own] / n)
+    lr_adata.var["log1p_total_counts"] = np.log1p(st[3][own])
+    _utils._write_obs_qc(lr_adata, sm, shard)
 
     # ---- ranking (reference :499-526) ----
     if shard is None:

@@ -48,6 +48,29 @@ def _log(verbose, *a):
         print(*a)
 
 
+def _write_obs_qc(lr_adata, sm, shard=None, percent_top=(50, 100, 200, 500)):
+    """The per-cell columns scanpy.pp.calculate_qc_metrics(lr_adata, inplace=True) adds to ``obs``
+    (reference laris/tools/__init__.py:493-496), computed on the device-resident scores:
+    n_genes_by_counts, total_counts, their log1p, and pct_counts_in_top_N_genes for every N < n_vars
+    (scanpy raises for N > n_vars; those columns are simply not written).  In a sharded run a rank only holds
+    a block of pairs: counts and totals are all-reduced, the top-N percentages are omitted."""
+    P = sm.P
+    tops = [] if shard is not None else [N for N in percent_top if N < P]
+    total, nnz, top = K.row_qc(sm.S, P, tops)
+    total, nnz, top = total.cpu().numpy(), nnz.cpu().numpy(), top.cpu().numpy()
+    if shard is not None:
+        both = _dist.all_reduce_sum(np.stack([total, nnz.astype(np.float64)]))
+        total, nnz = both[0], both[1].astype(np.int64)
+    obs = lr_adata.obs
+    obs["n_genes_by_counts"] = nnz
+    obs["log1p_n_genes_by_counts"] = np.log1p(nnz)
+    obs["total_counts"] = total.astype(np.float32)
+    obs["log1p_total_counts"] = np.log1p(total).astype(np.float32)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for j, N in enumerate(tops):
+            obs[f"pct_counts_in_top_{N}_genes"] = 100.0 * top[:, j] / total
+
+
 # ---------------------------------------------------------------------------
 # laris.pp re-exports (reference laris/preprocessing/__init__.py:28-38)
 # ---------------------------------------------------------------------------

@@ -694,3 +694,26 @@ def test_complex_argument_errors(dev):
         la.tl.prepareLRInteraction(a, bad, complex_sep="+")
     with pytest.raises(ValueError, match="complex_rule"):
         la.tl.prepareLRInteraction(a, lr, complex_sep="+", complex_rule="max")
+
+
+# ------------------------------------------------------------ per-cell QC ----
+def test_row_qc_matches_numpy(dev):
+    """Per-cell totals, counts and top-N sums (scanpy's obs QC columns) against a sort-based numpy computation."""
+    from laris_b200 import _kernels as K
+    rng = np.random.default_rng(21)
+    n, P = 700, 333
+    S = np.zeros((n, K.padded_ld(P)), np.float32)
+    S[:, :P] = (rng.random((n, P)) < 0.3) * rng.gamma(2.0, 1.0, (n, P)).astype(np.float32)
+    S[5, :P] = 0.0                                        # an empty cell
+    S[6, :P] = 1.25                                       # all ties
+    S[7, :P] = -S[8, :P]                                  # negative values order correctly too
+    tops = [1, 50, 100, 333, 500]
+    total, nnz, top = K.row_qc(torch.from_numpy(S).to(dev), P, tops[:4])
+    ref = S[:, :P].astype(np.float64)
+    assert np.allclose(total.cpu().numpy(), ref.sum(1), rtol=1e-12, atol=1e-12)
+    assert np.array_equal(nnz.cpu().numpy(), (ref != 0).sum(1))
+    srt = -np.sort(-ref, axis=1)
+    for j, N in enumerate(tops[:4]):
+        assert np.allclose(top.cpu().numpy()[:, j], srt[:, :min(N, P)].sum(1), rtol=1e-12, atol=1e-12), N
+    _, _, top5 = K.row_qc(torch.from_numpy(S).to(dev), P, [500])
+    assert np.allclose(top5.cpu().numpy()[:, 0], ref.sum(1), rtol=1e-12, atol=1e-12)        # N >= P: everything
