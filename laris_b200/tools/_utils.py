@@ -299,8 +299,14 @@ def _prepare_background_interactions(lr_adata, n_nearest_neighbors: int = 30, le
     mean = csum / n
     var = css / n - mean ** 2
     feats = np.column_stack([mean, var])
-    _, idx = KDTree(feats, leaf_size=leaf_size, metric="euclidean").query(feats, k=n_nearest_neighbors + 1)
-    return pd.DataFrame(idx[:, 1:], index=names, columns=range(n_nearest_neighbors))
+    kq = n_nearest_neighbors + 1
+    if 2 * kq < len(feats) and kq <= 64:
+        # same exact search as the spatial graphs (K1: sklearn KD-tree distances bit for bit, ties by index),
+        # self included and dropped as column 0 like the reference (:1098)
+        idx = K.knn_graph(K.to_device(feats, torch.float64), kq, True, want_order=False)[0].cpu().numpy().astype(np.int64)
+    else:      # tiny tables (k >= P/2: sklearn switches to brute force) or more than 63 neighbours: host KD-tree
+        _, idx = KDTree(feats, leaf_size=leaf_size, metric="euclidean").query(feats, k=min(kq, len(feats)))
+    return pd.DataFrame(idx[:, 1:], index=names, columns=range(idx.shape[1] - 1))
 
 
 def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_rep_spatial: str = "X_spatial",

@@ -460,6 +460,9 @@ def test_runlaris_matches_reference_fixture(dev, golden, tiny):
     assert np.allclose(res["p_value"].to_numpy()[o], golden["tbl_p"], rtol=1e-12), "p-values are count-derived: exact"
     assert np.allclose(res["p_value_fdr"].to_numpy()[o], golden["tbl_fdr"], rtol=1e-9)
     assert np.allclose(res["nlog10_p_value_fdr"].to_numpy()[o], golden["tbl_nlog"], rtol=1e-9, atol=1e-12)
+    # background sets (30-NN in (mean, variance) space) equal the reference's KD-tree result
+    from laris_b200.tools import _utils as U
+    assert np.array_equal(U._prepare_background_interactions(lr_adata, 30).to_numpy(), golden["bg"])
     u = lr_adata.uns["cosg_lr"]
     assert set(u) >= {"params", "COSG", "names", "scores"} and u["params"]["method"] == "COSG"
     assert u["COSG"].shape == (120, 2 * c.C * c.C) and u["scores"].dtype[0] == np.float32
