@@ -110,6 +110,36 @@ def upload_csr(X):
     return (K.to_device(X.indptr, torch.int64), K.to_device(X.indices, torch.int32), K.to_device(X.data, torch.float32))
 
 
+_COPY_STREAMS: dict = {}
+
+
+def upload_csr_async(X):
+    """``upload_csr`` on a dedicated copy stream: the host->device copies of the expression matrix (the bulk of the
+    input bytes) run while the caller builds the graph on the current stream.  Returns ``(csr_dev, join)``; call
+    ``join()`` on the consuming stream before the first kernel that reads the matrix."""
+    K.require_cuda()                     # "no CPU fallback": fail loudly before touching a stream
+    if not sp.issparse(X):
+        raise TypeError("adata.X must be a scipy sparse matrix (as in the reference, laris/tools/__init__.py:100)")
+    cur = torch.cuda.current_stream()
+    dev = torch.cuda.current_device()
+    side = _COPY_STREAMS.get(dev)
+    if side is None:
+        side = _COPY_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        csr_dev = upload_csr(X)
+        done = torch.cuda.Event()
+        done.record(side)
+
+    def join():
+        c = torch.cuda.current_stream()
+        c.wait_event(done)
+        for t in csr_dev:
+            t.record_stream(c)
+        return csr_dev
+    return csr_dev, join
+
+
 DENSE_PANEL_MIN_DENSITY = 0.15     # below this the packed sparse rows are the faster layout (measured, profiles/)
 
 
@@ -261,10 +291,35 @@ def lr_scores(xu: ExpressionU, graph: SpatialGraph, lig_u, rec_u) -> ScoreMatrix
     return ScoreMatrix(S, len(lig_u), row_nnz)
 
 
+def scores_to_csr_async(sm: ScoreMatrix, dtype=np.float32):
+    """Start the device CSR compaction and the device->host copies of the result; returns ``finish()`` which waits
+    for the copies and assembles the scipy matrix.  Host work done between the two calls overlaps the transfer."""
+    if sm.row_nnz is None:
+        raise ValueError("score matrix has no row counts")
+    parts = K.csr_compact(sm.S, sm.P, sm.row_nnz)
+    host = []
+    for t in parts:
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        host.append(h)
+    done = torch.cuda.Event()
+    done.record()
+
+    def finish():
+        done.synchronize()
+        indptr, indices, data = (h.numpy() for h in host)
+        return _assemble_csr(sm, indptr, indices, data, dtype)
+    return finish
+
+
 def scores_to_csr(sm: ScoreMatrix, dtype=np.float32) -> sp.csr_matrix:
     if sm.row_nnz is None:
         raise ValueError("score matrix has no row counts")
     indptr, indices, data = K.to_host(*K.csr_compact(sm.S, sm.P, sm.row_nnz))
+    return _assemble_csr(sm, indptr, indices, data, dtype)
+
+
+def _assemble_csr(sm, indptr, indices, data, dtype):
     # built without scipy's O(nnz) validation passes (check_format / index-dtype scans): the device
     # kernel guarantees a canonical CSR (sorted, duplicate-free, no explicit zeros)
     X = sp.csr_matrix((sm.n, sm.P), dtype=np.dtype(dtype))

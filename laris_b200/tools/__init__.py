@@ -67,6 +67,9 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     reference's tutorial.
     """
     xy = _utils._coords(adata, use_rep_spatial)
+    # schedule: the expression matrix goes up on the copy stream while the host resolves the LR table and the graph is
+    # built; the result comes down while the host prepares obs / var / obsm of the new AnnData
+    csr_dev, join_upload = engine.upload_csr_async(adata.X)
     complexes = None
     if complex_sep:
         lig_g, rec_g, complexes = _lr_units(adata, lr_df, complex_sep)
@@ -76,12 +79,14 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
         graph = engine.build_graph(xy, number_nearest_neighbors, True, None)
     else:
         graph = engine.build_radius_graph(xy, radius, True, None)
-    xu, lig_c, rec_c = engine.select_lr_genes(adata.X, lig_g, rec_g, layout=layout, complexes=complexes, rule=complex_rule)
+    xu, lig_c, rec_c = engine.select_lr_genes(adata.X, lig_g, rec_g, csr_dev=join_upload(), layout=layout,
+                                              complexes=complexes, rule=complex_rule)
     sm = engine.lr_scores(xu, graph, lig_c, rec_c)
-    X = engine.scores_to_csr(sm, dtype)
+    finish = engine.scores_to_csr_async(sm, dtype)
     lr_names = (lr_df["ligand"].astype(str) + "::" + lr_df["receptor"].astype(str)).to_numpy(dtype=object)
-    lr_adata = make_anndata(X, obs=adata.obs.copy(), var=pd.DataFrame(index=pd.Index(lr_names, dtype=object)),
-                            obsm={k: np.array(v, copy=True) for k, v in adata.obsm.items()})
+    obs, var = adata.obs.copy(), pd.DataFrame(index=pd.Index(lr_names, dtype=object))
+    obsm = {k: np.array(v, copy=True) for k, v in adata.obsm.items()}
+    lr_adata = make_anndata(finish(), obs=obs, var=var, obsm=obsm)
     _utils._remember_scores(lr_adata.X, sm)
     return lr_adata
 
