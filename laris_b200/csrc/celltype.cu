@@ -5,6 +5,7 @@
 //   celltype_pair_contract    num[p,(a,b)] = sum_i S[i,p] N[i,a] N[i,b]   (fp32 CUDA-core tiles; the
 //                             tcgen05 variant lives in celltype_mma.cu)
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace laris {
 
@@ -20,32 +21,70 @@ __global__ void neighborhood_composition_kernel(const int32_t* __restrict__ labe
 // ---- counts of non-zero scores per (cell type, pair): thread owns 4 columns, CTA-private
 //      shared table [C][4][128] so increments never collide and never conflict on banks
 constexpr int kCcThreads = 128;
+constexpr int kCcUnroll = 8;
 
-__global__ void __launch_bounds__(kCcThreads)
-celltype_nonzero_count_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t n, int P,
-                              const int32_t* __restrict__ labels, int C, int nchunks,
-                              unsigned long long* __restrict__ counts /*[C][P]*/) {
-    extern __shared__ uint32_t tbl[];                      // [C][4][kCcThreads]
-    const int tid = threadIdx.x;
-    for (int q = tid; q < C * 4 * kCcThreads; q += kCcThreads) tbl[q] = 0;
-    __syncthreads();
-    const int64_t col4 = (int64_t)blockIdx.x * kCcThreads + tid;
-    if (col4 < ld4) {
-        for (int64_t i = blockIdx.y; i < n; i += nchunks) {
-            const float4 s = ld_stream_f4(S4 + i * ld4 + col4);
-            uint32_t* t = tbl + (size_t)labels[i] * 4 * kCcThreads + tid;
-            t[0] += s.x != 0.f;
-            t[kCcThreads] += s.y != 0.f;
-            t[2 * kCcThreads] += s.z != 0.f;
-            t[3 * kCcThreads] += s.w != 0.f;
-        }
-        for (int c = 0; c < C; ++c)
-            for (int u = 0; u < 4; ++u) {
-                const int64_t p = col4 * 4 + u;
-                const uint32_t v = tbl[((size_t)c * 4 + u) * kCcThreads + tid];
-                if (p < P && v) atomicAdd(&counts[(int64_t)c * P + p], (unsigned long long)v);
-            }
+// cells grouped by type (device counting sort; the order inside a type does not matter for integer counts)
+__global__ void label_histogram_kernel(const int32_t* __restrict__ labels, int64_t n, int C, int32_t* __restrict__ hist) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int c = labels[i];
+        if (c >= 0 && c < C) atomicAdd(&hist[c], 1);
     }
+}
+__global__ void label_scatter_kernel(const int32_t* __restrict__ labels, int64_t n, int C, const int32_t* __restrict__ start,
+                                     int32_t* __restrict__ cursor, int32_t* __restrict__ rows, int32_t* __restrict__ row_label) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        const int c = labels[i];
+        if (c >= 0 && c < C) {
+            const int pos = start[c] + atomicAdd(&cursor[c], 1);
+            rows[pos] = (int32_t)i;
+            row_label[pos] = c;
+        }
+    }
+}
+
+// A thread owns 4 adjacent pair columns and a CTA one contiguous range of the type-grouped cell list: the counts of
+// the current type live in registers and are flushed (integer atomics, exact) only where the type changes, so the
+// loop is nothing but kCcUnroll independent 128-bit streaming loads per step - an HBM-bound pass over S.
+__global__ void __launch_bounds__(kCcThreads)
+celltype_nonzero_count_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t m, int P,
+                              const int32_t* __restrict__ rows, const int32_t* __restrict__ row_label, int nchunks,
+                              unsigned long long* __restrict__ counts /*[C][P]*/) {
+    const int64_t col4 = (int64_t)blockIdx.x * kCcThreads + threadIdx.x;
+    if (col4 >= ld4) return;
+    const int64_t per = (m + nchunks - 1) / nchunks;
+    const int64_t r0 = (int64_t)blockIdx.y * per, r1 = min(m, r0 + per);
+    if (r0 >= r1) return;
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    int cur = row_label[r0];
+    if (cur < 0) return;                                             // the chunk lies in the unused tail
+    auto flush = [&](int lab) {
+        const int64_t p = col4 * 4;
+        unsigned long long* o = counts + (int64_t)lab * P + p;
+        if (c0 && p < P) atomicAdd(o, (unsigned long long)c0);
+        if (c1 && p + 1 < P) atomicAdd(o + 1, (unsigned long long)c1);
+        if (c2 && p + 2 < P) atomicAdd(o + 2, (unsigned long long)c2);
+        if (c3 && p + 3 < P) atomicAdd(o + 3, (unsigned long long)c3);
+        c0 = c1 = c2 = c3 = 0;
+    };
+    for (int64_t r = r0; r < r1; r += kCcUnroll) {
+        float4 v[kCcUnroll];
+        int lab[kCcUnroll];
+#pragma unroll
+        for (int u = 0; u < kCcUnroll; ++u) {
+            lab[u] = r + u < r1 ? row_label[r + u] : -1;
+            const bool ok = lab[u] >= 0;
+            v[u] = ok ? ld_stream_f4(S4 + (int64_t)rows[r + u] * ld4 + col4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kCcUnroll; ++u) {
+            if (lab[u] < 0) break;
+            if (lab[u] != cur) { flush(cur); cur = lab[u]; }
+            c0 += v[u].x != 0.f; c1 += v[u].y != 0.f; c2 += v[u].z != 0.f; c3 += v[u].w != 0.f;
+        }
+    }
+    flush(cur);
 }
 
 // ---- per (type, gene) sums straight from the packed CSR: warp per row
@@ -172,20 +211,34 @@ extern "C" int laris_celltype_nonzero_count(const float* S, int64_t ldS, int64_t
     cudaStream_t st = (cudaStream_t)stream;
     LARIS_CHECK_ARG(S && labels && counts && n > 0 && P >= 1 && C >= 1, "laris_celltype_nonzero_count: bad arguments");
     LARIS_CHECK_ARG(ldS >= P && ldS % 4 == 0 && ((uintptr_t)S & 15) == 0, "laris_celltype_nonzero_count: S layout");
-    const size_t smem = (size_t)C * 4 * kCcThreads * sizeof(uint32_t);
-    if (smem > 200 * 1024) { set_error("laris_celltype_nonzero_count: C=%d exceeds the shared-memory table (limit 100)", C); return LARIS_E_LIMIT; }
-    LARIS_CUDA(cudaFuncSetAttribute(celltype_nonzero_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARIS_CHECK_ARG(n < (int64_t)INT32_MAX, "laris_celltype_nonzero_count: n must fit int32");
     LARIS_CUDA(cudaMemsetAsync(counts, 0, (size_t)C * P * sizeof(uint64_t), st));
+    // group the cells by type: histogram -> scan -> scatter (cells with a label outside [0,C) are skipped)
+    Scratch<int32_t> hist(st), start(st), cursor(st), rows(st), row_label(st);
+    LARIS_CUDA(hist.alloc(C));
+    LARIS_CUDA(start.alloc(C + 1));
+    LARIS_CUDA(cursor.alloc(C));
+    LARIS_CUDA(rows.alloc(n));
+    LARIS_CUDA(row_label.alloc(n));
+    LARIS_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)C * sizeof(int32_t), st));
+    LARIS_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)C * sizeof(int32_t), st));
+    LARIS_CUDA(cudaMemsetAsync(row_label.p, 0xff, (size_t)n * sizeof(int32_t), st));     // -1: unused tail
+    const unsigned gn = (unsigned)ceil_div(n, 256);
+    label_histogram_kernel<<<gn, 256, 0, st>>>(labels, n, C, hist.p);
+    LARIS_LAUNCH_CHECK();
+    int rc = exclusive_scan<int32_t>(hist.p, C, start.p, st);
+    if (rc) return rc;
+    label_scatter_kernel<<<gn, 256, 0, st>>>(labels, n, C, start.p, cursor.p, rows.p, row_label.p);
+    LARIS_LAUNCH_CHECK();
     const int64_t ld4 = ldS / 4;
     const int slabs = (int)ceil_div(ld4, kCcThreads);
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
-    int64_t nchunks = ceil_div((int64_t)kNumSMs * per_sm, slabs);
-    if (nchunks > n) nchunks = n;
+    int64_t nchunks = ceil_div((int64_t)kNumSMs * 16, slabs);          // ~16 resident 128-thread CTAs per SM
+    if (nchunks > ceil_div(n, kCcUnroll)) nchunks = ceil_div(n, kCcUnroll);
     if (nchunks > 65535) nchunks = 65535;
     dim3 grid((unsigned)slabs, (unsigned)nchunks);
-    celltype_nonzero_count_kernel<<<grid, kCcThreads, smem, st>>>((const float4*)S, ld4, n, P, labels, C, (int)nchunks,
-                                                                  (unsigned long long*)counts);
+    // rows beyond the number of validly labelled cells carry label -1 and end the chunk loops
+    celltype_nonzero_count_kernel<<<grid, kCcThreads, 0, st>>>((const float4*)S, ld4, n, P, rows.p, row_label.p, (int)nchunks,
+                                                               (unsigned long long*)counts);
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
 }

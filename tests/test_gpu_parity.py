@@ -720,3 +720,18 @@ def test_row_qc_matches_numpy(dev):
         assert np.allclose(top.cpu().numpy()[:, j], srt[:, :min(N, P)].sum(1), rtol=1e-12, atol=1e-12), N
     _, _, top5 = K.row_qc(torch.from_numpy(S).to(dev), P, [500])
     assert np.allclose(top5.cpu().numpy()[:, 0], ref.sum(1), rtol=1e-12, atol=1e-12)        # N >= P: everything
+
+
+@pytest.mark.parametrize("n,P,C,coherent", [(5000, 131, 7, False), (20000, 500, 40, True), (777, 3, 1, False),
+                                            (9001, 64, 150, False)])
+def test_celltype_nonzero_count_exact(dev, n, P, C, coherent):
+    """K5b: #{cells of type c with S[i,p] != 0} is an integer table - exact for any label arrangement and any C."""
+    from laris_b200 import _kernels as K
+    rng = np.random.default_rng(n + P)
+    S = np.zeros((n, K.padded_ld(P)), np.float32)
+    S[:, :P] = (rng.random((n, P)) < 0.25) * rng.random((n, P)).astype(np.float32)
+    labels = (np.arange(n) * C // n if coherent else rng.integers(0, C, n)).astype(np.int32)
+    got = K.celltype_nonzero_count(torch.from_numpy(S).to(dev), P, torch.from_numpy(labels).to(dev), C).cpu().numpy()
+    ref = np.zeros((C, P), np.int64)
+    np.add.at(ref, labels, (S[:, :P] != 0).astype(np.int64))
+    assert np.array_equal(got, ref)
