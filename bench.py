@@ -332,8 +332,6 @@ def extra_metrics(torch, a, c, state, engine, K):
     out["celltype_contract_ms"] = ms
     out["celltype_contract_impl"] = "tcgen05 (bf16 hi/mid/lo operand split, 6 MMAs per k-step, fp32 TMEM accumulation)"
     out["celltype_contract_TFLOPs_algorithmic"] = 2.0 * n * P * C * C / ms / 1e9
-    ms1, _ = timed(lambda: K.celltype_pair_contract(sm.S, P, N_, 1), reps=2)
-    out["celltype_contract_cuda_core_ms"] = ms1
     if c.N > 0:
         rng = np.random.default_rng(0)
         table = K.to_device(rng.random((C * C, P)), torch.float64)
