@@ -100,7 +100,7 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
              layer_celltype=None, n_neighbors_permutation: int = 30, n_permutations: int = 1000, chunk_size: int = 50000,
              prefilter_fdr: bool = True, prefilter_threshold: float = 0.0, score_threshold: float = 1e-6,
              spatial_weight: float = 1.0, use_conditional_pvalue: bool = False, *, rng: str = "numpy",
-             verbose: bool = True, contract_impl=None):
+             verbose: bool = True, contract_impl=None, radius=None):
     """Spatially-specific LR pairs and (optionally) the cell-type interaction table.
 
     Reference laris/tools/__init__.py:121-593, same arguments and returns
@@ -109,7 +109,11 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     number of LR pairs (the reference raises for P < 4000, SURVEY.md §9.9);
     ``remove_lowly_expressed``/``expressed_pct`` are accepted and unused, as in the
     reference body.  ``rng='numpy'`` replays the reference's random stream
-    bit-exactly; ``rng='philox'`` generates the nulls on the device.
+    bit-exactly; ``rng='philox'`` generates the nulls on the device.  ``radius`` (extension): both spatial graphs
+    (step 1 with ``exp(-d/sigma)`` weights, the neighbourhood profile with ``exp(-d/(mean(d)/2))``) are radius
+    graphs without self edges instead of kNN graphs; the random-graph null then re-deals the rows' padded
+    fixed-degree weight slots (zero padding included), which keeps the reference's construction for a graph whose
+    degree varies.
     """
     if by_celltype and adata is None:
         raise ValueError("Parameter 'adata' must be provided when by_celltype=True. "
@@ -128,7 +132,10 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     gather = (lambda x, axis=-1: x) if shard is None else (lambda x, axis=-1: _dist.all_gather_pairs(x, shard, axis))
     own = slice(None) if shard is None else slice(shard.start, shard.stop)
     sm = _utils._scores_of(lr_adata)
-    graph = engine.build_graph(_utils._coords(lr_adata, use_rep), n_nearest_neighbors, False, sigma)
+    if radius is None:
+        graph = engine.build_graph(_utils._coords(lr_adata, use_rep), n_nearest_neighbors, False, sigma)
+    else:
+        graph = engine.build_radius_graph(_utils._coords(lr_adata, use_rep), radius, False, sigma)
     st = engine.observed_stats(sm, graph)
     sm.cache.update(ss=st[1], sum=st[3], nnz=st[4])
     rand_each, rng_state = engine.null_cosines(sm, graph, n_repeats, random_seed, rng)
@@ -185,7 +192,7 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
         n_permutations=n_permutations, chunk_size=chunk_size, prefilter_fdr=prefilter_fdr,
         prefilter_threshold=prefilter_threshold, score_threshold=score_threshold, spatial_weight=spatial_weight,
         use_conditional_pvalue=use_conditional_pvalue, rng=rng, random_seed=random_seed, rng_state=rng_state,
-        verbose=verbose, contract_impl=contract_impl, shard=shard)
+        verbose=verbose, contract_impl=contract_impl, shard=shard, radius=radius)
     _log(verbose, f"\nResults: {len(laris_lr)} LR pairs, {len(celltype_results):,} cell type combinations")
     return laris_lr, celltype_results
 

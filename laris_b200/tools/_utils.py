@@ -236,7 +236,8 @@ def _calculate_specificity_in_spatial_neighborhood(adata, lr_adata, groupby: str
                                                    number_nearest_neighbors: int = 10, mu: float = 100,
                                                    expressed_pct: float = 0.1, remove_lowly_expressed: bool = True,
                                                    return_by_group: bool = True, key_added=None,
-                                                   column_delimiter: str = "@@", contract_impl=None, shard=None):
+                                                   column_delimiter: str = "@@", contract_impl=None, shard=None,
+                                                   radius=None):
     """Specificity of every LR pair for every sender::receiver neighbourhood profile.
 
     Reference :726-977.  Stores ``lr_adata.uns[key_added]`` with the reference's
@@ -249,7 +250,10 @@ def _calculate_specificity_in_spatial_neighborhood(adata, lr_adata, groupby: str
     codes, cats = _group_codes(adata.obs[groupby])
     C = len(cats)
     sm = _scores_of(lr_adata)
-    graph = engine.build_graph(_coords(adata, use_rep_spatial), number_nearest_neighbors, False, None)
+    if radius is None:
+        graph = engine.build_graph(_coords(adata, use_rep_spatial), number_nearest_neighbors, False, None)
+    else:
+        graph = engine.build_radius_graph(_coords(adata, use_rep_spatial), radius, False, None)
     ss = sm.cache.get("ss")
     if ss is None:
         ss = engine.observed_stats(sm, graph)[1]
@@ -317,7 +321,7 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_r
                                        prefilter_threshold: float = 0.0, score_threshold: float = 1e-6,
                                        spatial_weight: float = 1.0, use_conditional_pvalue: bool = False, *,
                                        rng: str = "numpy", random_seed: int = 27, rng_state=None, verbose: bool = True,
-                                       contract_impl=None, shard=None):
+                                       contract_impl=None, shard=None, radius=None):
     """Sender/receiver cell-type table with permutation p-values and BH-FDR.
 
     Reference laris/tools/_utils.py:1113-1688; same arguments (``mask_threshold`` and
@@ -388,7 +392,7 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_r
     ctc = _calculate_specificity_in_spatial_neighborhood(
         adata, lr_adata, groupby=groupby, use_rep_spatial=use_rep_spatial,
         number_nearest_neighbors=number_nearest_neighbors, mu=mu, return_by_group=True, key_added="cosg_lr",
-        column_delimiter="@@", contract_impl=contract_impl, shard=shard)
+        column_delimiter="@@", contract_impl=contract_impl, shard=shard, radius=radius)
     ctc_cols = [f"{a}::{b}" for a in cats for b in cats]
     ctc_m = ctc.loc[lr_names[pair_id], ctc_cols].to_numpy(dtype=np.float64).reshape(npair, C, C)
     flat = flat * ctc_m[row_pair, row_send, row_recv]

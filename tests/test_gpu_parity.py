@@ -735,3 +735,46 @@ def test_celltype_nonzero_count_exact(dev, n, P, C, coherent):
     ref = np.zeros((C, P), np.int64)
     np.add.at(ref, labels, (S[:, :P] != 0).astype(np.int64))
     assert np.array_equal(got, ref)
+
+
+def test_runlaris_on_radius_graphs(dev):
+    """runLARIS(radius=...): observed statistic, random-graph null (numpy stream on the padded weight slots) and the
+    neighbourhood co-localisation cosines against the oracle fed the sklearn radius graph."""
+    import laris_b200 as la
+    from laris_b200 import engine, _kernels as K
+    from laris_b200.synth import make_dataset
+    from oracle import restate as R, rng as orng
+    a, lr, c = make_dataset(5, n=4900, G=150, G_u=90, P=60, C=4, density=0.2)
+    radius, n = 1.5, 4900
+    lr_adata = la.tl.prepareLRInteraction(a, lr, radius=radius)
+    la.tl.runLARIS(lr_adata, a, by_celltype=False, n_repeats=2, random_seed=27, sigma=100.0, n_top_lr=60,
+                   n_cells_expressed_threshold=5, rng="numpy", verbose=False, radius=radius)
+    S = sp.csr_matrix(lr_adata.X).astype(np.float64)
+    indptr, indices, dist = R.radius_graph(a.obsm["X_spatial"], radius, False)
+    w = R.decay_weights(dist, 100.0)
+    W = sp.csr_matrix((w, indices, indptr), shape=(n, n))
+    gsp = R.column_cosine(S, W @ S)
+    assert np.allclose(lr_adata.var["LRSS_Target"], gsp, rtol=RTOL, atol=1e-9)
+    deg = np.diff(indptr)
+    kmax = int(deg.max())
+    wpad = np.zeros((n, kmax))
+    wpad[np.repeat(np.arange(n), deg), np.concatenate([np.arange(d) for d in deg])] = w
+    wpad = wpad.astype(np.float32).astype(np.float64).ravel()           # the device shuffles the fp32 weights
+    reps = []
+    for s in orng.numpy_repeat_seeds(27, 2):
+        cols, perm, _ = orng.numpy_null_graph(n, kmax, s)
+        reps.append(R.null_cosine(S, kmax, cols, wpad[perm]))
+    assert np.allclose(lr_adata.var["LRSS_Random"], np.mean(reps, axis=0), rtol=RTOL, atol=1e-9)
+    # neighbourhood profile on the radius graph with the mean/2 decay
+    labels = a.obs["CellTypes"].cat.codes.to_numpy().astype(np.int32)
+    w3 = R.decay_weights(dist)
+    onehot = sp.csr_matrix((np.ones(n), (labels, np.arange(n))), shape=(c.C, n))
+    N_ref = np.asarray((onehot @ sp.csr_matrix((w3, indices, indptr), shape=(n, n)).T).todense())
+    from laris_b200.tools import _utils as U
+    g3 = engine.build_radius_graph(a.obsm["X_spatial"], radius, False, None)
+    _, cos = engine.neighborhood_specificity(U._scores_of(lr_adata), K.to_device(labels, torch.int32), c.C, g3, 100.0)
+    assert np.allclose(cos, R.celltype_pair_cosine(S, N_ref), rtol=RTOL, atol=1e-8)
+    # and the whole cell-type step runs on it
+    laris_lr, table = la.tl.runLARIS(lr_adata, a, n_repeats=2, n_top_lr=60, n_cells_expressed_threshold=5, n_permutations=50,
+                                     rng="philox", verbose=False, radius=radius)
+    assert len(laris_lr) == 60 and len(table) == 60 * c.C * c.C and np.isfinite(table["interaction_score"]).all()

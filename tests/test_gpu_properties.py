@@ -55,7 +55,10 @@ def test_radius_graph_matches_sklearn_on_random_points(seed, n, dim, include_sel
     r_indptr, r_indices, r_dist = R.radius_graph(xy, radius, include_self)
     assert np.array_equal(indptr.cpu().numpy(), r_indptr)
     assert np.array_equal(indices.cpu().numpy(), r_indices)
-    assert np.array_equal(dist.cpu().numpy(), r_dist)
+    if n >= 12:
+        assert np.array_equal(dist.cpu().numpy(), r_dist)
+    else:       # NearestNeighbors' default n_neighbors=5 >= n//2 sends sklearn to brute force (GEMM-expanded distances)
+        assert np.allclose(dist.cpu().numpy(), r_dist, rtol=1e-9, atol=1e-9)
 
 
 def _tiny_problem(rng, n, G, P, density, signed=False):
