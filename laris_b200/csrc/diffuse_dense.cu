@@ -19,7 +19,6 @@
 //   phase 2  D goes to the warp's shared slab once (128-bit stores); lane owns 4 consecutive pairs of
 //            every 128: two shared gathers per score, 512 contiguous bytes of the S row per store
 // D never touches HBM.  Algorithmic bytes: 4*n*G_u + 8*n*k + 4*n*P.
-#include <stdlib.h>
 #include <type_traits>
 
 #include "common.cuh"
@@ -399,179 +398,6 @@ diffuse_dense_kernel(const float* __restrict__ Xd, int64_t ldX, const int32_t* _
 }
 
 
-// ------------------------------------------------------- K2+K3, one cell per warp --
-// Leaner variant of the dense-panel kernel: ONE WARP OWNS ONE CELL.  Its k neighbour rows are loaded through L1
-// (ld.global.nc, 128-bit, lane owns 4 consecutive columns of every 128) four at a time and FMA'd into a register
-// accumulator with the edge weight; nothing is de-duplicated across cells - consecutive cells of the spatial order
-// are walked by the warps of one SM, so the rows they share are L1 hits, and the match/ballot bookkeeping of the
-// 3-cell variant (which costs more issue slots than the loads it saves) disappears.  A neighbour listed twice
-// simply adds twice.  Flags, the shared slab, the complex pass and phase 2 are as in diffuse_dense_kernel.
-#ifndef LARIS_DENSE1_DEPTH
-#define LARIS_DENSE1_DEPTH 2
-#endif
-#ifndef LARIS_DENSE1_MINB
-#define LARIS_DENSE1_MINB 3
-#endif
-template <int NT, int NBT>
-__global__ void __launch_bounds__(NT, LARIS_DENSE1_MINB)
-diffuse_dense1_kernel(const float* __restrict__ Xd, int64_t ldX, const int32_t* __restrict__ neg_flag, int64_t n,
-                      const int32_t* __restrict__ idx, const float* __restrict__ w, int k, int nreg,
-                      const int32_t* __restrict__ order, const uint32_t* __restrict__ pairs, int p_words,
-                      float* __restrict__ S, int64_t ldS, int64_t* __restrict__ row_nnz, ComplexTable cx) {
-    constexpr int NW = NT / 32;
-    constexpr int NBS = NBT ? NBT : 4;
-    constexpr int DEPTH = LARIS_DENSE1_DEPTH;
-    constexpr unsigned FULL = 0xffffffffu;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NB = NBT ? NBT : (int)(ldX >> 7);
-    const int slab_words = NB * 128, bw_words = NB * 4;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t* pairs_s = reinterpret_cast<uint32_t*>(smem_raw);
-    float* slab = reinterpret_cast<float*>(pairs_s + p_words) + (size_t)warp * (slab_words + bw_words);
-    uint32_t* Bw = reinterpret_cast<uint32_t*>(slab + slab_words);
-    for (int p = tid; p < p_words; p += NT) pairs_s[p] = pairs[p];
-    __syncthreads();
-    const bool panel_signed = neg_flag ? (*neg_flag != 0) : true;
-
-    const int region = blockIdx.x % nreg, sub = blockIdx.x / nreg, nsub = gridDim.x / nreg;
-    const int64_t per_region = (n + nreg - 1) / nreg;
-    const int64_t q_begin = (int64_t)region * per_region, q_end = min(n, q_begin + per_region);
-    const int64_t qstride = (int64_t)nsub * NW;
-    // software pipeline over the warp's cells: cell id two ahead, its first 32 edges one ahead
-    auto load_cell = [&](int64_t q) -> int { return q < q_end ? (order ? order[q] : (int)q) : -1; };
-    auto load_edges = [&](int ci_, int j0, int& eid, float& ew) {
-        eid = -1;
-        ew = 0.f;
-        if (ci_ >= 0 && j0 + lane < k) {
-            eid = idx[(int64_t)ci_ * k + j0 + lane];
-            ew = w[(int64_t)ci_ * k + j0 + lane];
-        }
-    };
-    const int64_t q0 = q_begin + sub * NW + warp;
-    int ci_next = load_cell(q0), eid_next;
-    float ew_next;
-    load_edges(ci_next, 0, eid_next, ew_next);
-    int ci_next2 = load_cell(q0 + qstride);
-    for (int64_t q = q0; q < q_end; q += qstride) {
-        const int ci = ci_next, eid_first = eid_next;
-        const float ew_first = ew_next;
-        ci_next = ci_next2;
-        load_edges(ci_next, 0, eid_next, ew_next);
-        ci_next2 = load_cell(q + 2 * qstride);
-        bool wneg = false;
-
-        for (int b0 = 0; b0 < NB; b0 += NBS) {                       // passes over the column blocks (1 pass when NB <= 4)
-            float4 D[NBS];
-#pragma unroll
-            for (int b = 0; b < NBS; ++b) D[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-            uint32_t flags = 0u;
-            bool found = false;
-            const float* colp = Xd + ((int64_t)b0 << 7) + 4 * lane;
-            for (int j0 = 0; j0 < k; j0 += 32) {
-                int eid = eid_first;
-                float ew = ew_first;
-                if (j0) load_edges(ci, j0, eid, ew);
-                wneg |= __any_sync(FULL, ew < 0.f);
-                const int kc = min(32, k - j0);
-                for (int j = 0; j < kc; j += DEPTH) {
-                    float4 x[DEPTH][NBS];
-                    float wj[DEPTH];
-                    int id[DEPTH];
-#pragma unroll
-                    for (int d = 0; d < DEPTH; ++d) {                // DEPTH rows in flight
-                        id[d] = __shfl_sync(FULL, eid, (j + d) & 31);
-                        wj[d] = __shfl_sync(FULL, ew, (j + d) & 31);
-                        if (j + d < kc) {
-                            const float* p = colp + (int64_t)id[d] * ldX;
-#pragma unroll
-                            for (int b = 0; b < NBS; ++b)
-                                if (b0 + b < NB) x[d][b] = ldg_f4(p + 128 * b);
-                        }
-                    }
-#pragma unroll
-                    for (int d = 0; d < DEPTH; ++d) {
-                        if (j + d < kc) {
-                            const float2 w2 = make_float2(wj[d], wj[d]);
-#pragma unroll
-                            for (int b = 0; b < NBS; ++b)
-                                if (b0 + b < NB) {
-                                    const float2 lo = __ffma2_rn(w2, make_float2(x[d][b].x, x[d][b].y), make_float2(D[b].x, D[b].y));
-                                    const float2 hi = __ffma2_rn(w2, make_float2(x[d][b].z, x[d][b].w), make_float2(D[b].z, D[b].w));
-                                    D[b] = make_float4(lo.x, lo.y, hi.x, hi.y);
-                                }
-                            if (id[d] == ci) {                       // the cell's own row carries its expression flags
-                                found = true;
-#pragma unroll
-                                for (int b = 0; b < NBS; ++b)
-                                    if (b0 + b < NB) flags |= nz4(x[d][b]) << (4 * b);
-                            }
-                        }
-                    }
-                }
-            }
-            if (!found) {                                            // graph without self edges: fetch the own row
-                const float* p = colp + (int64_t)ci * ldX;
-#pragma unroll
-                for (int b = 0; b < NBS; ++b)
-                    if (b0 + b < NB) flags |= nz4(ldg_f4(p + 128 * b)) << (4 * b);
-            }
-            // ---- D (+ flags) -> the warp's shared slab ----
-            const bool signed_now = panel_signed || wneg;
-            float* sl = slab + (b0 << 7) + 4 * lane;
-#pragma unroll
-            for (int b = 0; b < NBS; ++b) {
-                if (b0 + b >= NB) continue;
-                float4 v = D[b];
-                const uint32_t f = flags >> (4 * b);
-                if (!signed_now) {
-                    v.x = flag_sign(v.x, f & 1u);
-                    v.y = flag_sign(v.y, (f >> 1) & 1u);
-                    v.z = flag_sign(v.z, (f >> 2) & 1u);
-                    v.w = flag_sign(v.w, (f >> 3) & 1u);
-                } else {                                             // 8 lanes share one bitmap word
-                    uint32_t word = (f & 15u) << ((lane & 7) * 4);
-                    word |= __shfl_xor_sync(FULL, word, 1);
-                    word |= __shfl_xor_sync(FULL, word, 2);
-                    word |= __shfl_xor_sync(FULL, word, 4);
-                    if ((lane & 7) == 0) Bw[4 * (b0 + b) + (lane >> 3)] = word;
-                }
-                *reinterpret_cast<float4*>(sl + 128 * b) = v;
-            }
-        }
-        const bool signed_data = panel_signed || wneg;
-        __syncwarp();
-        if (cx.nc) {                                                 // multi-subunit complexes -> their virtual columns
-            if (signed_data) complex_pass<true>(cx, slab, Bw, lane); else complex_pass<false>(cx, slab, Bw, lane);
-            __syncwarp();
-        }
-        // ---------------- phase 2: S[p] = D[l] * D[r] * (flag_l | flag_r) ----------------
-        int cnt = 0;
-        float* srow = S + (int64_t)ci * ldS;
-        auto phase2 = [&](auto signed_tag) {
-            constexpr bool SIGNED = decltype(signed_tag)::value;
-            for (int p0 = lane * 4; p0 < (int)ldS; p0 += 128) {
-                const uint4 pr4 = *reinterpret_cast<const uint4*>(pairs_s + p0);
-                const uint32_t q4[4] = {pr4.x, pr4.y, pr4.z, pr4.w};
-                float v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t l = q4[u] & 0xffffu, rr = q4[u] >> 16;
-                    uint32_t m = 0u;
-                    if (SIGNED) m = ((Bw[l >> 5] >> (l & 31)) | (Bw[rr >> 5] >> (rr & 31))) & 1u;
-                    v[u] = dense_score1<SIGNED>(slab[l], slab[rr], m, cnt);
-                }
-                st_stream_f4(reinterpret_cast<float4*>(srow + p0), make_float4(v[0], v[1], v[2], v[3]));
-            }
-        };
-        if (signed_data) phase2(std::true_type{}); else phase2(std::false_type{});
-        if (row_nnz) {
-            const int c = __reduce_add_sync(FULL, cnt);
-            if (lane == 0) row_nnz[ci] = c;
-        }
-        __syncwarp();                                                // the slab is rewritten by the next cell
-    }
-}
-
 __global__ void pack_pairs_dense_kernel(const int32_t* __restrict__ lig, const int32_t* __restrict__ rec, int P, int G_u,
                                         int p_words, uint32_t* __restrict__ pairs) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -622,37 +448,6 @@ static int diffuse_lr_score_dense_impl(const float* Xd, int64_t ldX, const int32
     LARIS_CUDA(pairs.alloc((size_t)p_words));
     pack_pairs_dense_kernel<<<(unsigned)ceil_div(p_words, 256), 256, 0, st>>>(lig, rec, P, G_u, p_words, pairs.p);
     LARIS_LAUNCH_CHECK();
-    static const int impl = getenv("LARIS_DENSE_IMPL") ? atoi(getenv("LARIS_DENSE_IMPL")) : 0;
-    if (impl == 1) {                                                 // one cell per warp
-        constexpr int NT1 = 256;
-        const size_t smem1 = ((size_t)p_words + (size_t)(NT1 / 32) * (ldX + ldX / 32)) * 4;
-        if (smem1 + 1024 > (size_t)227 * 1024) {
-            set_error("laris_diffuse_lr_score_dense: ldX=%lld, P=%d do not fit shared memory", (long long)ldX, P);
-            return LARIS_E_LIMIT;
-        }
-        using Kern1 = void (*)(const float*, int64_t, const int32_t*, int64_t, const int32_t*, const float*, int, int,
-                               const int32_t*, const uint32_t*, int, float*, int64_t, int64_t*, ComplexTable);
-        const int NB1 = (int)(ldX / 128);
-        const int nbt1 = NB1 <= 4 ? NB1 : 0;
-        Kern1 kern1 = nbt1 == 1 ? diffuse_dense1_kernel<NT1, 1> : nbt1 == 2 ? diffuse_dense1_kernel<NT1, 2>
-                    : nbt1 == 3 ? diffuse_dense1_kernel<NT1, 3> : nbt1 == 4 ? diffuse_dense1_kernel<NT1, 4>
-                    : diffuse_dense1_kernel<NT1, 0>;
-        LARIS_CUDA(cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-        int occ1 = 1;
-        LARIS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, kern1, NT1, smem1));
-        if (occ1 < 1) occ1 = 1;
-        int dev1 = 0, sms1 = kNumSMs;
-        cudaGetDevice(&dev1);
-        cudaDeviceGetAttribute(&sms1, cudaDevAttrMultiProcessorCount, dev1);
-        const int nreg1 = (int)(n < sms1 ? n : sms1);
-        int nsub1 = (int)ceil_div(ceil_div(n, nreg1), NT1 / 32);
-        if (nsub1 > occ1) nsub1 = occ1;
-        if (nsub1 < 1) nsub1 = 1;
-        kern1<<<(unsigned)(nreg1 * nsub1), NT1, smem1, st>>>(Xd, ldX, neg_flag, n, idx, w, k, nreg1, order, pairs.p, p_words,
-                                                             S, ldS, row_nnz, cx);
-        LARIS_LAUNCH_CHECK();
-        return LARIS_OK;
-    }
     const int R = k > 32 ? 1 : (32 / k < kDenseRMax ? 32 / k : kDenseRMax);
     const DenseLayout L((int)ldX, p_words, NT / 32);
     if (L.total + 1024 > (size_t)227 * 1024) {
