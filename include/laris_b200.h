@@ -57,8 +57,9 @@ LARIS_API const char* laris_last_error(void);
  *   out_idx   [n*k]   int32 neighbour ids (the CSR 'indices'; indptr = i*k)
  *   out_dist  [n*k]   fp64 distances (the CSR 'data' before the weight transform)
  *   out_order [n]     int32 spatial processing order (grid-cell sorted), may be NULL
- * Requires k(+1 if !include_self) <= 64 and n >= k+1.  Synchronises once
- * (reads the bounding box back to size the grid).
+ * Requires k(+1 if !include_self) <= 64 and n >= k+1.  Fully asynchronous: the grid shape is derived on
+ * the device from the bounding box (no host round trip).  Non-finite coordinates cannot be reported
+ * through the return code without a synchronisation: every out_idx is then -1 and every out_dist NaN.
  */
 LARIS_API int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int include_self,
                     int32_t* out_idx, double* out_dist, int32_t* out_order, void* stream);
@@ -72,7 +73,7 @@ LARIS_API int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int i
  *   count: counts [n] int64 row degrees (+ optional spatial processing order [n] int32);
  *          the caller scans them into indptr (laris_exclusive_scan_i64)
  *   fill:  indices [nnz] int32 column-sorted within a row (canonical CSR), dist [nnz] fp64
- * Each pass synchronises once (bounding box). */
+ * Both passes are asynchronous (grid shape derived on the device); non-finite coordinates give empty rows. */
 LARIS_API int laris_radius_graph_count(const double* xy, int64_t n, int dim, double radius, int include_self,
                                        int64_t* counts, int32_t* out_order, void* stream);
 LARIS_API int laris_radius_graph_fill(const double* xy, int64_t n, int dim, double radius, int include_self,

@@ -23,6 +23,11 @@ struct GridSpec {
     double h;
     int g[3];
     int dim;
+    int64_t ncell;      // g[0]*g[1]*g[2]
+    int64_t nslot;      // size of the strip-order slot table
+    int strip_h;        // strip height in cells (min(kStripH, g[1]))
+    int valid;          // 0: non-finite coordinates - every kernel leaves its outputs untouched except the
+                        //    searches, which write index -1 / distance NaN
 };
 
 // ------------------------------------------------------------------ bbox --
@@ -31,6 +36,7 @@ __global__ void bbox_partial_kernel(const double* __restrict__ xy, int64_t n, in
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         for (int a = 0; a < dim; ++a) {
             double v = xy[i * dim + a];
+            if (!isfinite(v)) v = -INFINITY;             // fmin/fmax drop NaN: make any non-finite value poison the box
             mn[a] = fmin(mn[a], v);
             mx[a] = fmax(mx[a], v);
         }
@@ -68,16 +74,63 @@ __global__ void bbox_final_kernel(const double* __restrict__ part, int nblocks, 
     if (lane == 0) out[t] = v;
 }
 
+// The grid shape is derived ON THE DEVICE from the bounding box (one thread), so the whole graph build is
+// asynchronous: no host round trip between the bounding box and the binning.  Host-side buffers are sized by the
+// bound ncell <= cell_bound that the loop below enforces.
+constexpr int kStripH = 8;
+
+__global__ void grid_spec_kernel(const double* __restrict__ box, int64_t n, int dim, double per_cell, double min_h,
+                                 int64_t cell_bound, GridSpec* __restrict__ out) {
+    if (threadIdx.x || blockIdx.x) return;
+    GridSpec gs;
+    gs.dim = dim;
+    gs.valid = 1;
+    double ext[3] = {0, 0, 0}, vol = 1.0;
+    int nz_dims = 0;
+    for (int a = 0; a < 3; ++a) { gs.lo[a] = 0; gs.g[a] = 1; }
+    for (int a = 0; a < dim; ++a) {
+        if (!isfinite(box[a]) || !isfinite(box[3 + a])) gs.valid = 0;
+        gs.lo[a] = box[a];
+        ext[a] = box[3 + a] - box[a];
+        if (ext[a] > 0) { vol *= ext[a]; ++nz_dims; }
+    }
+    double h = nz_dims ? pow(vol * per_cell / (double)n, 1.0 / nz_dims) : 1.0;
+    if (!(h > 0) || !isfinite(h)) h = 1.0;
+    if (h < min_h) h = min_h;
+    int64_t ncell = 1;
+    for (int it = 0; it < 4096 && gs.valid; ++it) {    // keep the grid within the buffers the host sized
+        ncell = 1;
+        for (int a = 0; a < dim; ++a) {
+            double g = floor(ext[a] / h) + 1.0;
+            if (g > 1e9) g = 1e9;
+            gs.g[a] = (int)g;
+            ncell *= gs.g[a];
+        }
+        if (ncell <= cell_bound) break;
+        h *= 1.5;
+    }
+    if (!gs.valid) { gs.g[0] = gs.g[1] = gs.g[2] = 1; ncell = 1; }
+    gs.h = h;
+    gs.inv_h = 1.0 / h;
+    gs.ncell = ncell;
+    gs.strip_h = gs.g[1] < kStripH ? gs.g[1] : kStripH;
+    const int64_t nstrip = (gs.g[1] + gs.strip_h - 1) / gs.strip_h;
+    gs.nslot = (int64_t)gs.g[2] * nstrip * gs.strip_h * gs.g[0];       // < 2 * ncell
+    *out = gs;
+}
+
 // --------------------------------------------------------------- binning --
 __device__ __forceinline__ int cell_coord(double v, double lo, double inv_h, int g) {
     int c = (int)floor((v - lo) * inv_h);
     return min(max(c, 0), g - 1);
 }
 
-__global__ void cell_count_kernel(const double* __restrict__ xy, int64_t n, GridSpec gs, int32_t* __restrict__ cell_of,
-                                  int32_t* __restrict__ counts) {
+__global__ void cell_count_kernel(const double* __restrict__ xy, int64_t n, const GridSpec* __restrict__ gsp,
+                                  int32_t* __restrict__ cell_of, int32_t* __restrict__ counts) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const GridSpec gs = *gsp;
+    if (!gs.valid) { cell_of[i] = 0; atomicAdd(&counts[0], 1); return; }
     int c = 0, stride = 1;
     for (int a = 0; a < gs.dim; ++a) {
         c += cell_coord(xy[i * gs.dim + a], gs.lo[a], gs.inv_h, gs.g[a]) * stride;
@@ -97,9 +150,10 @@ __global__ void cell_scatter_kernel(const int32_t* __restrict__ cell_of, int64_t
 
 // order inside a cell came from atomics: sort each (tiny) cell segment by point id
 // so that the emitted processing order is deterministic
-__global__ void cell_sort_kernel(const int32_t* __restrict__ cell_start, int64_t ncell, int32_t* __restrict__ sorted_id) {
+__global__ void cell_sort_kernel(const int32_t* __restrict__ cell_start, const GridSpec* __restrict__ gsp,
+                                 int32_t* __restrict__ sorted_id) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (c >= ncell) return;
+    if (c >= gsp->ncell) return;
     int s = cell_start[c], e = cell_start[c + 1];
     for (int a = s + 1; a < e; ++a) {
         int v = sorted_id[a], b = a - 1;
@@ -125,30 +179,30 @@ __global__ void gather_sorted_kernel(const double* __restrict__ xy, int64_t n, i
 // kStripH cells, column by column, boustrophedon in both directions: consecutive cells are
 // spatial neighbours and the set of "recently visited" cells is a compact patch, so a kernel
 // that lets one SM walk a contiguous range of the order finds most neighbour rows in its L1.
-constexpr int kStripH = 8;
-
 __device__ __forceinline__ int64_t strip_slot(int c, const GridSpec& gs) {
-    const int gx = gs.g[0], gy = gs.g[1];
+    const int gx = gs.g[0], gy = gs.g[1], H = gs.strip_h;
     const int cx = c % gx, cy = (c / gx) % gy, cz = c / (gx * gy);
-    const int s = cy / kStripH, yl = cy - s * kStripH;
+    const int s = cy / H, yl = cy - s * H;
     const int xi = (s & 1) ? gx - 1 - cx : cx;
-    const int yi = (xi & 1) ? kStripH - 1 - yl : yl;
-    const int64_t nstrip = (gy + kStripH - 1) / kStripH;
-    return ((int64_t)cz * nstrip + s) * ((int64_t)kStripH * gx) + (int64_t)xi * kStripH + yi;
+    const int yi = (xi & 1) ? H - 1 - yl : yl;
+    const int64_t nstrip = (gy + H - 1) / H;
+    return ((int64_t)cz * nstrip + s) * ((int64_t)H * gx) + (int64_t)xi * H + yi;
 }
 
-__global__ void strip_count_kernel(const int32_t* __restrict__ cell_start, int64_t ncell, GridSpec gs,
+__global__ void strip_count_kernel(const int32_t* __restrict__ cell_start, const GridSpec* __restrict__ gsp,
                                    int32_t* __restrict__ slot_count) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (c >= ncell) return;
+    const GridSpec gs = *gsp;
+    if (c >= gs.ncell) return;
     slot_count[strip_slot((int)c, gs)] = cell_start[c + 1] - cell_start[c];
 }
 
 __global__ void strip_order_kernel(const int32_t* __restrict__ cell_start, const int32_t* __restrict__ sorted_id,
-                                   const int32_t* __restrict__ sorted_cell, int64_t n, GridSpec gs,
+                                   const int32_t* __restrict__ sorted_cell, int64_t n, const GridSpec* __restrict__ gsp,
                                    const int32_t* __restrict__ slot_start, int32_t* __restrict__ order) {
     int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (q >= n) return;
+    const GridSpec gs = *gsp;
     const int c = sorted_cell[q];
     order[slot_start[strip_slot(c, gs)] + (int)(q - cell_start[c])] = sorted_id[q];
 }
@@ -182,14 +236,19 @@ struct TopK {
 
 template <int KMAX, int DIM>
 __global__ void __launch_bounds__(128)
-knn_search_kernel(int64_t n, GridSpec gs, int kq, int k, int include_self, const int32_t* __restrict__ cell_start,
+knn_search_kernel(int64_t n, const GridSpec* __restrict__ gsp, int kq, int k, int include_self, const int32_t* __restrict__ cell_start,
                   const int32_t* __restrict__ sorted_id, const int32_t* __restrict__ sorted_cell,
                   const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
                   int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
     int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (q >= n) return;
-    const double qx = sx[q], qy = sy[q], qz = DIM == 3 ? sz[q] : 0.0;
+    const GridSpec gs = *gsp;
     const int32_t self = sorted_id[q];
+    if (!gs.valid) {                                   // non-finite coordinates: the caller sees index -1 / NaN
+        for (int j = 0; j < k; ++j) { out_idx[(int64_t)self * k + j] = -1; out_dist[(int64_t)self * k + j] = nan(""); }
+        return;
+    }
+    const double qx = sx[q], qy = sy[q], qz = DIM == 3 ? sz[q] : 0.0;
     int c = sorted_cell[q];
     const int cx = c % gs.g[0];
     const int cy = (c / gs.g[0]) % gs.g[1];
@@ -266,15 +325,20 @@ knn_search_kernel(int64_t n, GridSpec gs, int kq, int k, int include_self, const
 // (column-sorted: a canonical CSR) at its indptr offset.
 template <int DIM, int MODE>
 __global__ void __launch_bounds__(128)
-radius_search_kernel(int64_t n, GridSpec gs, double r2, int include_self, const int32_t* __restrict__ cell_start,
+radius_search_kernel(int64_t n, const GridSpec* __restrict__ gsp, double r2, int include_self, const int32_t* __restrict__ cell_start,
                      const int32_t* __restrict__ sorted_id, const int32_t* __restrict__ sorted_cell,
                      const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
                      int64_t* __restrict__ counts, const int64_t* __restrict__ indptr, int32_t* __restrict__ indices,
                      double* __restrict__ dist) {
     const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (q >= n) return;
-    const double qx = sx[q], qy = sy[q], qz = DIM == 3 ? sz[q] : 0.0;
+    const GridSpec gs = *gsp;
     const int32_t self = sorted_id[q];
+    if (!gs.valid) {                                   // non-finite coordinates: empty rows
+        if (!MODE) counts[self] = 0;
+        return;
+    }
+    const double qx = sx[q], qy = sy[q], qz = DIM == 3 ? sz[q] : 0.0;
     const int c = sorted_cell[q];
     const int gx = gs.g[0], gy = gs.g[1], gz = DIM == 3 ? gs.g[2] : 1;
     const int cx = c % gx, cy = (c / gx) % gy, cz = DIM == 3 ? c / (gx * gy) : 0;
@@ -363,80 +427,53 @@ using namespace laris;
 // ------------------------------------------------------------ point grid --
 // Everything the searches need: the grid shape and the cell-sorted copies of the points.
 struct PointGrid {
-    GridSpec gs;
-    int64_t ncell = 0;
+    int64_t cell_bound = 0;             // ncell <= cell_bound (enforced by grid_spec_kernel), nslot < 2 * cell_bound
+    Scratch<GridSpec> gs;
     Scratch<int32_t> cell_of, counts, cell_start, fill, sorted_id, sorted_cell;
     Scratch<double> sx, sy, sz;
     explicit PointGrid(cudaStream_t st)
-        : cell_of(st), counts(st), cell_start(st), fill(st), sorted_id(st), sorted_cell(st), sx(st), sy(st), sz(st) {}
+        : gs(st), cell_of(st), counts(st), cell_start(st), fill(st), sorted_id(st), sorted_cell(st), sx(st), sy(st), sz(st) {}
 };
 
-// Bins the points on a uniform grid of about `per_cell` points per cell whose cell edge is at least `min_h`
-// (one host sync: the grid shape depends on the bounding box).
+// Bins the points on a uniform grid of about `per_cell` points per cell whose cell edge is at least `min_h`.
+// Fully asynchronous: the grid shape stays on the device (GridSpec), buffers are sized by cell_bound = 2n + 1024.
 static int build_point_grid(const double* xy, int64_t n, int dim, double per_cell, double min_h, cudaStream_t st,
                             PointGrid& G, const char* who) {
+    (void)who;
     const int nb = kNumSMs * 2;
     Scratch<double> part(st), box_d(st);
     LARIS_CUDA(part.alloc(nb * 6));
     LARIS_CUDA(box_d.alloc(6));
+    LARIS_CUDA(G.gs.alloc(1));
     bbox_partial_kernel<<<nb, 256, 0, st>>>(xy, n, dim, part.p);
     LARIS_LAUNCH_CHECK();
     bbox_final_kernel<<<1, 192, 0, st>>>(part.p, nb, box_d.p);
     LARIS_LAUNCH_CHECK();
-    double box[6];
-    LARIS_CUDA(cudaMemcpyAsync(box, box_d.p, sizeof(box), cudaMemcpyDeviceToHost, st));
-    LARIS_CUDA(cudaStreamSynchronize(st));
-
-    GridSpec& gs = G.gs;
-    gs.dim = dim;
-    double ext[3] = {0, 0, 0}, vol = 1.0;
-    int nz_dims = 0;
-    for (int a = 0; a < dim; ++a) {
-        LARIS_CHECK_ARG(isfinite(box[a]) && isfinite(box[3 + a]), "%s: non-finite coordinates", who);
-        gs.lo[a] = box[a];
-        ext[a] = box[3 + a] - box[a];
-        if (ext[a] > 0) { vol *= ext[a]; ++nz_dims; }
-    }
-    for (int a = dim; a < 3; ++a) { gs.lo[a] = 0; gs.g[a] = 1; }
-    double h = nz_dims ? pow(vol * per_cell / (double)n, 1.0 / nz_dims) : 1.0;
-    if (!(h > 0) || !isfinite(h)) h = 1.0;
-    if (h < min_h) h = min_h;
-    int64_t ncell;
-    for (;;) {                                         // keep the grid within int32 / memory limits
-        ncell = 1;
-        for (int a = 0; a < dim; ++a) {
-            double g = floor(ext[a] / h) + 1.0;
-            if (g > 1e9) g = 1e9;
-            gs.g[a] = (int)g;
-            ncell *= gs.g[a];
-        }
-        if (ncell <= 4 * n + 1024) break;
-        h *= 1.5;
-    }
-    gs.h = h;
-    gs.inv_h = 1.0 / h;
-    G.ncell = ncell;
+    const int64_t bound = 2 * n + 1024;
+    G.cell_bound = bound;
+    grid_spec_kernel<<<1, 32, 0, st>>>(box_d.p, n, dim, per_cell, min_h, bound, G.gs.p);
+    LARIS_LAUNCH_CHECK();
 
     LARIS_CUDA(G.cell_of.alloc(n));
-    LARIS_CUDA(G.counts.alloc(ncell));
-    LARIS_CUDA(G.cell_start.alloc(ncell + 1));
-    LARIS_CUDA(G.fill.alloc(ncell));
+    LARIS_CUDA(G.counts.alloc(bound));
+    LARIS_CUDA(G.cell_start.alloc(bound + 1));
+    LARIS_CUDA(G.fill.alloc(bound));
     LARIS_CUDA(G.sorted_id.alloc(n));
     LARIS_CUDA(G.sorted_cell.alloc(n));
     LARIS_CUDA(G.sx.alloc(n));
     LARIS_CUDA(G.sy.alloc(n));
     LARIS_CUDA(G.sz.alloc(dim == 3 ? n : 1));
-    LARIS_CUDA(cudaMemsetAsync(G.counts.p, 0, ncell * sizeof(int32_t), st));
-    LARIS_CUDA(cudaMemsetAsync(G.fill.p, 0, ncell * sizeof(int32_t), st));
+    LARIS_CUDA(cudaMemsetAsync(G.counts.p, 0, bound * sizeof(int32_t), st));
+    LARIS_CUDA(cudaMemsetAsync(G.fill.p, 0, bound * sizeof(int32_t), st));
     const int T = 256;
-    const unsigned gn = (unsigned)ceil_div(n, T), gc = (unsigned)ceil_div(ncell, T);
-    cell_count_kernel<<<gn, T, 0, st>>>(xy, n, gs, G.cell_of.p, G.counts.p);
+    const unsigned gn = (unsigned)ceil_div(n, T), gc = (unsigned)ceil_div(bound, T);
+    cell_count_kernel<<<gn, T, 0, st>>>(xy, n, G.gs.p, G.cell_of.p, G.counts.p);
     LARIS_LAUNCH_CHECK();
-    int rc = exclusive_scan<int32_t>(G.counts.p, ncell, G.cell_start.p, st);
+    int rc = exclusive_scan<int32_t>(G.counts.p, bound, G.cell_start.p, st);     // cells past ncell are empty
     if (rc) return rc;
     cell_scatter_kernel<<<gn, T, 0, st>>>(G.cell_of.p, n, G.cell_start.p, G.fill.p, G.sorted_id.p);
     LARIS_LAUNCH_CHECK();
-    cell_sort_kernel<<<gc, T, 0, st>>>(G.cell_start.p, ncell, G.sorted_id.p);
+    cell_sort_kernel<<<gc, T, 0, st>>>(G.cell_start.p, G.gs.p, G.sorted_id.p);
     LARIS_LAUNCH_CHECK();
     gather_sorted_kernel<<<gn, T, 0, st>>>(xy, n, dim, G.sorted_id.p, G.cell_of.p, G.sx.p, G.sy.p, G.sz.p, G.sorted_cell.p);
     LARIS_LAUNCH_CHECK();
@@ -445,20 +482,18 @@ static int build_point_grid(const double* xy, int64_t n, int dim, double per_cel
 
 // cell segments re-dealt in strip order -> the processing order handed to the gather kernels
 static int emit_strip_order(const PointGrid& G, int64_t n, int32_t* out_order, cudaStream_t st) {
-    const GridSpec& gs = G.gs;
     const int T = 256;
-    const unsigned gn = (unsigned)ceil_div(n, T), gc = (unsigned)ceil_div(G.ncell, T);
-    const int64_t nstrip = ceil_div(gs.g[1], kStripH);
-    const int64_t nslot = (int64_t)gs.g[2] * nstrip * kStripH * gs.g[0];
+    const unsigned gn = (unsigned)ceil_div(n, T), gc = (unsigned)ceil_div(G.cell_bound, T);
+    const int64_t slot_bound = 2 * G.cell_bound;
     Scratch<int32_t> slot_count(st), slot_start(st);
-    LARIS_CUDA(slot_count.alloc(nslot));
-    LARIS_CUDA(slot_start.alloc(nslot + 1));
-    LARIS_CUDA(cudaMemsetAsync(slot_count.p, 0, nslot * sizeof(int32_t), st));
-    strip_count_kernel<<<gc, T, 0, st>>>(G.cell_start.p, G.ncell, gs, slot_count.p);
+    LARIS_CUDA(slot_count.alloc(slot_bound));
+    LARIS_CUDA(slot_start.alloc(slot_bound + 1));
+    LARIS_CUDA(cudaMemsetAsync(slot_count.p, 0, slot_bound * sizeof(int32_t), st));
+    strip_count_kernel<<<gc, T, 0, st>>>(G.cell_start.p, G.gs.p, slot_count.p);
     LARIS_LAUNCH_CHECK();
-    int rc = exclusive_scan<int32_t>(slot_count.p, nslot, slot_start.p, st);
+    int rc = exclusive_scan<int32_t>(slot_count.p, slot_bound, slot_start.p, st);
     if (rc) return rc;
-    strip_order_kernel<<<gn, T, 0, st>>>(G.cell_start.p, G.sorted_id.p, G.sorted_cell.p, n, gs, slot_start.p, out_order);
+    strip_order_kernel<<<gn, T, 0, st>>>(G.cell_start.p, G.sorted_id.p, G.sorted_cell.p, n, G.gs.p, slot_start.p, out_order);
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
 }
@@ -475,7 +510,7 @@ extern "C" int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int 
     PointGrid G(st);
     int rc = build_point_grid(xy, n, dim, 2.5, 0.0, st, G, "laris_knn_graph");
     if (rc) return rc;
-    const GridSpec gs = G.gs;
+    const GridSpec* gs = G.gs.p;
     Scratch<int32_t>&cell_start = G.cell_start, &sorted_id = G.sorted_id, &sorted_cell = G.sorted_cell;
     Scratch<double>&sx = G.sx, &sy = G.sy, &sz = G.sz;
 
@@ -511,7 +546,7 @@ static int radius_graph_pass(const double* xy, int64_t n, int dim, double radius
     const unsigned gq = (unsigned)ceil_div(n, 128);
     const double r2 = radius * radius;
 #define LARIS_RADIUS_LAUNCH(DIM, MODE)                                                                              \
-    radius_search_kernel<DIM, MODE><<<gq, 128, 0, st>>>(n, G.gs, r2, include_self, G.cell_start.p, G.sorted_id.p,   \
+    radius_search_kernel<DIM, MODE><<<gq, 128, 0, st>>>(n, G.gs.p, r2, include_self, G.cell_start.p, G.sorted_id.p,   \
                                                         G.sorted_cell.p, G.sx.p, G.sy.p, G.sz.p, counts, indptr,    \
                                                         indices, dist)
     if (dim == 2) { if (mode) LARIS_RADIUS_LAUNCH(2, 1); else LARIS_RADIUS_LAUNCH(2, 0); }

@@ -50,11 +50,24 @@ class SpatialGraph:
                               np.arange(0, n * k + 1, k, dtype=np.int64)), shape=(n, n))
 
 
-def build_graph(xy, k, include_self, sigma=None) -> SpatialGraph:
-    """kNN graph + decay weights (K1).  ``sigma=None`` -> s = mean(d)/2."""
-    xy_d = xy if torch.is_tensor(xy) else K.to_device(np.asarray(xy, dtype=np.float64), torch.float64)
+def _coords_to_device(xy):
+    """Coordinates as an fp64 device tensor.  Host arrays are checked for NaN / inf here: the device graph build is
+    asynchronous and can only flag non-finite coordinates in its outputs (index -1)."""
+    if torch.is_tensor(xy):
+        xy_d = xy
+    else:
+        xy = np.asarray(xy, dtype=np.float64)
+        if xy.ndim == 2 and not np.isfinite(xy).all():
+            raise ValueError("spatial coordinates contain NaN or infinite values")
+        xy_d = K.to_device(xy, torch.float64)
     if xy_d.dim() != 2 or xy_d.shape[1] not in (2, 3):
         raise ValueError(f"spatial coordinates must be n x 2 or n x 3, got {tuple(xy_d.shape)}")
+    return xy_d
+
+
+def build_graph(xy, k, include_self, sigma=None) -> SpatialGraph:
+    """kNN graph + decay weights (K1).  ``sigma=None`` -> s = mean(d)/2."""
+    xy_d = _coords_to_device(xy)
     idx, dist, order = K.knn_graph(xy_d.contiguous(), int(k), include_self)
     w32, w64, scale = K.decay_weights(dist, sigma, want64=True)
     return SpatialGraph(idx, dist, w32, w64, order, scale, bool(include_self))
@@ -66,9 +79,7 @@ def build_radius_graph(xy, radius, include_self, sigma=None) -> SpatialGraph:
     The variable-degree CSR is kept in ``csr``; ``idx``/``w`` hold the same rows padded to the maximum degree with
     (own row, weight 0) edges, which is the fixed-degree layout every gather kernel takes.  ``sigma=None`` uses
     s = mean(stored distances)/2, the reference's rule for its kNN graphs."""
-    xy_d = xy if torch.is_tensor(xy) else K.to_device(np.asarray(xy, dtype=np.float64), torch.float64)
-    if xy_d.dim() != 2 or xy_d.shape[1] not in (2, 3):
-        raise ValueError(f"spatial coordinates must be n x 2 or n x 3, got {tuple(xy_d.shape)}")
+    xy_d = _coords_to_device(xy)
     indptr, indices, dist, order = K.radius_graph(xy_d.contiguous(), float(radius), include_self)
     if dist.numel() == 0:
         raise ValueError(f"radius={radius} leaves every cell without a neighbour")

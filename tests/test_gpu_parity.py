@@ -778,3 +778,14 @@ def test_runlaris_on_radius_graphs(dev):
     laris_lr, table = la.tl.runLARIS(lr_adata, a, n_repeats=2, n_top_lr=60, n_cells_expressed_threshold=5, n_permutations=50,
                                      rng="philox", verbose=False, radius=radius)
     assert len(laris_lr) == 60 and len(table) == 60 * c.C * c.C and np.isfinite(table["interaction_score"]).all()
+
+
+def test_non_finite_coordinates(dev):
+    """Host arrays are rejected up front; a device tensor with a NaN is flagged in the outputs (the build is asynchronous)."""
+    from laris_b200 import engine, _kernels as K
+    xy = _coords("uniform", 500)
+    xy[17, 1] = np.nan
+    with pytest.raises(ValueError, match="NaN or infinite"):
+        engine.build_graph(xy, 5, True)
+    idx, dist, _ = K.knn_graph(torch.from_numpy(xy).to(dev), 5, True)
+    assert (idx.cpu().numpy() == -1).all() and np.isnan(dist.cpu().numpy()).all()
