@@ -258,7 +258,10 @@ LARIS_API int laris_onehot_contract_csr(const int64_t* indptr, const int64_t* pa
  * rng_mode 1: draws [n_groups*n_slots*n_perm] uint8 supplied by the caller
  *   (host replay of the reference's numpy stream).
  *   table [n_groups*ldt] fp64, bg [n_slots*nb] int32, active [n_slots] uint8 or NULL
- *   ge, nz, ge_nz [n_groups*n_slots] int32, accumulated into (zero them first)
+ *   ge, nz, ge_nz [n_groups*n_slots] int32, accumulated into (zero them first); nz and ge_nz may both be
+ *   NULL when only the standard p-value is wanted (they feed the conditional variant, :1573-1590)
+ * Philox draws: for nb <= 64 each 32-bit word w gives three draws, the first three base-nb digits of w/2^32
+ * (idx = (w*nb) >> 32; w = (w*nb) mod 2^32), so permutation t uses word (t/3)%4 of call t/12; else one per word.
  */
 LARIS_API int laris_pvalue_counts(const double* table, int64_t ldt, int32_t n_groups, int32_t n_slots,
                         const int32_t* bg, int32_t nb, const uint8_t* active, const int64_t* slot_gid,

@@ -293,12 +293,14 @@ def row_qc(S, P, top_n=()):
 
 # -------------------------------------------------------------- K6/K7 ----
 def pvalue_counts(table, bg, n_perm, *, active=None, seed=0, draws=None, slot_gid=None, P_global=None, g0=0, t0=0,
-                  out=None):
+                  out=None, only_ge=False):
+    """Exceedance counts (ge, nz, ge_nz) - or (ge, None, None) with ``only_ge`` (the standard p-value needs no more)."""
     Gn, ldt = table.shape
     P, nb = bg.shape
     dev = table.device
     if out is None:
-        out = tuple(torch.zeros((Gn, P), dtype=torch.int32, device=dev) for _ in range(3))
+        out = tuple(torch.zeros((Gn, P), dtype=torch.int32, device=dev) if (i == 0 or not only_ge) else None
+                    for i in range(3))
     ge, nz, both = out
     check(lib.laris_pvalue_counts(_ptr(table, torch.float64), ldt, Gn, P, _ptr(bg, torch.int32), nb,
                                   _ptr(active, torch.uint8) if active is not None else None,
@@ -306,7 +308,8 @@ def pvalue_counts(table, bg, n_perm, *, active=None, seed=0, draws=None, slot_gi
                                   int(P if P_global is None else P_global), int(g0), int(t0), int(n_perm),
                                   0 if draws is None else 1, int(seed) & (2 ** 64 - 1),
                                   _ptr(draws, torch.uint8) if draws is not None else None,
-                                  _ptr(ge), _ptr(nz), _ptr(both), _stream()), "laris_pvalue_counts")
+                                  _ptr(ge), _ptr(nz) if nz is not None else None,
+                                  _ptr(both) if both is not None else None, _stream()), "laris_pvalue_counts")
     return ge, nz, both
 
 

@@ -3,9 +3,13 @@
 //
 // K6: one warp per (group, pair) row.  The nb candidate null values of the row
 // (scores of the pair's background pairs inside the same sender-receiver group)
-// are staged once in shared memory; each lane then turns Philox outputs into
-// draws (4 per call) and compares.  The score table (C^2 x P fp64) is read once
-// per row and stays L2-resident; the kernel is integer-ALU bound.
+// are compared with the observed score ONCE: what a draw contributes is two bits
+// per candidate (null >= obs, null > 0), held as register bitmasks (nb <= 32) or
+// flag bytes in shared memory.  Each lane then turns Philox outputs into draws -
+// for nb <= 64 three per 32-bit word (the first three base-nb digits of w / 2^32:
+// idx = umulhi(w, nb); w *= nb; independent and uniform to nb^3 / 2^32 < 6.2e-5),
+// i.e. 12 per Philox call - and adds the bits.  The score table (C^2 x P fp64) is
+// read once per row and stays L2-resident; the kernel is integer-ALU bound.
 #include <math.h>
 
 #include "common.cuh"
@@ -16,53 +20,90 @@ namespace laris {
 constexpr int kPvWarps = 8;
 constexpr int kPvMaxNb = 256;
 
+// SMALL: nb <= 32 (register bitmasks); DIGITS: draws per 32-bit word; ALL3: also count nz / ge_nz (only the
+// conditional p-value needs them - the default path adds one bit per draw)
+template <bool SMALL, int DIGITS, bool ALL3>
 __global__ void __launch_bounds__(kPvWarps * 32)
 pvalue_counts_kernel(const double* __restrict__ table, int64_t ldt, int n_groups, int n_slots,
                      const int32_t* __restrict__ bg, int nb, const uint8_t* __restrict__ active,
                      const int64_t* __restrict__ slot_gid, int64_t P_global, int g0, int t0, int n_perm, int rng_mode,
                      uint64_t seed, const uint8_t* __restrict__ draws, int32_t* __restrict__ ge, int32_t* __restrict__ nz,
                      int32_t* __restrict__ ge_nz) {
-    __shared__ double nullv[kPvWarps][kPvMaxNb];
+    __shared__ uint8_t flagv[kPvWarps][kPvMaxNb];                   // bit 0: null >= obs, bit 1: null > 0
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int per_call = 4 * DIGITS;
     const int64_t nrows = (int64_t)n_groups * n_slots;
     for (int64_t r = (int64_t)blockIdx.x * kPvWarps + warp; r < nrows; r += (int64_t)gridDim.x * kPvWarps) {
         const int g = (int)(r / n_slots), s = (int)(r - (int64_t)g * n_slots);
         if (active && !active[s]) continue;                         // warp-uniform
         const double* trow = table + (int64_t)g * ldt;
         const double obs = trow[s];
+        uint32_t mask_ge = 0u, mask_nz = 0u;                        // nb <= 32: the two bits of candidate m, bit m
         __syncwarp();
-        for (int m = lane; m < nb; m += 32) nullv[warp][m] = trow[bg[(int64_t)s * nb + m]];
+        for (int m0 = 0; m0 < nb; m0 += 32) {
+            const int m = m0 + lane;
+            bool a = false, b = false;
+            if (m < nb) {
+                const double v = trow[bg[(int64_t)s * nb + m]];
+                a = v >= obs;
+                b = v > 0.0;
+                flagv[warp][m] = (uint8_t)((a ? 1 : 0) | (b ? 2 : 0));
+            }
+            if (m0 == 0) { mask_ge = __ballot_sync(0xffffffffu, a); mask_nz = __ballot_sync(0xffffffffu, b); }
+        }
         __syncwarp();
+        const uint32_t mask_both = mask_ge & mask_nz;
         int c_ge = 0, c_nz = 0, c_both = 0;
+        auto count = [&](uint32_t idx) {
+            if (SMALL) {
+                c_ge += (mask_ge >> idx) & 1u;
+                if (ALL3) { c_nz += (mask_nz >> idx) & 1u; c_both += (mask_both >> idx) & 1u; }
+            } else {
+                const uint32_t f = flagv[warp][idx];
+                c_ge += f & 1u;
+                if (ALL3) { c_nz += (f >> 1) & 1u; c_both += f == 3u; }
+            }
+        };
         if (rng_mode == 0) {
             const uint64_t grow = (uint64_t)(g0 + g) * (uint64_t)P_global + (uint64_t)(slot_gid ? slot_gid[s] : s);
-            const int q_beg = t0 >> 2, q_end = (t0 + n_perm + 3) >> 2;
+            const int q_beg = t0 / per_call, q_end = (t0 + n_perm + per_call - 1) / per_call;
             for (int q = q_beg + lane; q < q_end; q += 32) {
                 const u32x4 o = philox4x32_10((uint32_t)q, (uint32_t)grow, (uint32_t)(grow >> 32), kStreamPval, seed);
                 const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
+                const int tq = q * per_call;
+                if (tq >= t0 && tq + per_call <= t0 + n_perm) {      // every draw of this call is in range: straight-line code
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int t = q * 4 + u;
-                    if (t >= t0 && t < t0 + n_perm) {
-                        const double v = nullv[warp][__umulhi(ov[u], (uint32_t)nb)];
-                        const bool a = v >= obs, b = v > 0.0;
-                        c_ge += a; c_nz += b; c_both += a && b;
+                    for (int u = 0; u < 4; ++u) {
+                        uint32_t wv = ov[u];
+#pragma unroll
+                        for (int j = 0; j < DIGITS; ++j) {
+                            count(__umulhi(wv, (uint32_t)nb));
+                            wv *= (uint32_t)nb;
+                        }
+                    }
+                } else {                                             // first / last call of a permutation shard
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint32_t wv = ov[u];
+#pragma unroll
+                        for (int j = 0; j < DIGITS; ++j) {
+                            const uint32_t idx = __umulhi(wv, (uint32_t)nb);
+                            wv *= (uint32_t)nb;
+                            const int t = tq + u * DIGITS + j;
+                            if (t >= t0 && t < t0 + n_perm) count(idx);
+                        }
                     }
                 }
             }
         } else {
             const uint8_t* d = draws + r * (int64_t)n_perm;
-            for (int t = lane; t < n_perm; t += 32) {
-                const double v = nullv[warp][d[t]];
-                const bool a = v >= obs, b = v > 0.0;
-                c_ge += a; c_nz += b; c_both += a && b;
-            }
+            for (int t = lane; t < n_perm; t += 32) count(d[t]);
         }
-        c_ge = warp_sum(c_ge); c_nz = warp_sum(c_nz); c_both = warp_sum(c_both);
+        c_ge = __reduce_add_sync(0xffffffffu, c_ge);
+        if (ALL3) { c_nz = __reduce_add_sync(0xffffffffu, c_nz); c_both = __reduce_add_sync(0xffffffffu, c_both); }
         if (lane == 0) {
             ge[r] += c_ge;                                          // one warp per row: plain RMW
-            nz[r] += c_nz;
-            ge_nz[r] += c_both;
+            if (ALL3) { nz[r] += c_nz; ge_nz[r] += c_both; }
         }
     }
 }
@@ -129,7 +170,7 @@ extern "C" int laris_pvalue_counts(const double* table, int64_t ldt, int32_t n_g
                                    int32_t nb, const uint8_t* active, const int64_t* slot_gid, int64_t P_global,
                                    int32_t g0, int32_t t0, int32_t n_perm, int rng_mode, uint64_t seed,
                                    const uint8_t* draws, int32_t* ge, int32_t* nz, int32_t* ge_nz, void* stream) {
-    LARIS_CHECK_ARG(table && bg && ge && nz && ge_nz, "laris_pvalue_counts: null pointer");
+    LARIS_CHECK_ARG(table && bg && ge && ((nz != nullptr) == (ge_nz != nullptr)), "laris_pvalue_counts: null pointer");
     LARIS_CHECK_ARG(n_groups >= 1 && n_slots >= 1 && ldt >= n_slots && n_perm >= 0, "laris_pvalue_counts: bad sizes");
     LARIS_CHECK_ARG(nb >= 1 && nb <= kPvMaxNb, "laris_pvalue_counts: nb must be in [1,%d] (got %d)", kPvMaxNb, nb);
     LARIS_CHECK_ARG(rng_mode == 0 || (rng_mode == 1 && draws), "laris_pvalue_counts: rng_mode 1 needs host draws");
@@ -137,8 +178,14 @@ extern "C" int laris_pvalue_counts(const double* table, int64_t ldt, int32_t n_g
     const int64_t nrows = (int64_t)n_groups * n_slots;
     int64_t grid = ceil_div(nrows, kPvWarps);
     if (grid > (int64_t)kNumSMs * 16) grid = (int64_t)kNumSMs * 16;
-    pvalue_counts_kernel<<<(unsigned)grid, kPvWarps * 32, 0, (cudaStream_t)stream>>>(
-        table, ldt, n_groups, n_slots, bg, nb, active, slot_gid, P_global, g0, t0, n_perm, rng_mode, seed, draws, ge, nz, ge_nz);
+    const bool all3 = nz != nullptr;
+#define LARIS_PV_LAUNCH(SMALL, DIGITS, ALL3)                                                                        \
+    pvalue_counts_kernel<SMALL, DIGITS, ALL3><<<(unsigned)grid, kPvWarps * 32, 0, (cudaStream_t)stream>>>(          \
+        table, ldt, n_groups, n_slots, bg, nb, active, slot_gid, P_global, g0, t0, n_perm, rng_mode, seed, draws, ge, nz, ge_nz)
+    if (nb <= 32) { if (all3) LARIS_PV_LAUNCH(true, 3, true); else LARIS_PV_LAUNCH(true, 3, false); }
+    else if (nb <= 64) { if (all3) LARIS_PV_LAUNCH(false, 3, true); else LARIS_PV_LAUNCH(false, 3, false); }
+    else { if (all3) LARIS_PV_LAUNCH(false, 1, true); else LARIS_PV_LAUNCH(false, 1, false); }
+#undef LARIS_PV_LAUNCH
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
 }

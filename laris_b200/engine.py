@@ -427,7 +427,7 @@ def cosg_gene_scores(xu: ExpressionU, labels_d, C, n_c, mu, expressed_pct, remov
 
 
 # --------------------------------------------------------------- p-values ----
-def pvalue_counts(table, bg, active, n_perm, *, rng="philox", seed=0, draws=None, t0=0):
+def pvalue_counts(table, bg, active, n_perm, *, rng="philox", seed=0, draws=None, t0=0, only_ge=False):
     """Exceedance counts (K6).  ``table`` [groups,P] fp64 host, ``bg`` [P,nb] host."""
     t = K.to_device(np.ascontiguousarray(table, dtype=np.float64), torch.float64)
     b = K.to_device(np.ascontiguousarray(bg, dtype=np.int32), torch.int32)
@@ -440,7 +440,10 @@ def pvalue_counts(table, bg, active, n_perm, *, rng="philox", seed=0, draws=None
     if n_perm == 0:
         z = np.zeros(t.shape, dtype=np.int32)
         return z, z.copy(), z.copy()
-    ge, nz, both = K.pvalue_counts(t, b, n_perm, active=a, seed=seed, draws=d, t0=t0)
+    ge, nz, both = K.pvalue_counts(t, b, n_perm, active=a, seed=seed, draws=d, t0=t0, only_ge=only_ge)
+    if only_ge:
+        ge = ge.cpu().numpy()
+        return ge, np.zeros_like(ge), np.zeros_like(ge)
     return ge.cpu().numpy(), nz.cpu().numpy(), both.cpu().numpy()
 
 

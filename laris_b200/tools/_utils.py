@@ -440,12 +440,14 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_r
     elif rng != "philox":
         raise ValueError(f"rng must be 'numpy' or 'philox', got {rng!r}")
     if shard is None:
-        ge, nz, both = engine.pvalue_counts(table, bg, active, n_permutations, rng=rng, seed=random_seed, draws=draws)
+        ge, nz, both = engine.pvalue_counts(table, bg, active, n_permutations, rng=rng, seed=random_seed, draws=draws,
+                                            only_ge=not use_conditional_pvalue)
     else:                       # permutations [t0, t1) on this rank; exceedance counts are integers, so the sum is exact
         pb = _dist.perm_bounds(n_permutations, shard.world)
         t0, t1 = int(pb[shard.rank]), int(pb[shard.rank + 1])
         part = engine.pvalue_counts(table, bg, active, t1 - t0, rng=rng, seed=random_seed, t0=t0,
-                                    draws=None if draws is None else np.ascontiguousarray(draws[:, :, t0:t1]))
+                                    draws=None if draws is None else np.ascontiguousarray(draws[:, :, t0:t1]),
+                                    only_ge=not use_conditional_pvalue)
         ge, nz, both = _dist.all_reduce_sum(np.stack(part).astype(np.int64))
     if use_conditional_pvalue:
         p_tab = np.ones_like(table)

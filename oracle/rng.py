@@ -114,12 +114,23 @@ def feistel_permutation(m: int, repeat: int, seed: int, idx=None):
 
 
 def philox_pvalue_draws(row_ids, n_perm: int, nb: int, seed: int):
-    """draws[row, t] in [0, nb) for global row ids (row = group * P + pair)."""
+    """draws[row, t] in [0, nb) for global row ids (row = group * P + pair).
+
+    For nb <= 64 every 32-bit Philox word w yields three draws, the first three base-nb digits of w / 2^32
+    (d = (w * nb) >> 32; w = (w * nb) mod 2^32), so one Philox call covers 12 permutations; else one draw per word."""
+    digits = 3 if nb <= 64 else 1
+    per_call = 4 * digits
     row = np.asarray(row_ids, dtype=np.uint64)[:, None]
-    q = np.arange((n_perm + 3) // 4, dtype=np.uint64)[None, :]
+    q = np.arange((n_perm + per_call - 1) // per_call, dtype=np.uint64)[None, :]
     outs = philox4x32(q, row & MASK32, row >> np.uint64(32), STREAM_PVAL, seed)
-    o = np.stack(outs, axis=-1).reshape(row.shape[0], -1)[:, :n_perm].astype(np.uint64)
-    return ((o * np.uint64(nb)) >> np.uint64(32)).astype(np.int64)
+    w = np.stack(outs, axis=-1).astype(np.uint64)                      # [rows, calls, 4]
+    ds = []
+    for _ in range(digits):
+        x = w * np.uint64(nb)
+        ds.append(x >> np.uint64(32))
+        w = x & MASK32
+    d = np.stack(ds, axis=-1).reshape(row.shape[0], -1)[:, :n_perm]    # [rows, calls * 4 * digits]
+    return d.astype(np.int64)
 
 
 # ---------------------------------------------------------------------------

@@ -789,3 +789,22 @@ def test_non_finite_coordinates(dev):
         engine.build_graph(xy, 5, True)
     idx, dist, _ = K.knn_graph(torch.from_numpy(xy).to(dev), 5, True)
     assert (idx.cpu().numpy() == -1).all() and np.isnan(dist.cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("nb", [7, 30, 32, 33, 64, 65, 200])
+def test_pvalue_counts_candidate_set_sizes(dev, nb):
+    """Every code path of K6 (register masks / flag bytes, 3 or 1 draws per Philox word, ge-only or all three
+    counts) against the oracle fed the CPU twin of the device draws."""
+    from laris_b200 import engine
+    from oracle import restate as R, rng as orng
+    rng = np.random.default_rng(nb)
+    groups, P, N = 5, max(nb + 1, 40), 157
+    table = rng.random((groups, P)) * (rng.random((groups, P)) < 0.6)
+    active = np.ones(P, np.uint8)
+    bg = np.stack([rng.permutation(P)[:nb] for _ in range(P)]).astype(np.int32)
+    ref = R.pvalue_counts(table, active.astype(bool), bg.astype(np.int64),
+                          lambda g, pidx: orng.philox_pvalue_draws(g * P + pidx, N, nb, 11))
+    ge, nz, both = engine.pvalue_counts(table, bg, active, N, rng="philox", seed=11)
+    assert np.array_equal(ge, ref[0]) and np.array_equal(nz, ref[1]) and np.array_equal(both, ref[2])
+    ge1, _, _ = engine.pvalue_counts(table, bg, active, N, rng="philox", seed=11, only_ge=True)
+    assert np.array_equal(ge1, ref[0])

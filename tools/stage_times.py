@@ -59,6 +59,7 @@ T("onehot_contract_csr", lambda: K.onehot_contract_csr(xu_indptr, xu_packed, len
 rng = np.random.default_rng(0)
 table = K.to_device(rng.random((c.C * c.C, P)), torch.float64)
 bg = K.to_device(np.stack([rng.permutation(P)[:30] for _ in range(P)]).astype(np.int32), torch.int32)
-T("pvalue_counts(N=1000)", lambda: K.pvalue_counts(table, bg, 1000, seed=27))
+T("pvalue_counts(N=1000, standard)", lambda: K.pvalue_counts(table, bg, 1000, seed=27, only_ge=True))
+T("pvalue_counts(N=1000, conditional)", lambda: K.pvalue_counts(table, bg, 1000, seed=27))
 pv = K.to_device(np.round(rng.random((c.C * c.C, P)), 6), torch.float64); sel = K.to_device(np.ones((c.C * c.C, P), np.uint8), torch.uint8)
 T("bh_fdr", lambda: K.bh_fdr(pv, sel))
