@@ -106,6 +106,13 @@ LARIS_API int laris_csr_select_count(const int64_t* indptr, const int32_t* indic
 LARIS_API int laris_csr_select_fill(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
                           const int32_t* gene_map, const int64_t* out_indptr, int64_t* out_packed,
                           void* stream);
+/* Single-pass variant of the two calls above: the kept entries of row r are written to
+ * out_packed[indptr[r] ...) - every row keeps its offset in the INPUT matrix, so neither a count pass nor a
+ * scan nor a host read of the total is needed - and row_end[r] (int64 [n]) marks where they stop.
+ * out_packed needs nnz(X) slots.  Consumers take (row_start = indptr, row_end): laris_diffuse_lr_score_rows,
+ * laris_onehot_contract_rows. */
+LARIS_API int laris_csr_select_rows(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
+                          const int32_t* gene_map, int64_t* out_packed, int64_t* row_end, void* stream);
 /* out[0]=0, out[i+1]=sum(in[0..i]); in [n], out [n+1]; may alias in == out+1 is NOT allowed. */
 LARIS_API int laris_exclusive_scan_i64(const int64_t* in, int64_t n, int64_t* out, void* stream);
 
@@ -158,6 +165,13 @@ LARIS_API int laris_diffuse_lr_score_complex(const int64_t* xu_indptr, const int
                            const int32_t* lig, const int32_t* rec, int32_t P,
                            float* S, int64_t ldS, int64_t* row_nnz, const int32_t* cx_ptr, const int32_t* cx_cols,
                            const int32_t* cx_vcol, int32_t n_complex, int32_t rule, void* stream);
+/* laris_diffuse_lr_score_complex over rows given as [row_start[i], row_end[i]) ranges of xu_packed (the layout
+ * laris_csr_select_rows produces; for a compact CSR pass indptr and indptr + 1). */
+LARIS_API int laris_diffuse_lr_score_rows(const int64_t* row_start, const int64_t* row_end, const int64_t* xu_packed,
+                           int64_t n, int32_t G_u, const int32_t* idx, const float* w, int k, const int32_t* order,
+                           const int32_t* lig, const int32_t* rec, int32_t P, float* S, int64_t ldS, int64_t* row_nnz,
+                           const int32_t* cx_ptr, const int32_t* cx_cols, const int32_t* cx_vcol, int32_t n_complex,
+                           int32_t rule, void* stream);
 LARIS_API int laris_diffuse_lr_score_dense_complex(const float* Xd, int64_t ldX, const int32_t* neg_flag, int64_t n,
                            int32_t G_u, const int32_t* idx, const float* w, int k, const int32_t* order,
                            const int32_t* lig, const int32_t* rec, int32_t P, float* S, int64_t ldS, int64_t* row_nnz,
@@ -243,6 +257,10 @@ LARIS_API int laris_celltype_nonzero_count(const float* S, int64_t ldS, int64_t 
  * laris/tools/_utils.py:580-588) and its low-expression mask.  fp64 outputs. */
 LARIS_API int laris_onehot_contract_csr(const int64_t* indptr, const int64_t* packed, int64_t n, int32_t G_u,
                               const int32_t* labels, int32_t C, double* sum, double* cnt, double* colsq,
+                              void* stream);
+/* The same over [row_start[i], row_end[i]) ranges (see laris_csr_select_rows). */
+LARIS_API int laris_onehot_contract_rows(const int64_t* row_start, const int64_t* row_end, const int64_t* packed, int64_t n,
+                              int32_t G_u, const int32_t* labels, int32_t C, double* sum, double* cnt, double* colsq,
                               void* stream);
 
 /* ---------------------------------------------------------------- K6 ----

@@ -124,6 +124,18 @@ def csr_select(indptr, indices, data, gene_map):
     return out_indptr, packed[:nnz] if nnz else packed[:0]
 
 
+def csr_select_rows(indptr, indices, data, gene_map):
+    """Single-pass selection: (packed int64 [nnz(X)], row_end int64 [n]); row i's kept entries are
+    packed[indptr[i] : row_end[i]].  No count pass, no scan, no host sync; costs nnz(X) slots."""
+    n = indptr.numel() - 1
+    packed = torch.empty(max(int(indices.numel()), 1), dtype=torch.int64, device=indptr.device)
+    row_end = torch.empty(max(n, 1), dtype=torch.int64, device=indptr.device)
+    check(lib.laris_csr_select_rows(_ptr(indptr, torch.int64), _ptr(indices, torch.int32), _ptr(data, torch.float32), n,
+                                    _ptr(gene_map, torch.int32), _ptr(packed), _ptr(row_end), _stream()),
+          "laris_csr_select_rows")
+    return packed, row_end
+
+
 # -------------------------------------------------------------- K2+K3 ----
 def lr_column_layout(lig_u, rec_u, n_genes):
     """Host call: (column_of [n_genes] int32, n_columns)."""
@@ -147,17 +159,20 @@ def _cx_args(cx):
     return _ptr(ptr, torch.int32), _ptr(cols, torch.int32), _ptr(vcol, torch.int32), int(vcol.numel()), int(rule)
 
 
-def diffuse_lr_score(xu_indptr, xu_packed, G_u, idx, w, order, lig, rec, want_row_nnz=True, cx=None):
+def diffuse_lr_score(xu_indptr, xu_packed, G_u, idx, w, order, lig, rec, want_row_nnz=True, cx=None, row_end=None):
+    """``row_end=None``: compact rows (row i = packed[indptr[i]:indptr[i+1]]); else row i = packed[indptr[i]:row_end[i]]."""
     n, k = idx.shape
     P = lig.numel()
     ld = padded_ld(P)
     S = torch.empty((n, ld), dtype=torch.float32, device=idx.device)
     row_nnz = torch.empty(n, dtype=torch.int64, device=idx.device) if want_row_nnz else None
     packed_ptr = xu_packed.data_ptr() if xu_packed.numel() else _ptr(torch.zeros(1, dtype=torch.int64, device=idx.device))
-    check(lib.laris_diffuse_lr_score_complex(_ptr(xu_indptr, torch.int64), packed_ptr, n, G_u, _ptr(idx, torch.int32),
-                                             _ptr(w, torch.float32), k, _ptr(order, torch.int32) if order is not None else None,
-                                             _ptr(lig, torch.int32), _ptr(rec, torch.int32), P, _ptr(S), ld, _ptr(row_nnz),
-                                             *_cx_args(cx), _stream()), "laris_diffuse_lr_score")
+    start = _ptr(xu_indptr, torch.int64)
+    end = start + 8 if row_end is None else _ptr(row_end, torch.int64)
+    check(lib.laris_diffuse_lr_score_rows(start, end, packed_ptr, n, G_u, _ptr(idx, torch.int32),
+                                          _ptr(w, torch.float32), k, _ptr(order, torch.int32) if order is not None else None,
+                                          _ptr(lig, torch.int32), _ptr(rec, torch.int32), P, _ptr(S), ld, _ptr(row_nnz),
+                                          *_cx_args(cx), _stream()), "laris_diffuse_lr_score")
     return S, row_nnz
 
 
@@ -267,15 +282,17 @@ def celltype_nonzero_count(S, P, labels, C):
     return cnt
 
 
-def onehot_contract_csr(xu_indptr, xu_packed, G_u, labels, C):
+def onehot_contract_csr(xu_indptr, xu_packed, G_u, labels, C, row_end=None):
     n = xu_indptr.numel() - 1
     dev = xu_indptr.device
     s = torch.empty((C, G_u), dtype=torch.float64, device=dev)
     c = torch.empty((C, G_u), dtype=torch.float64, device=dev)
     q = torch.empty(G_u, dtype=torch.float64, device=dev)
     packed_ptr = xu_packed.data_ptr() if xu_packed.numel() else None
-    check(lib.laris_onehot_contract_csr(_ptr(xu_indptr, torch.int64), packed_ptr, n, G_u, _ptr(labels, torch.int32), C,
-                                        _ptr(s), _ptr(c), _ptr(q), _stream()), "laris_onehot_contract_csr")
+    start = _ptr(xu_indptr, torch.int64)
+    end = start + 8 if row_end is None else _ptr(row_end, torch.int64)
+    check(lib.laris_onehot_contract_rows(start, end, packed_ptr, n, G_u, _ptr(labels, torch.int32), C,
+                                         _ptr(s), _ptr(c), _ptr(q), _stream()), "laris_onehot_contract_csr")
     return s, c, q
 
 

@@ -31,9 +31,11 @@ SIGNATURES = {
     "laris_csr_pad_rows": [_p, _p, _p, _i64, _i, _p, _p, _p],
     "laris_csr_select_count": [_p, _p, _p, _i64, _p, _p, _p],
     "laris_csr_select_fill": [_p, _p, _p, _i64, _p, _p, _p, _p],
+    "laris_csr_select_rows": [_p, _p, _p, _i64, _p, _p, _p, _p],
     "laris_exclusive_scan_i64": [_p, _i64, _p, _p],
     "laris_diffuse_lr_score": [_p, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i64, _p, _p],
     "laris_diffuse_lr_score_complex": [_p, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i64, _p, _p, _p, _p, _i, _i, _p],
+    "laris_diffuse_lr_score_rows": [_p, _p, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i64, _p, _p, _p, _p, _i, _i, _p],
     "laris_diffuse_lr_score_dense_complex": [_p, _i64, _p, _i64, _i, _p, _p, _i, _p, _p, _p, _i, _p, _i64, _p, _p, _p, _p,
                                              _i, _i, _p],
     "laris_csr_select_dense": [_p, _p, _p, _i64, _p, _p, _i64, _p, _p],
@@ -48,6 +50,7 @@ SIGNATURES = {
     "laris_celltype_pair_contract": [_p, _i64, _i64, _i, _p, _i, _p, _p, _p, _i, _p],
     "laris_celltype_nonzero_count": [_p, _i64, _i64, _i, _p, _i, _p, _p],
     "laris_onehot_contract_csr": [_p, _p, _i64, _i, _p, _i, _p, _p, _p, _p],
+    "laris_onehot_contract_rows": [_p, _p, _p, _i64, _i, _p, _i, _p, _p, _p, _p],
     "laris_pvalue_counts": [_p, _i64, _i, _i, _p, _i, _p, _p, _i64, _i, _i, _i, _i, _u64, _p, _p, _p, _p, _p],
     "laris_bh_fdr": [_p, _p, _i, _i, _p, _p],
     "laris_row_qc": [_p, _i64, _i64, _i, _p, _i, _p, _p, _p, _p],

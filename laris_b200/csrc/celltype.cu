@@ -88,14 +88,15 @@ celltype_nonzero_count_kernel(const float4* __restrict__ S4, int64_t ld4, int64_
 }
 
 // ---- per (type, gene) sums straight from the packed CSR: warp per row
-__global__ void onehot_contract_csr_kernel(const int64_t* __restrict__ indptr, const int64_t* __restrict__ packed,
+__global__ void onehot_contract_csr_kernel(const int64_t* __restrict__ row_start, const int64_t* __restrict__ row_end,
+                                           const int64_t* __restrict__ packed,
                                            int64_t n, int G_u, const int32_t* __restrict__ labels,
                                            double* __restrict__ sum, double* __restrict__ cnt, double* __restrict__ colsq) {
     const int lane = threadIdx.x & 31;
     const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (row >= n) return;
     const int64_t base = (int64_t)labels[row] * G_u;
-    for (int64_t t = indptr[row] + lane; t < indptr[row + 1]; t += 32) {
+    for (int64_t t = row_start[row] + lane; t < row_end[row]; t += 32) {
         const int64_t pk = packed[t];
         const uint32_t g = (uint32_t)(pk & 0xffffffffll);
         const double v = (double)__uint_as_float((uint32_t)((uint64_t)pk >> 32));
@@ -243,17 +244,32 @@ extern "C" int laris_celltype_nonzero_count(const float* S, int64_t ldS, int64_t
     return LARIS_OK;
 }
 
-extern "C" int laris_onehot_contract_csr(const int64_t* indptr, const int64_t* packed, int64_t n, int32_t G_u,
-                                         const int32_t* labels, int32_t C, double* sum, double* cnt, double* colsq,
-                                         void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    LARIS_CHECK_ARG(indptr && labels && sum && cnt && colsq && n > 0 && G_u >= 1 && C >= 1, "laris_onehot_contract_csr: bad arguments");
+static int onehot_contract_impl(const int64_t* row_start, const int64_t* row_end, const int64_t* packed, int64_t n,
+                                int32_t G_u, const int32_t* labels, int32_t C, double* sum, double* cnt, double* colsq,
+                                cudaStream_t st, const char* who) {
+    LARIS_CHECK_ARG(row_start && row_end && labels && sum && cnt && colsq && n > 0 && G_u >= 1 && C >= 1, "%s: bad arguments", who);
     LARIS_CUDA(cudaMemsetAsync(sum, 0, (size_t)C * G_u * sizeof(double), st));
     LARIS_CUDA(cudaMemsetAsync(cnt, 0, (size_t)C * G_u * sizeof(double), st));
     LARIS_CUDA(cudaMemsetAsync(colsq, 0, (size_t)G_u * sizeof(double), st));
-    onehot_contract_csr_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(indptr, packed, n, G_u, labels, sum, cnt, colsq);
+    onehot_contract_csr_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(row_start, row_end, packed, n, G_u, labels, sum,
+                                                                                cnt, colsq);
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
+}
+
+extern "C" int laris_onehot_contract_csr(const int64_t* indptr, const int64_t* packed, int64_t n, int32_t G_u,
+                                         const int32_t* labels, int32_t C, double* sum, double* cnt, double* colsq,
+                                         void* stream) {
+    LARIS_CHECK_ARG(indptr, "laris_onehot_contract_csr: bad arguments");
+    return onehot_contract_impl(indptr, indptr + 1, packed, n, G_u, labels, C, sum, cnt, colsq, (cudaStream_t)stream,
+                                "laris_onehot_contract_csr");
+}
+
+extern "C" int laris_onehot_contract_rows(const int64_t* row_start, const int64_t* row_end, const int64_t* packed, int64_t n,
+                                          int32_t G_u, const int32_t* labels, int32_t C, double* sum, double* cnt,
+                                          double* colsq, void* stream) {
+    return onehot_contract_impl(row_start, row_end, packed, n, G_u, labels, C, sum, cnt, colsq, (cudaStream_t)stream,
+                                "laris_onehot_contract_rows");
 }
 
 namespace laris {

@@ -66,6 +66,29 @@ __global__ void csr_select_fill_kernel(const int64_t* __restrict__ indptr, const
     }
 }
 
+// single pass: the kept entries of row r go to out[indptr[r] ...) - the row keeps its offset in the INPUT matrix, so no
+// count / scan / second read is needed; row_end[r] marks where the kept entries stop.  Costs nnz(X) slots of scratch.
+__global__ void csr_select_rows_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                       const float* __restrict__ data, int64_t n, const int32_t* __restrict__ gene_map,
+                                       int64_t* __restrict__ out, int64_t* __restrict__ row_end) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (row >= n) return;
+    const int64_t s = indptr[row], e = indptr[row + 1];
+    int64_t o = s;
+    for (int64_t t0 = s; t0 < e; t0 += 32) {
+        const int64_t t = t0 + lane;
+        int g = -1;
+        float v = 0.0f;
+        if (t < e) { g = gene_map[indices[t]]; v = data[t]; }
+        const bool keep = g >= 0 && v != 0.0f;
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) out[o + __popc(m & ((1u << lane) - 1u))] = (int64_t)(((uint64_t)__float_as_uint(v) << 32) | (uint32_t)g);
+        o += __popc(m);
+    }
+    if (lane == 0) row_end[row] = o;
+}
+
 // ---------------------------------------------------------------- K2+K3 --
 // Shared memory of one CTA:  [pair table p_words u32, only when the table does not fit registers]
 // then per warp  D [dw_words] fp32 (slot G_u = always-zero column of the padding pairs)  and
@@ -140,7 +163,8 @@ __device__ __forceinline__ float lr_score1(const float* Dw, const uint32_t* Bw, 
 // NT threads, CH entry chunks per row pass, PPL LR pairs per lane held in registers (0: table in smem)
 template <int NT, int CH, int PPL>
 __global__ void __launch_bounds__(NT)
-diffuse_score_kernel(const int64_t* __restrict__ xu_indptr, const int64_t* __restrict__ xu_packed, int64_t n, int G_u,
+diffuse_score_kernel(const int64_t* __restrict__ row_start, const int64_t* __restrict__ row_end,
+                     const int64_t* __restrict__ xu_packed, int64_t n, int G_u,
                      const int32_t* __restrict__ idx, const float* __restrict__ w, int k,
                      const int32_t* __restrict__ order, const uint32_t* __restrict__ pairs, int p_words,
                      float* __restrict__ S, int64_t ldS, int64_t* __restrict__ row_nnz, ComplexTable cx) {
@@ -171,8 +195,8 @@ diffuse_score_kernel(const int64_t* __restrict__ xu_indptr, const int64_t* __res
         const int64_t i = order ? (int64_t)order[q] : q;
         for (int t = lane * 4; t < L.dw_words; t += 128) *reinterpret_cast<float4*>(Dw + t) = make_float4(0.f, 0.f, 0.f, 0.f);
         // the cell's own row: its first 32*CH columns are fetched now and consumed after phase 1
-        const int64_t self_s = xu_indptr[i];
-        const int self_len = (int)(xu_indptr[i + 1] - self_s);
+        const int64_t self_s = row_start[i];
+        const int self_len = (int)(row_end[i] - self_s);
         int selfcol[CH];
 #pragma unroll
         for (int c = 0; c < CH; ++c)
@@ -190,8 +214,8 @@ diffuse_score_kernel(const int64_t* __restrict__ xu_indptr, const int64_t* __res
             if (lane < kc) {
                 const int64_t nb = idx[i * k + j0 + lane];
                 wv = w[i * k + j0 + lane];
-                const int64_t rs = xu_indptr[nb];
-                len = (int)(xu_indptr[nb + 1] - rs);
+                const int64_t rs = row_start[nb];
+                len = (int)(row_end[nb] - rs);
                 rowp = entries + rs;
             }
             signs |= __float_as_uint(wv);
@@ -343,11 +367,12 @@ extern "C" int laris_csr_select_fill(const int64_t* indptr, const int32_t* indic
     return LARIS_OK;
 }
 
-static int diffuse_lr_score_impl(const int64_t* xu_indptr, const int64_t* xu_packed, int64_t n, int32_t G_u,
+static int diffuse_lr_score_impl(const int64_t* row_start, const int64_t* row_end, const int64_t* xu_packed, int64_t n,
+                                 int32_t G_u,
                                  const int32_t* idx, const float* w, int k, const int32_t* order,
                                  const int32_t* lig, const int32_t* rec, int32_t P, float* S, int64_t ldS,
                                  int64_t* row_nnz, ComplexTable cx, cudaStream_t st) {
-    LARIS_CHECK_ARG(xu_indptr && idx && w && lig && rec && S, "laris_diffuse_lr_score: null pointer");
+    LARIS_CHECK_ARG(row_start && row_end && idx && w && lig && rec && S, "laris_diffuse_lr_score: null pointer");
     LARIS_CHECK_ARG(n > 0 && k >= 1 && P >= 1, "laris_diffuse_lr_score: empty problem");
     LARIS_CHECK_ARG(G_u >= 1 && G_u <= 65533, "laris_diffuse_lr_score: G_u must be in [1, 65533] (got %d)", G_u);
     LARIS_CHECK_ARG(ldS >= P && ldS % 4 == 0 && ((uintptr_t)S & 15) == 0,
@@ -368,8 +393,8 @@ static int diffuse_lr_score_impl(const int64_t* xu_indptr, const int64_t* xu_pac
         set_error("laris_diffuse_lr_score: G_u=%d, P=%d do not fit shared memory (limit ~6500 columns)", G_u, P);
         return LARIS_E_LIMIT;
     }
-    using Kern = void (*)(const int64_t*, const int64_t*, int64_t, int, const int32_t*, const float*, int, const int32_t*,
-                          const uint32_t*, int, float*, int64_t, int64_t*, ComplexTable);
+    using Kern = void (*)(const int64_t*, const int64_t*, const int64_t*, int64_t, int, const int32_t*, const float*, int,
+                          const int32_t*, const uint32_t*, int, float*, int64_t, int64_t*, ComplexTable);
     Kern kern = nullptr;
 #define DS_PICK(CH_, PPL_) if (ch == CH_ && ppl == PPL_) kern = diffuse_score_kernel<NT, CH_, PPL_>;
     DS_PICK(4, 0) DS_PICK(8, 0)
@@ -383,8 +408,8 @@ static int diffuse_lr_score_impl(const int64_t* xu_indptr, const int64_t* xu_pac
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t want = ceil_div(n, NT / 32);
     const int64_t grid = want < (int64_t)sms * occ ? want : (int64_t)sms * occ;
-    kern<<<(unsigned)grid, NT, L.total, st>>>(xu_indptr, xu_packed, n, G_u, idx, w, k, order, pairs.p, p_words, S, ldS,
-                                              row_nnz, cx);
+    kern<<<(unsigned)grid, NT, L.total, st>>>(row_start, row_end, xu_packed, n, G_u, idx, w, k, order, pairs.p, p_words, S,
+                                              ldS, row_nnz, cx);
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
 }
@@ -393,7 +418,8 @@ extern "C" int laris_diffuse_lr_score(const int64_t* xu_indptr, const int64_t* x
                                       const int32_t* idx, const float* w, int k, const int32_t* order,
                                       const int32_t* lig, const int32_t* rec, int32_t P, float* S, int64_t ldS,
                                       int64_t* row_nnz, void* stream) {
-    return diffuse_lr_score_impl(xu_indptr, xu_packed, n, G_u, idx, w, k, order, lig, rec, P, S, ldS, row_nnz,
+    LARIS_CHECK_ARG(xu_indptr, "laris_diffuse_lr_score: null pointer");
+    return diffuse_lr_score_impl(xu_indptr, xu_indptr + 1, xu_packed, n, G_u, idx, w, k, order, lig, rec, P, S, ldS, row_nnz,
                                  ComplexTable(), (cudaStream_t)stream);
 }
 
@@ -406,8 +432,32 @@ extern "C" int laris_diffuse_lr_score_complex(const int64_t* xu_indptr, const in
                     "laris_diffuse_lr_score_complex: bad complex table (n_complex=%d, rule=%d)", n_complex, rule);
     ComplexTable cx;
     cx.ptr = cx_ptr; cx.cols = cx_cols; cx.vcol = cx_vcol; cx.nc = n_complex; cx.rule = rule;
-    return diffuse_lr_score_impl(xu_indptr, xu_packed, n, G_u, idx, w, k, order, lig, rec, P, S, ldS, row_nnz, cx,
+    LARIS_CHECK_ARG(xu_indptr, "laris_diffuse_lr_score_complex: null pointer");
+    return diffuse_lr_score_impl(xu_indptr, xu_indptr + 1, xu_packed, n, G_u, idx, w, k, order, lig, rec, P, S, ldS, row_nnz,
+                                 cx, (cudaStream_t)stream);
+}
+
+extern "C" int laris_diffuse_lr_score_rows(const int64_t* row_start, const int64_t* row_end, const int64_t* xu_packed,
+                                           int64_t n, int32_t G_u, const int32_t* idx, const float* w, int k,
+                                           const int32_t* order, const int32_t* lig, const int32_t* rec, int32_t P, float* S,
+                                           int64_t ldS, int64_t* row_nnz, const int32_t* cx_ptr, const int32_t* cx_cols,
+                                           const int32_t* cx_vcol, int32_t n_complex, int32_t rule, void* stream) {
+    LARIS_CHECK_ARG(n_complex >= 0 && (n_complex == 0 || (cx_ptr && cx_cols && cx_vcol)) && (rule == 0 || rule == 1),
+                    "laris_diffuse_lr_score_rows: bad complex table (n_complex=%d, rule=%d)", n_complex, rule);
+    ComplexTable cx;
+    cx.ptr = cx_ptr; cx.cols = cx_cols; cx.vcol = cx_vcol; cx.nc = n_complex; cx.rule = rule;
+    return diffuse_lr_score_impl(row_start, row_end, xu_packed, n, G_u, idx, w, k, order, lig, rec, P, S, ldS, row_nnz, cx,
                                  (cudaStream_t)stream);
+}
+
+extern "C" int laris_csr_select_rows(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n,
+                                     const int32_t* gene_map, int64_t* out_packed, int64_t* row_end, void* stream) {
+    LARIS_CHECK_ARG(indptr && gene_map && out_packed && row_end && n >= 0, "laris_csr_select_rows: bad arguments");
+    if (n == 0) return LARIS_OK;
+    csr_select_rows_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, (cudaStream_t)stream>>>(indptr, indices, data, n,
+                                                                                            gene_map, out_packed, row_end);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
 }
 
 extern "C" int laris_csr_compact(const float* S, int64_t ldS, int64_t n, int32_t P, const int64_t* indptr,

@@ -103,6 +103,8 @@ class ExpressionU:
     dense: torch.Tensor | None = None     # [n, ldX] fp32
     neg_flag: torch.Tensor | None = None  # [1] int32: a negative value was seen
     cx: tuple | None = None               # complex table (ptr, cols, vcol int32 device tensors, rule) or None
+    row_end: torch.Tensor | None = None   # [n] int64: rows are packed[indptr[i]:row_end[i]] (single-pass selection);
+                                          # None: compact rows packed[indptr[i]:indptr[i+1]]
 
     @property
     def G_u(self):
@@ -165,6 +167,19 @@ def choose_layout(X, layout="auto"):
     return "dense" if X.nnz >= DENSE_PANEL_MIN_DENSITY * float(n) * float(G) else "sparse"
 
 
+SINGLE_PASS_MAX_BYTES = 24 << 30      # scratch the single-pass selection may take (8 bytes per stored entry of X)
+
+
+def _select_sparse(indptr, indices, data, gene_map_d, genes, n, cols, n_columns, cx) -> ExpressionU:
+    """Packed sparse rows of the LR genes.  Single pass (rows keep their offsets in X, no count / scan / host sync) when
+    its nnz(X)-slot scratch is affordable, else the compact two-pass form."""
+    if 8 * int(indices.numel()) <= SINGLE_PASS_MAX_BYTES:
+        packed, row_end = K.csr_select_rows(indptr, indices, data, gene_map_d)
+        return ExpressionU(indptr, packed, genes, n, cols, n_columns, cx=cx, row_end=row_end)
+    out_indptr, packed = K.csr_select(indptr, indices, data, gene_map_d)
+    return ExpressionU(out_indptr, packed, genes, n, cols, n_columns, cx=cx)
+
+
 def select_genes(X, genes, csr_dev=None, columns=None, n_columns=None, layout="sparse") -> ExpressionU:
     """Restrict X (n x G CSR) to ``genes`` (unique global columns) on the device.
     ``columns`` optionally gives the packed column of each gene (see ``lr_column_layout``)."""
@@ -178,8 +193,7 @@ def select_genes(X, genes, csr_dev=None, columns=None, n_columns=None, layout="s
         ncol = len(genes) if n_columns is None else int(n_columns)
         Xd, neg = K.csr_select_dense(indptr, indices, data, K.to_device(gene_map, torch.int32), ncol)
         return ExpressionU(None, None, genes, n, cols, n_columns, Xd, neg)
-    out_indptr, packed = K.csr_select(indptr, indices, data, K.to_device(gene_map, torch.int32))
-    return ExpressionU(out_indptr, packed, genes, n, cols, n_columns)
+    return _select_sparse(indptr, indices, data, K.to_device(gene_map, torch.int32), genes, n, cols, n_columns, None)
 
 
 def lr_column_layout(lig_u, rec_u, n_genes):
@@ -264,8 +278,7 @@ def select_planned(plan: LRPlan, csr_dev, n, layout) -> ExpressionU:
     if layout == "dense":
         Xd, neg = K.csr_select_dense(indptr, indices, data, plan.gene_map_d, plan.n_columns)
         return ExpressionU(None, None, plan.genes, n, plan.columns, plan.n_columns, Xd, neg, plan.cx)
-    out_indptr, packed = K.csr_select(indptr, indices, data, plan.gene_map_d)
-    return ExpressionU(out_indptr, packed, plan.genes, n, plan.columns, plan.n_columns, cx=plan.cx)
+    return _select_sparse(indptr, indices, data, plan.gene_map_d, plan.genes, n, plan.columns, plan.n_columns, plan.cx)
 
 
 def select_lr_genes(X, lig_g, rec_g, csr_dev=None, layout="auto", complexes=None, rule="min"):
@@ -298,7 +311,7 @@ def lr_scores(xu: ExpressionU, graph: SpatialGraph, lig_u, rec_u) -> ScoreMatrix
                                               cx=xu.cx)
     else:
         S, row_nnz = K.diffuse_lr_score(xu.indptr, xu.packed, xu.G_u, graph.idx, graph.w, graph.order, lig_d, rec_d,
-                                        cx=xu.cx)
+                                        cx=xu.cx, row_end=xu.row_end)
     return ScoreMatrix(S, len(lig_u), row_nnz)
 
 
@@ -415,7 +428,7 @@ def neighborhood_specificity(sm: ScoreMatrix, labels_d, C, graph: SpatialGraph, 
 
 def cosg_gene_scores(xu: ExpressionU, labels_d, C, n_c, mu, expressed_pct, remove_lowly_expressed):
     """COSG gene x group score of the packed expression (cosg.cosg semantics)."""
-    s, c, q = K.onehot_contract_csr(xu.indptr, xu.packed, xu.G_u, labels_d, C)
+    s, c, q = K.onehot_contract_csr(xu.indptr, xu.packed, xu.G_u, labels_d, C, row_end=xu.row_end)
     s, c, q = s.cpu().numpy(), c.cpu().numpy(), q.cpu().numpy()
     den = np.sqrt(q)[:, None] * np.sqrt(n_c.astype(np.float64))[None, :]
     cos = np.zeros((xu.G_u, C))

@@ -37,7 +37,10 @@ idx, dist, order = T("knn_graph(incl self)", lambda: K.knn_graph(xy, k, True))
 w32, w64, sc = T("decay_weights", lambda: K.decay_weights(dist, None, True))
 xu_indptr, xu_packed = T("csr_select", lambda: K.csr_select(*csr, gm_d))
 print("  nnz_u =", xu_packed.numel())
+pk_rows, row_end = T("csr_select_rows (single pass)", lambda: K.csr_select_rows(*csr, gm_d))
+S2, rn2 = T("diffuse_lr_score (row ranges)", lambda: K.diffuse_lr_score(csr[0], pk_rows, ncols, idx, w32, order, lig, rec, row_end=row_end))
 S, row_nnz = T("diffuse_lr_score", lambda: K.diffuse_lr_score(xu_indptr, xu_packed, ncols, idx, w32, order, lig, rec))
+print("  row-range result identical:", bool((S2 == S).all().item()), bool((rn2 == row_nnz).all().item()))
 T("diffuse_lr_score(order=None)", lambda: K.diffuse_lr_score(xu_indptr, xu_packed, ncols, idx, w32, None, lig, rec))
 Xd, neg = T("csr_select_dense", lambda: K.csr_select_dense(*csr, gm_d, ncols))
 Sd, rnd = T("diffuse_lr_score_dense", lambda: K.diffuse_lr_score_dense(Xd, neg, ncols, idx, w32, order, lig, rec))
