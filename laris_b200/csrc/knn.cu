@@ -428,54 +428,56 @@ using namespace laris;
 // Everything the searches need: the grid shape and the cell-sorted copies of the points.
 struct PointGrid {
     int64_t cell_bound = 0;             // ncell <= cell_bound (enforced by grid_spec_kernel), nslot < 2 * cell_bound
-    Scratch<GridSpec> gs;
-    Scratch<int32_t> cell_of, counts, cell_start, fill, sorted_id, sorted_cell;
-    Scratch<double> sx, sy, sz;
-    explicit PointGrid(cudaStream_t st)
-        : gs(st), cell_of(st), counts(st), cell_start(st), fill(st), sorted_id(st), sorted_cell(st), sx(st), sy(st), sz(st) {}
+    Scratch<unsigned char> arena;       // ONE stream-ordered allocation for everything below (a dozen separate
+                                        // allocations cost more host time than the small kernels they feed)
+    GridSpec* gs = nullptr;
+    int32_t *cell_of = nullptr, *counts = nullptr, *fill = nullptr, *slot_count = nullptr, *cell_start = nullptr,
+            *slot_start = nullptr, *sorted_id = nullptr, *sorted_cell = nullptr;
+    double *sx = nullptr, *sy = nullptr, *sz = nullptr, *part = nullptr, *box = nullptr;
+    explicit PointGrid(cudaStream_t st) : arena(st) {}
 };
 
 // Bins the points on a uniform grid of about `per_cell` points per cell whose cell edge is at least `min_h`.
 // Fully asynchronous: the grid shape stays on the device (GridSpec), buffers are sized by cell_bound = 2n + 1024.
-static int build_point_grid(const double* xy, int64_t n, int dim, double per_cell, double min_h, cudaStream_t st,
-                            PointGrid& G, const char* who) {
-    (void)who;
+static int build_point_grid(const double* xy, int64_t n, int dim, double per_cell, double min_h, bool want_order,
+                            cudaStream_t st, PointGrid& G) {
     const int nb = kNumSMs * 2;
-    Scratch<double> part(st), box_d(st);
-    LARIS_CUDA(part.alloc(nb * 6));
-    LARIS_CUDA(box_d.alloc(6));
-    LARIS_CUDA(G.gs.alloc(1));
-    bbox_partial_kernel<<<nb, 256, 0, st>>>(xy, n, dim, part.p);
-    LARIS_LAUNCH_CHECK();
-    bbox_final_kernel<<<1, 192, 0, st>>>(part.p, nb, box_d.p);
-    LARIS_LAUNCH_CHECK();
-    const int64_t bound = 2 * n + 1024;
+    const int64_t bound = 2 * n + 1024, slots = want_order ? 2 * bound : 0;
     G.cell_bound = bound;
-    grid_spec_kernel<<<1, 32, 0, st>>>(box_d.p, n, dim, per_cell, min_h, bound, G.gs.p);
+    size_t off = 0;
+    auto reserve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_gs = reserve(sizeof(GridSpec)), o_part = reserve((size_t)nb * 6 * 8), o_box = reserve(6 * 8);
+    // counts | fill | slot_count are zero-initialised together
+    const size_t o_counts = reserve((size_t)bound * 4), o_fill = reserve((size_t)bound * 4), o_slotc = reserve((size_t)slots * 4);
+    const size_t zero_bytes = off - o_counts;
+    const size_t o_cstart = reserve((size_t)(bound + 1) * 4), o_sstart = reserve((size_t)(slots + 1) * 4);
+    const size_t o_cellof = reserve((size_t)n * 4), o_sid = reserve((size_t)n * 4), o_scell = reserve((size_t)n * 4);
+    const size_t o_sx = reserve((size_t)n * 8), o_sy = reserve((size_t)n * 8), o_sz = reserve((size_t)(dim == 3 ? n : 1) * 8);
+    LARIS_CUDA(G.arena.alloc(off));
+    unsigned char* base = G.arena.p;
+    G.gs = (GridSpec*)(base + o_gs); G.part = (double*)(base + o_part); G.box = (double*)(base + o_box);
+    G.counts = (int32_t*)(base + o_counts); G.fill = (int32_t*)(base + o_fill); G.slot_count = (int32_t*)(base + o_slotc);
+    G.cell_start = (int32_t*)(base + o_cstart); G.slot_start = (int32_t*)(base + o_sstart);
+    G.cell_of = (int32_t*)(base + o_cellof); G.sorted_id = (int32_t*)(base + o_sid); G.sorted_cell = (int32_t*)(base + o_scell);
+    G.sx = (double*)(base + o_sx); G.sy = (double*)(base + o_sy); G.sz = (double*)(base + o_sz);
+    LARIS_CUDA(cudaMemsetAsync(G.counts, 0, zero_bytes, st));
+    bbox_partial_kernel<<<nb, 256, 0, st>>>(xy, n, dim, G.part);
     LARIS_LAUNCH_CHECK();
-
-    LARIS_CUDA(G.cell_of.alloc(n));
-    LARIS_CUDA(G.counts.alloc(bound));
-    LARIS_CUDA(G.cell_start.alloc(bound + 1));
-    LARIS_CUDA(G.fill.alloc(bound));
-    LARIS_CUDA(G.sorted_id.alloc(n));
-    LARIS_CUDA(G.sorted_cell.alloc(n));
-    LARIS_CUDA(G.sx.alloc(n));
-    LARIS_CUDA(G.sy.alloc(n));
-    LARIS_CUDA(G.sz.alloc(dim == 3 ? n : 1));
-    LARIS_CUDA(cudaMemsetAsync(G.counts.p, 0, bound * sizeof(int32_t), st));
-    LARIS_CUDA(cudaMemsetAsync(G.fill.p, 0, bound * sizeof(int32_t), st));
+    bbox_final_kernel<<<1, 192, 0, st>>>(G.part, nb, G.box);
+    LARIS_LAUNCH_CHECK();
+    grid_spec_kernel<<<1, 32, 0, st>>>(G.box, n, dim, per_cell, min_h, bound, G.gs);
+    LARIS_LAUNCH_CHECK();
     const int T = 256;
     const unsigned gn = (unsigned)ceil_div(n, T), gc = (unsigned)ceil_div(bound, T);
-    cell_count_kernel<<<gn, T, 0, st>>>(xy, n, G.gs.p, G.cell_of.p, G.counts.p);
+    cell_count_kernel<<<gn, T, 0, st>>>(xy, n, G.gs, G.cell_of, G.counts);
     LARIS_LAUNCH_CHECK();
-    int rc = exclusive_scan<int32_t>(G.counts.p, bound, G.cell_start.p, st);     // cells past ncell are empty
+    int rc = exclusive_scan<int32_t>(G.counts, bound, G.cell_start, st);         // cells past ncell are empty
     if (rc) return rc;
-    cell_scatter_kernel<<<gn, T, 0, st>>>(G.cell_of.p, n, G.cell_start.p, G.fill.p, G.sorted_id.p);
+    cell_scatter_kernel<<<gn, T, 0, st>>>(G.cell_of, n, G.cell_start, G.fill, G.sorted_id);
     LARIS_LAUNCH_CHECK();
-    cell_sort_kernel<<<gc, T, 0, st>>>(G.cell_start.p, G.gs.p, G.sorted_id.p);
+    cell_sort_kernel<<<gc, T, 0, st>>>(G.cell_start, G.gs, G.sorted_id);
     LARIS_LAUNCH_CHECK();
-    gather_sorted_kernel<<<gn, T, 0, st>>>(xy, n, dim, G.sorted_id.p, G.cell_of.p, G.sx.p, G.sy.p, G.sz.p, G.sorted_cell.p);
+    gather_sorted_kernel<<<gn, T, 0, st>>>(xy, n, dim, G.sorted_id, G.cell_of, G.sx, G.sy, G.sz, G.sorted_cell);
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
 }
@@ -485,15 +487,11 @@ static int emit_strip_order(const PointGrid& G, int64_t n, int32_t* out_order, c
     const int T = 256;
     const unsigned gn = (unsigned)ceil_div(n, T), gc = (unsigned)ceil_div(G.cell_bound, T);
     const int64_t slot_bound = 2 * G.cell_bound;
-    Scratch<int32_t> slot_count(st), slot_start(st);
-    LARIS_CUDA(slot_count.alloc(slot_bound));
-    LARIS_CUDA(slot_start.alloc(slot_bound + 1));
-    LARIS_CUDA(cudaMemsetAsync(slot_count.p, 0, slot_bound * sizeof(int32_t), st));
-    strip_count_kernel<<<gc, T, 0, st>>>(G.cell_start.p, G.gs.p, slot_count.p);
+    strip_count_kernel<<<gc, T, 0, st>>>(G.cell_start, G.gs, G.slot_count);
     LARIS_LAUNCH_CHECK();
-    int rc = exclusive_scan<int32_t>(slot_count.p, slot_bound, slot_start.p, st);
+    int rc = exclusive_scan<int32_t>(G.slot_count, slot_bound, G.slot_start, st);
     if (rc) return rc;
-    strip_order_kernel<<<gn, T, 0, st>>>(G.cell_start.p, G.sorted_id.p, G.sorted_cell.p, n, G.gs.p, slot_start.p, out_order);
+    strip_order_kernel<<<gn, T, 0, st>>>(G.cell_start, G.sorted_id, G.sorted_cell, n, G.gs, G.slot_start, out_order);
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
 }
@@ -508,16 +506,13 @@ extern "C" int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int 
     LARIS_CHECK_ARG(n >= kq && n < (int64_t)INT32_MAX, "laris_knn_graph: need k+1 <= n < 2^31 (n=%lld)", (long long)n);
 
     PointGrid G(st);
-    int rc = build_point_grid(xy, n, dim, 2.5, 0.0, st, G, "laris_knn_graph");
+    int rc = build_point_grid(xy, n, dim, 2.5, 0.0, out_order != nullptr, st, G);
     if (rc) return rc;
-    const GridSpec* gs = G.gs.p;
-    Scratch<int32_t>&cell_start = G.cell_start, &sorted_id = G.sorted_id, &sorted_cell = G.sorted_cell;
-    Scratch<double>&sx = G.sx, &sy = G.sy, &sz = G.sz;
 
     const unsigned gq = (unsigned)ceil_div(n, 128);
 #define LARIS_KNN_LAUNCH(KMAX, DIM)                                                                          \
-    knn_search_kernel<KMAX, DIM><<<gq, 128, 0, st>>>(n, gs, kq, k, include_self, cell_start.p, sorted_id.p,  \
-                                                     sorted_cell.p, sx.p, sy.p, sz.p, out_idx, out_dist)
+    knn_search_kernel<KMAX, DIM><<<gq, 128, 0, st>>>(n, G.gs, kq, k, include_self, G.cell_start, G.sorted_id, \
+                                                     G.sorted_cell, G.sx, G.sy, G.sz, out_idx, out_dist)
     if (dim == 2) {
         if (kq <= 16) LARIS_KNN_LAUNCH(16, 2); else if (kq <= 32) LARIS_KNN_LAUNCH(32, 2); else LARIS_KNN_LAUNCH(64, 2);
     } else {
@@ -541,13 +536,13 @@ static int radius_graph_pass(const double* xy, int64_t n, int dim, double radius
     LARIS_CHECK_ARG(radius > 0.0 && isfinite(radius), "%s: radius must be positive and finite", who);
     PointGrid G(st);
     // cell edge >= radius (plus rounding slack in the cell assignment) so that one ring of cells is enough
-    int rc = build_point_grid(xy, n, dim, 2.5, radius * (1.0 + 1e-9), st, G, who);
+    int rc = build_point_grid(xy, n, dim, 2.5, radius * (1.0 + 1e-9), out_order != nullptr, st, G);
     if (rc) return rc;
     const unsigned gq = (unsigned)ceil_div(n, 128);
     const double r2 = radius * radius;
 #define LARIS_RADIUS_LAUNCH(DIM, MODE)                                                                              \
-    radius_search_kernel<DIM, MODE><<<gq, 128, 0, st>>>(n, G.gs.p, r2, include_self, G.cell_start.p, G.sorted_id.p,   \
-                                                        G.sorted_cell.p, G.sx.p, G.sy.p, G.sz.p, counts, indptr,    \
+    radius_search_kernel<DIM, MODE><<<gq, 128, 0, st>>>(n, G.gs, r2, include_self, G.cell_start, G.sorted_id,         \
+                                                        G.sorted_cell, G.sx, G.sy, G.sz, counts, indptr,            \
                                                         indices, dist)
     if (dim == 2) { if (mode) LARIS_RADIUS_LAUNCH(2, 1); else LARIS_RADIUS_LAUNCH(2, 0); }
     else { if (mode) LARIS_RADIUS_LAUNCH(3, 1); else LARIS_RADIUS_LAUNCH(3, 0); }
