@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--config", type=int, default=2)
     ap.add_argument("--n", type=int, default=None, help="override the number of cells (debug)")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="time the eager schedule instead of the CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -194,24 +195,76 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step(False)
-    barrier()
-    launches0 = lib.laris_launch_count()
-    step_ms, kern_ms = [], []
-    with ClockSampler(local) as clocks:
-        barrier()
-        wall0 = time.perf_counter()
+    # The timed step is the CUDA-graph replay of the whole step (engine.CapturedScoring: the same ~20 kernels, no host
+    # launches inside the timed region); the eager schedule is timed beside it.  The dominant kernel is timed through a
+    # second, small graph holding only the fused score stage (pair-table pack + K2+K3).
+    schedule = "cuda-graph replay (engine.CapturedScoring)"
+    captured = kern_graph = None
+    if not args.eager:
+        try:
+            captured = engine.CapturedScoring(xy_d, csr_d, plan, k, layout)
+            kern_graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(kern_graph):
+                engine.lr_scores(captured.xu, captured.graph, plan.lig_d, plan.rec_d)
+        except Exception as exc:                    # noqa: BLE001 - fall back to the eager schedule, say why
+            captured = kern_graph = None
+            schedule = f"eager (graph capture failed: {type(exc).__name__}: {str(exc)[:120]})"
+            torch.cuda.synchronize()
+    else:
+        schedule = "eager (--eager)"
+
+    def timed_region(run_step):
+        out_step, out_kern = [], []
         for _ in range(args.steps):
             flush.fill_(1.0)                       # L2 flush between timed iterations (outside the event bracket)
             torch.cuda.synchronize()
-            e0, e1, e2 = step(True)
+            out = run_step()
             torch.cuda.synchronize()
-            step_ms.append(e0.elapsed_time(e2))
-            kern_ms.append(e1.elapsed_time(e2))
+            out_step.append(out[0].elapsed_time(out[-1]))
+            if len(out) == 3:
+                out_kern.append(out[1].elapsed_time(out[2]))
+        return out_step, out_kern
+
+    def replay_step():
+        e0, e1 = ev(), ev()
+        e0.record()
+        captured.replay()
+        e1.record()
+        return e0, e1
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+        if captured is not None:
+            captured.replay()
+            kern_graph.replay()
+    barrier()
+    launches0 = lib.laris_launch_count()
+    with ClockSampler(local) as clocks:
+        barrier()
+        wall0 = time.perf_counter()
+        if captured is not None:
+            step_ms, _ = timed_region(replay_step)
+            launches = captured.launches * args.steps
+        else:
+            step_ms, kern_ms = timed_region(lambda: step(True))
+            launches = lib.laris_launch_count() - launches0
         barrier()
         wall = time.perf_counter() - wall0
-        launches = lib.laris_launch_count() - launches0
+        if captured is not None:                   # beside it: the eager schedule, and the score stage alone
+            eager_ms, _ = timed_region(lambda: step(True))
+            kern_ms = []
+            for _ in range(args.steps):
+                flush.fill_(1.0)
+                torch.cuda.synchronize()
+                e0, e1 = ev(), ev()
+                e0.record()
+                kern_graph.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                kern_ms.append(e0.elapsed_time(e1))
+            state.update(graph=captured.graph, xu=captured.xu, sm=captured.scores)
+        else:
+            eager_ms = step_ms
 
         # ---- e2e: the public API with host buffers (pinned inputs) ----
         pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()
@@ -284,7 +337,8 @@ def run_ours(args):
             "config": {"workload": workload_name(c), "step": "kNN graph + decay weights + gene selection + fused "
                        "diffusion/LR score -> dense n x P score matrix in HBM",
                        "sharding": f"LR pairs: {P} per GPU x {world} GPUs, graph replicated, no collective",
-                       "l2": "512 MiB buffer written between timed iterations (outside the event bracket)"},
+                       "l2": "512 MiB buffer written between timed iterations (outside the event bracket)",
+                       "schedule": schedule, "ms_per_step_eager": float(np.mean(eager_ms))},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * t_e2e / args.steps, "ms_each": [round(1e3 * t, 3) for t in e2e_t],
                     "call": "laris_b200.tl.prepareLRInteraction(adata, lr_df) -> AnnData with scipy CSR on the host"},

@@ -315,6 +315,42 @@ def lr_scores(xu: ExpressionU, graph: SpatialGraph, lig_u, rec_u) -> ScoreMatrix
     return ScoreMatrix(S, len(lig_u), row_nnz)
 
 
+class CapturedScoring:
+    """The device-resident scoring step - graph build, decay weights, gene selection, fused diffusion / LR score -
+    captured once as a CUDA graph for a fixed problem shape and replayed with no host launches.
+
+    Every stage of the step is asynchronous (the kNN grid is derived on the device, the single-pass selection needs no
+    scan, scratch comes from the stream-ordered allocator), so the ~20 kernels of a step can be recorded into one graph;
+    a replay re-runs them on the CURRENT contents of the same device buffers (``xy_d`` and ``csr_dev`` may be
+    overwritten in place between replays, e.g. resampled expression values on a fixed sparsity pattern, or the same
+    tissue scored against another LR table of the same shape).  Replays are immune to host launch jitter, which
+    otherwise paces the many small kernels of the graph build."""
+
+    def __init__(self, xy_d, csr_dev, plan: LRPlan, k: int, layout: str, include_self: bool = True):
+        from ._lib import lib
+        n = xy_d.shape[0]
+        self._run = lambda: self._step(xy_d, csr_dev, plan, n, int(k), layout, include_self)
+        self._run()                                    # eager pass: lazy initialisation, function attributes, pools
+        torch.cuda.synchronize()
+        self.graph_exec = torch.cuda.CUDAGraph()
+        before = lib.laris_launch_count()
+        with torch.cuda.graph(self.graph_exec):
+            self.graph, self.xu, self.scores = self._run()
+        self.launches = int(lib.laris_launch_count() - before)       # kernels recorded = kernels run per replay
+
+    @staticmethod
+    def _step(xy_d, csr_dev, plan, n, k, layout, include_self):
+        graph = build_graph(xy_d, k, include_self, None)
+        xu = select_planned(plan, csr_dev, n, layout)
+        return graph, xu, lr_scores(xu, graph, plan.lig_d, plan.rec_d)
+
+    def replay(self) -> ScoreMatrix:
+        """Run the captured step; the returned ScoreMatrix (and ``self.graph`` / ``self.xu``) live in graph-owned
+        buffers that the next replay overwrites."""
+        self.graph_exec.replay()
+        return self.scores
+
+
 def scores_to_csr_async(sm: ScoreMatrix, dtype=np.float32):
     """Start the device CSR compaction and the device->host copies of the result; returns ``finish()`` which waits
     for the copies and assembles the scipy matrix.  Host work done between the two calls overlaps the transfer."""

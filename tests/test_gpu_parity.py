@@ -808,3 +808,34 @@ def test_pvalue_counts_candidate_set_sizes(dev, nb):
     assert np.array_equal(ge, ref[0]) and np.array_equal(nz, ref[1]) and np.array_equal(both, ref[2])
     ge1, _, _ = engine.pvalue_counts(table, bg, active, N, rng="philox", seed=11, only_ge=True)
     assert np.array_equal(ge1, ref[0])
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_captured_scoring_replays_the_step(dev, layout):
+    """engine.CapturedScoring: the CUDA-graph replay of the step equals the eager step, and a replay picks up
+    expression values overwritten in place in the same device buffers."""
+    import laris_b200 as la
+    from laris_b200 import engine, _kernels as K
+    from laris_b200.synth import make_dataset
+    a, lr, c = make_dataset(2, n=6000, G=200, G_u=120, P=70)
+    xy_d = K.to_device(a.obsm["X_spatial"], torch.float64)
+    csr = engine.upload_csr(a.X)
+    lg, rg = la.tl._lr_gene_indices(a, lr)
+    plan = engine.plan_lr_table(lg, rg, a.X.shape[1])
+
+    def eager():
+        g = engine.build_graph(xy_d, c.k, True, None)
+        return engine.lr_scores(engine.select_planned(plan, csr, c.n, layout), g, plan.lig_d, plan.rec_d)
+
+    ref = eager()
+    cap = engine.CapturedScoring(xy_d, csr, plan, c.k, layout)
+    assert cap.launches >= 10
+    for _ in range(2):
+        sm = cap.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(sm.S, ref.S) and torch.equal(sm.row_nnz, ref.row_nnz)
+    csr[2].mul_(2.0)                                     # same sparsity pattern, new values
+    ref2 = eager()
+    sm = cap.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(sm.S, ref2.S) and torch.equal(ref2.S, ref.S * 4.0)
