@@ -4,7 +4,9 @@
 One "step" = one pass of the hot path over one batch of synthetic input:
 kNN graph (incl. self) + decay weights + gene selection + fused diffusion/LR
 score, producing the n x P score matrix (metric M1
-"cell x LR-pair scores/s").  ``value`` times it with the inputs already in HBM;
+"cell x LR-pair scores/s").  ``value`` times it with the inputs already in HBM, as
+a CUDA-graph replay of the whole step (``engine.CapturedScoring``; the eager
+schedule is timed beside it and reported as ``config.ms_per_step_eager``);
 ``e2e`` times ``laris_b200.tl.prepareLRInteraction`` (host AnnData in, host
 AnnData with scipy CSR out: H2D, kernels, CSR compaction, D2H).  The
 permutation metrics (random-graph null repeats/s, p-value permutations/s) and
