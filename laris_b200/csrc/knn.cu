@@ -31,7 +31,14 @@ struct GridSpec {
 };
 
 // ------------------------------------------------------------------ bbox --
-__global__ void bbox_partial_kernel(const double* __restrict__ xy, int64_t n, int dim, double* __restrict__ part) {
+__device__ void derive_grid_spec(const double* box, int64_t n, int dim, double per_cell, double min_h, int64_t cell_bound,
+                                 GridSpec* out);
+
+// bbox partials + (last CTA to finish) the final box and the grid shape, in ONE launch: the CTA that takes the last
+// ticket sees every partial (threadfence before the ticket), reduces them in a fixed order and derives the GridSpec.
+__global__ void __launch_bounds__(256)
+bbox_grid_kernel(const double* __restrict__ xy, int64_t n, int dim, double per_cell, double min_h, int64_t cell_bound,
+                 double* __restrict__ part, unsigned int* __restrict__ ticket, GridSpec* __restrict__ out) {
     double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         for (int a = 0; a < dim; ++a) {
@@ -42,6 +49,8 @@ __global__ void bbox_partial_kernel(const double* __restrict__ xy, int64_t n, in
         }
     }
     __shared__ double sm[6][32];
+    __shared__ double box[6];
+    __shared__ bool last;
     for (int a = 0; a < 3; ++a) {
         double lo = mn[a], hi = mx[a];
         for (int o = 16; o > 0; o >>= 1) {
@@ -55,23 +64,30 @@ __global__ void bbox_partial_kernel(const double* __restrict__ xy, int64_t n, in
     }
     __syncthreads();
     if (threadIdx.x < 6) {
-        int nw = blockDim.x >> 5;
+        const int nw = blockDim.x >> 5;
         double v = sm[threadIdx.x][0];
         for (int w = 1; w < nw; ++w) v = threadIdx.x < 3 ? fmin(v, sm[threadIdx.x][w]) : fmax(v, sm[threadIdx.x][w]);
         part[blockIdx.x * 6 + threadIdx.x] = v;
+        __threadfence();
     }
-}
-
-__global__ void bbox_final_kernel(const double* __restrict__ part, int nblocks, double* __restrict__ out) {
-    // one warp per output component, lanes stride over the block partials
-    const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double v = t < 3 ? DBL_MAX : -DBL_MAX;
-    for (int b = lane; b < nblocks; b += 32) v = t < 3 ? fmin(v, part[b * 6 + t]) : fmax(v, part[b * 6 + t]);
-    for (int o = 16; o > 0; o >>= 1) {
-        const double u = __shfl_xor_sync(0xffffffffu, v, o);
-        v = t < 3 ? fmin(v, u) : fmax(v, u);
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int t = threadIdx.x >> 5, lane = threadIdx.x & 31;      // one warp per box component
+    if (t < 6) {
+        const volatile double* vp = part;
+        double v = t < 3 ? DBL_MAX : -DBL_MAX;
+        for (int b = lane; b < (int)gridDim.x; b += 32) v = t < 3 ? fmin(v, vp[b * 6 + t]) : fmax(v, vp[b * 6 + t]);
+        for (int o = 16; o > 0; o >>= 1) {
+            const double u = __shfl_xor_sync(0xffffffffu, v, o);
+            v = t < 3 ? fmin(v, u) : fmax(v, u);
+        }
+        if (lane == 0) box[t] = v;
     }
-    if (lane == 0) out[t] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) derive_grid_spec(box, n, dim, per_cell, min_h, cell_bound, out);
 }
 
 // The grid shape is derived ON THE DEVICE from the bounding box (one thread), so the whole graph build is
@@ -79,9 +95,8 @@ __global__ void bbox_final_kernel(const double* __restrict__ part, int nblocks, 
 // bound ncell <= cell_bound that the loop below enforces.
 constexpr int kStripH = 8;
 
-__global__ void grid_spec_kernel(const double* __restrict__ box, int64_t n, int dim, double per_cell, double min_h,
-                                 int64_t cell_bound, GridSpec* __restrict__ out) {
-    if (threadIdx.x || blockIdx.x) return;
+__device__ void derive_grid_spec(const double* box, int64_t n, int dim, double per_cell, double min_h, int64_t cell_bound,
+                                 GridSpec* out) {
     GridSpec gs;
     gs.dim = dim;
     gs.valid = 1;
@@ -402,20 +417,29 @@ __global__ void sum_partial_kernel(const double* __restrict__ v, int64_t m, doub
     }
 }
 
-__global__ void scale_final_kernel(const double* __restrict__ part, int nb, int64_t m, double sigma, double* __restrict__ scale) {
-    // one warp; fixed lane-strided order + butterfly, so the sum is deterministic
-    if (sigma > 0.0) { if (threadIdx.x == 0) *scale = sigma; return; }
-    double t = 0.0;
-    for (int b = threadIdx.x; b < nb; b += 32) t += part[b];
-    t = warp_sum(t);
-    if (threadIdx.x == 0) *scale = (t / (double)m) / 2.0;
-}
-
-__global__ void decay_weights_kernel(const double* __restrict__ dist, int64_t m, const double* __restrict__ scale,
-                                     double* __restrict__ w64, float* __restrict__ w32) {
+// Every CTA derives the scale itself from the block partials (warp 0: fixed lane-strided order + butterfly, so the
+// sum is deterministic and identical in all CTAs) - no separate one-warp kernel between the sum and the weights.
+__global__ void __launch_bounds__(256)
+decay_weights_kernel(const double* __restrict__ dist, int64_t m, const double* __restrict__ part, int nb, double sigma,
+                     double* __restrict__ w64, float* __restrict__ w32, double* __restrict__ scale_out) {
+    __shared__ double s_scale;
+    if (threadIdx.x < 32) {
+        double sc = sigma;
+        if (!(sigma > 0.0)) {
+            double t = 0.0;
+            for (int b = threadIdx.x; b < nb; b += 32) t += part[b];
+            t = warp_sum(t);
+            sc = (t / (double)m) / 2.0;
+        }
+        if (threadIdx.x == 0) {
+            s_scale = sc;
+            if (blockIdx.x == 0 && scale_out) *scale_out = sc;
+        }
+    }
+    __syncthreads();
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= m) return;
-    double w = 1.0 / exp(dist[i] / *scale);
+    double w = 1.0 / exp(dist[i] / s_scale);
     if (w64) w64[i] = w;
     if (w32) w32[i] = (float)w;
 }
@@ -427,13 +451,13 @@ using namespace laris;
 // ------------------------------------------------------------ point grid --
 // Everything the searches need: the grid shape and the cell-sorted copies of the points.
 struct PointGrid {
-    int64_t cell_bound = 0;             // ncell <= cell_bound (enforced by grid_spec_kernel), nslot < 2 * cell_bound
+    int64_t cell_bound = 0;             // ncell <= cell_bound (enforced by derive_grid_spec), nslot < 2 * cell_bound
     Scratch<unsigned char> arena;       // ONE stream-ordered allocation for everything below (a dozen separate
                                         // allocations cost more host time than the small kernels they feed)
     GridSpec* gs = nullptr;
     int32_t *cell_of = nullptr, *counts = nullptr, *fill = nullptr, *slot_count = nullptr, *cell_start = nullptr,
             *slot_start = nullptr, *sorted_id = nullptr, *sorted_cell = nullptr;
-    double *sx = nullptr, *sy = nullptr, *sz = nullptr, *part = nullptr, *box = nullptr;
+    double *sx = nullptr, *sy = nullptr, *sz = nullptr, *part = nullptr;
     explicit PointGrid(cudaStream_t st) : arena(st) {}
 };
 
@@ -446,26 +470,23 @@ static int build_point_grid(const double* xy, int64_t n, int dim, double per_cel
     G.cell_bound = bound;
     size_t off = 0;
     auto reserve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_gs = reserve(sizeof(GridSpec)), o_part = reserve((size_t)nb * 6 * 8), o_box = reserve(6 * 8);
-    // counts | fill | slot_count are zero-initialised together
+    const size_t o_gs = reserve(sizeof(GridSpec)), o_part = reserve((size_t)nb * 6 * 8);
+    // ticket | counts | fill | slot_count are zero-initialised together
+    const size_t o_ticket = reserve(4);
     const size_t o_counts = reserve((size_t)bound * 4), o_fill = reserve((size_t)bound * 4), o_slotc = reserve((size_t)slots * 4);
-    const size_t zero_bytes = off - o_counts;
+    const size_t zero_bytes = off - o_ticket;
     const size_t o_cstart = reserve((size_t)(bound + 1) * 4), o_sstart = reserve((size_t)(slots + 1) * 4);
     const size_t o_cellof = reserve((size_t)n * 4), o_sid = reserve((size_t)n * 4), o_scell = reserve((size_t)n * 4);
     const size_t o_sx = reserve((size_t)n * 8), o_sy = reserve((size_t)n * 8), o_sz = reserve((size_t)(dim == 3 ? n : 1) * 8);
     LARIS_CUDA(G.arena.alloc(off));
     unsigned char* base = G.arena.p;
-    G.gs = (GridSpec*)(base + o_gs); G.part = (double*)(base + o_part); G.box = (double*)(base + o_box);
+    G.gs = (GridSpec*)(base + o_gs); G.part = (double*)(base + o_part);
     G.counts = (int32_t*)(base + o_counts); G.fill = (int32_t*)(base + o_fill); G.slot_count = (int32_t*)(base + o_slotc);
     G.cell_start = (int32_t*)(base + o_cstart); G.slot_start = (int32_t*)(base + o_sstart);
     G.cell_of = (int32_t*)(base + o_cellof); G.sorted_id = (int32_t*)(base + o_sid); G.sorted_cell = (int32_t*)(base + o_scell);
     G.sx = (double*)(base + o_sx); G.sy = (double*)(base + o_sy); G.sz = (double*)(base + o_sz);
-    LARIS_CUDA(cudaMemsetAsync(G.counts, 0, zero_bytes, st));
-    bbox_partial_kernel<<<nb, 256, 0, st>>>(xy, n, dim, G.part);
-    LARIS_LAUNCH_CHECK();
-    bbox_final_kernel<<<1, 192, 0, st>>>(G.part, nb, G.box);
-    LARIS_LAUNCH_CHECK();
-    grid_spec_kernel<<<1, 32, 0, st>>>(G.box, n, dim, per_cell, min_h, bound, G.gs);
+    LARIS_CUDA(cudaMemsetAsync(base + o_ticket, 0, zero_bytes, st));
+    bbox_grid_kernel<<<nb, 256, 0, st>>>(xy, n, dim, per_cell, min_h, bound, G.part, (unsigned int*)(base + o_ticket), G.gs);
     LARIS_LAUNCH_CHECK();
     const int T = 256;
     const unsigned gn = (unsigned)ceil_div(n, T), gc = (unsigned)ceil_div(bound, T);
@@ -582,17 +603,13 @@ extern "C" int laris_decay_weights(const double* dist, int64_t m, double sigma, 
                                    double* scale_out, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     LARIS_CHECK_ARG(dist && m > 0, "laris_decay_weights: empty input");
-    Scratch<double> part(st), scale(st);
+    Scratch<double> part(st);
     LARIS_CUDA(part.alloc(kSumBlocks));
-    LARIS_CUDA(scale.alloc(1));
     if (!(sigma > 0.0)) {
         sum_partial_kernel<<<kSumBlocks, kSumThreads, 0, st>>>(dist, m, part.p);
         LARIS_LAUNCH_CHECK();
     }
-    scale_final_kernel<<<1, 32, 0, st>>>(part.p, kSumBlocks, m, sigma, scale.p);
+    decay_weights_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(dist, m, part.p, kSumBlocks, sigma, w64, w32, scale_out);
     LARIS_LAUNCH_CHECK();
-    decay_weights_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(dist, m, scale.p, w64, w32);
-    LARIS_LAUNCH_CHECK();
-    if (scale_out) LARIS_CUDA(cudaMemcpyAsync(scale_out, scale.p, sizeof(double), cudaMemcpyDeviceToDevice, st));
     return LARIS_OK;
 }
