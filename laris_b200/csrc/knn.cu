@@ -223,38 +223,59 @@ __global__ void strip_order_kernel(const int32_t* __restrict__ cell_start, const
 }
 
 // ---------------------------------------------------------------- search --
-template <int KMAX>
+// Sorted candidate list of one query.  SHARED: the lists of a CTA live in shared memory, entry-major
+// ([entry][thread]): a thread's entries all sit in "its" bank(s), so the data-dependent positions of the insertion
+// loop cost one wavefront per access whatever the lanes' positions are - in local memory the same loop touches up to 32
+// different lines per instruction, which is what bounded the search.  Otherwise (k > 32) the list is thread-local.
+constexpr int kKnnThreads = 128;
+
+template <int KMAX, bool SHARED>
 struct TopK {
-    double d2[KMAX];
-    int32_t id[KMAX];
+    double d2_local[SHARED ? 1 : KMAX];
+    int32_t id_local[SHARED ? 1 : KMAX];
+    double* d2s;
+    int32_t* ids;
     int count;
     int K;
-    __device__ __forceinline__ void init(int k) { count = 0; K = k; }
+    __device__ __forceinline__ void init(int k, double* sm_d2, int32_t* sm_id) {
+        count = 0;
+        K = k;
+        d2s = sm_d2 + threadIdx.x;
+        ids = sm_id + threadIdx.x;
+    }
+    __device__ __forceinline__ double& d2(int j) { return SHARED ? d2s[j * kKnnThreads] : d2_local[j]; }
+    __device__ __forceinline__ int32_t& id(int j) { return SHARED ? ids[j * kKnnThreads] : id_local[j]; }
     __device__ __forceinline__ bool full() const { return count == K; }
-    __device__ __forceinline__ double worst() const { return d2[count - 1]; }
+    __device__ __forceinline__ double worst() { return d2(count - 1); }
     __device__ __forceinline__ void offer(double v, int32_t pid) {
         if (count == K) {
-            double wv = d2[K - 1];
-            if (v > wv || (v == wv && pid > id[K - 1])) return;
+            double wv = d2(K - 1);
+            if (v > wv || (v == wv && pid > id(K - 1))) return;
         }
         int pos = count < K ? count : K - 1;
-        while (pos > 0 && (d2[pos - 1] > v || (d2[pos - 1] == v && id[pos - 1] > pid))) {
-            d2[pos] = d2[pos - 1];
-            id[pos] = id[pos - 1];
+        while (pos > 0) {
+            const double dp = d2(pos - 1);
+            const int32_t ip = id(pos - 1);
+            if (!(dp > v || (dp == v && ip > pid))) break;
+            d2(pos) = dp;
+            id(pos) = ip;
             --pos;
         }
-        d2[pos] = v;
-        id[pos] = pid;
+        d2(pos) = v;
+        id(pos) = pid;
         if (count < K) ++count;
     }
 };
 
 template <int KMAX, int DIM>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(kKnnThreads)
 knn_search_kernel(int64_t n, const GridSpec* __restrict__ gsp, int kq, int k, int include_self, const int32_t* __restrict__ cell_start,
                   const int32_t* __restrict__ sorted_id, const int32_t* __restrict__ sorted_cell,
                   const double* __restrict__ sx, const double* __restrict__ sy, const double* __restrict__ sz,
                   int32_t* __restrict__ out_idx, double* __restrict__ out_dist) {
+    constexpr bool SHARED = KMAX <= 32;                // 12 * KMAX * 128 bytes of shared memory: 24 KB / 48 KB
+    __shared__ double sm_d2[SHARED ? KMAX * kKnnThreads : 1];
+    __shared__ int32_t sm_id[SHARED ? KMAX * kKnnThreads : 1];
     int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (q >= n) return;
     const GridSpec gs = *gsp;
@@ -270,8 +291,8 @@ knn_search_kernel(int64_t n, const GridSpec* __restrict__ gsp, int kq, int k, in
     const int cz = DIM == 3 ? c / (gs.g[0] * gs.g[1]) : 0;
     const int gx = gs.g[0], gy = gs.g[1], gz = DIM == 3 ? gs.g[2] : 1;
 
-    TopK<KMAX> top;
-    top.init(kq);
+    TopK<KMAX, SHARED> top;
+    top.init(kq, sm_d2, sm_id);
     const int rmax = max(max(max(cx, gx - 1 - cx), max(cy, gy - 1 - cy)), max(cz, gz - 1 - cz));
     for (int r = 0; r <= rmax; ++r) {
         const int z0 = DIM == 3 ? max(cz - r, 0) : 0, z1 = DIM == 3 ? min(cz + r, gz - 1) : 0;
@@ -317,15 +338,15 @@ knn_search_kernel(int64_t n, const GridSpec* __restrict__ gsp, int kq, int k, in
     int32_t* oi = out_idx + (int64_t)self * k;
     double* od = out_dist + (int64_t)self * k;
     if (include_self) {
-        for (int j = 0; j < k; ++j) { oi[j] = top.id[j]; od[j] = __dsqrt_rn(top.d2[j]); }
+        for (int j = 0; j < k; ++j) { oi[j] = top.id(j); od[j] = __dsqrt_rn(top.d2(j)); }
     } else {
         int drop = 0;                                  // sklearn: drop own index, else the first entry
-        for (int j = 0; j < kq; ++j) if (top.id[j] == self) { drop = j; break; }
+        for (int j = 0; j < kq; ++j) if (top.id(j) == self) { drop = j; break; }
         int o = 0;
         for (int j = 0; j < kq; ++j) {
             if (j == drop) continue;
-            oi[o] = top.id[j];
-            od[o] = __dsqrt_rn(top.d2[j]);
+            oi[o] = top.id(j);
+            od[o] = __dsqrt_rn(top.d2(j));
             ++o;
         }
     }
@@ -530,9 +551,9 @@ extern "C" int laris_knn_graph(const double* xy, int64_t n, int dim, int k, int 
     int rc = build_point_grid(xy, n, dim, 2.5, 0.0, out_order != nullptr, st, G);
     if (rc) return rc;
 
-    const unsigned gq = (unsigned)ceil_div(n, 128);
+    const unsigned gq = (unsigned)ceil_div(n, kKnnThreads);
 #define LARIS_KNN_LAUNCH(KMAX, DIM)                                                                          \
-    knn_search_kernel<KMAX, DIM><<<gq, 128, 0, st>>>(n, G.gs, kq, k, include_self, G.cell_start, G.sorted_id, \
+    knn_search_kernel<KMAX, DIM><<<gq, kKnnThreads, 0, st>>>(n, G.gs, kq, k, include_self, G.cell_start, G.sorted_id, \
                                                      G.sorted_cell, G.sx, G.sy, G.sz, out_idx, out_dist)
     if (dim == 2) {
         if (kq <= 16) LARIS_KNN_LAUNCH(16, 2); else if (kq <= 32) LARIS_KNN_LAUNCH(32, 2); else LARIS_KNN_LAUNCH(64, 2);
