@@ -167,3 +167,52 @@ def test_scores_are_quadratic_in_expression_and_relabelling_invariant():
     shuf.sort_indices()
     assert np.array_equal(shuf.indptr, ref.indptr) and np.array_equal(shuf.indices, ref.indices)
     assert np.allclose(shuf.data, ref.data, rtol=2e-6, atol=0)              # the dense kernel sums a cell's rows in warp-group order
+
+
+@settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 3000), P=st.integers(1, 300), C=st.integers(1, 40),
+       dens=st.floats(0.01, 1.0), types=st.integers(1, 4), perm=st.booleans())
+def test_tensor_core_contraction_on_random_shapes(seed, n, P, C, dens, types, perm):
+    """tcgen05 pair contraction (three-way bf16 split) against a float64 contraction: 1e-5 on every non-zero entry,
+    exact zeros stay exact - ragged tiles, single cells, dense and very sparse score matrices, any cell order."""
+    from laris_b200 import _kernels as K
+    rng = np.random.default_rng(seed)
+    ld = K.padded_ld(P)
+    S = np.zeros((n, ld), np.float32)
+    S[:, :P] = (rng.random((n, P)) < dens) * rng.gamma(2.0, 1.0, (n, P)).astype(np.float32) * \
+        np.float32(10.0) ** rng.integers(-3, 4, (1, P)).astype(np.float32)          # columns of very different scale
+    N = np.zeros((n, C), np.float32)
+    for _ in range(types):
+        N[np.arange(n), rng.integers(0, C, n)] += rng.random(n).astype(np.float32)
+    Sd, Nd = torch.from_numpy(S).cuda(), torch.from_numpy(N).cuda()
+    order = torch.from_numpy(rng.permutation(n).astype(np.int32)).cuda() if perm else None
+    num, q = K.celltype_pair_contract(Sd, P, Nd, 0, order=order)
+    Q = (N[:, :, None].astype(np.float64) * N[:, None, :]).reshape(n, C * C)
+    ref = S[:, :P].astype(np.float64).T @ Q
+    got = num.cpu().numpy()
+    assert np.array_equal(got == 0, ref == 0)
+    assert np.allclose(got, ref, rtol=RTOL, atol=0)
+    assert np.allclose(q.cpu().numpy(), (Q * Q).sum(0), rtol=1e-6)
+
+
+@settings(**COMMON)
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 2000), P=st.integers(1, 200), C=st.integers(1, 60))
+def test_celltype_counts_and_cell_qc_on_random_shapes(seed, n, P, C):
+    from laris_b200 import _kernels as K
+    rng = np.random.default_rng(seed)
+    S = np.zeros((n, K.padded_ld(P)), np.float32)
+    S[:, :P] = (rng.random((n, P)) < 0.3) * rng.random((n, P)).astype(np.float32)
+    labels = rng.integers(0, C, n).astype(np.int32)
+    Sd = torch.from_numpy(S).cuda()
+    got = K.celltype_nonzero_count(Sd, P, torch.from_numpy(labels).cuda(), C).cpu().numpy()
+    ref = np.zeros((C, P), np.int64)
+    np.add.at(ref, labels, (S[:, :P] != 0).astype(np.int64))
+    assert np.array_equal(got, ref)
+    tops = [t for t in (1, 7, 50) if t < P] or [1]
+    total, nnz, top = K.row_qc(Sd, P, tops)
+    r = S[:, :P].astype(np.float64)
+    srt = -np.sort(-r, axis=1)
+    assert np.allclose(total.cpu().numpy(), r.sum(1), rtol=1e-12, atol=1e-12)
+    assert np.array_equal(nnz.cpu().numpy(), (r != 0).sum(1))
+    for j, t in enumerate(tops):
+        assert np.allclose(top.cpu().numpy()[:, j], srt[:, :min(t, P)].sum(1), rtol=1e-12, atol=1e-12)
