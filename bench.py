@@ -111,27 +111,33 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], threading.Event()
-        self.th = threading.Thread(target=self._run, daemon=True)
+    def __init__(self, indices):
+        """``indices``: GPU indices to sample in ONE nvidia-smi call per tick (rank 0 samples the whole job's GPUs;
+        the other ranks pass an empty list and do not poll - eight pollers on one host perturb the run they watch)."""
+        self.indices, self.rows, self.stop = list(indices), [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True) if self.indices else None
 
     def _run(self):
         while not self.stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                                      "-i", ",".join(str(i) for i in self.indices)],
+                                     capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([x.strip() for x in line.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.1 if len(self.indices) == 1 else 0.25)
 
     def __enter__(self):
-        self.th.start()
+        if self.th is not None:
+            self.th.start()
         return self
 
     def __exit__(self, *exc):
         self.stop.set()
-        self.th.join(timeout=6)
+        if self.th is not None:
+            self.th.join(timeout=6)
 
     def summary(self):
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
@@ -152,6 +158,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"        # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
 
     import laris_b200 as la
@@ -241,7 +249,7 @@ def run_ours(args):
             kern_graph.replay()
     barrier()
     launches0 = lib.laris_launch_count()
-    with ClockSampler(local) as clocks:
+    with ClockSampler(range(world) if rank == 0 else []) as clocks:
         barrier()
         wall0 = time.perf_counter()
         if captured is not None:
