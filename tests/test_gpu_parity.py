@@ -839,3 +839,25 @@ def test_captured_scoring_replays_the_step(dev, layout):
     sm = cap.replay()
     torch.cuda.synchronize()
     assert torch.equal(sm.S, ref2.S) and torch.equal(ref2.S, ref.S * 4.0)
+
+
+def test_compact_and_single_pass_selection_agree(dev, monkeypatch):
+    """The sparse layout's two gene-selection forms (single pass with row ranges / compact two-pass CSR, used when the
+    single-pass scratch would be too large) give bit-identical scores and COSG sums."""
+    import laris_b200 as la
+    from laris_b200 import engine, _kernels as K
+    from laris_b200.synth import make_dataset
+    a, lr, c = make_dataset(3, n=4000, G=600, G_u=300, P=150)
+    lg, rg = la.tl._lr_gene_indices(a, lr)
+    g = engine.build_graph(a.obsm["X_spatial"], c.k, True, None)
+    labels = K.to_device(a.obs["CellTypes"].cat.codes.to_numpy().astype(np.int32), torch.int32)
+    res = []
+    for cap in (engine.SINGLE_PASS_MAX_BYTES, 0):
+        monkeypatch.setattr(engine, "SINGLE_PASS_MAX_BYTES", cap)
+        xu, lc, rc = engine.select_lr_genes(a.X, lg, rg, layout="sparse")
+        assert (xu.row_end is None) == (cap == 0)
+        sm = engine.lr_scores(xu, g, lc, rc)
+        s, cnt, q = K.onehot_contract_csr(xu.indptr, xu.packed, xu.G_u, labels, c.C, row_end=xu.row_end)
+        res.append((sm.S.clone(), sm.row_nnz.clone(), cnt.clone(), q.clone(), s.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    assert torch.allclose(res[0][3], res[1][3], rtol=1e-12) and torch.allclose(res[0][4], res[1][4], rtol=1e-12)
