@@ -137,3 +137,46 @@ def test_lr_column_layout_is_injective_and_conflict_free():
                     ident += np.bincount(g % 32).max()
                     groups += 1
         assert got <= ident and (G_u < 64 or got <= 0.7 * ident), (got, ident, groups)
+
+
+def test_complex_name_parsing(tiny):
+    """Host side of the multi-subunit extension: names with the separator become complexes (ids >= n_genes), a
+    trailing separator is just the gene, unknown subunits raise."""
+    import laris_b200 as la
+    a, _, _ = tiny
+    G = a.shape[1]
+    names = list(a.var_names)
+    lr = pd.DataFrame({"ligand": [names[3], f"{names[4]}+{names[5]}", names[3], f"{names[6]}+"],
+                       "receptor": [f"{names[7]}+{names[8]}+{names[9]}", names[10], f"{names[4]}+{names[5]}", names[11]]})
+    lig, rec, complexes = la.tl._lr_units(a, lr, "+")
+    assert lig[0] == 3 and lig[2] == 3 and rec[1] == 10 and rec[3] == 11 and lig[3] == 6       # "g+" is the gene itself
+    assert lig[1] >= G and rec[0] >= G and lig[1] == rec[2]                                     # one id per distinct complex
+    assert sorted(len(c) for c in complexes) == [2, 3]
+    assert list(complexes[lig[1] - G]) == [4, 5] and list(complexes[rec[0] - G]) == [7, 8, 9]
+    bad = lr.copy()
+    bad.loc[0, "receptor"] = f"{names[7]}+missing_gene"
+    with pytest.raises(KeyError, match="missing_gene"):
+        la.tl._lr_units(a, bad, "+")
+
+
+def test_index_by_gene_is_a_pivot():
+    """cosg_compat.index_by_gene (vectorised) equals the per-column definition on a ranked frame with ties and -1."""
+    from laris_b200 import cosg_compat
+    rng = np.random.default_rng(3)
+    names = np.array([f"n{i}" for i in range(40)], dtype=object)
+    scores = rng.random((40, 6))
+    scores[rng.random((40, 6)) < 0.2] = -1.0
+    groups = [f"a::{j}" for j in range(6)]
+    frame, order = cosg_compat.ranked_frame(names, scores, groups, "@@")
+    assert all((np.diff(frame[f"scores@@{g}"].to_numpy()) <= 0).all() for g in groups)
+    table = cosg_compat.index_by_gene(frame, column_delimiter="@@")
+    want = pd.DataFrame(np.where(scores == -1, 0.0, scores), index=names, columns=groups)
+    assert np.allclose(table.loc[names, groups].to_numpy(), want.to_numpy())
+
+
+def test_shard_bounds_and_layout_choice():
+    from laris_b200 import dist as ld, engine
+    assert list(ld.pair_bounds(10, 4)) == [0, 3, 6, 8, 10]
+    X = sp.random(100, 50, density=0.3, format="csr", random_state=1)
+    assert engine.choose_layout(X) == "dense" and engine.choose_layout(X, "sparse") == "sparse"
+    assert engine.choose_layout(sp.random(100, 50, density=0.05, format="csr", random_state=1)) == "sparse"
