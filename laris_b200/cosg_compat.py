@@ -26,6 +26,43 @@ import numpy as np
 import pandas as pd
 
 
+class StringTaker:
+    """``values[codes]`` as DataFrame columns, many times for one ``values``.  With pandas' Arrow-backed default string
+    dtype a column is built by decoding an Arrow dictionary (a few unique names, up to millions of rows) instead of
+    converting an object array element by element - same dtype, same values, ~6x faster for the 3.2 M-row cell-type
+    table and the 3200-column ranked frame of config 3.  Anything else (non-string values, no pyarrow, older pandas)
+    falls back to the plain gather."""
+
+    def __init__(self, values):
+        self.values = np.asarray(values, dtype=object)
+        self.dtype = self.dictionary = None
+        try:
+            if len(self.values) and all(isinstance(v, str) for v in self.values):
+                probe = pd.Series(self.values[:1]).dtype
+                if isinstance(probe, pd.StringDtype) and getattr(probe, "storage", None) == "pyarrow":
+                    import pyarrow as pa
+                    self._pa = pa
+                    self.dictionary = pa.array(list(self.values), type=pa.large_string())
+                    self.dtype = probe
+        except Exception:        # noqa: BLE001 - any pyarrow / pandas version quirk: plain gather
+            self.dtype = self.dictionary = None
+
+    def take(self, codes):
+        codes = np.asarray(codes)
+        if self.dictionary is not None:
+            try:
+                pa = self._pa
+                arr = pa.DictionaryArray.from_arrays(pa.array(codes.astype(np.int64)), self.dictionary).dictionary_decode()
+                return pd.array(arr, dtype=self.dtype)
+            except Exception:    # noqa: BLE001
+                pass
+        return self.values[codes]
+
+
+def take_strings(values, codes):
+    return StringTaker(values).take(codes)
+
+
 def real_cosg():
     try:
         import cosg  # type: ignore
@@ -50,8 +87,9 @@ def ranked_frame(names, scores, groups, delimiter="@@"):
     # descending, ties in reversed-ascending order
     order = np.argsort(scores, axis=0, kind="stable")[::-1]
     cols = {}
+    taker = StringTaker(names)
     for g, grp in enumerate(groups):
-        cols[f"names{delimiter}{grp}"] = names[order[:, g]]
+        cols[f"names{delimiter}{grp}"] = taker.take(order[:, g])
     for g, grp in enumerate(groups):
         cols[f"scores{delimiter}{grp}"] = scores[order[:, g], g]
     return pd.DataFrame(cols), order
@@ -81,6 +119,27 @@ def index_by_gene(df, gene_key="names", score_key="scores", set_nan_to_zero=Fals
     if set_nan_to_zero:
         out = out.fillna(0.0)
     return out
+
+
+def index_by_gene_of_ranking(frame, names, scores, groups, order, set_nan_to_zero=False,
+                             convert_negative_one_to_zero=True, column_delimiter="@@"):
+    """``index_by_gene(frame)`` for a frame that ``ranked_frame(names, scores, groups)`` just built: with the real
+    ``cosg`` the frame goes through ``cosg.indexByGene``; otherwise the pivot of a complete ranking is the score matrix
+    itself (rows in first-appearance order = the ranking of the first group), so the 2 * len(groups) string / float
+    columns are not parsed back."""
+    cosg = real_cosg()
+    if cosg is not None:
+        return cosg.indexByGene(frame, gene_key="names", score_key="scores", set_nan_to_zero=set_nan_to_zero,
+                                convert_negative_one_to_zero=convert_negative_one_to_zero,
+                                column_delimiter=column_delimiter)
+    names = np.asarray(names, dtype=object)
+    rows = order[:, 0] if len(groups) else np.arange(len(names))
+    vals = np.asarray(scores, dtype=np.float64)[rows]
+    if convert_negative_one_to_zero:
+        vals = np.where(vals == -1, 0.0, vals)
+    if set_nan_to_zero:
+        vals = np.nan_to_num(vals, nan=0.0)
+    return pd.DataFrame(vals, index=pd.Index(names[rows], dtype=object), columns=list(groups))
 
 
 def iqr_log_normalize(df, q_upper=0.95, q_lower=0.75):

@@ -43,6 +43,9 @@ def _scores_of(lr_adata) -> engine.ScoreMatrix:
     return sm
 
 
+_take_strings = cosg_compat.take_strings
+
+
 def _log(verbose, *a):
     if verbose:
         print(*a)
@@ -225,8 +228,9 @@ def _calculate_ligand_receptor_specificity(adata, laris_lr, groupby, mu: float =
     xu = engine.select_genes(adata.X, _gene_columns(adata, lr_set))
     score = engine.cosg_gene_scores(xu, K.to_device(codes, torch.int32), len(cats), n_c, mu, expressed_pct,
                                     remove_lowly_expressed)
-    frame, _ = cosg_compat.ranked_frame(lr_set, score, cats, "@@")
-    table = cosg_compat.index_by_gene(frame, set_nan_to_zero=True, convert_negative_one_to_zero=True)
+    frame, order = cosg_compat.ranked_frame(lr_set, score, cats, "@@")
+    table = cosg_compat.index_by_gene_of_ranking(frame, lr_set, score, [str(c) for c in cats], order, set_nan_to_zero=True,
+                                                 convert_negative_one_to_zero=True)
     table = table.loc[:, [str(c) for c in cats]]
     table.columns = cats
     return cosg_compat.iqr_log_normalize(table)
@@ -278,7 +282,7 @@ def _calculate_specificity_in_spatial_neighborhood(adata, lr_adata, groupby: str
                                    dtype=[(nm, "float32") for nm in pair_names])
     lr_adata.uns[key_added]["names"] = names_rec
     lr_adata.uns[key_added]["scores"] = scores_rec
-    table = cosg_compat.index_by_gene(frame, column_delimiter=column_delimiter)
+    table = cosg_compat.index_by_gene_of_ranking(frame, lr_names, raw, pair_names, order, column_delimiter=column_delimiter)
     return cosg_compat.iqr_log_normalize(table)
 
 
@@ -403,9 +407,11 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_r
     flat = flat.astype(np.float64)
     flat[flat < score_threshold] = 0.0
 
+    cat_taker = cosg_compat.StringTaker(cats_arr)
     res = pd.DataFrame({
-        "sender": cats_arr[row_send], "receiver": cats_arr[row_recv], "interaction_score": flat,
-        "ligand": lig[row_pair], "receptor": rec[row_pair], "interaction_name": inter_names[row_pair]})
+        "sender": cat_taker.take(row_send), "receiver": cat_taker.take(row_recv), "interaction_score": flat,
+        "ligand": _take_strings(lig, row_pair), "receptor": _take_strings(rec, row_pair),
+        "interaction_name": _take_strings(inter_names, row_pair)})
 
     if not calculate_pvalues:
         res["p_value"] = np.nan

@@ -180,3 +180,30 @@ def test_shard_bounds_and_layout_choice():
     X = sp.random(100, 50, density=0.3, format="csr", random_state=1)
     assert engine.choose_layout(X) == "dense" and engine.choose_layout(X, "sparse") == "sparse"
     assert engine.choose_layout(sp.random(100, 50, density=0.05, format="csr", random_state=1)) == "sparse"
+
+
+def test_take_strings_equals_object_gather():
+    from laris_b200.tools._utils import _take_strings
+    vals = np.array(["ct00", "ct01", "b::c", "é"], dtype=object)
+    codes = np.random.default_rng(0).integers(0, 4, 1000)
+    a = pd.DataFrame({"x": _take_strings(vals, codes)})["x"]
+    b = pd.DataFrame({"x": vals[codes]})["x"]
+    assert a.dtype == b.dtype and a.equals(b)
+    cats = np.array([3, 1, 2], dtype=object)                       # non-string categories: plain gather
+    assert list(_take_strings(cats, np.array([2, 0]))) == [2, 3]
+    assert len(_take_strings(np.array([], dtype=object), np.array([], dtype=np.int64))) == 0
+
+
+def test_pivot_of_a_ranking_equals_index_by_gene():
+    from laris_b200 import cosg_compat
+    rng = np.random.default_rng(5)
+    names = np.array([f"n{i}" for i in range(60)], dtype=object)
+    scores = rng.random((60, 7))
+    scores[rng.random((60, 7)) < 0.15] = -1.0
+    groups = [f"g{j}" for j in range(7)]
+    frame, order = cosg_compat.ranked_frame(names, scores, groups, "@@")
+    for kw in (dict(), dict(set_nan_to_zero=True, convert_negative_one_to_zero=True), dict(convert_negative_one_to_zero=False)):
+        a = cosg_compat.index_by_gene(frame, **kw)
+        b = cosg_compat.index_by_gene_of_ranking(frame, names, scores, groups, order, **kw)
+        assert list(a.index) == list(b.index) and list(a.columns) == list(b.columns)
+        assert np.array_equal(a.to_numpy(), b.to_numpy())
