@@ -236,8 +236,8 @@ LARIS_API int laris_neighborhood_composition(const int32_t* labels, const int32_
  *   qnorm2[a*C+b] = sum_i (N[i,a]*N[i,b])^2
  * Replaces _pairwise_row_multiply + sklearn cosine_similarity at
  * laris/tools/_utils.py:859-866.  impl: 0 = tcgen05 tensor-core kernel
- * (fp32 inputs split into bf16 hi/lo, three MMAs per K step, fp32 TMEM accumulation in 256-cell
- * chunks, fp64 combine; needs 8 <= C <= ~44), 1 = fp32 CUDA-core kernel (any C).
+ * (fp32 inputs split three ways into bf16 hi/mid/lo, six MMAs per 16-cell K step, fp32 TMEM accumulation
+ * in 256-cell chunks, fixed-order fp64 combine; needs C <= 64), 1 = fp32 CUDA-core kernel (any C).
  *   order [n] int32 or NULL: cell processing order for impl=0 (a spatially coherent order lets the
  *   operand builder skip the all-zero cell-type blocks); the result does not depend on it beyond
  *   fp32 summation order.
@@ -247,7 +247,8 @@ LARIS_API int laris_celltype_pair_contract(const float* S, int64_t ldS, int64_t 
 
 /* cnt[c*P + p] = #{i : labels[i]==c and S[i,p] != 0}.  Replaces
  * _compute_avg_expression on the binarised scores (laris/tools/_utils.py:1325-1337,
- * :334-338); frac = cnt / n_c on the host.  counts [C*P] uint64.  C <= 100. */
+ * :334-338); frac = cnt / n_c on the host.  counts [C*P] uint64; any C (cells are grouped by type on the
+ * device and counted in registers, integer atomics only where the type changes); labels outside [0,C) are skipped. */
 LARIS_API int laris_celltype_nonzero_count(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* labels,
                                  int32_t C, uint64_t* counts, void* stream);
 /* One-hot contraction straight from a packed CSR (laris_csr_select_fill layout):
