@@ -88,6 +88,7 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     obsm = {k: np.array(v, copy=True) for k, v in adata.obsm.items()}
     lr_adata = make_anndata(finish(), obs=obs, var=var, obsm=obsm)
     _utils._remember_scores(lr_adata.X, sm)
+    _utils._remember_expression(adata.X, xu)
     return lr_adata
 
 

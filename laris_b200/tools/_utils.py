@@ -30,6 +30,32 @@ def _remember_scores(X, sm):
     _SCORE_CACHE[key] = (weakref.ref(X, lambda _r, key=key: _SCORE_CACHE.pop(key, None)), sm)
 
 
+# the packed LR-gene expression prepareLRInteraction built stays on the device the same way (weakly keyed on the
+# expression matrix object): runLARIS's gene-specificity step then needs neither a second upload of X nor a second
+# selection pass.  Like the score cache it assumes the matrix object is not modified in place between the two calls.
+_EXPR_CACHE: dict = {}
+
+
+def _remember_expression(X, xu):
+    if xu.packed is None:                  # dense-panel layout: the COSG contraction reads packed rows
+        return
+    key = id(X)
+    _EXPR_CACHE[key] = (weakref.ref(X, lambda _r, key=key: _EXPR_CACHE.pop(key, None)), xu, X.shape, int(X.nnz))
+
+
+def _expression_of(X, gene_idx):
+    """(ExpressionU, packed column of every gene in ``gene_idx``) if X's LR-gene rows are resident and cover the genes."""
+    hit = _EXPR_CACHE.get(id(X))
+    if hit is None or hit[0]() is not X or hit[2] != X.shape or hit[3] != int(X.nnz):
+        return None
+    xu = hit[1]
+    pos = np.searchsorted(xu.genes, gene_idx)
+    pos[pos >= len(xu.genes)] = 0
+    if len(xu.genes) == 0 or not np.array_equal(xu.genes[pos], gene_idx):
+        return None
+    return xu, (pos if xu.columns is None else np.asarray(xu.columns)[pos])
+
+
 def _scores_of(lr_adata) -> engine.ScoreMatrix:
     X = lr_adata.X
     hit = _SCORE_CACHE.get(id(X))
@@ -225,9 +251,16 @@ def _calculate_ligand_receptor_specificity(adata, laris_lr, groupby, mu: float =
     lr_set = np.unique(np.hstack([laris_lr["ligand"].values, laris_lr["receptor"].values]))
     codes, cats = _group_codes(adata.obs[groupby])
     n_c = np.bincount(codes, minlength=len(cats))
-    xu = engine.select_genes(adata.X, _gene_columns(adata, lr_set))
-    score = engine.cosg_gene_scores(xu, K.to_device(codes, torch.int32), len(cats), n_c, mu, expressed_pct,
-                                    remove_lowly_expressed)
+    gene_idx = _gene_columns(adata, lr_set)
+    hit = _expression_of(adata.X, gene_idx)
+    if hit is not None:                    # rows of the LR genes are still on the device from prepareLRInteraction
+        xu, rows = hit
+        score = engine.cosg_gene_scores(xu, K.to_device(codes, torch.int32), len(cats), n_c, mu, expressed_pct,
+                                        remove_lowly_expressed)[rows]
+    else:
+        xu = engine.select_genes(adata.X, gene_idx)
+        score = engine.cosg_gene_scores(xu, K.to_device(codes, torch.int32), len(cats), n_c, mu, expressed_pct,
+                                        remove_lowly_expressed)
     frame, order = cosg_compat.ranked_frame(lr_set, score, cats, "@@")
     table = cosg_compat.index_by_gene_of_ranking(frame, lr_set, score, [str(c) for c in cats], order, set_nan_to_zero=True,
                                                  convert_negative_one_to_zero=True)
