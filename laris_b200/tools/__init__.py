@@ -64,7 +64,8 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     name containing this separator (e.g. ``"TGFBR1+TGFBR2"`` with ``complex_sep="+"``) is a multi-subunit
     complex; its diffused expression is the ``complex_rule`` ('min' | 'gmean') of its subunits' and it counts as
     expressed in a cell only if every subunit is.  Without it, complexes are pre-expanded rows as in the
-    reference's tutorial.
+    reference's tutorial.  (The spatial-specificity step of ``runLARIS`` takes such rows as they are; its
+    cell-type step looks ligand / receptor names up as genes, like the reference, so it needs expanded rows.)
     """
     xy = _utils._coords(adata, use_rep_spatial)
     # schedule: the expression matrix goes up on the copy stream while the host resolves the LR table and the graph is
