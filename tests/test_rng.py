@@ -48,3 +48,24 @@ def test_numpy_replay_known_answers():
     np.random.shuffle(x)
     assert np.array_equal(cols, c2) and np.array_equal(x, (np.arange(150) * 1.5)[perm])
     assert np.array_equal(rs.randint(0, 30, size=(4, 7)), np.random.randint(0, 30, size=(4, 7)))
+
+
+def test_pvalue_draw_digits_are_uniform_and_independent():
+    """Three draws per Philox word (base-nb digits of w / 2^32): each digit uniform on [0, nb), consecutive digits of one
+    word independent (chi-square on singles and on pairs), and the single-draw scheme is kept for nb > 64."""
+    nb = 30
+    d = rng.philox_pvalue_draws(np.arange(4000), 1200, nb, 27)
+    assert d.min() == 0 and d.max() == nb - 1
+    for j in range(3):                                       # digit j of every word
+        c = np.bincount(d[:, j::3].ravel(), minlength=nb)
+        chi2 = ((c - c.mean()) ** 2 / c.mean()).sum()
+        assert chi2 < 2.5 * nb, (j, chi2)                    # dof 29: far inside the 1e-6 tail bound
+    first, second = d[:, 0::3], d[:, 1::3]
+    m = min(first.shape[1], second.shape[1])
+    c = np.bincount((first[:, :m] * nb + second[:, :m]).ravel(), minlength=nb * nb)
+    chi2 = ((c - c.mean()) ** 2 / c.mean()).sum()
+    assert chi2 < 1.25 * nb * nb, chi2                       # dof 899
+    wide = rng.philox_pvalue_draws(np.arange(50), 101, 200, 27)
+    assert wide.shape == (50, 101) and wide.max() < 200
+    # prefix property: fewer permutations are a prefix of more (sharding by permutation ranges relies on it)
+    assert np.array_equal(rng.philox_pvalue_draws(np.arange(7), 100, nb, 5), rng.philox_pvalue_draws(np.arange(7), 250, nb, 5)[:, :100])
