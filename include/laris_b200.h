@@ -295,6 +295,63 @@ LARIS_API int laris_pvalue_counts(const double* table, int64_t ldt, int32_t n_gr
 LARIS_API int laris_bh_fdr(const double* p, const uint8_t* sel, int32_t n_groups, int32_t len, double* fdr,
                  void* stream);
 
+/* ------------------------------------------- step-2 tables (T1..T5) ----
+ * The P x C^2-sized fp64 tables between the S-sized passes and K6/K7 stay on the device; these entry points
+ * replace the reference's pandas / numpy / sklearn arithmetic on them.  L = C*C, group g = sender*C + receiver.
+ *
+ * T1 (laris/tools/_utils.py:862-880): cos[p,l] = num[p,l] / (sqrt(ss[p]) * sqrt(qn2[l])) (0 where the
+ * denominator is 0) - sklearn cosine_similarity of the score columns against the cell-type-pair profiles - and
+ * reg = cos^2 / ((1-mu) cos^2 + mu * sum_l cos^2) * cos (mu == 1: / sum_l cos^2), exact zeros staying zero.
+ * num, cos_out (may be NULL), reg_out: [P*L] fp64; ss [P], qn2 [L] fp64. */
+LARIS_API int laris_pair_cosine_regularise(const double* num, const double* ss, const double* qn2, int32_t P, int32_t L,
+                                           double mu, double* cos_out, double* reg_out, void* stream);
+/* T2: stand-in of cosg.iqrLogNormalize (call sites laris/tools/_utils.py:596, :975; the package is not vendored
+ * by the reference - PARITY UNPINNED).  Per column of table [rows*cols]: scale = Q(q_upper) - Q(q_lower) of the
+ * positive entries (numpy 'linear' quantiles; their maximum when that difference is not positive),
+ * out = log1p(max(x,0)/scale) / max over the column, i.e. values in [0,1]; a column without positive entries is 0. */
+LARIS_API int laris_column_iqr_log(const double* table, int64_t rows, int64_t cols, double q_upper, double q_lower,
+                                   double* out, void* stream);
+/* T3a (laris/tools/_utils.py:1351-1406): inter[t,s,r] = (frac[p,s]*frac[p,r]) * ((spec_l[t,s]*spec_r[t,r]) * factor[t]),
+ * p = pair_id[t], frac[p,c] = cnt[c*P+p] / n_c[c] (K5b counts).  spec_l, spec_r [Pt*C], factor [Pt], n_c [C] fp64;
+ * cnt [C*P] int64; pair_id [Pt] int32; inter [Pt*C*C] fp64. */
+LARIS_API int laris_interaction_scores(const double* spec_l, const double* spec_r, const double* factor,
+                                       const int64_t* cnt, const double* n_c, const int32_t* pair_id, int32_t Pt,
+                                       int32_t P, int32_t C, double* inter, void* stream);
+/* T3b (:1426-1437): out2[0] = mean of the min(k, m) largest of values[0..m), out2[1] = 0.1 / out2[0] (1 when the
+ * mean is not positive).  Exact (radix select); k <= 4096. */
+LARIS_API int laris_topk_mean(const double* values, int64_t m, int32_t k, double* out2, void* stream);
+/* T3c (:1463-1489): flat[t,g] = (inter[t,g] * rescale2[1]) * ctc[pair_id[t]*L + g], values below score_threshold
+ * -> 0; also scattered into the group-major table [L*P] (zero elsewhere) and active [P] that K6 reads. */
+LARIS_API int laris_finalize_scores(const double* inter, const double* rescale2, const double* ctc,
+                                    const int32_t* pair_id, int32_t Pt, int32_t P, int32_t L, double score_threshold,
+                                    double* flat, double* table, uint8_t* active, void* stream);
+/* T5a (:1573-1594, :1617-1634): p = (ge+1)/(n_perm+1), or the conditional (ge_nz+1)/(nz+1) where the score is
+ * positive and 1 elsewhere; p_round = numpy.round(p, 6); sel = active pair and (score > prefilter_threshold when
+ * prefilter).  All arrays group-major [L*P]. */
+LARIS_API int laris_pvalues_from_counts(const double* table, const uint8_t* active, const int32_t* ge, const int32_t* nz,
+                                        const int32_t* ge_nz, int32_t L, int32_t P, int32_t n_perm, int conditional,
+                                        int prefilter, double prefilter_threshold, double* p_out, double* p_round,
+                                        uint8_t* sel, void* stream);
+/* T5b (:1648-1658): rows layout [Pt*L] of the group-major p / fdr tables; fdr clipped to <= 1, NaN -> 1,
+ * nlog = max(-log10(fdr + 1e-10), 0). */
+LARIS_API int laris_gather_result_rows(const double* p_tab, const double* fdr_tab, const int32_t* pair_id, int32_t Pt,
+                                       int32_t P, int32_t L, double* p_rows, double* fdr_rows, double* nlog_rows,
+                                       void* stream);
+
+/* ------------------------------------------------- K4a + K4b batched ----
+ * Observed statistics and n_repeats random-graph repeats of the same score matrix in one call
+ * (laris/tools/__init__.py:468-481, laris/tools/_utils.py:496-518), out [(obs ? 1 : 0) + n_repeats][5][P] fp64 with the
+ * rows of laris_spatial_stats (dot, sum S^2, sum T^2, sum S, nnz); row 0 is the observed graph when idx != NULL.
+ *   observed graph (idx, w [n*k], order [n] or NULL): for k <= 15 the distinct neighbour rows of every 128-cell tile
+ *     of the processing order are staged in shared memory by the TMA engine (cp.async.bulk + mbarrier, double
+ *     buffered) and read from there, so DRAM / L2 see each row piece ~1.6 times instead of 1+k times;
+ *   random graphs (null_idx int32, null_w fp32, each [n_repeats][n][k]; rows are L1-normalised, duplicates add):
+ *     up to three repeats share one pass, so S[i,:] and its sums are read / formed once per batch;
+ *     (1/RB + k) * 4*n*P bytes per repeat, the HBM-bound pass of the path. */
+LARIS_API int laris_spatial_stats_batched(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* idx,
+                                          const float* w, int k, const int32_t* order, const int32_t* null_idx,
+                                          const float* null_w, int32_t n_repeats, double* out, void* stream);
+
 /* ------------------------------------------------------- per-cell QC ----
  * Per-cell metrics of the score matrix that scanpy.pp.calculate_qc_metrics writes to lr_adata.obs at
  * laris/tools/__init__.py:493-496: total[i] = sum_p S[i,p], nnz[i] = #{p: S[i,p] != 0} and, for each N of

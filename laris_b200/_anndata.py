@@ -21,7 +21,7 @@ class AnnDataLite:
     """Duck-typed stand-in for ``anndata.AnnData`` (container only)."""
 
     def __init__(self, X=None, obs=None, var=None, obsm=None, uns=None, layers=None):
-        if X is not None and not sp.issparse(X):
+        if X is not None and not sp.issparse(X) and not getattr(X, "_laris_resident", False):
             X = np.asarray(X)
         self._X = X
         n_obs, n_vars = (X.shape if X is not None else (0, 0))
@@ -81,7 +81,7 @@ class AnnDataLite:
 
     # -- copy / slice ---------------------------------------------------
     def copy(self):
-        X = self._X.copy() if self._X is not None else None
+        X = self._X.copy() if self._X is not None and hasattr(self._X, "copy") else self._X
         return type(self)(
             X, self.obs.copy(), self.var.copy(),
             {k: (v.copy() if hasattr(v, "copy") else v) for k, v in self.obsm.items()},

@@ -233,9 +233,23 @@ def spatial_stats(S, P, idx, w, l1_normalise, order=None):
     return out
 
 
-def null_graph_philox(n, k, w, repeat, seed):
-    cols = torch.empty((n, k), dtype=torch.int32, device=w.device)
-    wout = torch.empty((n, k), dtype=torch.float32, device=w.device)
+def spatial_stats_batched(S, P, idx, w, order, null_idx=None, null_w=None):
+    """[1+R, 5, P] fp64: observed graph (row 0) and the R random graphs ``null_idx`` / ``null_w`` [R, n, k]."""
+    n, ld = S.shape
+    k = idx.shape[1]
+    R = 0 if null_idx is None else int(null_idx.shape[0])
+    out = torch.empty((1 + R, 5, P), dtype=torch.float64, device=S.device)
+    check(lib.laris_spatial_stats_batched(_ptr(S, torch.float32), ld, n, P, _ptr(idx, torch.int32), _ptr(w, torch.float32),
+                                          k, _ptr(order, torch.int32) if order is not None else None,
+                                          _ptr(null_idx, torch.int32) if R else None,
+                                          _ptr(null_w, torch.float32) if R else None, R, _ptr(out), _stream()),
+          "laris_spatial_stats_batched")
+    return out
+
+
+def null_graph_philox(n, k, w, repeat, seed, out=None):
+    cols, wout = out if out is not None else (torch.empty((n, k), dtype=torch.int32, device=w.device),
+                                              torch.empty((n, k), dtype=torch.float32, device=w.device))
     check(lib.laris_null_graph_philox(n, k, _ptr(w, torch.float32), int(repeat), int(seed) & (2 ** 64 - 1), _ptr(cols),
                                       _ptr(wout), _stream()), "laris_null_graph_philox")
     return cols, wout
@@ -335,3 +349,77 @@ def bh_fdr(p, sel):
     out = torch.empty((Gn, L), dtype=torch.float64, device=p.device)
     check(lib.laris_bh_fdr(_ptr(p, torch.float64), _ptr(sel, torch.uint8), Gn, L, _ptr(out), _stream()), "laris_bh_fdr")
     return out
+
+
+# --------------------------------------------------- step-2 tables (T1..T5) ----
+def pair_cosine_regularise(num, ss, qn2, mu, want_cos=False):
+    """(cos or None, reg) [P, L] fp64 from the K5 numerators, the column sums of squares and the profile norms."""
+    P, L = num.shape
+    cos = torch.empty((P, L), dtype=torch.float64, device=num.device) if want_cos else None
+    reg = torch.empty((P, L), dtype=torch.float64, device=num.device)
+    check(lib.laris_pair_cosine_regularise(_ptr(num, torch.float64), _ptr(ss, torch.float64), _ptr(qn2, torch.float64),
+                                           P, L, float(mu), _ptr(cos), _ptr(reg), _stream()),
+          "laris_pair_cosine_regularise")
+    return cos, reg
+
+
+def column_iqr_log(table, q_upper=0.95, q_lower=0.75):
+    rows, cols = table.shape
+    out = torch.empty_like(table)
+    check(lib.laris_column_iqr_log(_ptr(table, torch.float64), rows, cols, float(q_upper), float(q_lower), _ptr(out),
+                                   _stream()), "laris_column_iqr_log")
+    return out
+
+
+def interaction_scores(spec_l, spec_r, factor, cnt, n_c, pair_id, P):
+    Pt, C = spec_l.shape
+    inter = torch.empty((Pt, C * C), dtype=torch.float64, device=spec_l.device)
+    check(lib.laris_interaction_scores(_ptr(spec_l, torch.float64), _ptr(spec_r, torch.float64),
+                                       _ptr(factor, torch.float64), _ptr(cnt, torch.int64), _ptr(n_c, torch.float64),
+                                       _ptr(pair_id, torch.int32), Pt, int(P), C, _ptr(inter), _stream()),
+          "laris_interaction_scores")
+    return inter
+
+
+def topk_mean(values, k=100):
+    """Device pair (mean of the k largest, 0.1 / mean or 1)."""
+    out = torch.empty(2, dtype=torch.float64, device=values.device)
+    check(lib.laris_topk_mean(_ptr(values, torch.float64), values.numel(), int(k), _ptr(out), _stream()),
+          "laris_topk_mean")
+    return out
+
+
+def finalize_scores(inter, rescale2, ctc, pair_id, P, score_threshold):
+    Pt, L = inter.shape
+    dev = inter.device
+    flat = torch.empty((Pt, L), dtype=torch.float64, device=dev)
+    table = torch.empty((L, P), dtype=torch.float64, device=dev)
+    active = torch.empty(P, dtype=torch.uint8, device=dev)
+    check(lib.laris_finalize_scores(_ptr(inter, torch.float64), _ptr(rescale2, torch.float64), _ptr(ctc, torch.float64),
+                                    _ptr(pair_id, torch.int32), Pt, int(P), L, float(score_threshold), _ptr(flat),
+                                    _ptr(table), _ptr(active), _stream()), "laris_finalize_scores")
+    return flat, table, active
+
+
+def pvalues_from_counts(table, active, ge, nz, both, n_perm, conditional, prefilter, prefilter_threshold):
+    L, P = table.shape
+    dev = table.device
+    p = torch.empty((L, P), dtype=torch.float64, device=dev)
+    pr = torch.empty((L, P), dtype=torch.float64, device=dev)
+    sel = torch.empty((L, P), dtype=torch.uint8, device=dev)
+    check(lib.laris_pvalues_from_counts(_ptr(table, torch.float64), _ptr(active, torch.uint8), _ptr(ge, torch.int32),
+                                        _ptr(nz, torch.int32) if nz is not None else None,
+                                        _ptr(both, torch.int32) if both is not None else None, L, P, int(n_perm),
+                                        int(bool(conditional)), int(bool(prefilter)), float(prefilter_threshold),
+                                        _ptr(p), _ptr(pr), _ptr(sel), _stream()), "laris_pvalues_from_counts")
+    return p, pr, sel
+
+
+def gather_result_rows(p_tab, fdr_tab, pair_id):
+    L, P = p_tab.shape
+    Pt = pair_id.numel()
+    dev = p_tab.device
+    outs = [torch.empty((Pt, L), dtype=torch.float64, device=dev) for _ in range(3)]
+    check(lib.laris_gather_result_rows(_ptr(p_tab, torch.float64), _ptr(fdr_tab, torch.float64), _ptr(pair_id, torch.int32),
+                                       Pt, P, L, *[_ptr(o) for o in outs], _stream()), "laris_gather_result_rows")
+    return outs

@@ -44,6 +44,7 @@ SIGNATURES = {
     "laris_csr_compact": [_p, _i64, _i64, _i, _p, _p, _p, _p],
     "laris_csr_to_dense": [_p, _p, _p, _i64, _i, _p, _i64, _p],
     "laris_spatial_stats": [_p, _i64, _i64, _i, _p, _p, _i, _i, _p, _p, _p],
+    "laris_spatial_stats_batched": [_p, _i64, _i64, _i, _p, _p, _i, _p, _p, _p, _i, _p, _p],
     "laris_null_graph_philox": [_i64, _i, _p, _i, _u64, _p, _p, _p],
     "laris_gather_f32": [_p, _p, _i64, _p, _p],
     "laris_neighborhood_composition": [_p, _p, _p, _i64, _i, _i, _p, _p],
@@ -53,6 +54,13 @@ SIGNATURES = {
     "laris_onehot_contract_rows": [_p, _p, _p, _i64, _i, _p, _i, _p, _p, _p, _p],
     "laris_pvalue_counts": [_p, _i64, _i, _i, _p, _i, _p, _p, _i64, _i, _i, _i, _i, _u64, _p, _p, _p, _p, _p],
     "laris_bh_fdr": [_p, _p, _i, _i, _p, _p],
+    "laris_pair_cosine_regularise": [_p, _p, _p, _i, _i, _d, _p, _p, _p],
+    "laris_column_iqr_log": [_p, _i64, _i64, _d, _d, _p, _p],
+    "laris_interaction_scores": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p],
+    "laris_topk_mean": [_p, _i64, _i, _p, _p],
+    "laris_finalize_scores": [_p, _p, _p, _p, _i, _i, _i, _d, _p, _p, _p, _p],
+    "laris_pvalues_from_counts": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _d, _p, _p, _p, _p],
+    "laris_gather_result_rows": [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p],
     "laris_row_qc": [_p, _i64, _i64, _i, _p, _i, _p, _p, _p, _p],
     "laris_rowwise_cosine": [_p, _p, _i64, _i64, _i64, _i64, _p, _p],
     "laris_pairwise_row_multiply": [_p, _i, _i64, _p, _p],

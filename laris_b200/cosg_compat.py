@@ -10,15 +10,17 @@ tree, so:
 * otherwise the functions below are used.  ``index_by_gene`` is a plain pivot
   of the ranked ``names@@group`` / ``scores@@group`` frame and is determined by
   the frame layout the reference itself builds (laris/tools/_utils.py:945-953).
-  ``iqr_log_normalize`` is a LABELLED PLACEHOLDER (monotone per-column
-  rescale); it is **excluded from every parity claim** (SURVEY.md §8c,
-  DESIGN.md "cosg").
+  ``iqr_log_normalize`` is a LABELLED STAND-IN (monotone per-column rescale
+  to [0, 1]); it is **excluded from every parity claim** (SURVEY.md §8c,
+  DESIGN.md "cosg"), and ``runLARIS(by_celltype=True)`` warns loudly whenever
+  it is in use.
 
 The COSG score itself (cosine to the one-hot group indicator + the
 ``cos^3/((1-mu)cos^2 + mu*sum cos^2)`` regularisation, which the reference
 clones in laris/tools/_utils.py:861-880) runs on the device
-(``laris_celltype_cosine`` in include/laris_b200.h); only table reshaping
-lives here.
+(``laris_onehot_contract_rows`` for genes, ``laris_celltype_pair_contract`` +
+``laris_pair_cosine_regularise`` for the neighbourhood table, include/laris_b200.h);
+only table reshaping lives here.
 """
 from __future__ import annotations
 
@@ -143,10 +145,14 @@ def index_by_gene_of_ranking(frame, names, scores, groups, order, set_nan_to_zer
 
 
 def iqr_log_normalize(df, q_upper=0.95, q_lower=0.75):
-    """PLACEHOLDER for ``cosg.iqrLogNormalize`` - parity unpinned.
+    """STAND-IN for ``cosg.iqrLogNormalize`` - parity unpinned (the package is not vendored by the reference and not
+    installable here; the reference only documents that the result is a specificity score in [0, 1],
+    laris/tools/_utils.py:556-561).
 
-    Per column: scale = Q_upper - Q_lower of the positive entries (max if that
-    is 0), result = log1p(max(x,0)/scale).  Monotone, keeps zeros at zero.
+    Per column: scale = Q_upper - Q_lower of the positive entries (their maximum when that difference is not
+    positive), y = log1p(max(x, 0) / scale), result = y / max(y): monotone, zeros stay zero, the most specific
+    entry of every column is 1.  ``laris_column_iqr_log`` (include/laris_b200.h, T2) is the same arithmetic on the
+    device.  With the real ``cosg`` installed this function is never used.
     """
     cosg = real_cosg()
     if cosg is not None:
@@ -161,5 +167,24 @@ def iqr_log_normalize(df, q_upper=0.95, q_lower=0.75):
         scale = np.quantile(pos, q_upper) - np.quantile(pos, q_lower)
         if not scale > 0:
             scale = pos.max()
-        out[:, j] = np.log1p(np.maximum(col, 0.0) / scale)
+        y = np.log1p(np.maximum(col, 0.0) / scale)
+        out[:, j] = y / np.log1p(pos.max() / scale)
     return pd.DataFrame(out, index=df.index, columns=df.columns)
+
+
+_WARNED = False
+
+
+def warn_if_stand_in():
+    """One loud warning per process when the cell-type step runs without the real ``cosg``: its interaction scores
+    then go through the stand-in normalisation above and DIFFER from the reference's (ranking within a column is
+    preserved, values are not)."""
+    global _WARNED
+    if _WARNED or real_cosg() is not None:
+        return
+    _WARNED = True
+    import warnings
+    warnings.warn(
+        "laris_b200: the 'cosg' package (cosg>=1.0.3) is not importable; cosg.indexByGene / cosg.iqrLogNormalize are "
+        "replaced by laris_b200.cosg_compat stand-ins whose parity with cosg is UNPINNED. Cell-type interaction scores, "
+        "their p-values and FDR will differ from genecell/LARIS until cosg is installed.", RuntimeWarning, stacklevel=3)

@@ -151,7 +151,7 @@ __global__ void bh_fdr_kernel(const double* __restrict__ p, const uint8_t* __res
     __syncthreads();
     // suffix minimum (Hillis-Steele)
     for (int off = 1; off < cap; off <<= 1) {
-        double v[8];
+        double v[16];
         int cnt = 0;
         for (int i = tid; i < cap; i += blockDim.x) { v[cnt++] = i + off < cap ? fmin(key[i], key[i + off]) : key[i]; }
         __syncthreads();
@@ -194,7 +194,7 @@ extern "C" int laris_bh_fdr(const double* p, const uint8_t* sel, int32_t n_group
     LARIS_CHECK_ARG(p && sel && fdr && n_groups >= 1 && len >= 1, "laris_bh_fdr: bad arguments");
     int cap = 32;
     while (cap < len) cap <<= 1;
-    if (cap > 8192) { set_error("laris_bh_fdr: group length %d exceeds the shared-memory sort (limit 8192)", len); return LARIS_E_LIMIT; }
+    if (cap > 16384) { set_error("laris_bh_fdr: group length %d exceeds the shared-memory sort (limit 16384 LR pairs per group)", len); return LARIS_E_LIMIT; }
     const size_t smem = (size_t)cap * 12;
     LARIS_CUDA(cudaFuncSetAttribute(bh_fdr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int threads = cap >= 1024 ? 1024 : cap;

@@ -10,8 +10,10 @@
 // fetched by one CTA is an L2 hit for the others (real graph).  For the random
 // graph every neighbour row is a fresh 4*P-byte HBM read - that pass is the
 // HBM-bound one: (1+k)*4*n*P + 8*n*k bytes.
+#include "async.cuh"
 #include "common.cuh"
 #include "rng.cuh"
+#include "scan.cuh"
 
 namespace laris {
 
@@ -139,6 +141,404 @@ stats_reduce_kernel(const double* __restrict__ partial, int nchunks, int64_t Ppa
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// K4b batched: RB random-graph repeats in one pass.  S[i,:] is read once for all repeats, sum S^2 / sum S / nnz
+// are formed once; every neighbour row of every repeat is a fresh HBM read (k * RB independent 128-bit streaming
+// loads per thread and row).  partial layout [chunk][2*RB+3][Ppad]: (dot_r, tt_r) per repeat, then ss, sum, nnz.
+// ---------------------------------------------------------------------------------------------------------
+template <int RB>
+__global__ void __launch_bounds__(kStThreads)
+spatial_null_stats_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t n, const int32_t* __restrict__ nidx,
+                          const float* __restrict__ nw, int k, int nchunks, double* __restrict__ partial) {
+    constexpr int RBATCH = 4;                                        // rows staged per barrier
+    __shared__ int32_t s_idx[RBATCH * RB * kStMaxK];
+    __shared__ float s_w[RBATCH * RB * kStMaxK];
+    const int tid = threadIdx.x;
+    const int64_t col4 = (int64_t)blockIdx.x * kStThreads + tid;
+    const bool active = col4 < ld4;
+    const int chunk = blockIdx.y;
+    double a_dot[RB][4], a_tt[RB][4], a_ss[4] = {0, 0, 0, 0}, a_s[4] = {0, 0, 0, 0};
+    int a_nz[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { a_dot[r][c] = 0.0; a_tt[r][c] = 0.0; }
+    const int64_t nk = n * (int64_t)k;
+    for (int64_t m0 = chunk; m0 < n; m0 += (int64_t)RBATCH * nchunks) {
+        __syncthreads();
+        for (int e = tid; e < RBATCH * RB * k; e += kStThreads) {
+            const int rb = e / (RB * k), rem = e - rb * (RB * k), r = rem / k, j = rem - r * k;
+            const int64_t i = m0 + (int64_t)rb * nchunks;
+            if (i < n) { s_idx[e] = nidx[(int64_t)r * nk + i * k + j]; s_w[e] = nw[(int64_t)r * nk + i * k + j]; }
+        }
+        __syncthreads();
+        if (!active) continue;
+#pragma unroll 1
+        for (int rb = 0; rb < RBATCH; ++rb) {
+            const int64_t i = m0 + (int64_t)rb * nchunks;
+            if (i >= n) break;
+            const float4 s = ld_stream_f4(S4 + i * ld4 + col4);
+            const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int32_t* ni = s_idx + (rb * RB + r) * k;
+                const float* wv = s_w + (rb * RB + r) * k;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                float wsum = 0.f;
+                int j = 0;
+                for (; j + 4 <= k; j += 4) {
+                    const float4 v0 = ld_stream_f4(S4 + (int64_t)ni[j] * ld4 + col4);
+                    const float4 v1 = ld_stream_f4(S4 + (int64_t)ni[j + 1] * ld4 + col4);
+                    const float4 v2 = ld_stream_f4(S4 + (int64_t)ni[j + 2] * ld4 + col4);
+                    const float4 v3 = ld_stream_f4(S4 + (int64_t)ni[j + 3] * ld4 + col4);
+                    const float w0 = wv[j], w1 = wv[j + 1], w2 = wv[j + 2], w3 = wv[j + 3];
+                    t.x = fmaf(w0, v0.x, t.x); t.y = fmaf(w0, v0.y, t.y); t.z = fmaf(w0, v0.z, t.z); t.w = fmaf(w0, v0.w, t.w);
+                    t.x = fmaf(w1, v1.x, t.x); t.y = fmaf(w1, v1.y, t.y); t.z = fmaf(w1, v1.z, t.z); t.w = fmaf(w1, v1.w, t.w);
+                    t.x = fmaf(w2, v2.x, t.x); t.y = fmaf(w2, v2.y, t.y); t.z = fmaf(w2, v2.z, t.z); t.w = fmaf(w2, v2.w, t.w);
+                    t.x = fmaf(w3, v3.x, t.x); t.y = fmaf(w3, v3.y, t.y); t.z = fmaf(w3, v3.z, t.z); t.w = fmaf(w3, v3.w, t.w);
+                    wsum += (w0 + w1) + (w2 + w3);
+                }
+                for (; j < k; ++j) {
+                    const float4 v0 = ld_stream_f4(S4 + (int64_t)ni[j] * ld4 + col4);
+                    const float w0 = wv[j];
+                    t.x = fmaf(w0, v0.x, t.x); t.y = fmaf(w0, v0.y, t.y); t.z = fmaf(w0, v0.z, t.z); t.w = fmaf(w0, v0.w, t.w);
+                    wsum += w0;
+                }
+                if (wsum != 0.f) {                                   // L1 row normalisation of the random graph
+                    const float inv = 1.0f / wsum;
+                    t.x *= inv; t.y *= inv; t.z *= inv; t.w *= inv;
+                }
+                const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    a_dot[r][c] += (double)(sv[c] * tv[c]);
+                    a_tt[r][c] += (double)(tv[c] * tv[c]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                a_ss[c] += (double)(sv[c] * sv[c]);
+                a_s[c] += (double)sv[c];
+                a_nz[c] += sv[c] != 0.f ? 1 : 0;
+            }
+        }
+    }
+    if (active) {
+        const int64_t Ppad = ld4 * 4;
+        constexpr int Q = 2 * RB + 3;
+        double* o = partial + (int64_t)chunk * Q * Ppad + col4 * 4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                o[(2 * r) * Ppad + c] = a_dot[r][c];
+                o[(2 * r + 1) * Ppad + c] = a_tt[r][c];
+            }
+            o[(2 * RB) * Ppad + c] = a_ss[c];
+            o[(2 * RB + 1) * Ppad + c] = a_s[c];
+            o[(2 * RB + 2) * Ppad + c] = (double)a_nz[c];
+        }
+    }
+}
+
+// partial [nchunks][2*RB+3][Ppad] -> out rows [RB][5][P] (dot, ss, tt, sum, nnz per repeat; ss / sum / nnz repeated)
+__global__ void __launch_bounds__(256)
+null_stats_reduce_kernel(const double* __restrict__ partial, int nchunks, int64_t Ppad, int P, int RB,
+                         double* __restrict__ out) {
+    __shared__ double red[8][33];
+    const int cx = threadIdx.x & 31, cy = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + cx, q = blockIdx.y, Q = 2 * RB + 3;
+    double s = 0.0;
+    if (p < P)
+        for (int c = cy; c < nchunks; c += 8) s += partial[((int64_t)c * Q + q) * Ppad + p];
+    red[cy][cx] = s;
+    __syncthreads();
+    if (cy == 0 && p < P) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += red[r][cx];
+        if (q < 2 * RB) {
+            out[((int64_t)(q >> 1) * 5 + ((q & 1) ? 2 : 0)) * P + p] = t;
+        } else {
+            const int stat = q == 2 * RB ? 1 : (q == 2 * RB + 1 ? 3 : 4);
+            for (int r = 0; r < RB; ++r) out[((int64_t)r * 5 + stat) * P + p] = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4a tiled: observed-graph statistics with the neighbour rows staged in shared memory by the TMA engine.
+//
+// The graph is spatial and `order` walks the tissue, so the k neighbours of kTileCells consecutive cells are
+// mostly the same few rows.  tile_plan_kernel finds, per tile, the DISTINCT rows (own rows included) and rewrites
+// every edge as (slot in that list, weight).  spatial_obs_tile_kernel is persistent (one CTA per SM): a producer
+// warp brings the 64-column pieces of a tile's distinct rows into shared memory with cp.async.bulk (one bulk copy
+// per row piece, completion counted on an mbarrier), double buffered, while 16 consumer warps form
+// T = sum_j w_j * row[slot_j] and the five sums from shared memory.  HBM / L2 then see each row piece about
+// u/128 ~ 1.6 times per slab instead of 1+k times.  Work items (slab, tile) are dealt to CTAs as contiguous
+// ranges; a CTA writes one partial record per slab segment and the records are reduced in a fixed order.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kTileCells = 128;
+constexpr int kTileCap = 352;            // distinct rows staged per tile; larger unions read global rows directly
+constexpr int kTileIds = 2048;           // kTileCells * (k + 1) <= kTileIds
+constexpr int kTileMaxK = 15;
+constexpr int kSlabCols = 64;            // columns per work item: 256-byte row pieces
+constexpr int kTileConsumers = 512;      // 16 quads x 32 cell lanes
+constexpr int kTileThreads = kTileConsumers + 32;
+
+struct TilePlan {
+    int32_t* cnt;      // [ntiles]                 distinct rows, or -1: the tile reads global rows directly
+    int32_t* rows;     // [ntiles][kTileCap]       the distinct rows
+    int2* ent;         // [ntiles][kTileCells][k]  {slot (or row when cnt < 0), weight bits}
+    int32_t* self;     // [ntiles][kTileCells]     slot (or row) of the cell itself; -1 = past the end
+};
+
+__global__ void __launch_bounds__(256)
+tile_plan_kernel(const int32_t* __restrict__ idx, const float* __restrict__ w, int k, const int32_t* __restrict__ order,
+                 int64_t n, TilePlan plan) {
+    __shared__ int32_t arr[kTileIds];
+    __shared__ int32_t uniq[kTileIds];
+    __shared__ int32_t cell[kTileCells];
+    __shared__ int32_t scan_s[33];
+    const int tid = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    for (int c = tid; c < kTileCells; c += 256) {
+        const int64_t q = tile * kTileCells + c;
+        cell[c] = q < n ? (order ? order[q] : (int32_t)q) : -1;
+    }
+    __syncthreads();
+    for (int e = tid; e < kTileIds; e += 256) {
+        int32_t v = INT32_MAX;
+        if (e < kTileCells) {
+            if (cell[e] >= 0) v = cell[e];
+        } else if (e < kTileCells * (k + 1)) {
+            const int c = (e - kTileCells) / k, j = (e - kTileCells) - c * k;
+            if (cell[c] >= 0) {
+                const int32_t id = idx[(int64_t)cell[c] * k + j];
+                if (id >= 0) v = id;
+            }
+        }
+        arr[e] = v;
+    }
+    __syncthreads();
+    for (int kk = 2; kk <= kTileIds; kk <<= 1)
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < kTileIds; i += 256) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const bool up = (i & kk) == 0;
+                    const int32_t a = arr[i], b = arr[l];
+                    if ((a > b) == up) { arr[i] = b; arr[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // distinct values -> uniq (8 consecutive elements per thread, block scan of the counts)
+    int flags = 0, cntl = 0;
+    const int base = tid * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int i = base + j;
+        const bool f = arr[i] != INT32_MAX && (i == 0 || arr[i] != arr[i - 1]);
+        flags |= (f ? 1 : 0) << j;
+        cntl += f;
+    }
+    int total;
+    int pos = block_exclusive_scan<int>(cntl, &total, scan_s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        if (flags & (1 << j)) uniq[pos++] = arr[base + j];
+    __syncthreads();
+    const int u = total;
+    const bool staged = u <= kTileCap;
+    if (tid == 0) plan.cnt[tile] = staged ? u : -1;
+    if (staged)
+        for (int r = tid; r < kTileCap; r += 256) plan.rows[tile * kTileCap + r] = r < u ? uniq[r] : 0;
+    auto slot_of = [&](int32_t id) {
+        int lo = 0, hi = u;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (uniq[mid] < id) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+    };
+    for (int c = tid; c < kTileCells; c += 256)
+        plan.self[tile * kTileCells + c] = cell[c] < 0 ? -1 : (staged ? slot_of(cell[c]) : cell[c]);
+    for (int e = tid; e < kTileCells * k; e += 256) {
+        const int c = e / k, j = e - c * k;
+        int2 out = make_int2(0, 0);
+        if (cell[c] >= 0) {
+            const int32_t id = idx[(int64_t)cell[c] * k + j];
+            const float wv = w[(int64_t)cell[c] * k + j];
+            if (id >= 0) out = make_int2(staged ? slot_of(id) : id, __float_as_int(wv));
+            else out = make_int2(staged ? slot_of(cell[c]) : cell[c], 0);       // flagged edge: weight 0 on the own row
+        }
+        plan.ent[(tile * kTileCells + c) * k + j] = out;
+    }
+}
+
+struct TileSmem {
+    static __host__ __device__ size_t stage_bytes(int k) {
+        return (size_t)kTileCap * kSlabCols * 4 + (size_t)kTileCells * k * 8 + (size_t)kTileCells * 4;
+    }
+    static __host__ __device__ size_t total(int k) { return 2 * stage_bytes(k) + 16 * 16 * 4 * 8 + 64; }
+};
+
+__global__ void __launch_bounds__(kTileThreads, 1)
+spatial_obs_tile_kernel(const float* __restrict__ S, int64_t ldS, int k, TilePlan plan, int64_t ntiles, int nslabs,
+                        int maxseg, double* __restrict__ partial, int32_t* __restrict__ rec_slab) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const size_t stage_b = TileSmem::stage_bytes(k);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double* red = reinterpret_cast<double*>(smem + 2 * stage_b);                 // [16 warps][16 quads][4]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_b + 16 * 16 * 4 * 8);
+    const uint32_t full0 = aio::smem_addr(bars), empty0 = aio::smem_addr(bars + 2);
+    if (tid == 0) {
+        aio::mbar_init(full0, 1); aio::mbar_init(full0 + 8, 1);
+        aio::mbar_init(empty0, kTileConsumers / 32); aio::mbar_init(empty0 + 8, kTileConsumers / 32);
+        aio::mbar_init_fence();
+    }
+    __syncthreads();
+    const int64_t W = (int64_t)nslabs * ntiles;
+    const int64_t w0 = W * blockIdx.x / gridDim.x, w1 = W * (blockIdx.x + 1) / gridDim.x;
+    const uint32_t ent_bytes = (uint32_t)kTileCells * k * 8, self_bytes = kTileCells * 4;
+
+    if (warp == kTileConsumers / 32) {
+        // ------------------------------ producer warp ------------------------------
+        for (int64_t wi = w0, it = 0; wi < w1; ++wi, ++it) {
+            const int st = (int)(it & 1);
+            const uint32_t ph = (uint32_t)((it >> 1) & 1);
+            const int slab = (int)(wi / ntiles);
+            const int64_t tile = wi - (int64_t)slab * ntiles;
+            aio::mbar_wait_sleep(empty0 + 8 * st, ph ^ 1u);
+            unsigned char* stage = smem + st * stage_b;
+            const uint32_t tile_s = aio::smem_addr(stage);
+            const uint32_t ent_s = tile_s + kTileCap * kSlabCols * 4, self_s = ent_s + ent_bytes;
+            const int cnt = plan.cnt[tile];
+            const int64_t col0 = (int64_t)slab * kSlabCols;
+            const uint32_t colbytes = (uint32_t)min((int64_t)kSlabCols, ldS - col0) * 4u;
+            const uint32_t bar = full0 + 8 * st;
+            if (lane == 0) {
+                aio::mbar_expect_tx(bar, ent_bytes + self_bytes + (cnt > 0 ? (uint32_t)cnt * colbytes : 0u));
+                aio::bulk_g2s(ent_s, plan.ent + tile * kTileCells * k, ent_bytes, bar);
+                aio::bulk_g2s(self_s, plan.self + tile * kTileCells, self_bytes, bar);
+            }
+            __syncwarp();
+            for (int r = lane; r < cnt; r += 32) {
+                const int64_t row = plan.rows[tile * kTileCap + r];
+                aio::bulk_g2s(tile_s + (uint32_t)r * (kSlabCols * 4), S + row * ldS + col0, colbytes, bar);
+            }
+        }
+        return;
+    }
+    // --------------------------------- consumers ---------------------------------
+    const int quad = tid & 15, cl = tid >> 4;                                   // 16 column quads x 32 cell lanes
+    double a_dot[4] = {0, 0, 0, 0}, a_ss[4] = {0, 0, 0, 0}, a_tt[4] = {0, 0, 0, 0}, a_s[4] = {0, 0, 0, 0};
+    int a_nz[4] = {0, 0, 0, 0};
+    int seg = 0;
+    for (int64_t wi = w0, it = 0; wi < w1; ++wi, ++it) {
+        const int st = (int)(it & 1);
+        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        const int slab = (int)(wi / ntiles);
+        const int64_t tile = wi - (int64_t)slab * ntiles;
+        const int64_t col0 = (int64_t)slab * kSlabCols;
+        const bool col_ok = col0 + quad * 4 < ldS;
+        const bool direct = plan.cnt[tile] < 0;
+        aio::mbar_wait(full0 + 8 * st, ph);
+        const unsigned char* stage = smem + st * stage_b;
+        const float4* tile_s = reinterpret_cast<const float4*>(stage);
+        const int2* ent_s = reinterpret_cast<const int2*>(stage + (size_t)kTileCap * kSlabCols * 4);
+        const int32_t* self_s = reinterpret_cast<const int32_t*>(stage + (size_t)kTileCap * kSlabCols * 4 + ent_bytes);
+        float p_dot[4] = {0, 0, 0, 0}, p_ss[4] = {0, 0, 0, 0}, p_tt[4] = {0, 0, 0, 0}, p_s[4] = {0, 0, 0, 0};
+        if (col_ok) {
+#pragma unroll
+            for (int m = 0; m < kTileCells / 32; ++m) {
+                const int c = cl + 32 * m;
+                const int sf = self_s[c];
+                if (sf < 0) continue;
+                const int2* e = ent_s + c * k;
+                float4 s, t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (!direct) {
+                    s = tile_s[sf * (kSlabCols / 4) + quad];
+                    for (int j = 0; j < k; ++j) {
+                        const int2 ej = e[j];
+                        const float wj = __int_as_float(ej.y);
+                        const float4 v = tile_s[ej.x * (kSlabCols / 4) + quad];
+                        t.x = fmaf(wj, v.x, t.x); t.y = fmaf(wj, v.y, t.y); t.z = fmaf(wj, v.z, t.z); t.w = fmaf(wj, v.w, t.w);
+                    }
+                } else {
+                    const float4* S4 = reinterpret_cast<const float4*>(S + col0) + quad;
+                    s = ld_cached_f4(S4 + (int64_t)sf * (ldS / 4));
+                    for (int j = 0; j < k; ++j) {
+                        const int2 ej = e[j];
+                        const float wj = __int_as_float(ej.y);
+                        const float4 v = ld_cached_f4(S4 + (int64_t)ej.x * (ldS / 4));
+                        t.x = fmaf(wj, v.x, t.x); t.y = fmaf(wj, v.y, t.y); t.z = fmaf(wj, v.z, t.z); t.w = fmaf(wj, v.w, t.w);
+                    }
+                }
+                const float sv[4] = {s.x, s.y, s.z, s.w}, tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    p_dot[q] = fmaf(sv[q], tv[q], p_dot[q]);
+                    p_ss[q] = fmaf(sv[q], sv[q], p_ss[q]);
+                    p_tt[q] = fmaf(tv[q], tv[q], p_tt[q]);
+                    p_s[q] += sv[q];
+                    a_nz[q] += sv[q] != 0.f ? 1 : 0;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) aio::mbar_arrive(empty0 + 8 * st);                       // this warp is done with the stage
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            a_dot[q] += (double)p_dot[q]; a_ss[q] += (double)p_ss[q]; a_tt[q] += (double)p_tt[q]; a_s[q] += (double)p_s[q];
+        }
+        const bool last = wi + 1 == w1 || (wi + 1) / ntiles != slab;
+        if (last) {
+            // slab segment finished: reduce the 32 cell lanes of every quad in a fixed order, write one record
+            const int64_t rec = (int64_t)blockIdx.x * maxseg + seg;
+            double* out = partial + rec * 5 * kSlabCols;
+            for (int stat = 0; stat < 5; ++stat) {
+                double v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    v[q] = stat == 0 ? a_dot[q] : stat == 1 ? a_ss[q] : stat == 2 ? a_tt[q] : stat == 3 ? a_s[q] : (double)a_nz[q];
+                    v[q] += __shfl_xor_sync(0xffffffffu, v[q], 16);             // the warp's two cell lanes
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kTileConsumers) : "memory");
+                if (lane < 16) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) red[(warp * 16 + quad) * 4 + q] = v[q];
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kTileConsumers) : "memory");
+                if (tid < kSlabCols) {
+                    const int qd = tid >> 2, q = tid & 3;
+                    double t = 0.0;
+                    for (int wq = 0; wq < 16; ++wq) t += red[(wq * 16 + qd) * 4 + q];
+                    out[stat * kSlabCols + tid] = t;
+                }
+            }
+            if (tid == 0) rec_slab[rec] = slab;
+            ++seg;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { a_dot[q] = 0; a_ss[q] = 0; a_tt[q] = 0; a_s[q] = 0; a_nz[q] = 0; }
+        }
+    }
+}
+
+// records [nrec][5][kSlabCols] (+ their slab) -> out [5][P]; one CTA per slab, records summed in index order
+__global__ void __launch_bounds__(5 * kSlabCols)
+tile_records_reduce_kernel(const double* __restrict__ partial, const int32_t* __restrict__ rec_slab, int nrec, int P,
+                           double* __restrict__ out) {
+    const int slab = blockIdx.x, stat = threadIdx.x / kSlabCols, c = threadIdx.x % kSlabCols;
+    const int p = slab * kSlabCols + c;
+    double t = 0.0;
+    for (int r = 0; r < nrec; ++r)
+        if (rec_slab[r] == slab) t += partial[((int64_t)r * 5 + stat) * kSlabCols + c];
+    if (p < P) out[(int64_t)stat * P + p] = t;
+}
+
 __global__ void null_graph_kernel(int64_t n, int64_t m, const float* __restrict__ w, uint32_t repeat, uint64_t seed,
                                   FeistelKeys fk, int32_t* __restrict__ cols, float* __restrict__ wout) {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -192,5 +592,94 @@ extern "C" int laris_null_graph_philox(int64_t n, int k, const float* w, int32_t
     const FeistelKeys fk = make_feistel_keys((uint64_t)m, (uint32_t)repeat, seed);
     null_graph_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, (cudaStream_t)stream>>>(n, m, w, (uint32_t)repeat, seed, fk, cols, wout);
     LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
+// observed statistics through the staged-tile kernel -> out [5][P]
+static int observed_stats_tiled(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* idx, const float* w, int k,
+                                const int32_t* order, double* out, cudaStream_t st) {
+    const int64_t ntiles = ceil_div(n, kTileCells);
+    Scratch<int32_t> cnt(st), rows(st), self(st), rec_slab(st);
+    Scratch<int2> ent(st);
+    Scratch<double> partial(st);
+    LARIS_CUDA(cnt.alloc((size_t)ntiles));
+    LARIS_CUDA(rows.alloc((size_t)ntiles * kTileCap));
+    LARIS_CUDA(self.alloc((size_t)ntiles * kTileCells));
+    LARIS_CUDA(ent.alloc((size_t)ntiles * kTileCells * k));
+    TilePlan plan{cnt.p, rows.p, ent.p, self.p};
+    tile_plan_kernel<<<(unsigned)ntiles, 256, 0, st>>>(idx, w, k, order, n, plan);
+    LARIS_LAUNCH_CHECK();
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int nslabs = (int)ceil_div(ldS, kSlabCols);
+    const int64_t W = (int64_t)nslabs * ntiles;
+    const int grid = (int)(W < sms ? W : sms);
+    const int maxseg = (int)ceil_div(nslabs, grid) + 1;
+    const int nrec = grid * maxseg;
+    LARIS_CUDA(partial.alloc((size_t)nrec * 5 * kSlabCols));
+    LARIS_CUDA(rec_slab.alloc((size_t)nrec));
+    LARIS_CUDA(cudaMemsetAsync(rec_slab.p, 0xff, sizeof(int32_t) * (size_t)nrec, st));
+    const size_t smem = TileSmem::total(k);
+    LARIS_CUDA(cudaFuncSetAttribute(spatial_obs_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spatial_obs_tile_kernel<<<grid, kTileThreads, smem, st>>>(S, ldS, k, plan, ntiles, nslabs, maxseg, partial.p, rec_slab.p);
+    LARIS_LAUNCH_CHECK();
+    tile_records_reduce_kernel<<<nslabs, 5 * kSlabCols, 0, st>>>(partial.p, rec_slab.p, nrec, P, out);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
+template <int RB>
+static int null_stats_batch(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* nidx, const float* nw, int k,
+                            double* out, cudaStream_t st) {
+    const int64_t ld4 = ldS / 4;
+    const int slabs = (int)ceil_div(ld4, kStThreads);
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t nchunks = ceil_div((int64_t)sms * 8, slabs);
+    if (nchunks > n) nchunks = n;
+    if (nchunks > 65535) nchunks = 65535;
+    constexpr int Q = 2 * RB + 3;
+    Scratch<double> partial(st);
+    LARIS_CUDA(partial.alloc((size_t)nchunks * Q * ld4 * 4));
+    spatial_null_stats_kernel<RB><<<dim3((unsigned)slabs, (unsigned)nchunks), kStThreads, 0, st>>>(
+        (const float4*)S, ld4, n, nidx, nw, k, (int)nchunks, partial.p);
+    LARIS_LAUNCH_CHECK();
+    null_stats_reduce_kernel<<<dim3((unsigned)ceil_div(P, 32), Q), 256, 0, st>>>(partial.p, (int)nchunks, ld4 * 4, P, RB, out);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
+extern "C" int laris_spatial_stats_batched(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* idx,
+                                           const float* w, int k, const int32_t* order, const int32_t* null_idx,
+                                           const float* null_w, int32_t n_repeats, double* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LARIS_CHECK_ARG(S && out && (idx || n_repeats > 0), "laris_spatial_stats_batched: null pointer");
+    LARIS_CHECK_ARG(n > 0 && P >= 1 && ldS >= P && ldS % 4 == 0 && ((uintptr_t)S & 15) == 0,
+                    "laris_spatial_stats_batched: S needs ldS >= P, ldS %% 4 == 0 and 16-byte alignment");
+    LARIS_CHECK_ARG(k >= 1 && k <= kStMaxK, "laris_spatial_stats_batched: k must be in [1,%d] (got %d)", kStMaxK, k);
+    LARIS_CHECK_ARG(n_repeats >= 0 && (n_repeats == 0 || (null_idx && null_w)), "laris_spatial_stats_batched: bad null graphs");
+    int row0 = 0;
+    if (idx) {
+        LARIS_CHECK_ARG(w, "laris_spatial_stats_batched: null weights");
+        int rc;
+        if (k <= kTileMaxK) rc = observed_stats_tiled(S, ldS, n, P, idx, w, k, order, out, st);
+        else rc = laris_spatial_stats(S, ldS, n, P, idx, w, k, 0, order, out, stream);
+        if (rc) return rc;
+        row0 = 1;
+    }
+    const int64_t nk = n * (int64_t)k;
+    for (int r = 0; r < n_repeats;) {
+        const int rb = n_repeats - r >= 3 ? 3 : n_repeats - r;
+        double* o = out + (int64_t)(row0 + r) * 5 * P;
+        const int32_t* ni = null_idx + (int64_t)r * nk;
+        const float* nw = null_w + (int64_t)r * nk;
+        int rc = rb == 3 ? null_stats_batch<3>(S, ldS, n, P, ni, nw, k, o, st)
+               : rb == 2 ? null_stats_batch<2>(S, ldS, n, P, ni, nw, k, o, st)
+                         : null_stats_batch<1>(S, ldS, n, P, ni, nw, k, o, st);
+        if (rc) return rc;
+        r += rb;
+    }
     return LARIS_OK;
 }

@@ -351,9 +351,26 @@ class CapturedScoring:
         return self.scores
 
 
+FP_SAMPLES = 1 << 22
+
+
+def device_fingerprint_async(data_d):
+    """Content fingerprint of a device ``.data`` array (see tools/_utils.py): returns a thunk giving (nnz, checksum)
+    once the stream work queued so far is complete."""
+    nnz = int(data_d.numel())
+    if nnz == 0:
+        return lambda: (0, 0)
+    stride = max(1, nnz // FP_SAMPLES)
+    t = data_d[::stride].contiguous().view(torch.int32).sum(dtype=torch.int64).reshape(1)
+    h = torch.empty(1, dtype=torch.int64, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    return lambda: (nnz, int(h.item()))
+
+
 def scores_to_csr_async(sm: ScoreMatrix, dtype=np.float32):
     """Start the device CSR compaction and the device->host copies of the result; returns ``finish()`` which waits
-    for the copies and assembles the scipy matrix.  Host work done between the two calls overlaps the transfer."""
+    for the copies and gives (scipy matrix, content fingerprint).  Host work done between the two calls overlaps the
+    transfer."""
     if sm.row_nnz is None:
         raise ValueError("score matrix has no row counts")
     parts = K.csr_compact(sm.S, sm.P, sm.row_nnz)
@@ -362,13 +379,14 @@ def scores_to_csr_async(sm: ScoreMatrix, dtype=np.float32):
         h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         h.copy_(t, non_blocking=True)
         host.append(h)
+    fp = device_fingerprint_async(parts[2])
     done = torch.cuda.Event()
     done.record()
 
     def finish():
         done.synchronize()
         indptr, indices, data = (h.numpy() for h in host)
-        return _assemble_csr(sm, indptr, indices, data, dtype)
+        return _assemble_csr(sm, indptr, indices, data, dtype), fp()
     return finish
 
 
@@ -412,24 +430,41 @@ def observed_stats(sm: ScoreMatrix, graph: SpatialGraph):
     return K.spatial_stats(sm.S, sm.P, graph.idx, graph.w, False, graph.order).cpu().numpy()
 
 
-def null_cosines(sm: ScoreMatrix, graph: SpatialGraph, n_repeats, random_seed, rng="numpy"):
-    """Per-repeat cosine of the random-graph null (K4b).  Returns ([R,P], rng_state)."""
+def null_graphs(graph: SpatialGraph, n_repeats, random_seed, rng="numpy"):
+    """The R random graphs of the null as device tensors: (cols [R,n,k] int32, w [R,n,k] fp32, rng_state).
+    'numpy' replays the reference's MT19937 stream on the host (laris/tools/_utils.py:436-446, :497-499) and uploads
+    the indices; 'philox' generates them on the device."""
     n, k = graph.n, graph.k
-    out, state = [], None
+    dev = graph.w.device
+    cols = torch.empty((n_repeats, n, k), dtype=torch.int32, device=dev)
+    wts = torch.empty((n_repeats, n, k), dtype=torch.float32, device=dev)
+    state = None
     if rng == "numpy":
-        seeds = _rng_compat.repeat_seeds(random_seed, n_repeats)
-        for s in seeds:
-            cols, perm, state = _rng_compat.null_graph(n, k, s)
-            cols_d = K.to_device(cols.astype(np.int32), torch.int32).view(n, k)
-            wperm = K.gather_f32(graph.w.view(-1), K.to_device(perm, torch.int64)).view(n, k)
-            out.append(_cosine(K.spatial_stats(sm.S, sm.P, cols_d, wperm, True, None).cpu().numpy()))
+        for r, s in enumerate(_rng_compat.repeat_seeds(random_seed, n_repeats)):
+            c, perm, state = _rng_compat.null_graph(n, k, s)
+            cols[r].copy_(K.to_device(c.astype(np.int32), torch.int32).view(n, k))
+            wts[r].copy_(K.gather_f32(graph.w.view(-1), K.to_device(perm, torch.int64)).view(n, k))
     elif rng == "philox":
         for r in range(n_repeats):
-            cols_d, wperm = K.null_graph_philox(n, k, graph.w, r, random_seed)
-            out.append(_cosine(K.spatial_stats(sm.S, sm.P, cols_d, wperm, True, None).cpu().numpy()))
+            K.null_graph_philox(n, k, graph.w, r, random_seed, out=(cols[r], wts[r]))
     else:
         raise ValueError(f"rng must be 'numpy' or 'philox', got {rng!r}")
-    return np.asarray(out).reshape(n_repeats, sm.P), state
+    return cols, wts, state
+
+
+def spatial_stats_all(sm: ScoreMatrix, graph: SpatialGraph, n_repeats, random_seed, rng="numpy"):
+    """Observed statistics and the R null repeats (K4a + K4b) as ONE device tensor [1+R, 5, P] fp64 - no host
+    synchronisation; row 0 is the observed graph.  Returns (stats_d, rng_state)."""
+    cols, wts, state = null_graphs(graph, n_repeats, random_seed, rng)
+    out = K.spatial_stats_batched(sm.S, sm.P, graph.idx, graph.w, graph.order, cols, wts)
+    return out, state
+
+
+def null_cosines(sm: ScoreMatrix, graph: SpatialGraph, n_repeats, random_seed, rng="numpy"):
+    """Per-repeat cosine of the random-graph null (K4b).  Returns ([R,P], rng_state)."""
+    st, state = spatial_stats_all(sm, graph, n_repeats, random_seed, rng)
+    st = st.cpu().numpy()
+    return np.asarray([_cosine(st[1 + r]) for r in range(n_repeats)]).reshape(n_repeats, sm.P), state
 
 
 # ------------------------------------------------------------ cell types ----

@@ -48,7 +48,7 @@ def _lr_gene_indices(adata, lr_df):
 
 def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_rep_spatial: str = "X_spatial", *,
                          dtype=np.float32, layout: str = "auto", radius=None, complex_sep=None,
-                         complex_rule: str = "min"):
+                         complex_rule: str = "min", csr_dev=None, to_host: bool = True):
     """Per-cell diffused ligand-receptor scores as a new AnnData (cells x LR pairs).
 
     Reference laris/tools/__init__.py:29-119: kNN graph incl. self with
@@ -66,11 +66,19 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     expressed in a cell only if every subunit is.  Without it, complexes are pre-expanded rows as in the
     reference's tutorial.  (The spatial-specificity step of ``runLARIS`` takes such rows as they are; its
     cell-type step looks ligand / receptor names up as genes, like the reference, so it needs expanded rows.)
+    ``csr_dev`` (extension): ``adata.X`` already on the device as ``(indptr int64, indices int32, data fp32)``
+    tensors (e.g. from ``laris_b200.dist.upload_csr_replicated``) - nothing is uploaded.  ``to_host=False``
+    (extension): skip the CSR compaction and download; ``.X`` of the returned (AnnDataLite) object is then a
+    ``ResidentScores`` handle that ``runLARIS`` consumes directly and ``.X.tocsr()`` materialises on demand.
     """
     xy = _utils._coords(adata, use_rep_spatial)
     # schedule: the expression matrix goes up on the copy stream while the host resolves the LR table and the graph is
     # built; the result comes down while the host prepares obs / var / obsm of the new AnnData
-    csr_dev, join_upload = engine.upload_csr_async(adata.X)
+    if csr_dev is None:
+        csr_dev, join_upload = engine.upload_csr_async(adata.X)
+    else:
+        K.require_cuda()
+        join_upload = lambda: csr_dev                                      # noqa: E731
     complexes = None
     if complex_sep:
         lig_g, rec_g, complexes = _lr_units(adata, lr_df, complex_sep)
@@ -80,16 +88,23 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
         graph = engine.build_graph(xy, number_nearest_neighbors, True, None)
     else:
         graph = engine.build_radius_graph(xy, radius, True, None)
-    xu, lig_c, rec_c = engine.select_lr_genes(adata.X, lig_g, rec_g, csr_dev=join_upload(), layout=layout,
+    csr_dev = join_upload()
+    xu, lig_c, rec_c = engine.select_lr_genes(adata.X, lig_g, rec_g, csr_dev=csr_dev, layout=layout,
                                               complexes=complexes, rule=complex_rule)
     sm = engine.lr_scores(xu, graph, lig_c, rec_c)
-    finish = engine.scores_to_csr_async(sm, dtype)
+    expr_fp = engine.device_fingerprint_async(csr_dev[2])
+    finish = engine.scores_to_csr_async(sm, dtype) if to_host else None
     lr_names = (lr_df["ligand"].astype(str) + "::" + lr_df["receptor"].astype(str)).to_numpy(dtype=object)
     obs, var = adata.obs.copy(), pd.DataFrame(index=pd.Index(lr_names, dtype=object))
     obsm = {k: np.array(v, copy=True) for k, v in adata.obsm.items()}
-    lr_adata = make_anndata(finish(), obs=obs, var=var, obsm=obsm)
-    _utils._remember_scores(lr_adata.X, sm)
-    _utils._remember_expression(adata.X, xu)
+    if to_host:
+        X, score_fp = finish()
+        lr_adata = make_anndata(X, obs=obs, var=var, obsm=obsm)
+        _utils._remember_scores(lr_adata.X, sm, score_fp)
+    else:
+        from .._anndata import AnnDataLite
+        lr_adata = AnnDataLite(_utils.ResidentScores(sm), obs, var, obsm)
+    _utils._remember_expression(adata.X, xu, expr_fp())
     return lr_adata
 
 
@@ -102,7 +117,7 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
              layer_celltype=None, n_neighbors_permutation: int = 30, n_permutations: int = 1000, chunk_size: int = 50000,
              prefilter_fdr: bool = True, prefilter_threshold: float = 0.0, score_threshold: float = 1e-6,
              spatial_weight: float = 1.0, use_conditional_pvalue: bool = False, *, rng: str = "numpy",
-             verbose: bool = True, contract_impl=None, radius=None):
+             verbose: bool = True, contract_impl=None, radius=None, output: str = "frames"):
     """Spatially-specific LR pairs and (optionally) the cell-type interaction table.
 
     Reference laris/tools/__init__.py:121-593, same arguments and returns
@@ -115,7 +130,9 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     (step 1 with ``exp(-d/sigma)`` weights, the neighbourhood profile with ``exp(-d/(mean(d)/2))``) are radius
     graphs without self edges instead of kNN graphs; the random-graph null then re-deals the rows' padded
     fixed-degree weight slots (zero padding included), which keeps the reference's construction for a graph whose
-    degree varies.
+    degree varies.  ``output='arrays'`` (extension): skip the materialisation of the results - the per-cell QC
+    columns, ``uns['cosg_lr']`` and the sorted long DataFrame - and return the cell-type step as a dict of device
+    tensors ([pair, sender*C + receiver] layout); the ranking DataFrame and the ``var`` columns are still written.
     """
     if by_celltype and adata is None:
         raise ValueError("Parameter 'adata' must be provided when by_celltype=True. "
@@ -123,6 +140,8 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     if use_rep not in lr_adata.obsm:
         raise KeyError(f"Representation '{use_rep}' not found in lr_adata.obsm. "
                        f"Available keys: {list(lr_adata.obsm.keys())}")
+    if output not in ("frames", "arrays"):
+        raise ValueError(f"output must be 'frames' or 'arrays', got {output!r}")
     _log(verbose, "\n" + "=" * 70 + "\nLARIS ANALYSIS\n" + "=" * 70)
     _log(verbose, f"\nInput data: {lr_adata.shape[0]} cells x {lr_adata.shape[1]} LR pairs")
 
@@ -131,17 +150,27 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     # multi-GPU: this rank holds a block of LR pairs (laris_b200.dist.prepare_sharded); per-pair results are
     # all-gathered in global pair order, so everything from the ranking on is identical on every rank
     shard = _dist.shard_of(lr_adata)
-    gather = (lambda x, axis=-1: x) if shard is None else (lambda x, axis=-1: _dist.all_gather_pairs(x, shard, axis))
     own = slice(None) if shard is None else slice(shard.start, shard.stop)
     sm = _utils._scores_of(lr_adata)
     if radius is None:
         graph = engine.build_graph(_utils._coords(lr_adata, use_rep), n_nearest_neighbors, False, sigma)
     else:
         graph = engine.build_radius_graph(_utils._coords(lr_adata, use_rep), radius, False, sigma)
-    st = engine.observed_stats(sm, graph)
-    sm.cache.update(ss=st[1], sum=st[3], nnz=st[4])
-    rand_each, rng_state = engine.null_cosines(sm, graph, n_repeats, random_seed, rng)
-    st, rand_each = gather(st), gather(rand_each)
+    # observed statistics + all null repeats: one device tensor [1+R, 5, P_local], one gather, one download
+    st_d, rng_state = engine.spatial_stats_all(sm, graph, n_repeats, random_seed, rng)
+    sm.cache["stats_d"] = st_d[0]
+    st_local = None
+    if shard is not None:
+        st_local = st_d[0].cpu().numpy()
+        st_d = _dist.all_gather_pairs_dev(st_d, shard, axis=-1)
+    st_all = st_d.cpu().numpy()
+    st = st_all[0]
+    if st_local is None:
+        st_local = st
+    else:
+        sm.cache.update(sum_global=st[3], ss_global=st[1])
+    sm.cache.update(ss=st_local[1], sum=st_local[3], nnz=st_local[4])
+    rand_each = np.asarray([engine._cosine(st_all[1 + r]) for r in range(n_repeats)]).reshape(n_repeats, st.shape[1])
     gsp = engine._cosine(st)
     random_gsp = np.mean(rand_each, axis=0)
     gsp_score = gsp - mu * random_gsp
@@ -156,7 +185,8 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     lr_adata.var["total_counts"] = st[3][own]
     lr_adata.var["log1p_mean_counts"] = np.log1p(st[3][own] / n)
     lr_adata.var["log1p_total_counts"] = np.log1p(st[3][own])
-    _utils._write_obs_qc(lr_adata, sm, shard)
+    if output == "frames":
+        _utils._write_obs_qc(lr_adata, sm, shard)
 
     # ---- ranking (reference :499-526) ----
     if shard is None:
@@ -194,7 +224,7 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
         n_permutations=n_permutations, chunk_size=chunk_size, prefilter_fdr=prefilter_fdr,
         prefilter_threshold=prefilter_threshold, score_threshold=score_threshold, spatial_weight=spatial_weight,
         use_conditional_pvalue=use_conditional_pvalue, rng=rng, random_seed=random_seed, rng_state=rng_state,
-        verbose=verbose, contract_impl=contract_impl, shard=shard, radius=radius)
+        verbose=verbose, contract_impl=contract_impl, shard=shard, radius=radius, output=output)
     _log(verbose, f"\nResults: {len(laris_lr)} LR pairs, {len(celltype_results):,} cell type combinations")
     return laris_lr, celltype_results
 

@@ -19,34 +19,59 @@ from .. import _rng_compat, cosg_compat, engine
 from .. import dist as _dist
 
 # ---------------------------------------------------------------------------
-# device-resident score cache: prepareLRInteraction leaves S on the GPU so that
-# runLARIS does not re-upload lr_adata.X
+# device-resident caches: prepareLRInteraction leaves S (and the packed LR-gene rows of X) on the GPU so that
+# runLARIS neither re-uploads lr_adata.X nor re-selects adata.X.  A hit needs the SAME matrix
+# object with the SAME contents: entries are keyed by id() (weakly referenced) and validated against a content
+# fingerprint - nnz plus an exact integer checksum of the float32 bit patterns of a strided sample of ``.data``
+# (every element for matrices below 2^22 stored entries) - so in-place edits such as ``X.data *= c`` or a scanpy
+# ``log1p`` / ``scale`` between the two calls invalidate the entry instead of being silently ignored.
 # ---------------------------------------------------------------------------
 _SCORE_CACHE: dict = {}
-
-
-def _remember_scores(X, sm):
-    key = id(X)
-    _SCORE_CACHE[key] = (weakref.ref(X, lambda _r, key=key: _SCORE_CACHE.pop(key, None)), sm)
-
-
-# the packed LR-gene expression prepareLRInteraction built stays on the device the same way (weakly keyed on the
-# expression matrix object): runLARIS's gene-specificity step then needs neither a second upload of X nor a second
-# selection pass.  Like the score cache it assumes the matrix object is not modified in place between the two calls.
 _EXPR_CACHE: dict = {}
+_FP_SAMPLES = 1 << 22
 
 
-def _remember_expression(X, xu):
+def _fp_stride(nnz):
+    return max(1, int(nnz) // _FP_SAMPLES)
+
+
+def _fingerprint_host(X):
+    """(nnz, checksum) of a scipy sparse matrix; the checksum is the wrapped int64 sum of the int32 views of
+    float32(data[::stride]) - exactly reproducible on the device."""
+    data = np.asarray(X.data)
+    nnz = int(data.shape[0])
+    sample = np.ascontiguousarray(data[:: _fp_stride(nnz)], dtype=np.float32)
+    return nnz, int(sample.view(np.int32).sum(dtype=np.int64))
+
+
+def _fingerprint_device(data_d):
+    """Same fingerprint from the device copy of ``.data`` (fp32 tensor)."""
+    nnz = int(data_d.numel())
+    if nnz == 0:
+        return 0, 0
+    return nnz, int(data_d[:: _fp_stride(nnz)].contiguous().view(torch.int32).sum(dtype=torch.int64).item())
+
+
+def _remember_scores(X, sm, fingerprint):
+    key = id(X)
+    _SCORE_CACHE[key] = (weakref.ref(X, lambda _r, key=key: _SCORE_CACHE.pop(key, None)), sm, fingerprint)
+
+
+def _remember_expression(X, xu, fingerprint):
     if xu.packed is None:                  # dense-panel layout: the COSG contraction reads packed rows
         return
     key = id(X)
-    _EXPR_CACHE[key] = (weakref.ref(X, lambda _r, key=key: _EXPR_CACHE.pop(key, None)), xu, X.shape, int(X.nnz))
+    _EXPR_CACHE[key] = (weakref.ref(X, lambda _r, key=key: _EXPR_CACHE.pop(key, None)), xu, X.shape, fingerprint)
 
 
 def _expression_of(X, gene_idx):
-    """(ExpressionU, packed column of every gene in ``gene_idx``) if X's LR-gene rows are resident and cover the genes."""
+    """(ExpressionU, packed column of every gene in ``gene_idx``) if X's LR-gene rows are resident, still describe
+    the matrix (fingerprint) and cover the genes."""
     hit = _EXPR_CACHE.get(id(X))
-    if hit is None or hit[0]() is not X or hit[2] != X.shape or hit[3] != int(X.nnz):
+    if hit is None or hit[0]() is not X or hit[2] != X.shape:
+        return None
+    if hit[3] is not None and _fingerprint_host(X) != hit[3]:
+        _EXPR_CACHE.pop(id(X), None)                       # edited in place since prepareLRInteraction
         return None
     xu = hit[1]
     pos = np.searchsorted(xu.genes, gene_idx)
@@ -56,16 +81,33 @@ def _expression_of(X, gene_idx):
     return xu, (pos if xu.columns is None else np.asarray(xu.columns)[pos])
 
 
+class ResidentScores:
+    """``lr_adata.X`` of ``prepareLRInteraction(..., to_host=False)``: the score matrix stays on the device
+    (``.sm``); ``tocsr()`` brings it to the host on demand."""
+    _laris_resident = True
+
+    def __init__(self, sm):
+        self.sm = sm
+        self.shape = (sm.n, sm.P)
+
+    def tocsr(self):
+        return engine.scores_to_csr(self.sm)
+
+
 def _scores_of(lr_adata) -> engine.ScoreMatrix:
     X = lr_adata.X
+    if isinstance(X, ResidentScores):
+        return X.sm
     hit = _SCORE_CACHE.get(id(X))
     if hit is not None and hit[0]() is X and hit[1].S.shape[0] == X.shape[0] and hit[1].P == X.shape[1]:
-        return hit[1]
+        if hit[2] is None or _fingerprint_host(X) == hit[2]:
+            return hit[1]
+        _SCORE_CACHE.pop(id(X), None)                      # edited in place: score the current values
     if not sp.issparse(X):
         X = sp.csr_matrix(np.asarray(X))
     sm = engine.scores_from_csr(X)
     if sp.issparse(lr_adata.X):
-        _remember_scores(lr_adata.X, sm)
+        _remember_scores(lr_adata.X, sm, _fingerprint_host(lr_adata.X))
     return sm
 
 
@@ -156,12 +198,12 @@ def _coords(adata, use_rep):
     return np.ascontiguousarray(np.asarray(adata.obsm[use_rep]), dtype=np.float64)
 
 
-def _build_adjacency_matrix(adata, use_rep: str = "X_spatial", n_nearest_neighbors: int = 10, sigma: float = 100.0):
+def _build_adjacency_matrix(adata, use_rep: str = "X_pca", n_nearest_neighbors: int = 10, sigma: float = 100.0):
     """kNN (self excluded) with w = exp(-d/sigma) as an n x n CSR (reference :343-394)."""
     return engine.build_graph(_coords(adata, use_rep), n_nearest_neighbors, False, sigma).to_scipy()
 
 
-def _build_random_adjacency_matrix(adata, cellxcell, n_nearest_neighbors: int = 10, random_seed: int = 27):
+def _build_random_adjacency_matrix(adata, cellxcell, n_nearest_neighbors: int = 10, random_seed: int = 0):
     """Random columns + shuffled real weights (reference :397-446); pure index
     generation on the reference's numpy stream (also reseeds ``np.random`` like it)."""
     n, k = adata.n_obs, n_nearest_neighbors
@@ -181,7 +223,7 @@ def _graph_from_scipy(cellxcell, k):
 
 
 def _generate_random_background(adata, cellxcell, genexcell, n_nearest_neighbors: int = 10, n_repeats: int = 30,
-                                random_seed: int = 27, rng: str = "numpy"):
+                                random_seed: int = 0, *, rng: str = "numpy"):
     """List of per-repeat cosine vectors of the random-graph null (reference :449-518)."""
     sm = engine.scores_from_csr(sp.csr_matrix(genexcell).T.tocsr())
     graph = _graph_from_scipy(cellxcell, n_nearest_neighbors)
@@ -195,10 +237,16 @@ def _generate_random_background(adata, cellxcell, genexcell, n_nearest_neighbors
 # cell-type machinery
 # ---------------------------------------------------------------------------
 def _group_codes(obs_col):
-    """(codes int32, category names) with the reference's ordering rule (:816-836)."""
+    """(codes int32, category names) with the reference's ordering rule (:816-836).  A missing label (NaN
+    category, code -1) has no one-hot row in the reference either; here it is rejected up front because the
+    device kernels index by code."""
     if hasattr(obs_col, "cat"):
         cats = list(obs_col.cat.categories)
-        return obs_col.cat.codes.to_numpy().astype(np.int32), cats
+        codes = obs_col.cat.codes.to_numpy().astype(np.int32)
+        if (codes < 0).any():
+            raise ValueError(f"{int((codes < 0).sum())} cells have no cell-type label (NaN category); "
+                             "drop or label them before calling runLARIS")
+        return codes, cats
     uniq = obs_col.unique()
     try:
         [float(x) for x in uniq]
@@ -241,8 +289,20 @@ def _gene_columns(adata, names):
     return idx.astype(np.int64)
 
 
-def _calculate_ligand_receptor_specificity(adata, laris_lr, groupby, mu: float = 100, expressed_pct: float = 0.1,
-                                           remove_lowly_expressed: bool = True, mask_threshold: float = 1e-6):
+def _cosg_table(names, score, cats):
+    """``cosg.indexByGene`` + ``cosg.iqrLogNormalize`` of a freshly computed COSG score matrix [names x groups]
+    (reference :590-596): ranked frame -> pivot -> per-column normalisation, columns in category order."""
+    frame, order = cosg_compat.ranked_frame(names, score, cats, "@@")
+    table = cosg_compat.index_by_gene_of_ranking(frame, names, score, [str(c) for c in cats], order, set_nan_to_zero=True,
+                                                 convert_negative_one_to_zero=True)
+    table = table.loc[:, [str(c) for c in cats]]
+    table.columns = cats
+    return cosg_compat.iqr_log_normalize(table)
+
+
+def _calculate_ligand_receptor_specificity(adata, laris_lr, groupby: str = "CellTypes", mu: float = 100,
+                                           expressed_pct: float = 0.1, remove_lowly_expressed: bool = True,
+                                           mask_threshold: float = 1e-6):
     """Gene x cell-type specificity of every ligand/receptor in ``laris_lr``.
 
     Reference :521-620 (``cosg.cosg`` -> ``indexByGene`` -> ``iqrLogNormalize``).  The
@@ -261,25 +321,42 @@ def _calculate_ligand_receptor_specificity(adata, laris_lr, groupby, mu: float =
         xu = engine.select_genes(adata.X, gene_idx)
         score = engine.cosg_gene_scores(xu, K.to_device(codes, torch.int32), len(cats), n_c, mu, expressed_pct,
                                         remove_lowly_expressed)
-    frame, order = cosg_compat.ranked_frame(lr_set, score, cats, "@@")
-    table = cosg_compat.index_by_gene_of_ranking(frame, lr_set, score, [str(c) for c in cats], order, set_nan_to_zero=True,
-                                                 convert_negative_one_to_zero=True)
-    table = table.loc[:, [str(c) for c in cats]]
-    table.columns = cats
-    return cosg_compat.iqr_log_normalize(table)
+    return _cosg_table(lr_set, score, cats)
 
 
-def _calculate_specificity_in_spatial_neighborhood(adata, lr_adata, groupby: str, use_rep_spatial: str = "X_spatial",
-                                                   number_nearest_neighbors: int = 10, mu: float = 100,
-                                                   expressed_pct: float = 0.1, remove_lowly_expressed: bool = True,
-                                                   return_by_group: bool = True, key_added=None,
-                                                   column_delimiter: str = "@@", contract_impl=None, shard=None,
-                                                   radius=None):
-    """Specificity of every LR pair for every sender::receiver neighbourhood profile.
+def _calculate_diffused_lr_specificity(lr_adata, groupby: str = "CellTypes", mu: float = 100, expressed_pct: float = 0.05,
+                                       remove_lowly_expressed: bool = True, mask_threshold: float = 1e-6):
+    """Cell-type specificity of the diffused LR scores themselves: COSG over the columns of ``lr_adata.X``
+    (reference :623-723; no caller inside the reference, kept for API parity).  The score matrix is compacted and
+    packed on the device and goes through the same one-hot contraction as the gene table."""
+    if groupby not in lr_adata.obs:
+        raise ValueError(f"'{groupby}' not found in lr_adata.obs")
+    codes, cats = _group_codes(lr_adata.obs[groupby])
+    n_c = np.bincount(codes, minlength=len(cats))
+    sm = _scores_of(lr_adata)
+    row_nnz = sm.row_nnz if sm.row_nnz is not None else K.row_qc(sm.S, sm.P, ())[1]
+    indptr, indices, data = K.csr_compact(sm.S, sm.P, row_nnz)
+    ident = torch.arange(sm.P, dtype=torch.int32, device=sm.S.device)
+    out_indptr, packed = K.csr_select(indptr, indices, data, ident)
+    xu = engine.ExpressionU(out_indptr, packed, np.arange(sm.P), sm.n)
+    score = engine.cosg_gene_scores(xu, K.to_device(codes, torch.int32), len(cats), n_c, mu, expressed_pct,
+                                    remove_lowly_expressed)
+    return _cosg_table(np.asarray(lr_adata.var_names, dtype=object), score, cats)
 
-    Reference :726-977.  Stores ``lr_adata.uns[key_added]`` with the reference's
-    layout (params / COSG frame / names+scores recarrays) and returns the
-    normalised P x C^2 DataFrame."""
+
+def _observed_ss_device(sm, graph):
+    """Device [P] fp64 column sums of squares of S (row 1 of the observed statistics), cached on the score matrix."""
+    st_d = sm.cache.get("stats_d")
+    if st_d is None:
+        st_d = K.spatial_stats(sm.S, sm.P, graph.idx, graph.w, False, graph.order)
+        sm.cache["stats_d"] = st_d
+    return st_d[1].contiguous()
+
+
+def _neighborhood_tables(adata, lr_adata, groupby, use_rep_spatial, number_nearest_neighbors, mu, contract_impl, shard,
+                         radius):
+    """Device tables of the co-localisation step: (raw [P, C^2] fp64 regularised cosines, global pair order;
+    LR names; sender::receiver names).  Reference :838-880."""
     if groupby not in adata.obs:
         raise ValueError(f"'{groupby}' not found in adata.obs")
     if use_rep_spatial not in adata.obsm:
@@ -291,41 +368,100 @@ def _calculate_specificity_in_spatial_neighborhood(adata, lr_adata, groupby: str
         graph = engine.build_graph(_coords(adata, use_rep_spatial), number_nearest_neighbors, False, None)
     else:
         graph = engine.build_radius_graph(_coords(adata, use_rep_spatial), radius, False, None)
-    ss = sm.cache.get("ss")
-    if ss is None:
-        ss = engine.observed_stats(sm, graph)[1]
-        sm.cache["ss"] = ss
+    labels_d = K.to_device(codes, torch.int32)
+    N = K.neighborhood_composition(labels_d, graph.idx, graph.w, C)
+    num, qn2 = K.celltype_pair_contract(sm.S, sm.P, N, contract_impl, order=graph.order)
+    _, raw = K.pair_cosine_regularise(num, _observed_ss_device(sm, graph), qn2, mu)
     if shard is None:
-        raw, _ = engine.neighborhood_specificity(sm, K.to_device(codes, torch.int32), C, graph, mu, ss, contract_impl)
         lr_names = np.asarray(lr_adata.var_names, dtype=object)
-    else:                       # cosines of this rank's pairs, gathered; the regularisation runs over a pair's C^2 row
-        _, cos = engine.neighborhood_specificity(sm, K.to_device(codes, torch.int32), C, graph, mu, ss, contract_impl)
-        raw = engine.cosg_regularise(_dist.all_gather_pairs(cos, shard, axis=0), mu)
+    else:        # the regularisation runs over a pair's own C^2 row, so rows are final before the gather
+        raw = _dist.all_gather_pairs_dev(raw, shard, axis=0)
         lr_names = np.asarray(shard.names_global, dtype=object)
     pair_names = [f"{a}::{b}" for a in cats for b in cats]
-    if key_added is None:
-        key_added = "cosg"
+    return raw, lr_names, pair_names
+
+
+def _normalise_table_device(raw_d):
+    """``cosg.iqrLogNormalize`` of a device table: the real function (through the host) when ``cosg`` is importable,
+    else the device stand-in T2 (parity unpinned, see laris_b200.cosg_compat)."""
+    cosg = cosg_compat.real_cosg()
+    if cosg is None:
+        return K.column_iqr_log(raw_d)
+    host = cosg.iqrLogNormalize(pd.DataFrame(raw_d.cpu().numpy()))
+    return K.to_device(np.ascontiguousarray(host.to_numpy(dtype=np.float64)), torch.float64)
+
+
+def _store_neighborhood_uns(lr_adata, key_added, groupby, mu, raw, lr_names, pair_names, return_by_group,
+                            column_delimiter):
+    """``lr_adata.uns[key_added]`` in the reference's layout (params / COSG frame / names + scores recarrays,
+    reference :886-968): every column ranked by descending score."""
     frame, order = cosg_compat.ranked_frame(lr_names, raw, pair_names, column_delimiter)
     lr_adata.uns[key_added] = {"params": dict(groupby=groupby, method="COSG", mu=mu)}
     if return_by_group:
         lr_adata.uns[key_added]["COSG"] = frame
-    names_rec = np.rec.fromarrays([lr_names[order[:, j]] for j in range(C * C)],
-                                  dtype=[(nm, "O") for nm in pair_names])
-    scores_rec = np.rec.fromarrays([raw[order[:, j], j].astype(np.float32) for j in range(C * C)],
-                                   dtype=[(nm, "float32") for nm in pair_names])
-    lr_adata.uns[key_added]["names"] = names_rec
-    lr_adata.uns[key_added]["scores"] = scores_rec
-    table = cosg_compat.index_by_gene_of_ranking(frame, lr_names, raw, pair_names, order, column_delimiter=column_delimiter)
-    return cosg_compat.iqr_log_normalize(table)
+    L = len(pair_names)
+    lr_adata.uns[key_added]["names"] = np.rec.fromarrays([lr_names[order[:, j]] for j in range(L)],
+                                                         dtype=[(nm, "O") for nm in pair_names])
+    lr_adata.uns[key_added]["scores"] = np.rec.fromarrays([raw[order[:, j], j].astype(np.float32) for j in range(L)],
+                                                          dtype=[(nm, "float32") for nm in pair_names])
+    return frame, order
 
 
-def _prepare_background_interactions(lr_adata, n_nearest_neighbors: int = 30, leaf_size: int = 40, shard=None):
+def _calculate_specificity_in_spatial_neighborhood(adata, lr_adata, groupby: str = "CellTypes",
+                                                   use_rep_spatial: str = "X_spatial", number_nearest_neighbors: int = 10,
+                                                   mu: float = 100, return_by_group: bool = True, key_added: str = "cosg",
+                                                   column_delimiter: str = "@@", *, contract_impl=None, shard=None,
+                                                   radius=None):
+    """Specificity of every LR pair for every sender::receiver neighbourhood profile.
+
+    Reference :726-977.  Stores ``lr_adata.uns[key_added]`` with the reference's
+    layout (params / COSG frame / names+scores recarrays) and returns the
+    normalised P x C^2 DataFrame."""
+    raw_d, lr_names, pair_names = _neighborhood_tables(adata, lr_adata, groupby, use_rep_spatial, number_nearest_neighbors,
+                                                       mu, contract_impl, shard, radius)
+    if key_added is None:
+        key_added = "cosg"
+    raw = raw_d.cpu().numpy()
+    frame, order = _store_neighborhood_uns(lr_adata, key_added, groupby, mu, raw, lr_names, pair_names, return_by_group,
+                                           column_delimiter)
+    if cosg_compat.real_cosg() is not None:
+        table = cosg_compat.index_by_gene_of_ranking(frame, lr_names, raw, pair_names, order,
+                                                     column_delimiter=column_delimiter)
+        return cosg_compat.iqr_log_normalize(table)
+    rows = order[:, 0] if len(pair_names) else np.arange(len(lr_names))     # indexByGene: first-appearance order
+    norm = _normalise_table_device(raw_d).cpu().numpy()
+    return pd.DataFrame(norm[rows], index=pd.Index(lr_names[rows], dtype=object), columns=list(pair_names))
+
+
+def _mean_variance_neighbors(feats, n_nearest_neighbors, leaf_size):
+    """Indices of the ``n_nearest_neighbors`` nearest points of every (mean, variance) point, own row dropped as
+    column 0 like the reference (:1094-1098).  The search runs on the device (K1: sklearn's KD-tree distances bit for
+    bit, ties by index) when the points are distinct; with duplicated points the KD-tree's tie order depends on its
+    traversal, so those tables (and tiny ones, where sklearn itself switches to brute force) go through the host
+    KD-tree exactly as the reference does."""
+    from sklearn.neighbors import KDTree
+    kq = n_nearest_neighbors + 1
+    distinct = len(np.unique(feats, axis=0)) == len(feats)
+    if distinct and 2 * kq < len(feats) and kq <= 64:
+        return K.knn_graph(K.to_device(feats, torch.float64), kq, True, want_order=False)[0].cpu().numpy().astype(np.int64)
+    _, idx = KDTree(feats, leaf_size=leaf_size, metric="euclidean").query(feats, k=min(kq, len(feats)))
+    return idx
+
+
+def _prepare_background_genes(adata, layer: str = None, n_nearest_neighbors: int = 30, leaf_size: int = 30):
+    """Nearest genes in (mean, variance) space (reference :979-1010; no caller inside the reference)."""
+    M = adata.layers[layer] if layer is not None and layer in adata.layers else adata.X
+    M = sp.csr_matrix(M)
+    mean = np.asarray(M.mean(axis=0)).ravel()
+    var = np.asarray(M.power(2).mean(axis=0)).ravel() - mean ** 2
+    idx = _mean_variance_neighbors(np.column_stack([mean, var]), n_nearest_neighbors, leaf_size)
+    return pd.DataFrame(idx[:, 1:], index=adata.var_names)
+
+
+def _prepare_background_interactions(lr_adata, n_nearest_neighbors: int = 30, leaf_size: int = 30, *, shard=None):
     """30-NN of every LR pair in (mean, variance) space (reference :1013-1109).
 
-    The column moments come from the device pass over S; the neighbour search
-    over the P feature points is sklearn's KD-tree, exactly as in the reference
-    (P is a few thousand: host-sized)."""
-    from sklearn.neighbors import KDTree
+    The column moments come from the device pass over S; see ``_mean_variance_neighbors`` for the search."""
     sm = _scores_of(lr_adata)
     if "sum" not in sm.cache:
         graph = engine.SpatialGraph(torch.zeros((sm.n, 1), dtype=torch.int32, device=sm.S.device), None,
@@ -335,41 +471,83 @@ def _prepare_background_interactions(lr_adata, n_nearest_neighbors: int = 30, le
     n = sm.n
     csum, css, names = sm.cache["sum"], sm.cache["ss"], lr_adata.var_names
     if shard is not None:
-        csum, css = _dist.all_gather_pairs(csum, shard), _dist.all_gather_pairs(css, shard)
+        if "sum_global" in sm.cache:
+            csum, css = sm.cache["sum_global"], sm.cache["ss_global"]
+        else:
+            csum, css = _dist.all_gather_pairs(csum, shard), _dist.all_gather_pairs(css, shard)
         names = pd.Index(shard.names_global, dtype=object)
     mean = csum / n
     var = css / n - mean ** 2
-    feats = np.column_stack([mean, var])
-    kq = n_nearest_neighbors + 1
-    if 2 * kq < len(feats) and kq <= 64:
-        # same exact search as the spatial graphs (K1: sklearn KD-tree distances bit for bit, ties by index),
-        # self included and dropped as column 0 like the reference (:1098)
-        idx = K.knn_graph(K.to_device(feats, torch.float64), kq, True, want_order=False)[0].cpu().numpy().astype(np.int64)
-    else:      # tiny tables (k >= P/2: sklearn switches to brute force) or more than 63 neighbours: host KD-tree
-        _, idx = KDTree(feats, leaf_size=leaf_size, metric="euclidean").query(feats, k=min(kq, len(feats)))
+    idx = _mean_variance_neighbors(np.column_stack([mean, var]), n_nearest_neighbors, leaf_size)
     return pd.DataFrame(idx[:, 1:], index=names, columns=range(idx.shape[1] - 1))
 
 
-def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_rep_spatial: str = "X_spatial",
-                                       number_nearest_neighbors: int = 10, mu: float = 100, expressed_pct: float = 0.1,
-                                       remove_lowly_expressed: bool = True, mask_threshold: float = 1e-6,
-                                       calculate_pvalues: bool = True, layer=None, n_nearest_neighbors: int = 30,
-                                       n_permutations: int = 1000, chunk_size: int = 50000, prefilter_fdr: bool = True,
-                                       prefilter_threshold: float = 0.0, score_threshold: float = 1e-6,
-                                       spatial_weight: float = 1.0, use_conditional_pvalue: bool = False, *,
-                                       rng: str = "numpy", random_seed: int = 27, rng_state=None, verbose: bool = True,
-                                       contract_impl=None, shard=None, radius=None):
+_NUMPY_DRAW_BYTES = 256 << 20          # host / device bytes of reference-stream draws alive at a time
+
+
+def _numpy_mode_counts(table_d, bg_d, active_d, order_rows, group_of, pair_of, cats, C, P, n_permutations, nb, rs,
+                       chunk_size, only_ge, t0, t1):
+    """Exceedance counts with the reference's own random stream (``rng='numpy'``): ``randint(0, nb, (rows, N))`` per
+    sender-receiver group in sorted NAME order, rows in final table order, chunked by ``chunk_size`` exactly as
+    reference :1518-1570 consumes the stream.  Draws are generated, uploaded and consumed a batch of groups at a
+    time, so the peak is O(batch) instead of C^2 * P * N bytes."""
+    dev = table_d.device
+    L = C * C
+    ge = torch.zeros((L, P), dtype=torch.int32, device=dev)
+    nz = None if only_ge else torch.zeros((L, P), dtype=torch.int32, device=dev)
+    both = None if only_ge else torch.zeros((L, P), dtype=torch.int32, device=dev)
+    g_sorted = group_of[order_rows]
+    p_sorted = pair_of[order_rows]
+    by_group = np.argsort(g_sorted, kind="stable")                    # rows of a group, still in table order
+    starts = np.searchsorted(g_sorted[by_group], np.arange(L + 1))
+    gkeys = sorted((str(cats[g // C]), str(cats[g % C]), g) for g in np.unique(g_sorted))
+    per_group = P * n_permutations
+    batch = max(1, _NUMPY_DRAW_BYTES // max(per_group, 1))
+    for b0 in range(0, len(gkeys), batch):
+        part = gkeys[b0:b0 + batch]
+        draws = np.zeros((len(part), P, n_permutations), dtype=np.uint8)
+        for slot, (_, _, g) in enumerate(part):
+            rows = by_group[starts[g]:starts[g + 1]]
+            for s in range(0, len(rows), chunk_size):
+                rr = rows[s:s + chunk_size]
+                draws[slot, p_sorted[rr], :] = _rng_compat.pvalue_draws(rs, len(rr), n_permutations, nb)
+        d_dev = K.to_device(np.ascontiguousarray(draws[:, :, t0:t1]), torch.uint8)
+        for slot, (_, _, g) in enumerate(part):
+            K.pvalue_counts(table_d[g:g + 1], bg_d, t1 - t0, active=active_d, draws=d_dev[slot],
+                            out=(ge[g:g + 1], None if nz is None else nz[g:g + 1],
+                                 None if both is None else both[g:g + 1]), only_ge=only_ge)
+    return ge, nz, both
+
+
+def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str = "CellTypes",
+                                       use_rep_spatial: str = "X_spatial", number_nearest_neighbors: int = 10,
+                                       mu: float = 100, expressed_pct: float = 0.1, remove_lowly_expressed: bool = True,
+                                       mask_threshold: float = 1e-6, calculate_pvalues: bool = True, layer=None,
+                                       n_nearest_neighbors: int = 30, n_permutations: int = 1000, chunk_size: int = 50000,
+                                       prefilter_fdr: bool = True, prefilter_threshold: float = 0.0,
+                                       score_threshold: float = 1e-6, spatial_weight: float = 1.0,
+                                       use_conditional_pvalue: bool = False, *, rng: str = "numpy", random_seed: int = 27,
+                                       rng_state=None, verbose: bool = True, contract_impl=None, shard=None, radius=None,
+                                       output: str = "frames"):
     """Sender/receiver cell-type table with permutation p-values and BH-FDR.
 
     Reference laris/tools/_utils.py:1113-1688; same arguments (``mask_threshold`` and
     ``layer`` are accepted and ignored there too), plus keyword-only
     ``rng`` ('numpy' replays the reference's MT19937 stream from ``rng_state``,
-    'philox' uses the device generator keyed by ``random_seed``)."""
+    'philox' uses the device generator keyed by ``random_seed``).  Every P x C^2-sized table lives on the
+    device from the contraction to the FDR (include/laris_b200.h, T1..T5); ``output='arrays'`` returns them as a
+    dict of device tensors in [pair, sender*C + receiver] layout instead of assembling the sorted DataFrame."""
+    if rng not in ("numpy", "philox"):
+        raise ValueError(f"rng must be 'numpy' or 'philox', got {rng!r}")
+    if output not in ("frames", "arrays"):
+        raise ValueError(f"output must be 'frames' or 'arrays', got {output!r}")
     cols6 = ["sender", "receiver", "ligand", "receptor", "interaction_name", "interaction_score"]
     codes, cats = _group_codes(adata.obs[groupby])
     if not hasattr(adata.obs[groupby], "cat"):
         raise AttributeError(f"adata.obs['{groupby}'] must be categorical (reference _compute_avg_expression)")
+    cosg_compat.warn_if_stand_in()
     C = len(cats)
+    L = C * C
     cats_arr = np.asarray(cats, dtype=object)
     n_c = np.bincount(codes, minlength=C)
     labels_d = K.to_device(codes, torch.int32)
@@ -384,15 +562,14 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_r
                                                   mask_threshold)
     spec = spec.loc[:, cats] if list(spec.columns) != list(cats) else spec
 
-    # ---- step 2: fraction of cells with a non-zero score (reference :1325-1337) ----
+    # ---- step 2: cells with a non-zero score per type (reference :1325-1337), counts stay on the device ----
     _log(verbose, "\n--- Step 2: Calculating diffused LR-score distribution ---")
     sm = _scores_of(lr_adata)
-    with np.errstate(invalid="ignore", divide="ignore"):
-        frac_all = engine.celltype_fraction(sm, labels_d, C, n_c.astype(np.float64))          # [P, C]
+    cnt_d = K.celltype_nonzero_count(sm.S, sm.P, labels_d, C)                                   # [C, P_local] int64
     if shard is not None:
-        frac_all = _dist.all_gather_pairs(frac_all, shard, axis=0)
+        cnt_d = _dist.all_gather_pairs_dev(cnt_d, shard, axis=1)
 
-    # ---- step 3: interaction scores, pair-major / receiver-major / sender fastest (:1351-1406) ----
+    # ---- step 3: interaction scores (:1351-1406), [pair, sender, receiver] on the device ----
     _log(verbose, f"\n--- Step 3: Computing interaction scores (spatial_weight={spatial_weight}) ---")
     lig = laris_lr["ligand"].to_numpy(dtype=object)
     rec = laris_lr["receptor"].to_numpy(dtype=object)
@@ -405,106 +582,108 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby, use_r
     pair_id = pd.Index(lr_names).get_indexer(inter_names)
     if (pair_id < 0).any():
         raise KeyError(f"interactions not found in lr_adata.var_names: {list(inter_names[pair_id < 0][:5])}")
-    sl = spec.loc[lig].to_numpy(dtype=np.float64)
-    sr = spec.loc[rec].to_numpy(dtype=np.float64)
+    gene_row = pd.Index(spec.index).get_indexer
+    spec_m = spec.to_numpy(dtype=np.float64)
     with np.errstate(invalid="ignore"):
         factor = np.ones_like(sp_score) if spatial_weight == 0 else np.power(sp_score, spatial_weight)
-    frac = frac_all[pair_id]
-    inter = (frac[:, :, None] * frac[:, None, :]) * (sl[:, :, None] * sr[:, None, :] * factor[:, None, None])
     npair = len(lig)
-    flat = inter.transpose(0, 2, 1).reshape(-1)
-    row_pair = np.repeat(np.arange(npair), C * C)
-    row_recv = np.tile(np.repeat(np.arange(C), C), npair)
-    row_send = np.tile(np.arange(C), npair * C)
-    o = np.argsort(-flat, kind="stable")
-    flat, row_pair, row_recv, row_send = flat[o], row_pair[o], row_recv[o], row_send[o]
+    pair_id_d = K.to_device(pair_id.astype(np.int32), torch.int32)
+    inter_d = K.interaction_scores(K.to_device(spec_m[gene_row(lig)], torch.float64),
+                                   K.to_device(spec_m[gene_row(rec)], torch.float64), K.to_device(factor, torch.float64),
+                                   cnt_d, K.to_device(n_c.astype(np.float64), torch.float64), pair_id_d, P)
 
-    # ---- step 3.5: rescale (:1426-1437) ----
-    top_mean = flat[: min(100, flat.size)].mean()
-    if top_mean > 0:
-        flat = flat * (0.1 / top_mean)
+    # ---- step 3.5: rescale by 0.1 / mean(top 100) (:1426-1437) ----
+    rescale_d = K.topk_mean(inter_d.view(-1), 100)
 
-    # ---- step 4: co-localisation weight (:1448-1472) ----
+    # ---- step 4: co-localisation weight (:1448-1472) and clean-up (:1480-1489) ----
     _log(verbose, "\n--- Step 4: Incorporating spatial cell type co-localization ---")
-    ctc = _calculate_specificity_in_spatial_neighborhood(
-        adata, lr_adata, groupby=groupby, use_rep_spatial=use_rep_spatial,
-        number_nearest_neighbors=number_nearest_neighbors, mu=mu, return_by_group=True, key_added="cosg_lr",
-        column_delimiter="@@", contract_impl=contract_impl, shard=shard, radius=radius)
-    ctc_cols = [f"{a}::{b}" for a in cats for b in cats]
-    ctc_m = ctc.loc[lr_names[pair_id], ctc_cols].to_numpy(dtype=np.float64).reshape(npair, C, C)
-    flat = flat * ctc_m[row_pair, row_send, row_recv]
-    o = np.argsort(-flat, kind="stable")
-    flat, row_pair, row_recv, row_send = flat[o], row_pair[o], row_recv[o], row_send[o]
+    raw_d, ctc_names, pair_names = _neighborhood_tables(adata, lr_adata, groupby, use_rep_spatial,
+                                                        number_nearest_neighbors, mu, contract_impl, shard, radius)
+    ctc_d = _normalise_table_device(raw_d)
+    if output == "frames":
+        _store_neighborhood_uns(lr_adata, "cosg_lr", groupby, mu, raw_d.cpu().numpy(), ctc_names, pair_names, True, "@@")
+    flat_d, table_d, active_d = K.finalize_scores(inter_d, rescale_d, ctc_d, pair_id_d, P, score_threshold)
 
-    # ---- step 4.5: clean-up (:1480-1489) ----
-    flat = flat.astype(np.float64)
-    flat[flat < score_threshold] = 0.0
+    def rows_in_table_order(host_inter, host_flat):
+        """Row order of the reference's result: melt order (pair-major, receiver-major, sender fastest), stably
+        sorted by the pre-weight score and then by the final score, both descending (:1422, :1472)."""
+        melt = np.arange(npair * L).reshape(npair, C, C).transpose(0, 2, 1).reshape(-1)     # [pair, r, s] -> flat [pair, s, r]
+        o1 = melt[np.argsort(-host_inter.reshape(-1)[melt], kind="stable")]
+        return o1[np.argsort(-host_flat.reshape(-1)[o1], kind="stable")]
 
+    result = {"pair_id": pair_id, "C": C, "cats": cats_arr, "ligand": lig, "receptor": rec, "interaction_name": inter_names,
+              "interaction_score": flat_d, "ctc_raw": raw_d}
+    p_rows = fdr_rows = nlog_rows = None
+    order_rows = None
+    if calculate_pvalues:
+        # ---- step 5.1: background sets (:1507) ----
+        _log(verbose, "\n--- Step 5.1: Preparing background interaction sets ---")
+        bg = _prepare_background_interactions(lr_adata, n_nearest_neighbors=n_nearest_neighbors, shard=shard).to_numpy()
+        nb = bg.shape[1]
+        bg_d = K.to_device(np.ascontiguousarray(bg, dtype=np.int32), torch.int32)
+
+        # ---- step 5.2: permutation p-values (:1518-1596) ----
+        _log(verbose, f"\n--- Step 5.2: Calculating p-values ({n_permutations:,} permutations, rng={rng}) ---")
+        only_ge = not use_conditional_pvalue
+        if shard is None:
+            t0, t1 = 0, int(n_permutations)
+        else:                       # permutations [t0, t1) on this rank; exceedance counts are integers, so the sum is exact
+            pb = _dist.perm_bounds(n_permutations, shard.world)
+            t0, t1 = int(pb[shard.rank]), int(pb[shard.rank + 1])
+        if rng == "numpy":
+            if nb > 256:
+                raise ValueError(f"rng='numpy' stores draws as uint8: n_neighbors_permutation must be <= 256 (got {nb})")
+            rs = rng_state if rng_state is not None else np.random.RandomState(random_seed)
+            order_rows = rows_in_table_order(inter_d.cpu().numpy(), flat_d.cpu().numpy())
+            group_of = np.tile(np.arange(L), npair)
+            pair_of = np.repeat(pair_id, L)
+            ge, nz, both = _numpy_mode_counts(table_d, bg_d, active_d, order_rows, group_of, pair_of, cats, C, P,
+                                              int(n_permutations), nb, rs, chunk_size, only_ge, t0, t1)
+            _rng_compat.sync_global(rs)
+        elif t1 > t0:
+            ge, nz, both = K.pvalue_counts(table_d, bg_d, t1 - t0, active=active_d, seed=random_seed, t0=t0,
+                                           only_ge=only_ge)
+        else:
+            ge = torch.zeros((L, P), dtype=torch.int32, device=table_d.device)
+            nz = both = None if only_ge else torch.zeros_like(ge)
+        if shard is not None:
+            for t in (ge, nz, both):
+                if t is not None:
+                    _dist.all_reduce_sum_dev(t)
+        p_tab, p_round, sel = K.pvalues_from_counts(table_d, active_d, ge, nz, both, n_permutations,
+                                                    use_conditional_pvalue, prefilter_fdr, prefilter_threshold)
+
+        # ---- step 5.3: BH-FDR per group (:1617-1658) ----
+        _log(verbose, "\n--- Step 5.3: Applying FDR correction (Benjamini-Hochberg) ---")
+        fdr_tab = K.bh_fdr(p_round, sel)
+        p_rows, fdr_rows, nlog_rows = K.gather_result_rows(p_tab, fdr_tab, pair_id_d)
+        result.update(p_value=p_rows, p_value_fdr=fdr_rows, nlog10_p_value_fdr=nlog_rows)
+    elif rng == "numpy" and rng_state is not None:
+        _rng_compat.sync_global(rng_state)
+    if output == "arrays":
+        return result
+
+    # ---- the reference's long table, rows by descending score ----
+    flat = flat_d.cpu().numpy()
+    if order_rows is None:
+        order_rows = rows_in_table_order(inter_d.cpu().numpy(), flat)
+    row_pair, rem = np.divmod(order_rows, L)
+    row_send, row_recv = np.divmod(rem, C)
     cat_taker = cosg_compat.StringTaker(cats_arr)
     res = pd.DataFrame({
-        "sender": cat_taker.take(row_send), "receiver": cat_taker.take(row_recv), "interaction_score": flat,
+        "sender": cat_taker.take(row_send), "receiver": cat_taker.take(row_recv),
+        "interaction_score": flat.reshape(-1)[order_rows],
         "ligand": _take_strings(lig, row_pair), "receptor": _take_strings(rec, row_pair),
         "interaction_name": _take_strings(inter_names, row_pair)})
-
     if not calculate_pvalues:
         res["p_value"] = np.nan
         res["p_value_fdr"] = np.nan
         res["nlog10_p_value_fdr"] = np.nan
         return res
-
-    # ---- step 5.1: background sets (:1507) ----
-    _log(verbose, "\n--- Step 5.1: Preparing background interaction sets ---")
-    bg = _prepare_background_interactions(lr_adata, n_nearest_neighbors=n_nearest_neighbors, shard=shard).to_numpy()
-    nb = bg.shape[1]
-
-    # ---- step 5.2: permutation p-values (:1518-1596) ----
-    _log(verbose, f"\n--- Step 5.2: Calculating p-values ({n_permutations:,} permutations, rng={rng}) ---")
-    group_of = row_send * C + row_recv
-    table = np.zeros((C * C, P))
-    active = np.zeros(P, dtype=np.uint8)
-    table[group_of, pair_id[row_pair]] = flat
-    active[pair_id] = 1
-    draws = None
-    if rng == "numpy":
-        rs = rng_state if rng_state is not None else np.random.RandomState(random_seed)
-        draws = np.zeros((C * C, P, n_permutations), dtype=np.uint8)
-        # groups in sorted (sender, receiver) NAME order, rows in table order, chunked like the reference
-        gkeys = sorted({(str(cats[g // C]), str(cats[g % C]), g) for g in np.unique(group_of)})
-        for _, _, g in gkeys:
-            rows = np.flatnonzero(group_of == g)
-            for s in range(0, len(rows), chunk_size):
-                rr = rows[s:s + chunk_size]
-                draws[g, pair_id[row_pair[rr]], :] = _rng_compat.pvalue_draws(rs, len(rr), n_permutations, nb)
-        _rng_compat.sync_global(rs)
-    elif rng != "philox":
-        raise ValueError(f"rng must be 'numpy' or 'philox', got {rng!r}")
-    if shard is None:
-        ge, nz, both = engine.pvalue_counts(table, bg, active, n_permutations, rng=rng, seed=random_seed, draws=draws,
-                                            only_ge=not use_conditional_pvalue)
-    else:                       # permutations [t0, t1) on this rank; exceedance counts are integers, so the sum is exact
-        pb = _dist.perm_bounds(n_permutations, shard.world)
-        t0, t1 = int(pb[shard.rank]), int(pb[shard.rank + 1])
-        part = engine.pvalue_counts(table, bg, active, t1 - t0, rng=rng, seed=random_seed, t0=t0,
-                                    draws=None if draws is None else np.ascontiguousarray(draws[:, :, t0:t1]),
-                                    only_ge=not use_conditional_pvalue)
-        ge, nz, both = _dist.all_reduce_sum(np.stack(part).astype(np.int64))
-    if use_conditional_pvalue:
-        p_tab = np.ones_like(table)
-        pos = table > 0
-        p_tab[pos] = (both[pos] + 1) / (nz[pos] + 1)
-    else:
-        p_tab = (ge + 1) / (n_permutations + 1)
-    res["p_value"] = p_tab[group_of, pair_id[row_pair]]
-
-    # ---- step 5.3: BH-FDR per group (:1617-1658) ----
-    _log(verbose, "\n--- Step 5.3: Applying FDR correction (Benjamini-Hochberg) ---")
-    sel = np.broadcast_to(active[None, :].astype(bool), table.shape).copy()
-    if prefilter_fdr:
-        sel &= table > prefilter_threshold
-    fdr_tab = engine.bh_fdr(np.round(p_tab, 6), sel.astype(np.uint8))
-    fdr = np.nan_to_num(np.minimum(fdr_tab[group_of, pair_id[row_pair]], 1.0), nan=1.0)
-    res["p_value_fdr"] = fdr
-    res["nlog10_p_value_fdr"] = np.maximum(-np.log10(fdr + 1e-10), 0.0)
+    host = K.to_host(p_rows, fdr_rows, nlog_rows)
+    res["p_value"] = host[0].reshape(-1)[order_rows]
+    res["p_value_fdr"] = host[1].reshape(-1)[order_rows]
+    res["nlog10_p_value_fdr"] = host[2].reshape(-1)[order_rows]
     return res
 
 

@@ -24,8 +24,8 @@ import numpy as np
 import pandas as pd
 import scipy.sparse as sp
 
-from laris_b200 import cosg_compat
 from laris_b200.synth import make_dataset
+from oracle import cosg_standin
 from oracle import restate as R
 from oracle import rng as orng
 from oracle.ref_loader import load_reference_tools
@@ -38,7 +38,7 @@ PARAMS = dict(k_prepare=8, k_step1=8, k_ct=8, sigma=100.0, R=3, seed=27, mu=1.0,
 
 
 def normalise(M):
-    return cosg_compat.iqr_log_normalize(pd.DataFrame(M)).to_numpy()
+    return cosg_standin.iqr_log_normalize(np.asarray(M))
 
 
 def main():
@@ -86,7 +86,7 @@ def main():
             n_nearest_neighbors=p["nb"], n_permutations=p["N"], chunk_size=50000, prefilter_fdr=True,
             prefilter_threshold=0.0, score_threshold=1e-6, spatial_weight=1.0, use_conditional_pvalue=False)
     res["p_value_fdr"] = res["p_value_fdr"].fillna(1.0)       # intended effect of the no-op at _utils.py:1654
-    ctc_raw_ref = cosg_compat.index_by_gene(ref.uns["cosg_lr"]["COSG"]).loc[ref.var_names].to_numpy()
+    ctc_raw_ref = cosg_standin.index_by_gene(ref.uns["cosg_lr"]["COSG"]).loc[ref.var_names].to_numpy()
     bg_ref = U._prepare_background_interactions(ref, n_nearest_neighbors=p["nb"]).to_numpy()
 
     # ---- restatement on the same inputs --------------------------------

@@ -67,12 +67,12 @@ def _cosg_stub():
     """Stand-in for the absent ``cosg`` package so that the reference's
     ``_calculate_laris_score_by_celltype`` can run end to end.  ``cosg.cosg`` is
     the CPU restatement (oracle.restate.cosg_scores, parity unpinned);
-    ``indexByGene`` / ``iqrLogNormalize`` are the same placeholders the product
-    falls back to (laris_b200.cosg_compat), so everything AROUND them - table
-    assembly, rescaling, the permutation null, BH-FDR - is pinned by the
-    unmodified reference code."""
-    from laris_b200 import cosg_compat
-    from . import restate
+    ``indexByGene`` / ``iqrLogNormalize`` are the oracle's own stand-ins
+    (oracle.cosg_standin, written independently of the product's
+    laris_b200.cosg_compat), so everything AROUND them - table assembly,
+    rescaling, the permutation null, BH-FDR - is pinned by the unmodified
+    reference code, and the product's stand-ins are checked against them."""
+    from . import cosg_standin, restate
 
     def cosg(adata, key_added="cosg", mu=1, expressed_pct=0.1, remove_lowly_expressed=False,
              n_genes_user=50, groupby="CellTypes", **_):
@@ -80,14 +80,14 @@ def _cosg_stub():
         cats = list(lab.cat.categories)
         score = restate.cosg_scores(adata.X, lab.cat.codes.to_numpy(), len(cats), mu,
                                     expressed_pct, remove_lowly_expressed)
-        frame, _ = cosg_compat.ranked_frame(adata.var_names.to_numpy(), score, cats, "@@")
+        frame = cosg_standin.ranked_frame(adata.var_names.to_numpy(), score, cats, "@@")
         adata.uns[key_added] = {"COSG": frame.iloc[:n_genes_user]}
 
     m = types.ModuleType("cosg")
     m.__laris_stub__ = True
     m.cosg = cosg
-    m.indexByGene = lambda df, **kw: cosg_compat.index_by_gene(df, **kw)
-    m.iqrLogNormalize = lambda df, **kw: cosg_compat.iqr_log_normalize(df, **kw)
+    m.indexByGene = lambda df, **kw: cosg_standin.index_by_gene(df, **kw)
+    m.iqrLogNormalize = lambda df, **kw: cosg_standin.iqr_log_normalize(df, **kw)
     return m
 
 

@@ -207,3 +207,58 @@ def test_pivot_of_a_ranking_equals_index_by_gene():
         b = cosg_compat.index_by_gene_of_ranking(frame, names, scores, groups, order, **kw)
         assert list(a.index) == list(b.index) and list(a.columns) == list(b.columns)
         assert np.array_equal(a.to_numpy(), b.to_numpy())
+
+
+def test_signatures_match_the_reference():
+    """Drop-in boundary: every function the reference defines in its hot-path modules exists here with the same
+    positional parameters (names, order, defaults); anything extra is keyword-only.  The list was generated from the
+    unmodified reference by oracle/make_signatures.py."""
+    import ast
+    import json
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_signatures.json")))
+    for rel, spec in ref.items():
+        tree = ast.parse(open(os.path.join(ROOT, "laris_b200", rel)).read())
+        ours = {n.name: n for n in tree.body if isinstance(n, ast.FunctionDef)}
+        for name, sig in spec["functions"].items():
+            assert name in ours, f"{rel}: reference function {name} is missing"
+            a = ours[name].args
+            pos = [x.arg for x in a.posonlyargs + a.args]
+            defaults = [ast.unparse(d) for d in a.defaults]
+            dmap = dict(zip(pos[len(pos) - len(defaults):], defaults))
+            got = [[p, dmap.get(p)] for p in pos]
+            want = [[p, d] for p, d in sig["positional"]]
+            norm = lambda s: None if s is None else s.replace('"', "'")        # noqa: E731
+            assert [[p, norm(d)] for p, d in got] == [[p, norm(d)] for p, d in want], f"{rel}:{name} signature drifted"
+    import laris_b200 as la
+    for name in ref["tools/__init__.py"]["__all__"]:
+        assert hasattr(la.tl, name)
+    for name in ref["tools/_utils.py"]["__all__"]:
+        assert hasattr(la.tl._utils, name)
+    for name in ref["preprocessing/__init__.py"]["__all__"]:
+        assert hasattr(la.pp, name)
+
+
+def test_product_stand_ins_equal_the_oracle_stand_ins():
+    """laris_b200.cosg_compat (product) and oracle.cosg_standin (test infrastructure) are written independently;
+    on random tables with ties, zeros, -1 marks and empty columns they must agree."""
+    from laris_b200 import cosg_compat
+    from oracle import cosg_standin
+    rng = np.random.default_rng(11)
+    names = np.array([f"n{i}" for i in range(57)], dtype=object)
+    scores = rng.random((57, 6)) ** 3
+    scores[rng.random((57, 6)) < 0.3] = 0.0
+    scores[rng.random((57, 6)) < 0.1] = -1.0
+    scores[:, 4] = 0.0                                  # a column without positive entries
+    scores[:5, 5] = scores[5, 5]                        # ties
+    groups = [f"g{j}" for j in range(6)]
+    f1, _ = cosg_compat.ranked_frame(names, scores, groups, "@@")
+    f2 = cosg_standin.ranked_frame(names, scores, groups, "@@")
+    assert list(f1.columns) == list(f2.columns)
+    for c in f1.columns:
+        assert list(f1[c]) == list(f2[c]), c
+    t1 = cosg_compat.index_by_gene(f1, set_nan_to_zero=True)
+    t2 = cosg_standin.index_by_gene(f2, set_nan_to_zero=True)
+    assert list(t1.index) == list(t2.index) and np.array_equal(t1.to_numpy(), t2.to_numpy())
+    n1 = cosg_compat.iqr_log_normalize(t1).to_numpy()
+    n2 = cosg_standin.iqr_log_normalize(t2).to_numpy()
+    assert np.allclose(n1, n2, rtol=1e-14, atol=0) and n1.max() == 1.0 and n1.min() == 0.0 and (n1[:, 4] == 0).all()
