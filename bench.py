@@ -1,22 +1,30 @@
 #!/usr/bin/env python
-"""bench.py - headline benchmark of the LR scoring path (BASELINE.json metric).
+"""bench.py - headline benchmark of the LR scoring path (BASELINE.json metric) on the north-star configuration.
 
-One "step" = one pass of the hot path over one batch of synthetic input:
-kNN graph (incl. self) + decay weights + gene selection + fused diffusion/LR
-score, producing the n x P score matrix (metric M1
-"cell x LR-pair scores/s").  ``value`` times it with the inputs already in HBM, as
-a CUDA-graph replay of the whole step (``engine.CapturedScoring``; the eager
-schedule is timed beside it and reported as ``config.ms_per_step_eager``);
-``e2e`` times ``laris_b200.tl.prepareLRInteraction`` (host AnnData in, host
-AnnData with scipy CSR out: H2D, kernels, CSR compaction, D2H).  The
-permutation metrics (random-graph null repeats/s, p-value permutations/s) and
-the remaining stages are reported under ``extra``.
+Workload: BASELINE.json configs[2] (Xenium-like: 1e6 cells x 5000 genes, 2000 LR pairs, 40 cell types, 1000
+permutations) - the largest configuration that fits one GPU.  One "step" = one pass of the WHOLE hot path over it:
+
+    kNN graph + decay weights + gene selection + fused diffusion / LR score   (prepareLRInteraction)
+    + observed spatial statistic + R random-graph repeats + ranking           (runLARIS step 1)
+    + COSG gene table, fraction table, cell-type-pair contraction, score table,
+      1000-permutation p-values, BH-FDR                                       (runLARIS step 2)
+
+``value`` = n * P / t (cell x LR-pair scores per second of the whole path) with the inputs resident in HBM and the
+results left on the device: ``prepareLRInteraction(csr_dev=..., to_host=False)`` followed by
+``runLARIS(rng='philox', output='arrays')`` - the product's own code path, minus the host-side materialisation.
+``e2e`` = the same path through the public API with host buffers: host AnnData in, host AnnData (scipy CSR) and the two
+DataFrames out, every host<->device copy inside the timed region.
+
+N > 1 (torchrun, one rank per GPU): STRONG scaling of the same workload.  LR pairs are sharded over the ranks
+(``laris_b200.dist``), the graph is replicated, and the timed region contains the NCCL collectives of the path: the
+all-gathers of the per-pair statistics [1+R,5,P], of the K5b counts [C,P] and of the P x C^2 co-localisation table, and
+the all-reduce of the permutation-sharded exceedance counts.  Time is the max over ranks.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C]
 
-N > 1 is launched by torchrun (one rank per GPU); LR pairs shard across ranks
-with no data-path collective (weak scaling: every rank scores its own P pairs
-over the same cells), timing is the max over ranks.
+``--impl reference`` times the reference's CPU path (the oracle port, oracle/restate.py - the reference is pure Python
+over scipy / sklearn, so there is nothing to compile) on a bounded sample of the same workload, each stage scaled
+linearly to the full size; the same estimate is reported as ``cpu_baseline`` by the GPU arm at N=1.
 """
 from __future__ import annotations
 
@@ -35,71 +43,126 @@ sys.path.insert(0, ROOT)
 
 METRIC = "cell_x_lrpair_scores_per_sec"
 UNIT = "scores/s"
+CPU_SAMPLE_CELLS = 20000        # cells of the bounded CPU sample
+CPU_SAMPLE_GROUPS = 8           # sender-receiver groups of the bounded p-value sample
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--config", type=int, default=3)
     ap.add_argument("--n", type=int, default=None, help="override the number of cells (debug)")
     ap.add_argument("--no-extra", action="store_true")
-    ap.add_argument("--eager", action="store_true", help="time the eager schedule instead of the CUDA-graph replay")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
-def workload_name(c):
-    return (f"config{c.cfg_id}:{c.name} n={c.n} G={c.G} G_u<={c.G_u} P={c.P} k={c.k} C={c.C} R={c.R} N={c.N}")
+def workload_name(c, cfg_id):
+    return (f"config{cfg_id}:{c.name} n={c.n} G={c.G} G_u<={c.G_u} P={c.P} k={c.k} C={c.C} R={c.R} N={c.N} "
+            f"whole path (graph + scores + {c.R} null repeats + cell-type table + {c.N} permutations + FDR)")
 
 
-def make_inputs(cfg, n, rank=0):
+def run_kwargs(c):
+    return dict(n_nearest_neighbors=c.k, n_repeats=c.R, n_top_lr=c.P, number_nearest_neighbors=c.k,
+                n_permutations=c.N, calculate_pvalues=c.N > 0, verbose=False)
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's path on a bounded sample, scaled to the full workload
+# ---------------------------------------------------------------------------
+def cpu_whole_path(cfg_id, c_full):
+    """Stage times of the reference's CPU path (oracle/restate.py: the same sklearn / scipy / numpy routines the
+    reference dispatches to, single thread like the reference) on a sample of CPU_SAMPLE_CELLS cells of the same
+    configuration, and the whole-path time scaled to the full workload: per-cell stages scale with n, the
+    permutation null with the number of sender-receiver groups (its cost does not depend on n).  The p-value stage
+    times the oracle's VECTORISED restatement (~1e8 draws/s); the reference's own Python loop
+    (laris/tools/_utils.py:1560-1565) runs ~40x slower, so this baseline is conservative."""
+    import scipy.sparse as sp
     from laris_b200.synth import make_dataset
-    a, lr, c = make_dataset(cfg, n=n)
-    if rank:      # weak scaling: rank r scores its own P pairs over the same cells
-        from laris_b200.synth import make_lr_table
-        lr = make_lr_table(c, np.random.default_rng(5000 + 97 * rank + cfg))
-    object.__setattr__(c, "cfg_id", cfg)
-    return a, lr, c
-
-
-# ---------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference's prepareLRInteraction
-# ---------------------------------------------------------------------------
-def cpu_prepare(a, lr, k):
-    """Reference laris/tools/__init__.py:80-117 as restated in oracle/restate.py
-    (same sklearn / scipy routines the reference dispatches to; single thread,
-    like the reference: scipy.sparse is serial and sklearn runs n_jobs=None)."""
+    from oracle import cosg_standin
     from oracle import restate as R
+    ns = min(c_full.n, CPU_SAMPLE_CELLS)
+    a, lr, c = make_dataset(cfg_id, n=ns)
+    xy, k, C, P = a.obsm["X_spatial"], c.k, c.C, c.P
+    labels = a.obs["CellTypes"].cat.codes.to_numpy()
+    t = {}
     t0 = time.perf_counter()
-    li = R.gene_index(a.var_names, lr["ligand"])
-    ri = R.gene_index(a.var_names, lr["receptor"])
-    ind, dist = R.knn_graph(a.obsm["X_spatial"], k, True)
+    li, ri = R.gene_index(a.var_names, lr["ligand"]), R.gene_index(a.var_names, lr["receptor"])
+    ind, dist = R.knn_graph(xy, k, True)
     S = R.lr_scores(a.X, ind, R.decay_weights(dist), li, ri)
-    return time.perf_counter() - t0, S
+    t["prepare"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ind2, d2 = R.knn_graph(xy, k, False)
+    w2 = R.decay_weights(d2, 100.0)
+    gsp = R.observed_cosine(S, ind2, w2)
+    t["observed"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    cols, wperm = next(iter(R.null_graphs(ns, k, w2, 1, 27, "numpy")))
+    rand = R.null_cosine(S, k, cols, wperm)
+    t["null_repeat"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    Sz = sp.csr_matrix(S, copy=True)
+    Sz.eliminate_zeros()
+    order, ranked = R.rank_pairs(gsp - rand, np.asarray(Sz.getnnz(axis=0)).ravel(), 100, P)
+    genes = np.unique(np.concatenate([li, ri]))
+    sc = R.cosg_scores(sp.csc_matrix(a.X)[:, genes], labels, C, 100.0, 0.1, True)
+    spec = cosg_standin.iqr_log_normalize(np.where(sc == -1, 0.0, sc))
+    frac = R.celltype_fraction(S, labels, C)
+    ind3, d3 = R.knn_graph(xy, k, False)
+    N = R.neighborhood_composition(labels, ind3, R.decay_weights(d3), C)
+    ctc = cosg_standin.iqr_log_normalize(R.cosg_regularise(R.celltype_pair_cosine(S, N), 100.0))
+    pos = {g: i for i, g in enumerate(genes)}
+    inter = R.interaction_table(spec[[pos[g] for g in li[order]]], spec[[pos[g] for g in ri[order]]], ranked, frac[order], 1.0)
+    flat = inter.reshape(len(order), C * C) * R.rescale_top100(inter.reshape(-1)) * ctc[order]
+    t["celltype_table"] = time.perf_counter() - t0
+    groups = min(C * C, CPU_SAMPLE_GROUPS)
+    if c.N > 0:
+        bg, _ = R.background_interactions(S, 30)
+        table = np.zeros((groups, P))
+        table[:, order] = flat[:, :groups].T
+        rs = np.random.RandomState(27)
+        t0 = time.perf_counter()
+        ge, _, _ = R.pvalue_counts(table, np.ones(P, bool), bg, lambda g, pidx: rs.randint(0, 30, (len(pidx), c.N)))
+        R.fdr_by_group(R.pvalues_from_counts(table, ge, None, None, c.N, False), table, True, 0.0)
+        t["pvalues_sample"] = time.perf_counter() - t0
+    scale_n = c_full.n / ns
+    total = (t["prepare"] + t["observed"] + c_full.R * t["null_repeat"] + t["celltype_table"]) * scale_n
+    if c.N > 0:
+        total += t["pvalues_sample"] * (C * C / groups)
+    sample = (f"{ns} of {c_full.n} cells (same genes, LR table, k, cell types), per-cell stages scaled by {scale_n:.1f}; "
+              f"p-value null: {groups} of {C * C} groups x {P} pairs x {c.N} permutations with the oracle's vectorised "
+              f"restatement, scaled by {C * C / groups:.0f} (the reference's own per-draw Python loop is ~40x slower); "
+              f"oracle port of the reference path, 1 thread like the reference (host has {os.cpu_count()} cores)")
+    return total, t, sample
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    a, lr, c = make_inputs(args.config, args.n)
-    for _ in range(min(args.warmup, 1)):
-        cpu_prepare(a, lr, c.k)
-    times = [cpu_prepare(a, lr, c.k)[0] for _ in range(args.steps)]
-    t = float(np.mean(times))
+    from laris_b200.synth import scaled
+    c = scaled(args.config, args.n)
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        cpu_whole_path(args.config, c)
+    tot, stages, sample = [], None, ""
+    for _ in range(args.steps):
+        t, stages, sample = cpu_whole_path(args.config, c)
+        tot.append(t)
+    t = float(np.mean(tot))
     val = c.n * c.P / t
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(c), "step": "prepareLRInteraction (graph + diffusion + LR scores)"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"full workload, {args.steps} runs (reference path is single-threaded: "
-                                   f"scipy.sparse serial, sklearn n_jobs=None; host has {os.cpu_count()} cores)"},
+        "config": {"workload": workload_name(c, args.config)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "extra": {"sample_stage_seconds": stages, "ms_per_step_is": "whole-path CPU time scaled to the full workload"},
     }
     print(json.dumps(line), flush=True)
 
@@ -148,6 +211,51 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def pin_cpus(local, world):
+    """A disjoint slice of the host cores per local rank: eight ranks otherwise share one affinity mask and their
+    pandas / numpy work migrates over each other."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(world, 1))
+        mine = cores[local * per:(local + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return len(mine)
+    except Exception:
+        return None
+
+
+def kernel_rooflines(stage_ms, calls, c, P_local, nnz_u, k, hbm_peak, bf16_peak, step_ms, world):
+    """Per-kernel roofline records from the stage timer: ALGORITHMIC bytes (SURVEY 8d with the sparse
+    layout's own bytes) divided by the stage's average device time inside the timed steps."""
+    n, C, R = c.n, c.C, c.R
+    recs = []
+
+    def add(stage, bytes_per_call, note, bound="hbm", flops=None):
+        if stage not in stage_ms or calls[stage] == 0:
+            return
+        ms = stage_ms[stage] / calls[stage]
+        rec = {"kernel": stage, "bound": bound, "ms_per_launch": ms, "launches_per_step": calls[stage] / max(1, calls["_steps"]),
+               "share_of_step": stage_ms[stage] / max(1, calls["_steps"]) / step_ms, "note": note}
+        if bound == "hbm":
+            rec.update(algorithmic_bytes=int(bytes_per_call), achieved=bytes_per_call / (ms * 1e-3) / 1e9, peak=hbm_peak,
+                       unit="GB/s")
+        else:
+            rec.update(algorithmic_flops=flops, achieved=flops / (ms * 1e-3) / 1e12, peak=bf16_peak, unit="TFLOP/s")
+        rec["frac"] = rec["achieved"] / rec["peak"]
+        recs.append(rec)
+
+    add("K2+K3 diffuse_score (sparse)", 8 * nnz_u + 8 * n * k + 8 * (n + 1) + 4 * n * P_local,
+        "8 nnz(Xu) + 8nk + 8(n+1) + 4nP: packed LR-gene rows read once, graph, dense fp32 S written once")
+    add("K2+K3 diffuse_score (dense)", 4 * n * c.G_u + 8 * n * k + 4 * n * P_local, "4nG_u + 8nk + 4nP (SURVEY 8d)")
+    add("K4a observed_stats", 4 * n * P_local + 8 * n * k, "4nP + 8nk: S read once, neighbour rows from shared memory")
+    add("K4b null_stats", 4 * (1 + R * k) * n * P_local + 8 * n * k * R,
+        f"(1 + R k) 4nP + 8nkR per batch of R={R} repeats: every random neighbour row is a fresh HBM read")
+    add("K5b nonzero_count", 4 * n * P_local, "4nP: S read once")
+    add("K5 pair_contract", None, "2 n P C^2 algorithmic flop (tensor cores, fp32 accumulate)", bound="tensor",
+        flops=2.0 * n * P_local * C * C)
+    return recs
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -157,291 +265,212 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cores = pin_cpus(local, world) if world > 1 else None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
             os.environ.pop("NCCL_DEBUG")             # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
 
     import laris_b200 as la
-    from laris_b200 import _kernels as K, engine
+    from laris_b200 import _kernels as K, dist as ld, engine
     from laris_b200._lib import lib
+    from laris_b200.synth import make_dataset
 
-    a, lr, c = make_inputs(args.config, args.n, rank)
+    a, lr, c = make_dataset(args.config, n=args.n)
     n, P, k = c.n, c.P, c.k
+    kw = run_kwargs(c)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    bf16_peak = peaks.get("bf16_tflops_sustained", 1400.0)
 
-    # ---- inputs resident in HBM ----
-    xy_d = K.to_device(a.obsm["X_spatial"], torch.float64)
-    csr_d = engine.upload_csr(a.X)
-    lig_g, rec_g = la.tl._lr_gene_indices(a, lr)
+    names = (lr["ligand"].astype(str) + "::" + lr["receptor"].astype(str)).to_numpy(dtype=object)
+    shard = ld.Shard(rank, world, P, names) if world > 1 else None
+    lr_local = lr if shard is None else lr.iloc[shard.start:shard.stop].reset_index(drop=True)
+    P_local = len(lr_local)
+
+    # ---- inputs resident in HBM: coordinates, the expression matrix (replicated), labels come with adata.obs ----
+    csr_d = ld.upload_csr_replicated(a.X) if world > 1 else engine.upload_csr(a.X)
+    from laris_b200._anndata import AnnDataLite
+    a_dev = AnnDataLite(a.X, a.obs, a.var, {"X_spatial": K.to_device(a.obsm["X_spatial"], torch.float64)})
     flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # > 126 MB L2
-
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    state = {}
-
-    # the LR table's plan (distinct genes, bank-conflict-free columns, packed pair indices) depends on
-    # the table only; prepareLRInteraction caches it per table, the step reuses it the same way
-    plan = engine.plan_lr_table(lig_g, rec_g, a.X.shape[1])
-    layout = engine.choose_layout(a.X)
-
-    def step(timed):
-        e0, e1, e2 = ev(), ev(), ev()
-        e0.record()
-        graph = engine.build_graph(xy_d, k, True, None)
-        xu = engine.select_planned(plan, csr_d, n, layout)
-        e1.record()
-        sm = engine.lr_scores(xu, graph, plan.lig_d, plan.rec_d)
-        e2.record()
-        state.update(graph=graph, xu=xu, sm=sm)
-        return e0, e1, e2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # The timed step is the CUDA-graph replay of the whole step (engine.CapturedScoring: the same ~20 kernels, no host
-    # launches inside the timed region); the eager schedule is timed beside it.  The dominant kernel is timed through a
-    # second, small graph holding only the fused score stage (pair-table pack + K2+K3).
-    schedule = "cuda-graph replay (engine.CapturedScoring)"
-    captured = kern_graph = None
-    if not args.eager:
-        try:
-            captured = engine.CapturedScoring(xy_d, csr_d, plan, k, layout)
-            kern_graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(kern_graph):
-                engine.lr_scores(captured.xu, captured.graph, plan.lig_d, plan.rec_d)
-        except Exception as exc:                    # noqa: BLE001 - fall back to the eager schedule, say why
-            captured = kern_graph = None
-            schedule = f"eager (graph capture failed: {type(exc).__name__}: {str(exc)[:120]})"
-            torch.cuda.synchronize()
-    else:
-        schedule = "eager (--eager)"
+    state = {}
 
-    def timed_region(run_step):
-        out_step, out_kern = [], []
-        for _ in range(args.steps):
-            flush.fill_(1.0)                       # L2 flush between timed iterations (outside the event bracket)
-            torch.cuda.synchronize()
-            out = run_step()
-            torch.cuda.synchronize()
-            out_step.append(out[0].elapsed_time(out[-1]))
-            if len(out) == 3:
-                out_kern.append(out[1].elapsed_time(out[2]))
-        return out_step, out_kern
-
-    def replay_step():
-        e0, e1 = ev(), ev()
-        e0.record()
-        captured.replay()
-        e1.record()
-        return e0, e1
+    def device_step():
+        lr_ad = la.tl.prepareLRInteraction(a_dev, lr_local, number_nearest_neighbors=k, csr_dev=csr_d, to_host=False)
+        if shard is not None:
+            lr_ad.uns[ld.SHARD_KEY] = shard
+        out = la.tl.runLARIS(lr_ad, a_dev, rng="philox", output="arrays", **kw)
+        state.update(lr_ad=lr_ad, out=out)
 
     for _ in range(max(args.warmup, 3)):
-        step(False)
-        if captured is not None:
-            captured.replay()
-            kern_graph.replay()
+        device_step()
     barrier()
     launches0 = lib.laris_launch_count()
+    step_ms = []
     with ClockSampler(range(world) if rank == 0 else []) as clocks:
         barrier()
         wall0 = time.perf_counter()
-        if captured is not None:
-            step_ms, _ = timed_region(replay_step)
-            launches = captured.launches * args.steps
-        else:
-            step_ms, kern_ms = timed_region(lambda: step(True))
-            launches = lib.laris_launch_count() - launches0
-        barrier()
-        wall = time.perf_counter() - wall0
-        if captured is not None:                   # beside it: the eager schedule, and the score stage alone
-            eager_ms, _ = timed_region(lambda: step(True))
-            kern_ms = []
+        with K.timing() as timer:
             for _ in range(args.steps):
-                flush.fill_(1.0)
-                torch.cuda.synchronize()
+                flush.fill_(1.0)                       # L2 flush between timed iterations (outside the event bracket)
+                barrier()
                 e0, e1 = ev(), ev()
                 e0.record()
-                kern_graph.replay()
+                device_step()
                 e1.record()
                 torch.cuda.synchronize()
-                kern_ms.append(e0.elapsed_time(e1))
-            state.update(graph=captured.graph, xu=captured.xu, sm=captured.scores)
-        else:
-            eager_ms = step_ms
+                step_ms.append(e0.elapsed_time(e1))
+        barrier()
+        wall = time.perf_counter() - wall0
+        launches = lib.laris_launch_count() - launches0
+        stage = timer.summary()
 
-        # ---- e2e: the public API with host buffers (pinned inputs) ----
-        pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()
-        import scipy.sparse as sp
-        Xh = sp.csr_matrix((pin(a.X.data.astype(np.float32)), pin(a.X.indices.astype(np.int32)),
-                            pin(a.X.indptr.astype(np.int64))), shape=a.X.shape)
-        a_h = a.copy()
-        a_h.X = Xh
-        a_h.obsm["X_spatial"] = pin(a.obsm["X_spatial"])
-        h2d = Xh.data.nbytes + Xh.indices.nbytes + Xh.indptr.nbytes + a_h.obsm["X_spatial"].nbytes
-        out = None
-        for _ in range(max(args.warmup, 3)):        # warm-up: page-locked staging buffers of both result generations
-            out = la.tl.prepareLRInteraction(a_h, lr, number_nearest_neighbors=k)
-        barrier()
-        e2e_t = []
-        for _ in range(args.steps):
-            flush.fill_(1.0)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            out = la.tl.prepareLRInteraction(a_h, lr, number_nearest_neighbors=k)
-            torch.cuda.synchronize()
-            e2e_t.append(time.perf_counter() - t0)
-        d2h = out.X.data.nbytes + out.X.indices.nbytes + out.X.indptr.nbytes
-        barrier()
+        # ---- e2e: the public API with host buffers (pinned caller inputs) ----
+        e2e_t, h2d, d2h = [], 0, 0
+        if not args.no_e2e:
+            import scipy.sparse as sp
+            pin = lambda x: torch.from_numpy(np.ascontiguousarray(x)).pin_memory().numpy()
+            Xh = sp.csr_matrix((pin(a.X.data.astype(np.float32)), pin(a.X.indices.astype(np.int32)),
+                                pin(a.X.indptr.astype(np.int64))), shape=a.X.shape)
+            a_h = a.copy()
+            a_h.X = Xh
+            a_h.obsm["X_spatial"] = pin(a.obsm["X_spatial"])
+
+            def host_step():
+                if world > 1:
+                    lr_ad = ld.prepare_sharded(a_h, lr, number_nearest_neighbors=k)
+                else:
+                    lr_ad = la.tl.prepareLRInteraction(a_h, lr, number_nearest_neighbors=k)
+                res = la.tl.runLARIS(lr_ad, a_h, rng="philox", **kw)
+                torch.cuda.synchronize()
+                return lr_ad, res
+
+            for _ in range(2):                          # warm-up: page-locked staging buffers of both result generations
+                host_step()
+            barrier()
+            for _ in range(args.steps):
+                flush.fill_(1.0)
+                barrier()
+                t0 = time.perf_counter()
+                lr_ad, res = host_step()
+                e2e_t.append(time.perf_counter() - t0)
+            barrier()
+            X_share = (Xh.data.nbytes + Xh.indices.nbytes) // world + Xh.indptr.nbytes
+            h2d = X_share + 3 * a_h.obsm["X_spatial"].nbytes + 4 * n
+            d2h = (lr_ad.X.data.nbytes + lr_ad.X.indices.nbytes + lr_ad.X.indptr.nbytes + 6 * 8 * P * c.C * c.C
+                   + 8 * (1 + c.R) * 5 * P + 2 * 8 * n)
 
     t_step = float(np.sum(step_ms)) / 1e3
-    t_e2e = float(np.sum(e2e_t))
+    t_e2e = float(np.sum(e2e_t)) if e2e_t else 0.0
     if world > 1:
         tt = torch.tensor([t_step, t_e2e, wall], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_step, t_e2e, wall = tt.tolist()
-    value = world * n * P * args.steps / t_step
-    e2e_value = world * n * P * args.steps / t_e2e
+    value = n * P * args.steps / t_step
+    ms_step = 1e3 * t_step / args.steps
 
-    # ---- roofline of the dominant kernel (fused diffusion + LR score) ----
-    # algorithmic bytes of K2+K3 per SURVEY 8(d): dense fp32 X_u read once, graph read once, dense fp32 S written once
-    G_u = len(plan.genes)
-    alg_bytes = 4 * n * G_u + 8 * n * k + 4 * n * P
-    kname = "diffuse_dense_kernel" if layout == "dense" else "diffuse_score_kernel"
-    k_ms = float(np.mean(kern_ms))
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
-                "bytes_per_score": alg_bytes / (n * P), "kernel_ms": k_ms, "layout": layout, "traffic": None}
+    # ---- rooflines from the stage timer (device time of each C-ABI stage inside the timed steps) ----
+    stage_ms = {s: v[1] for s, v in stage.items()}
+    calls = {s: v[0] for s, v in stage.items()}
+    calls["_steps"] = args.steps
+    xu = engine_last_xu(la)
+    nnz_u = xu_nnz(xu)
+    recs = kernel_rooflines(stage_ms, calls, c, P_local, nnz_u, k, hbm_peak, bf16_peak, float(np.mean(step_ms)), world)
+    traffic = {}
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.isfile(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get(f"config{args.config}", {}).get(kname)
+            traffic = json.load(open(prof)).get(f"config{args.config}", {})
         except Exception:
             pass
-
-    extra = {}
-    if not args.no_extra and rank == 0:
-        extra = extra_metrics(torch, a, c, state, engine, K)
-        if not args.no_cpu_baseline:
-            extra.update(cpu_permutation_baselines(a, c, out.X, extra))
+    for r in recs:
+        r["traffic"] = traffic.get(r["kernel"])
+    hbm_recs = [r for r in recs if r["bound"] == "hbm"]
+    dominant = max(hbm_recs, key=lambda r: r["share_of_step"]) if hbm_recs else None
+    roofline = None
+    if dominant is not None:
+        roofline = {"bound": "hbm", "kernel": dominant["kernel"], "achieved": dominant["achieved"], "peak": hbm_peak,
+                    "unit": "GB/s", "frac": dominant["frac"], "traffic": dominant["traffic"], "peak_source": peak_src,
+                    "algorithmic_bytes": dominant["algorithmic_bytes"], "kernel_ms": dominant["ms_per_launch"],
+                    "share_of_step": dominant["share_of_step"], "note": dominant["note"],
+                    "why_this_kernel": "largest share of the timed step among the HBM-bound kernels; all kernels under extra.kernels"}
+    device_ms = sum(v for s, v in stage_ms.items()) / args.steps
+    # M1 of round 1 (graph + selection + fused score only), from the same timers: one of the path's three graph builds
+    prep_ms = ((stage_ms.get("K1 knn_graph", 0.0) + stage_ms.get("K1 decay_weights", 0.0)) / 3.0 + stage_ms.get("select genes", 0.0)
+               + stage_ms.get("K2+K3 diffuse_score (sparse)", 0.0) + stage_ms.get("K2+K3 diffuse_score (dense)", 0.0)) / args.steps
+    m1 = n * P_local / (prep_ms * 1e-3) if prep_ms > 0 else None
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
-        t_cpu, _ = cpu_prepare(a, lr, k)
-        cpu = {"value": n * P / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"full workload once ({t_cpu:.2f} s); reference path is single-threaded "
-                         f"(host has {os.cpu_count()} cores)"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t_cpu, stages_cpu, sample = cpu_whole_path(args.config, c)
+        cpu = {"value": n * P / t_cpu, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+               "sample_stage_seconds": stages_cpu, "scaled_whole_path_seconds": t_cpu}
 
     if rank == 0:
+        e2e = None
+        if e2e_t:
+            e2e = {"value": n * P * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps,
+                   "ms_each": [round(1e3 * t, 1) for t in e2e_t],
+                   "call": ("laris_b200.dist.prepare_sharded + " if world > 1 else "laris_b200.tl.prepareLRInteraction + ")
+                           + "laris_b200.tl.runLARIS(rng='philox'): host AnnData in, host AnnData (scipy CSR) + two DataFrames out",
+                   "state": "caller's input arrays are page-locked; the LR-table plan and the pinned result buffers are warm "
+                            "(2 untimed calls); bytes are per rank"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_step / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(c), "step": "kNN graph + decay weights + gene selection + fused "
-                       "diffusion/LR score -> dense n x P score matrix in HBM",
-                       "sharding": f"LR pairs: {P} per GPU x {world} GPUs, graph replicated, no collective",
-                       "l2": "512 MiB buffer written between timed iterations (outside the event bracket)",
-                       "schedule": schedule, "ms_per_step_eager": float(np.mean(eager_ms))},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * t_e2e / args.steps, "ms_each": [round(1e3 * t, 3) for t in e2e_t],
-                    "call": "laris_b200.tl.prepareLRInteraction(adata, lr_df) -> AnnData with scipy CSR on the host"},
-            "gpu_launches": int(launches), "wall_s_timed_region": wall, "clocks": clocks.summary(),
-            "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(c, args.config)},
+            "e2e": e2e, "gpu_launches": int(launches), "wall_s_timed_region": wall, "clocks": clocks.summary(),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "extra": {
+                "step": "prepareLRInteraction(csr_dev, to_host=False) + runLARIS(rng='philox', output='arrays'), inputs "
+                        "resident in HBM, results left on the device",
+                "sharding": (f"strong scaling: {P} LR pairs over {world} ranks ({P_local} on rank 0), graph and expression "
+                             "replicated; collectives inside the timed step: all-gather [1+R,5,P] statistics, all-gather "
+                             "[C,P] counts, all-gather [P,C^2] co-localisation table, all-reduce [C^2,P] exceedance counts"
+                             if world > 1 else "single GPU, no collective"),
+                "l2": "512 MiB buffer written between timed iterations; S alone is 4nP bytes >> L2",
+                "ms_each": [round(x, 2) for x in step_ms],
+                "device_ms_per_step_sum_of_stages": device_ms,
+                "host_glue_ms_per_step": float(np.mean(step_ms)) - device_ms,
+                "stage_ms_per_step": {s: round(v / args.steps, 3) for s, v in sorted(stage_ms.items())},
+                "stage_calls_per_step": {s: v / args.steps for s, v in sorted(calls.items()) if s != "_steps"},
+                "kernels": recs,
+                "m1_prepare_only_scores_per_sec": m1,
+                "cpu_cores_per_rank": cores, "gpu_launches_are": "rank 0's library launch counter over the timed steps",
+            },
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def extra_metrics(torch, a, c, state, engine, K):
-    """Permutation metrics (M2a/M2b) and the remaining stages, device-timed once each."""
-    out = {}
-    sm, n, P, k = state["sm"], c.n, c.P, c.k
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-
-    def timed(fn, reps=3):
-        fn()
-        torch.cuda.synchronize()
-        ts = []
-        for _ in range(reps):
-            e0, e1 = ev(), ev()
-            e0.record()
-            r = fn()
-            e1.record()
-            torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-        return float(np.min(ts)), r
-
-    g2 = engine.build_graph(a.obsm["X_spatial"], k, False, 100.0)
-    ms, _ = timed(lambda: K.spatial_stats(sm.S, P, g2.idx, g2.w, False, g2.order))
-    out["observed_stats_ms"] = ms
-    out["observed_stats_GBps_algorithmic"] = (4 * n * P + 8 * n * k) / ms / 1e6
-    cols, wperm = K.null_graph_philox(n, k, g2.w, 0, 27)
-    ms, _ = timed(lambda: K.spatial_stats(sm.S, P, cols, wperm, True, None))
-    out["null_repeat_ms"] = ms
-    out["null_repeats_per_sec"] = 1e3 / ms
-    out["null_repeat_GBps_algorithmic"] = (4 * (1 + k) * n * P + 8 * n * k) / ms / 1e6
-    labels = a.obs["CellTypes"].cat.codes.to_numpy().astype(np.int32)
-    lab_d = K.to_device(labels, torch.int32)
-    C = c.C
-    N_ = K.neighborhood_composition(lab_d, g2.idx, g2.w, C)
-    ms, _ = timed(lambda: K.celltype_pair_contract(sm.S, P, N_, 0, order=g2.order), reps=3)
-    out["celltype_contract_ms"] = ms
-    out["celltype_contract_impl"] = "tcgen05 (bf16 hi/mid/lo operand split, 6 MMAs per k-step, fp32 TMEM accumulation)"
-    out["celltype_contract_TFLOPs_algorithmic"] = 2.0 * n * P * C * C / ms / 1e9
-    if c.N > 0:
-        rng = np.random.default_rng(0)
-        table = K.to_device(rng.random((C * C, P)), torch.float64)
-        bg = K.to_device(np.stack([rng.permutation(P)[:30] for _ in range(P)]).astype(np.int32), torch.int32)
-        ms, _ = timed(lambda: K.pvalue_counts(table, bg, c.N, seed=27, only_ge=True))       # runLARIS default (standard p-value)
-        out["pvalue_null_ms"] = ms
-        out["pvalue_null_conditional_ms"] = timed(lambda: K.pvalue_counts(table, bg, c.N, seed=27))[0]
-        out["pvalue_permutations_per_sec"] = c.N / (ms * 1e-3)
-        out["pvalue_draws_per_sec"] = C * C * P * c.N / (ms * 1e-3)
-    return out
+def engine_last_xu(la):
+    """The packed LR-gene expression the last prepareLRInteraction left on the device (for nnz(Xu))."""
+    from laris_b200.tools import _utils
+    for hit in _utils._EXPR_CACHE.values():
+        return hit[1]
+    return None
 
 
-def cpu_permutation_baselines(a, c, S_host, gpu):
-    """The permutation half of the metric on the host cores (oracle port, 1 core - scipy.sparse / numpy are serial):
-    one random-graph null repeat on the full score matrix, and the p-value resampling on a bounded sample of
-    sender-receiver groups (its cost is linear in the number of groups)."""
-    from oracle import restate as R
-    import scipy.sparse as sp
-    out = {}
-    n, k, P, C = c.n, c.k, c.P, c.C
-    S = sp.csr_matrix(S_host).astype(np.float64)
-    ind, dist = R.knn_graph(a.obsm["X_spatial"], k, False)
-    w = R.decay_weights(dist, 100.0)
-    t0 = time.perf_counter()
-    cols, wperm = next(iter(R.null_graphs(n, k, w, 1, 27, "numpy")))
-    R.null_cosine(S, k, cols, wperm)
-    t = time.perf_counter() - t0
-    out["cpu_null_repeats_per_sec"] = 1.0 / t
-    out["cpu_null_repeat_sample"] = f"1 repeat, full {n} x {P} score matrix ({t:.2f} s), oracle port, 1 core"
-    if "null_repeats_per_sec" in gpu:
-        out["null_repeats_speedup_vs_cpu"] = gpu["null_repeats_per_sec"] / out["cpu_null_repeats_per_sec"]
-    if c.N > 0:
-        rng = np.random.default_rng(0)
-        groups = min(C * C, 40)                                    # bounded sample: 40 of the C^2 groups
-        table = rng.random((groups, P))
-        bg = np.stack([rng.permutation(P)[:30] for _ in range(P)]).astype(np.int64)
-        rs = np.random.RandomState(27)
-        t0 = time.perf_counter()
-        R.pvalue_counts(table, np.ones(P, bool), bg, lambda g, pidx: rs.randint(0, 30, (len(pidx), c.N)))
-        t = (time.perf_counter() - t0) * (C * C / groups)          # linear in the number of groups
-        out["cpu_pvalue_permutations_per_sec"] = c.N / t
-        out["cpu_pvalue_draws_per_sec"] = C * C * P * c.N / t
-        out["cpu_pvalue_sample"] = f"{groups} of {C * C} groups x {P} pairs x {c.N} permutations, scaled linearly, oracle port, 1 core"
-        if "pvalue_permutations_per_sec" in gpu:
-            out["pvalue_permutations_speedup_vs_cpu"] = gpu["pvalue_permutations_per_sec"] / out["cpu_pvalue_permutations_per_sec"]
-    return out
+def xu_nnz(xu):
+    if xu is None or xu.packed is None:
+        return 0
+    if xu.row_end is not None:
+        return int((xu.row_end - xu.indptr[:-1]).sum().item())
+    return int(xu.packed.numel())
 
 
 if __name__ == "__main__":

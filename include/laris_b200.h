@@ -264,6 +264,24 @@ LARIS_API int laris_onehot_contract_rows(const int64_t* row_start, const int64_t
                               int32_t G_u, const int32_t* labels, int32_t C, double* sum, double* cnt, double* colsq,
                               void* stream);
 
+/* ------------------------------------------ K5, key-gather ("sparse B") ----
+ * The same numerators as laris_celltype_pair_contract for neighbourhoods that hold few cell types (k <= ~10
+ * neighbours: 1-3 non-zero N[i,a] per cell, so the n x C^2 operand is > 99 % zeros).  Q is kept sparse with the key
+ * (a <= b) as column; each key's cells are gathered (contiguous row pieces, 128-bit streaming loads) and q*S is
+ * accumulated in fp64 - no operand split, no TMEM truncation.  HBM bytes: 4*P per entry, i.e. S is read once per key
+ * a cell takes part in.  Two calls, because the entry total sizes the scratch and picks the implementation:
+ *   laris_celltype_pair_keys:  key_count [C*C+1] int32 <- number of cells per key a*C+b (a <= b), rest 0;
+ *                              the caller sums it (one tiny device->host read) to get total_entries
+ *   laris_celltype_pair_contract_sparse: num [P*C*C] fp64 (both (a,b) and (b,a) written); key_count is consumed
+ * laris_pair_profile_norm: qnorm2 [C*C] = sum_i (N[i,a] N[i,b])^2 (what laris_celltype_pair_contract also returns).
+ * C <= 64, n < 2^31.  Entry order inside a key follows device atomics: fp64 sums can differ in the last bits
+ * between runs. */
+LARIS_API int laris_celltype_pair_keys(const float* Ncomp, int64_t n, int32_t C, int32_t* key_count, void* stream);
+LARIS_API int laris_celltype_pair_contract_sparse(const float* S, int64_t ldS, int64_t n, int32_t P, const float* Ncomp,
+                                                  int32_t C, int32_t* key_count, int64_t total_entries, double* num,
+                                                  void* stream);
+LARIS_API int laris_pair_profile_norm(const float* Ncomp, int64_t n, int32_t C, double* qnorm2, void* stream);
+
 /* ---------------------------------------------------------------- K6 ----
  * Exceedance counts of the background-resampling null
  * (laris/tools/_utils.py:1518-1596).  Row r = (group g, pair s), s over ALL pairs:

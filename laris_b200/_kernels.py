@@ -12,6 +12,49 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# ------------------------------------------------------------ stage timer ----
+# bench.py brackets the C-ABI calls of a step with CUDA events on the launching stream (``with timing() as t``) to get
+# each stage's device time INSIDE the timed region; outside such a block the wrappers add nothing.
+class StageTimer:
+    def __init__(self):
+        self.events = {}
+
+    def summary(self):
+        """{stage: (calls, total ms)}; call after a synchronisation."""
+        return {k: (len(v), float(sum(a.elapsed_time(b) for a, b in v))) for k, v in self.events.items()}
+
+
+_TIMER = None
+
+
+class timing:
+    def __enter__(self):
+        global _TIMER
+        self.prev, _TIMER = _TIMER, StageTimer()
+        return _TIMER
+
+    def __exit__(self, *exc):
+        global _TIMER
+        _TIMER = self.prev
+
+
+def _staged(name):
+    def deco(fn):
+        def wrapped(*a, **kw):
+            t = _TIMER
+            if t is None:
+                return fn(*a, **kw)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **kw)
+            e1.record()
+            t.events.setdefault(name(*a, **kw) if callable(name) else name, []).append((e0, e1))
+            return out
+        wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+        return wrapped
+    return deco
+
+
 def _ptr(t, dtype=None):
     if t is None:
         return None
@@ -54,6 +97,7 @@ def to_host(*tensors):
 
 
 # ----------------------------------------------------------------- K1 ----
+@_staged("K1 knn_graph")
 def knn_graph(xy, k, include_self, want_order=True):
     n, dim = xy.shape
     dev = xy.device
@@ -65,6 +109,7 @@ def knn_graph(xy, k, include_self, want_order=True):
     return idx, dist, order
 
 
+@_staged("K1 decay_weights")
 def decay_weights(dist, sigma=None, want64=False):
     m = dist.numel()
     w32 = torch.empty(dist.shape, dtype=torch.float32, device=dist.device)
@@ -75,6 +120,7 @@ def decay_weights(dist, sigma=None, want64=False):
     return w32, w64, scale
 
 
+@_staged("K1r radius_graph")
 def radius_graph(xy, radius, include_self, want_order=True):
     """K1r: (indptr int64[n+1], indices int32[nnz] column-sorted, dist fp64[nnz], order int32[n])."""
     n, dim = xy.shape
@@ -110,6 +156,7 @@ def exclusive_scan(counts):
     return out
 
 
+@_staged("select genes")
 def csr_select(indptr, indices, data, gene_map):
     """(indptr_u int64[n+1], packed int64[nnz_u]) restricted to gene_map >= 0."""
     n = indptr.numel() - 1
@@ -124,6 +171,7 @@ def csr_select(indptr, indices, data, gene_map):
     return out_indptr, packed[:nnz] if nnz else packed[:0]
 
 
+@_staged("select genes")
 def csr_select_rows(indptr, indices, data, gene_map):
     """Single-pass selection: (packed int64 [nnz(X)], row_end int64 [n]); row i's kept entries are
     packed[indptr[i] : row_end[i]].  No count pass, no scan, no host sync; costs nnz(X) slots."""
@@ -159,6 +207,7 @@ def _cx_args(cx):
     return _ptr(ptr, torch.int32), _ptr(cols, torch.int32), _ptr(vcol, torch.int32), int(vcol.numel()), int(rule)
 
 
+@_staged("K2+K3 diffuse_score (sparse)")
 def diffuse_lr_score(xu_indptr, xu_packed, G_u, idx, w, order, lig, rec, want_row_nnz=True, cx=None, row_end=None):
     """``row_end=None``: compact rows (row i = packed[indptr[i]:indptr[i+1]]); else row i = packed[indptr[i]:row_end[i]]."""
     n, k = idx.shape
@@ -176,6 +225,7 @@ def diffuse_lr_score(xu_indptr, xu_packed, G_u, idx, w, order, lig, rec, want_ro
     return S, row_nnz
 
 
+@_staged("select genes")
 def csr_select_dense(indptr, indices, data, gene_map, n_columns):
     """(Xd fp32 [n, ldX] dense over the packed columns, neg_flag int32[1]); ldX = 128-multiple > n_columns."""
     n = indptr.numel() - 1
@@ -188,6 +238,7 @@ def csr_select_dense(indptr, indices, data, gene_map, n_columns):
     return Xd, neg
 
 
+@_staged("K2+K3 diffuse_score (dense)")
 def diffuse_lr_score_dense(Xd, neg_flag, G_u, idx, w, order, lig, rec, want_row_nnz=True, cx=None):
     n, k = idx.shape
     P = lig.numel()
@@ -202,6 +253,7 @@ def diffuse_lr_score_dense(Xd, neg_flag, G_u, idx, w, order, lig, rec, want_row_
     return S, row_nnz
 
 
+@_staged("csr_compact")
 def csr_compact(S, P, row_nnz):
     n, ld = S.shape
     indptr = exclusive_scan(row_nnz)
@@ -223,6 +275,7 @@ def csr_to_dense(indptr, indices, data, n, P):
 
 
 # ----------------------------------------------------------------- K4 ----
+@_staged("K4 spatial_stats (legacy)")
 def spatial_stats(S, P, idx, w, l1_normalise, order=None):
     n, ld = S.shape
     k = idx.shape[1]
@@ -233,13 +286,17 @@ def spatial_stats(S, P, idx, w, l1_normalise, order=None):
     return out
 
 
+@_staged(lambda S, P, idx, w, order, null_idx=None, null_w=None: "K4a observed_stats" if null_idx is None else ("K4b null_stats" if idx is None else "K4a+K4b"))
 def spatial_stats_batched(S, P, idx, w, order, null_idx=None, null_w=None):
-    """[1+R, 5, P] fp64: observed graph (row 0) and the R random graphs ``null_idx`` / ``null_w`` [R, n, k]."""
+    """[(1 if idx is given) + R, 5, P] fp64: observed graph (row 0) and the R random graphs ``null_idx`` / ``null_w``
+    [R, n, k]; either part may be omitted."""
     n, ld = S.shape
-    k = idx.shape[1]
+    k = idx.shape[1] if idx is not None else null_idx.shape[2]
     R = 0 if null_idx is None else int(null_idx.shape[0])
-    out = torch.empty((1 + R, 5, P), dtype=torch.float64, device=S.device)
-    check(lib.laris_spatial_stats_batched(_ptr(S, torch.float32), ld, n, P, _ptr(idx, torch.int32), _ptr(w, torch.float32),
+    out = torch.empty(((1 if idx is not None else 0) + R, 5, P), dtype=torch.float64, device=S.device)
+    check(lib.laris_spatial_stats_batched(_ptr(S, torch.float32), ld, n, P,
+                                          _ptr(idx, torch.int32) if idx is not None else None,
+                                          _ptr(w, torch.float32) if idx is not None else None,
                                           k, _ptr(order, torch.int32) if order is not None else None,
                                           _ptr(null_idx, torch.int32) if R else None,
                                           _ptr(null_w, torch.float32) if R else None, R, _ptr(out), _stream()),
@@ -247,6 +304,7 @@ def spatial_stats_batched(S, P, idx, w, order, null_idx=None, null_w=None):
     return out
 
 
+@_staged("K4b null_graph")
 def null_graph_philox(n, k, w, repeat, seed, out=None):
     cols, wout = out if out is not None else (torch.empty((n, k), dtype=torch.int32, device=w.device),
                                               torch.empty((n, k), dtype=torch.float32, device=w.device))
@@ -263,6 +321,7 @@ def gather_f32(w, perm):
 
 
 # ----------------------------------------------------------------- K5 ----
+@_staged("K5 composition")
 def neighborhood_composition(labels, idx, w, C):
     n, k = idx.shape
     N = torch.empty((n, C), dtype=torch.float32, device=idx.device)
@@ -272,22 +331,39 @@ def neighborhood_composition(labels, idx, w, C):
 
 
 MMA_MIN_C, MMA_MAX_C = 1, 64      # cell-type counts the tcgen05 contraction handles (N row = two values per lane)
+SPARSE_MAX_ENTRIES_PER_CELL = 8.0   # above this many (a <= b) keys per cell the dense tensor-core contraction wins
 
 
+@_staged("K5 pair_contract")
 def celltype_pair_contract(S, P, N, impl=None, order=None):
-    """impl: 0 tcgen05 tensor cores, 1 fp32 CUDA cores, None = 0 whenever the number of cell types allows it."""
+    """Numerators num[P, C*C] and profile norms qn2[C*C] of the cell-type-pair cosines.
+    impl: 0 tcgen05 tensor cores (dense B operand), 1 fp32 CUDA cores, 2 key-gather ("sparse B", fp64 accumulation);
+    None = 2 when the neighbourhoods hold few cell types (<= SPARSE_MAX_ENTRIES_PER_CELL keys per cell on average - the
+    regime of every kNN graph with k ~ 10), else 0 whenever the number of cell types allows it, else 1."""
     n, ld = S.shape
     C = N.shape[1]
-    if impl is None:
-        impl = 0 if MMA_MIN_C <= C <= MMA_MAX_C else 1
     num = torch.empty((P, C * C), dtype=torch.float64, device=S.device)
     qn2 = torch.empty(C * C, dtype=torch.float64, device=S.device)
+    if impl in (None, 2) and C <= MMA_MAX_C:
+        key_count = torch.empty(C * C + 1, dtype=torch.int32, device=S.device)
+        check(lib.laris_celltype_pair_keys(_ptr(N, torch.float32), n, C, _ptr(key_count), _stream()),
+              "laris_celltype_pair_keys")
+        total = int(key_count[: C * C].sum().item())             # sizes the entry list and picks the implementation
+        if impl == 2 or total <= SPARSE_MAX_ENTRIES_PER_CELL * n:
+            check(lib.laris_pair_profile_norm(_ptr(N, torch.float32), n, C, _ptr(qn2), _stream()), "laris_pair_profile_norm")
+            check(lib.laris_celltype_pair_contract_sparse(_ptr(S, torch.float32), ld, n, P, _ptr(N, torch.float32), C,
+                                                          _ptr(key_count), total, _ptr(num), _stream()),
+                  "laris_celltype_pair_contract_sparse")
+            return num, qn2
+    if impl in (None, 2):
+        impl = 0 if MMA_MIN_C <= C <= MMA_MAX_C else 1
     check(lib.laris_celltype_pair_contract(_ptr(S, torch.float32), ld, n, P, _ptr(N, torch.float32), C,
                                            _ptr(order, torch.int32) if order is not None else None, _ptr(num),
                                            _ptr(qn2), int(impl), _stream()), "laris_celltype_pair_contract")
     return num, qn2
 
 
+@_staged("K5b nonzero_count")
 def celltype_nonzero_count(S, P, labels, C):
     n, ld = S.shape
     cnt = torch.empty((C, P), dtype=torch.int64, device=S.device)
@@ -296,6 +372,7 @@ def celltype_nonzero_count(S, P, labels, C):
     return cnt
 
 
+@_staged("COSG onehot_contract")
 def onehot_contract_csr(xu_indptr, xu_packed, G_u, labels, C, row_end=None):
     n = xu_indptr.numel() - 1
     dev = xu_indptr.device
@@ -310,6 +387,7 @@ def onehot_contract_csr(xu_indptr, xu_packed, G_u, labels, C, row_end=None):
     return s, c, q
 
 
+@_staged("row_qc")
 def row_qc(S, P, top_n=()):
     """Per-cell (total fp64 [n], nnz int64 [n], top_sum fp64 [n, len(top_n)]) of the score matrix."""
     n, ld = S.shape
@@ -323,6 +401,7 @@ def row_qc(S, P, top_n=()):
 
 
 # -------------------------------------------------------------- K6/K7 ----
+@_staged("K6 pvalue_counts")
 def pvalue_counts(table, bg, n_perm, *, active=None, seed=0, draws=None, slot_gid=None, P_global=None, g0=0, t0=0,
                   out=None, only_ge=False):
     """Exceedance counts (ge, nz, ge_nz) - or (ge, None, None) with ``only_ge`` (the standard p-value needs no more)."""
@@ -344,6 +423,7 @@ def pvalue_counts(table, bg, n_perm, *, active=None, seed=0, draws=None, slot_gi
     return ge, nz, both
 
 
+@_staged("K7 bh_fdr")
 def bh_fdr(p, sel):
     Gn, L = p.shape
     out = torch.empty((Gn, L), dtype=torch.float64, device=p.device)
@@ -352,6 +432,7 @@ def bh_fdr(p, sel):
 
 
 # --------------------------------------------------- step-2 tables (T1..T5) ----
+@_staged("tables")
 def pair_cosine_regularise(num, ss, qn2, mu, want_cos=False):
     """(cos or None, reg) [P, L] fp64 from the K5 numerators, the column sums of squares and the profile norms."""
     P, L = num.shape
@@ -363,6 +444,7 @@ def pair_cosine_regularise(num, ss, qn2, mu, want_cos=False):
     return cos, reg
 
 
+@_staged("tables")
 def column_iqr_log(table, q_upper=0.95, q_lower=0.75):
     rows, cols = table.shape
     out = torch.empty_like(table)
@@ -371,6 +453,7 @@ def column_iqr_log(table, q_upper=0.95, q_lower=0.75):
     return out
 
 
+@_staged("tables")
 def interaction_scores(spec_l, spec_r, factor, cnt, n_c, pair_id, P):
     Pt, C = spec_l.shape
     inter = torch.empty((Pt, C * C), dtype=torch.float64, device=spec_l.device)
@@ -381,6 +464,7 @@ def interaction_scores(spec_l, spec_r, factor, cnt, n_c, pair_id, P):
     return inter
 
 
+@_staged("tables")
 def topk_mean(values, k=100):
     """Device pair (mean of the k largest, 0.1 / mean or 1)."""
     out = torch.empty(2, dtype=torch.float64, device=values.device)
@@ -389,6 +473,7 @@ def topk_mean(values, k=100):
     return out
 
 
+@_staged("tables")
 def finalize_scores(inter, rescale2, ctc, pair_id, P, score_threshold):
     Pt, L = inter.shape
     dev = inter.device
@@ -401,6 +486,7 @@ def finalize_scores(inter, rescale2, ctc, pair_id, P, score_threshold):
     return flat, table, active
 
 
+@_staged("tables")
 def pvalues_from_counts(table, active, ge, nz, both, n_perm, conditional, prefilter, prefilter_threshold):
     L, P = table.shape
     dev = table.device
@@ -415,6 +501,7 @@ def pvalues_from_counts(table, active, ge, nz, both, n_perm, conditional, prefil
     return p, pr, sel
 
 
+@_staged("tables")
 def gather_result_rows(p_tab, fdr_tab, pair_id):
     L, P = p_tab.shape
     Pt = pair_id.numel()

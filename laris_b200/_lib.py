@@ -49,6 +49,9 @@ SIGNATURES = {
     "laris_gather_f32": [_p, _p, _i64, _p, _p],
     "laris_neighborhood_composition": [_p, _p, _p, _i64, _i, _i, _p, _p],
     "laris_celltype_pair_contract": [_p, _i64, _i64, _i, _p, _i, _p, _p, _p, _i, _p],
+    "laris_celltype_pair_keys": [_p, _i64, _i, _p, _p],
+    "laris_celltype_pair_contract_sparse": [_p, _i64, _i64, _i, _p, _i, _p, _i64, _p, _p],
+    "laris_pair_profile_norm": [_p, _i64, _i, _p, _p],
     "laris_celltype_nonzero_count": [_p, _i64, _i64, _i, _p, _i, _p, _p],
     "laris_onehot_contract_csr": [_p, _p, _i64, _i, _p, _i, _p, _p, _p, _p],
     "laris_onehot_contract_rows": [_p, _p, _p, _i64, _i, _p, _i, _p, _p, _p, _p],

@@ -277,6 +277,15 @@ int celltype_pair_contract_mma(const float* S, int64_t ldS, int64_t n, int32_t P
                                const int32_t* order, double* num, cudaStream_t st);   // celltype_mma.cu
 }
 
+extern "C" int laris_pair_profile_norm(const float* Ncomp, int64_t n, int32_t C, double* qnorm2, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LARIS_CHECK_ARG(Ncomp && qnorm2 && n > 0 && C >= 1, "laris_pair_profile_norm: bad arguments");
+    LARIS_CUDA(cudaMemsetAsync(qnorm2, 0, (size_t)C * C * sizeof(double), st));
+    pair_profile_norm_kernel<<<(unsigned)ceil_div(n, 64), 256, 64 * C * sizeof(float), st>>>(Ncomp, n, C, qnorm2);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
 extern "C" int laris_celltype_pair_contract(const float* S, int64_t ldS, int64_t n, int32_t P, const float* Ncomp,
                                             int32_t C, const int32_t* order, double* num, double* qnorm2, int impl,
                                             void* stream) {

@@ -615,7 +615,7 @@ static int observed_stats_tiled(const float* S, int64_t ldS, int64_t n, int32_t 
     const int nslabs = (int)ceil_div(ldS, kSlabCols);
     const int64_t W = (int64_t)nslabs * ntiles;
     const int grid = (int)(W < sms ? W : sms);
-    const int maxseg = (int)ceil_div(nslabs, grid) + 1;
+    const int maxseg = (int)ceil_div(nslabs, grid) + 2;
     const int nrec = grid * maxseg;
     LARIS_CUDA(partial.alloc((size_t)nrec * 5 * kSlabCols));
     LARIS_CUDA(rec_slab.alloc((size_t)nrec));

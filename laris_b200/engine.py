@@ -351,7 +351,7 @@ class CapturedScoring:
         return self.scores
 
 
-FP_SAMPLES = 1 << 22
+FP_SAMPLES = 1 << 20
 
 
 def device_fingerprint_async(data_d):
@@ -455,8 +455,12 @@ def null_graphs(graph: SpatialGraph, n_repeats, random_seed, rng="numpy"):
 def spatial_stats_all(sm: ScoreMatrix, graph: SpatialGraph, n_repeats, random_seed, rng="numpy"):
     """Observed statistics and the R null repeats (K4a + K4b) as ONE device tensor [1+R, 5, P] fp64 - no host
     synchronisation; row 0 is the observed graph.  Returns (stats_d, rng_state)."""
-    cols, wts, state = null_graphs(graph, n_repeats, random_seed, rng)
-    out = K.spatial_stats_batched(sm.S, sm.P, graph.idx, graph.w, graph.order, cols, wts)
+    out = torch.empty((1 + n_repeats, 5, sm.P), dtype=torch.float64, device=sm.S.device)
+    out[0].copy_(K.spatial_stats_batched(sm.S, sm.P, graph.idx, graph.w, graph.order)[0])
+    state = None
+    if n_repeats > 0:
+        cols, wts, state = null_graphs(graph, n_repeats, random_seed, rng)
+        out[1:].copy_(K.spatial_stats_batched(sm.S, sm.P, None, None, None, cols, wts))
     return out, state
 
 

@@ -96,7 +96,7 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     finish = engine.scores_to_csr_async(sm, dtype) if to_host else None
     lr_names = (lr_df["ligand"].astype(str) + "::" + lr_df["receptor"].astype(str)).to_numpy(dtype=object)
     obs, var = adata.obs.copy(), pd.DataFrame(index=pd.Index(lr_names, dtype=object))
-    obsm = {k: np.array(v, copy=True) for k, v in adata.obsm.items()}
+    obsm = {k: (v.clone() if torch.is_tensor(v) else np.array(v, copy=True)) for k, v in adata.obsm.items()}
     if to_host:
         X, score_fp = finish()
         lr_adata = make_anndata(X, obs=obs, var=var, obsm=obsm)
@@ -225,7 +225,8 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
         prefilter_threshold=prefilter_threshold, score_threshold=score_threshold, spatial_weight=spatial_weight,
         use_conditional_pvalue=use_conditional_pvalue, rng=rng, random_seed=random_seed, rng_state=rng_state,
         verbose=verbose, contract_impl=contract_impl, shard=shard, radius=radius, output=output)
-    _log(verbose, f"\nResults: {len(laris_lr)} LR pairs, {len(celltype_results):,} cell type combinations")
+    if output == "frames":
+        _log(verbose, f"\nResults: {len(laris_lr)} LR pairs, {len(celltype_results):,} cell type combinations")
     return laris_lr, celltype_results
 
 

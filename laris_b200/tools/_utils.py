@@ -23,12 +23,12 @@ from .. import dist as _dist
 # runLARIS neither re-uploads lr_adata.X nor re-selects adata.X.  A hit needs the SAME matrix
 # object with the SAME contents: entries are keyed by id() (weakly referenced) and validated against a content
 # fingerprint - nnz plus an exact integer checksum of the float32 bit patterns of a strided sample of ``.data``
-# (every element for matrices below 2^22 stored entries) - so in-place edits such as ``X.data *= c`` or a scanpy
+# (every element for matrices below 2^20 stored entries) - so in-place edits such as ``X.data *= c`` or a scanpy
 # ``log1p`` / ``scale`` between the two calls invalidate the entry instead of being silently ignored.
 # ---------------------------------------------------------------------------
 _SCORE_CACHE: dict = {}
 _EXPR_CACHE: dict = {}
-_FP_SAMPLES = 1 << 22
+_FP_SAMPLES = engine.FP_SAMPLES
 
 
 def _fp_stride(nnz):
@@ -195,6 +195,8 @@ def _pairwise_row_multiply(sparse_matrix, cell_types, delimiter: str = "::"):
 def _coords(adata, use_rep):
     if use_rep not in adata.obsm:
         raise KeyError(f"Representation '{use_rep}' not found in adata.obsm. Available keys: {list(adata.obsm.keys())}")
+    if torch.is_tensor(adata.obsm[use_rep]):           # coordinates already resident on the device
+        return adata.obsm[use_rep]
     return np.ascontiguousarray(np.asarray(adata.obsm[use_rep]), dtype=np.float64)
 
 

@@ -364,7 +364,7 @@ def rescale_top100(flat_scores):
 # ---------------------------------------------------------------------------
 
 
-def background_interactions(S, nb, leaf_size=40):
+def background_interactions(S, nb, leaf_size=30):
     """30-NN of each pair in (mean, variance) space; laris/tools/_utils.py:1075-1105."""
     from sklearn.neighbors import KDTree
     S = sp.csr_matrix(S)

@@ -306,10 +306,12 @@ def test_celltype_contractions(dev, golden, tiny):
     N_ref = R.neighborhood_composition(labels, ind, R.decay_weights(dist), C)
     N = K.neighborhood_composition(lab_d, g.idx, g.w, C).cpu().numpy()
     assert np.allclose(N.T, N_ref, rtol=1e-5, atol=1e-7)
-    for impl in (0, 1):                                             # tcgen05 tensor cores / fp32 CUDA cores
+    for impl in (None, 2, 0, 1):                    # default (= key-gather here) / key-gather / tcgen05 / fp32 CUDA cores
         raw, cos = engine.neighborhood_specificity(sm, lab_d, C, g, 100.0, impl=impl)
         assert np.allclose(cos, R.celltype_pair_cosine(S, N_ref), rtol=RTOL, atol=1e-8), impl
-        assert np.allclose(raw, golden["ctc_raw"], rtol=2e-5, atol=1e-10), impl   # the reference's own table
+        # the reference's own table.  raw ~ cos^3: the default path holds the 1e-5 bar; the tensor-core path
+        # (bf16 operand split, truncating TMEM accumulation) is documented at 2e-5 on this cubed quantity
+        assert np.allclose(raw, golden["ctc_raw"], rtol=2e-5 if impl == 0 else RTOL, atol=1e-10), impl
     # COSG gene scores
     X = sp.csr_matrix(a.X)
     genes = np.unique(np.concatenate([golden["lig_idx"], golden["rec_idx"]]))
@@ -456,7 +458,7 @@ def test_runlaris_matches_reference_fixture(dev, golden, tiny):
     assert np.array_equal(key[o], golden["tbl_key"])
     sc = res["interaction_score"].to_numpy()[o]
     assert np.array_equal(sc == 0, golden["tbl_score"] == 0)
-    assert np.allclose(sc, golden["tbl_score"], rtol=5e-5, atol=1e-12)
+    assert np.allclose(sc, golden["tbl_score"], rtol=RTOL, atol=1e-12)
     assert np.allclose(res["p_value"].to_numpy()[o], golden["tbl_p"], rtol=1e-12), "p-values are count-derived: exact"
     assert np.allclose(res["p_value_fdr"].to_numpy()[o], golden["tbl_fdr"], rtol=1e-9)
     assert np.allclose(res["nlog10_p_value_fdr"].to_numpy()[o], golden["tbl_nlog"], rtol=1e-9, atol=1e-12)
@@ -540,41 +542,43 @@ def test_utils_wrappers(dev, golden, tiny):
     assert R_.shape == A.shape and np.isclose(R_.sum(), A.sum())
 
 
-# ------------------------------------------- full-size properties ----
-def test_full_size_properties_config2(dev):
-    """BASELINE configs[1] at full size: size-independent invariants instead of an O(n) oracle run."""
+# ------------------------------------------- full-size parity ----
+def test_full_size_config2_vs_oracle(dev):
+    """BASELINE configs[1] at FULL size (1e5 cells x 500 pairs): prepareLRInteraction against the oracle (exact CSR
+    structure, scores to 1e-5), the observed statistics / null cosines against the oracle on the same scores, plus
+    the size-independent invariants (checksum of checksums, linearity)."""
     import laris_b200 as la
     from laris_b200 import engine
     from laris_b200.synth import make_dataset
     from laris_b200.tools import _utils as U
+    from oracle import restate as R
     a, lr, c = make_dataset(2)
     out = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=c.k)
     X = out.X
     assert X.shape == (c.n, c.P) and X.has_sorted_indices and (X.data != 0).all()
+    li, ri = R.gene_index(a.var_names, lr["ligand"]), R.gene_index(a.var_names, lr["receptor"])
+    ind, dist = R.knn_graph(a.obsm["X_spatial"], c.k, True)
+    S = R.lr_scores(a.X, ind, R.decay_weights(dist), li, ri)
+    _assert_csr_equal(X, S)
     sm = U._scores_of(out)
     g = engine.build_graph(a.obsm["X_spatial"], c.k, False, sigma=100.0)
-    st = engine.observed_stats(sm, g)
+    st_all, _ = engine.spatial_stats_all(sm, g, 1, 27, "philox")
+    st = st_all[0].cpu().numpy()
+    ind2, d2 = R.knn_graph(a.obsm["X_spatial"], c.k, False)
+    w2 = R.decay_weights(d2, 100.0)
+    assert np.array_equal(g.idx.cpu().numpy(), ind2)
+    assert np.allclose(engine._cosine(st), R.observed_cosine(S, ind2, w2), rtol=RTOL, atol=1e-9)
+    cols, wp = next(iter(R.null_graphs(c.n, c.k, w2.astype(np.float32), 1, 27, "philox")))
+    ref_null = R.null_cosine(S, c.k, cols, wp.astype(np.float32).astype(np.float64))
+    assert np.allclose(engine._cosine(st_all[1].cpu().numpy()), ref_null, rtol=RTOL, atol=1e-9)
     # checksum of checksums: device column sums == host sums of the materialised CSR
     assert np.allclose(st[3], np.asarray(X.sum(0)).ravel(), rtol=1e-5)
     assert np.array_equal(st[4].astype(np.int64), np.asarray(X.getnnz(0)).ravel())
-    # mask property: a score is non-zero only where the ligand or receptor is expressed in that cell
-    li = pd.Index(a.var_names).get_indexer(lr["ligand"])
-    ri = pd.Index(a.var_names).get_indexer(lr["receptor"])
-    Xc = sp.csc_matrix(a.X)
-    rows = slice(0, 5000)
-    expr = ((Xc[rows][:, li] != 0) + (Xc[rows][:, ri] != 0)).toarray()
-    assert not (X[rows].toarray() != 0)[~expr].any()
     # linearity of the diffusion: scaling X by 2 scales every score by 4
     b = a.copy()
     b.X = a.X * 2.0
     X2 = la.tl.prepareLRInteraction(b, lr, number_nearest_neighbors=c.k).X
     assert np.array_equal(X2.indices, X.indices) and np.allclose(X2.data, 4.0 * X.data, rtol=1e-6)
-    # cosines are bounded and the null is reproducible
-    cos = engine._cosine(st)
-    assert (np.abs(cos) <= 1 + 1e-9).all()
-    n1, _ = engine.null_cosines(sm, g, 2, 27, "philox")
-    n2, _ = engine.null_cosines(sm, g, 2, 27, "philox")
-    assert np.array_equal(n1, n2) and (np.abs(n1) <= 1 + 1e-9).all()
 
 
 # ----------------------------------------------------------------- K1r ----

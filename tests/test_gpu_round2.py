@@ -1,0 +1,325 @@
+"""GPU tier, round-2 additions: the device tables of runLARIS step 2 (T1..T5), the batched K4 (TMA-staged observed
+tiles, multi-repeat null pass), the key-gather K5, device-resident outputs, cache validation - each against the CPU
+oracle / numpy on the same seeded inputs."""
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse as sp
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    import laris_b200._lib  # noqa: F401
+    return torch.device("cuda:0")
+
+
+def _d(x, dtype):
+    from laris_b200 import _kernels as K
+    return K.to_device(np.ascontiguousarray(x), dtype)
+
+
+# ------------------------------------------------------------- tables ----
+@pytest.mark.parametrize("P,C,mu", [(37, 3, 100.0), (500, 20, 1.0), (2000, 40, 100.0), (5, 1, 0.5)])
+def test_pair_cosine_regularise(dev, P, C, mu):
+    from laris_b200 import _kernels as K
+    from oracle import restate as R
+    rng = np.random.default_rng(P + C)
+    L = C * C
+    num = rng.random((P, L)) * (rng.random((P, L)) < 0.6)
+    ss = rng.random(P) + 0.1
+    qn2 = rng.random(L) + 0.05
+    ss[0] = 0.0                                            # an all-zero pair
+    qn2[L - 1] = 0.0                                       # an empty profile
+    cos, reg = K.pair_cosine_regularise(_d(num, torch.float64), _d(ss, torch.float64), _d(qn2, torch.float64), mu, want_cos=True)
+    den = np.sqrt(ss)[:, None] * np.sqrt(qn2)[None, :]
+    ref_cos = np.zeros_like(num)
+    np.divide(num, den, out=ref_cos, where=den != 0)
+    assert np.allclose(cos.cpu().numpy(), ref_cos, rtol=1e-14, atol=0)
+    assert np.allclose(reg.cpu().numpy(), R.cosg_regularise(ref_cos, mu), rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("rows,cols", [(2000, 1600), (120, 25), (7, 3), (9001, 5)])
+def test_column_iqr_log_matches_the_oracle_stand_in(dev, rows, cols):
+    from laris_b200 import _kernels as K
+    from oracle import cosg_standin
+    rng = np.random.default_rng(rows)
+    t = rng.random((rows, cols)) ** 4
+    t[rng.random((rows, cols)) < 0.5] = 0.0
+    t[rng.random((rows, cols)) < 0.05] *= -1.0
+    t[:, 0] = 0.0                                          # no positive entry
+    if cols > 2:
+        t[:, 1] = np.where(np.arange(rows) % 3 == 0, 0.25, 0.0)       # all positives equal: IQR = 0 -> scale = max
+        t[:, 2] = 0.0
+        t[rows // 2, 2] = 3.0                              # a single positive entry
+    got = K.column_iqr_log(_d(t, torch.float64)).cpu().numpy()
+    ref = cosg_standin.iqr_log_normalize(t)
+    assert np.allclose(got, ref, rtol=1e-12, atol=0)
+    assert got.min() == 0.0 and got.max() == 1.0
+
+
+@pytest.mark.parametrize("m,k", [(3_200_000, 100), (50, 100), (100, 100), (16385, 7), (1, 1), (40000, 4096)])
+def test_topk_mean(dev, m, k):
+    from laris_b200 import _kernels as K
+    rng = np.random.default_rng(m)
+    v = rng.random(m) ** 8
+    v[rng.random(m) < 0.3] = 0.0
+    if m > 1000:
+        v[:300] = v.max()                                  # ties at the top, crossing the cut
+    out = K.topk_mean(_d(v, torch.float64), k).cpu().numpy()
+    top = np.sort(v)[::-1][: min(k, m)]
+    assert np.isclose(out[0], top.mean(), rtol=1e-13, atol=0)
+    assert np.isclose(out[1], 0.1 / top.mean() if top.mean() > 0 else 1.0, rtol=1e-13)
+    z = K.topk_mean(_d(np.zeros(500), torch.float64), 100).cpu().numpy()
+    assert z[0] == 0.0 and z[1] == 1.0
+
+
+def test_interaction_tables_match_the_oracle(dev):
+    """T3a + T3b + T3c + T5 + K7 chained on random inputs == the oracle's table arithmetic."""
+    from laris_b200 import _kernels as K
+    from oracle import restate as R
+    rng = np.random.default_rng(5)
+    P, Pt, C, N = 300, 257, 6, 200
+    L = C * C
+    sl, sr = rng.random((Pt, C)), rng.random((Pt, C))
+    sl[rng.random((Pt, C)) < 0.3] = 0.0
+    score = rng.random(Pt) + 0.01
+    cnt = rng.integers(0, 50, (C, P))
+    n_c = rng.integers(50, 90, C).astype(np.float64)
+    pair_id = rng.permutation(P)[:Pt]
+    ctc = rng.random((P, L)) * (rng.random((P, L)) < 0.7)
+    pid_d = _d(pair_id.astype(np.int32), torch.int32)
+    inter = K.interaction_scores(_d(sl, torch.float64), _d(sr, torch.float64), _d(score, torch.float64),
+                                 _d(cnt, torch.int64), _d(n_c, torch.float64), pid_d, P)
+    frac = (cnt / n_c[:, None]).T
+    ref_inter = R.interaction_table(sl, sr, score, frac[pair_id], 1.0).reshape(Pt, L)
+    assert np.array_equal(inter.cpu().numpy(), ref_inter)                     # same operation order: same bits
+    resc = K.topk_mean(inter.view(-1), 100)
+    ref_scale = R.rescale_top100(ref_inter.reshape(-1))
+    assert np.isclose(resc.cpu().numpy()[1], ref_scale, rtol=1e-13)
+    flat, table, active = K.finalize_scores(inter, resc, _d(ctc, torch.float64), pid_d, P, 1e-3)
+    ref_flat = ref_inter * resc.cpu().numpy()[1] * ctc[pair_id]
+    ref_flat[ref_flat < 1e-3] = 0.0
+    assert np.array_equal(flat.cpu().numpy(), ref_flat)
+    ref_table = np.zeros((L, P))
+    ref_table[:, pair_id] = ref_flat.T
+    assert np.array_equal(table.cpu().numpy(), ref_table)
+    ref_active = np.zeros(P, bool)
+    ref_active[pair_id] = True
+    assert np.array_equal(active.cpu().numpy().astype(bool), ref_active)
+    # counts -> p -> BH, both p-value definitions
+    bg = np.stack([rng.permutation(P)[:30] for _ in range(P)]).astype(np.int32)
+    for conditional in (False, True):
+        ge, nz, both = K.pvalue_counts(table, _d(bg, torch.int32), N, active=active, seed=3, only_ge=not conditional)
+        p, pr, sel = K.pvalues_from_counts(table, active, ge, nz, both, N, conditional, True, 0.0)
+        ref_p = R.pvalues_from_counts(ref_table, ge.cpu().numpy(), None if nz is None else nz.cpu().numpy(),
+                                      None if both is None else both.cpu().numpy(), N, conditional)
+        assert np.array_equal(p.cpu().numpy(), ref_p)
+        assert np.array_equal(pr.cpu().numpy(), np.round(ref_p, 6))
+        assert np.array_equal(sel.cpu().numpy().astype(bool), ref_active[None, :] & (ref_table > 0.0))
+        fdr = K.bh_fdr(pr, sel)
+        p_rows, f_rows, l_rows = (x.cpu().numpy() for x in K.gather_result_rows(p, fdr, pid_d))
+        ref_fdr, ref_nlog = R.fdr_by_group(ref_p[:, pair_id], ref_table[:, pair_id], True, 0.0)
+        assert np.array_equal(p_rows, ref_p[:, pair_id].T)
+        assert np.allclose(f_rows, ref_fdr.T, rtol=1e-12, atol=0)
+        assert np.allclose(l_rows, ref_nlog.T, rtol=1e-9, atol=1e-12)
+
+
+# ----------------------------------------------------------------- K4 ----
+def _uniform(n, seed):
+    return np.random.default_rng(seed).random((n, 2)) * 10.0 * np.sqrt(n)
+
+
+@pytest.mark.parametrize("n,P,k,use_order", [(3001, 131, 13, True), (20000, 500, 10, True), (1500, 64, 8, False),
+                                              (129, 7, 3, True), (5000, 2000, 15, True), (4000, 40, 20, True)])
+def test_batched_stats_equal_legacy_and_oracle(dev, n, P, k, use_order):
+    """Tiled observed pass (k <= 15; legacy path above) and the multi-repeat null pass against the single-graph kernel
+    and the oracle; n % 128 != 0, column tails, and a processing order that is not spatial (tiles overflow their
+    staging capacity and read global rows directly)."""
+    from laris_b200 import _kernels as K, engine
+    from oracle import restate as R
+    xy = _uniform(n, 3)
+    S = sp.random(n, P, 0.25, random_state=7, format="csr", dtype=np.float32)
+    sm = engine.scores_from_csr(S)
+    g = engine.build_graph(xy, k, False, sigma=40.0)
+    order = g.order if use_order else None
+    legacy = K.spatial_stats(sm.S, P, g.idx, g.w, False, g.order).cpu().numpy()
+    R_ = 4
+    cols, wts, _ = engine.null_graphs(g, R_, 11, "philox")
+    both = K.spatial_stats_batched(sm.S, P, g.idx, g.w, order, cols, wts).cpu().numpy()
+    assert both.shape == (1 + R_, 5, P)
+    assert np.allclose(both[0], legacy, rtol=1e-6, atol=1e-9)                # fp32 tile partials vs fp32 products
+    assert np.array_equal(both[0][4], legacy[4]) and np.allclose(both[0][3], legacy[3], rtol=1e-6)
+    ind, dist = R.knn_graph(xy, k, False)
+    ref = R.observed_cosine(S.astype(np.float64), ind, R.decay_weights(dist, 40.0))
+    assert np.allclose(engine._cosine(both[0]), ref, rtol=RTOL, atol=1e-9)
+    for r in range(R_):
+        one = K.spatial_stats(sm.S, P, cols[r].contiguous(), wts[r].contiguous(), True, None).cpu().numpy()
+        assert np.allclose(both[1 + r], one, rtol=1e-12, atol=1e-300)
+    only_null = K.spatial_stats_batched(sm.S, P, None, None, None, cols, wts).cpu().numpy()
+    assert np.array_equal(only_null, both[1:])
+    # a scrambled processing order: tiles are no longer local, the union of neighbour rows exceeds the staging cap
+    perm = torch.randperm(n, device=dev).to(torch.int32)
+    scr = K.spatial_stats_batched(sm.S, P, g.idx, g.w, perm).cpu().numpy()[0]
+    assert np.allclose(scr, both[0], rtol=1e-6, atol=1e-9) and np.array_equal(scr[4], legacy[4])
+
+
+def test_observed_stats_on_padded_radius_rows(dev):
+    """Fixed-degree rows padded with (own row, weight 0) edges - the radius-graph layout - through the tiled pass."""
+    from laris_b200 import _kernels as K, engine
+    n, P = 6000, 90
+    xy = _uniform(n, 5)
+    S = sp.random(n, P, 0.3, random_state=2, format="csr", dtype=np.float32)
+    sm = engine.scores_from_csr(S)
+    g = engine.build_radius_graph(xy, 14.0, False, sigma=30.0)
+    assert g.k <= 15
+    a = K.spatial_stats(sm.S, P, g.idx, g.w, False, g.order).cpu().numpy()
+    b = K.spatial_stats_batched(sm.S, P, g.idx, g.w, g.order).cpu().numpy()[0]
+    assert np.allclose(a, b, rtol=1e-6, atol=1e-9)
+
+
+# ----------------------------------------------------------------- K5 ----
+@pytest.mark.parametrize("n,P,C,k,coherent", [(5000, 131, 7, 10, True), (20000, 500, 40, 10, True), (3000, 33, 1, 6, False),
+                                              (4097, 64, 64, 12, False), (257, 5, 3, 4, False), (30000, 2000, 20, 10, True)])
+def test_key_gather_contraction(dev, n, P, C, k, coherent):
+    from laris_b200 import _kernels as K, engine
+    rng = np.random.default_rng(n + C)
+    xy = _uniform(n, 1)
+    if coherent:
+        labels = (np.floor(xy[:, 0] / xy[:, 0].max() * 0.999 * C)).astype(np.int32)
+    else:
+        labels = rng.integers(0, C, n).astype(np.int32)
+    S = sp.random(n, P, 0.2, random_state=4, format="csr", dtype=np.float32)
+    sm = engine.scores_from_csr(S)
+    g = engine.build_graph(xy, k, False, None)
+    N = K.neighborhood_composition(_d(labels, torch.int32), g.idx, g.w, C)
+    num2, qn2 = K.celltype_pair_contract(sm.S, P, N, 2)
+    num1, qn1 = K.celltype_pair_contract(sm.S, P, N, 1)
+    Nh = N.cpu().numpy().astype(np.float64)
+    Q = (Nh[:, :, None] * Nh[:, None, :]).reshape(n, C * C)
+    ref = np.asarray(S.astype(np.float64).T @ Q)
+    got = num2.cpu().numpy()
+    assert np.allclose(got, ref, rtol=1e-6, atol=1e-9 * np.abs(ref).max())
+    assert np.allclose(num1.cpu().numpy(), ref, rtol=1e-4, atol=1e-6 * np.abs(ref).max())
+    assert np.allclose(qn2.cpu().numpy(), qn1.cpu().numpy(), rtol=1e-12)
+    sym = got.reshape(P, C, C)
+    assert np.array_equal(sym, sym.transpose(0, 2, 1))
+    auto, _ = K.celltype_pair_contract(sm.S, P, N, None, order=g.order)
+    assert np.allclose(auto.cpu().numpy(), ref, rtol=2e-5, atol=1e-6 * np.abs(ref).max())
+
+
+# ------------------------------------------------- device-resident path ----
+def test_resident_scores_and_array_output_equal_the_frames(dev):
+    """prepareLRInteraction(to_host=False, csr_dev=...) + runLARIS(output='arrays') - the path bench.py times - gives
+    the numbers of the default host-to-host calls."""
+    import laris_b200 as la
+    from laris_b200 import _kernels as K, engine
+    from laris_b200._anndata import AnnDataLite
+    from laris_b200.synth import make_dataset
+    a, lr, c = make_dataset(1, n=3000, G=200, G_u=100, P=61, C=4)
+    kw = dict(n_nearest_neighbors=8, n_repeats=2, number_nearest_neighbors=8, n_permutations=60, n_top_lr=61,
+              n_cells_expressed_threshold=10, rng="philox", verbose=False)
+    ref_ad = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=8)
+    ref_lr, ref_tab = la.tl.runLARIS(ref_ad, a, **kw)
+    csr_d = engine.upload_csr(a.X)
+    a_dev = AnnDataLite(a.X, a.obs, a.var, {"X_spatial": K.to_device(a.obsm["X_spatial"], torch.float64)})
+    ad = la.tl.prepareLRInteraction(a_dev, lr, number_nearest_neighbors=8, csr_dev=csr_d, to_host=False)
+    assert not sp.issparse(ad.X) and ad.shape == ref_ad.shape
+    Xd = ad.X.tocsr()
+    assert (Xd != ref_ad.X).nnz == 0
+    lr2, arr = la.tl.runLARIS(ad, a_dev, output="arrays", **kw)
+    assert list(lr2.index) == list(ref_lr.index) and np.allclose(lr2["score"], ref_lr["score"], rtol=1e-12)
+    assert "n_genes_by_counts" not in ad.obs and "cosg_lr" not in ad.uns and "n_genes_by_counts" in ref_ad.obs
+    C, names = c.C, np.asarray(ref_ad.var_names)
+    pid = pd.Index(names).get_indexer(ref_tab["interaction_name"].to_numpy())
+    cats = list(a.obs["CellTypes"].cat.categories)
+    g = pd.Index(cats).get_indexer(ref_tab["sender"]) * C + pd.Index(cats).get_indexer(ref_tab["receiver"])
+    row_of = np.empty(len(names), np.int64)
+    row_of[arr["pair_id"]] = np.arange(len(arr["pair_id"]))
+    for col in ("interaction_score", "p_value", "p_value_fdr", "nlog10_p_value_fdr"):
+        got = arr[col].cpu().numpy()[row_of[pid], g]
+        assert np.allclose(got, ref_tab[col].to_numpy(), rtol=1e-12, atol=0), col
+
+
+def test_cached_scores_are_revalidated_after_in_place_edits(dev):
+    """an in-place edit of lr_adata.X / adata.X between the two calls must not be served from the device cache."""
+    import laris_b200 as la
+    from laris_b200.synth import make_dataset
+    from laris_b200.tools import _utils as U
+    a, lr, c = make_dataset(1, n=2500, G=150, G_u=80, P=40, C=3)
+    kw = dict(n_nearest_neighbors=8, by_celltype=False, n_cells_expressed_threshold=10, verbose=False)
+    ad = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=8)
+    sm0 = U._scores_of(ad)
+    assert U._scores_of(ad) is sm0                                  # untouched: served from the cache
+    base = la.tl.runLARIS(ad, None, **kw)
+    ad.X.data[:] = np.log1p(ad.X.data)                              # scanpy-style in-place transform
+    sm1 = U._scores_of(ad)
+    assert sm1 is not sm0
+    assert np.allclose(sm1.S[:, :40].cpu().numpy(), ad.X.toarray(), rtol=1e-6)
+    edited = la.tl.runLARIS(ad, None, **kw)
+    assert not np.allclose(edited["score"].to_numpy(), base["score"].to_numpy())
+    fresh = la.tl.runLARIS(la._anndata.AnnDataLite(ad.X.copy(), ad.obs.copy(), pd.DataFrame(index=ad.var_names),
+                                                   {"X_spatial": a.obsm["X_spatial"]}), None, **kw)
+    assert np.allclose(edited["score"].to_numpy(), fresh["score"].to_numpy(), rtol=1e-12)
+    # expression cache: same rule
+    genes = U._gene_columns(a, np.unique(np.hstack([lr["ligand"], lr["receptor"]])))
+    assert U._expression_of(a.X, genes) is not None
+    a.X.data *= 2.0
+    assert U._expression_of(a.X, genes) is None
+
+
+def test_numpy_stream_draws_are_chunked(dev, golden, tiny, monkeypatch):
+    """the reference-stream p-value draws are generated a batch of groups at a time; the result does not
+    depend on the batch size (and equals the reference fixture)."""
+    import laris_b200 as la
+    from laris_b200.tools import _utils as U
+    a, lr, c = tiny
+    kw = dict(n_nearest_neighbors=8, random_seed=27, n_repeats=3, n_cells_expressed_threshold=20, number_nearest_neighbors=8,
+              n_permutations=200, rng="numpy", verbose=False)
+    res = []
+    for nbytes in (256 << 20, 3 * 120 * 200):                       # one batch / three groups per batch
+        monkeypatch.setattr(U, "_NUMPY_DRAW_BYTES", nbytes)
+        ad = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=8)
+        _, t = la.tl.runLARIS(ad, a, **kw)
+        res.append(t.sort_values(["sender", "receiver", "interaction_name"]).reset_index(drop=True))
+    assert np.array_equal(res[0]["p_value"].to_numpy(), res[1]["p_value"].to_numpy())
+    with pytest.raises(ValueError, match="<= 256"):
+        ad = la.tl.prepareLRInteraction(a, lr.iloc[:5], number_nearest_neighbors=8)
+        la.tl.runLARIS(ad, a, n_neighbors_permutation=300, n_permutations=10, rng="numpy", n_cells_expressed_threshold=1,
+                       verbose=False)
+
+
+def test_background_sets_with_duplicate_feature_points(dev):
+    """identical (mean, variance) points (e.g. all-zero LR pairs) follow the host KD-tree like the reference."""
+    import laris_b200 as la
+    from laris_b200._anndata import AnnDataLite
+    from laris_b200.tools import _utils as U
+    from oracle import restate as R
+    rng = np.random.default_rng(0)
+    n, P = 800, 90
+    S = sp.random(n, P, 0.2, random_state=1, format="csr", dtype=np.float32).tolil()
+    S[:, 10:25] = 0.0                                               # fifteen all-zero pairs: identical feature points
+    S[:, 30] = S[:, 31]
+    S = sp.csr_matrix(S)
+    ad = AnnDataLite(S, obs=pd.DataFrame(index=[f"c{i}" for i in range(n)]), var=pd.DataFrame(index=[f"a::b{j}" for j in range(P)]),
+                     obsm={"X_spatial": rng.random((n, 2))})
+    got = U._prepare_background_interactions(ad, 30).to_numpy()
+    ref, _ = R.background_interactions(S.astype(np.float64), 30, leaf_size=30)
+    assert np.array_equal(got, ref)
+
+
+def test_missing_labels_are_rejected(dev, tiny):
+    import laris_b200 as la
+    a, lr, _ = tiny
+    b = a.copy()
+    lab = b.obs["CellTypes"].astype(object)
+    lab.iloc[3] = None
+    b.obs["CellTypes"] = pd.Categorical(lab)
+    ad = la.tl.prepareLRInteraction(a, lr.iloc[:10], number_nearest_neighbors=8)
+    with pytest.raises(ValueError, match="no cell-type label"):
+        la.tl.runLARIS(ad, b, n_nearest_neighbors=8, n_cells_expressed_threshold=1, n_permutations=10, verbose=False)
