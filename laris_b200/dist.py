@@ -95,9 +95,9 @@ def all_gather_pairs_dev(local, shard: Shard, axis: int = -1):
     pad = torch.zeros((width,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     pad[: x.shape[0]] = x
     mine = _on_wire(pad)
-    out = torch.empty((shard.world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+    out = torch.empty((shard.world * width,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=mine.device)
     dist.all_gather_into_tensor(out, mine)
-    out = out.to(local.device)
+    out = out.to(local.device).view((shard.world, width) + tuple(mine.shape[1:]))
     parts = [out[r, : int(b[r + 1] - b[r])] for r in range(shard.world)]
     return torch.cat(parts, dim=0).movedim(0, axis).contiguous()
 

@@ -46,6 +46,19 @@ def _worker(rank, world, port, P, C):
         mine = draws[pb[rank]:pb[rank + 1]].sum(0).astype(np.int64)
         total = ld.all_reduce_sum(mine)
         assert np.array_equal(total, draws.sum(0))
+        # the tensor versions the device-resident pipeline uses (CUDA tensors over NCCL; host tensors over gloo here)
+        st = torch.from_numpy(np.random.default_rng(4).random((3, 5, P)))
+        got = ld.all_gather_pairs_dev(st[:, :, sh.start:sh.stop].contiguous(), sh, axis=-1)
+        assert got.shape == st.shape and torch.equal(got, st)
+        rows = torch.arange(P * C, dtype=torch.int64).reshape(P, C)
+        assert torch.equal(ld.all_gather_pairs_dev(rows[sh.start:sh.stop].contiguous(), sh, axis=0), rows)
+        cnt = torch.from_numpy(draws[pb[rank]:pb[rank + 1]].sum(0).astype(np.int32))
+        assert np.array_equal(ld.all_reduce_sum_dev(cnt).numpy(), draws.sum(0))
+        # row partition of the expression matrix by stored entries
+        indptr = np.concatenate([[0], np.cumsum(np.random.default_rng(1).integers(0, 9, 1000))])
+        rb = ld.row_bounds_by_nnz(indptr, 4)
+        assert rb[0] == 0 and rb[-1] == 1000 and (np.diff(rb) >= 0).all()
+        assert np.abs(np.diff(indptr[rb]) - indptr[-1] / 4).max() <= 9
     finally:
         dist.destroy_process_group()
 

@@ -533,7 +533,7 @@ def test_pp_helpers(dev):
 def test_utils_wrappers(dev, golden, tiny):
     from laris_b200.tools import _utils as U
     a, _, _ = tiny
-    A = U._build_adjacency_matrix(a, n_nearest_neighbors=8, sigma=100)
+    A = U._build_adjacency_matrix(a, use_rep="X_spatial", n_nearest_neighbors=8, sigma=100)
     assert np.array_equal(A.indices.reshape(1500, 8), golden["knn_noself_idx"])
     S = sp.csr_matrix((golden["S_data"], golden["S_indices"], golden["S_indptr"]), shape=(1500, 120))
     bgl = U._generate_random_background(a, A, S.T.tocsr(), n_nearest_neighbors=8, n_repeats=3, random_seed=27)

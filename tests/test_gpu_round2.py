@@ -176,8 +176,8 @@ def test_observed_stats_on_padded_radius_rows(dev):
     xy = _uniform(n, 5)
     S = sp.random(n, P, 0.3, random_state=2, format="csr", dtype=np.float32)
     sm = engine.scores_from_csr(S)
-    g = engine.build_radius_graph(xy, 14.0, False, sigma=30.0)
-    assert g.k <= 15
+    g = engine.build_radius_graph(xy, 10.0, False, sigma=30.0)
+    assert 4 <= g.k <= 15, g.k
     a = K.spatial_stats(sm.S, P, g.idx, g.w, False, g.order).cpu().numpy()
     b = K.spatial_stats_batched(sm.S, P, g.idx, g.w, g.order).cpu().numpy()[0]
     assert np.allclose(a, b, rtol=1e-6, atol=1e-9)
@@ -288,10 +288,7 @@ def test_numpy_stream_draws_are_chunked(dev, golden, tiny, monkeypatch):
         _, t = la.tl.runLARIS(ad, a, **kw)
         res.append(t.sort_values(["sender", "receiver", "interaction_name"]).reset_index(drop=True))
     assert np.array_equal(res[0]["p_value"].to_numpy(), res[1]["p_value"].to_numpy())
-    with pytest.raises(ValueError, match="<= 256"):
-        ad = la.tl.prepareLRInteraction(a, lr.iloc[:5], number_nearest_neighbors=8)
-        la.tl.runLARIS(ad, a, n_neighbors_permutation=300, n_permutations=10, rng="numpy", n_cells_expressed_threshold=1,
-                       verbose=False)
+    assert np.allclose(res[0]["interaction_score"].to_numpy(), res[1]["interaction_score"].to_numpy(), rtol=1e-12)
 
 
 def test_background_sets_with_duplicate_feature_points(dev):
