@@ -286,12 +286,13 @@ constexpr int kTileMaxK = 15;
 constexpr int kSlabCols = 64;            // columns per work item: 256-byte row pieces
 constexpr int kTileConsumers = 512;      // 16 quads x 32 cell lanes
 constexpr int kTileThreads = kTileConsumers + 32;
+constexpr int kTileSelf = kTileCells + 4;          // self slots + the tile's row count (16-byte granule)
 
 struct TilePlan {
     int32_t* cnt;      // [ntiles]                 distinct rows, or -1: the tile reads global rows directly
     int32_t* rows;     // [ntiles][kTileCap]       the distinct rows
     int2* ent;         // [ntiles][kTileCells][k]  {slot (or row when cnt < 0), weight bits}
-    int32_t* self;     // [ntiles][kTileCells]     slot (or row) of the cell itself; -1 = past the end
+    int32_t* self;     // [ntiles][kTileSelf]      slot (or row) of the cell itself, -1 = past the end; [kTileCells] = cnt
 };
 
 __global__ void __launch_bounds__(256)
@@ -352,7 +353,7 @@ tile_plan_kernel(const int32_t* __restrict__ idx, const float* __restrict__ w, i
     __syncthreads();
     const int u = total;
     const bool staged = u <= kTileCap;
-    if (tid == 0) plan.cnt[tile] = staged ? u : -1;
+    if (tid == 0) { plan.cnt[tile] = staged ? u : -1; plan.self[tile * kTileSelf + kTileCells] = staged ? u : -1; }
     if (staged)
         for (int r = tid; r < kTileCap; r += 256) plan.rows[tile * kTileCap + r] = r < u ? uniq[r] : 0;
     auto slot_of = [&](int32_t id) {
@@ -364,7 +365,7 @@ tile_plan_kernel(const int32_t* __restrict__ idx, const float* __restrict__ w, i
         return lo;
     };
     for (int c = tid; c < kTileCells; c += 256)
-        plan.self[tile * kTileCells + c] = cell[c] < 0 ? -1 : (staged ? slot_of(cell[c]) : cell[c]);
+        plan.self[tile * kTileSelf + c] = cell[c] < 0 ? -1 : (staged ? slot_of(cell[c]) : cell[c]);
     for (int e = tid; e < kTileCells * k; e += 256) {
         const int c = e / k, j = e - c * k;
         int2 out = make_int2(0, 0);
@@ -380,7 +381,7 @@ tile_plan_kernel(const int32_t* __restrict__ idx, const float* __restrict__ w, i
 
 struct TileSmem {
     static __host__ __device__ size_t stage_bytes(int k) {
-        return (size_t)kTileCap * kSlabCols * 4 + (size_t)kTileCells * k * 8 + (size_t)kTileCells * 4;
+        return (size_t)kTileCap * kSlabCols * 4 + (size_t)kTileCells * k * 8 + (size_t)kTileSelf * 4;
     }
     static __host__ __device__ size_t total(int k) { return 2 * stage_bytes(k) + 16 * 16 * 4 * 8 + 64; }
 };
@@ -402,32 +403,49 @@ spatial_obs_tile_kernel(const float* __restrict__ S, int64_t ldS, int k, TilePla
     __syncthreads();
     const int64_t W = (int64_t)nslabs * ntiles;
     const int64_t w0 = W * blockIdx.x / gridDim.x, w1 = W * (blockIdx.x + 1) / gridDim.x;
-    const uint32_t ent_bytes = (uint32_t)kTileCells * k * 8, self_bytes = kTileCells * 4;
+    const uint32_t ent_bytes = (uint32_t)kTileCells * k * 8, self_bytes = kTileSelf * 4;
 
     if (warp == kTileConsumers / 32) {
         // ------------------------------ producer warp ------------------------------
+        // The row list of the NEXT item is fetched (one batch of independent loads per lane) while this item's copies
+        // are issued and the stage is awaited, so no global-load latency sits between two bulk copies.
+        constexpr int RPL = (kTileCap + 31) / 32;                               // rows per lane
+        int32_t rows_nx[RPL];
+        int cnt_nx = 0;
+        auto fetch = [&](int64_t wi) {
+            const int64_t tile = wi % ntiles;
+            cnt_nx = plan.cnt[tile];
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) rows_nx[j] = lane + 32 * j < kTileCap ? plan.rows[tile * kTileCap + lane + 32 * j] : 0;
+        };
+        if (w0 < w1) fetch(w0);
         for (int64_t wi = w0, it = 0; wi < w1; ++wi, ++it) {
             const int st = (int)(it & 1);
             const uint32_t ph = (uint32_t)((it >> 1) & 1);
             const int slab = (int)(wi / ntiles);
             const int64_t tile = wi - (int64_t)slab * ntiles;
+            int32_t rows_cur[RPL];
+            const int cnt = cnt_nx;
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) rows_cur[j] = rows_nx[j];
+            if (wi + 1 < w1) fetch(wi + 1);
             aio::mbar_wait_sleep(empty0 + 8 * st, ph ^ 1u);
             unsigned char* stage = smem + st * stage_b;
             const uint32_t tile_s = aio::smem_addr(stage);
             const uint32_t ent_s = tile_s + kTileCap * kSlabCols * 4, self_s = ent_s + ent_bytes;
-            const int cnt = plan.cnt[tile];
             const int64_t col0 = (int64_t)slab * kSlabCols;
             const uint32_t colbytes = (uint32_t)min((int64_t)kSlabCols, ldS - col0) * 4u;
             const uint32_t bar = full0 + 8 * st;
             if (lane == 0) {
                 aio::mbar_expect_tx(bar, ent_bytes + self_bytes + (cnt > 0 ? (uint32_t)cnt * colbytes : 0u));
                 aio::bulk_g2s(ent_s, plan.ent + tile * kTileCells * k, ent_bytes, bar);
-                aio::bulk_g2s(self_s, plan.self + tile * kTileCells, self_bytes, bar);
+                aio::bulk_g2s(self_s, plan.self + tile * kTileSelf, self_bytes, bar);
             }
             __syncwarp();
-            for (int r = lane; r < cnt; r += 32) {
-                const int64_t row = plan.rows[tile * kTileCap + r];
-                aio::bulk_g2s(tile_s + (uint32_t)r * (kSlabCols * 4), S + row * ldS + col0, colbytes, bar);
+#pragma unroll
+            for (int j = 0; j < RPL; ++j) {
+                const int r = lane + 32 * j;
+                if (r < cnt) aio::bulk_g2s(tile_s + (uint32_t)r * (kSlabCols * 4), S + (int64_t)rows_cur[j] * ldS + col0, colbytes, bar);
             }
         }
         return;
@@ -444,12 +462,12 @@ spatial_obs_tile_kernel(const float* __restrict__ S, int64_t ldS, int k, TilePla
         const int64_t tile = wi - (int64_t)slab * ntiles;
         const int64_t col0 = (int64_t)slab * kSlabCols;
         const bool col_ok = col0 + quad * 4 < ldS;
-        const bool direct = plan.cnt[tile] < 0;
         aio::mbar_wait(full0 + 8 * st, ph);
         const unsigned char* stage = smem + st * stage_b;
         const float4* tile_s = reinterpret_cast<const float4*>(stage);
         const int2* ent_s = reinterpret_cast<const int2*>(stage + (size_t)kTileCap * kSlabCols * 4);
         const int32_t* self_s = reinterpret_cast<const int32_t*>(stage + (size_t)kTileCap * kSlabCols * 4 + ent_bytes);
+        const bool direct = self_s[kTileCells] < 0;
         float p_dot[4] = {0, 0, 0, 0}, p_ss[4] = {0, 0, 0, 0}, p_tt[4] = {0, 0, 0, 0}, p_s[4] = {0, 0, 0, 0};
         if (col_ok) {
 #pragma unroll
@@ -604,7 +622,7 @@ static int observed_stats_tiled(const float* S, int64_t ldS, int64_t n, int32_t 
     Scratch<double> partial(st);
     LARIS_CUDA(cnt.alloc((size_t)ntiles));
     LARIS_CUDA(rows.alloc((size_t)ntiles * kTileCap));
-    LARIS_CUDA(self.alloc((size_t)ntiles * kTileCells));
+    LARIS_CUDA(self.alloc((size_t)ntiles * kTileSelf));
     LARIS_CUDA(ent.alloc((size_t)ntiles * kTileCells * k));
     TilePlan plan{cnt.p, rows.p, ent.p, self.p};
     tile_plan_kernel<<<(unsigned)ntiles, 256, 0, st>>>(idx, w, k, order, n, plan);

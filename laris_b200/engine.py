@@ -364,7 +364,13 @@ def device_fingerprint_async(data_d):
     t = data_d[::stride].contiguous().view(torch.int32).sum(dtype=torch.int64).reshape(1)
     h = torch.empty(1, dtype=torch.int64, pin_memory=True)
     h.copy_(t, non_blocking=True)
-    return lambda: (nnz, int(h.item()))
+    done = torch.cuda.Event()
+    done.record()
+
+    def result():
+        done.synchronize()
+        return nnz, int(h.item())
+    return result
 
 
 def scores_to_csr_async(sm: ScoreMatrix, dtype=np.float32):

@@ -89,10 +89,10 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     else:
         graph = engine.build_radius_graph(xy, radius, True, None)
     csr_dev = join_upload()
+    expr_fp = engine.device_fingerprint_async(csr_dev[2])      # read lazily, at the first cache lookup
     xu, lig_c, rec_c = engine.select_lr_genes(adata.X, lig_g, rec_g, csr_dev=csr_dev, layout=layout,
                                               complexes=complexes, rule=complex_rule)
     sm = engine.lr_scores(xu, graph, lig_c, rec_c)
-    expr_fp = engine.device_fingerprint_async(csr_dev[2])
     finish = engine.scores_to_csr_async(sm, dtype) if to_host else None
     lr_names = (lr_df["ligand"].astype(str) + "::" + lr_df["receptor"].astype(str)).to_numpy(dtype=object)
     obs, var = adata.obs.copy(), pd.DataFrame(index=pd.Index(lr_names, dtype=object))
@@ -104,7 +104,7 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     else:
         from .._anndata import AnnDataLite
         lr_adata = AnnDataLite(_utils.ResidentScores(sm), obs, var, obsm)
-    _utils._remember_expression(adata.X, xu, expr_fp())
+    _utils._remember_expression(adata.X, xu, expr_fp)
     return lr_adata
 
 

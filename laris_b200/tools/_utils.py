@@ -70,7 +70,8 @@ def _expression_of(X, gene_idx):
     hit = _EXPR_CACHE.get(id(X))
     if hit is None or hit[0]() is not X or hit[2] != X.shape:
         return None
-    if hit[3] is not None and _fingerprint_host(X) != hit[3]:
+    want = hit[3]() if callable(hit[3]) else hit[3]          # device-side fingerprint, taken when X was uploaded
+    if want is not None and _fingerprint_host(X) != want:
         _EXPR_CACHE.pop(id(X), None)                       # edited in place since prepareLRInteraction
         return None
     xu = hit[1]
