@@ -10,6 +10,9 @@
 // fetched by one CTA is an L2 hit for the others (real graph).  For the random
 // graph every neighbour row is a fresh 4*P-byte HBM read - that pass is the
 // HBM-bound one: (1+k)*4*n*P + 8*n*k bytes.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "async.cuh"
 #include "common.cuh"
 #include "rng.cuh"
@@ -381,14 +384,15 @@ tile_plan_kernel(const int32_t* __restrict__ idx, const float* __restrict__ w, i
 
 struct TileSmem {
     static __host__ __device__ size_t stage_bytes(int k) {
-        return (size_t)kTileCap * kSlabCols * 4 + (size_t)kTileCells * k * 8 + (size_t)kTileSelf * 4;
+        return (((size_t)kTileCap * kSlabCols * 4 + (size_t)kTileCells * k * 8 + (size_t)kTileSelf * 4) + 127) & ~(size_t)127;
     }
     static __host__ __device__ size_t total(int k) { return 2 * stage_bytes(k) + 16 * 16 * 4 * 8 + 64; }
 };
 
 __global__ void __launch_bounds__(kTileThreads, 1)
 spatial_obs_tile_kernel(const float* __restrict__ S, int64_t ldS, int k, TilePlan plan, int64_t ntiles, int nslabs,
-                        int maxseg, double* __restrict__ partial, int32_t* __restrict__ rec_slab) {
+                        int maxseg, double* __restrict__ partial, int32_t* __restrict__ rec_slab,
+                        const __grid_constant__ CUtensorMap tmap, int gather4) {
     extern __shared__ __align__(128) unsigned char smem[];
     const size_t stage_b = TileSmem::stage_bytes(k);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -409,14 +413,17 @@ spatial_obs_tile_kernel(const float* __restrict__ S, int64_t ldS, int k, TilePla
         // ------------------------------ producer warp ------------------------------
         // The row list of the NEXT item is fetched (one batch of independent loads per lane) while this item's copies
         // are issued and the stage is awaited, so no global-load latency sits between two bulk copies.
-        constexpr int RPL = (kTileCap + 31) / 32;                               // rows per lane
-        int32_t rows_nx[RPL];
+        // gather4 != 0: rows travel four at a time through a 2-D tensor map of S (cp.async.bulk.tensor ... tile::gather4:
+        // one TMA operation gathers the 64-column pieces of four arbitrary rows); else one 1-D bulk copy per row.
+        constexpr int GPL = (kTileCap / 4 + 31) / 32;                           // row groups per lane
+        int4 rows_nx[GPL];
         int cnt_nx = 0;
         auto fetch = [&](int64_t wi) {
             const int64_t tile = wi % ntiles;
             cnt_nx = plan.cnt[tile];
+            const int4* rp = reinterpret_cast<const int4*>(plan.rows + tile * kTileCap);
 #pragma unroll
-            for (int j = 0; j < RPL; ++j) rows_nx[j] = lane + 32 * j < kTileCap ? plan.rows[tile * kTileCap + lane + 32 * j] : 0;
+            for (int j = 0; j < GPL; ++j) rows_nx[j] = lane + 32 * j < kTileCap / 4 ? rp[lane + 32 * j] : make_int4(0, 0, 0, 0);
         };
         if (w0 < w1) fetch(w0);
         for (int64_t wi = w0, it = 0; wi < w1; ++wi, ++it) {
@@ -424,10 +431,10 @@ spatial_obs_tile_kernel(const float* __restrict__ S, int64_t ldS, int k, TilePla
             const uint32_t ph = (uint32_t)((it >> 1) & 1);
             const int slab = (int)(wi / ntiles);
             const int64_t tile = wi - (int64_t)slab * ntiles;
-            int32_t rows_cur[RPL];
+            int4 rows_cur[GPL];
             const int cnt = cnt_nx;
 #pragma unroll
-            for (int j = 0; j < RPL; ++j) rows_cur[j] = rows_nx[j];
+            for (int j = 0; j < GPL; ++j) rows_cur[j] = rows_nx[j];
             if (wi + 1 < w1) fetch(wi + 1);
             aio::mbar_wait_sleep(empty0 + 8 * st, ph ^ 1u);
             unsigned char* stage = smem + st * stage_b;
@@ -436,16 +443,28 @@ spatial_obs_tile_kernel(const float* __restrict__ S, int64_t ldS, int k, TilePla
             const int64_t col0 = (int64_t)slab * kSlabCols;
             const uint32_t colbytes = (uint32_t)min((int64_t)kSlabCols, ldS - col0) * 4u;
             const uint32_t bar = full0 + 8 * st;
+            const int groups = cnt > 0 ? (cnt + 3) >> 2 : 0;
             if (lane == 0) {
-                aio::mbar_expect_tx(bar, ent_bytes + self_bytes + (cnt > 0 ? (uint32_t)cnt * colbytes : 0u));
+                const uint32_t row_bytes = gather4 ? (uint32_t)groups * (4u * kSlabCols * 4u) : (cnt > 0 ? (uint32_t)cnt * colbytes : 0u);
+                aio::mbar_expect_tx(bar, ent_bytes + self_bytes + row_bytes);
                 aio::bulk_g2s(ent_s, plan.ent + tile * kTileCells * k, ent_bytes, bar);
                 aio::bulk_g2s(self_s, plan.self + tile * kTileSelf, self_bytes, bar);
             }
             __syncwarp();
 #pragma unroll
-            for (int j = 0; j < RPL; ++j) {
-                const int r = lane + 32 * j;
-                if (r < cnt) aio::bulk_g2s(tile_s + (uint32_t)r * (kSlabCols * 4), S + (int64_t)rows_cur[j] * ldS + col0, colbytes, bar);
+            for (int j = 0; j < GPL; ++j) {
+                const int g = lane + 32 * j;
+                if (g >= groups) continue;
+                const int4 r4 = rows_cur[j];
+                const uint32_t dst = tile_s + (uint32_t)g * (4u * kSlabCols * 4u);
+                if (gather4) {
+                    aio::tma_gather4(dst, &tmap, (int)col0, r4.x, r4.y, r4.z, r4.w, bar);
+                } else {
+                    const int rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (4 * g + q < cnt) aio::bulk_g2s(dst + (uint32_t)q * (kSlabCols * 4), S + (int64_t)rr[q] * ldS + col0, colbytes, bar);
+                }
             }
         }
         return;
@@ -613,6 +632,38 @@ extern "C" int laris_null_graph_philox(int64_t n, int k, const float* w, int32_t
     return LARIS_OK;
 }
 
+// staging of the tile rows: 1 = TMA tile::gather4 through a tensor map (default), 0 = one 1-D bulk copy per row.
+// LARIS_B200_K4A_STAGING=bulk|gather4 overrides it (used to measure the two against each other).
+static int tile_staging_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("LARIS_B200_K4A_STAGING");
+        mode = (e && strcmp(e, "bulk") == 0) ? 0 : 1;
+    }
+    return mode;
+}
+
+static int encode_row_gather_map(CUtensorMap* tmap, const float* S, int64_t ldS, int64_t n) {
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return -1;
+        encode = (EncodeTiled)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)ldS, (cuuint64_t)n};
+    const cuuint64_t strides[1] = {(cuuint64_t)ldS * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kSlabCols, 1u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)S, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
+}
+
 // observed statistics through the staged-tile kernel -> out [5][P]
 static int observed_stats_tiled(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* idx, const float* w, int k,
                                 const int32_t* order, double* out, cudaStream_t st) {
@@ -640,7 +691,17 @@ static int observed_stats_tiled(const float* S, int64_t ldS, int64_t n, int32_t 
     LARIS_CUDA(cudaMemsetAsync(rec_slab.p, 0xff, sizeof(int32_t) * (size_t)nrec, st));
     const size_t smem = TileSmem::total(k);
     LARIS_CUDA(cudaFuncSetAttribute(spatial_obs_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    spatial_obs_tile_kernel<<<grid, kTileThreads, smem, st>>>(S, ldS, k, plan, ntiles, nslabs, maxseg, partial.p, rec_slab.p);
+    // 2-D tensor map of S for the gather4 staging: [n rows][ldS columns] fp32, box = 64 columns x 1 row (four rows per
+    // operation come from the instruction's four row coordinates); columns past ldS are zero-filled by the TMA engine
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int gather4 = tile_staging_mode();
+    if (gather4) {
+        const int rc = encode_row_gather_map(&tmap, S, ldS, n);
+        if (rc) gather4 = 0;                                      // driver without tensor-map support: 1-D bulk copies
+    }
+    spatial_obs_tile_kernel<<<grid, kTileThreads, smem, st>>>(S, ldS, k, plan, ntiles, nslabs, maxseg, partial.p, rec_slab.p,
+                                                              tmap, gather4);
     LARIS_LAUNCH_CHECK();
     tile_records_reduce_kernel<<<nslabs, 5 * kSlabCols, 0, st>>>(partial.p, rec_slab.p, nrec, P, out);
     LARIS_LAUNCH_CHECK();

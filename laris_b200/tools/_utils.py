@@ -578,14 +578,15 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
     rec = laris_lr["receptor"].to_numpy(dtype=object)
     sp_score = laris_lr["score"].to_numpy(dtype=np.float64)
     inter_names = np.array([f"{l}::{r}" for l, r in zip(lig, rec)], dtype=object)
-    keep = np.isin(lig, spec.index) & np.isin(rec, spec.index)
+    spec_index = pd.Index(spec.index)
+    keep = (spec_index.get_indexer(lig) >= 0) & (spec_index.get_indexer(rec) >= 0)
     lig, rec, sp_score, inter_names = lig[keep], rec[keep], sp_score[keep], inter_names[keep]
     if len(lig) == 0:
         return pd.DataFrame(columns=cols6)
     pair_id = pd.Index(lr_names).get_indexer(inter_names)
     if (pair_id < 0).any():
         raise KeyError(f"interactions not found in lr_adata.var_names: {list(inter_names[pair_id < 0][:5])}")
-    gene_row = pd.Index(spec.index).get_indexer
+    gene_row = spec_index.get_indexer
     spec_m = spec.to_numpy(dtype=np.float64)
     with np.errstate(invalid="ignore"):
         factor = np.ones_like(sp_score) if spatial_weight == 0 else np.power(sp_score, spatial_weight)
