@@ -157,19 +157,26 @@ def iqr_log_normalize(df, q_upper=0.95, q_lower=0.75):
     cosg = real_cosg()
     if cosg is not None:
         return cosg.iqrLogNormalize(df)
-    v = df.to_numpy(dtype=np.float64)
+    return pd.DataFrame(iqr_log_normalize_array(df.to_numpy(dtype=np.float64), q_upper, q_lower), index=df.index,
+                        columns=df.columns)
+
+
+def iqr_log_normalize_array(v, q_upper=0.95, q_lower=0.75):
+    """The stand-in above on a plain [rows, columns] fp64 array."""
+    v = np.asarray(v, dtype=np.float64)
     out = np.zeros_like(v)
     for j in range(v.shape[1]):
         col = v[:, j]
         pos = col[col > 0]
         if pos.size == 0:
             continue
-        scale = np.quantile(pos, q_upper) - np.quantile(pos, q_lower)
+        qu, ql = np.quantile(pos, [q_upper, q_lower])
+        scale = qu - ql
         if not scale > 0:
             scale = pos.max()
         y = np.log1p(np.maximum(col, 0.0) / scale)
         out[:, j] = y / np.log1p(pos.max() / scale)
-    return pd.DataFrame(out, index=df.index, columns=df.columns)
+    return out
 
 
 _WARNED = False

@@ -38,6 +38,7 @@ class SpatialGraph:
         return self.idx.shape[1]
 
     csr: tuple | None = None   # radius graphs: (indptr int64, indices int32, dist fp64, w64 fp64) on the device
+    xy: torch.Tensor | None = None   # the coordinates the search ran on (device), for re-use by a later graph
 
     def to_scipy(self):
         """The reference's ``cellxcell`` (n x n CSR, fp64 weights, int64 indices)."""
@@ -65,12 +66,20 @@ def _coords_to_device(xy):
     return xy_d
 
 
-def build_graph(xy, k, include_self, sigma=None) -> SpatialGraph:
-    """kNN graph + decay weights (K1).  ``sigma=None`` -> s = mean(d)/2."""
-    xy_d = _coords_to_device(xy)
-    idx, dist, order = K.knn_graph(xy_d.contiguous(), int(k), include_self)
+def build_graph(xy, k, include_self, sigma=None, like: SpatialGraph | None = None) -> SpatialGraph:
+    """kNN graph + decay weights (K1).  ``sigma=None`` -> s = mean(d)/2.  ``like``: a graph built earlier in the same
+    run; when it was searched with the same k / self rule over the SAME coordinates (compared on the device), its
+    neighbour lists are re-used and only the weights are recomputed (runLARIS builds two graphs that differ only in
+    the decay rule, reference laris/tools/_utils.py:383-394 and :846-853)."""
+    xy_d = _coords_to_device(xy).contiguous()
+    if (like is not None and like.xy is not None and like.csr is None and like.k == int(k)
+            and like.include_self == bool(include_self) and like.xy.shape == xy_d.shape and like.xy.dtype == xy_d.dtype
+            and (like.xy.data_ptr() == xy_d.data_ptr() or bool(torch.equal(like.xy, xy_d)))):
+        idx, dist, order = like.idx, like.dist, like.order
+    else:
+        idx, dist, order = K.knn_graph(xy_d, int(k), include_self)
     w32, w64, scale = K.decay_weights(dist, sigma, want64=True)
-    return SpatialGraph(idx, dist, w32, w64, order, scale, bool(include_self))
+    return SpatialGraph(idx, dist, w32, w64, order, scale, bool(include_self), xy=xy_d)
 
 
 def build_radius_graph(xy, radius, include_self, sigma=None) -> SpatialGraph:

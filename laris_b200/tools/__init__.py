@@ -159,6 +159,7 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     # observed statistics + all null repeats: one device tensor [1+R, 5, P_local], one gather, one download
     st_d, rng_state = engine.spatial_stats_all(sm, graph, n_repeats, random_seed, rng)
     sm.cache["stats_d"] = st_d[0]
+    sm.cache["graph"] = graph                 # the cell-type step re-uses the neighbour search when it can
     st_local = None
     if shard is not None:
         st_local = st_d[0].cpu().numpy()

@@ -303,6 +303,21 @@ def _cosg_table(names, score, cats):
     return cosg_compat.iqr_log_normalize(table)
 
 
+def _gene_cosg_scores(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_expressed):
+    """Raw COSG scores [len(lr_set), C] of the named genes (``cosg.cosg`` semantics, -1 = lowly expressed), on the
+    device; re-uses the packed LR-gene rows prepareLRInteraction left resident when they cover the genes."""
+    codes, cats = _group_codes(adata.obs[groupby])
+    n_c = np.bincount(codes, minlength=len(cats))
+    gene_idx = _gene_columns(adata, lr_set)
+    labels_d = K.to_device(codes, torch.int32)
+    hit = _expression_of(adata.X, gene_idx)
+    if hit is not None:
+        xu, rows = hit
+        return engine.cosg_gene_scores(xu, labels_d, len(cats), n_c, mu, expressed_pct, remove_lowly_expressed)[rows], cats
+    xu = engine.select_genes(adata.X, gene_idx)
+    return engine.cosg_gene_scores(xu, labels_d, len(cats), n_c, mu, expressed_pct, remove_lowly_expressed), cats
+
+
 def _calculate_ligand_receptor_specificity(adata, laris_lr, groupby: str = "CellTypes", mu: float = 100,
                                            expressed_pct: float = 0.1, remove_lowly_expressed: bool = True,
                                            mask_threshold: float = 1e-6):
@@ -312,19 +327,24 @@ def _calculate_ligand_receptor_specificity(adata, laris_lr, groupby: str = "Cell
     COSG score runs on the device; the two reshaping helpers come from the real
     ``cosg`` when importable, else from laris_b200.cosg_compat (parity unpinned)."""
     lr_set = np.unique(np.hstack([laris_lr["ligand"].values, laris_lr["receptor"].values]))
-    codes, cats = _group_codes(adata.obs[groupby])
-    n_c = np.bincount(codes, minlength=len(cats))
-    gene_idx = _gene_columns(adata, lr_set)
-    hit = _expression_of(adata.X, gene_idx)
-    if hit is not None:                    # rows of the LR genes are still on the device from prepareLRInteraction
-        xu, rows = hit
-        score = engine.cosg_gene_scores(xu, K.to_device(codes, torch.int32), len(cats), n_c, mu, expressed_pct,
-                                        remove_lowly_expressed)[rows]
-    else:
-        xu = engine.select_genes(adata.X, gene_idx)
-        score = engine.cosg_gene_scores(xu, K.to_device(codes, torch.int32), len(cats), n_c, mu, expressed_pct,
-                                        remove_lowly_expressed)
+    score, cats = _gene_cosg_scores(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_expressed)
     return _cosg_table(lr_set, score, cats)
+
+
+def _specificity_rows(adata, laris_lr, groupby, mu, expressed_pct, remove_lowly_expressed, mask_threshold):
+    """What ``_calculate_laris_score_by_celltype`` needs of the table above: (gene names, [genes, C] fp64 matrix with the
+    columns in category order).  With the real ``cosg`` it IS the table above; with the stand-ins the ranked frame and
+    its pivot are skipped - normalising the score matrix column by column gives the same numbers."""
+    if cosg_compat.real_cosg() is not None:
+        spec = _calculate_ligand_receptor_specificity(adata, laris_lr, groupby, mu, expressed_pct, remove_lowly_expressed,
+                                                      mask_threshold)
+        cats = list(_group_codes(adata.obs[groupby])[1])
+        spec = spec.loc[:, cats] if list(spec.columns) != cats else spec
+        return np.asarray(spec.index, dtype=object), spec.to_numpy(dtype=np.float64)
+    lr_set = np.unique(np.hstack([laris_lr["ligand"].values, laris_lr["receptor"].values]))
+    score, _ = _gene_cosg_scores(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_expressed)
+    table = np.nan_to_num(np.where(score == -1, 0.0, score), nan=0.0)          # indexByGene(set_nan_to_zero, -1 -> 0)
+    return lr_set, cosg_compat.iqr_log_normalize_array(table)
 
 
 def _calculate_diffused_lr_specificity(lr_adata, groupby: str = "CellTypes", mu: float = 100, expressed_pct: float = 0.05,
@@ -368,7 +388,8 @@ def _neighborhood_tables(adata, lr_adata, groupby, use_rep_spatial, number_neare
     C = len(cats)
     sm = _scores_of(lr_adata)
     if radius is None:
-        graph = engine.build_graph(_coords(adata, use_rep_spatial), number_nearest_neighbors, False, None)
+        graph = engine.build_graph(_coords(adata, use_rep_spatial), number_nearest_neighbors, False, None,
+                                   like=sm.cache.get("graph"))
     else:
         graph = engine.build_radius_graph(_coords(adata, use_rep_spatial), radius, False, None)
     labels_d = K.to_device(codes, torch.int32)
@@ -561,9 +582,8 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
     _log(verbose, "\n--- Step 1: Calculating ligand and receptor cell type specificity ---")
     if len(laris_lr) == 0:
         return pd.DataFrame(columns=cols6)
-    spec = _calculate_ligand_receptor_specificity(adata, laris_lr, groupby, mu, expressed_pct, remove_lowly_expressed,
-                                                  mask_threshold)
-    spec = spec.loc[:, cats] if list(spec.columns) != list(cats) else spec
+    spec_genes, spec_m = _specificity_rows(adata, laris_lr, groupby, mu, expressed_pct, remove_lowly_expressed,
+                                           mask_threshold)
 
     # ---- step 2: cells with a non-zero score per type (reference :1325-1337), counts stay on the device ----
     _log(verbose, "\n--- Step 2: Calculating diffused LR-score distribution ---")
@@ -578,7 +598,7 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
     rec = laris_lr["receptor"].to_numpy(dtype=object)
     sp_score = laris_lr["score"].to_numpy(dtype=np.float64)
     inter_names = np.array([f"{l}::{r}" for l, r in zip(lig, rec)], dtype=object)
-    spec_index = pd.Index(spec.index)
+    spec_index = pd.Index(spec_genes)
     keep = (spec_index.get_indexer(lig) >= 0) & (spec_index.get_indexer(rec) >= 0)
     lig, rec, sp_score, inter_names = lig[keep], rec[keep], sp_score[keep], inter_names[keep]
     if len(lig) == 0:
@@ -587,7 +607,6 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
     if (pair_id < 0).any():
         raise KeyError(f"interactions not found in lr_adata.var_names: {list(inter_names[pair_id < 0][:5])}")
     gene_row = spec_index.get_indexer
-    spec_m = spec.to_numpy(dtype=np.float64)
     with np.errstate(invalid="ignore"):
         factor = np.ones_like(sp_score) if spatial_weight == 0 else np.power(sp_score, spatial_weight)
     npair = len(lig)
