@@ -415,20 +415,78 @@ def _normalise_table_device(raw_d):
     return K.to_device(np.ascontiguousarray(host.to_numpy(dtype=np.float64)), torch.float64)
 
 
+class _LazyRankedGroups(dict):
+    """``lr_adata.uns[key]`` of the neighbourhood-specificity step in the reference's layout (reference :886-968):
+    ``params`` plus, ranked per sender::receiver column by descending score, the ``COSG`` frame
+    (``names@@g`` / ``scores@@g`` columns) and the ``names`` / ``scores`` record arrays.  The 2 * C^2 ranked columns
+    of P entries each (3200 columns at 40 cell types) are only BUILT when one of those keys is first read - most
+    runs never look at them, and building them eagerly cost a third of a whole 1e6-cell run.  It is a real dict
+    afterwards: iteration, ``in``, ``keys()``, copying and pickling all see the materialised entries."""
+    _LAZY = ("COSG", "names", "scores")
+
+    def __init__(self, params, raw, lr_names, pair_names, return_by_group, delimiter):
+        super().__init__(params=params)
+        self._pending = (raw, lr_names, pair_names, return_by_group, delimiter)
+
+    def _materialise(self):
+        if self._pending is None:
+            return
+        raw, lr_names, pair_names, return_by_group, delimiter = self._pending
+        self._pending = None
+        frame, order = cosg_compat.ranked_frame(lr_names, raw, pair_names, delimiter)
+        if return_by_group:
+            dict.__setitem__(self, "COSG", frame)
+        L = len(pair_names)
+        dict.__setitem__(self, "names", np.rec.fromarrays([lr_names[order[:, j]] for j in range(L)],
+                                                          dtype=[(nm, "O") for nm in pair_names]))
+        dict.__setitem__(self, "scores", np.rec.fromarrays([raw[order[:, j], j].astype(np.float32) for j in range(L)],
+                                                           dtype=[(nm, "float32") for nm in pair_names]))
+
+    def __getitem__(self, key):
+        if key in self._LAZY:
+            self._materialise()
+        return dict.__getitem__(self, key)
+
+    def get(self, key, default=None):
+        if key in self._LAZY:
+            self._materialise()
+        return dict.get(self, key, default)
+
+    def __contains__(self, key):
+        self._materialise()
+        return dict.__contains__(self, key)
+
+    def __iter__(self):
+        self._materialise()
+        return dict.__iter__(self)
+
+    def __len__(self):
+        self._materialise()
+        return dict.__len__(self)
+
+    def keys(self):
+        self._materialise()
+        return dict.keys(self)
+
+    def items(self):
+        self._materialise()
+        return dict.items(self)
+
+    def values(self):
+        self._materialise()
+        return dict.values(self)
+
+    def __reduce__(self):                    # copy / deepcopy / pickle: a plain dict of the materialised entries
+        self._materialise()
+        return (dict, (dict(self),))
+
+
 def _store_neighborhood_uns(lr_adata, key_added, groupby, mu, raw, lr_names, pair_names, return_by_group,
                             column_delimiter):
     """``lr_adata.uns[key_added]`` in the reference's layout (params / COSG frame / names + scores recarrays,
-    reference :886-968): every column ranked by descending score."""
-    frame, order = cosg_compat.ranked_frame(lr_names, raw, pair_names, column_delimiter)
-    lr_adata.uns[key_added] = {"params": dict(groupby=groupby, method="COSG", mu=mu)}
-    if return_by_group:
-        lr_adata.uns[key_added]["COSG"] = frame
-    L = len(pair_names)
-    lr_adata.uns[key_added]["names"] = np.rec.fromarrays([lr_names[order[:, j]] for j in range(L)],
-                                                         dtype=[(nm, "O") for nm in pair_names])
-    lr_adata.uns[key_added]["scores"] = np.rec.fromarrays([raw[order[:, j], j].astype(np.float32) for j in range(L)],
-                                                          dtype=[(nm, "float32") for nm in pair_names])
-    return frame, order
+    reference :886-968), ranked lazily (see ``_LazyRankedGroups``)."""
+    lr_adata.uns[key_added] = _LazyRankedGroups(dict(groupby=groupby, method="COSG", mu=mu), raw, lr_names, pair_names,
+                                                return_by_group, column_delimiter)
 
 
 def _calculate_specificity_in_spatial_neighborhood(adata, lr_adata, groupby: str = "CellTypes",
@@ -446,13 +504,14 @@ def _calculate_specificity_in_spatial_neighborhood(adata, lr_adata, groupby: str
     if key_added is None:
         key_added = "cosg"
     raw = raw_d.cpu().numpy()
-    frame, order = _store_neighborhood_uns(lr_adata, key_added, groupby, mu, raw, lr_names, pair_names, return_by_group,
-                                           column_delimiter)
+    _store_neighborhood_uns(lr_adata, key_added, groupby, mu, raw, lr_names, pair_names, return_by_group, column_delimiter)
     if cosg_compat.real_cosg() is not None:
+        frame, order = cosg_compat.ranked_frame(lr_names, raw, pair_names, column_delimiter)
         table = cosg_compat.index_by_gene_of_ranking(frame, lr_names, raw, pair_names, order,
                                                      column_delimiter=column_delimiter)
         return cosg_compat.iqr_log_normalize(table)
-    rows = order[:, 0] if len(pair_names) else np.arange(len(lr_names))     # indexByGene: first-appearance order
+    # indexByGene keeps first-appearance order = the ranking of the first column
+    rows = np.argsort(raw[:, 0], kind="stable")[::-1] if len(pair_names) else np.arange(len(lr_names))
     norm = _normalise_table_device(raw_d).cpu().numpy()
     return pd.DataFrame(norm[rows], index=pd.Index(lr_names[rows], dtype=object), columns=list(pair_names))
 
