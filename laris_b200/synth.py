@@ -100,6 +100,28 @@ def make_expression(c: SynthConfig, labels: np.ndarray, rng, chunk: int = 65536)
     return X
 
 
+_FAST_VALUES = np.log1p(1.0 + np.arange(16, dtype=np.float64)).astype(np.float32)
+
+
+def make_expression_fast(c: SynthConfig, rng) -> sp.csr_matrix:
+    """A cheaper generator for the full-size parity tests of configs 3-5 (tens of seconds instead of minutes): the
+    non-zeros of the n x G matrix are placed by geometric gaps over the row-major index space (uniform density
+    ``c.density``, no cell-type modulation), values from a 16-entry table of log1p counts.  Canonical CSR."""
+    total = c.n * c.G
+    m = int(total * c.density * 1.02) + 4096
+    pos = np.cumsum(rng.geometric(c.density, m), dtype=np.int64) - 1
+    pos = pos[: np.searchsorted(pos, total)]
+    rows, cols = np.divmod(pos, c.G)
+    del pos
+    indptr = np.zeros(c.n + 1, dtype=np.int64)
+    np.cumsum(np.bincount(rows, minlength=c.n), out=indptr[1:])
+    del rows
+    vals = _FAST_VALUES[rng.integers(0, 16, len(cols), dtype=np.uint8)]
+    X = sp.csr_matrix((vals, cols.astype(np.int32), indptr), shape=(c.n, c.G))
+    X.has_sorted_indices = True
+    return X
+
+
 def make_lr_table(c: SynthConfig, rng) -> pd.DataFrame:
     """P distinct (ligand, receptor) rows over the first G_u genes.
 
@@ -128,13 +150,14 @@ def gene_names(G: int) -> np.ndarray:
     return np.array([f"g{g:05d}" for g in range(G)], dtype=object)
 
 
-def make_dataset(cfg: int, n: int | None = None, seed: int | None = None, **over):
-    """Return ``(adata, lr_df, config)`` for BASELINE config ``cfg``."""
+def make_dataset(cfg: int, n: int | None = None, seed: int | None = None, fast: bool = False, **over):
+    """Return ``(adata, lr_df, config)`` for BASELINE config ``cfg``.  ``fast=True`` swaps the expression generator
+    for ``make_expression_fast`` (different bytes, same shape / density; used by the full-size parity tests)."""
     c = scaled(cfg, n, **over)
     rng = np.random.default_rng(1000 + cfg if seed is None else seed)
     xy = make_coords(c, rng)
     labels = make_labels(c, xy, rng)
-    X = make_expression(c, labels, rng)
+    X = make_expression_fast(c, rng) if fast else make_expression(c, labels, rng)
     lr_df = make_lr_table(c, rng)
     cats = [f"ct{t:02d}" for t in range(c.C)]
     obs = pd.DataFrame(

@@ -303,19 +303,40 @@ def _cosg_table(names, score, cats):
     return cosg_compat.iqr_log_normalize(table)
 
 
-def _gene_cosg_scores(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_expressed):
+def _gene_cosg_scores(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_expressed, shard=None):
     """Raw COSG scores [len(lr_set), C] of the named genes (``cosg.cosg`` semantics, -1 = lowly expressed), on the
-    device; re-uses the packed LR-gene rows prepareLRInteraction left resident when they cover the genes."""
+    device; re-uses the packed LR-gene rows prepareLRInteraction left resident when they cover the genes.
+
+    Sharded run: a rank only holds the genes of its own pair block.  Every gene is scored by its OWNER - the lowest
+    rank whose pairs use it, which every rank can work out from the global pair names - and the rows are summed
+    over the ranks (each row has exactly one non-zero contributor)."""
     codes, cats = _group_codes(adata.obs[groupby])
     n_c = np.bincount(codes, minlength=len(cats))
-    gene_idx = _gene_columns(adata, lr_set)
     labels_d = K.to_device(codes, torch.int32)
-    hit = _expression_of(adata.X, gene_idx)
-    if hit is not None:
-        xu, rows = hit
-        return engine.cosg_gene_scores(xu, labels_d, len(cats), n_c, mu, expressed_pct, remove_lowly_expressed)[rows], cats
-    xu = engine.select_genes(adata.X, gene_idx)
-    return engine.cosg_gene_scores(xu, labels_d, len(cats), n_c, mu, expressed_pct, remove_lowly_expressed), cats
+    lr_set = np.asarray(lr_set, dtype=object)
+    mine = np.ones(len(lr_set), dtype=bool)
+    if shard is not None:
+        owner = {}
+        b = shard.bounds
+        for r in range(shard.world - 1, -1, -1):                          # descending: the lowest rank wins
+            for nm in shard.names_global[int(b[r]):int(b[r + 1])]:
+                lig, rec = nm.split("::")
+                owner[lig] = r
+                owner[rec] = r
+        mine = np.array([owner.get(g, 0) == shard.rank for g in lr_set], dtype=bool)
+    score = np.zeros((len(lr_set), len(cats)))
+    if mine.any():
+        gene_idx = _gene_columns(adata, lr_set[mine])
+        hit = _expression_of(adata.X, gene_idx)
+        if hit is not None:
+            xu, rows = hit
+            score[mine] = engine.cosg_gene_scores(xu, labels_d, len(cats), n_c, mu, expressed_pct, remove_lowly_expressed)[rows]
+        else:
+            xu = engine.select_genes(adata.X, gene_idx)
+            score[mine] = engine.cosg_gene_scores(xu, labels_d, len(cats), n_c, mu, expressed_pct, remove_lowly_expressed)
+    if shard is not None:
+        score = _dist.all_reduce_sum(score)
+    return score, cats
 
 
 def _calculate_ligand_receptor_specificity(adata, laris_lr, groupby: str = "CellTypes", mu: float = 100,
@@ -331,18 +352,19 @@ def _calculate_ligand_receptor_specificity(adata, laris_lr, groupby: str = "Cell
     return _cosg_table(lr_set, score, cats)
 
 
-def _specificity_rows(adata, laris_lr, groupby, mu, expressed_pct, remove_lowly_expressed, mask_threshold):
+def _specificity_rows(adata, laris_lr, groupby, mu, expressed_pct, remove_lowly_expressed, mask_threshold, shard=None):
     """What ``_calculate_laris_score_by_celltype`` needs of the table above: (gene names, [genes, C] fp64 matrix with the
     columns in category order).  With the real ``cosg`` it IS the table above; with the stand-ins the ranked frame and
     its pivot are skipped - normalising the score matrix column by column gives the same numbers."""
     if cosg_compat.real_cosg() is not None:
-        spec = _calculate_ligand_receptor_specificity(adata, laris_lr, groupby, mu, expressed_pct, remove_lowly_expressed,
-                                                      mask_threshold)
-        cats = list(_group_codes(adata.obs[groupby])[1])
+        lr_set = np.unique(np.hstack([laris_lr["ligand"].values, laris_lr["receptor"].values]))
+        score, cats = _gene_cosg_scores(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_expressed, shard)
+        spec = _cosg_table(lr_set, score, cats)
+        cats = list(cats)
         spec = spec.loc[:, cats] if list(spec.columns) != cats else spec
         return np.asarray(spec.index, dtype=object), spec.to_numpy(dtype=np.float64)
     lr_set = np.unique(np.hstack([laris_lr["ligand"].values, laris_lr["receptor"].values]))
-    score, _ = _gene_cosg_scores(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_expressed)
+    score, _ = _gene_cosg_scores(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_expressed, shard)
     table = np.nan_to_num(np.where(score == -1, 0.0, score), nan=0.0)          # indexByGene(set_nan_to_zero, -1 -> 0)
     return lr_set, cosg_compat.iqr_log_normalize_array(table)
 
@@ -642,7 +664,7 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
     if len(laris_lr) == 0:
         return pd.DataFrame(columns=cols6)
     spec_genes, spec_m = _specificity_rows(adata, laris_lr, groupby, mu, expressed_pct, remove_lowly_expressed,
-                                           mask_threshold)
+                                           mask_threshold, shard)
 
     # ---- step 2: cells with a non-zero score per type (reference :1325-1337), counts stay on the device ----
     _log(verbose, "\n--- Step 2: Calculating diffused LR-score distribution ---")
