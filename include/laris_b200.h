@@ -282,6 +282,20 @@ LARIS_API int laris_celltype_pair_contract_sparse(const float* S, int64_t ldS, i
                                                   void* stream);
 LARIS_API int laris_pair_profile_norm(const float* Ncomp, int64_t n, int32_t C, double* qnorm2, void* stream);
 
+/* ------------------------------------ label-permutation null (extension) ----
+ * North-star item 4 names a "label permutation null"; the reference has none (its nulls are the random graph,
+ * laris/tools/_utils.py:436-446, and the background-pair resampling, :1544-1570).  Extension with its own CPU oracle
+ * (oracle/restate.py: label_permutation_null): permutation t relabels the cells with a keyed bijection of [0, n)
+ * (the Feistel network of the K4b weight shuffle, key stream 0x40000000 + t, bit-exact numpy twin in oracle/rng.py),
+ * the neighbourhood composition and the P x C^2 co-localisation cosines are recomputed, and
+ * ge[p,(a,b)] counts cos_t >= cos_observed.  Relabelled neighbourhoods are maximally mixed, i.e. the B operand of the
+ * contraction is dense: this is the workload the tcgen05 kernel (laris_celltype_pair_contract impl 0) is for.
+ *   laris_permute_labels: out[i] = labels[pi_t(i)]
+ *   laris_count_exceed:   ge[e] += val[e] >= obs[e]   (fp64 tables of `total` entries, int32 counts) */
+LARIS_API int laris_permute_labels(const int32_t* labels, int64_t n, int32_t permutation, uint64_t seed, int32_t* out,
+                                   void* stream);
+LARIS_API int laris_count_exceed(const double* obs, const double* val, int64_t total, int32_t* ge, void* stream);
+
 /* ---------------------------------------------------------------- K6 ----
  * Exceedance counts of the background-resampling null
  * (laris/tools/_utils.py:1518-1596).  Row r = (group g, pair s), s over ALL pairs:

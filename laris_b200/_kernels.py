@@ -510,3 +510,18 @@ def gather_result_rows(p_tab, fdr_tab, pair_id):
     check(lib.laris_gather_result_rows(_ptr(p_tab, torch.float64), _ptr(fdr_tab, torch.float64), _ptr(pair_id, torch.int32),
                                        Pt, P, L, *[_ptr(o) for o in outs], _stream()), "laris_gather_result_rows")
     return outs
+
+
+# ------------------------------------------- label-permutation null (extension) ----
+@_staged("label null: permute")
+def permute_labels(labels, permutation, seed):
+    out = torch.empty_like(labels)
+    check(lib.laris_permute_labels(_ptr(labels, torch.int32), labels.numel(), int(permutation), int(seed) & (2 ** 64 - 1),
+                                   _ptr(out), _stream()), "laris_permute_labels")
+    return out
+
+
+def count_exceed(obs, val, ge):
+    check(lib.laris_count_exceed(_ptr(obs, torch.float64), _ptr(val, torch.float64), obs.numel(), _ptr(ge, torch.int32),
+                                 _stream()), "laris_count_exceed")
+    return ge

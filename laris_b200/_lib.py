@@ -52,6 +52,8 @@ SIGNATURES = {
     "laris_celltype_pair_keys": [_p, _i64, _i, _p, _p],
     "laris_celltype_pair_contract_sparse": [_p, _i64, _i64, _i, _p, _i, _p, _i64, _p, _p],
     "laris_pair_profile_norm": [_p, _i64, _i, _p, _p],
+    "laris_permute_labels": [_p, _i64, _i, _u64, _p, _p],
+    "laris_count_exceed": [_p, _p, _i64, _p, _p],
     "laris_celltype_nonzero_count": [_p, _i64, _i64, _i, _p, _i, _p, _p],
     "laris_onehot_contract_csr": [_p, _p, _i64, _i, _p, _i, _p, _p, _p, _p],
     "laris_onehot_contract_rows": [_p, _p, _p, _i64, _i, _p, _i, _p, _p, _p, _p],

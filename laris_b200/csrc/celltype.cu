@@ -5,6 +5,7 @@
 //   celltype_pair_contract    num[p,(a,b)] = sum_i S[i,p] N[i,a] N[i,b]   (fp32 CUDA-core tiles; the
 //                             tcgen05 variant lives in celltype_mma.cu)
 #include "common.cuh"
+#include "rng.cuh"
 #include "scan.cuh"
 
 namespace laris {
@@ -275,6 +276,23 @@ extern "C" int laris_onehot_contract_rows(const int64_t* row_start, const int64_
 namespace laris {
 int celltype_pair_contract_mma(const float* S, int64_t ldS, int64_t n, int32_t P, const float* Ncomp, int32_t C,
                                const int32_t* order, double* num, cudaStream_t st);   // celltype_mma.cu
+}
+
+// ---- label-permutation null (extension): labels_out[i] = labels[pi_t(i)], pi_t a keyed Feistel bijection of [0, n)
+namespace laris {
+__global__ void permute_labels_kernel(const int32_t* __restrict__ labels, int64_t n, FeistelKeys fk, int32_t* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = labels[feistel_perm((uint64_t)i, (uint64_t)n, fk)];
+}
+}  // namespace laris
+
+extern "C" int laris_permute_labels(const int32_t* labels, int64_t n, int32_t permutation, uint64_t seed, int32_t* out,
+                                    void* stream) {
+    LARIS_CHECK_ARG(labels && out && n > 0 && permutation >= 0, "laris_permute_labels: bad arguments");
+    const FeistelKeys fk = make_feistel_keys((uint64_t)n, kLabelPermBase + (uint32_t)permutation, seed);
+    permute_labels_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(labels, n, fk, out);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
 }
 
 extern "C" int laris_pair_profile_norm(const float* Ncomp, int64_t n, int32_t C, double* qnorm2, void* stream) {

@@ -40,6 +40,8 @@ __host__ __device__ __forceinline__ uint32_t fmix32(uint32_t x) {
     return x;
 }
 
+constexpr uint32_t kLabelPermBase = 0x40000000u;      // permutation ids of the label-permutation null (K4b repeats count from 0)
+
 struct FeistelKeys { uint32_t k[kFeistelRounds]; uint32_t half_bits; };
 
 inline FeistelKeys make_feistel_keys(uint64_t m, uint32_t repeat, uint64_t seed) {

@@ -332,9 +332,24 @@ __global__ void gather_rows_kernel(const double* __restrict__ p_tab, const doubl
     nlog_rows[e] = fmax(-log10(f + 1e-10), 0.0);
 }
 
+// exceedance counts of a permutation null over a table: ge[e] += (val[e] >= obs[e])
+__global__ void count_exceed_kernel(const double* __restrict__ obs, const double* __restrict__ val, int64_t total,
+                                    int32_t* __restrict__ ge) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e < total && val[e] >= obs[e]) ge[e] += 1;
+}
+
 }  // namespace laris
 
 using namespace laris;
+
+extern "C" int laris_count_exceed(const double* obs, const double* val, int64_t total, int32_t* ge, void* stream) {
+    LARIS_CHECK_ARG(obs && val && ge && total >= 0, "laris_count_exceed: bad arguments");
+    if (total == 0) return LARIS_OK;
+    count_exceed_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(obs, val, total, ge);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
 
 extern "C" int laris_pair_cosine_regularise(const double* num, const double* ss, const double* qn2, int32_t P, int32_t L,
                                             double mu, double* cos_out, double* reg_out, void* stream) {

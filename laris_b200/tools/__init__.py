@@ -117,7 +117,7 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
              layer_celltype=None, n_neighbors_permutation: int = 30, n_permutations: int = 1000, chunk_size: int = 50000,
              prefilter_fdr: bool = True, prefilter_threshold: float = 0.0, score_threshold: float = 1e-6,
              spatial_weight: float = 1.0, use_conditional_pvalue: bool = False, *, rng: str = "numpy",
-             verbose: bool = True, contract_impl=None, radius=None, output: str = "frames"):
+             verbose: bool = True, contract_impl=None, radius=None, output: str = "frames", label_permutations: int = 0):
     """Spatially-specific LR pairs and (optionally) the cell-type interaction table.
 
     Reference laris/tools/__init__.py:121-593, same arguments and returns
@@ -133,6 +133,9 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     degree varies.  ``output='arrays'`` (extension): skip the materialisation of the results - the per-cell QC
     columns, ``uns['cosg_lr']`` and the sorted long DataFrame - and return the cell-type step as a dict of device
     tensors ([pair, sender*C + receiver] layout); the ranking DataFrame and the ``var`` columns are still written.
+    ``label_permutations=T`` (extension, default 0 = the reference's behaviour): additionally relabel the cells T times
+    and add ``p_value_label_null`` - the label-permutation p-value of the row's co-localisation cosine
+    (``labelPermutationNull``).
     """
     if by_celltype and adata is None:
         raise ValueError("Parameter 'adata' must be provided when by_celltype=True. "
@@ -225,10 +228,25 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
         n_permutations=n_permutations, chunk_size=chunk_size, prefilter_fdr=prefilter_fdr,
         prefilter_threshold=prefilter_threshold, score_threshold=score_threshold, spatial_weight=spatial_weight,
         use_conditional_pvalue=use_conditional_pvalue, rng=rng, random_seed=random_seed, rng_state=rng_state,
-        verbose=verbose, contract_impl=contract_impl, shard=shard, radius=radius, output=output)
+        verbose=verbose, contract_impl=contract_impl, shard=shard, radius=radius, output=output,
+        label_permutations=label_permutations)
     if output == "frames":
         _log(verbose, f"\nResults: {len(laris_lr)} LR pairs, {len(celltype_results):,} cell type combinations")
     return laris_lr, celltype_results
+
+
+def labelPermutationNull(lr_adata, adata, groupby: str = "CellTypes", use_rep_spatial: str = "X_spatial",
+                         number_nearest_neighbors: int = 10, n_permutations: int = 100, random_seed: int = 27, *,
+                         contract_impl=None, radius=None):
+    """EXTENSION (not in the reference): label-permutation p-values of the sender::receiver co-localisation cosine of
+    every LR pair, as a P x C^2 DataFrame (also stored in ``lr_adata.uns['laris_label_null']``).
+    See ``laris_b200.tl._utils._label_permutation_null``."""
+    table = _utils._label_permutation_null(adata, lr_adata, groupby, use_rep_spatial, number_nearest_neighbors,
+                                           n_permutations, random_seed, contract_impl=contract_impl,
+                                           shard=_dist.shard_of(lr_adata), radius=radius)
+    lr_adata.uns["laris_label_null"] = {"params": dict(groupby=groupby, n_permutations=int(n_permutations),
+                                                       random_seed=int(random_seed)), "p_value": table}
+    return table
 
 
 __all__ = ["prepareLRInteraction", "runLARIS"]

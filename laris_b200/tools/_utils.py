@@ -427,6 +427,52 @@ def _neighborhood_tables(adata, lr_adata, groupby, use_rep_spatial, number_neare
     return raw, lr_names, pair_names
 
 
+def _label_permutation_null(adata, lr_adata, groupby: str = "CellTypes", use_rep_spatial: str = "X_spatial",
+                            number_nearest_neighbors: int = 10, n_permutations: int = 100, random_seed: int = 27, *,
+                            contract_impl=None, shard=None, radius=None, as_frame: bool = True):
+    """EXTENSION (north-star item 4; the reference has no label permutation): empirical p-values of the
+    co-localisation cosines cos[p, sender::receiver] (reference :859-866) under ``n_permutations`` relabellings of
+    the cells.  Permutation t applies a keyed bijection of [0, n) to the label vector (device Feistel network, bit-exact
+    numpy twin in oracle/rng.py), the neighbourhood composition and the P x C^2 contraction are recomputed - relabelled
+    neighbourhoods are mixed, so the contraction runs on the tcgen05 kernel - and p = (1 + #{cos_t >= cos}) / (T + 1).
+    Returns the P x C^2 DataFrame (global pair order in a sharded run) or, with ``as_frame=False``, the device tensor."""
+    if groupby not in adata.obs:
+        raise ValueError(f"'{groupby}' not found in adata.obs")
+    if use_rep_spatial not in adata.obsm:
+        raise ValueError(f"'{use_rep_spatial}' not found in adata.obsm")
+    if n_permutations < 1:
+        raise ValueError("n_permutations must be >= 1")
+    codes, cats = _group_codes(adata.obs[groupby])
+    C = len(cats)
+    sm = _scores_of(lr_adata)
+    if radius is None:
+        graph = engine.build_graph(_coords(adata, use_rep_spatial), number_nearest_neighbors, False, None,
+                                   like=sm.cache.get("graph"))
+    else:
+        graph = engine.build_radius_graph(_coords(adata, use_rep_spatial), radius, False, None)
+    labels_d = K.to_device(codes, torch.int32)
+    ss_d = _observed_ss_device(sm, graph)
+
+    def cosines(lab):
+        N = K.neighborhood_composition(lab, graph.idx, graph.w, C)
+        num, qn2 = K.celltype_pair_contract(sm.S, sm.P, N, contract_impl, order=graph.order)
+        return K.pair_cosine_regularise(num, ss_d, qn2, 1.0, want_cos=True)[0]
+
+    cos0 = cosines(labels_d)
+    ge = torch.zeros(cos0.shape, dtype=torch.int32, device=cos0.device)
+    for t in range(int(n_permutations)):
+        K.count_exceed(cos0, cosines(K.permute_labels(labels_d, t, random_seed)), ge)
+    p_d = (ge.to(torch.float64) + 1.0) / (float(n_permutations) + 1.0)
+    lr_names = np.asarray(lr_adata.var_names, dtype=object)
+    if shard is not None:
+        p_d = _dist.all_gather_pairs_dev(p_d, shard, axis=0)
+        lr_names = np.asarray(shard.names_global, dtype=object)
+    if not as_frame:
+        return p_d
+    return pd.DataFrame(p_d.cpu().numpy(), index=pd.Index(lr_names, dtype=object),
+                        columns=[f"{a}::{b}" for a in cats for b in cats])
+
+
 def _normalise_table_device(raw_d):
     """``cosg.iqrLogNormalize`` of a device table: the real function (through the host) when ``cosg`` is importable,
     else the device stand-in T2 (parity unpinned, see laris_b200.cosg_compat)."""
@@ -633,7 +679,7 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
                                        score_threshold: float = 1e-6, spatial_weight: float = 1.0,
                                        use_conditional_pvalue: bool = False, *, rng: str = "numpy", random_seed: int = 27,
                                        rng_state=None, verbose: bool = True, contract_impl=None, shard=None, radius=None,
-                                       output: str = "frames"):
+                                       output: str = "frames", label_permutations: int = 0):
     """Sender/receiver cell-type table with permutation p-values and BH-FDR.
 
     Reference laris/tools/_utils.py:1113-1688; same arguments (``mask_threshold`` and
@@ -764,6 +810,15 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
         result.update(p_value=p_rows, p_value_fdr=fdr_rows, nlog10_p_value_fdr=nlog_rows)
     elif rng == "numpy" and rng_state is not None:
         _rng_compat.sync_global(rng_state)
+    label_rows = None
+    if label_permutations and label_permutations > 0:
+        # extension: label-permutation null of the co-localisation cosine of every (pair, sender::receiver) row
+        _log(verbose, f"\n--- Extension: label-permutation null ({label_permutations} relabellings) ---")
+        label_p = _label_permutation_null(adata, lr_adata, groupby, use_rep_spatial, number_nearest_neighbors,
+                                          label_permutations, random_seed, contract_impl=contract_impl, shard=shard,
+                                          radius=radius, as_frame=False)
+        label_rows = label_p[pair_id_d.to(torch.int64)]                      # [pair, sender*C + receiver]
+        result["p_value_label_null"] = label_rows
     if output == "arrays":
         return result
 
@@ -783,11 +838,13 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
         res["p_value"] = np.nan
         res["p_value_fdr"] = np.nan
         res["nlog10_p_value_fdr"] = np.nan
-        return res
-    host = K.to_host(p_rows, fdr_rows, nlog_rows)
-    res["p_value"] = host[0].reshape(-1)[order_rows]
-    res["p_value_fdr"] = host[1].reshape(-1)[order_rows]
-    res["nlog10_p_value_fdr"] = host[2].reshape(-1)[order_rows]
+    else:
+        host = K.to_host(p_rows, fdr_rows, nlog_rows)
+        res["p_value"] = host[0].reshape(-1)[order_rows]
+        res["p_value_fdr"] = host[1].reshape(-1)[order_rows]
+        res["nlog10_p_value_fdr"] = host[2].reshape(-1)[order_rows]
+    if label_rows is not None:
+        res["p_value_label_null"] = label_rows.cpu().numpy().reshape(-1)[order_rows]
     return res
 
 

@@ -441,6 +441,29 @@ def fdr_by_group(pvals, scores, prefilter_fdr, prefilter_threshold):
 
 
 # ---------------------------------------------------------------------------
+# extension: label-permutation null of the co-localisation cosines (no reference counterpart; the reference's nulls
+# are the random graph, laris/tools/_utils.py:436-446, and the background-pair resampling, :1544-1570)
+# ---------------------------------------------------------------------------
+
+LABEL_PERM_BASE = 0x40000000          # key stream of permutation t: LABEL_PERM_BASE + t (csrc/rng.cuh kLabelPermBase)
+
+
+def label_permutation_null(S, labels, ind, w, C, n_perm, seed):
+    """Cell-type labels are permuted over the cells (a keyed bijection of [0, n): oracle.rng.feistel_permutation), the
+    neighbourhood composition (:839-856) and the P x C^2 cosines (:859-866) are recomputed, and
+    ge[p,(a,b)] = #{t : cos_t >= cos_observed}.  Returns (cos_observed, ge, p = (ge + 1) / (n_perm + 1))."""
+    from . import rng as orng
+    labels = np.asarray(labels)
+    n = len(labels)
+    cos0 = celltype_pair_cosine(S, neighborhood_composition(labels, ind, w, C))
+    ge = np.zeros(cos0.shape, dtype=np.int64)
+    for t in range(n_perm):
+        lt = labels[orng.feistel_permutation(n, LABEL_PERM_BASE + t, seed)]
+        ge += celltype_pair_cosine(S, neighborhood_composition(lt, ind, w, C)) >= cos0
+    return cos0, ge, (ge + 1.0) / (n_perm + 1.0)
+
+
+# ---------------------------------------------------------------------------
 # whole-path drivers (chain the pieces in the reference's order)
 # ---------------------------------------------------------------------------
 

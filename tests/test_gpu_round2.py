@@ -320,3 +320,51 @@ def test_missing_labels_are_rejected(dev, tiny):
     ad = la.tl.prepareLRInteraction(a, lr.iloc[:10], number_nearest_neighbors=8)
     with pytest.raises(ValueError, match="no cell-type label"):
         la.tl.runLARIS(ad, b, n_nearest_neighbors=8, n_cells_expressed_threshold=1, n_permutations=10, verbose=False)
+
+
+# ------------------------------------------- label-permutation null ----
+def test_permuted_labels_are_the_oracle_bijection(dev):
+    from laris_b200 import _kernels as K
+    from oracle import restate as R
+    from oracle import rng as orng
+    n = 40_013
+    labels = np.random.default_rng(1).integers(0, 7, n).astype(np.int32)
+    lab_d = _d(labels, torch.int32)
+    for t in (0, 3, 99):
+        got = K.permute_labels(lab_d, t, 27).cpu().numpy()
+        perm = orng.feistel_permutation(n, R.LABEL_PERM_BASE + t, 27)
+        assert np.array_equal(np.sort(perm), np.arange(n))
+        assert np.array_equal(got, labels[perm])
+        assert np.array_equal(np.bincount(got, minlength=7), np.bincount(labels, minlength=7))
+
+
+@pytest.mark.parametrize("C,contract_impl", [(4, None), (9, 0), (9, 2)])
+def test_label_permutation_null_matches_the_oracle(dev, C, contract_impl):
+    import laris_b200 as la
+    from laris_b200.synth import make_dataset
+    from oracle import restate as R
+    a, lr, c = make_dataset(1, n=3000, G=200, G_u=100, P=40, C=C)
+    k, T = 8, 12
+    ad = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=k)
+    got = la.tl.labelPermutationNull(ad, a, number_nearest_neighbors=k, n_permutations=T, random_seed=5,
+                                     contract_impl=contract_impl)
+    assert got.shape == (40, C * C) and list(got.index) == list(ad.var_names) and "laris_label_null" in ad.uns
+    S = sp.csr_matrix(ad.X).astype(np.float64)
+    labels = a.obs["CellTypes"].cat.codes.to_numpy()
+    ind, dist = R.knn_graph(a.obsm["X_spatial"], k, False)
+    cos0, ge, p = R.label_permutation_null(S, labels, ind, R.decay_weights(dist), C, T, 5)
+    g = got.to_numpy()
+    assert ((g > 0) & (g <= 1)).all() and np.allclose(g * (T + 1), np.round(g * (T + 1)))
+    # counts are integers: identical except where a permuted cosine ties the observed one to ~1e-6
+    assert (np.abs(g - p) > 1e-12).mean() < 0.01
+    # relabelling destroys the spatial coherence: the observed same-type cosines sit in the upper tail
+    diag = [t * C + t for t in range(C)]
+    assert np.median(g[:, diag]) < np.median(g)
+    # runLARIS(label_permutations=...) attaches the same numbers to the long table
+    _, tab = la.tl.runLARIS(ad, a, n_nearest_neighbors=k, number_nearest_neighbors=k, n_permutations=20, n_top_lr=40,
+                            n_cells_expressed_threshold=10, rng="philox", random_seed=5, label_permutations=T,
+                            contract_impl=contract_impl, verbose=False)
+    assert "p_value_label_null" in tab.columns
+    key = tab["sender"].astype(str) + "::" + tab["receiver"].astype(str)
+    want = np.array([got.loc[nm, kk] for nm, kk in zip(tab["interaction_name"].iloc[:200], key.iloc[:200])])
+    assert np.array_equal(tab["p_value_label_null"].to_numpy()[:200], want)

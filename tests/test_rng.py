@@ -69,3 +69,21 @@ def test_pvalue_draw_digits_are_uniform_and_independent():
     assert wide.shape == (50, 101) and wide.max() < 200
     # prefix property: fewer permutations are a prefix of more (sharding by permutation ranges relies on it)
     assert np.array_equal(rng.philox_pvalue_draws(np.arange(7), 100, nb, 5), rng.philox_pvalue_draws(np.arange(7), 250, nb, 5)[:, :100])
+
+
+def test_label_permutation_is_a_keyed_bijection():
+    """The label-permutation null (extension) relabels cells with a Feistel bijection keyed by (permutation, seed):
+    a permutation of [0, n), different per permutation id and seed, and disjoint from the K4b weight-shuffle streams."""
+    from oracle import restate as R
+    from oracle import rng as orng
+    n = 10_007
+    base = R.LABEL_PERM_BASE
+    p0 = orng.feistel_permutation(n, base + 0, 27)
+    p1 = orng.feistel_permutation(n, base + 1, 27)
+    q0 = orng.feistel_permutation(n, base + 0, 28)
+    k0 = orng.feistel_permutation(n, 0, 27)                     # what K4b repeat 0 would use on the same domain
+    for p in (p0, p1, q0):
+        assert np.array_equal(np.sort(p), np.arange(n))
+    assert (p0 != p1).mean() > 0.99 and (p0 != q0).mean() > 0.99 and (p0 != k0).mean() > 0.99
+    fixed = (p0 == np.arange(n)).sum()
+    assert fixed < 10                                           # ~1 fixed point expected for a random permutation
