@@ -169,7 +169,27 @@ __global__ void cell_sort_kernel(const int32_t* __restrict__ cell_start, const G
                                  int32_t* __restrict__ sorted_id) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= gsp->ncell) return;
-    int s = cell_start[c], e = cell_start[c + 1];
+    const int s = cell_start[c], e = cell_start[c + 1], len = e - s;
+    if (len < 2) return;
+    constexpr int CAP = 16;                 // ~2.5 points per cell: the segment is sorted in a thread-private array
+    if (len <= CAP) {                       // (one load and one store per point instead of a read-modify-write chain)
+        int32_t v[CAP];
+#pragma unroll
+        for (int a = 0; a < CAP; ++a) v[a] = a < len ? sorted_id[s + a] : INT32_MAX;
+#pragma unroll
+        for (int a = 1; a < CAP; ++a) {
+#pragma unroll
+            for (int b = a; b > 0; --b) {
+                const int32_t lo = min(v[b - 1], v[b]), hi = max(v[b - 1], v[b]);
+                v[b - 1] = lo;
+                v[b] = hi;
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < CAP; ++a)
+            if (a < len) sorted_id[s + a] = v[a];
+        return;
+    }
     for (int a = s + 1; a < e; ++a) {
         int v = sorted_id[a], b = a - 1;
         while (b >= s && sorted_id[b] > v) { sorted_id[b + 1] = sorted_id[b]; --b; }

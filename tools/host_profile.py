@@ -53,4 +53,5 @@ for name, fn in (("device-resident step", device_step), ("public API step", host
     pr.disable()
     s = io.StringIO()
     pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(45)
+    pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(40)
     print(s.getvalue())
