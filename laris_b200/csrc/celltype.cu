@@ -246,11 +246,12 @@ extern "C" int laris_celltype_nonzero_count(const float* S, int64_t ldS, int64_t
 }
 
 // ---- the same sums with the cells grouped by type: a CTA takes <= kOhRows rows of ONE type and accumulates its
-// (gene) sums, squares and counts in shared memory (native fp32 / integer shared-memory atomics; a gene is hit
-// ~density * kOhRows times per CTA), then adds each touched gene to the fp64 tables once - ~13x fewer global
-// fp64 atomics than the row-at-a-time kernel above (5.4 -> ~1 ms at 1e6 cells x 1350 genes).  fp32 partial sums over
-// <= kOhRows terms keep the relative error below 1e-6.
-constexpr int kOhRows = 128, kOhThreads = 128, kOhMaxColumns = 16000;
+// per-gene sums, squares and counts in shared memory, then adds each touched gene to the fp64 tables once - ~13x fewer
+// global fp64 atomics than the row-at-a-time kernel above (5.4 -> ~1 ms at 1e6 cells x 1350 genes).  The rows of a CTA
+// are taken one after the other by all threads (a row's genes are distinct, so the adds of one row never collide and
+// need no atomics; a barrier separates rows; the next row's entries are already in registers), in fp64: the result
+// differs from the row-at-a-time kernel only in fp64 summation order.
+constexpr int kOhRows = 128, kOhThreads = 128, kOhMaxColumns = 8000, kOhPerThread = 4;
 
 __global__ void onehot_chunk_base_kernel(const int32_t* __restrict__ start, int C, int32_t* __restrict__ chunk_base) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -268,10 +269,10 @@ onehot_contract_grouped_kernel(const int64_t* __restrict__ row_start, const int6
                                const int64_t* __restrict__ packed, int G_u, const int32_t* __restrict__ rows,
                                const int32_t* __restrict__ start, const int32_t* __restrict__ chunk_base, int C,
                                double* __restrict__ sum, double* __restrict__ cnt, double* __restrict__ colsq) {
-    extern __shared__ float oh_smem[];
-    float* s_sum = oh_smem;
-    float* s_sq = oh_smem + G_u;
-    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(oh_smem + 2 * G_u);
+    extern __shared__ double oh_smem[];
+    double* s_sum = oh_smem;
+    double* s_sq = oh_smem + G_u;
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(oh_smem + 2 * (size_t)G_u);
     const int b = blockIdx.x;
     if (b >= chunk_base[C]) return;
     int lo = 0, hi = C;                                     // type t with chunk_base[t] <= b < chunk_base[t+1]
@@ -281,28 +282,48 @@ onehot_contract_grouped_kernel(const int64_t* __restrict__ row_start, const int6
     }
     const int t = lo;
     const int p0 = start[t] + (b - chunk_base[t]) * kOhRows, p1 = min(start[t + 1], p0 + kOhRows);
-    for (int g = threadIdx.x; g < G_u; g += kOhThreads) { s_sum[g] = 0.f; s_sq[g] = 0.f; s_cnt[g] = 0u; }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int pos = p0 + warp; pos < p1; pos += kOhThreads / 32) {
+    for (int g = threadIdx.x; g < G_u; g += kOhThreads) { s_sum[g] = 0.0; s_sq[g] = 0.0; s_cnt[g] = 0u; }
+    // entries of a row: thread e, e + 128, ...; the first kOhPerThread of the NEXT row are fetched before this row is added
+    int64_t nx[kOhPerThread];
+    int64_t nx_s = 0, nx_e = 0;
+    auto fetch = [&](int pos) {
         const int64_t row = rows[pos];
-        for (int64_t e = row_start[row] + lane; e < row_end[row]; e += 32) {
-            const int64_t pk = packed[e];
-            const uint32_t g = (uint32_t)(pk & 0xffffffffll);
-            const float v = __uint_as_float((uint32_t)((uint64_t)pk >> 32));
-            atomicAdd(&s_sum[g], v);
-            atomicAdd(&s_sq[g], v * v);
-            atomicAdd(&s_cnt[g], 1u);
+        nx_s = row_start[row];
+        nx_e = row_end[row];
+#pragma unroll
+        for (int j = 0; j < kOhPerThread; ++j) {
+            const int64_t e = nx_s + threadIdx.x + (int64_t)j * kOhThreads;
+            nx[j] = e < nx_e ? packed[e] : -1;
         }
-    }
+    };
+    if (p0 < p1) fetch(p0);
     __syncthreads();
+    for (int pos = p0; pos < p1; ++pos) {
+        int64_t cur[kOhPerThread];
+        const int64_t cs = nx_s, ce = nx_e;
+#pragma unroll
+        for (int j = 0; j < kOhPerThread; ++j) cur[j] = nx[j];
+        if (pos + 1 < p1) fetch(pos + 1);
+        auto add = [&](int64_t pk) {
+            const uint32_t g = (uint32_t)(pk & 0xffffffffll);
+            const double v = (double)__uint_as_float((uint32_t)((uint64_t)pk >> 32));
+            s_sum[g] += v;
+            s_sq[g] += v * v;
+            s_cnt[g] += 1u;
+        };
+#pragma unroll
+        for (int j = 0; j < kOhPerThread; ++j)
+            if (cs + threadIdx.x + (int64_t)j * kOhThreads < ce) add(cur[j]);
+        for (int64_t e = cs + threadIdx.x + (int64_t)kOhPerThread * kOhThreads; e < ce; e += kOhThreads) add(packed[e]);
+        __syncthreads();                                    // the next row may touch the same genes
+    }
     const int64_t base = (int64_t)t * G_u;
     for (int g = threadIdx.x; g < G_u; g += kOhThreads) {
         const uint32_t c = s_cnt[g];
         if (c) {
-            atomicAdd(&sum[base + g], (double)s_sum[g]);
+            atomicAdd(&sum[base + g], s_sum[g]);
             atomicAdd(&cnt[base + g], (double)c);
-            atomicAdd(&colsq[g], (double)s_sq[g]);
+            atomicAdd(&colsq[g], s_sq[g]);
         }
     }
 }
@@ -339,7 +360,7 @@ static int onehot_contract_impl(const int64_t* row_start, const int64_t* row_end
     LARIS_LAUNCH_CHECK();
     onehot_chunk_base_kernel<<<1, 32, 0, st>>>(start.p, C, chunk_base.p);
     LARIS_LAUNCH_CHECK();
-    const size_t smem = (size_t)3 * G_u * sizeof(float);
+    const size_t smem = (size_t)G_u * (2 * sizeof(double) + sizeof(uint32_t)) + 16;
     LARIS_CUDA(cudaFuncSetAttribute(onehot_contract_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t bound = ceil_div(n, kOhRows) + C;
     onehot_contract_grouped_kernel<<<(unsigned)bound, kOhThreads, smem, st>>>(row_start, row_end, packed, G_u, rows.p, start.p,

@@ -66,11 +66,19 @@ def _coords_to_device(xy):
     return xy_d
 
 
+def _check_sigma(sigma):
+    """The reference divides by sigma (laris/tools/_utils.py:392): zero / negative / non-finite scales are rejected up
+    front (the C ABI uses sigma <= 0 as its own marker for the mean(d)/2 rule)."""
+    if sigma is not None and not (np.isfinite(sigma) and sigma > 0):
+        raise ValueError(f"sigma must be a positive finite number (got {sigma!r}); pass None for the mean(d)/2 rule")
+
+
 def build_graph(xy, k, include_self, sigma=None, like: SpatialGraph | None = None) -> SpatialGraph:
     """kNN graph + decay weights (K1).  ``sigma=None`` -> s = mean(d)/2.  ``like``: a graph built earlier in the same
     run; when it was searched with the same k / self rule over the SAME coordinates (compared on the device), its
     neighbour lists are re-used and only the weights are recomputed (runLARIS builds two graphs that differ only in
     the decay rule, reference laris/tools/_utils.py:383-394 and :846-853)."""
+    _check_sigma(sigma)
     xy_d = _coords_to_device(xy).contiguous()
     if (like is not None and like.xy is not None and like.csr is None and like.k == int(k)
             and like.include_self == bool(include_self) and like.xy.shape == xy_d.shape and like.xy.dtype == xy_d.dtype
@@ -88,6 +96,7 @@ def build_radius_graph(xy, radius, include_self, sigma=None) -> SpatialGraph:
     The variable-degree CSR is kept in ``csr``; ``idx``/``w`` hold the same rows padded to the maximum degree with
     (own row, weight 0) edges, which is the fixed-degree layout every gather kernel takes.  ``sigma=None`` uses
     s = mean(stored distances)/2, the reference's rule for its kNN graphs."""
+    _check_sigma(sigma)
     xy_d = _coords_to_device(xy)
     indptr, indices, dist, order = K.radius_graph(xy_d.contiguous(), float(radius), include_self)
     if dist.numel() == 0:
