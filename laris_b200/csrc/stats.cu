@@ -389,6 +389,87 @@ struct TileSmem {
     static __host__ __device__ size_t total(int k) { return 2 * stage_bytes(k) + 16 * 16 * 4 * 8 + 64; }
 };
 
+// per-thread running sums of a (column quad, cell lane) of the tile kernels
+struct TileAcc {
+    double dot[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0}, tt[4] = {0, 0, 0, 0}, s[4] = {0, 0, 0, 0};
+    int nz[4] = {0, 0, 0, 0};
+};
+
+// one work item (128 cells x 64 columns) from the staged tile: T = sum_j w_j * row[slot_j] and the five sums, fp32 over the
+// four cells of this thread, fp64 across items.  `direct`: the tile's rows were not staged (union over the cap) - read global.
+__device__ __forceinline__ void tile_accumulate(TileAcc& A, const float4* tile_s, const int2* ent_s, const int32_t* self_s,
+                                                const float* S, int64_t ldS, int64_t col0, int k, int quad, int cl) {
+    if (!(col0 + quad * 4 < ldS)) return;
+    const bool direct = self_s[kTileCells] < 0;
+    float p_dot[4] = {0, 0, 0, 0}, p_ss[4] = {0, 0, 0, 0}, p_tt[4] = {0, 0, 0, 0}, p_s[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int m = 0; m < kTileCells / 32; ++m) {
+        const int c = cl + 32 * m;
+        const int sf = self_s[c];
+        if (sf < 0) continue;
+        const int2* e = ent_s + c * k;
+        float4 s, t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!direct) {
+            s = tile_s[sf * (kSlabCols / 4) + quad];
+            for (int j = 0; j < k; ++j) {
+                const int2 ej = e[j];
+                const float wj = __int_as_float(ej.y);
+                const float4 v = tile_s[ej.x * (kSlabCols / 4) + quad];
+                t.x = fmaf(wj, v.x, t.x); t.y = fmaf(wj, v.y, t.y); t.z = fmaf(wj, v.z, t.z); t.w = fmaf(wj, v.w, t.w);
+            }
+        } else {
+            const float4* S4 = reinterpret_cast<const float4*>(S + col0) + quad;
+            s = ld_cached_f4(S4 + (int64_t)sf * (ldS / 4));
+            for (int j = 0; j < k; ++j) {
+                const int2 ej = e[j];
+                const float wj = __int_as_float(ej.y);
+                const float4 v = ld_cached_f4(S4 + (int64_t)ej.x * (ldS / 4));
+                t.x = fmaf(wj, v.x, t.x); t.y = fmaf(wj, v.y, t.y); t.z = fmaf(wj, v.z, t.z); t.w = fmaf(wj, v.w, t.w);
+            }
+        }
+        const float sv[4] = {s.x, s.y, s.z, s.w}, tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            p_dot[q] = fmaf(sv[q], tv[q], p_dot[q]);
+            p_ss[q] = fmaf(sv[q], sv[q], p_ss[q]);
+            p_tt[q] = fmaf(tv[q], tv[q], p_tt[q]);
+            p_s[q] += sv[q];
+            A.nz[q] += sv[q] != 0.f ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        A.dot[q] += (double)p_dot[q]; A.ss[q] += (double)p_ss[q]; A.tt[q] += (double)p_tt[q]; A.s[q] += (double)p_s[q];
+    }
+}
+
+// slab segment finished: reduce the 32 cell lanes of every quad in a fixed order, write one record, clear the sums.
+// Called by the kTileConsumers consumer threads together (named barrier 1).
+__device__ __forceinline__ void tile_flush_record(TileAcc& A, double* red, double* out, int tid) {
+    const int lane = tid & 31, warp = tid >> 5, quad = tid & 15;
+    for (int stat = 0; stat < 5; ++stat) {
+        double v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            v[q] = stat == 0 ? A.dot[q] : stat == 1 ? A.ss[q] : stat == 2 ? A.tt[q] : stat == 3 ? A.s[q] : (double)A.nz[q];
+            v[q] += __shfl_xor_sync(0xffffffffu, v[q], 16);                     // the warp's two cell lanes
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTileConsumers) : "memory");
+        if (lane < 16) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) red[(warp * 16 + quad) * 4 + q] = v[q];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTileConsumers) : "memory");
+        if (tid < kSlabCols) {
+            const int qd = tid >> 2, q = tid & 3;
+            double t = 0.0;
+            for (int wq = 0; wq < 16; ++wq) t += red[(wq * 16 + qd) * 4 + q];
+            out[stat * kSlabCols + tid] = t;
+        }
+    }
+    A = TileAcc();
+}
+
 __global__ void __launch_bounds__(kTileThreads, 1)
 spatial_obs_tile_kernel(const float* __restrict__ S, int64_t ldS, int k, TilePlan plan, int64_t ntiles, int nslabs,
                         int maxseg, double* __restrict__ partial, int32_t* __restrict__ rec_slab,
@@ -471,97 +552,125 @@ spatial_obs_tile_kernel(const float* __restrict__ S, int64_t ldS, int k, TilePla
     }
     // --------------------------------- consumers ---------------------------------
     const int quad = tid & 15, cl = tid >> 4;                                   // 16 column quads x 32 cell lanes
-    double a_dot[4] = {0, 0, 0, 0}, a_ss[4] = {0, 0, 0, 0}, a_tt[4] = {0, 0, 0, 0}, a_s[4] = {0, 0, 0, 0};
-    int a_nz[4] = {0, 0, 0, 0};
+    TileAcc A;
     int seg = 0;
     for (int64_t wi = w0, it = 0; wi < w1; ++wi, ++it) {
         const int st = (int)(it & 1);
         const uint32_t ph = (uint32_t)((it >> 1) & 1);
         const int slab = (int)(wi / ntiles);
-        const int64_t tile = wi - (int64_t)slab * ntiles;
         const int64_t col0 = (int64_t)slab * kSlabCols;
-        const bool col_ok = col0 + quad * 4 < ldS;
         aio::mbar_wait(full0 + 8 * st, ph);
         const unsigned char* stage = smem + st * stage_b;
-        const float4* tile_s = reinterpret_cast<const float4*>(stage);
-        const int2* ent_s = reinterpret_cast<const int2*>(stage + (size_t)kTileCap * kSlabCols * 4);
-        const int32_t* self_s = reinterpret_cast<const int32_t*>(stage + (size_t)kTileCap * kSlabCols * 4 + ent_bytes);
-        const bool direct = self_s[kTileCells] < 0;
-        float p_dot[4] = {0, 0, 0, 0}, p_ss[4] = {0, 0, 0, 0}, p_tt[4] = {0, 0, 0, 0}, p_s[4] = {0, 0, 0, 0};
-        if (col_ok) {
-#pragma unroll
-            for (int m = 0; m < kTileCells / 32; ++m) {
-                const int c = cl + 32 * m;
-                const int sf = self_s[c];
-                if (sf < 0) continue;
-                const int2* e = ent_s + c * k;
-                float4 s, t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (!direct) {
-                    s = tile_s[sf * (kSlabCols / 4) + quad];
-                    for (int j = 0; j < k; ++j) {
-                        const int2 ej = e[j];
-                        const float wj = __int_as_float(ej.y);
-                        const float4 v = tile_s[ej.x * (kSlabCols / 4) + quad];
-                        t.x = fmaf(wj, v.x, t.x); t.y = fmaf(wj, v.y, t.y); t.z = fmaf(wj, v.z, t.z); t.w = fmaf(wj, v.w, t.w);
-                    }
-                } else {
-                    const float4* S4 = reinterpret_cast<const float4*>(S + col0) + quad;
-                    s = ld_cached_f4(S4 + (int64_t)sf * (ldS / 4));
-                    for (int j = 0; j < k; ++j) {
-                        const int2 ej = e[j];
-                        const float wj = __int_as_float(ej.y);
-                        const float4 v = ld_cached_f4(S4 + (int64_t)ej.x * (ldS / 4));
-                        t.x = fmaf(wj, v.x, t.x); t.y = fmaf(wj, v.y, t.y); t.z = fmaf(wj, v.z, t.z); t.w = fmaf(wj, v.w, t.w);
-                    }
-                }
-                const float sv[4] = {s.x, s.y, s.z, s.w}, tv[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    p_dot[q] = fmaf(sv[q], tv[q], p_dot[q]);
-                    p_ss[q] = fmaf(sv[q], sv[q], p_ss[q]);
-                    p_tt[q] = fmaf(tv[q], tv[q], p_tt[q]);
-                    p_s[q] += sv[q];
-                    a_nz[q] += sv[q] != 0.f ? 1 : 0;
-                }
-            }
-        }
+        tile_accumulate(A, reinterpret_cast<const float4*>(stage),
+                        reinterpret_cast<const int2*>(stage + (size_t)kTileCap * kSlabCols * 4),
+                        reinterpret_cast<const int32_t*>(stage + (size_t)kTileCap * kSlabCols * 4 + ent_bytes), S, ldS, col0, k,
+                        quad, cl);
         __syncwarp();
         if (lane == 0) aio::mbar_arrive(empty0 + 8 * st);                       // this warp is done with the stage
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            a_dot[q] += (double)p_dot[q]; a_ss[q] += (double)p_ss[q]; a_tt[q] += (double)p_tt[q]; a_s[q] += (double)p_s[q];
-        }
-        const bool last = wi + 1 == w1 || (wi + 1) / ntiles != slab;
-        if (last) {
-            // slab segment finished: reduce the 32 cell lanes of every quad in a fixed order, write one record
+        if (wi + 1 == w1 || (wi + 1) / ntiles != slab) {
             const int64_t rec = (int64_t)blockIdx.x * maxseg + seg;
-            double* out = partial + rec * 5 * kSlabCols;
-            for (int stat = 0; stat < 5; ++stat) {
-                double v[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    v[q] = stat == 0 ? a_dot[q] : stat == 1 ? a_ss[q] : stat == 2 ? a_tt[q] : stat == 3 ? a_s[q] : (double)a_nz[q];
-                    v[q] += __shfl_xor_sync(0xffffffffu, v[q], 16);             // the warp's two cell lanes
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(kTileConsumers) : "memory");
-                if (lane < 16) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) red[(warp * 16 + quad) * 4 + q] = v[q];
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(kTileConsumers) : "memory");
-                if (tid < kSlabCols) {
-                    const int qd = tid >> 2, q = tid & 3;
-                    double t = 0.0;
-                    for (int wq = 0; wq < 16; ++wq) t += red[(wq * 16 + qd) * 4 + q];
-                    out[stat * kSlabCols + tid] = t;
-                }
-            }
+            tile_flush_record(A, red, partial + rec * 5 * kSlabCols, tid);
             if (tid == 0) rec_slab[rec] = slab;
             ++seg;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { a_dot[q] = 0; a_ss[q] = 0; a_tt[q] = 0; a_s[q] = 0; a_nz[q] = 0; }
         }
     }
+}
+
+// The same pass with the rows staged by cp.async (LDGSTS): no producer warp, no TMA operations - all 512 threads issue
+// 16-byte global->shared copies (16 per 256-byte row piece).  A 1-D bulk copy costs the TMA engine ~71 cycles and a
+// gather4 ~146 cycles per operation per SM (measured); LDGSTS sustains ~64 B/clk/SM.  Three plan buffers
+// (row list, edges, own slots) and two tile buffers are software-pipelined with cp.async groups:
+//   iteration `it`:  issue plan(it+2) | wait plan(it+1), barrier | issue rows(it+1) | wait rows(it), barrier | compute(it)
+struct TileSmemCp {
+    static __host__ __device__ size_t plan_bytes(int k) {
+        return (((size_t)kTileCap * 4 + (size_t)kTileCells * k * 8 + (size_t)kTileSelf * 4) + 127) & ~(size_t)127;
+    }
+    static __host__ __device__ size_t tile_bytes() { return (size_t)kTileCap * kSlabCols * 4; }
+    static __host__ __device__ size_t total(int k) { return 2 * tile_bytes() + 3 * plan_bytes(k) + 16 * 16 * 4 * 8; }
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(kTileConsumers, 1)
+spatial_obs_tile_cpasync_kernel(const float* __restrict__ S, int64_t ldS, int k, TilePlan plan, int64_t ntiles, int nslabs,
+                                int maxseg, double* __restrict__ partial, int32_t* __restrict__ rec_slab) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const size_t tile_b = TileSmemCp::tile_bytes(), plan_b = TileSmemCp::plan_bytes(k);
+    const int tid = threadIdx.x;
+    unsigned char* tile_base = smem;
+    unsigned char* plan_base = smem + 2 * tile_b;
+    double* red = reinterpret_cast<double*>(smem + 2 * tile_b + 3 * plan_b);
+    const uint32_t rows_bytes = kTileCap * 4, ent_bytes = (uint32_t)kTileCells * k * 8, self_bytes = kTileSelf * 4;
+    const int64_t W = (int64_t)nslabs * ntiles;
+    const int64_t w0 = W * blockIdx.x / gridDim.x, w1 = W * (blockIdx.x + 1) / gridDim.x;
+
+    auto issue_plan = [&](int64_t wi, int buf) {           // rows | ent | self of the item's tile -> plan buffer `buf`
+        if (wi < w1) {
+            const int64_t tile = wi % ntiles;
+            const uint32_t dst = aio::smem_addr(plan_base + (size_t)buf * plan_b);
+            const unsigned char* src_rows = reinterpret_cast<const unsigned char*>(plan.rows + tile * kTileCap);
+            const unsigned char* src_ent = reinterpret_cast<const unsigned char*>(plan.ent + tile * kTileCells * k);
+            const unsigned char* src_self = reinterpret_cast<const unsigned char*>(plan.self + tile * kTileSelf);
+            const int n_rows = rows_bytes / 16, n_ent = ent_bytes / 16, n_self = self_bytes / 16;
+            for (int c = tid; c < n_rows + n_ent + n_self; c += kTileConsumers) {
+                if (c < n_rows) cp_async16(dst + 16 * c, src_rows + 16 * c, 16);
+                else if (c < n_rows + n_ent) cp_async16(dst + 16 * c, src_ent + 16 * (c - n_rows), 16);
+                else cp_async16(dst + 16 * c, src_self + 16 * (c - n_rows - n_ent), 16);
+            }
+        }
+        cp_async_commit();
+    };
+    auto issue_rows = [&](int64_t wi, int pbuf, int tbuf) { // the tile's distinct row pieces, 16 copies of 16 bytes per row
+        if (wi < w1) {
+            const unsigned char* pl = plan_base + (size_t)pbuf * plan_b;
+            const int32_t* rows_s = reinterpret_cast<const int32_t*>(pl);
+            const int cnt = reinterpret_cast<const int32_t*>(pl + rows_bytes + ent_bytes)[kTileCells];
+            const int64_t col0 = (wi / ntiles) * kSlabCols;
+            const uint32_t dst = aio::smem_addr(tile_base + (size_t)tbuf * tile_b);
+            for (int c = tid; c < cnt * 16; c += kTileConsumers) {
+                const int r = c >> 4, piece = c & 15;
+                const bool ok = col0 + piece * 4 < ldS;
+                const float* src = S + (int64_t)rows_s[r] * ldS + (ok ? col0 + piece * 4 : 0);
+                cp_async16(dst + (uint32_t)r * (kSlabCols * 4) + piece * 16, src, ok ? 16u : 0u);
+            }
+        }
+        cp_async_commit();
+    };
+
+    const int quad = tid & 15, cl = tid >> 4;
+    TileAcc A;
+    int seg = 0;
+    issue_plan(w0, 0);
+    issue_plan(w0 + 1, 1);
+    cp_async_wait<1>();                                     // plan(0)
+    __syncthreads();
+    issue_rows(w0, 0, 0);
+    for (int64_t wi = w0, it = 0; wi < w1; ++wi, ++it) {
+        issue_plan(wi + 2, (int)((it + 2) % 3));
+        cp_async_wait<2>();                                 // plan(it+1): everything but the two youngest groups
+        __syncthreads();
+        issue_rows(wi + 1, (int)((it + 1) % 3), (int)((it + 1) & 1));
+        cp_async_wait<2>();                                 // rows(it)
+        __syncthreads();
+        const int slab = (int)(wi / ntiles);
+        const unsigned char* pl = plan_base + (size_t)(it % 3) * plan_b;
+        tile_accumulate(A, reinterpret_cast<const float4*>(tile_base + (size_t)(it & 1) * tile_b),
+                        reinterpret_cast<const int2*>(pl + rows_bytes), reinterpret_cast<const int32_t*>(pl + rows_bytes + ent_bytes),
+                        S, ldS, (int64_t)slab * kSlabCols, k, quad, cl);
+        if (wi + 1 == w1 || (wi + 1) / ntiles != slab) {
+            const int64_t rec = (int64_t)blockIdx.x * maxseg + seg;
+            tile_flush_record(A, red, partial + rec * 5 * kSlabCols, tid);
+            if (tid == 0) rec_slab[rec] = slab;
+            ++seg;
+        }
+        __syncthreads();                                    // the buffers of item `it` are free for items it+2 / it+3
+    }
+    cp_async_wait<0>();
 }
 
 // records [nrec][5][kSlabCols] (+ their slab) -> out [5][P]; one CTA per slab, records summed in index order
@@ -632,13 +741,14 @@ extern "C" int laris_null_graph_philox(int64_t n, int k, const float* w, int32_t
     return LARIS_OK;
 }
 
-// staging of the tile rows: 1 = TMA tile::gather4 through a tensor map (default), 0 = one 1-D bulk copy per row.
-// LARIS_B200_K4A_STAGING=bulk|gather4 overrides it (used to measure the two against each other).
+// staging of the tile rows: 2 = cp.async 16-byte copies by all threads (default for k <= 12), 1 = TMA tile::gather4 through
+// a tensor map (k 13..15, or on request), 0 = one 1-D bulk copy per row.  LARIS_B200_K4A_STAGING=bulk|gather4|cpasync
+// overrides it (used to measure the three against each other, tools/time_k4.py).
 static int tile_staging_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("LARIS_B200_K4A_STAGING");
-        mode = (e && strcmp(e, "bulk") == 0) ? 0 : 1;
+        mode = !e ? 2 : strcmp(e, "bulk") == 0 ? 0 : strcmp(e, "gather4") == 0 ? 1 : 2;
     }
     return mode;
 }
@@ -689,13 +799,25 @@ static int observed_stats_tiled(const float* S, int64_t ldS, int64_t n, int32_t 
     LARIS_CUDA(partial.alloc((size_t)nrec * 5 * kSlabCols));
     LARIS_CUDA(rec_slab.alloc((size_t)nrec));
     LARIS_CUDA(cudaMemsetAsync(rec_slab.p, 0xff, sizeof(int32_t) * (size_t)nrec, st));
+    int mode = tile_staging_mode();
+    if (mode == 2 && TileSmemCp::total(k) <= (size_t)227 * 1024) {
+        const size_t smem_cp = TileSmemCp::total(k);
+        LARIS_CUDA(cudaFuncSetAttribute(spatial_obs_tile_cpasync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cp));
+        spatial_obs_tile_cpasync_kernel<<<grid, kTileConsumers, smem_cp, st>>>(S, ldS, k, plan, ntiles, nslabs, maxseg, partial.p,
+                                                                             rec_slab.p);
+        LARIS_LAUNCH_CHECK();
+        tile_records_reduce_kernel<<<nslabs, 5 * kSlabCols, 0, st>>>(partial.p, rec_slab.p, nrec, P, out);
+        LARIS_LAUNCH_CHECK();
+        return LARIS_OK;
+    }
+    if (mode == 2) mode = 1;                                      // k 13..15: the three plan buffers do not fit
     const size_t smem = TileSmem::total(k);
     LARIS_CUDA(cudaFuncSetAttribute(spatial_obs_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // 2-D tensor map of S for the gather4 staging: [n rows][ldS columns] fp32, box = 64 columns x 1 row (four rows per
     // operation come from the instruction's four row coordinates); columns past ldS are zero-filled by the TMA engine
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    int gather4 = tile_staging_mode();
+    int gather4 = mode;
     if (gather4) {
         const int rc = encode_row_gather_map(&tmap, S, ldS, n);
         if (rc) gather4 = 0;                                      // driver without tensor-map support: 1-D bulk copies

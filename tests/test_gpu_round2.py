@@ -169,6 +169,21 @@ def test_batched_stats_equal_legacy_and_oracle(dev, n, P, k, use_order):
     assert np.allclose(scr, both[0], rtol=1e-6, atol=1e-9) and np.array_equal(scr[4], legacy[4])
 
 
+@pytest.mark.parametrize("mode", ["bulk", "gather4", "cpasync"])
+def test_tile_staging_modes_agree(dev, mode):
+    """The three ways the tiled K4a brings neighbour rows into shared memory (1-D bulk copies, TMA tile::gather4 through a
+    tensor map, cp.async) give the legacy kernel's numbers; the mode is fixed per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, LARIS_B200_K4A_STAGING=mode)
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "time_k4.py"), "30001", "131", "10"], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert f"staging={mode}" in out.stdout and "equal=True" in out.stdout, out.stdout
+
+
 def test_observed_stats_on_padded_radius_rows(dev):
     """Fixed-degree rows padded with (own row, weight 0) edges - the radius-graph layout - through the tiled pass."""
     from laris_b200 import _kernels as K, engine

@@ -1,5 +1,5 @@
 """Device time of the observed-statistics pass (tiled K4a, both staging modes) and of the legacy kernel on synthetic
-scores of a given shape:  [LARIS_B200_K4A_STAGING=bulk|gather4] python tools/time_k4.py [n] [P] [k]"""
+scores of a given shape:  [LARIS_B200_K4A_STAGING=bulk|gather4|cpasync] python tools/time_k4.py [n] [P] [k]"""
 import os
 import sys
 
@@ -33,7 +33,7 @@ def timed(fn, reps=5):
     return min(ts), out
 
 
-mode = os.environ.get("LARIS_B200_K4A_STAGING", "gather4")
+mode = os.environ.get("LARIS_B200_K4A_STAGING", "cpasync")
 t_new, a = timed(lambda: K.spatial_stats_batched(S, P, g.idx, g.w, g.order))
 t_old, b = timed(lambda: K.spatial_stats(S, P, g.idx, g.w, False, g.order))
 ok = bool(torch.allclose(a[0], b, rtol=1e-5))
