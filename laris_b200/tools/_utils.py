@@ -756,10 +756,19 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
 
     def rows_in_table_order(host_inter, host_flat):
         """Row order of the reference's result: melt order (pair-major, receiver-major, sender fastest), stably
-        sorted by the pre-weight score and then by the final score, both descending (:1422, :1472)."""
+        sorted by the pre-weight score and then by the final score, both descending (:1422, :1472).  The reference's own
+        sorts are unstable (pandas quicksort), so the order among EQUAL final scores is not defined by it; here the
+        thresholded-away rows (score exactly 0, the bulk of the table) keep melt order and only the rows with a positive
+        score go through the two stable sorts."""
         melt = np.arange(npair * L).reshape(npair, C, C).transpose(0, 2, 1).reshape(-1)     # [pair, r, s] -> flat [pair, s, r]
-        o1 = melt[np.argsort(-host_inter.reshape(-1)[melt], kind="stable")]
-        return o1[np.argsort(-host_flat.reshape(-1)[o1], kind="stable")]
+        fm = host_flat.reshape(-1)[melt]
+        if (fm < 0).any() or np.isnan(fm).any():             # negative / NaN scores can only occur with exotic thresholds
+            o1 = melt[np.argsort(-host_inter.reshape(-1)[melt], kind="stable")]
+            return o1[np.argsort(-host_flat.reshape(-1)[o1], kind="stable")]
+        pos = melt[fm > 0]
+        o1 = pos[np.argsort(-host_inter.reshape(-1)[pos], kind="stable")]
+        o2 = o1[np.argsort(-host_flat.reshape(-1)[o1], kind="stable")]
+        return np.concatenate([o2, melt[fm == 0]])
 
     result = {"pair_id": pair_id, "C": C, "cats": cats_arr, "ligand": lig, "receptor": rec, "interaction_name": inter_names,
               "interaction_score": flat_d, "ctc_raw": raw_d}
