@@ -397,8 +397,13 @@ struct TileAcc {
 
 // one work item (128 cells x 64 columns) from the staged tile: T = sum_j w_j * row[slot_j] and the five sums, fp32 over the
 // four cells of this thread, fp64 across items.  `direct`: the tile's rows were not staged (union over the cap) - read global.
-__device__ __forceinline__ void tile_accumulate(TileAcc& A, const float4* tile_s, const int2* ent_s, const int32_t* self_s,
-                                                const float* S, int64_t ldS, int64_t col0, int k, int quad, int cl) {
+// KT > 0: k known at compile time - the edge words and the row quads of a cell are loaded in batches of 5 before the FMAs,
+// so the two dependent shared-memory latencies per edge overlap instead of forming a chain (the pass is latency-bound:
+// 16 warps per SM, ncu short-scoreboard stall 2.9 of 5.6 cycles per issue).
+template <int KT>
+__device__ __forceinline__ void tile_accumulate(TileAcc& A, const float4* __restrict__ tile_s, const int2* __restrict__ ent_s,
+                                                const int32_t* __restrict__ self_s, const float* __restrict__ S, int64_t ldS,
+                                                int64_t col0, int k, int quad, int cl) {
     if (!(col0 + quad * 4 < ldS)) return;
     const bool direct = self_s[kTileCells] < 0;
     float p_dot[4] = {0, 0, 0, 0}, p_ss[4] = {0, 0, 0, 0}, p_tt[4] = {0, 0, 0, 0}, p_s[4] = {0, 0, 0, 0};
@@ -411,11 +416,30 @@ __device__ __forceinline__ void tile_accumulate(TileAcc& A, const float4* tile_s
         float4 s, t = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!direct) {
             s = tile_s[sf * (kSlabCols / 4) + quad];
-            for (int j = 0; j < k; ++j) {
-                const int2 ej = e[j];
-                const float wj = __int_as_float(ej.y);
-                const float4 v = tile_s[ej.x * (kSlabCols / 4) + quad];
-                t.x = fmaf(wj, v.x, t.x); t.y = fmaf(wj, v.y, t.y); t.z = fmaf(wj, v.z, t.z); t.w = fmaf(wj, v.w, t.w);
+            if (KT > 0) {
+                constexpr int B = 5;
+#pragma unroll
+                for (int j0 = 0; j0 < KT; j0 += B) {
+                    int2 ej[B];
+                    float4 v[B];
+#pragma unroll
+                    for (int j = 0; j < B; ++j) if (j0 + j < KT) ej[j] = e[j0 + j];
+#pragma unroll
+                    for (int j = 0; j < B; ++j) if (j0 + j < KT) v[j] = tile_s[ej[j].x * (kSlabCols / 4) + quad];
+#pragma unroll
+                    for (int j = 0; j < B; ++j)
+                        if (j0 + j < KT) {
+                            const float wj = __int_as_float(ej[j].y);
+                            t.x = fmaf(wj, v[j].x, t.x); t.y = fmaf(wj, v[j].y, t.y); t.z = fmaf(wj, v[j].z, t.z); t.w = fmaf(wj, v[j].w, t.w);
+                        }
+                }
+            } else {
+                for (int j = 0; j < k; ++j) {
+                    const int2 ej = e[j];
+                    const float wj = __int_as_float(ej.y);
+                    const float4 v = tile_s[ej.x * (kSlabCols / 4) + quad];
+                    t.x = fmaf(wj, v.x, t.x); t.y = fmaf(wj, v.y, t.y); t.z = fmaf(wj, v.z, t.z); t.w = fmaf(wj, v.w, t.w);
+                }
             }
         } else {
             const float4* S4 = reinterpret_cast<const float4*>(S + col0) + quad;
@@ -561,7 +585,7 @@ spatial_obs_tile_kernel(const float* __restrict__ S, int64_t ldS, int k, TilePla
         const int64_t col0 = (int64_t)slab * kSlabCols;
         aio::mbar_wait(full0 + 8 * st, ph);
         const unsigned char* stage = smem + st * stage_b;
-        tile_accumulate(A, reinterpret_cast<const float4*>(stage),
+        tile_accumulate<0>(A, reinterpret_cast<const float4*>(stage),
                         reinterpret_cast<const int2*>(stage + (size_t)kTileCap * kSlabCols * 4),
                         reinterpret_cast<const int32_t*>(stage + (size_t)kTileCap * kSlabCols * 4 + ent_bytes), S, ldS, col0, k,
                         quad, cl);
@@ -596,6 +620,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+template <int KT>
 __global__ void __launch_bounds__(kTileConsumers, 1)
 spatial_obs_tile_cpasync_kernel(const float* __restrict__ S, int64_t ldS, int k, TilePlan plan, int64_t ntiles, int nslabs,
                                 int maxseg, double* __restrict__ partial, int32_t* __restrict__ rec_slab) {
@@ -659,7 +684,7 @@ spatial_obs_tile_cpasync_kernel(const float* __restrict__ S, int64_t ldS, int k,
         __syncthreads();
         const int slab = (int)(wi / ntiles);
         const unsigned char* pl = plan_base + (size_t)(it % 3) * plan_b;
-        tile_accumulate(A, reinterpret_cast<const float4*>(tile_base + (size_t)(it & 1) * tile_b),
+        tile_accumulate<KT>(A, reinterpret_cast<const float4*>(tile_base + (size_t)(it & 1) * tile_b),
                         reinterpret_cast<const int2*>(pl + rows_bytes), reinterpret_cast<const int32_t*>(pl + rows_bytes + ent_bytes),
                         S, ldS, (int64_t)slab * kSlabCols, k, quad, cl);
         if (wi + 1 == w1 || (wi + 1) / ntiles != slab) {
@@ -802,9 +827,10 @@ static int observed_stats_tiled(const float* S, int64_t ldS, int64_t n, int32_t 
     int mode = tile_staging_mode();
     if (mode == 2 && TileSmemCp::total(k) <= (size_t)227 * 1024) {
         const size_t smem_cp = TileSmemCp::total(k);
-        LARIS_CUDA(cudaFuncSetAttribute(spatial_obs_tile_cpasync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cp));
-        spatial_obs_tile_cpasync_kernel<<<grid, kTileConsumers, smem_cp, st>>>(S, ldS, k, plan, ntiles, nslabs, maxseg, partial.p,
-                                                                             rec_slab.p);
+        auto kern = k == 10 ? spatial_obs_tile_cpasync_kernel<10> : k == 8 ? spatial_obs_tile_cpasync_kernel<8>
+                  : k == 6 ? spatial_obs_tile_cpasync_kernel<6> : spatial_obs_tile_cpasync_kernel<0>;
+        LARIS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cp));
+        kern<<<grid, kTileConsumers, smem_cp, st>>>(S, ldS, k, plan, ntiles, nslabs, maxseg, partial.p, rec_slab.p);
         LARIS_LAUNCH_CHECK();
         tile_records_reduce_kernel<<<nslabs, 5 * kSlabCols, 0, st>>>(partial.p, rec_slab.p, nrec, P, out);
         LARIS_LAUNCH_CHECK();
