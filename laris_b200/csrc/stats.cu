@@ -271,6 +271,132 @@ null_stats_reduce_kernel(const double* __restrict__ partial, int nchunks, int64_
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// K4b from L2.  The random neighbour rows of the null cannot be cached when every gather drags a whole 4*P-byte row
+// through the SM - but a BLOCK of 16 or 32 columns of S (64 / 128 bytes per row, n rows) fits the 126 MB L2 for n up to
+// ~1.6e6 cells.  Measured on B200 (tools/probes/l2_gather_probe.cu): random 128-byte row gathers run at 14.7-17 TB/s from a
+// working set of <= 128 MB, against 5.4-6.8 TB/s from HBM.  So the pass is run once per column block (one launch per
+// block: the stream order is the grid-wide barrier that keeps all SMs on the same block): the block is read from HBM
+// once (compulsory misses) and the R*k gathers per cell are L2 hits.  Thread mapping: a warp covers 4 (8) rows x 8 (4)
+// column quads, a thread owns one quad of the rows of its lane; the R*k (index, weight) pairs of a batch of rows are
+// staged in shared memory.  HBM bytes: 4nP (S once) + 8nkR per column block (the edge lists are re-read per block).
+// ---------------------------------------------------------------------------------------------------------
+template <int RB, int QUADS>
+__global__ void __launch_bounds__(256)
+spatial_null_stats_l2_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t n, int64_t q0, int nq,
+                             const int32_t* __restrict__ nidx, const float* __restrict__ nw, int k,
+                             double* __restrict__ partial /*[grid][2*RB+3][QUADS*4]*/) {
+    constexpr int ROWS = 256 / QUADS, Q = 2 * RB + 3, WB = QUADS * 4;
+    extern __shared__ __align__(16) unsigned char l2_smem[];
+    int32_t* s_idx = reinterpret_cast<int32_t*>(l2_smem);                         // [RB][ROWS][k]
+    float* s_w = reinterpret_cast<float*>(l2_smem) + (size_t)RB * ROWS * k;
+    const int tid = threadIdx.x, quad = tid % QUADS, rl = tid / QUADS;
+    const bool col_ok = quad < nq;
+    double a_dot[RB][4], a_tt[RB][4], a_ss[4] = {0, 0, 0, 0}, a_s[4] = {0, 0, 0, 0};
+    int a_nz[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int r = 0; r < RB; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { a_dot[r][c] = 0.0; a_tt[r][c] = 0.0; }
+    const int64_t nk = n * (int64_t)k;
+    const float4* base = S4 + q0 + quad;
+    for (int64_t b = blockIdx.x; b * ROWS < n; b += gridDim.x) {
+        const int64_t i0 = b * ROWS;
+        const int rows = (int)min((int64_t)ROWS, n - i0);
+        __syncthreads();
+        for (int r = 0; r < RB; ++r)
+            for (int e = tid; e < rows * k; e += 256) {
+                s_idx[(r * ROWS) * k + e] = nidx[(int64_t)r * nk + i0 * k + e];
+                s_w[(r * ROWS) * k + e] = nw[(int64_t)r * nk + i0 * k + e];
+            }
+        __syncthreads();
+        if (rl >= rows || !col_ok) continue;
+        const float4 s = ld_stream_f4(base + (i0 + rl) * ld4);
+        const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            const int32_t* ni = s_idx + (r * ROWS + rl) * k;
+            const float* wv = s_w + (r * ROWS + rl) * k;
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            float wsum = 0.f;
+            int j = 0;
+            for (; j + 5 <= k; j += 5) {
+                float4 v[5];
+#pragma unroll
+                for (int u = 0; u < 5; ++u) v[u] = ld_stream_f4(base + (int64_t)ni[j + u] * ld4);
+#pragma unroll
+                for (int u = 0; u < 5; ++u) {
+                    const float w0 = wv[j + u];
+                    t.x = fmaf(w0, v[u].x, t.x); t.y = fmaf(w0, v[u].y, t.y); t.z = fmaf(w0, v[u].z, t.z); t.w = fmaf(w0, v[u].w, t.w);
+                    wsum += w0;
+                }
+            }
+            for (; j < k; ++j) {
+                const float4 v0 = ld_stream_f4(base + (int64_t)ni[j] * ld4);
+                const float w0 = wv[j];
+                t.x = fmaf(w0, v0.x, t.x); t.y = fmaf(w0, v0.y, t.y); t.z = fmaf(w0, v0.z, t.z); t.w = fmaf(w0, v0.w, t.w);
+                wsum += w0;
+            }
+            if (wsum != 0.f) {                                       // L1 row normalisation of the random graph
+                const float inv = 1.0f / wsum;
+                t.x *= inv; t.y *= inv; t.z *= inv; t.w *= inv;
+            }
+            const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                a_dot[r][c] += (double)(sv[c] * tv[c]);
+                a_tt[r][c] += (double)(tv[c] * tv[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            a_ss[c] += (double)(sv[c] * sv[c]);
+            a_s[c] += (double)sv[c];
+            a_nz[c] += sv[c] != 0.f ? 1 : 0;
+        }
+    }
+    // the ROWS row lanes of every quad, summed in lane order; one partial row block per CTA
+    __syncthreads();
+    double* red = reinterpret_cast<double*>(l2_smem);                // [ROWS][QUADS][4] doubles = 8 KB, re-uses the staging area
+    double* out = partial + (int64_t)blockIdx.x * Q * WB;
+#pragma unroll
+    for (int stat = 0; stat < Q; ++stat) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double v;
+            if (stat < 2 * RB) v = (stat & 1) ? a_tt[stat >> 1][c] : a_dot[stat >> 1][c];
+            else v = stat == 2 * RB ? a_ss[c] : stat == 2 * RB + 1 ? a_s[c] : (double)a_nz[c];
+            red[(rl * QUADS + quad) * 4 + c] = v;
+        }
+        __syncthreads();
+        if (tid < WB) {
+            double t = 0.0;
+            for (int r = 0; r < ROWS; ++r) t += red[r * WB + tid];
+            out[stat * WB + tid] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// partial [nblk][ncta][2*RB+3][WB] -> out rows [RB][5][P]
+__global__ void __launch_bounds__(256)
+null_l2_reduce_kernel(const double* __restrict__ partial, int nblk, int ncta, int WB, int P, int RB, double* __restrict__ out) {
+    const int Q = 2 * RB + 3;
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;           // (blk, stat, col)
+    if (e >= (int64_t)nblk * Q * WB) return;
+    const int col = (int)(e % WB), stat = (int)((e / WB) % Q), blk = (int)(e / ((int64_t)WB * Q));
+    const int p = blk * WB + col;
+    if (p >= P) return;
+    double t = 0.0;
+    for (int c = 0; c < ncta; ++c) t += partial[(((int64_t)blk * ncta + c) * Q + stat) * WB + col];
+    if (stat < 2 * RB) {
+        out[((int64_t)(stat >> 1) * 5 + ((stat & 1) ? 2 : 0)) * P + p] = t;
+    } else {
+        const int which = stat == 2 * RB ? 1 : (stat == 2 * RB + 1 ? 3 : 4);
+        for (int r = 0; r < RB; ++r) out[((int64_t)r * 5 + which) * P + p] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // K4a tiled: observed-graph statistics with the neighbour rows staged in shared memory by the TMA engine.
 //
 // The graph is spatial and `order` walks the tissue, so the k neighbours of kTileCells consecutive cells are
@@ -856,9 +982,54 @@ static int observed_stats_tiled(const float* S, int64_t ldS, int64_t n, int32_t 
     return LARIS_OK;
 }
 
+// bytes of one column block (n rows x WB columns) that still gather from L2 at full rate (probe: 128-byte rows hold
+// 14.7 TB/s at 128 MB, 64-byte rows 16.8 TB/s at 64 MB and 9.8 TB/s at 96 MB)
+static int null_l2_quads(int64_t n) {
+    static int mode = -1;                                   // LARIS_B200_K4B=hbm forces the streaming kernel (A/B measurements)
+    if (mode < 0) {
+        const char* e = getenv("LARIS_B200_K4B");
+        mode = (e && strcmp(e, "hbm") == 0) ? 0 : 1;
+    }
+    if (!mode) return 0;
+    if (n * 128 <= (int64_t)136 << 20) return 8;            // 32-column blocks
+    if (n * 64 <= (int64_t)80 << 20) return 4;              // 16-column blocks
+    return 0;                                               // the block would not stay in L2: stream from HBM
+}
+
+template <int RB, int QUADS>
+static int null_stats_batch_l2(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* nidx, const float* nw, int k,
+                               double* out, cudaStream_t st) {
+    constexpr int Q = 2 * RB + 3, WB = QUADS * 4, ROWS = 256 / QUADS;
+    const int64_t ld4 = ldS / 4;
+    int dev = 0, sms = kNumSMs;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t ncta = (int64_t)sms * 4;
+    if (ncta > ceil_div(n, ROWS)) ncta = ceil_div(n, ROWS);
+    const int nblk = (int)ceil_div(ld4, QUADS);
+    Scratch<double> partial(st);
+    LARIS_CUDA(partial.alloc((size_t)nblk * ncta * Q * WB));
+    size_t smem = (size_t)RB * ROWS * k * 8;
+    if (smem < (size_t)ROWS * WB * 8) smem = (size_t)ROWS * WB * 8;
+    LARIS_CUDA(cudaFuncSetAttribute(spatial_null_stats_l2_kernel<RB, QUADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int blk = 0; blk < nblk; ++blk) {
+        const int64_t q0 = (int64_t)blk * QUADS;
+        const int nq = (int)(ld4 - q0 < QUADS ? ld4 - q0 : QUADS);
+        spatial_null_stats_l2_kernel<RB, QUADS><<<(unsigned)ncta, 256, smem, st>>>(
+            (const float4*)S, ld4, n, q0, nq, nidx, nw, k, partial.p + (size_t)blk * ncta * Q * WB);
+        LARIS_LAUNCH_CHECK();
+    }
+    null_l2_reduce_kernel<<<(unsigned)ceil_div((int64_t)nblk * Q * WB, 256), 256, 0, st>>>(partial.p, nblk, (int)ncta, WB, P, RB, out);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
 template <int RB>
 static int null_stats_batch(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* nidx, const float* nw, int k,
                             double* out, cudaStream_t st) {
+    const int quads = null_l2_quads(n);
+    if (quads == 8) return null_stats_batch_l2<RB, 8>(S, ldS, n, P, nidx, nw, k, out, st);
+    if (quads == 4) return null_stats_batch_l2<RB, 4>(S, ldS, n, P, nidx, nw, k, out, st);
     const int64_t ld4 = ldS / 4;
     const int slabs = (int)ceil_div(ld4, kStThreads);
     int dev = 0, sms = kNumSMs;
