@@ -196,7 +196,10 @@ def lr_column_layout(lig_u, rec_u, n_genes):
 
 
 def padded_ld(P):
-    return (P + 7) // 8 * 8
+    """Row stride of the dense score matrix: a multiple of 32 floats, so every 32-column block of a row is one aligned
+    128-byte line (the column-blocked null pass keeps such blocks L2-resident; a row piece that straddles two lines
+    would cost two tags)."""
+    return (P + 31) // 32 * 32
 
 
 def _cx_args(cx):

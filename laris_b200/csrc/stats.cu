@@ -280,93 +280,108 @@ null_stats_reduce_kernel(const double* __restrict__ partial, int nchunks, int64_
 // column quads, a thread owns one quad of the rows of its lane; the R*k (index, weight) pairs of a batch of rows are
 // staged in shared memory.  HBM bytes: 4nP (S once) + 8nkR per column block (the edge lists are re-read per block).
 // ---------------------------------------------------------------------------------------------------------
-template <int RB, int QUADS>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// One (column block, repeat) per launch.  The edge lists of the NEXT batch of rows are brought into shared memory by
+// cp.async while the current batch gathers, a thread keeps ten 128-bit L2 gathers in flight, and its sums stay in fp32
+// (a thread sees <= 64 rows per launch; the CTA reduction and everything after it is fp64): ~75 registers, three CTAs
+// per SM.  FIRST: also sum S^2, sum S and nnz of the block (needed once, not per repeat).
+template <int QUADS, bool FIRST>
+__global__ void __launch_bounds__(256, 3)
 spatial_null_stats_l2_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t n, int64_t q0, int nq,
                              const int32_t* __restrict__ nidx, const float* __restrict__ nw, int k,
-                             double* __restrict__ partial /*[grid][2*RB+3][QUADS*4]*/) {
-    constexpr int ROWS = 256 / QUADS, Q = 2 * RB + 3, WB = QUADS * 4;
+                             double* __restrict__ partial /*[grid][5][QUADS*4]*/) {
+    constexpr int ROWS = 256 / QUADS, WB = QUADS * 4;
     extern __shared__ __align__(16) unsigned char l2_smem[];
-    int32_t* s_idx = reinterpret_cast<int32_t*>(l2_smem);                         // [RB][ROWS][k]
-    float* s_w = reinterpret_cast<float*>(l2_smem) + (size_t)RB * ROWS * k;
     const int tid = threadIdx.x, quad = tid % QUADS, rl = tid / QUADS;
     const bool col_ok = quad < nq;
-    double a_dot[RB][4], a_tt[RB][4], a_ss[4] = {0, 0, 0, 0}, a_s[4] = {0, 0, 0, 0};
+    const int per_buf = ROWS * k;                                    // idx then w, per buffer
+    int32_t* s_idx = reinterpret_cast<int32_t*>(l2_smem);
+    float* s_w = reinterpret_cast<float*>(l2_smem) + 2 * per_buf;
+    float a_dot[4] = {0, 0, 0, 0}, a_tt[4] = {0, 0, 0, 0}, a_ss[4] = {0, 0, 0, 0}, a_s[4] = {0, 0, 0, 0};
     int a_nz[4] = {0, 0, 0, 0};
-#pragma unroll
-    for (int r = 0; r < RB; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) { a_dot[r][c] = 0.0; a_tt[r][c] = 0.0; }
-    const int64_t nk = n * (int64_t)k;
     const float4* base = S4 + q0 + quad;
-    for (int64_t b = blockIdx.x; b * ROWS < n; b += gridDim.x) {
+    auto stage = [&](int64_t b, int buf) {
         const int64_t i0 = b * ROWS;
-        const int rows = (int)min((int64_t)ROWS, n - i0);
-        __syncthreads();
-        for (int r = 0; r < RB; ++r)
-            for (int e = tid; e < rows * k; e += 256) {
-                s_idx[(r * ROWS) * k + e] = nidx[(int64_t)r * nk + i0 * k + e];
-                s_w[(r * ROWS) * k + e] = nw[(int64_t)r * nk + i0 * k + e];
+        if (i0 < n) {
+            const int cnt = (int)min((int64_t)ROWS, n - i0) * k;
+            const uint32_t di = aio::smem_addr(s_idx + buf * per_buf), dw = aio::smem_addr(s_w + buf * per_buf);
+            for (int e = tid; e < cnt; e += 256) {
+                cp_async4(di + 4 * e, nidx + i0 * k + e);
+                cp_async4(dw + 4 * e, nw + i0 * k + e);
             }
+        }
+        cp_async_commit_group();
+    };
+    stage(blockIdx.x, 0);
+    int buf = 0;
+    for (int64_t b = blockIdx.x; b * ROWS < n; b += gridDim.x, buf ^= 1) {
+        stage(b + gridDim.x, buf ^ 1);
+        cp_async_wait_group<1>();
         __syncthreads();
-        if (rl >= rows || !col_ok) continue;
-        const float4 s = ld_stream_f4(base + (i0 + rl) * ld4);
-        const float sv[4] = {s.x, s.y, s.z, s.w};
-#pragma unroll
-        for (int r = 0; r < RB; ++r) {
-            const int32_t* ni = s_idx + (r * ROWS + rl) * k;
-            const float* wv = s_w + (r * ROWS + rl) * k;
+        const int64_t i = b * ROWS + rl;
+        if (i < n && col_ok) {
+            const int32_t* ni = s_idx + buf * per_buf + rl * k;
+            const float* wv = s_w + buf * per_buf + rl * k;
+            const float4 s = ld_stream_f4(base + i * ld4);
             float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-            float wsum = 0.f;
+            float wsum = 0.f;                                        // same association as the streaming kernel
+            {
+                int j = 0;
+                for (; j + 4 <= k; j += 4) wsum += (wv[j] + wv[j + 1]) + (wv[j + 2] + wv[j + 3]);
+                for (; j < k; ++j) wsum += wv[j];
+            }
             int j = 0;
-            for (; j + 5 <= k; j += 5) {
-                float4 v[5];
+            for (; j + 10 <= k; j += 10) {                           // ten independent 128-bit L2 gathers in flight
+                float4 v[10];
 #pragma unroll
-                for (int u = 0; u < 5; ++u) v[u] = ld_stream_f4(base + (int64_t)ni[j + u] * ld4);
+                for (int u = 0; u < 10; ++u) v[u] = ld_stream_f4(base + (int64_t)ni[j + u] * ld4);
 #pragma unroll
-                for (int u = 0; u < 5; ++u) {
+                for (int u = 0; u < 10; ++u) {
                     const float w0 = wv[j + u];
                     t.x = fmaf(w0, v[u].x, t.x); t.y = fmaf(w0, v[u].y, t.y); t.z = fmaf(w0, v[u].z, t.z); t.w = fmaf(w0, v[u].w, t.w);
-                    wsum += w0;
                 }
             }
             for (; j < k; ++j) {
                 const float4 v0 = ld_stream_f4(base + (int64_t)ni[j] * ld4);
                 const float w0 = wv[j];
                 t.x = fmaf(w0, v0.x, t.x); t.y = fmaf(w0, v0.y, t.y); t.z = fmaf(w0, v0.z, t.z); t.w = fmaf(w0, v0.w, t.w);
-                wsum += w0;
             }
             if (wsum != 0.f) {                                       // L1 row normalisation of the random graph
                 const float inv = 1.0f / wsum;
                 t.x *= inv; t.y *= inv; t.z *= inv; t.w *= inv;
             }
-            const float tv[4] = {t.x, t.y, t.z, t.w};
+            const float sv[4] = {s.x, s.y, s.z, s.w}, tv[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                a_dot[r][c] += (double)(sv[c] * tv[c]);
-                a_tt[r][c] += (double)(tv[c] * tv[c]);
+                a_dot[c] = fmaf(sv[c], tv[c], a_dot[c]);
+                a_tt[c] = fmaf(tv[c], tv[c], a_tt[c]);
+                if (FIRST) {
+                    a_ss[c] = fmaf(sv[c], sv[c], a_ss[c]);
+                    a_s[c] += sv[c];
+                    a_nz[c] += sv[c] != 0.f ? 1 : 0;
+                }
             }
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            a_ss[c] += (double)(sv[c] * sv[c]);
-            a_s[c] += (double)sv[c];
-            a_nz[c] += sv[c] != 0.f ? 1 : 0;
-        }
+        __syncthreads();                                             // buffer `buf` is refilled two iterations from now
     }
-    // the ROWS row lanes of every quad, summed in lane order; one partial row block per CTA
+    cp_async_wait_group<0>();
     __syncthreads();
-    double* red = reinterpret_cast<double*>(l2_smem);                // [ROWS][QUADS][4] doubles = 8 KB, re-uses the staging area
-    double* out = partial + (int64_t)blockIdx.x * Q * WB;
+    // the ROWS row lanes of every quad, summed in lane order in fp64; one partial row block per CTA
+    double* red = reinterpret_cast<double*>(l2_smem);                // [ROWS][WB] doubles = 8 KB
+    double* out = partial + (int64_t)blockIdx.x * 5 * WB;
 #pragma unroll
-    for (int stat = 0; stat < Q; ++stat) {
+    for (int stat = 0; stat < 5; ++stat) {
+        if (!FIRST && stat != 0 && stat != 2) continue;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            double v;
-            if (stat < 2 * RB) v = (stat & 1) ? a_tt[stat >> 1][c] : a_dot[stat >> 1][c];
-            else v = stat == 2 * RB ? a_ss[c] : stat == 2 * RB + 1 ? a_s[c] : (double)a_nz[c];
-            red[(rl * QUADS + quad) * 4 + c] = v;
-        }
+        for (int c = 0; c < 4; ++c)
+            red[(rl * QUADS + quad) * 4 + c] = stat == 0 ? (double)a_dot[c] : stat == 1 ? (double)a_ss[c] : stat == 2 ? (double)a_tt[c]
+                                               : stat == 3 ? (double)a_s[c] : (double)a_nz[c];
         __syncthreads();
         if (tid < WB) {
             double t = 0.0;
@@ -377,23 +392,18 @@ spatial_null_stats_l2_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t
     }
 }
 
-// partial [nblk][ncta][2*RB+3][WB] -> out rows [RB][5][P]
+// partial [nblk][R][ncta][5][WB] -> out rows [R][5][P]; sum S^2 / sum S / nnz come from repeat 0's launch
 __global__ void __launch_bounds__(256)
-null_l2_reduce_kernel(const double* __restrict__ partial, int nblk, int ncta, int WB, int P, int RB, double* __restrict__ out) {
-    const int Q = 2 * RB + 3;
-    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;           // (blk, stat, col)
-    if (e >= (int64_t)nblk * Q * WB) return;
-    const int col = (int)(e % WB), stat = (int)((e / WB) % Q), blk = (int)(e / ((int64_t)WB * Q));
+null_l2_reduce_kernel(const double* __restrict__ partial, int nblk, int R, int ncta, int WB, int P, double* __restrict__ out) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;           // (blk, r, stat, col)
+    if (e >= (int64_t)nblk * R * 5 * WB) return;
+    const int col = (int)(e % WB), stat = (int)((e / WB) % 5), r = (int)((e / (5 * WB)) % R), blk = (int)(e / ((int64_t)5 * WB * R));
     const int p = blk * WB + col;
     if (p >= P) return;
+    const int src_r = (stat == 0 || stat == 2) ? r : 0;
     double t = 0.0;
-    for (int c = 0; c < ncta; ++c) t += partial[(((int64_t)blk * ncta + c) * Q + stat) * WB + col];
-    if (stat < 2 * RB) {
-        out[((int64_t)(stat >> 1) * 5 + ((stat & 1) ? 2 : 0)) * P + p] = t;
-    } else {
-        const int which = stat == 2 * RB ? 1 : (stat == 2 * RB + 1 ? 3 : 4);
-        for (int r = 0; r < RB; ++r) out[((int64_t)r * 5 + which) * P + p] = t;
-    }
+    for (int c = 0; c < ncta; ++c) t += partial[((((int64_t)blk * R + src_r) * ncta + c) * 5 + stat) * WB + col];
+    out[((int64_t)r * 5 + stat) * P + p] = t;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -996,30 +1006,39 @@ static int null_l2_quads(int64_t n) {
     return 0;                                               // the block would not stay in L2: stream from HBM
 }
 
-template <int RB, int QUADS>
-static int null_stats_batch_l2(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* nidx, const float* nw, int k,
-                               double* out, cudaStream_t st) {
-    constexpr int Q = 2 * RB + 3, WB = QUADS * 4, ROWS = 256 / QUADS;
-    const int64_t ld4 = ldS / 4;
+template <int QUADS>
+static int null_stats_l2(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* nidx, const float* nw, int k, int R,
+                         double* out, cudaStream_t st) {
+    constexpr int WB = QUADS * 4, ROWS = 256 / QUADS;
+    const int64_t ld4 = ldS / 4, nk = n * (int64_t)k;
     int dev = 0, sms = kNumSMs;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int64_t ncta = (int64_t)sms * 4;
+    int64_t ncta = (int64_t)sms * 3;
+    if (ncta < ceil_div(n, (int64_t)ROWS * 64)) ncta = ceil_div(n, (int64_t)ROWS * 64);   // <= 64 rows per thread: fp32 partials
     if (ncta > ceil_div(n, ROWS)) ncta = ceil_div(n, ROWS);
     const int nblk = (int)ceil_div(ld4, QUADS);
     Scratch<double> partial(st);
-    LARIS_CUDA(partial.alloc((size_t)nblk * ncta * Q * WB));
-    size_t smem = (size_t)RB * ROWS * k * 8;
+    LARIS_CUDA(partial.alloc((size_t)nblk * R * ncta * 5 * WB));
+    size_t smem = (size_t)4 * ROWS * k * 4;                                              // two buffers of (idx, w)
     if (smem < (size_t)ROWS * WB * 8) smem = (size_t)ROWS * WB * 8;
-    LARIS_CUDA(cudaFuncSetAttribute(spatial_null_stats_l2_kernel<RB, QUADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARIS_CUDA(cudaFuncSetAttribute(spatial_null_stats_l2_kernel<QUADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARIS_CUDA(cudaFuncSetAttribute(spatial_null_stats_l2_kernel<QUADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int blk = 0; blk < nblk; ++blk) {
         const int64_t q0 = (int64_t)blk * QUADS;
         const int nq = (int)(ld4 - q0 < QUADS ? ld4 - q0 : QUADS);
-        spatial_null_stats_l2_kernel<RB, QUADS><<<(unsigned)ncta, 256, smem, st>>>(
-            (const float4*)S, ld4, n, q0, nq, nidx, nw, k, partial.p + (size_t)blk * ncta * Q * WB);
-        LARIS_LAUNCH_CHECK();
+        for (int r = 0; r < R; ++r) {                      // the block's 30 gathers per cell, one repeat per launch, all L2 hits
+            double* dst = partial.p + ((size_t)blk * R + r) * ncta * 5 * WB;
+            if (r == 0)
+                spatial_null_stats_l2_kernel<QUADS, true><<<(unsigned)ncta, 256, smem, st>>>((const float4*)S, ld4, n, q0, nq, nidx,
+                                                                                            nw, k, dst);
+            else
+                spatial_null_stats_l2_kernel<QUADS, false><<<(unsigned)ncta, 256, smem, st>>>(
+                    (const float4*)S, ld4, n, q0, nq, nidx + (int64_t)r * nk, nw + (int64_t)r * nk, k, dst);
+            LARIS_LAUNCH_CHECK();
+        }
     }
-    null_l2_reduce_kernel<<<(unsigned)ceil_div((int64_t)nblk * Q * WB, 256), 256, 0, st>>>(partial.p, nblk, (int)ncta, WB, P, RB, out);
+    null_l2_reduce_kernel<<<(unsigned)ceil_div((int64_t)nblk * R * 5 * WB, 256), 256, 0, st>>>(partial.p, nblk, R, (int)ncta, WB, P, out);
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
 }
@@ -1027,9 +1046,6 @@ static int null_stats_batch_l2(const float* S, int64_t ldS, int64_t n, int32_t P
 template <int RB>
 static int null_stats_batch(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* nidx, const float* nw, int k,
                             double* out, cudaStream_t st) {
-    const int quads = null_l2_quads(n);
-    if (quads == 8) return null_stats_batch_l2<RB, 8>(S, ldS, n, P, nidx, nw, k, out, st);
-    if (quads == 4) return null_stats_batch_l2<RB, 4>(S, ldS, n, P, nidx, nw, k, out, st);
     const int64_t ld4 = ldS / 4;
     const int slabs = (int)ceil_div(ld4, kStThreads);
     int dev = 0, sms = kNumSMs;
@@ -1068,6 +1084,12 @@ extern "C" int laris_spatial_stats_batched(const float* S, int64_t ldS, int64_t 
         row0 = 1;
     }
     const int64_t nk = n * (int64_t)k;
+    const int quads = n_repeats > 0 ? null_l2_quads(n) : 0;
+    if (quads) {
+        double* o = out + (int64_t)row0 * 5 * P;
+        return quads == 8 ? null_stats_l2<8>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st)
+                          : null_stats_l2<4>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st);
+    }
     for (int r = 0; r < n_repeats;) {
         const int rb = n_repeats - r >= 3 ? 3 : n_repeats - r;
         double* o = out + (int64_t)(row0 + r) * 5 * P;

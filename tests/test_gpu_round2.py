@@ -160,7 +160,9 @@ def test_batched_stats_equal_legacy_and_oracle(dev, n, P, k, use_order):
     assert np.allclose(engine._cosine(both[0]), ref, rtol=RTOL, atol=1e-9)
     for r in range(R_):
         one = K.spatial_stats(sm.S, P, cols[r].contiguous(), wts[r].contiguous(), True, None).cpu().numpy()
-        assert np.allclose(both[1 + r], one, rtol=1e-12, atol=1e-300)
+        # the column-blocked (L2-resident) null pass keeps fp32 partial sums over <= 64 rows per thread
+        assert np.allclose(both[1 + r], one, rtol=2e-6, atol=1e-300)
+        assert np.array_equal(both[1 + r][4], one[4])
     only_null = K.spatial_stats_batched(sm.S, P, None, None, None, cols, wts).cpu().numpy()
     assert np.array_equal(only_null, both[1:])
     # a scrambled processing order: tiles are no longer local, the union of neighbour rows exceeds the staging cap

@@ -36,7 +36,7 @@ def timed(fn, reps=4):
 
 t_new, a = timed(lambda: K.spatial_stats_batched(S, P, None, None, None, cols, wts))
 ref = torch.stack([K.spatial_stats(S, P, cols[r].contiguous(), wts[r].contiguous(), True, None) for r in range(R)])
-ok = bool(torch.allclose(a, ref, rtol=1e-9, atol=1e-300))
+ok = bool(torch.allclose(a, ref, rtol=2e-6, atol=1e-300))
 gb = (4.0 * (1 + R * k) * n * P + 8.0 * n * k * R) / 1e9
 print(f"n={n} P={P} k={k} R={R} mode={os.environ.get('LARIS_B200_K4B', 'l2')}: {t_new:.3f} ms "
       f"({gb / t_new * 1e3:.0f} GB/s of algorithmic bytes), equal to the per-repeat kernel={ok}")
