@@ -995,14 +995,18 @@ static int observed_stats_tiled(const float* S, int64_t ldS, int64_t n, int32_t 
 // bytes of one column block (n rows x WB columns) that still gather from L2 at full rate (probe: 128-byte rows hold
 // 14.7 TB/s at 128 MB, 64-byte rows 16.8 TB/s at 64 MB and 9.8 TB/s at 96 MB)
 static int null_l2_quads(int64_t n) {
-    static int mode = -1;                                   // LARIS_B200_K4B=hbm forces the streaming kernel (A/B measurements)
+    static int mode = -1;                 // LARIS_B200_K4B=hbm forces the streaming kernel, =q2|q4|q8 a block width (A/B runs)
     if (mode < 0) {
         const char* e = getenv("LARIS_B200_K4B");
-        mode = (e && strcmp(e, "hbm") == 0) ? 0 : 1;
+        mode = !e ? 1 : strcmp(e, "hbm") == 0 ? 0 : strcmp(e, "q2") == 0 ? 2 : strcmp(e, "q4") == 0 ? 4 : strcmp(e, "q8") == 0 ? 8 : 1;
     }
-    if (!mode) return 0;
-    if (n * 128 <= (int64_t)136 << 20) return 8;            // 32-column blocks
-    if (n * 64 <= (int64_t)80 << 20) return 4;              // 16-column blocks
+    if (mode != 1) return mode;
+    // ncu: a 128 MB block (1e6 rows x 128 B) misses L2 72 % of the time - data shared by the SMs of both dies is cached in
+    // both L2 partitions, so the budget is ~half of the 126 MB.  Blocks are sized to <= 48 MB.
+    const int64_t budget = (int64_t)48 << 20;
+    if (n * 128 <= budget) return 8;                        // 32-column blocks
+    if (n * 64 <= budget) return 4;                         // 16-column blocks
+    if (n * 32 <= budget) return 2;                         // 8-column blocks
     return 0;                                               // the block would not stay in L2: stream from HBM
 }
 
@@ -1087,8 +1091,9 @@ extern "C" int laris_spatial_stats_batched(const float* S, int64_t ldS, int64_t 
     const int quads = n_repeats > 0 ? null_l2_quads(n) : 0;
     if (quads) {
         double* o = out + (int64_t)row0 * 5 * P;
-        return quads == 8 ? null_stats_l2<8>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st)
-                          : null_stats_l2<4>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st);
+        return quads == 8   ? null_stats_l2<8>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st)
+               : quads == 4 ? null_stats_l2<4>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st)
+                            : null_stats_l2<2>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st);
     }
     for (int r = 0; r < n_repeats;) {
         const int rb = n_repeats - r >= 3 ? 3 : n_repeats - r;
