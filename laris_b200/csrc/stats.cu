@@ -280,6 +280,9 @@ null_stats_reduce_kernel(const double* __restrict__ partial, int nchunks, int64_
 // column quads, a thread owns one quad of the rows of its lane; the R*k (index, weight) pairs of a batch of rows are
 // staged in shared memory.  HBM bytes: 4nP (S once) + 8nkR per column block (the edge lists are re-read per block).
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -287,48 +290,57 @@ __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// One (column block, repeat) per launch.  The edge lists of the NEXT batch of rows are brought into shared memory by
-// cp.async while the current batch gathers, a thread keeps ten 128-bit L2 gathers in flight, and its sums stay in fp32
-// (a thread sees <= 64 rows per launch; the CTA reduction and everything after it is fp64): ~75 registers, three CTAs
-// per SM.  FIRST: also sum S^2, sum S and nnz of the block (needed once, not per repeat).
+// One (column block, repeat) per launch over the COMPACT block (see compact_block_kernel).  Warps are independent: a warp
+// covers 32/QUADS rows x QUADS column quads per step, brings the edge lists of its NEXT step into its own slice of
+// shared memory with cp.async while the current step gathers (no CTA barrier in the loop), keeps ten 128-bit L2
+// gathers in flight per thread, and its sums stay in fp32 (a thread sees <= 64 rows per launch; the CTA reduction and
+// everything after it is fp64): ~76 registers, three CTAs per SM.  FIRST: also sum S^2, sum S and nnz of the block
+// (needed once, not per repeat).
 template <int QUADS, bool FIRST>
 __global__ void __launch_bounds__(256, 3)
-spatial_null_stats_l2_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t n, int64_t q0, int nq,
-                             const int32_t* __restrict__ nidx, const float* __restrict__ nw, int k,
-                             double* __restrict__ partial /*[grid][5][QUADS*4]*/) {
-    constexpr int ROWS = 256 / QUADS, WB = QUADS * 4;
+spatial_null_stats_l2_kernel(const float4* __restrict__ B4, int64_t n, const int32_t* __restrict__ nidx,
+                             const float* __restrict__ nw, int k, double* __restrict__ partial /*[grid][5][QUADS*4]*/) {
+    constexpr int ROWS = 256 / QUADS, WB = QUADS * 4, RW = 32 / QUADS;              // rows per CTA step / per warp step
     extern __shared__ __align__(16) unsigned char l2_smem[];
-    const int tid = threadIdx.x, quad = tid % QUADS, rl = tid / QUADS;
-    const bool col_ok = quad < nq;
-    const int per_buf = ROWS * k;                                    // idx then w, per buffer
-    int32_t* s_idx = reinterpret_cast<int32_t*>(l2_smem);
-    float* s_w = reinterpret_cast<float*>(l2_smem) + 2 * per_buf;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, quad = tid % QUADS, rl = tid / QUADS;
+    const int per_buf = RW * k;                                      // words of idx (and of w) per warp buffer
+    int32_t* w_idx = reinterpret_cast<int32_t*>(l2_smem) + (size_t)warp * 4 * per_buf;     // [2][per_buf] idx, then [2][per_buf] w
+    float* w_w = reinterpret_cast<float*>(w_idx + 2 * per_buf);
     float a_dot[4] = {0, 0, 0, 0}, a_tt[4] = {0, 0, 0, 0}, a_ss[4] = {0, 0, 0, 0}, a_s[4] = {0, 0, 0, 0};
     int a_nz[4] = {0, 0, 0, 0};
-    const float4* base = S4 + q0 + quad;
+    const float4* base = B4 + quad;
+    const int64_t nwarps = (int64_t)gridDim.x * 8, gw = (int64_t)blockIdx.x * 8 + warp;
     auto stage = [&](int64_t b, int buf) {
-        const int64_t i0 = b * ROWS;
+        const int64_t i0 = b * RW;
         if (i0 < n) {
-            const int cnt = (int)min((int64_t)ROWS, n - i0) * k;
-            const uint32_t di = aio::smem_addr(s_idx + buf * per_buf), dw = aio::smem_addr(s_w + buf * per_buf);
-            for (int e = tid; e < cnt; e += 256) {
-                cp_async4(di + 4 * e, nidx + i0 * k + e);
-                cp_async4(dw + 4 * e, nw + i0 * k + e);
+            const int rows = (int)min((int64_t)RW, n - i0);
+            const uint32_t di = aio::smem_addr(w_idx + buf * per_buf), dw = aio::smem_addr(w_w + buf * per_buf);
+            const bool vec = rows == RW && ((((uintptr_t)(nidx + i0 * k)) | ((uintptr_t)(nw + i0 * k))) & 15) == 0;
+            if (vec) {                                               // RW * k * 4 bytes is a multiple of 16 (RW >= 4)
+                for (int c = lane; c < per_buf / 4; c += 32) {
+                    cp_async16(di + 16 * c, nidx + i0 * k + 4 * c, 16);
+                    cp_async16(dw + 16 * c, nw + i0 * k + 4 * c, 16);
+                }
+            } else {
+                for (int e = lane; e < rows * k; e += 32) {
+                    cp_async4(di + 4 * e, nidx + i0 * k + e);
+                    cp_async4(dw + 4 * e, nw + i0 * k + e);
+                }
             }
         }
         cp_async_commit_group();
     };
-    stage(blockIdx.x, 0);
+    stage(gw, 0);
     int buf = 0;
-    for (int64_t b = blockIdx.x; b * ROWS < n; b += gridDim.x, buf ^= 1) {
-        stage(b + gridDim.x, buf ^ 1);
+    for (int64_t b = gw; b * RW < n; b += nwarps, buf ^= 1) {
+        stage(b + nwarps, buf ^ 1);
         cp_async_wait_group<1>();
-        __syncthreads();
-        const int64_t i = b * ROWS + rl;
-        if (i < n && col_ok) {
-            const int32_t* ni = s_idx + buf * per_buf + rl * k;
-            const float* wv = s_w + buf * per_buf + rl * k;
-            const float4 s = ld_stream_f4(base + i * ld4);
+        __syncwarp();
+        const int64_t i = b * RW + (lane / QUADS);
+        if (i < n) {
+            const int32_t* ni = w_idx + buf * per_buf + (lane / QUADS) * k;
+            const float* wv = w_w + buf * per_buf + (lane / QUADS) * k;
+            const float4 s = __ldg(base + i * QUADS);
             float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
             float wsum = 0.f;                                        // same association as the streaming kernel
             {
@@ -340,7 +352,7 @@ spatial_null_stats_l2_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t
             for (; j + 10 <= k; j += 10) {                           // ten independent 128-bit L2 gathers in flight
                 float4 v[10];
 #pragma unroll
-                for (int u = 0; u < 10; ++u) v[u] = ld_stream_f4(base + (int64_t)ni[j + u] * ld4);
+                for (int u = 0; u < 10; ++u) v[u] = __ldg(base + (int64_t)ni[j + u] * QUADS);
 #pragma unroll
                 for (int u = 0; u < 10; ++u) {
                     const float w0 = wv[j + u];
@@ -348,7 +360,7 @@ spatial_null_stats_l2_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t
                 }
             }
             for (; j < k; ++j) {
-                const float4 v0 = ld_stream_f4(base + (int64_t)ni[j] * ld4);
+                const float4 v0 = __ldg(base + (int64_t)ni[j] * QUADS);
                 const float w0 = wv[j];
                 t.x = fmaf(w0, v0.x, t.x); t.y = fmaf(w0, v0.y, t.y); t.z = fmaf(w0, v0.z, t.z); t.w = fmaf(w0, v0.w, t.w);
             }
@@ -368,7 +380,7 @@ spatial_null_stats_l2_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t
                 }
             }
         }
-        __syncthreads();                                             // buffer `buf` is refilled two iterations from now
+        __syncwarp();                                                // buffer `buf` is refilled two steps from now
     }
     cp_async_wait_group<0>();
     __syncthreads();
@@ -390,6 +402,19 @@ spatial_null_stats_l2_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t
         }
         __syncthreads();
     }
+}
+
+// the column block as a COMPACT [n][QUADS] matrix: the gathers then address n*QUADS*16 contiguous bytes - inside the TLB
+// reach (256 MB) and the L2 - instead of pieces strewn over the whole 4nP-byte matrix (measured: gathering the strided
+// pieces in place is bound by address translation at ~4e10 requests/s, whatever their size)
+template <int QUADS>
+__global__ void compact_block_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t n, int64_t q0, int nq,
+                                     float4* __restrict__ blk) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= n * QUADS) return;
+    const int64_t i = e / QUADS;
+    const int q = (int)(e - i * QUADS);
+    blk[e] = q < nq ? ld_stream_f4(S4 + i * ld4 + q0 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // partial [nblk][R][ncta][5][WB] -> out rows [R][5][P]; sum S^2 / sum S / nnz come from repeat 0's launch
@@ -749,9 +774,6 @@ struct TileSmemCp {
     static __host__ __device__ size_t total(int k) { return 2 * tile_bytes() + 3 * plan_bytes(k) + 16 * 16 * 4 * 8; }
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -1002,8 +1024,9 @@ static int null_l2_quads(int64_t n) {
     }
     if (mode != 1) return mode;
     // ncu: a 128 MB block (1e6 rows x 128 B) misses L2 72 % of the time - data shared by the SMs of both dies is cached in
-    // both L2 partitions, so the budget is ~half of the 126 MB.  Blocks are sized to <= 48 MB.
-    const int64_t budget = (int64_t)48 << 20;
+    // both L2 partitions, so the budget is ~half of the 126 MB (probe: 64-byte rows gather at 16.8 TB/s from 64 MB, 14.5 from
+    // 80 MB, 9.8 from 96 MB).  Blocks are sized to <= 72 MB.
+    const int64_t budget = (int64_t)72 << 20;
     if (n * 128 <= budget) return 8;                        // 32-column blocks
     if (n * 64 <= budget) return 4;                         // 16-column blocks
     if (n * 32 <= budget) return 2;                         // 8-column blocks
@@ -1023,22 +1046,25 @@ static int null_stats_l2(const float* S, int64_t ldS, int64_t n, int32_t P, cons
     if (ncta > ceil_div(n, ROWS)) ncta = ceil_div(n, ROWS);
     const int nblk = (int)ceil_div(ld4, QUADS);
     Scratch<double> partial(st);
+    Scratch<float4> blkbuf(st);
     LARIS_CUDA(partial.alloc((size_t)nblk * R * ncta * 5 * WB));
-    size_t smem = (size_t)4 * ROWS * k * 4;                                              // two buffers of (idx, w)
+    LARIS_CUDA(blkbuf.alloc((size_t)n * QUADS));
+    size_t smem = (size_t)4 * ROWS * k * 4;                                              // per warp: two buffers of (idx, w)
     if (smem < (size_t)ROWS * WB * 8) smem = (size_t)ROWS * WB * 8;
     LARIS_CUDA(cudaFuncSetAttribute(spatial_null_stats_l2_kernel<QUADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LARIS_CUDA(cudaFuncSetAttribute(spatial_null_stats_l2_kernel<QUADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int blk = 0; blk < nblk; ++blk) {
         const int64_t q0 = (int64_t)blk * QUADS;
         const int nq = (int)(ld4 - q0 < QUADS ? ld4 - q0 : QUADS);
-        for (int r = 0; r < R; ++r) {                      // the block's 30 gathers per cell, one repeat per launch, all L2 hits
+        compact_block_kernel<QUADS><<<(unsigned)ceil_div(n * QUADS, 256), 256, 0, st>>>((const float4*)S, ld4, n, q0, nq, blkbuf.p);
+        LARIS_LAUNCH_CHECK();
+        for (int r = 0; r < R; ++r) {                      // the block's R*k gathers per cell, one repeat per launch, all L2 hits
             double* dst = partial.p + ((size_t)blk * R + r) * ncta * 5 * WB;
             if (r == 0)
-                spatial_null_stats_l2_kernel<QUADS, true><<<(unsigned)ncta, 256, smem, st>>>((const float4*)S, ld4, n, q0, nq, nidx,
-                                                                                            nw, k, dst);
+                spatial_null_stats_l2_kernel<QUADS, true><<<(unsigned)ncta, 256, smem, st>>>(blkbuf.p, n, nidx, nw, k, dst);
             else
-                spatial_null_stats_l2_kernel<QUADS, false><<<(unsigned)ncta, 256, smem, st>>>(
-                    (const float4*)S, ld4, n, q0, nq, nidx + (int64_t)r * nk, nw + (int64_t)r * nk, k, dst);
+                spatial_null_stats_l2_kernel<QUADS, false><<<(unsigned)ncta, 256, smem, st>>>(blkbuf.p, n, nidx + (int64_t)r * nk,
+                                                                                             nw + (int64_t)r * nk, k, dst);
             LARIS_LAUNCH_CHECK();
         }
     }
