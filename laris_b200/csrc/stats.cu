@@ -1026,11 +1026,9 @@ static int null_l2_quads(int64_t n) {
     // ncu: a 128 MB block (1e6 rows x 128 B) misses L2 72 % of the time - data shared by the SMs of both dies is cached in
     // both L2 partitions, so the budget is ~half of the 126 MB (probe: 64-byte rows gather at 16.8 TB/s from 64 MB, 14.5 from
     // 80 MB, 9.8 from 96 MB).  Blocks are sized to <= 72 MB.
-    const int64_t budget = (int64_t)72 << 20;
-    if (n * 128 <= budget) return 8;                        // 32-column blocks
-    if (n * 64 <= budget) return 4;                         // 16-column blocks
-    if (n * 32 <= budget) return 2;                         // 8-column blocks
-    return 0;                                               // the block would not stay in L2: stream from HBM
+    if (n * 128 <= (int64_t)48 << 20) return 8;             // 32-column blocks (<= 393 k cells)
+    if (n * 64 <= (int64_t)72 << 20) return 4;              // 16-column blocks (<= 1.18 M cells)
+    return 0;   // larger n: 8-column blocks measured no faster than streaming (2e6 cells: 23.7 vs ~22 ms) - stream from HBM
 }
 
 template <int QUADS>
