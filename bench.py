@@ -249,7 +249,9 @@ def kernel_rooflines(stage_ms, calls, c, P_local, nnz_u, k, hbm_peak, bf16_peak,
     add("K2+K3 diffuse_score (dense)", 4 * n * c.G_u + 8 * n * k + 4 * n * P_local, "4nG_u + 8nk + 4nP (SURVEY 8d)")
     add("K4a observed_stats", 4 * n * P_local + 8 * n * k, "4nP + 8nk: S read once, neighbour rows from shared memory")
     add("K4b null_stats", 4 * (1 + R * k) * n * P_local + 8 * n * k * R,
-        f"(1 + R k) 4nP + 8nkR per batch of R={R} repeats: every random neighbour row is a fresh HBM read")
+        f"(1 + R k) 4nP + 8nkR for the R={R} repeats - SURVEY 8(d)'s bytes, which count every random neighbour row as a fresh "
+        "HBM read.  Up to 1.18 M cells the pass runs per 16-column block on a compacted copy that stays in L2, so the gathers "
+        "are L2 hits and this figure can exceed the HBM peak; the DRAM bytes actually moved are in `traffic`")
     add("K5b nonzero_count", 4 * n * P_local, "4nP: S read once")
     add("K5 pair_contract", None, "2 n P C^2 algorithmic flop (tensor cores, fp32 accumulate)", bound="tensor",
         flops=2.0 * n * P_local * C * C)
