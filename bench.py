@@ -358,8 +358,8 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 return lr_ad, res
 
-            for _ in range(2):                          # warm-up: page-locked staging buffers of both result generations
-                host_step()
+            for _ in range(3):                          # warm-up: page-locked staging buffers of BOTH result generations -
+                lr_ad, res = host_step()                # the previous call's results stay alive while the next one runs
             barrier()
             for _ in range(args.steps):
                 flush.fill_(1.0)

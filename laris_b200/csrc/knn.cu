@@ -190,10 +190,49 @@ __global__ void cell_sort_kernel(const int32_t* __restrict__ cell_start, const G
             if (a < len) sorted_id[s + a] = v[a];
         return;
     }
-    for (int a = s + 1; a < e; ++a) {
-        int v = sorted_id[a], b = a - 1;
-        while (b >= s && sorted_id[b] > v) { sorted_id[b + 1] = sorted_id[b]; --b; }
-        sorted_id[b + 1] = v;
+    // longer segments (clustered inputs, e.g. the (mean, variance) points of the background search): cell_sort_big_kernel
+}
+
+// cells with more than 16 points, sorted by a whole CTA: bitonic sort in shared memory (<= kBigCellCap points; beyond
+// that one thread falls back to insertion sort in place).  A CTA scans 64 cells; almost all of them are small and skipped.
+constexpr int kBigCellCap = 4096;
+__global__ void __launch_bounds__(256)
+cell_sort_big_kernel(const int32_t* __restrict__ cell_start, const GridSpec* __restrict__ gsp, int32_t* __restrict__ sorted_id) {
+    __shared__ int32_t buf[kBigCellCap];
+    const int64_t ncell = gsp->ncell;
+    for (int q = 0; q < 64; ++q) {
+        const int64_t c = (int64_t)blockIdx.x * 64 + q;
+        if (c >= ncell) return;
+        const int s = cell_start[c], e = cell_start[c + 1], len = e - s;
+        if (len <= 16) continue;                                      // uniform over the CTA
+        if (len > kBigCellCap) {
+            if (threadIdx.x == 0)
+                for (int a = s + 1; a < e; ++a) {
+                    int v = sorted_id[a], b = a - 1;
+                    while (b >= s && sorted_id[b] > v) { sorted_id[b + 1] = sorted_id[b]; --b; }
+                    sorted_id[b + 1] = v;
+                }
+            __syncthreads();
+            continue;
+        }
+        int cap = 32;
+        while (cap < len) cap <<= 1;
+        for (int i = threadIdx.x; i < cap; i += 256) buf[i] = i < len ? sorted_id[s + i] : INT32_MAX;
+        __syncthreads();
+        for (int kk = 2; kk <= cap; kk <<= 1)
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < cap; i += 256) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const bool up = (i & kk) == 0;
+                        const int32_t a = buf[i], b = buf[l];
+                        if ((a > b) == up) { buf[i] = b; buf[l] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int i = threadIdx.x; i < len; i += 256) sorted_id[s + i] = buf[i];
+        __syncthreads();
     }
 }
 
@@ -538,6 +577,8 @@ static int build_point_grid(const double* xy, int64_t n, int dim, double per_cel
     cell_scatter_kernel<<<gn, T, 0, st>>>(G.cell_of, n, G.cell_start, G.fill, G.sorted_id);
     LARIS_LAUNCH_CHECK();
     cell_sort_kernel<<<gc, T, 0, st>>>(G.cell_start, G.gs, G.sorted_id);
+    LARIS_LAUNCH_CHECK();
+    cell_sort_big_kernel<<<(unsigned)ceil_div(G.cell_bound, 64), 256, 0, st>>>(G.cell_start, G.gs, G.sorted_id);
     LARIS_LAUNCH_CHECK();
     gather_sorted_kernel<<<gn, T, 0, st>>>(xy, n, dim, G.sorted_id, G.cell_of, G.sx, G.sy, G.sz, G.sorted_cell);
     LARIS_LAUNCH_CHECK();
