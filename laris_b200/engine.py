@@ -525,17 +525,27 @@ def neighborhood_specificity(sm: ScoreMatrix, labels_d, C, graph: SpatialGraph, 
     return cosg_regularise(cos, mu), cos
 
 
+def cosg_gene_scores_async(xu: ExpressionU, labels_d, C, n_c, mu, expressed_pct, remove_lowly_expressed):
+    """Enqueue the per (type, gene) sums of the packed expression and return ``finish()``, which downloads them and
+    gives the COSG gene x group score (cosg.cosg semantics).  Host work placed between the two calls overlaps the kernel."""
+    s_d, c_d, q_d = K.onehot_contract_csr(xu.indptr, xu.packed, xu.G_u, labels_d, C, row_end=xu.row_end)
+    G_u = xu.G_u
+
+    def finish():
+        s, c, q = s_d.cpu().numpy(), c_d.cpu().numpy(), q_d.cpu().numpy()
+        den = np.sqrt(q)[:, None] * np.sqrt(n_c.astype(np.float64))[None, :]
+        cos = np.zeros((G_u, C))
+        np.divide(s.T, den, out=cos, where=den != 0)
+        score = cosg_regularise(cos, mu)
+        if remove_lowly_expressed:
+            score[c.T < n_c[None, :] * expressed_pct] = -1.0
+        return score
+    return finish
+
+
 def cosg_gene_scores(xu: ExpressionU, labels_d, C, n_c, mu, expressed_pct, remove_lowly_expressed):
     """COSG gene x group score of the packed expression (cosg.cosg semantics)."""
-    s, c, q = K.onehot_contract_csr(xu.indptr, xu.packed, xu.G_u, labels_d, C, row_end=xu.row_end)
-    s, c, q = s.cpu().numpy(), c.cpu().numpy(), q.cpu().numpy()
-    den = np.sqrt(q)[:, None] * np.sqrt(n_c.astype(np.float64))[None, :]
-    cos = np.zeros((xu.G_u, C))
-    np.divide(s.T, den, out=cos, where=den != 0)
-    score = cosg_regularise(cos, mu)
-    if remove_lowly_expressed:
-        score[c.T < n_c[None, :] * expressed_pct] = -1.0
-    return score
+    return cosg_gene_scores_async(xu, labels_d, C, n_c, mu, expressed_pct, remove_lowly_expressed)()
 
 
 # --------------------------------------------------------------- p-values ----

@@ -163,6 +163,16 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     st_d, rng_state = engine.spatial_stats_all(sm, graph, n_repeats, random_seed, rng)
     sm.cache["stats_d"] = st_d[0]
     sm.cache["graph"] = graph                 # the cell-type step re-uses the neighbour search when it can
+    pre = None
+    if by_celltype:
+        # queue the ranking-independent part of the cell-type step BEFORE waiting for the statistics: the device then has
+        # work while the host ranks the pairs (reference order of operations is unchanged where it matters: rng='numpy'
+        # consumes the random stream in the same order, nothing here draws from it)
+        if groupby not in adata.obs:
+            raise ValueError(f"Cell type column '{groupby}' not found in adata.obs. "
+                             f"Available columns: {list(adata.obs.columns)}")
+        pre = _utils._celltype_prefetch(adata, lr_adata, groupby, use_rep_spatial, number_nearest_neighbors, mu_celltype,
+                                        expressed_pct_celltype, remove_lowly_expressed_celltype, contract_impl, shard, radius)
     st_local = None
     if shard is not None:
         st_local = st_d[0].cpu().numpy()
@@ -229,7 +239,7 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
         prefilter_threshold=prefilter_threshold, score_threshold=score_threshold, spatial_weight=spatial_weight,
         use_conditional_pvalue=use_conditional_pvalue, rng=rng, random_seed=random_seed, rng_state=rng_state,
         verbose=verbose, contract_impl=contract_impl, shard=shard, radius=radius, output=output,
-        label_permutations=label_permutations)
+        label_permutations=label_permutations, _pre=pre)
     if output == "frames":
         _log(verbose, f"\nResults: {len(laris_lr)} LR pairs, {len(celltype_results):,} cell type combinations")
     return laris_lr, celltype_results

@@ -303,16 +303,15 @@ def _cosg_table(names, score, cats):
     return cosg_compat.iqr_log_normalize(table)
 
 
-def _gene_cosg_scores(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_expressed, shard=None):
-    """Raw COSG scores [len(lr_set), C] of the named genes (``cosg.cosg`` semantics, -1 = lowly expressed), on the
-    device; re-uses the packed LR-gene rows prepareLRInteraction left resident when they cover the genes.
+def _gene_cosg_scores_async(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_expressed, shard=None, labels=None):
+    """Raw COSG scores [len(lr_set), C] of the named genes (``cosg.cosg`` semantics, -1 = lowly expressed): the device
+    contraction is enqueued now, ``finish()`` (returned) downloads and finishes it.  Re-uses the packed LR-gene rows
+    prepareLRInteraction left resident when they cover the genes.
 
     Sharded run: a rank only holds the genes of its own pair block.  Every gene is scored by its OWNER - the lowest
     rank whose pairs use it, which every rank can work out from the global pair names - and the rows are summed
     over the ranks (each row has exactly one non-zero contributor)."""
-    codes, cats = _group_codes(adata.obs[groupby])
-    n_c = np.bincount(codes, minlength=len(cats))
-    labels_d = K.to_device(codes, torch.int32)
+    codes, cats, n_c, labels_d = labels if labels is not None else _labels_on_device(adata.obs[groupby])
     lr_set = np.asarray(lr_set, dtype=object)
     mine = np.ones(len(lr_set), dtype=bool)
     if shard is not None:
@@ -324,19 +323,35 @@ def _gene_cosg_scores(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_ex
                 owner[lig] = r
                 owner[rec] = r
         mine = np.array([owner.get(g, 0) == shard.rank for g in lr_set], dtype=bool)
-    score = np.zeros((len(lr_set), len(cats)))
+    part, rows = None, None
     if mine.any():
         gene_idx = _gene_columns(adata, lr_set[mine])
         hit = _expression_of(adata.X, gene_idx)
         if hit is not None:
             xu, rows = hit
-            score[mine] = engine.cosg_gene_scores(xu, labels_d, len(cats), n_c, mu, expressed_pct, remove_lowly_expressed)[rows]
         else:
             xu = engine.select_genes(adata.X, gene_idx)
-            score[mine] = engine.cosg_gene_scores(xu, labels_d, len(cats), n_c, mu, expressed_pct, remove_lowly_expressed)
-    if shard is not None:
-        score = _dist.all_reduce_sum(score)
-    return score, cats
+        part = engine.cosg_gene_scores_async(xu, labels_d, len(cats), n_c, mu, expressed_pct, remove_lowly_expressed)
+
+    def finish():
+        score = np.zeros((len(lr_set), len(cats)))
+        if part is not None:
+            got = part()
+            score[mine] = got if rows is None else got[rows]
+        if shard is not None:
+            score = _dist.all_reduce_sum(score)
+        return score, cats
+    return finish
+
+
+def _gene_cosg_scores(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_expressed, shard=None):
+    return _gene_cosg_scores_async(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_expressed, shard)()
+
+
+def _labels_on_device(obs_col):
+    """(codes, categories, cells per category, device label tensor) of a cell-type column."""
+    codes, cats = _group_codes(obs_col)
+    return codes, cats, np.bincount(codes, minlength=len(cats)), K.to_device(codes, torch.int32)
 
 
 def _calculate_ligand_receptor_specificity(adata, laris_lr, groupby: str = "CellTypes", mu: float = 100,
@@ -352,21 +367,52 @@ def _calculate_ligand_receptor_specificity(adata, laris_lr, groupby: str = "Cell
     return _cosg_table(lr_set, score, cats)
 
 
-def _specificity_rows(adata, laris_lr, groupby, mu, expressed_pct, remove_lowly_expressed, mask_threshold, shard=None):
+def _specificity_rows(laris_lr, genes_all, score_all, cats):
     """What ``_calculate_laris_score_by_celltype`` needs of the table above: (gene names, [genes, C] fp64 matrix with the
-    columns in category order).  With the real ``cosg`` it IS the table above; with the stand-ins the ranked frame and
-    its pivot are skipped - normalising the score matrix column by column gives the same numbers."""
+    columns in category order) for the ligands / receptors of ``laris_lr``, from raw COSG scores of a superset of genes
+    (a gene's COSG score does not depend on which other genes are scored; the column normalisation does, so it runs on
+    exactly the reference's gene set).  With the real ``cosg`` the reference's frame -> ``indexByGene`` ->
+    ``iqrLogNormalize`` route is taken; with the stand-ins the ranked frame and its pivot are skipped - normalising the
+    score matrix column by column gives the same numbers."""
+    lr_set = np.unique(np.hstack([laris_lr["ligand"].values, laris_lr["receptor"].values]))
+    score = score_all[pd.Index(genes_all).get_indexer(lr_set)]
     if cosg_compat.real_cosg() is not None:
-        lr_set = np.unique(np.hstack([laris_lr["ligand"].values, laris_lr["receptor"].values]))
-        score, cats = _gene_cosg_scores(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_expressed, shard)
         spec = _cosg_table(lr_set, score, cats)
         cats = list(cats)
         spec = spec.loc[:, cats] if list(spec.columns) != cats else spec
         return np.asarray(spec.index, dtype=object), spec.to_numpy(dtype=np.float64)
-    lr_set = np.unique(np.hstack([laris_lr["ligand"].values, laris_lr["receptor"].values]))
-    score, _ = _gene_cosg_scores(adata, lr_set, groupby, mu, expressed_pct, remove_lowly_expressed, shard)
     table = np.nan_to_num(np.where(score == -1, 0.0, score), nan=0.0)          # indexByGene(set_nan_to_zero, -1 -> 0)
     return lr_set, cosg_compat.iqr_log_normalize_array(table)
+
+
+def _celltype_prefetch(adata, lr_adata, groupby, use_rep_spatial, number_nearest_neighbors, mu, expressed_pct,
+                       remove_lowly_expressed, contract_impl, shard, radius):
+    """Everything of the cell-type step that does NOT depend on the ranking, enqueued on the device in one go: the COSG
+    gene sums of every LR gene, the per-type non-zero counts (K5b), the neighbourhood composition, the cell-type-pair
+    contraction (K5), its cosine / regularisation (T1), the gathers of a sharded run and the column normalisation (T2).
+    ``runLARIS`` calls it right after queueing the spatial statistics, i.e. BEFORE it waits for them: the host work in
+    here and the ranking that follows run while the device is busy.  Returns a dict for
+    ``_calculate_laris_score_by_celltype(_pre=...)``."""
+    if groupby not in adata.obs:
+        raise ValueError(f"'{groupby}' not found in adata.obs")
+    if use_rep_spatial not in adata.obsm:
+        raise ValueError(f"'{use_rep_spatial}' not found in adata.obsm")
+    if not hasattr(adata.obs[groupby], "cat"):
+        raise AttributeError(f"adata.obs['{groupby}'] must be categorical (reference _compute_avg_expression)")
+    labels = _labels_on_device(adata.obs[groupby])
+    codes, cats, n_c, labels_d = labels
+    C = len(cats)
+    lr_names = np.asarray(lr_adata.var_names if shard is None else shard.names_global, dtype=object)
+    genes_all = np.unique(np.array([g for nm in lr_names for g in nm.split("::")], dtype=object))
+    cosg_finish = _gene_cosg_scores_async(adata, genes_all, groupby, mu, expressed_pct, remove_lowly_expressed, shard, labels)
+    sm = _scores_of(lr_adata)
+    cnt_d = K.celltype_nonzero_count(sm.S, sm.P, labels_d, C)                                   # [C, P_local] int64
+    if shard is not None:
+        cnt_d = _dist.all_gather_pairs_dev(cnt_d, shard, axis=1)
+    raw_d, pair_names = _neighborhood_raw(adata, sm, labels, use_rep_spatial, number_nearest_neighbors, mu, contract_impl,
+                                          shard, radius)
+    return dict(labels=labels, lr_names=lr_names, genes_all=genes_all, cosg_finish=cosg_finish, cnt_d=cnt_d, raw_d=raw_d,
+                pair_names=pair_names, ctc_d=_normalise_table_device(raw_d))
 
 
 def _calculate_diffused_lr_specificity(lr_adata, groupby: str = "CellTypes", mu: float = 100, expressed_pct: float = 0.05,
@@ -398,32 +444,34 @@ def _observed_ss_device(sm, graph):
     return st_d[1].contiguous()
 
 
-def _neighborhood_tables(adata, lr_adata, groupby, use_rep_spatial, number_nearest_neighbors, mu, contract_impl, shard,
-                         radius):
-    """Device tables of the co-localisation step: (raw [P, C^2] fp64 regularised cosines, global pair order;
-    LR names; sender::receiver names).  Reference :838-880."""
-    if groupby not in adata.obs:
-        raise ValueError(f"'{groupby}' not found in adata.obs")
-    if use_rep_spatial not in adata.obsm:
-        raise ValueError(f"'{use_rep_spatial}' not found in adata.obsm")
-    codes, cats = _group_codes(adata.obs[groupby])
+def _neighborhood_raw(adata, sm, labels, use_rep_spatial, number_nearest_neighbors, mu, contract_impl, shard, radius):
+    """Device table of the co-localisation step: raw [P, C^2] fp64 regularised cosines in global pair order, and the
+    sender::receiver names.  Reference :838-880."""
+    codes, cats, n_c, labels_d = labels
     C = len(cats)
-    sm = _scores_of(lr_adata)
     if radius is None:
         graph = engine.build_graph(_coords(adata, use_rep_spatial), number_nearest_neighbors, False, None,
                                    like=sm.cache.get("graph"))
     else:
         graph = engine.build_radius_graph(_coords(adata, use_rep_spatial), radius, False, None)
-    labels_d = K.to_device(codes, torch.int32)
     N = K.neighborhood_composition(labels_d, graph.idx, graph.w, C)
     num, qn2 = K.celltype_pair_contract(sm.S, sm.P, N, contract_impl, order=graph.order)
     _, raw = K.pair_cosine_regularise(num, _observed_ss_device(sm, graph), qn2, mu)
-    if shard is None:
-        lr_names = np.asarray(lr_adata.var_names, dtype=object)
-    else:        # the regularisation runs over a pair's own C^2 row, so rows are final before the gather
+    if shard is not None:        # the regularisation runs over a pair's own C^2 row, so rows are final before the gather
         raw = _dist.all_gather_pairs_dev(raw, shard, axis=0)
-        lr_names = np.asarray(shard.names_global, dtype=object)
-    pair_names = [f"{a}::{b}" for a in cats for b in cats]
+    return raw, [f"{a}::{b}" for a in cats for b in cats]
+
+
+def _neighborhood_tables(adata, lr_adata, groupby, use_rep_spatial, number_nearest_neighbors, mu, contract_impl, shard,
+                         radius):
+    """(raw [P, C^2] device table, LR names in global pair order, sender::receiver names)."""
+    if groupby not in adata.obs:
+        raise ValueError(f"'{groupby}' not found in adata.obs")
+    if use_rep_spatial not in adata.obsm:
+        raise ValueError(f"'{use_rep_spatial}' not found in adata.obsm")
+    raw, pair_names = _neighborhood_raw(adata, _scores_of(lr_adata), _labels_on_device(adata.obs[groupby]), use_rep_spatial,
+                                        number_nearest_neighbors, mu, contract_impl, shard, radius)
+    lr_names = np.asarray(lr_adata.var_names if shard is None else shard.names_global, dtype=object)
     return raw, lr_names, pair_names
 
 
@@ -679,7 +727,7 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
                                        score_threshold: float = 1e-6, spatial_weight: float = 1.0,
                                        use_conditional_pvalue: bool = False, *, rng: str = "numpy", random_seed: int = 27,
                                        rng_state=None, verbose: bool = True, contract_impl=None, shard=None, radius=None,
-                                       output: str = "frames", label_permutations: int = 0):
+                                       output: str = "frames", label_permutations: int = 0, _pre=None):
     """Sender/receiver cell-type table with permutation p-values and BH-FDR.
 
     Reference laris/tools/_utils.py:1113-1688; same arguments (``mask_threshold`` and
@@ -693,31 +741,28 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
     if output not in ("frames", "arrays"):
         raise ValueError(f"output must be 'frames' or 'arrays', got {output!r}")
     cols6 = ["sender", "receiver", "ligand", "receptor", "interaction_name", "interaction_score"]
-    codes, cats = _group_codes(adata.obs[groupby])
-    if not hasattr(adata.obs[groupby], "cat"):
-        raise AttributeError(f"adata.obs['{groupby}'] must be categorical (reference _compute_avg_expression)")
     cosg_compat.warn_if_stand_in()
+    if len(laris_lr) == 0:
+        return pd.DataFrame(columns=cols6)
+    # the ranking-independent part (COSG sums, K5b counts, K5 contraction, T1, T2): runLARIS queues it before it waits for
+    # the spatial statistics and hands it in; a direct call queues it here
+    pre = _pre if _pre is not None else _celltype_prefetch(adata, lr_adata, groupby, use_rep_spatial, number_nearest_neighbors,
+                                                           mu, expressed_pct, remove_lowly_expressed, contract_impl, shard, radius)
+    codes, cats, n_c, labels_d = pre["labels"]
     C = len(cats)
     L = C * C
     cats_arr = np.asarray(cats, dtype=object)
-    n_c = np.bincount(codes, minlength=C)
-    labels_d = K.to_device(codes, torch.int32)
-    lr_names = np.asarray(lr_adata.var_names if shard is None else shard.names_global, dtype=object)
+    lr_names = pre["lr_names"]
     P = len(lr_names)
 
     # ---- step 1: ligand / receptor specificity (reference :1306) ----
     _log(verbose, "\n--- Step 1: Calculating ligand and receptor cell type specificity ---")
-    if len(laris_lr) == 0:
-        return pd.DataFrame(columns=cols6)
-    spec_genes, spec_m = _specificity_rows(adata, laris_lr, groupby, mu, expressed_pct, remove_lowly_expressed,
-                                           mask_threshold, shard)
+    score_all, _ = pre["cosg_finish"]()
+    spec_genes, spec_m = _specificity_rows(laris_lr, pre["genes_all"], score_all, cats)
 
     # ---- step 2: cells with a non-zero score per type (reference :1325-1337), counts stay on the device ----
     _log(verbose, "\n--- Step 2: Calculating diffused LR-score distribution ---")
-    sm = _scores_of(lr_adata)
-    cnt_d = K.celltype_nonzero_count(sm.S, sm.P, labels_d, C)                                   # [C, P_local] int64
-    if shard is not None:
-        cnt_d = _dist.all_gather_pairs_dev(cnt_d, shard, axis=1)
+    cnt_d = pre["cnt_d"]
 
     # ---- step 3: interaction scores (:1351-1406), [pair, sender, receiver] on the device ----
     _log(verbose, f"\n--- Step 3: Computing interaction scores (spatial_weight={spatial_weight}) ---")
@@ -747,9 +792,7 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
 
     # ---- step 4: co-localisation weight (:1448-1472) and clean-up (:1480-1489) ----
     _log(verbose, "\n--- Step 4: Incorporating spatial cell type co-localization ---")
-    raw_d, ctc_names, pair_names = _neighborhood_tables(adata, lr_adata, groupby, use_rep_spatial,
-                                                        number_nearest_neighbors, mu, contract_impl, shard, radius)
-    ctc_d = _normalise_table_device(raw_d)
+    raw_d, ctc_names, pair_names, ctc_d = pre["raw_d"], lr_names, pre["pair_names"], pre["ctc_d"]
     if output == "frames":
         _store_neighborhood_uns(lr_adata, "cosg_lr", groupby, mu, raw_d.cpu().numpy(), ctc_names, pair_names, True, "@@")
     flat_d, table_d, active_d = K.finalize_scores(inter_d, rescale_d, ctc_d, pair_id_d, P, score_threshold)
