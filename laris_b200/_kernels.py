@@ -18,6 +18,7 @@ def _stream():
 class StageTimer:
     def __init__(self):
         self.events = {}
+        self.timeline = []          # (stage, start event, end event, host time at enqueue start / end) in call order
 
     def summary(self):
         """{stage: (calls, total ms)}; call after a synchronisation."""
@@ -44,11 +45,15 @@ def _staged(name):
             t = _TIMER
             if t is None:
                 return fn(*a, **kw)
+            import time
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0 = time.perf_counter()
             e0.record()
             out = fn(*a, **kw)
             e1.record()
-            t.events.setdefault(name(*a, **kw) if callable(name) else name, []).append((e0, e1))
+            stage = name(*a, **kw) if callable(name) else name
+            t.events.setdefault(stage, []).append((e0, e1))
+            t.timeline.append((stage, e0, e1, h0, time.perf_counter()))
             return out
         wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
         return wrapped
