@@ -76,14 +76,25 @@ def require_cuda():
     return torch.device("cuda", torch.cuda.current_device())
 
 
+PIN_STAGE_MAX_BYTES = 64 << 20
+
+
 def to_device(a, dtype):
-    """numpy -> device tensor of ``dtype`` (async when the source is pinned)."""
+    """numpy -> device tensor of ``dtype``, without blocking the host: a pageable source is first copied into a page-locked
+    staging buffer (torch's caching pinned allocator) so that the upload is an asynchronous copy on the current stream -
+    a synchronous ``cudaMemcpy`` would make the host wait for every kernel queued before it (arrays above 64 MB go the
+    plain way; the expression matrix has its own copy stream)."""
     a = np.ascontiguousarray(a)
     t = torch.from_numpy(a) if a.dtype != np.dtype(object) else None
     if t is None:
         raise TypeError("object arrays cannot be uploaded")
     dev = require_cuda()
-    return t.to(dev, dtype=dtype, non_blocking=t.is_pinned())
+    if not t.is_pinned() and 0 < t.numel() * t.element_size() <= PIN_STAGE_MAX_BYTES:
+        t = t.pin_memory()
+    if t.is_pinned():
+        out = t.to(dev, non_blocking=True)
+        return out if out.dtype == dtype else out.to(dtype)
+    return t.to(dev, dtype=dtype)
 
 
 def to_host(*tensors):
@@ -342,8 +353,17 @@ MMA_MIN_C, MMA_MAX_C = 1, 64      # cell-type counts the tcgen05 contraction han
 SPARSE_MAX_ENTRIES_PER_CELL = 8.0   # above this many (a <= b) keys per cell the dense tensor-core contraction wins
 
 
+def celltype_pair_keys(N):
+    """Queue the key histogram of the key-gather contraction (no host synchronisation): int32 [C*C + 1] device tensor to
+    hand to ``celltype_pair_contract(key_count=...)`` later."""
+    n, C = N.shape
+    key_count = torch.empty(C * C + 1, dtype=torch.int32, device=N.device)
+    check(lib.laris_celltype_pair_keys(_ptr(N, torch.float32), n, C, _ptr(key_count), _stream()), "laris_celltype_pair_keys")
+    return key_count
+
+
 @_staged("K5 pair_contract")
-def celltype_pair_contract(S, P, N, impl=None, order=None):
+def celltype_pair_contract(S, P, N, impl=None, order=None, key_count=None):
     """Numerators num[P, C*C] and profile norms qn2[C*C] of the cell-type-pair cosines.
     impl: 0 tcgen05 tensor cores (dense B operand), 1 fp32 CUDA cores, 2 key-gather ("sparse B", fp64 accumulation);
     None = 2 when the neighbourhoods hold few cell types (<= SPARSE_MAX_ENTRIES_PER_CELL keys per cell on average - the
@@ -353,9 +373,8 @@ def celltype_pair_contract(S, P, N, impl=None, order=None):
     num = torch.empty((P, C * C), dtype=torch.float64, device=S.device)
     qn2 = torch.empty(C * C, dtype=torch.float64, device=S.device)
     if impl in (None, 2) and C <= MMA_MAX_C:
-        key_count = torch.empty(C * C + 1, dtype=torch.int32, device=S.device)
-        check(lib.laris_celltype_pair_keys(_ptr(N, torch.float32), n, C, _ptr(key_count), _stream()),
-              "laris_celltype_pair_keys")
+        if key_count is None:
+            key_count = celltype_pair_keys(N)
         total = int(key_count[: C * C].sum().item())             # sizes the entry list and picks the implementation
         if impl == 2 or total <= SPARSE_MAX_ENTRIES_PER_CELL * n:
             check(lib.laris_pair_profile_norm(_ptr(N, torch.float32), n, C, _ptr(qn2), _stream()), "laris_pair_profile_norm")

@@ -162,20 +162,34 @@ def iqr_log_normalize(df, q_upper=0.95, q_lower=0.75):
 
 
 def iqr_log_normalize_array(v, q_upper=0.95, q_lower=0.75):
-    """The stand-in above on a plain [rows, columns] fp64 array."""
+    """The stand-in above on a plain [rows, columns] fp64 array, all columns at once: one sort per column, the two
+    quantiles of the positive entries by numpy's 'linear' rule (same ``_lerp`` arithmetic as ``numpy.quantile``)."""
     v = np.asarray(v, dtype=np.float64)
+    rows, cols = v.shape
     out = np.zeros_like(v)
-    for j in range(v.shape[1]):
-        col = v[:, j]
-        pos = col[col > 0]
-        if pos.size == 0:
-            continue
-        qu, ql = np.quantile(pos, [q_upper, q_lower])
-        scale = qu - ql
-        if not scale > 0:
-            scale = pos.max()
-        y = np.log1p(np.maximum(col, 0.0) / scale)
-        out[:, j] = y / np.log1p(pos.max() / scale)
+    if rows == 0 or cols == 0:
+        return out
+    pos = v > 0
+    m = pos.sum(axis=0)                                             # positive entries per column
+    srt = np.sort(np.where(pos, v, np.inf), axis=0)                  # positives ascending, then +inf
+    ar = np.arange(cols)
+    live = m > 0
+    mm = np.maximum(m, 1)
+
+    def quantile(q):
+        h = (mm - 1) * q
+        lo = np.floor(h).astype(np.int64)
+        hi = np.minimum(lo + 1, mm - 1)
+        a, b, t = srt[lo, ar], srt[hi, ar], h - lo
+        d = b - a
+        return np.where(t >= 0.5, b - d * (1 - t), a + d * t)
+
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        mx = np.where(live, srt[mm - 1, ar], 1.0)
+        scale = quantile(q_upper) - quantile(q_lower)
+        scale = np.where(scale > 0, scale, mx)
+        y = np.log1p(np.maximum(v, 0.0) / scale[None, :]) / np.log1p(mx / scale)[None, :]
+    out[:, live] = y[:, live]
     return out
 
 

@@ -188,32 +188,24 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     gsp = engine._cosine(st)
     random_gsp = np.mean(rand_each, axis=0)
     gsp_score = gsp - mu * random_gsp
-    lr_adata.var["LRSS_Target"] = gsp[own]
-    lr_adata.var["LRSS_Random"] = random_gsp[own]
-    lr_adata.var["LR_SpatialSpecificity"] = gsp_score[own]
-    # the QC column the ranking consumes (reference :493-504 via scanpy) + its cheap siblings
+    # the reference's three var columns (:488-490), the QC column the ranking consumes (:493-504 via scanpy) and its cheap
+    # siblings, written in one go
     n = lr_adata.shape[0]
-    lr_adata.var["n_cells_by_counts"] = st[4][own].astype(np.int64)
-    lr_adata.var["mean_counts"] = st[3][own] / n
-    lr_adata.var["pct_dropout_by_counts"] = 100.0 * (1.0 - st[4][own] / n)
-    lr_adata.var["total_counts"] = st[3][own]
-    lr_adata.var["log1p_mean_counts"] = np.log1p(st[3][own] / n)
-    lr_adata.var["log1p_total_counts"] = np.log1p(st[3][own])
+    nnz_own, sum_own = st[4][own], st[3][own]
+    lr_adata.var = lr_adata.var.assign(
+        LRSS_Target=gsp[own], LRSS_Random=random_gsp[own], LR_SpatialSpecificity=gsp_score[own],
+        n_cells_by_counts=nnz_own.astype(np.int64), mean_counts=sum_own / n, pct_dropout_by_counts=100.0 * (1.0 - nnz_own / n),
+        total_counts=sum_own, log1p_mean_counts=np.log1p(sum_own / n), log1p_total_counts=np.log1p(sum_own))
     if output == "frames":
         _utils._write_obs_qc(lr_adata, sm, shard)
 
-    # ---- ranking (reference :499-526) ----
-    if shard is None:
-        lr_var = lr_adata.var
-    else:
-        lr_var = pd.DataFrame({"LR_SpatialSpecificity": gsp_score, "n_cells_by_counts": st[4].astype(np.int64)},
-                              index=pd.Index(shard.names_global, dtype=object))
-    lr_var = lr_var.sort_values(by="LR_SpatialSpecificity", ascending=False).copy()
-    n_cells_expressed = lr_var["n_cells_by_counts"].to_numpy()
-    ranking = lr_var["LR_SpatialSpecificity"].to_numpy().copy()
-    ranking[n_cells_expressed < n_cells_expressed_threshold] = np.min(ranking) - 0.001
+    # ---- ranking (reference :499-526): sort by score (descending), penalise pairs seen in too few cells, keep the top ----
+    names_all = np.asarray(lr_adata.var_names if shard is None else shard.names_global, dtype=object)
+    by_score = np.argsort(-gsp_score, kind="stable")                 # = sort_values(ascending=False); NaN scores last
+    ranking = gsp_score[by_score].copy()
+    ranking[st[4][by_score].astype(np.int64) < n_cells_expressed_threshold] = np.min(ranking) - 0.001
     top = _utils._select_top_n(ranking, min(int(n_top_lr), len(ranking)))
-    names = lr_var.index.to_numpy(dtype=object)[top]
+    names = names_all[by_score][top]
     ligs = [nm.split("::")[0] for nm in names]
     recs = [nm.split("::")[1] for nm in names]
     laris_lr = pd.DataFrame({"ligand": ligs, "receptor": recs, "score": ranking[top]})

@@ -387,12 +387,12 @@ def _specificity_rows(laris_lr, genes_all, score_all, cats):
 
 def _celltype_prefetch(adata, lr_adata, groupby, use_rep_spatial, number_nearest_neighbors, mu, expressed_pct,
                        remove_lowly_expressed, contract_impl, shard, radius):
-    """Everything of the cell-type step that does NOT depend on the ranking, enqueued on the device in one go: the COSG
-    gene sums of every LR gene, the per-type non-zero counts (K5b), the neighbourhood composition, the cell-type-pair
-    contraction (K5), its cosine / regularisation (T1), the gathers of a sharded run and the column normalisation (T2).
-    ``runLARIS`` calls it right after queueing the spatial statistics, i.e. BEFORE it waits for them: the host work in
-    here and the ranking that follows run while the device is busy.  Returns a dict for
-    ``_calculate_laris_score_by_celltype(_pre=...)``."""
+    """The part of the cell-type step that does NOT depend on the ranking, queued on the device without a single host
+    synchronisation: the COSG gene sums of every LR gene, the per-type non-zero counts (K5b), the neighbourhood graph and
+    composition and the key histogram of the contraction (K5).  ``runLARIS`` calls it right after queueing the spatial
+    statistics, i.e. BEFORE it waits for them: the host work in here, the ranking that follows and the host side of the
+    gene table all run while the device is busy.  Returns a dict for ``_calculate_laris_score_by_celltype(_pre=...)``
+    whose ``*_finish`` entries complete the queued pieces."""
     if groupby not in adata.obs:
         raise ValueError(f"'{groupby}' not found in adata.obs")
     if use_rep_spatial not in adata.obsm:
@@ -409,10 +409,10 @@ def _celltype_prefetch(adata, lr_adata, groupby, use_rep_spatial, number_nearest
     cnt_d = K.celltype_nonzero_count(sm.S, sm.P, labels_d, C)                                   # [C, P_local] int64
     if shard is not None:
         cnt_d = _dist.all_gather_pairs_dev(cnt_d, shard, axis=1)
-    raw_d, pair_names = _neighborhood_raw(adata, sm, labels, use_rep_spatial, number_nearest_neighbors, mu, contract_impl,
-                                          shard, radius)
-    return dict(labels=labels, lr_names=lr_names, genes_all=genes_all, cosg_finish=cosg_finish, cnt_d=cnt_d, raw_d=raw_d,
-                pair_names=pair_names, ctc_d=_normalise_table_device(raw_d))
+    raw_finish = _neighborhood_raw_async(adata, sm, labels, use_rep_spatial, number_nearest_neighbors, mu, contract_impl,
+                                         shard, radius)
+    return dict(labels=labels, lr_names=lr_names, genes_all=genes_all, cosg_finish=cosg_finish, cnt_d=cnt_d,
+                raw_finish=raw_finish)
 
 
 def _calculate_diffused_lr_specificity(lr_adata, groupby: str = "CellTypes", mu: float = 100, expressed_pct: float = 0.05,
@@ -444,9 +444,11 @@ def _observed_ss_device(sm, graph):
     return st_d[1].contiguous()
 
 
-def _neighborhood_raw(adata, sm, labels, use_rep_spatial, number_nearest_neighbors, mu, contract_impl, shard, radius):
-    """Device table of the co-localisation step: raw [P, C^2] fp64 regularised cosines in global pair order, and the
-    sender::receiver names.  Reference :838-880."""
+def _neighborhood_raw_async(adata, sm, labels, use_rep_spatial, number_nearest_neighbors, mu, contract_impl, shard, radius):
+    """Co-localisation step, reference :838-880.  Queues the graph, the neighbourhood composition and the key histogram
+    of the contraction (nothing here synchronises the host) and returns ``finish()``, which runs the contraction (its
+    entry total is read back there), the cosine / regularisation and the gather of a sharded run: the raw [P, C^2] fp64
+    device table in global pair order, and the sender::receiver names."""
     codes, cats, n_c, labels_d = labels
     C = len(cats)
     if radius is None:
@@ -455,11 +457,21 @@ def _neighborhood_raw(adata, sm, labels, use_rep_spatial, number_nearest_neighbo
     else:
         graph = engine.build_radius_graph(_coords(adata, use_rep_spatial), radius, False, None)
     N = K.neighborhood_composition(labels_d, graph.idx, graph.w, C)
-    num, qn2 = K.celltype_pair_contract(sm.S, sm.P, N, contract_impl, order=graph.order)
-    _, raw = K.pair_cosine_regularise(num, _observed_ss_device(sm, graph), qn2, mu)
-    if shard is not None:        # the regularisation runs over a pair's own C^2 row, so rows are final before the gather
-        raw = _dist.all_gather_pairs_dev(raw, shard, axis=0)
-    return raw, [f"{a}::{b}" for a in cats for b in cats]
+    keys = K.celltype_pair_keys(N) if (contract_impl in (None, 2) and C <= K.MMA_MAX_C) else None
+    ss_d = _observed_ss_device(sm, graph)
+
+    def finish():
+        num, qn2 = K.celltype_pair_contract(sm.S, sm.P, N, contract_impl, order=graph.order, key_count=keys)
+        _, raw = K.pair_cosine_regularise(num, ss_d, qn2, mu)
+        if shard is not None:    # the regularisation runs over a pair's own C^2 row, so rows are final before the gather
+            raw = _dist.all_gather_pairs_dev(raw, shard, axis=0)
+        return raw, [f"{a}::{b}" for a in cats for b in cats]
+    return finish
+
+
+def _neighborhood_raw(adata, sm, labels, use_rep_spatial, number_nearest_neighbors, mu, contract_impl, shard, radius):
+    return _neighborhood_raw_async(adata, sm, labels, use_rep_spatial, number_nearest_neighbors, mu, contract_impl, shard,
+                                   radius)()
 
 
 def _neighborhood_tables(adata, lr_adata, groupby, use_rep_spatial, number_nearest_neighbors, mu, contract_impl, shard,
@@ -755,6 +767,10 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
     lr_names = pre["lr_names"]
     P = len(lr_names)
 
+    # the contraction (K5), T1 and T2 go to the device first: they run while the host finishes the gene table below
+    raw_d0, pair_names0 = pre["raw_finish"]()
+    ctc_d = _normalise_table_device(raw_d0)
+
     # ---- step 1: ligand / receptor specificity (reference :1306) ----
     _log(verbose, "\n--- Step 1: Calculating ligand and receptor cell type specificity ---")
     score_all, _ = pre["cosg_finish"]()
@@ -792,7 +808,8 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
 
     # ---- step 4: co-localisation weight (:1448-1472) and clean-up (:1480-1489) ----
     _log(verbose, "\n--- Step 4: Incorporating spatial cell type co-localization ---")
-    raw_d, ctc_names, pair_names, ctc_d = pre["raw_d"], lr_names, pre["pair_names"], pre["ctc_d"]
+    raw_d, pair_names = raw_d0, pair_names0
+    ctc_names = lr_names
     if output == "frames":
         _store_neighborhood_uns(lr_adata, "cosg_lr", groupby, mu, raw_d.cpu().numpy(), ctc_names, pair_names, True, "@@")
     flat_d, table_d, active_d = K.finalize_scores(inter_d, rescale_d, ctc_d, pair_id_d, P, score_threshold)
