@@ -65,15 +65,25 @@ def take_strings(values, codes):
     return StringTaker(values).take(codes)
 
 
+_REAL_COSG = [False, None]          # [looked up, module]: a failing ``import cosg`` walks sys.path every time it is tried
+
+
 def real_cosg():
-    try:
-        import cosg  # type: ignore
-        if (hasattr(cosg, "indexByGene") and hasattr(cosg, "iqrLogNormalize")
-                and not getattr(cosg, "__laris_stub__", False)):
-            return cosg
-    except ImportError:
-        pass
-    return None
+    """The installed ``cosg`` package, or None (looked up once per process; a stub module put into ``sys.modules`` by the
+    oracle is not the real thing)."""
+    import sys
+    mod = sys.modules.get("cosg")
+    if mod is not None and getattr(mod, "__laris_stub__", False):
+        return None
+    if not _REAL_COSG[0]:
+        _REAL_COSG[0] = True
+        try:
+            import cosg  # type: ignore
+            if hasattr(cosg, "indexByGene") and hasattr(cosg, "iqrLogNormalize") and not getattr(cosg, "__laris_stub__", False):
+                _REAL_COSG[1] = cosg
+        except ImportError:
+            pass
+    return _REAL_COSG[1]
 
 
 def ranked_frame(names, scores, groups, delimiter="@@"):

@@ -39,6 +39,7 @@ class SpatialGraph:
 
     csr: tuple | None = None   # radius graphs: (indptr int64, indices int32, dist fp64, w64 fp64) on the device
     xy: torch.Tensor | None = None   # the coordinates the search ran on (device), for re-use by a later graph
+    xy_host: np.ndarray | None = None   # ... and the host array they were uploaded from, if any
 
     def to_scipy(self):
         """The reference's ``cellxcell`` (n x n CSR, fp64 weights, int64 indices)."""
@@ -79,15 +80,24 @@ def build_graph(xy, k, include_self, sigma=None, like: SpatialGraph | None = Non
     neighbour lists are re-used and only the weights are recomputed (runLARIS builds two graphs that differ only in
     the decay rule, reference laris/tools/_utils.py:383-394 and :846-853)."""
     _check_sigma(sigma)
-    xy_d = _coords_to_device(xy).contiguous()
-    if (like is not None and like.xy is not None and like.csr is None and like.k == int(k)
-            and like.include_self == bool(include_self) and like.xy.shape == xy_d.shape and like.xy.dtype == xy_d.dtype
-            and (like.xy.data_ptr() == xy_d.data_ptr() or bool(torch.equal(like.xy, xy_d)))):
-        idx, dist, order = like.idx, like.dist, like.order
+    xy_host = None if torch.is_tensor(xy) else np.asarray(xy)
+    same = (like is not None and like.xy is not None and like.csr is None and like.k == int(k)
+            and like.include_self == bool(include_self))
+    if same:
+        # the coordinates are compared WITHOUT a device round trip (a torch.equal would make the host wait for everything
+        # queued so far): the same device tensor, or host arrays with equal contents
+        if torch.is_tensor(xy):
+            same = like.xy.data_ptr() == xy.data_ptr() and tuple(like.xy.shape) == tuple(xy.shape)
+        else:
+            same = like.xy_host is not None and (like.xy_host is xy_host or (like.xy_host.shape == xy_host.shape
+                                                                          and np.array_equal(like.xy_host, xy_host)))
+    if same:
+        xy_d, idx, dist, order = like.xy, like.idx, like.dist, like.order
     else:
+        xy_d = _coords_to_device(xy).contiguous()
         idx, dist, order = K.knn_graph(xy_d, int(k), include_self)
     w32, w64, scale = K.decay_weights(dist, sigma, want64=True)
-    return SpatialGraph(idx, dist, w32, w64, order, scale, bool(include_self), xy=xy_d)
+    return SpatialGraph(idx, dist, w32, w64, order, scale, bool(include_self), xy=xy_d, xy_host=xy_host)
 
 
 def build_radius_graph(xy, radius, include_self, sigma=None) -> SpatialGraph:

@@ -96,7 +96,8 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     finish = engine.scores_to_csr_async(sm, dtype) if to_host else None
     lr_names = (lr_df["ligand"].astype(str) + "::" + lr_df["receptor"].astype(str)).to_numpy(dtype=object)
     obs, var = adata.obs.copy(), pd.DataFrame(index=pd.Index(lr_names, dtype=object))
-    obsm = {k: (v.clone() if torch.is_tensor(v) else np.array(v, copy=True)) for k, v in adata.obsm.items()}
+    # device-resident coordinates are shared, not cloned (nothing on this path writes to them)
+    obsm = {k: (v if torch.is_tensor(v) else np.array(v, copy=True)) for k, v in adata.obsm.items()}
     if to_host:
         X, score_fp = finish()
         lr_adata = make_anndata(X, obs=obs, var=var, obsm=obsm)
