@@ -112,6 +112,24 @@ def to_host(*tensors):
     return tuple(h.numpy() for h in outs) if len(outs) != 1 else outs[0].numpy()
 
 
+def to_host_async(*tensors):
+    """Queue device -> pinned-host copies of small result tensors NOW and return ``get()``, which waits for exactly these
+    copies (an event) and gives the numpy arrays.  Unlike ``t.cpu()`` - a copy queued at the time of the call, behind
+    whatever was launched in between - the data is on the host as soon as the kernels before this point are done."""
+    outs = []
+    for t in tensors:
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        outs.append(h)
+    done = torch.cuda.Event()
+    done.record()
+
+    def get():
+        done.synchronize()
+        return tuple(h.numpy() for h in outs) if len(outs) != 1 else outs[0].numpy()
+    return get
+
+
 # ----------------------------------------------------------------- K1 ----
 @_staged("K1 knn_graph")
 def knn_graph(xy, k, include_self, want_order=True):

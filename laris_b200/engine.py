@@ -540,9 +540,10 @@ def cosg_gene_scores_async(xu: ExpressionU, labels_d, C, n_c, mu, expressed_pct,
     gives the COSG gene x group score (cosg.cosg semantics).  Host work placed between the two calls overlaps the kernel."""
     s_d, c_d, q_d = K.onehot_contract_csr(xu.indptr, xu.packed, xu.G_u, labels_d, C, row_end=xu.row_end)
     G_u = xu.G_u
+    sums = K.to_host_async(s_d, c_d, q_d)            # on the host as soon as the contraction is done, whatever is queued after it
 
     def finish():
-        s, c, q = s_d.cpu().numpy(), c_d.cpu().numpy(), q_d.cpu().numpy()
+        s, c, q = sums()
         den = np.sqrt(q)[:, None] * np.sqrt(n_c.astype(np.float64))[None, :]
         cos = np.zeros((G_u, C))
         np.divide(s.T, den, out=cos, where=den != 0)

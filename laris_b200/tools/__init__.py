@@ -164,6 +164,12 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     st_d, rng_state = engine.spatial_stats_all(sm, graph, n_repeats, random_seed, rng)
     sm.cache["stats_d"] = st_d[0]
     sm.cache["graph"] = graph                 # the cell-type step re-uses the neighbour search when it can
+    # the statistics come down through a copy queued NOW (K.to_host_async), so that waiting for them below does not also
+    # wait for the cell-type work queued in between
+    if shard is not None:
+        stats_get = K.to_host_async(_dist.all_gather_pairs_dev(st_d, shard, axis=-1), st_d[0].contiguous())
+    else:
+        stats_get = K.to_host_async(st_d)
     pre = None
     if by_celltype:
         # queue the ranking-independent part of the cell-type step BEFORE waiting for the statistics: the device then has
@@ -174,16 +180,13 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
                              f"Available columns: {list(adata.obs.columns)}")
         pre = _utils._celltype_prefetch(adata, lr_adata, groupby, use_rep_spatial, number_nearest_neighbors, mu_celltype,
                                         expressed_pct_celltype, remove_lowly_expressed_celltype, contract_impl, shard, radius)
-    st_local = None
     if shard is not None:
-        st_local = st_d[0].cpu().numpy()
-        st_d = _dist.all_gather_pairs_dev(st_d, shard, axis=-1)
-    st_all = st_d.cpu().numpy()
-    st = st_all[0]
-    if st_local is None:
-        st_local = st
-    else:
+        st_all, st_local = stats_get()
+        st = st_all[0]
         sm.cache.update(sum_global=st[3], ss_global=st[1])
+    else:
+        st_all = stats_get()
+        st = st_local = st_all[0]
     sm.cache.update(ss=st_local[1], sum=st_local[3], nnz=st_local[4])
     rand_each = np.asarray([engine._cosine(st_all[1 + r]) for r in range(n_repeats)]).reshape(n_repeats, st.shape[1])
     gsp = engine._cosine(st)
