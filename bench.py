@@ -253,8 +253,10 @@ def kernel_rooflines(stage_ms, calls, c, P_local, nnz_u, k, hbm_peak, bf16_peak,
         "HBM read.  Up to 1.18 M cells the pass runs per 16-column block on a compacted copy that stays in L2, so the gathers "
         "are L2 hits and this figure can exceed the HBM peak; the DRAM bytes actually moved are in `traffic`")
     add("K5b nonzero_count", 4 * n * P_local, "4nP: S read once")
-    add("K5 pair_contract", None, "2 n P C^2 algorithmic flop (tensor cores, fp32 accumulate)", bound="tensor",
-        flops=2.0 * n * P_local * C * C)
+    add("K5 pair_contract", 4 * n * P_local,
+        "4nP: one read of S is the floor of the key-gather contraction (the default at <= 8 cell-type pairs per cell); it reads S "
+        "once per key a cell takes part in (3.0x at config 3, mostly L2 hits).  The tcgen05 variant (mixed neighbourhoods, "
+        "label-permutation null) is reported by tools/check_mma.py in TFLOP/s")
     return recs
 
 
@@ -397,7 +399,7 @@ def run_ours(args):
         except Exception:
             pass
     for r in recs:
-        r["traffic"] = traffic.get(r["kernel"])
+        r["traffic"] = traffic.get(r["kernel"]) if world == 1 else None     # the ncu captures are single-GPU, whole table
     hbm_recs = [r for r in recs if r["bound"] == "hbm"]
     dominant = max(hbm_recs, key=lambda r: r["share_of_step"]) if hbm_recs else None
     roofline = None
