@@ -290,13 +290,47 @@ __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// L2 residency control for the column-blocked pass: the compact block (written once, gathered R*k times per row) is
+// marked evict_last, everything that merely streams past it (S on its way into the block, the edge lists) evict_first, so
+// that 80 MB of edge lists per launch do not push block lines out (ncu before: 38 % of the gathers missed L2).
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ldg_f4_policy(const float4* p, uint64_t pol) {
+    float4 r;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float4 ldg_f4_stream_policy(const float4* p, uint64_t pol) {
+    float4 r;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_f4_policy(float4* p, float4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async16_policy(uint32_t dst, const void* src, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async4_policy(uint32_t dst, const void* src, uint64_t pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+
 // One (column block, repeat) per launch over the COMPACT block (see compact_block_kernel).  Warps are independent: a warp
 // covers 32/QUADS rows x QUADS column quads per step, brings the edge lists of its NEXT step into its own slice of
 // shared memory with cp.async while the current step gathers (no CTA barrier in the loop), keeps ten 128-bit L2
 // gathers in flight per thread, and its sums stay in fp32 (a thread sees <= 64 rows per launch; the CTA reduction and
 // everything after it is fp64): ~76 registers, three CTAs per SM.  FIRST: also sum S^2, sum S and nnz of the block
 // (needed once, not per repeat).
-template <int QUADS, bool FIRST>
+template <int QUADS, bool FIRST, bool HINT>
 __global__ void __launch_bounds__(256, 3)
 spatial_null_stats_l2_kernel(const float4* __restrict__ B4, int64_t n, const int32_t* __restrict__ nidx,
                              const float* __restrict__ nw, int k, double* __restrict__ partial /*[grid][5][QUADS*4]*/) {
@@ -310,6 +344,8 @@ spatial_null_stats_l2_kernel(const float4* __restrict__ B4, int64_t n, const int
     int a_nz[4] = {0, 0, 0, 0};
     const float4* base = B4 + quad;
     const int64_t nwarps = (int64_t)gridDim.x * 8, gw = (int64_t)blockIdx.x * 8 + warp;
+    const uint64_t keep = HINT ? l2_policy_keep() : 0, pass = HINT ? l2_policy_stream() : 0;
+    auto row_piece = [&](int64_t r) { return HINT ? ldg_f4_policy(base + r * QUADS, keep) : __ldg(base + r * QUADS); };
     auto stage = [&](int64_t b, int buf) {
         const int64_t i0 = b * RW;
         if (i0 < n) {
@@ -318,13 +354,23 @@ spatial_null_stats_l2_kernel(const float4* __restrict__ B4, int64_t n, const int
             const bool vec = rows == RW && ((((uintptr_t)(nidx + i0 * k)) | ((uintptr_t)(nw + i0 * k))) & 15) == 0;
             if (vec) {                                               // RW * k * 4 bytes is a multiple of 16 (RW >= 4)
                 for (int c = lane; c < per_buf / 4; c += 32) {
-                    cp_async16(di + 16 * c, nidx + i0 * k + 4 * c, 16);
-                    cp_async16(dw + 16 * c, nw + i0 * k + 4 * c, 16);
+                    if (HINT) {
+                        cp_async16_policy(di + 16 * c, nidx + i0 * k + 4 * c, pass);
+                        cp_async16_policy(dw + 16 * c, nw + i0 * k + 4 * c, pass);
+                    } else {
+                        cp_async16(di + 16 * c, nidx + i0 * k + 4 * c, 16);
+                        cp_async16(dw + 16 * c, nw + i0 * k + 4 * c, 16);
+                    }
                 }
             } else {
                 for (int e = lane; e < rows * k; e += 32) {
-                    cp_async4(di + 4 * e, nidx + i0 * k + e);
-                    cp_async4(dw + 4 * e, nw + i0 * k + e);
+                    if (HINT) {
+                        cp_async4_policy(di + 4 * e, nidx + i0 * k + e, pass);
+                        cp_async4_policy(dw + 4 * e, nw + i0 * k + e, pass);
+                    } else {
+                        cp_async4(di + 4 * e, nidx + i0 * k + e);
+                        cp_async4(dw + 4 * e, nw + i0 * k + e);
+                    }
                 }
             }
         }
@@ -340,7 +386,7 @@ spatial_null_stats_l2_kernel(const float4* __restrict__ B4, int64_t n, const int
         if (i < n) {
             const int32_t* ni = w_idx + buf * per_buf + (lane / QUADS) * k;
             const float* wv = w_w + buf * per_buf + (lane / QUADS) * k;
-            const float4 s = __ldg(base + i * QUADS);
+            const float4 s = row_piece(i);
             float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
             float wsum = 0.f;                                        // same association as the streaming kernel
             {
@@ -352,7 +398,7 @@ spatial_null_stats_l2_kernel(const float4* __restrict__ B4, int64_t n, const int
             for (; j + 10 <= k; j += 10) {                           // ten independent 128-bit L2 gathers in flight
                 float4 v[10];
 #pragma unroll
-                for (int u = 0; u < 10; ++u) v[u] = __ldg(base + (int64_t)ni[j + u] * QUADS);
+                for (int u = 0; u < 10; ++u) v[u] = row_piece(ni[j + u]);
 #pragma unroll
                 for (int u = 0; u < 10; ++u) {
                     const float w0 = wv[j + u];
@@ -360,7 +406,7 @@ spatial_null_stats_l2_kernel(const float4* __restrict__ B4, int64_t n, const int
                 }
             }
             for (; j < k; ++j) {
-                const float4 v0 = __ldg(base + (int64_t)ni[j] * QUADS);
+                const float4 v0 = row_piece(ni[j]);
                 const float w0 = wv[j];
                 t.x = fmaf(w0, v0.x, t.x); t.y = fmaf(w0, v0.y, t.y); t.z = fmaf(w0, v0.z, t.z); t.w = fmaf(w0, v0.w, t.w);
             }
@@ -407,14 +453,26 @@ spatial_null_stats_l2_kernel(const float4* __restrict__ B4, int64_t n, const int
 // the column block as a COMPACT [n][QUADS] matrix: the gathers then address n*QUADS*16 contiguous bytes - inside the TLB
 // reach (256 MB) and the L2 - instead of pieces strewn over the whole 4nP-byte matrix (measured: gathering the strided
 // pieces in place is bound by address translation at ~4e10 requests/s, whatever their size)
-template <int QUADS>
+template <int QUADS, bool HINT>
 __global__ void compact_block_kernel(const float4* __restrict__ S4, int64_t ld4, int64_t n, int64_t q0, int nq,
                                      float4* __restrict__ blk) {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= n * QUADS) return;
     const int64_t i = e / QUADS;
     const int q = (int)(e - i * QUADS);
-    blk[e] = q < nq ? ld_stream_f4(S4 + i * ld4 + q0 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (HINT) {
+        const float4 v = q < nq ? ldg_f4_stream_policy(S4 + i * ld4 + q0 + q, l2_policy_stream()) : make_float4(0.f, 0.f, 0.f, 0.f);
+        st_f4_policy(blk + e, v, l2_policy_keep());
+    } else {
+        blk[e] = q < nq ? ld_stream_f4(S4 + i * ld4 + q0 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// hands the block's L2 lines back: without this they would stay marked evict_last after the pass and shrink the L2 the
+// following kernels see.  The buffer is scratch, its contents are dead.
+__global__ void release_block_kernel(float4* __restrict__ blk, int64_t n128) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e < n128) asm volatile("discard.global.L2 [%0], 128;" ::"l"(reinterpret_cast<char*>(blk) + e * 128) : "memory");
 }
 
 // partial [nblk][R][ncta][5][WB] -> out rows [R][5][P]; sum S^2 / sum S / nnz come from repeat 0's launch
@@ -1031,7 +1089,16 @@ static int null_l2_quads(int64_t n) {
     return 0;   // larger n: 8-column blocks measured no faster than streaming (2e6 cells: 23.7 vs ~22 ms) - stream from HBM
 }
 
-template <int QUADS>
+static bool null_l2_hints() {             // LARIS_B200_K4B_HINTS=0 switches the L2 eviction hints off (A/B runs)
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("LARIS_B200_K4B_HINTS");
+        on = !(e && e[0] == '0');
+    }
+    return on != 0;
+}
+
+template <int QUADS, bool HINT>
 static int null_stats_l2(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* nidx, const float* nw, int k, int R,
                          double* out, cudaStream_t st) {
     constexpr int WB = QUADS * 4, ROWS = 256 / QUADS;
@@ -1049,25 +1116,30 @@ static int null_stats_l2(const float* S, int64_t ldS, int64_t n, int32_t P, cons
     LARIS_CUDA(blkbuf.alloc((size_t)n * QUADS));
     size_t smem = (size_t)4 * ROWS * k * 4;                                              // per warp: two buffers of (idx, w)
     if (smem < (size_t)ROWS * WB * 8) smem = (size_t)ROWS * WB * 8;
-    LARIS_CUDA(cudaFuncSetAttribute(spatial_null_stats_l2_kernel<QUADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    LARIS_CUDA(cudaFuncSetAttribute(spatial_null_stats_l2_kernel<QUADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARIS_CUDA(cudaFuncSetAttribute(spatial_null_stats_l2_kernel<QUADS, true, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LARIS_CUDA(cudaFuncSetAttribute(spatial_null_stats_l2_kernel<QUADS, false, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int blk = 0; blk < nblk; ++blk) {
         const int64_t q0 = (int64_t)blk * QUADS;
         const int nq = (int)(ld4 - q0 < QUADS ? ld4 - q0 : QUADS);
-        compact_block_kernel<QUADS><<<(unsigned)ceil_div(n * QUADS, 256), 256, 0, st>>>((const float4*)S, ld4, n, q0, nq, blkbuf.p);
+        compact_block_kernel<QUADS, HINT><<<(unsigned)ceil_div(n * QUADS, 256), 256, 0, st>>>((const float4*)S, ld4, n, q0, nq, blkbuf.p);
         LARIS_LAUNCH_CHECK();
         for (int r = 0; r < R; ++r) {                      // the block's R*k gathers per cell, one repeat per launch, all L2 hits
             double* dst = partial.p + ((size_t)blk * R + r) * ncta * 5 * WB;
             if (r == 0)
-                spatial_null_stats_l2_kernel<QUADS, true><<<(unsigned)ncta, 256, smem, st>>>(blkbuf.p, n, nidx, nw, k, dst);
+                spatial_null_stats_l2_kernel<QUADS, true, HINT><<<(unsigned)ncta, 256, smem, st>>>(blkbuf.p, n, nidx, nw, k, dst);
             else
-                spatial_null_stats_l2_kernel<QUADS, false><<<(unsigned)ncta, 256, smem, st>>>(blkbuf.p, n, nidx + (int64_t)r * nk,
+                spatial_null_stats_l2_kernel<QUADS, false, HINT><<<(unsigned)ncta, 256, smem, st>>>(blkbuf.p, n, nidx + (int64_t)r * nk,
                                                                                              nw + (int64_t)r * nk, k, dst);
             LARIS_LAUNCH_CHECK();
         }
     }
     null_l2_reduce_kernel<<<(unsigned)ceil_div((int64_t)nblk * R * 5 * WB, 256), 256, 0, st>>>(partial.p, nblk, R, (int)ncta, WB, P, out);
     LARIS_LAUNCH_CHECK();
+    if (HINT) {
+        const int64_t n128 = n * QUADS * 16 / 128;          // whole 128-byte lines of the block buffer
+        if (n128 > 0) release_block_kernel<<<(unsigned)ceil_div(n128, 256), 256, 0, st>>>(blkbuf.p, n128);
+        LARIS_LAUNCH_CHECK();
+    }
     return LARIS_OK;
 }
 
@@ -1115,9 +1187,13 @@ extern "C" int laris_spatial_stats_batched(const float* S, int64_t ldS, int64_t 
     const int quads = n_repeats > 0 ? null_l2_quads(n) : 0;
     if (quads) {
         double* o = out + (int64_t)row0 * 5 * P;
-        return quads == 8   ? null_stats_l2<8>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st)
-               : quads == 4 ? null_stats_l2<4>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st)
-                            : null_stats_l2<2>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st);
+        if (null_l2_hints())
+            return quads == 8   ? null_stats_l2<8, true>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st)
+                   : quads == 4 ? null_stats_l2<4, true>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st)
+                                : null_stats_l2<2, true>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st);
+        return quads == 8   ? null_stats_l2<8, false>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st)
+               : quads == 4 ? null_stats_l2<4, false>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st)
+                            : null_stats_l2<2, false>(S, ldS, n, P, null_idx, null_w, k, n_repeats, o, st);
     }
     for (int r = 0; r < n_repeats;) {
         const int rb = n_repeats - r >= 3 ? 3 : n_repeats - r;
