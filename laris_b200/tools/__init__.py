@@ -79,15 +79,15 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     else:
         K.require_cuda()
         join_upload = lambda: csr_dev                                      # noqa: E731
+    if radius is None:                                  # the device builds the graph while the host resolves the LR table
+        graph = engine.build_graph(xy, number_nearest_neighbors, True, None)
+    else:
+        graph = engine.build_radius_graph(xy, radius, True, None)
     complexes = None
     if complex_sep:
         lig_g, rec_g, complexes = _lr_units(adata, lr_df, complex_sep)
     else:
         lig_g, rec_g = _lr_gene_indices(adata, lr_df)
-    if radius is None:
-        graph = engine.build_graph(xy, number_nearest_neighbors, True, None)
-    else:
-        graph = engine.build_radius_graph(xy, radius, True, None)
     csr_dev = join_upload()
     expr_fp = engine.device_fingerprint_async(csr_dev[2])      # read lazily, at the first cache lookup
     xu, lig_c, rec_c = engine.select_lr_genes(adata.X, lig_g, rec_g, csr_dev=csr_dev, layout=layout,
@@ -203,6 +203,11 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     if output == "frames":
         _utils._write_obs_qc(lr_adata, sm, shard)
 
+    if pre is not None and calculate_pvalues:
+        # the background sets only need the column moments that just arrived: queue their search now, K6 finds them
+        # on the device
+        pre["bg"] = (n_neighbors_permutation, _utils._background_sets_device(lr_adata, n_neighbors_permutation, shard=shard))
+
     # ---- ranking (reference :499-526): sort by score (descending), penalise pairs seen in too few cells, keep the top ----
     names_all = np.asarray(lr_adata.var_names if shard is None else shard.names_global, dtype=object)
     by_score = np.argsort(-gsp_score, kind="stable")                 # = sort_values(ascending=False); NaN scores last
@@ -214,6 +219,8 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     recs = [nm.split("::")[1] for nm in names]
     laris_lr = pd.DataFrame({"ligand": ligs, "receptor": recs, "score": ranking[top]})
     laris_lr.index = pd.Index([f"{l}::{r}" for l, r in zip(ligs, recs)], dtype=object)
+    if pre is not None:
+        pre["pair_id"] = np.asarray(by_score[top], dtype=np.int64)       # rows of laris_lr as positions in names_all
     laris_lr["Rank"] = np.arange(len(laris_lr))
     _log(verbose, f"  Identified {len(laris_lr)} top spatially-specific LR pairs")
 

@@ -403,7 +403,11 @@ def _celltype_prefetch(adata, lr_adata, groupby, use_rep_spatial, number_nearest
     codes, cats, n_c, labels_d = labels
     C = len(cats)
     lr_names = np.asarray(lr_adata.var_names if shard is None else shard.names_global, dtype=object)
-    genes_all = np.unique(np.array([g for nm in lr_names for g in nm.split("::")], dtype=object))
+    halves = [nm.split("::") for nm in lr_names]
+    genes_all = np.unique(np.array([g for h in halves for g in h], dtype=object))
+    gene_pos = pd.Index(genes_all)
+    lig_g = gene_pos.get_indexer([h[0] for h in halves])              # position of every pair's ligand / receptor in genes_all
+    rec_g = gene_pos.get_indexer([h[-1] for h in halves])
     cosg_finish = _gene_cosg_scores_async(adata, genes_all, groupby, mu, expressed_pct, remove_lowly_expressed, shard, labels)
     sm = _scores_of(lr_adata)
     cnt_d = K.celltype_nonzero_count(sm.S, sm.P, labels_d, C)                                   # [C, P_local] int64
@@ -411,8 +415,8 @@ def _celltype_prefetch(adata, lr_adata, groupby, use_rep_spatial, number_nearest
         cnt_d = _dist.all_gather_pairs_dev(cnt_d, shard, axis=1)
     raw_finish = _neighborhood_raw_async(adata, sm, labels, use_rep_spatial, number_nearest_neighbors, mu, contract_impl,
                                          shard, radius)
-    return dict(labels=labels, lr_names=lr_names, genes_all=genes_all, cosg_finish=cosg_finish, cnt_d=cnt_d,
-                raw_finish=raw_finish)
+    return dict(labels=labels, lr_names=lr_names, genes_all=genes_all, lig_g=lig_g, rec_g=rec_g, cosg_finish=cosg_finish,
+                cnt_d=cnt_d, raw_finish=raw_finish)
 
 
 def _calculate_diffused_lr_specificity(lr_adata, groupby: str = "CellTypes", mu: float = 100, expressed_pct: float = 0.05,
@@ -650,11 +654,18 @@ def _mean_variance_neighbors(feats, n_nearest_neighbors, leaf_size):
     bit, ties by index) when the points are distinct; with duplicated points the KD-tree's tie order depends on its
     traversal, so those tables (and tiny ones, where sklearn itself switches to brute force) go through the host
     KD-tree exactly as the reference does."""
+    idx = _mean_variance_neighbors_device(feats, n_nearest_neighbors, leaf_size)
+    return idx.cpu().numpy().astype(np.int64) if torch.is_tensor(idx) else idx
+
+
+def _mean_variance_neighbors_device(feats, n_nearest_neighbors, leaf_size):
+    """``_mean_variance_neighbors`` without the download: a device int32 tensor when the search ran on the device, the
+    host KD-tree's int64 array otherwise."""
     from sklearn.neighbors import KDTree
     kq = n_nearest_neighbors + 1
     distinct = len(np.unique(feats, axis=0)) == len(feats)
     if distinct and 2 * kq < len(feats) and kq <= 64:
-        return K.knn_graph(K.to_device(feats, torch.float64), kq, True, want_order=False)[0].cpu().numpy().astype(np.int64)
+        return K.knn_graph(K.to_device(feats, torch.float64), kq, True, want_order=False)[0]
     _, idx = KDTree(feats, leaf_size=leaf_size, metric="euclidean").query(feats, k=min(kq, len(feats)))
     return idx
 
@@ -673,6 +684,14 @@ def _prepare_background_interactions(lr_adata, n_nearest_neighbors: int = 30, le
     """30-NN of every LR pair in (mean, variance) space (reference :1013-1109).
 
     The column moments come from the device pass over S; see ``_mean_variance_neighbors`` for the search."""
+    idx = _background_sets_device(lr_adata, n_nearest_neighbors, leaf_size, shard).cpu().numpy().astype(np.int64)
+    names = lr_adata.var_names if shard is None else pd.Index(shard.names_global, dtype=object)
+    return pd.DataFrame(idx, index=names, columns=range(idx.shape[1]))
+
+
+def _background_sets_device(lr_adata, n_nearest_neighbors=30, leaf_size=30, shard=None):
+    """The background sets as a device int32 tensor [P, n_nearest_neighbors] (what K6 reads); nothing comes back to the
+    host when the search itself ran on the device."""
     sm = _scores_of(lr_adata)
     if "sum" not in sm.cache:
         graph = engine.SpatialGraph(torch.zeros((sm.n, 1), dtype=torch.int32, device=sm.S.device), None,
@@ -680,17 +699,18 @@ def _prepare_background_interactions(lr_adata, n_nearest_neighbors: int = 30, le
         st = engine.observed_stats(sm, graph)
         sm.cache.update(ss=st[1], sum=st[3], nnz=st[4])
     n = sm.n
-    csum, css, names = sm.cache["sum"], sm.cache["ss"], lr_adata.var_names
+    csum, css = sm.cache["sum"], sm.cache["ss"]
     if shard is not None:
         if "sum_global" in sm.cache:
             csum, css = sm.cache["sum_global"], sm.cache["ss_global"]
         else:
             csum, css = _dist.all_gather_pairs(csum, shard), _dist.all_gather_pairs(css, shard)
-        names = pd.Index(shard.names_global, dtype=object)
     mean = csum / n
     var = css / n - mean ** 2
-    idx = _mean_variance_neighbors(np.column_stack([mean, var]), n_nearest_neighbors, leaf_size)
-    return pd.DataFrame(idx[:, 1:], index=names, columns=range(idx.shape[1] - 1))
+    idx = _mean_variance_neighbors_device(np.column_stack([mean, var]), n_nearest_neighbors, leaf_size)
+    if torch.is_tensor(idx):
+        return idx[:, 1:].contiguous()
+    return K.to_device(np.ascontiguousarray(idx[:, 1:], dtype=np.int32), torch.int32)
 
 
 _NUMPY_DRAW_BYTES = 256 << 20          # host / device bytes of reference-stream draws alive at a time
@@ -767,14 +787,51 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
     lr_names = pre["lr_names"]
     P = len(lr_names)
 
-    # the contraction (K5), T1 and T2 go to the device first: they run while the host finishes the gene table below
-    raw_d0, pair_names0 = pre["raw_finish"]()
-    ctc_d = _normalise_table_device(raw_d0)
-
-    # ---- step 1: ligand / receptor specificity (reference :1306) ----
+    # ---- step 1: ligand / receptor specificity (reference :1306).  The gene sums came down through a copy queued right
+    # after their kernel, so this host work runs while the device is still busy with K5b / the composition; the
+    # contraction (K5), T1 and T2 are awaited after it ----
     _log(verbose, "\n--- Step 1: Calculating ligand and receptor cell type specificity ---")
     score_all, _ = pre["cosg_finish"]()
-    spec_genes, spec_m = _specificity_rows(laris_lr, pre["genes_all"], score_all, cats)
+    sp_score = laris_lr["score"].to_numpy(dtype=np.float64)
+    ranked = pre.get("pair_id")
+    if ranked is not None and len(ranked) == len(laris_lr) and cosg_compat.real_cosg() is None:
+        # runLARIS ranked the pairs itself and hands their ids in: no name look-ups.  Every gene of a pair is in
+        # genes_all (sorted), so the gene set of the kept pairs in sorted-name order is a sorted set of indices
+        pair_id = np.asarray(ranked, dtype=np.int64)
+        lig_g, rec_g = pre["lig_g"][pair_id], pre["rec_g"][pair_id]
+        used = np.unique(np.concatenate([lig_g, rec_g]))
+        table = np.nan_to_num(np.where(score_all[used] == -1, 0.0, score_all[used]), nan=0.0)
+        spec_m = cosg_compat.iqr_log_normalize_array(table)
+        lig_row, rec_row = np.searchsorted(used, lig_g), np.searchsorted(used, rec_g)
+        lig = laris_lr["ligand"].to_numpy(dtype=object)
+        rec = laris_lr["receptor"].to_numpy(dtype=object)
+        inter_names = pre["lr_names"][pair_id]
+    else:
+        spec_genes, spec_m = _specificity_rows(laris_lr, pre["genes_all"], score_all, cats)
+        lig = laris_lr["ligand"].to_numpy(dtype=object)
+        rec = laris_lr["receptor"].to_numpy(dtype=object)
+        inter_names = np.array([f"{l}::{r}" for l, r in zip(lig, rec)], dtype=object)
+        spec_index = pd.Index(spec_genes)
+        keep = (spec_index.get_indexer(lig) >= 0) & (spec_index.get_indexer(rec) >= 0)
+        lig, rec, sp_score, inter_names = lig[keep], rec[keep], sp_score[keep], inter_names[keep]
+        if len(lig) == 0:
+            return pd.DataFrame(columns=cols6)
+        pair_id = pd.Index(lr_names).get_indexer(inter_names)
+        if (pair_id < 0).any():
+            raise KeyError(f"interactions not found in lr_adata.var_names: {list(inter_names[pair_id < 0][:5])}")
+        lig_row, rec_row = spec_index.get_indexer(lig), spec_index.get_indexer(rec)
+    with np.errstate(invalid="ignore"):
+        factor = np.ones_like(sp_score) if spatial_weight == 0 else np.power(sp_score, spatial_weight)
+    npair = len(lig)
+    pair_id_d = K.to_device(pair_id.astype(np.int32), torch.int32)
+    spec_lig_d = K.to_device(spec_m[lig_row], torch.float64)
+    spec_rec_d = K.to_device(spec_m[rec_row], torch.float64)
+    factor_d = K.to_device(factor, torch.float64)
+    n_c_d = K.to_device(n_c.astype(np.float64), torch.float64)
+
+    # the contraction (K5), T1 and T2
+    raw_d0, pair_names0 = pre["raw_finish"]()
+    ctc_d = _normalise_table_device(raw_d0)
 
     # ---- step 2: cells with a non-zero score per type (reference :1325-1337), counts stay on the device ----
     _log(verbose, "\n--- Step 2: Calculating diffused LR-score distribution ---")
@@ -782,26 +839,7 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
 
     # ---- step 3: interaction scores (:1351-1406), [pair, sender, receiver] on the device ----
     _log(verbose, f"\n--- Step 3: Computing interaction scores (spatial_weight={spatial_weight}) ---")
-    lig = laris_lr["ligand"].to_numpy(dtype=object)
-    rec = laris_lr["receptor"].to_numpy(dtype=object)
-    sp_score = laris_lr["score"].to_numpy(dtype=np.float64)
-    inter_names = np.array([f"{l}::{r}" for l, r in zip(lig, rec)], dtype=object)
-    spec_index = pd.Index(spec_genes)
-    keep = (spec_index.get_indexer(lig) >= 0) & (spec_index.get_indexer(rec) >= 0)
-    lig, rec, sp_score, inter_names = lig[keep], rec[keep], sp_score[keep], inter_names[keep]
-    if len(lig) == 0:
-        return pd.DataFrame(columns=cols6)
-    pair_id = pd.Index(lr_names).get_indexer(inter_names)
-    if (pair_id < 0).any():
-        raise KeyError(f"interactions not found in lr_adata.var_names: {list(inter_names[pair_id < 0][:5])}")
-    gene_row = spec_index.get_indexer
-    with np.errstate(invalid="ignore"):
-        factor = np.ones_like(sp_score) if spatial_weight == 0 else np.power(sp_score, spatial_weight)
-    npair = len(lig)
-    pair_id_d = K.to_device(pair_id.astype(np.int32), torch.int32)
-    inter_d = K.interaction_scores(K.to_device(spec_m[gene_row(lig)], torch.float64),
-                                   K.to_device(spec_m[gene_row(rec)], torch.float64), K.to_device(factor, torch.float64),
-                                   cnt_d, K.to_device(n_c.astype(np.float64), torch.float64), pair_id_d, P)
+    inter_d = K.interaction_scores(spec_lig_d, spec_rec_d, factor_d, cnt_d, n_c_d, pair_id_d, P)
 
     # ---- step 3.5: rescale by 0.1 / mean(top 100) (:1426-1437) ----
     rescale_d = K.topk_mean(inter_d.view(-1), 100)
@@ -837,9 +875,12 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
     if calculate_pvalues:
         # ---- step 5.1: background sets (:1507) ----
         _log(verbose, "\n--- Step 5.1: Preparing background interaction sets ---")
-        bg = _prepare_background_interactions(lr_adata, n_nearest_neighbors=n_nearest_neighbors, shard=shard).to_numpy()
-        nb = bg.shape[1]
-        bg_d = K.to_device(np.ascontiguousarray(bg, dtype=np.int32), torch.int32)
+        queued = pre.get("bg")                       # runLARIS queues the search as soon as the column moments are known
+        if queued is not None and queued[0] == n_nearest_neighbors:
+            bg_d = queued[1]
+        else:
+            bg_d = _background_sets_device(lr_adata, n_nearest_neighbors, shard=shard)
+        nb = bg_d.shape[1]
 
         # ---- step 5.2: permutation p-values (:1518-1596) ----
         _log(verbose, f"\n--- Step 5.2: Calculating p-values ({n_permutations:,} permutations, rng={rng}) ---")
