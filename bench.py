@@ -224,7 +224,7 @@ def pin_cpus(local, world):
         return None
 
 
-def kernel_rooflines(stage_ms, calls, c, P_local, nnz_u, k, hbm_peak, bf16_peak, step_ms, world):
+def kernel_rooflines(stage_ms, calls, c, P_local, nnz_u, k, hbm_peak, bf16_peak, step_ms, world, n_entries=0):
     """Per-kernel roofline records from the stage timer: ALGORITHMIC bytes (SURVEY 8d with the sparse
     layout's own bytes) divided by the stage's average device time inside the timed steps."""
     n, C, R = c.n, c.C, c.R
@@ -252,6 +252,12 @@ def kernel_rooflines(stage_ms, calls, c, P_local, nnz_u, k, hbm_peak, bf16_peak,
         f"(1 + R k) 4nP + 8nkR for the R={R} repeats - SURVEY 8(d)'s bytes, which count every random neighbour row as a fresh "
         "HBM read.  Up to 1.18 M cells the pass runs per 16-column block on a compacted copy that stays in L2, so the gathers "
         "are L2 hits and this figure can exceed the HBM peak; the DRAM bytes actually moved are in `traffic`")
+    add("K4 sparse_stats", 8 * k * n_entries * (1 + R) + 4 * n * P_local + 8 * n * k * (1 + R),
+        f"8 k E (1+R) + 4nP + 8nk(1+R), E = {n_entries} packed entries (non-zeros of S padded to whole 32-entry chunks): the "
+        f"packed neighbour rows of the observed graph and the R={R} random graphs, S once, the edge lists.  The dense passes "
+        "it replaces (K4a tiles + K4b) are charged (1+k)4nP per graph by SURVEY 8(d); this stage moves 8 bytes per non-zero "
+        "instead of 4P bytes per gathered row")
+    add("K4 pack scores", 4 * n * P_local + 8 * n_entries + 8 * (n + 1), "4nP + 8E + 8(n+1): S read once, packed rows written once")
     add("K5b nonzero_count", 4 * n * P_local, "4nP: S read once")
     add("K5 pair_contract", 4 * n * P_local,
         "4nP: one read of S is the floor of the key-gather contraction (the default at <= 8 cell-type pairs per cell); it reads S "
@@ -390,7 +396,10 @@ def run_ours(args):
     calls["_steps"] = args.steps
     xu = engine_last_xu(la)
     nnz_u = xu_nnz(xu)
-    recs = kernel_rooflines(stage_ms, calls, c, P_local, nnz_u, k, hbm_peak, bf16_peak, float(np.mean(step_ms)), world)
+    from laris_b200.tools import _utils as U
+    packed = U._scores_of(state["lr_ad"]).cache.get("packed")
+    n_entries = int(packed[1].numel()) if packed else 0
+    recs = kernel_rooflines(stage_ms, calls, c, P_local, nnz_u, k, hbm_peak, bf16_peak, float(np.mean(step_ms)), world, n_entries)
     traffic = {}
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.isfile(prof):

@@ -384,6 +384,26 @@ LARIS_API int laris_spatial_stats_batched(const float* S, int64_t ldS, int64_t n
                                           const float* w, int k, const int32_t* order, const int32_t* null_idx,
                                           const float* null_w, int32_t n_repeats, double* out, void* stream);
 
+/* --------------------------------------- K4a + K4b over packed score rows ----
+ * Same statistics as laris_spatial_stats_batched (laris/tools/__init__.py:468-481, laris/tools/_utils.py:496-518; the
+ * reference keeps lr_adata.X as a scipy CSR matrix and runs both products as sparse matrix products), for score matrices
+ * that are mostly zeros: the neighbour rows are gathered from a PACKED copy of S - 8 bytes per non-zero instead of
+ * 4*P bytes per row.
+ *   laris_scores_pack: sp_ptr [n+1] int64 = exclusive scan of the per-row non-zero counts (row_nnz of
+ *     laris_diffuse_lr_score*) ROUNDED UP to multiples of 32; entries [sp_ptr[n]] int64 = {int32 column, fp32 bits} of
+ *     the non-zeros of every row (dealt over the shared-memory banks, not ascending), then padding {ldS + j, 0}.
+ *   laris_spatial_stats_sparse: out as laris_spatial_stats_batched; a warp adds the k packed neighbour rows of a cell
+ *     into a shared-memory slab in neighbour order (the same fma chain per element as the dense kernels, zeros skipped),
+ *     column-owner threads fold the slabs and the cell's own dense row into the sums; up to 4 graphs share one read of S.
+ *     n_entries = sp_ptr[n] (picks the row-length variant).  ldS <= laris_spatial_stats_sparse_max_ld(). */
+LARIS_API int32_t laris_spatial_stats_sparse_max_ld(void);
+LARIS_API int laris_scores_pack(const float* S, int64_t ldS, int64_t n, int32_t P, const int64_t* sp_ptr, int64_t* entries,
+                                void* stream);
+LARIS_API int laris_spatial_stats_sparse(const float* S, int64_t ldS, int64_t n, int32_t P, const int64_t* sp_ptr,
+                                         const int64_t* entries, int64_t n_entries, const int32_t* idx, const float* w, int k,
+                                         const int32_t* order, const int32_t* null_idx, const float* null_w,
+                                         int32_t n_repeats, double* out, void* stream);
+
 /* ------------------------------------------------------- per-cell QC ----
  * Per-cell metrics of the score matrix that scanpy.pp.calculate_qc_metrics writes to lr_adata.obs at
  * laris/tools/__init__.py:493-496: total[i] = sum_p S[i,p], nnz[i] = #{p: S[i,p] != 0} and, for each N of

@@ -341,6 +341,39 @@ def spatial_stats_batched(S, P, idx, w, order, null_idx=None, null_w=None):
     return out
 
 
+@_staged("K4 pack scores")
+def scores_pack(S, P, sp_ptr, nnz):
+    """Packed rows of the score matrix: int64 entries {column, fp32 bits}, row i = entries[sp_ptr[i] : sp_ptr[i+1]] - its
+    non-zeros, padded with zero-valued entries to a multiple of 32 (``sp_ptr`` = scan of the padded row counts,
+    ``nnz`` = sp_ptr[n])."""
+    n, ld = S.shape
+    entries = torch.empty(max(int(nnz), 1), dtype=torch.int64, device=S.device)
+    check(lib.laris_scores_pack(_ptr(S, torch.float32), ld, n, P, _ptr(sp_ptr, torch.int64), _ptr(entries), _stream()),
+          "laris_scores_pack")
+    return entries
+
+
+def spatial_stats_sparse_max_ld():
+    return int(lib.laris_spatial_stats_sparse_max_ld())
+
+
+@_staged("K4 sparse_stats")
+def spatial_stats_sparse(S, P, sp_ptr, entries, idx, w, order, null_idx=None, null_w=None):
+    """``spatial_stats_batched`` from the packed rows (``scores_pack``) - for mostly-zero score matrices."""
+    n, ld = S.shape
+    k = idx.shape[1] if idx is not None else null_idx.shape[2]
+    R = 0 if null_idx is None else int(null_idx.shape[0])
+    out = torch.empty(((1 if idx is not None else 0) + R, 5, P), dtype=torch.float64, device=S.device)
+    check(lib.laris_spatial_stats_sparse(_ptr(S, torch.float32), ld, n, P, _ptr(sp_ptr, torch.int64), _ptr(entries, torch.int64), entries.numel(),
+                                         _ptr(idx, torch.int32) if idx is not None else None,
+                                         _ptr(w, torch.float32) if idx is not None else None,
+                                         k, _ptr(order, torch.int32) if order is not None else None,
+                                         _ptr(null_idx, torch.int32) if R else None,
+                                         _ptr(null_w, torch.float32) if R else None, R, _ptr(out), _stream()),
+          "laris_spatial_stats_sparse")
+    return out
+
+
 @_staged("K4b null_graph")
 def null_graph_philox(n, k, w, repeat, seed, out=None):
     cols, wout = out if out is not None else (torch.empty((n, k), dtype=torch.int32, device=w.device),

@@ -10,6 +10,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
+import os
+
 import numpy as np
 import scipy.sparse as sp
 import torch
@@ -330,8 +332,9 @@ class ScoreMatrix:
         return self.S.shape[0]
 
 
-def lr_scores(xu: ExpressionU, graph: SpatialGraph, lig_u, rec_u) -> ScoreMatrix:
-    """Fused diffusion + LR score (K2+K3)."""
+def lr_scores(xu: ExpressionU, graph: SpatialGraph, lig_u, rec_u, queue_pointers: bool = True) -> ScoreMatrix:
+    """Fused diffusion + LR score (K2+K3).  ``queue_pointers``: also start the row pointers of the packed form and
+    their total on the way to the host (not possible while a CUDA graph is being captured)."""
     lig_d = lig_u if torch.is_tensor(lig_u) else K.to_device(np.asarray(lig_u, dtype=np.int32), torch.int32)
     rec_d = rec_u if torch.is_tensor(rec_u) else K.to_device(np.asarray(rec_u, dtype=np.int32), torch.int32)
     if xu.dense is not None:
@@ -340,7 +343,51 @@ def lr_scores(xu: ExpressionU, graph: SpatialGraph, lig_u, rec_u) -> ScoreMatrix
     else:
         S, row_nnz = K.diffuse_lr_score(xu.indptr, xu.packed, xu.G_u, graph.idx, graph.w, graph.order, lig_d, rec_d,
                                         cx=xu.cx, row_end=xu.row_end)
-    return ScoreMatrix(S, len(lig_u), row_nnz)
+    sm = ScoreMatrix(S, len(lig_u), row_nnz)
+    if queue_pointers:
+        queue_row_pointers(sm)
+    return sm
+
+
+def queue_row_pointers(sm: "ScoreMatrix"):
+    """Row pointers of the packed form of S (exclusive scan of the row counts, rounded up to whole 32-entry chunks) and
+    their total, which starts its way to the host now - ``packed_scores`` needs it to size the entry array and by then
+    it has arrived."""
+    if sm.row_nnz is None:
+        sm.row_nnz = K.row_qc(sm.S, sm.P, ())[1].to(torch.int64)
+    sm.cache["sp_ptr"] = K.exclusive_scan((sm.row_nnz + 31) & ~31)
+    sm.cache["nnz_get"] = K.to_host_async(sm.cache["sp_ptr"][-1:])
+
+
+def sparse_stats_pays(n, P, k, n_obs, n_null, n_entries):
+    """Cost model (ms at 1e6 cells, fitted to B200 measurements, tools/time_k4s.py) choosing between the dense K4 passes
+    (tiles for the observed graph, L2-blocked / streaming for the nulls: time ~ P per cell and graph) and the packed-row
+    pass (time ~ a latency floor per (cell, graph) + the entries it gathers, + the packing pass).  The packed pass wins for
+    wide, mostly-zero tables (config 3: P = 2000 at 10 % non-zeros, 21.7 ms against 37.3 ms) and loses for narrow shards
+    or above ~15 % non-zeros."""
+    row = n_entries / max(n, 1)
+    dense = n * P * (n_null * 4.95e-3 + n_obs * 3.8e-3)
+    sparse = n * (n_obs + n_null) * (1.9 + 0.0018 * k * row) + n * P * 1.0e-3
+    return k <= 32 and sparse < 0.9 * dense
+
+
+def packed_scores(sm: "ScoreMatrix", k, n_obs, n_null):
+    """(sp_ptr, entries) - the packed rows of S for the sparse K4 pass - or None when the dense passes are expected to be
+    faster (``sparse_stats_pays``) or S is too wide for the pass.  LARIS_B200_K4_SPARSE=0 / 1 forces the dense / the
+    packed pass (A/B runs)."""
+    mode = os.environ.get("LARIS_B200_K4_SPARSE", "auto")
+    if mode == "0" or sm.S.shape[1] > K.spatial_stats_sparse_max_ld() or sm.P > 12800 or k > 64:
+        return None
+    if "packed" in sm.cache:
+        return sm.cache["packed"]
+    if "nnz_get" not in sm.cache:
+        queue_row_pointers(sm)
+    n_entries = int(np.asarray(sm.cache["nnz_get"]()).ravel()[0])
+    if mode != "1" and not sparse_stats_pays(sm.n, sm.P, k, n_obs, n_null, n_entries):
+        return None
+    packed = (sm.cache["sp_ptr"], K.scores_pack(sm.S, sm.P, sm.cache["sp_ptr"], n_entries))
+    sm.cache["packed"] = packed
+    return packed
 
 
 class CapturedScoring:
@@ -370,12 +417,13 @@ class CapturedScoring:
     def _step(xy_d, csr_dev, plan, n, k, layout, include_self):
         graph = build_graph(xy_d, k, include_self, None)
         xu = select_planned(plan, csr_dev, n, layout)
-        return graph, xu, lr_scores(xu, graph, plan.lig_d, plan.rec_d)
+        return graph, xu, lr_scores(xu, graph, plan.lig_d, plan.rec_d, queue_pointers=False)
 
     def replay(self) -> ScoreMatrix:
         """Run the captured step; the returned ScoreMatrix (and ``self.graph`` / ``self.xu``) live in graph-owned
         buffers that the next replay overwrites."""
         self.graph_exec.replay()
+        self.scores.cache.clear()                      # statistics / packed rows of the previous contents
         return self.scores
 
 
@@ -489,6 +537,12 @@ def null_graphs(graph: SpatialGraph, n_repeats, random_seed, rng="numpy"):
 def spatial_stats_all(sm: ScoreMatrix, graph: SpatialGraph, n_repeats, random_seed, rng="numpy"):
     """Observed statistics and the R null repeats (K4a + K4b) as ONE device tensor [1+R, 5, P] fp64 - no host
     synchronisation; row 0 is the observed graph.  Returns (stats_d, rng_state)."""
+    packed = packed_scores(sm, graph.idx.shape[1], 1, n_repeats)
+    if packed is not None:                        # mostly-zero scores: all graphs in one pass over the packed rows
+        cols = wts = state = None
+        if n_repeats > 0:
+            cols, wts, state = null_graphs(graph, n_repeats, random_seed, rng)
+        return K.spatial_stats_sparse(sm.S, sm.P, packed[0], packed[1], graph.idx, graph.w, graph.order, cols, wts), state
     out = torch.empty((1 + n_repeats, 5, sm.P), dtype=torch.float64, device=sm.S.device)
     out[0].copy_(K.spatial_stats_batched(sm.S, sm.P, graph.idx, graph.w, graph.order)[0])
     state = None

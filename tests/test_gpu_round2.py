@@ -383,3 +383,89 @@ def test_label_permutation_null_matches_the_oracle(dev, C, contract_impl):
     key = tab["sender"].astype(str) + "::" + tab["receiver"].astype(str)
     want = np.array([got.loc[nm, kk] for nm, kk in zip(tab["interaction_name"].iloc[:200], key.iloc[:200])])
     assert np.array_equal(tab["p_value_label_null"].to_numpy()[:200], want)
+
+
+# --------------------------------------------------------------------------- K4 over packed score rows
+def _sparse_case(n, P, k, R, density, seed=0, dense_row=True):
+    from laris_b200 import _kernels as K, engine
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    xy = torch.rand((n, 2), dtype=torch.float64, device=dev, generator=g) * 10.0 * np.sqrt(n)
+    graph = engine.build_graph(xy, k, False, 100.0)
+    ld = K.padded_ld(P)
+    S = torch.rand((n, ld), dtype=torch.float32, device=dev, generator=g)
+    S *= (torch.rand((n, ld), device=dev, generator=g) < density)
+    S[:, P:] = 0
+    if dense_row:
+        S[n // 2, :P] = 1.5                         # a row longer than one segment
+        S[n // 3, :P] = 0                           # and an empty one
+    cols, wts, _ = engine.null_graphs(graph, R, 27, "philox") if R else (None, None, None)
+    return S, graph, cols, wts
+
+
+@pytest.mark.parametrize("n,P,k,R,density", [(5000, 37, 3, 1, 0.3), (20000, 100, 5, 2, 0.2), (30000, 700, 10, 3, 0.1),
+                                             (8000, 1500, 12, 5, 0.05), (6000, 2500, 40, 2, 0.04), (4001, 2700, 7, 0, 0.1)])
+def test_packed_row_statistics_equal_the_dense_passes(n, P, k, R, density):
+    """K4 from packed rows (laris_scores_pack + laris_spatial_stats_sparse) against the dense passes (tiles / L2 blocks /
+    streaming): same fma chain per element, so sums agree to fp32-partial rounding; counts exactly.  Covers short- and
+    long-row variants, 1-4 column quads per owner, k > 32, a dense and an empty row, several launches (R + 1 > 4)."""
+    from laris_b200 import _kernels as K, engine
+    S, graph, cols, wts = _sparse_case(n, P, k, R, density)
+    sm = engine.ScoreMatrix(S, P)
+    engine.queue_row_pointers(sm)
+    n_entries = int(sm.cache["nnz_get"]()[0])
+    sp_ptr = sm.cache["sp_ptr"]
+    entries = K.scores_pack(S, P, sp_ptr, n_entries)
+    # the packed rows: whole chunks, exactly the non-zeros of S, zero-valued padding behind the last column
+    ptr = sp_ptr.cpu().numpy()
+    e = entries.cpu().numpy()
+    col, val = (e & 0xffffffff).astype(np.int64), ((e >> 32) & 0xffffffff).astype(np.uint32).view(np.float32)
+    assert (np.diff(ptr) % 32 == 0).all() and ptr[-1] == n_entries
+    real = col < S.shape[1]
+    assert (val[~real] == 0).all() and (col[~real] < S.shape[1] + 32).all()
+    rows = np.repeat(np.arange(n), np.diff(ptr))
+    Sh = S.cpu().numpy()
+    assert int(real.sum()) == int((Sh != 0).sum())
+    assert np.array_equal(Sh[rows[real], col[real]], val[real])
+    back = np.zeros_like(Sh)
+    back[rows[real], col[real]] = val[real]
+    assert np.array_equal(back, Sh)                                   # every non-zero exactly once
+    got = K.spatial_stats_sparse(S, P, sp_ptr, entries, graph.idx, graph.w, graph.order, cols, wts)
+    ref = K.spatial_stats_batched(S, P, graph.idx, graph.w, graph.order, cols, wts)
+    assert got.shape == ref.shape == (1 + R, 5, P)
+    assert torch.equal(got[:, 4], ref[:, 4])
+    assert torch.allclose(got, ref, rtol=2e-6, atol=1e-300)
+    again = K.spatial_stats_sparse(S, P, sp_ptr, entries, graph.idx, graph.w, graph.order, cols, wts)
+    assert torch.equal(got, again)                                    # bitwise reproducible
+    if R:
+        only_null = K.spatial_stats_sparse(S, P, sp_ptr, entries, None, None, None, cols, wts)
+        assert torch.allclose(only_null, ref[1:], rtol=2e-6, atol=1e-300)
+
+
+def test_whole_path_same_with_packed_and_dense_statistics(monkeypatch):
+    """runLARIS with K4 forced through the packed-row pass and through the dense passes: same ranking, same tables."""
+    import laris_b200 as la
+    from laris_b200.synth import make_dataset
+    a, lr, c = make_dataset(1)
+    outs = []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LARIS_B200_K4_SPARSE", mode)
+        ad = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=c.k)
+        laris_lr, table = la.tl.runLARIS(ad, a, n_nearest_neighbors=c.k, n_repeats=c.R, n_top_lr=c.P,
+                                         number_nearest_neighbors=c.k, n_permutations=200, verbose=False, rng="philox")
+        outs.append((ad.var.copy(), laris_lr, table))
+    (v1, l1, t1), (v0, l0, t0) = outs
+    for colname in ("LRSS_Target", "LRSS_Random", "LR_SpatialSpecificity", "total_counts"):
+        assert np.allclose(v1[colname].to_numpy(), v0[colname].to_numpy(), rtol=1e-6, atol=1e-12)
+    assert np.array_equal(v1["n_cells_by_counts"].to_numpy(), v0["n_cells_by_counts"].to_numpy())
+    assert list(l1.index) == list(l0.index)
+    assert np.allclose(t1["interaction_score"].to_numpy(), t0["interaction_score"].to_numpy(), rtol=1e-5, atol=1e-12)
+
+
+def test_sparse_statistics_cost_model():
+    from laris_b200 import engine
+    # config 3: wide and ~10 % non-zeros -> packed rows; an 8-way shard of it, or 20 % non-zeros -> dense passes
+    assert engine.sparse_stats_pays(1_000_000, 2000, 10, 1, 3, 216_000_000)
+    assert not engine.sparse_stats_pays(1_000_000, 250, 10, 1, 3, 34_000_000)
+    assert not engine.sparse_stats_pays(1_000_000, 2000, 10, 1, 3, 416_000_000)
+    assert not engine.sparse_stats_pays(1_000_000, 2000, 40, 1, 3, 216_000_000)
