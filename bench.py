@@ -181,16 +181,18 @@ class ClockSampler:
         self.th = threading.Thread(target=self._run, daemon=True) if self.indices else None
 
     def _run(self):
-        while not self.stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", ",".join(str(i) for i in self.indices)],
-                                     capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([x.strip() for x in line.split(",")])
-            except Exception:
-                pass
-            self.stop.wait(0.1 if len(self.indices) == 1 else 0.25)
+        # ONE nvidia-smi process in loop mode for the whole region: a fresh process per sample re-initialises the driver
+        # state every time and was measured to stall the kernel launches of the run it watches (bursts of +10 ms steps)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", ",".join(str(i) for i in self.indices), "-lms", "250"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop.is_set():
+                    break
+        except Exception:
+            pass
 
     def __enter__(self):
         if self.th is not None:
@@ -199,6 +201,13 @@ class ClockSampler:
 
     def __exit__(self, *exc):
         self.stop.set()
+        proc = getattr(self, "proc", None)
+        if proc is not None:
+            try:
+                proc.terminate()                         # the exact process started above
+                proc.wait(timeout=5)
+            except Exception:
+                pass
         if self.th is not None:
             self.th.join(timeout=6)
 
@@ -326,7 +335,12 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         device_step()
     barrier()
+    if os.environ.get("BENCH_NOGC") == "1":              # diagnostic: are step-time outliers Python GC pauses?
+        import gc
+        gc.collect()
+        gc.disable()
     launches0 = lib.laris_launch_count()
+    mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     step_ms = []
     with ClockSampler(range(world) if rank == 0 else []) as clocks:
         barrier()
@@ -344,6 +358,7 @@ def run_ours(args):
         barrier()
         wall = time.perf_counter() - wall0
         launches = lib.laris_launch_count() - launches0
+        device_mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0
         stage = timer.summary()
 
         # ---- e2e: the public API with host buffers (pinned caller inputs) ----
@@ -455,6 +470,7 @@ def run_ours(args):
                              "[C,P] counts, all-gather [P,C^2] co-localisation table, all-reduce [C^2,P] exceedance counts"
                              if world > 1 else "single GPU, no collective"),
                 "l2": "512 MiB buffer written between timed iterations; S alone is 4nP bytes >> L2",
+                "cudaMalloc_calls_in_timed_region": int(device_mallocs),
                 "ms_each": [round(x, 2) for x in step_ms],
                 "device_ms_per_step_sum_of_stages": device_ms,
                 "host_glue_ms_per_step": float(np.mean(step_ms)) - device_ms,

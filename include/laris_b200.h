@@ -395,10 +395,12 @@ LARIS_API int laris_spatial_stats_batched(const float* S, int64_t ldS, int64_t n
  *   laris_spatial_stats_sparse: out as laris_spatial_stats_batched; a warp adds the k packed neighbour rows of a cell
  *     into a shared-memory slab in neighbour order (the same fma chain per element as the dense kernels, zeros skipped),
  *     column-owner threads fold the slabs and the cell's own dense row into the sums; up to 4 graphs share one read of S.
- *     n_entries = sp_ptr[n] (picks the row-length variant).  ldS <= laris_spatial_stats_sparse_max_ld(). */
+ *     `capacity` / `n_entries` = length of `entries`: normally sp_ptr[n]; a caller that sizes the array from an estimate
+ *     (to avoid reading sp_ptr[n] back) may pass less - rows that do not fit are skipped by both calls and the caller
+ *     must discard the result once it knows sp_ptr[n] > capacity.  ldS <= laris_spatial_stats_sparse_max_ld(). */
 LARIS_API int32_t laris_spatial_stats_sparse_max_ld(void);
 LARIS_API int laris_scores_pack(const float* S, int64_t ldS, int64_t n, int32_t P, const int64_t* sp_ptr, int64_t* entries,
-                                void* stream);
+                                int64_t capacity, void* stream);
 LARIS_API int laris_spatial_stats_sparse(const float* S, int64_t ldS, int64_t n, int32_t P, const int64_t* sp_ptr,
                                          const int64_t* entries, int64_t n_entries, const int32_t* idx, const float* w, int k,
                                          const int32_t* order, const int32_t* null_idx, const float* null_w,

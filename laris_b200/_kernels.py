@@ -345,10 +345,10 @@ def spatial_stats_batched(S, P, idx, w, order, null_idx=None, null_w=None):
 def scores_pack(S, P, sp_ptr, nnz):
     """Packed rows of the score matrix: int64 entries {column, fp32 bits}, row i = entries[sp_ptr[i] : sp_ptr[i+1]] - its
     non-zeros, padded with zero-valued entries to a multiple of 32 (``sp_ptr`` = scan of the padded row counts,
-    ``nnz`` = sp_ptr[n])."""
+    ``nnz`` = sp_ptr[n], or an estimate of it: rows that do not fit are left out)."""
     n, ld = S.shape
     entries = torch.empty(max(int(nnz), 1), dtype=torch.int64, device=S.device)
-    check(lib.laris_scores_pack(_ptr(S, torch.float32), ld, n, P, _ptr(sp_ptr, torch.int64), _ptr(entries), _stream()),
+    check(lib.laris_scores_pack(_ptr(S, torch.float32), ld, n, P, _ptr(sp_ptr, torch.int64), _ptr(entries), entries.numel(), _stream()),
           "laris_scores_pack")
     return entries
 

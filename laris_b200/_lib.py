@@ -46,7 +46,7 @@ SIGNATURES = {
     "laris_spatial_stats": [_p, _i64, _i64, _i, _p, _p, _i, _i, _p, _p, _p],
     "laris_spatial_stats_batched": [_p, _i64, _i64, _i, _p, _p, _i, _p, _p, _p, _i, _p, _p],
     "laris_spatial_stats_sparse_max_ld": [],
-    "laris_scores_pack": [_p, _i64, _i64, _i, _p, _p, _p],
+    "laris_scores_pack": [_p, _i64, _i64, _i, _p, _p, _i64, _p],
     "laris_spatial_stats_sparse": [_p, _i64, _i64, _i, _p, _p, _i64, _p, _p, _i, _p, _p, _p, _i, _p, _p],
     "laris_null_graph_philox": [_i64, _i, _p, _i, _u64, _p, _p, _p],
     "laris_gather_f32": [_p, _p, _i64, _p, _p],

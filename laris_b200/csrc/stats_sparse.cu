@@ -43,7 +43,7 @@ constexpr int kPackBatch = 16;
 
 __global__ void __launch_bounds__(kPackWarps * 32)
 scores_pack_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, int P, const int64_t* __restrict__ sp_ptr,
-                   int2* __restrict__ out) {
+                   int2* __restrict__ out, int64_t capacity) {
     extern __shared__ uint16_t pack_q[];                         // [warp][T][32]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int T = (P + 31) / 32;
@@ -69,7 +69,8 @@ scores_pack_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, int P, c
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(kFull, maxc, o));
         int64_t base = sp_ptr[row];
-        const int64_t end = sp_ptr[row + 1];                     // counts that do not describe S must not corrupt memory
+        // counts that do not describe S, or an entry array sized from an estimate, must not corrupt memory
+        const int64_t end = min(sp_ptr[row + 1], capacity);
         const unsigned lt = (1u << lane) - 1u;
         for (int t0 = 0; t0 < maxc; t0 += 4) {                    // four rounds at a time: their value reads overlap
             int col[4];
@@ -265,7 +266,7 @@ template <int NQ, int CH, int RING>
 __global__ void __launch_bounds__(512, 1)
 spatial_stats_sparse_kernel(const int64_t* __restrict__ sp_ptr, const int2* __restrict__ entries,
                             const float4* __restrict__ S4, int64_t ld4, int64_t n, SparseGraphs gs, int NG, int k,
-                            const int32_t* __restrict__ order, int n_slots, double* __restrict__ partial) {
+                            const int32_t* __restrict__ order, int n_slots, double* __restrict__ partial, int64_t capacity) {
     const bool first = gs.slot0 == 0;
     extern __shared__ __align__(16) unsigned char sp_smem[];
     __shared__ float inv_s[2][kSpCells];
@@ -309,7 +310,7 @@ spatial_stats_sparse_kernel(const int64_t* __restrict__ sp_ptr, const int2* __re
             }
         };
         auto finish = [&](SpItem& it, long long rs, long long re) {
-            it.len = (int)(re - rs);
+            it.len = re <= capacity ? (int)(re - rs) : 0;            // rows beyond an under-sized entry array are not read
             it.rowp = entries + rs;
         };
         SpSeg<CH> ring[RING];
@@ -465,7 +466,7 @@ spatial_stats_sparse_kernel(const int64_t* __restrict__ sp_ptr, const int2* __re
     auto o_prefetch_row = [&](int nb) {
         if (nb < 0) return;
         const long long rs = ldv_s64(sp_ptr + nb), re = ldv_s64(sp_ptr + nb + 1);
-        if (re > rs)
+        if (re > rs && re <= capacity)
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(entries + rs), "r"((uint32_t)((re - rs) * 8)) : "memory");
     };
     constexpr int kAhead = 3;                                        // items between the prefetch and the builder's use (5: slower)
@@ -575,20 +576,20 @@ static size_t sparse_smem(int64_t ldS, int ng) { return (size_t)(2 * kSpCells) *
 constexpr size_t kSparseSmemMax = 200 * 1024;
 
 template <int NQ, int CH, int RING>
-static int launch_sparse_cfg(int ng, const int64_t* sp_ptr, const int2* entries, const float* S, int64_t ld4, int64_t n,
+static int launch_sparse_cfg(int64_t gs_capacity, int ng, const int64_t* sp_ptr, const int2* entries, const float* S, int64_t ld4, int64_t n,
                              const SparseGraphs& gs, int k, const int32_t* order, int n_slots, double* partial,
                              int grid, cudaStream_t st) {
     LARIS_CUDA(cudaFuncSetAttribute(spatial_stats_sparse_kernel<NQ, CH, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)kSparseSmemMax));
     spatial_stats_sparse_kernel<NQ, CH, RING><<<grid, 512, sparse_smem(ld4 * 4, ng), st>>>(
-        sp_ptr, entries, (const float4*)S, ld4, n, gs, ng, k, order, n_slots, partial);
+        sp_ptr, entries, (const float4*)S, ld4, n, gs, ng, k, order, n_slots, partial, gs_capacity);
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
 }
 
 // long_rows: segments of 8 chunks, 2 in flight (3 spill registers); else segments of 2 chunks, 8 in flight
 template <int NQ>
-static int launch_sparse(bool long_rows, int ng, const int64_t* sp_ptr, const int2* entries, const float* S, int64_t ld4,
+static int launch_sparse(int64_t cap, bool long_rows, int ng, const int64_t* sp_ptr, const int2* entries, const float* S, int64_t ld4,
                          int64_t n, const SparseGraphs& gs, int k, const int32_t* order, int n_slots,
                          double* partial, int grid, cudaStream_t st) {
     static int ring = -1;                  // LARIS_B200_K4S_RING=3: three 8-chunk segments in flight instead of two (A/B runs; spills)
@@ -597,9 +598,9 @@ static int launch_sparse(bool long_rows, int ng, const int64_t* sp_ptr, const in
         ring = e ? atoi(e) : 2;
     }
     if (long_rows && ring == 3)
-        return launch_sparse_cfg<NQ, 8, 3>(ng, sp_ptr, entries, S, ld4, n, gs, k, order, n_slots, partial, grid, st);
-    return long_rows ? launch_sparse_cfg<NQ, 8, 2>(ng, sp_ptr, entries, S, ld4, n, gs, k, order, n_slots, partial, grid, st)
-                     : launch_sparse_cfg<NQ, 2, 8>(ng, sp_ptr, entries, S, ld4, n, gs, k, order, n_slots, partial, grid, st);
+        return launch_sparse_cfg<NQ, 8, 3>(cap, ng, sp_ptr, entries, S, ld4, n, gs, k, order, n_slots, partial, grid, st);
+    return long_rows ? launch_sparse_cfg<NQ, 8, 2>(cap, ng, sp_ptr, entries, S, ld4, n, gs, k, order, n_slots, partial, grid, st)
+                     : launch_sparse_cfg<NQ, 2, 8>(cap, ng, sp_ptr, entries, S, ld4, n, gs, k, order, n_slots, partial, grid, st);
 }
 
 }  // namespace laris
@@ -609,10 +610,10 @@ using namespace laris;
 extern "C" int32_t laris_spatial_stats_sparse_max_ld(void) { return (int32_t)((kSparseSmemMax - 2 * kSpCells * 128) / (4 * (2 * kSpCells + 2)) / 4 * 4); }
 
 extern "C" int laris_scores_pack(const float* S, int64_t ldS, int64_t n, int32_t P, const int64_t* sp_ptr, int64_t* entries,
-                                 void* stream) {
+                                 int64_t capacity, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     LARIS_CHECK_ARG(S && sp_ptr && entries, "laris_scores_pack: null pointer");
-    LARIS_CHECK_ARG(n > 0 && P >= 1 && ldS >= P, "laris_scores_pack: need n > 0 and ldS >= P >= 1");
+    LARIS_CHECK_ARG(n > 0 && P >= 1 && ldS >= P && capacity >= 0, "laris_scores_pack: need n > 0, ldS >= P >= 1, capacity >= 0");
     LARIS_CHECK_ARG(P <= 65536 * 32, "laris_scores_pack: P too large");
     const int T = (P + 31) / 32;
     const size_t smem = (size_t)kPackWarps * T * 32 * sizeof(uint16_t);
@@ -626,7 +627,7 @@ extern "C" int laris_scores_pack(const float* S, int64_t ldS, int64_t n, int32_t
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)sms * per_sm;
     if (grid > ceil_div(n, kPackWarps)) grid = ceil_div(n, kPackWarps);
-    scores_pack_kernel<<<(unsigned)grid, kPackWarps * 32, smem, st>>>(S, ldS, n, P, sp_ptr, reinterpret_cast<int2*>(entries));
+    scores_pack_kernel<<<(unsigned)grid, kPackWarps * 32, smem, st>>>(S, ldS, n, P, sp_ptr, reinterpret_cast<int2*>(entries), capacity);
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
 }
@@ -672,10 +673,10 @@ extern "C" int laris_spatial_stats_sparse(const float* S, int64_t ldS, int64_t n
         gs.obs_idx = idx; gs.obs_w = w; gs.null_idx = null_idx; gs.null_w = null_w;
         gs.nk = nk; gs.slot0 = s0; gs.has_obs = idx ? 1 : 0;
         int rc;
-        if (nq == 1) rc = launch_sparse<1>(long_rows, ng, sp_ptr, ent, S, ld4, n, gs, k, order, n_slots, partial.p, (int)grid, st);
-        else if (nq == 2) rc = launch_sparse<2>(long_rows, ng, sp_ptr, ent, S, ld4, n, gs, k, order, n_slots, partial.p, (int)grid, st);
-        else if (nq == 3) rc = launch_sparse<3>(long_rows, ng, sp_ptr, ent, S, ld4, n, gs, k, order, n_slots, partial.p, (int)grid, st);
-        else rc = launch_sparse<4>(long_rows, ng, sp_ptr, ent, S, ld4, n, gs, k, order, n_slots, partial.p, (int)grid, st);
+        if (nq == 1) rc = launch_sparse<1>(n_entries, long_rows, ng, sp_ptr, ent, S, ld4, n, gs, k, order, n_slots, partial.p, (int)grid, st);
+        else if (nq == 2) rc = launch_sparse<2>(n_entries, long_rows, ng, sp_ptr, ent, S, ld4, n, gs, k, order, n_slots, partial.p, (int)grid, st);
+        else if (nq == 3) rc = launch_sparse<3>(n_entries, long_rows, ng, sp_ptr, ent, S, ld4, n, gs, k, order, n_slots, partial.p, (int)grid, st);
+        else rc = launch_sparse<4>(n_entries, long_rows, ng, sp_ptr, ent, S, ld4, n, gs, k, order, n_slots, partial.p, (int)grid, st);
         if (rc) return rc;
     }
     sparse_stats_reduce_kernel<<<(unsigned)ceil_div((int64_t)n_slots * 5 * P, 256), 256, 0, st>>>(partial.p, (int)grid, n_slots,

@@ -371,10 +371,18 @@ def sparse_stats_pays(n, P, k, n_obs, n_null, n_entries):
     return k <= 32 and sparse < 0.9 * dense
 
 
-def packed_scores(sm: "ScoreMatrix", k, n_obs, n_null):
+_ENTRY_HINT: dict = {}            # (n, P) -> packed entries of the last score matrix of that shape
+
+
+def packed_scores(sm: "ScoreMatrix", k, n_obs, n_null, speculative=False):
     """(sp_ptr, entries) - the packed rows of S for the sparse K4 pass - or None when the dense passes are expected to be
     faster (``sparse_stats_pays``) or S is too wide for the pass.  LARIS_B200_K4_SPARSE=0 / 1 forces the dense / the
-    packed pass (A/B runs)."""
+    packed pass (A/B runs).
+
+    The entry array is sized by the number of packed entries, a device-side result.  ``speculative``: when a score matrix
+    of this shape was packed before, size the array (and take the decision) from THAT count plus 6 % instead of waiting
+    for this one - the host then never blocks between the scoring kernels and the statistics pass; the caller must call
+    ``packed_ok`` once the statistics are on the host and redo them if it says no (rows beyond the array were skipped)."""
     mode = os.environ.get("LARIS_B200_K4_SPARSE", "auto")
     if mode == "0" or sm.S.shape[1] > K.spatial_stats_sparse_max_ld() or sm.P > 12800 or k > 64:
         return None
@@ -382,12 +390,34 @@ def packed_scores(sm: "ScoreMatrix", k, n_obs, n_null):
         return sm.cache["packed"]
     if "nnz_get" not in sm.cache:
         queue_row_pointers(sm)
-    n_entries = int(np.asarray(sm.cache["nnz_get"]()).ravel()[0])
+    hint = _ENTRY_HINT.get((sm.n, sm.P)) if speculative else None
+    if hint is None:
+        n_entries = capacity = int(np.asarray(sm.cache["nnz_get"]()).ravel()[0])
+        _ENTRY_HINT[(sm.n, sm.P)] = n_entries
+    else:
+        n_entries = hint
+        capacity = (int(hint * 1.06) + 1024) // 32 * 32
+        sm.cache["packed_check"] = capacity
     if mode != "1" and not sparse_stats_pays(sm.n, sm.P, k, n_obs, n_null, n_entries):
+        sm.cache.pop("packed_check", None)
         return None
-    packed = (sm.cache["sp_ptr"], K.scores_pack(sm.S, sm.P, sm.cache["sp_ptr"], n_entries))
+    packed = (sm.cache["sp_ptr"], K.scores_pack(sm.S, sm.P, sm.cache["sp_ptr"], capacity))
     sm.cache["packed"] = packed
     return packed
+
+
+def packed_ok(sm: "ScoreMatrix"):
+    """False if the speculatively sized entry array of ``packed_scores`` turned out too small for this score matrix
+    (its statistics are then invalid and the packed rows are dropped).  Call after a host synchronisation."""
+    capacity = sm.cache.pop("packed_check", None)
+    if capacity is None:
+        return True
+    actual = int(np.asarray(sm.cache["nnz_get"]()).ravel()[0])
+    _ENTRY_HINT[(sm.n, sm.P)] = actual
+    if actual <= capacity:
+        return True
+    sm.cache.pop("packed", None)
+    return False
 
 
 class CapturedScoring:
@@ -534,10 +564,10 @@ def null_graphs(graph: SpatialGraph, n_repeats, random_seed, rng="numpy"):
     return cols, wts, state
 
 
-def spatial_stats_all(sm: ScoreMatrix, graph: SpatialGraph, n_repeats, random_seed, rng="numpy"):
+def spatial_stats_all(sm: ScoreMatrix, graph: SpatialGraph, n_repeats, random_seed, rng="numpy", speculative=False):
     """Observed statistics and the R null repeats (K4a + K4b) as ONE device tensor [1+R, 5, P] fp64 - no host
     synchronisation; row 0 is the observed graph.  Returns (stats_d, rng_state)."""
-    packed = packed_scores(sm, graph.idx.shape[1], 1, n_repeats)
+    packed = packed_scores(sm, graph.idx.shape[1], 1, n_repeats, speculative)     # speculative: see packed_scores
     if packed is not None:                        # mostly-zero scores: all graphs in one pass over the packed rows
         cols = wts = state = None
         if n_repeats > 0:

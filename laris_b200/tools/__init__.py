@@ -161,7 +161,7 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     else:
         graph = engine.build_radius_graph(_utils._coords(lr_adata, use_rep), radius, False, sigma)
     # observed statistics + all null repeats: one device tensor [1+R, 5, P_local], one gather, one download
-    st_d, rng_state = engine.spatial_stats_all(sm, graph, n_repeats, random_seed, rng)
+    st_d, rng_state = engine.spatial_stats_all(sm, graph, n_repeats, random_seed, rng, speculative=True)
     sm.cache["stats_d"] = st_d[0]
     sm.cache["graph"] = graph                 # the cell-type step re-uses the neighbour search when it can
     # the statistics come down through a copy queued NOW (K.to_host_async), so that waiting for them below does not also
@@ -180,6 +180,16 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
                              f"Available columns: {list(adata.obs.columns)}")
         pre = _utils._celltype_prefetch(adata, lr_adata, groupby, use_rep_spatial, number_nearest_neighbors, mu_celltype,
                                         expressed_pct_celltype, remove_lowly_expressed_celltype, contract_impl, shard, radius)
+    if not engine.packed_ok(sm):
+        # the packed-row pass ran on an entry array sized from the previous matrix of this shape and this one is denser:
+        # its statistics are incomplete - redo them with the exact size (the cell-type work queued above is unaffected)
+        # (the random graphs are regenerated from random_seed: same graphs, same continued rng state)
+        st_d, rng_state = engine.spatial_stats_all(sm, graph, n_repeats, random_seed, rng)
+        sm.cache["stats_d"] = st_d[0]
+        if shard is not None:
+            stats_get = K.to_host_async(_dist.all_gather_pairs_dev(st_d, shard, axis=-1), st_d[0].contiguous())
+        else:
+            stats_get = K.to_host_async(st_d)
     if shard is not None:
         st_all, st_local = stats_get()
         st = st_all[0]

@@ -469,3 +469,33 @@ def test_sparse_statistics_cost_model():
     assert not engine.sparse_stats_pays(1_000_000, 250, 10, 1, 3, 34_000_000)
     assert not engine.sparse_stats_pays(1_000_000, 2000, 10, 1, 3, 416_000_000)
     assert not engine.sparse_stats_pays(1_000_000, 2000, 40, 1, 3, 216_000_000)
+
+
+def test_speculative_entry_array_is_validated(monkeypatch):
+    """runLARIS sizes the packed-entry array from the previous score matrix of the same shape (no host wait).  When the
+    next matrix is denser than that estimate allows, the statistics are redone with the exact size: results equal the
+    dense passes either way."""
+    import laris_b200 as la
+    from laris_b200 import engine
+    from laris_b200.synth import make_dataset
+    a, lr, c = make_dataset(1)
+    kw = dict(n_nearest_neighbors=c.k, n_repeats=c.R, n_top_lr=c.P, number_nearest_neighbors=c.k, by_celltype=False,
+              verbose=False, rng="philox")
+    monkeypatch.setenv("LARIS_B200_K4_SPARSE", "0")
+    ad0 = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=c.k)
+    ref = la.tl.runLARIS(ad0, **kw)
+    monkeypatch.setenv("LARIS_B200_K4_SPARSE", "1")
+    engine._ENTRY_HINT.clear()
+    ad1 = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=c.k)
+    first = la.tl.runLARIS(ad1, **kw)                                    # no estimate yet: exact size
+    key = (ad1.shape[0], ad1.shape[1])
+    exact = engine._ENTRY_HINT[key]
+    ad2 = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=c.k)
+    second = la.tl.runLARIS(ad2, **kw)                                   # estimate fits
+    engine._ENTRY_HINT[key] = exact // 3                                 # pretend the previous matrix was much sparser
+    ad3 = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=c.k)
+    third = la.tl.runLARIS(ad3, **kw)                                    # estimate too small -> redone
+    assert engine._ENTRY_HINT[key] == exact
+    for got in (first, second, third):
+        assert list(got.index) == list(ref.index)
+        assert np.allclose(got["score"].to_numpy(), ref["score"].to_numpy(), rtol=1e-6, atol=1e-12)

@@ -6,6 +6,7 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
 import torch
 
 import laris_b200 as la
@@ -30,19 +31,36 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
-with K.timing() as t:
-    base = torch.cuda.Event(enable_timing=True)
-    h_base = time.perf_counter()
-    base.record()
-    step()
-    end = torch.cuda.Event(enable_timing=True)
-    end.record()
-    torch.cuda.synchronize()
-    h_end = time.perf_counter()
-print(f"step: host {1e3 * (h_end - h_base):.2f} ms, device {base.elapsed_time(end):.2f} ms")
-print(f"{'stage':34s} {'host enq':>9s} {'host ret':>9s} | {'dev start':>9s} {'dev end':>9s} {'dev ms':>7s} {'idle before':>11s}")
-prev_end = 0.0
-for stage, e0, e1, h0, h1 in t.timeline:
-    d0, d1 = base.elapsed_time(e0), base.elapsed_time(e1)
-    print(f"{stage:34s} {1e3 * (h0 - h_base):9.2f} {1e3 * (h1 - h_base):9.2f} | {d0:9.2f} {d1:9.2f} {d1 - d0:7.2f} {d0 - prev_end:11.2f}")
-    prev_end = d1
+
+
+def one():
+    with K.timing() as t:
+        base = torch.cuda.Event(enable_timing=True)
+        h_base = time.perf_counter()
+        base.record()
+        step()
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        torch.cuda.synchronize()
+        h_end = time.perf_counter()
+    return t, base, end, h_base, h_end
+
+
+def show(t, base, end, h_base, h_end):
+    print(f"step: host {1e3 * (h_end - h_base):.2f} ms, device {base.elapsed_time(end):.2f} ms")
+    print(f"{'stage':34s} {'host enq':>9s} {'host ret':>9s} | {'dev start':>9s} {'dev end':>9s} {'dev ms':>7s} {'idle before':>11s}")
+    prev_end = 0.0
+    for stage, e0, e1, h0, h1 in t.timeline:
+        d0, d1 = base.elapsed_time(e0), base.elapsed_time(e1)
+        print(f"{stage:34s} {1e3 * (h0 - h_base):9.2f} {1e3 * (h1 - h_base):9.2f} | {d0:9.2f} {d1:9.2f} {d1 - d0:7.2f} {d0 - prev_end:11.2f}")
+        prev_end = d1
+
+
+# LARIS_TIMELINE_TRIES > 1: also show the slowest of that many steps (intermittent host stalls)
+tries = int(os.environ.get("LARIS_TIMELINE_TRIES", "1"))
+runs = [one() for _ in range(tries)]
+times = [r[1].elapsed_time(r[2]) for r in runs]
+show(*runs[int(np.argsort(times)[len(times) // 2])])
+if tries > 1:
+    print("\nall steps (ms):", [round(x, 2) for x in times], "\nslowest:")
+    show(*runs[int(np.argmax(times))])
