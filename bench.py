@@ -391,6 +391,8 @@ def run_ours(args):
                 lr_ad, res = host_step()
                 e2e_t.append(time.perf_counter() - t0)
             barrier()
+            if os.environ.get("BENCH_E2E_PROFILE") and rank == 0:      # diagnostic, after the timed region
+                _profile_e2e(host_step, Xh, os.environ["BENCH_E2E_PROFILE"])
             X_share = (Xh.data.nbytes + Xh.indices.nbytes) // world + Xh.indptr.nbytes
             h2d = X_share + 3 * a_h.obsm["X_spatial"].nbytes + 4 * n
             d2h = (lr_ad.X.data.nbytes + lr_ad.X.indices.nbytes + lr_ad.X.indptr.nbytes + 6 * 8 * P * c.C * c.C
@@ -484,6 +486,57 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _profile_e2e(host_step, Xh, path):
+    """BENCH_E2E_PROFILE=<file>: where the public-API call spends its time - the raw PCIe rates of this box (pinned
+    2 GB up / down), the split between the two calls, and a cProfile of one call.  Runs after the timed region."""
+    import cProfile
+    import io
+    import pstats
+    import torch
+    out = io.StringIO()
+    src = torch.from_numpy(Xh.data)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record()
+    d = src.to("cuda", non_blocking=True)
+    e[1].record()
+    back = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+    back.copy_(d, non_blocking=True)
+    e[2].record()
+    torch.cuda.synchronize()
+    gb = src.numel() * 4 / 1e9
+    out.write(f"pinned H2D {gb:.2f} GB: {e[0].elapsed_time(e[1]):.1f} ms = {gb / e[0].elapsed_time(e[1]) * 1e3:.1f} GB/s; "
+              f"D2H (fresh pinned buffer, alloc outside): {e[1].elapsed_time(e[2]):.1f} ms = "
+              f"{gb / e[1].elapsed_time(e[2]) * 1e3:.1f} GB/s\n")
+    del d, back
+    import laris_b200 as la
+    real_prep, real_run = la.tl.prepareLRInteraction, la.tl.runLARIS
+    marks = {}
+
+    def timed(name, fn):
+        def w(*a, **k):
+            t0 = time.perf_counter()
+            r = fn(*a, **k)
+            marks[name] = marks.get(name, 0.0) + time.perf_counter() - t0
+            return r
+        return w
+    la.tl.prepareLRInteraction, la.tl.runLARIS = timed("prepareLRInteraction", real_prep), timed("runLARIS", real_run)
+    try:
+        for _ in range(3):
+            host_step()
+        out.write("mean ms per call over 3: " + ", ".join(f"{k} {1e3 * v / 3:.1f}" for k, v in marks.items()) + "\n")
+    finally:
+        la.tl.prepareLRInteraction, la.tl.runLARIS = real_prep, real_run
+    pr = cProfile.Profile()
+    pr.enable()
+    host_step()
+    pr.disable()
+    pstats.Stats(pr, stream=out).sort_stats("cumulative").print_stats(70)
+    pstats.Stats(pr, stream=out).sort_stats("tottime").print_stats(45)
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, "w") as f:
+        f.write(out.getvalue())
 
 
 def engine_last_xu(la):
