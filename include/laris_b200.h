@@ -369,6 +369,22 @@ LARIS_API int laris_pvalues_from_counts(const double* table, const uint8_t* acti
 LARIS_API int laris_gather_result_rows(const double* p_tab, const double* fdr_tab, const int32_t* pair_id, int32_t Pt,
                                        int32_t P, int32_t L, double* p_rows, double* fdr_rows, double* nlog_rows,
                                        void* stream);
+/* T6a (laris/tools/_utils.py:1408-1422, :1472): the row order of the reference's long result table.  The reference
+ * melts the [pair][receiver][sender] cube (pandas melt: pair-major, receiver-major, sender fastest) and sorts it by
+ * the pre-weight score and then by the final score, both descending.  order[j] = element (pair*C + sender)*C +
+ * receiver of the [Pt][C][C] tables `inter` / `flat` at row j: the rows with a positive final score stably sorted by
+ * both keys, every other row behind them in melt order.  *exotic (device int32) is set when a final score is negative
+ * or NaN (only possible with exotic thresholds; the caller then orders on the host).  Two stable 64-bit LSD radix
+ * sorts (cub::DeviceRadixSort); Pt*C*C < 2^31. */
+LARIS_API int laris_result_row_order(const double* inter, const double* flat, int32_t Pt, int32_t C, int32_t* order,
+                                     int32_t* exotic, void* stream);
+/* T6b (:1408-1420, :1660-1688): the result table's numeric columns and per-row codes in table order, one pass:
+ * score_o[j] = flat[order[j]], likewise p / fdr / nlog / extra (null sources are skipped), pair_o / send_o / recv_o =
+ * the row's position in the ranked pair list, sender and receiver category codes. */
+LARIS_API int laris_result_rows_gather(const int32_t* order, int64_t total, int32_t C, const double* flat,
+                                       const double* p_rows, const double* fdr_rows, const double* nlog_rows,
+                                       const double* extra, double* score_o, double* p_o, double* fdr_o, double* nlog_o,
+                                       double* extra_o, int32_t* pair_o, int32_t* send_o, int32_t* recv_o, void* stream);
 
 /* ------------------------------------------------- K4a + K4b batched ----
  * Observed statistics and n_repeats random-graph repeats of the same score matrix in one call

@@ -590,6 +590,36 @@ def gather_result_rows(p_tab, fdr_tab, pair_id):
     return outs
 
 
+@_staged("tables")
+def result_row_order(inter, flat, C):
+    """T6a: (order int32 [Pt*C*C], exotic int32 [1]) - the reference's table row order, sorted on the device."""
+    total = flat.numel()
+    Pt = total // (C * C)
+    order = torch.empty(total, dtype=torch.int32, device=flat.device)
+    exotic = torch.empty(1, dtype=torch.int32, device=flat.device)
+    check(lib.laris_result_row_order(_ptr(inter, torch.float64), _ptr(flat, torch.float64), Pt, C, _ptr(order),
+                                     _ptr(exotic), _stream()), "laris_result_row_order")
+    return order, exotic
+
+
+@_staged("tables")
+def result_rows_gather(order, C, flat, p_rows=None, fdr_rows=None, nlog_rows=None, extra=None):
+    """T6b: the numeric columns of the result table and the per-row (pair, sender, receiver) codes in table order.
+    Returns (score, p, fdr, nlog, extra, pair, sender, receiver); columns without a source are None."""
+    total = order.numel()
+    dev = order.device
+    f64 = lambda src: None if src is None else torch.empty(total, dtype=torch.float64, device=dev)   # noqa: E731
+    score = torch.empty(total, dtype=torch.float64, device=dev)
+    outs = [f64(p_rows), f64(fdr_rows), f64(nlog_rows), f64(extra)]
+    codes = [torch.empty(total, dtype=torch.int32, device=dev) for _ in range(3)]
+    check(lib.laris_result_rows_gather(_ptr(order, torch.int32), total, C, _ptr(flat, torch.float64),
+                                       _ptr(p_rows, torch.float64), _ptr(fdr_rows, torch.float64),
+                                       _ptr(nlog_rows, torch.float64), _ptr(extra, torch.float64), _ptr(score),
+                                       *[_ptr(o) for o in outs], *[_ptr(c) for c in codes], _stream()),
+          "laris_result_rows_gather")
+    return (score, *outs, *codes)
+
+
 # ------------------------------------------- label-permutation null (extension) ----
 @_staged("label null: permute")
 def permute_labels(labels, permutation, seed):

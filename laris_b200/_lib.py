@@ -69,6 +69,8 @@ SIGNATURES = {
     "laris_finalize_scores": [_p, _p, _p, _p, _i, _i, _i, _d, _p, _p, _p, _p],
     "laris_pvalues_from_counts": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _d, _p, _p, _p, _p],
     "laris_gather_result_rows": [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p],
+    "laris_result_row_order": [_p, _p, _i, _i, _p, _p, _p],
+    "laris_result_rows_gather": [_p, _i64, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "laris_row_qc": [_p, _i64, _i64, _i, _p, _i, _p, _p, _p, _p],
     "laris_rowwise_cosine": [_p, _p, _i64, _i64, _i64, _i64, _p, _p],
     "laris_pairwise_row_multiply": [_p, _i, _i64, _p, _p],

@@ -54,7 +54,9 @@ class StringTaker:
         if self.dictionary is not None:
             try:
                 pa = self._pa
-                arr = pa.DictionaryArray.from_arrays(pa.array(codes.astype(np.int64)), self.dictionary).dictionary_decode()
+                if codes.dtype not in (np.dtype(np.int32), np.dtype(np.int64)):
+                    codes = codes.astype(np.int64)
+                arr = pa.DictionaryArray.from_arrays(pa.array(codes), self.dictionary).dictionary_decode()
                 return pd.array(arr, dtype=self.dtype)
             except Exception:    # noqa: BLE001
                 pass
@@ -63,6 +65,25 @@ class StringTaker:
 
 def take_strings(values, codes):
     return StringTaker(values).take(codes)
+
+
+_POOL = []
+
+
+def take_many(jobs):
+    """``[taker.take(codes) for taker, codes in jobs]`` with the takes running side by side: decoding an Arrow dictionary
+    releases the GIL, so the five string columns of the 3.2 M-row cell-type table are built in the time of one."""
+    import os
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    if cores < 2 or len(jobs) < 2 or max(len(c) for _, c in jobs) < 200_000:
+        return [t.take(c) for t, c in jobs]
+    if not _POOL:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL.append(ThreadPoolExecutor(max_workers=min(8, cores), thread_name_prefix="laris-take"))
+    return [f.result() for f in [_POOL[0].submit(t.take, c) for t, c in jobs]]
 
 
 _REAL_COSG = [False, None]          # [looked up, module]: a failing ``import cosg`` walks sys.path every time it is tried

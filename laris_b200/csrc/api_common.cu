@@ -93,53 +93,89 @@ __device__ __forceinline__ uint32_t order_key(float v) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-// warp per row: the row is staged in shared memory; total / non-zero count in one pass, then for every N of the list
-// the N-th largest value by a 32-step radix select on the ordered keys, and the sum of the N largest from it
+// warp per row.  The row is read once (128-bit loads, two in flight per lane); its NON-ZERO values are compacted into
+// shared memory on the way (ballot + prefix popcount - the order inside the list is irrelevant), together with the total,
+// the non-zero count and the sum / count of the positive values.  The sum of the N largest values then needs no search at
+// all when the positives number at most N and the zeros fill the rest (the common case for mostly-zero score rows);
+// otherwise the N-th largest value comes from a 32-step radix select on the ordered keys of the LIST - the P - m zeros
+// join every count at the key of 0.0f - i.e. ~m/32 instead of P/32 shared loads per step.
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 row_qc_kernel(const float* __restrict__ S, int64_t ldS, int64_t n, int P, TopList tops, double* __restrict__ total,
               int64_t* __restrict__ nnz, double* __restrict__ top_sum) {
     extern __shared__ float qc_rows[];
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr uint32_t KEY0 = 0x80000000u;                          // order_key(0.0f)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* row = qc_rows + (size_t)warp * P;
+    const unsigned lt = (1u << lane) - 1u;
+    float* list = qc_rows + (size_t)warp * P;
     const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; i < n; i += nwarps) {
-        double s = 0.0;
-        int c = 0;
-        for (int p = lane; p < P; p += 32) {
-            const float v = S[i * ldS + p];
-            row[p] = v;
-            s += (double)v;
-            c += v != 0.f;
+        const float* row = S + i * ldS;
+        double s = 0.0, sp = 0.0;
+        int m = 0, cp = 0;
+        auto take = [&](float v) {                                  // warp-uniform call
+            const bool nz = v != 0.f;
+            const unsigned mask = __ballot_sync(FULL, nz);
+            if (nz) {
+                list[m + __popc(mask & lt)] = v;
+                s += (double)v;
+                if (v > 0.f) { sp += (double)v; ++cp; }
+            }
+            m += __popc(mask);
+        };
+        if (VEC) {
+            const int nq = (P + 3) >> 2;                            // ldS % 4 == 0 and ldS >= P: quads stay inside the row
+            const float4* rq = reinterpret_cast<const float4*>(row);
+            for (int q0 = 0; q0 < nq; q0 += 64) {
+                const int qa = q0 + lane, qb = q0 + 32 + lane;
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                if (qa < nq) a = ld_stream_f4(rq + qa);
+                if (qb < nq) b = ld_stream_f4(rq + qb);
+                const int pa = 4 * qa, pb = 4 * qb;                 // columns >= P do not belong to the table
+                take(pa + 0 < P ? a.x : 0.f); take(pa + 1 < P ? a.y : 0.f);
+                take(pa + 2 < P ? a.z : 0.f); take(pa + 3 < P ? a.w : 0.f);
+                take(pb + 0 < P ? b.x : 0.f); take(pb + 1 < P ? b.y : 0.f);
+                take(pb + 2 < P ? b.z : 0.f); take(pb + 3 < P ? b.w : 0.f);
+            }
+        } else {
+            for (int p0 = 0; p0 < P; p0 += 32) take(p0 + lane < P ? row[p0 + lane] : 0.f);
         }
         s = warp_sum(s);
-        c = __reduce_add_sync(FULL, c);
+        sp = warp_sum(sp);
+        cp = __reduce_add_sync(FULL, cp);
         __syncwarp();
-        if (lane == 0) { total[i] = s; nnz[i] = c; }
+        if (lane == 0) { total[i] = s; nnz[i] = m; }
+        const int z = P - m;                                        // zeros of the row
         for (int t = 0; t < tops.count; ++t) {
             const int N = tops.n[t];
-            double ts = s;
-            if (N < P) {
+            double ts;
+            if (N >= P) {
+                ts = s;
+            } else if (cp <= N && N <= cp + z) {
+                ts = sp;                                            // every positive value, then zeros
+            } else {
                 uint32_t key = 0u;                                  // largest key with #{key(v) >= key} >= N
                 for (int bit = 31; bit >= 0; --bit) {
                     const uint32_t cand = key | (1u << bit);
                     int cnt = 0;
-                    for (int p = lane; p < P; p += 32) cnt += order_key(row[p]) >= cand;
-                    if (__reduce_add_sync(FULL, cnt) >= N) key = cand;
+                    for (int q = lane; q < m; q += 32) cnt += order_key(list[q]) >= cand;
+                    if (__reduce_add_sync(FULL, cnt) + (KEY0 >= cand ? z : 0) >= N) key = cand;
                 }
                 double sg = 0.0;
                 int cg = 0;
                 float vN = 0.f;
-                for (int p = lane; p < P; p += 32) {
-                    const float v = row[p];
+                bool found = false;
+                for (int q = lane; q < m; q += 32) {
+                    const float v = list[q];
                     const uint32_t kv = order_key(v);
                     if (kv > key) { sg += (double)v; ++cg; }
-                    if (kv == key) vN = v;
+                    if (kv == key) { vN = v; found = true; }
                 }
                 sg = warp_sum(sg);
-                cg = __reduce_add_sync(FULL, cg);
-                const unsigned has = __ballot_sync(FULL, order_key(vN) == key);
-                vN = __shfl_sync(FULL, vN, has ? __ffs(has) - 1 : 0);
+                cg = __reduce_add_sync(FULL, cg) + (KEY0 > key ? z : 0);
+                const unsigned has = __ballot_sync(FULL, found);
+                vN = has ? __shfl_sync(FULL, vN, __ffs(has) - 1) : 0.f;     // no list entry at the key: the N-th is a zero
                 ts = sg + (double)(N - cg) * (double)vN;
             }
             if (lane == 0) top_sum[i * tops.count + t] = ts;
@@ -161,10 +197,15 @@ extern "C" int laris_row_qc(const float* S, int64_t ldS, int64_t n, int32_t P, c
     for (int t = 0; t < 4; ++t) tl.n[t] = t < n_top ? top_n[t] : 0;          // top_n is HOST memory
     for (int t = 0; t < n_top; ++t) LARIS_CHECK_ARG(tl.n[t] >= 1, "laris_row_qc: top sizes must be >= 1");
     const size_t smem = (size_t)P * 8 * sizeof(float);
-    LARIS_CUDA(cudaFuncSetAttribute(row_qc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t want = ceil_div(n, 8);
     const int64_t grid = want < (int64_t)kNumSMs * 4 ? want : (int64_t)kNumSMs * 4;
-    row_qc_kernel<<<(unsigned)grid, 256, smem, st>>>(S, ldS, n, P, tl, total, nnz, top_sum);
+    if (ldS % 4 == 0 && (reinterpret_cast<uintptr_t>(S) & 15) == 0) {
+        LARIS_CUDA(cudaFuncSetAttribute(row_qc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        row_qc_kernel<true><<<(unsigned)grid, 256, smem, st>>>(S, ldS, n, P, tl, total, nnz, top_sum);
+    } else {
+        LARIS_CUDA(cudaFuncSetAttribute(row_qc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        row_qc_kernel<false><<<(unsigned)grid, 256, smem, st>>>(S, ldS, n, P, tl, total, nnz, top_sum);
+    }
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
 }

@@ -479,26 +479,93 @@ def device_fingerprint_async(data_d):
     return result
 
 
+class PendingCSR(sp.csr_matrix):
+    """A scipy CSR matrix whose three arrays may still be on their way from the device.
+
+    ``prepareLRInteraction`` returns the score matrix as soon as the device->host copies are QUEUED (on a copy stream of
+    their own): the arrays already exist - views of page-locked buffers - and the first access to ``data`` / ``indices`` /
+    ``indptr`` (any scipy operation, ``nnz``, a copy, pickling) waits for the copies' event, once.  A following
+    ``runLARIS`` works on the device-resident scores and never touches them, so the 1.6 GB download of a 1e6-cell
+    matrix overlaps its kernels instead of preceding them.  Copies, slices and pickles are ordinary matrices."""
+
+    def _laris_join(self):
+        wait = self.__dict__.pop("_laris_wait", None)
+        if wait is not None:
+            wait(self)
+
+    def _laris_pending(self):
+        """True while nobody has looked at the arrays (they then still equal the device copy)."""
+        return "_laris_wait" in self.__dict__
+
+    def __reduce__(self):
+        return (sp.csr_matrix, ((self.data, self.indices, self.indptr), self.shape))
+
+
+def _pending_array(name):
+    slot = "_laris_" + name
+
+    def get(self):
+        self._laris_join()
+        return self.__dict__[slot]
+
+    def put(self, value):
+        self.__dict__[slot] = value
+    return property(get, put)
+
+
+for _name in ("data", "indices", "indptr"):
+    setattr(PendingCSR, _name, _pending_array(_name))
+
+_D2H_STREAMS: dict = {}
+
+
 def scores_to_csr_async(sm: ScoreMatrix, dtype=np.float32):
-    """Start the device CSR compaction and the device->host copies of the result; returns ``finish()`` which waits
-    for the copies and gives (scipy matrix, content fingerprint).  Host work done between the two calls overlaps the
-    transfer."""
+    """Start the device CSR compaction and the device->host copies of the result (on a dedicated copy stream, so that
+    kernels queued afterwards on the caller's stream overlap them).  Returns ``finish(wait=True)`` giving (scipy matrix,
+    content fingerprint): ``wait=False`` returns a ``PendingCSR`` immediately, whose arrays are joined on first access."""
     if sm.row_nnz is None:
         raise ValueError("score matrix has no row counts")
-    parts = K.csr_compact(sm.S, sm.P, sm.row_nnz)
+    indptr_d, indices_d, data_d = K.csr_compact(sm.S, sm.P, sm.row_nnz)
+    nnz = int(data_d.numel())
+    if nnz < 2 ** 31 - 1:                            # scipy's own choice of index dtype for this size, made on the device
+        indptr_d = indptr_d.to(torch.int32)
+    else:
+        indices_d = indices_d.to(torch.int64)
+    parts = (indptr_d, indices_d, data_d)
+    fp = device_fingerprint_async(data_d)
+    cur = torch.cuda.current_stream()
+    dev = torch.cuda.current_device()
+    side = _D2H_STREAMS.get(dev)
+    if side is None:
+        side = _D2H_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    side.wait_stream(cur)
     host = []
-    for t in parts:
-        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        h.copy_(t, non_blocking=True)
-        host.append(h)
-    fp = device_fingerprint_async(parts[2])
-    done = torch.cuda.Event()
-    done.record()
+    with torch.cuda.stream(side):
+        for t in parts:
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            t.record_stream(side)
+            host.append(h)
+        done = torch.cuda.Event()
+        done.record(side)
+    np_dtype = np.dtype(dtype)
 
-    def finish():
+    def join(X):
         done.synchronize()
-        indptr, indices, data = (h.numpy() for h in host)
-        return _assemble_csr(sm, indptr, indices, data, dtype), fp()
+        if np_dtype != np.float32:
+            X.data = X.__dict__["_laris_data"].astype(np_dtype)
+
+    def finish(wait=True):
+        # built without scipy's O(nnz) validation passes (check_format / index-dtype scans): the device kernel guarantees
+        # a canonical CSR (sorted, duplicate-free, no explicit zeros)
+        X = PendingCSR((sm.n, sm.P), dtype=np_dtype)
+        X.indptr, X.indices, X.data = (h.numpy() for h in host)
+        X.has_sorted_indices = True
+        X.has_canonical_format = True
+        X.__dict__["_laris_wait"] = join
+        if wait:
+            X._laris_join()
+        return X, fp
     return finish
 
 

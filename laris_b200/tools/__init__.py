@@ -99,7 +99,9 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     # device-resident coordinates are shared, not cloned (nothing on this path writes to them)
     obsm = {k: (v if torch.is_tensor(v) else np.array(v, copy=True)) for k, v in adata.obsm.items()}
     if to_host:
-        X, score_fp = finish()
+        # the matrix is handed over while its arrays are still coming down (engine.PendingCSR): whoever reads them first
+        # waits for the copies; a following runLARIS does not, it scores the device-resident copy
+        X, score_fp = finish(wait=False)
         lr_adata = make_anndata(X, obs=obs, var=var, obsm=obsm)
         _utils._remember_scores(lr_adata.X, sm, score_fp)
     else:
@@ -210,8 +212,9 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
         LRSS_Target=gsp[own], LRSS_Random=random_gsp[own], LR_SpatialSpecificity=gsp_score[own],
         n_cells_by_counts=nnz_own.astype(np.int64), mean_counts=sum_own / n, pct_dropout_by_counts=100.0 * (1.0 - nnz_own / n),
         total_counts=sum_own, log1p_mean_counts=np.log1p(sum_own / n), log1p_total_counts=np.log1p(sum_own))
-    if output == "frames":
-        _utils._write_obs_qc(lr_adata, sm, shard)
+    # the per-cell QC columns: kernel and download queued here, written to obs just before returning (the host does not
+    # wait for the device at this point)
+    qc_finish = _utils._write_obs_qc_async(lr_adata, sm, shard) if output == "frames" else (lambda: None)
 
     if pre is not None and calculate_pvalues:
         # the background sets only need the column moments that just arrived: queue their search now, K6 finds them
@@ -237,6 +240,7 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     if not by_celltype:
         if rng_state is not None:
             _rng_compat.sync_global(rng_state)
+        qc_finish()
         return laris_lr
 
     # ---- step 2: cell-type table (reference :536-572) ----
@@ -253,6 +257,7 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
         use_conditional_pvalue=use_conditional_pvalue, rng=rng, random_seed=random_seed, rng_state=rng_state,
         verbose=verbose, contract_impl=contract_impl, shard=shard, radius=radius, output=output,
         label_permutations=label_permutations, _pre=pre)
+    qc_finish()
     if output == "frames":
         _log(verbose, f"\nResults: {len(laris_lr)} LR pairs, {len(celltype_results):,} cell type combinations")
     return laris_lr, celltype_results

@@ -101,7 +101,11 @@ def _scores_of(lr_adata) -> engine.ScoreMatrix:
         return X.sm
     hit = _SCORE_CACHE.get(id(X))
     if hit is not None and hit[0]() is X and hit[1].S.shape[0] == X.shape[0] and hit[1].P == X.shape[1]:
-        if hit[2] is None or _fingerprint_host(X) == hit[2]:
+        pending = getattr(X, "_laris_pending", None)
+        if pending is not None and pending():              # arrays still in flight, never looked at: they equal the device copy
+            return hit[1]
+        want = hit[2]() if callable(hit[2]) else hit[2]
+        if want is None or _fingerprint_host(X) == want:
             return hit[1]
         _SCORE_CACHE.pop(id(X), None)                      # edited in place: score the current values
     if not sp.issparse(X):
@@ -120,27 +124,36 @@ def _log(verbose, *a):
         print(*a)
 
 
-def _write_obs_qc(lr_adata, sm, shard=None, percent_top=(50, 100, 200, 500)):
+def _write_obs_qc_async(lr_adata, sm, shard=None, percent_top=(50, 100, 200, 500)):
     """The per-cell columns scanpy.pp.calculate_qc_metrics(lr_adata, inplace=True) adds to ``obs``
     (reference laris/tools/__init__.py:493-496), computed on the device-resident scores:
     n_genes_by_counts, total_counts, their log1p, and pct_counts_in_top_N_genes for every N < n_vars
     (scanpy raises for N > n_vars; those columns are simply not written).  In a sharded run a rank only holds
-    a block of pairs: counts and totals are all-reduced, the top-N percentages are omitted."""
+    a block of pairs: counts and totals are all-reduced, the top-N percentages are omitted.
+    The kernel and the download are queued now; ``finish()`` (returned) waits for them and writes the columns, so the
+    caller can put it behind other host work."""
     P = sm.P
     tops = [] if shard is not None else [N for N in percent_top if N < P]
-    total, nnz, top = K.row_qc(sm.S, P, tops)
-    total, nnz, top = total.cpu().numpy(), nnz.cpu().numpy(), top.cpu().numpy()
-    if shard is not None:
-        both = _dist.all_reduce_sum(np.stack([total, nnz.astype(np.float64)]))
-        total, nnz = both[0], both[1].astype(np.int64)
-    obs = lr_adata.obs
-    obs["n_genes_by_counts"] = nnz
-    obs["log1p_n_genes_by_counts"] = np.log1p(nnz)
-    obs["total_counts"] = total.astype(np.float32)
-    obs["log1p_total_counts"] = np.log1p(total).astype(np.float32)
-    with np.errstate(invalid="ignore", divide="ignore"):
-        for j, N in enumerate(tops):
-            obs[f"pct_counts_in_top_{N}_genes"] = 100.0 * top[:, j] / total
+    get = K.to_host_async(*K.row_qc(sm.S, P, tops))
+
+    def finish():
+        total, nnz, top = get()
+        if shard is not None:
+            both = _dist.all_reduce_sum(np.stack([total, nnz.astype(np.float64)]))
+            total, nnz = both[0], both[1].astype(np.int64)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            cols = {"n_genes_by_counts": nnz, "log1p_n_genes_by_counts": np.log1p(nnz),
+                    "total_counts": total.astype(np.float32), "log1p_total_counts": np.log1p(total).astype(np.float32)}
+            for j, N in enumerate(tops):
+                cols[f"pct_counts_in_top_{N}_genes"] = 100.0 * top[:, j] / total
+        obs = lr_adata.obs
+        for name, col in cols.items():
+            obs[name] = col
+    return finish
+
+
+def _write_obs_qc(lr_adata, sm, shard=None, percent_top=(50, 100, 200, 500)):
+    _write_obs_qc_async(lr_adata, sm, shard, percent_top)()
 
 
 # ---------------------------------------------------------------------------
@@ -565,6 +578,8 @@ class _LazyRankedGroups(dict):
             return
         raw, lr_names, pair_names, return_by_group, delimiter = self._pending
         self._pending = None
+        if callable(raw):                     # still on its way from the device (K.to_host_async)
+            raw = raw()
         frame, order = cosg_compat.ranked_frame(lr_names, raw, pair_names, delimiter)
         if return_by_group:
             dict.__setitem__(self, "COSG", frame)
@@ -750,6 +765,25 @@ def _numpy_mode_counts(table_d, bg_d, active_d, order_rows, group_of, pair_of, c
     return ge, nz, both
 
 
+def _rows_in_table_order(host_inter, host_flat, npair, C):
+    """Row order of the reference's result: melt order (pair-major, receiver-major, sender fastest), stably
+    sorted by the pre-weight score and then by the final score, both descending (:1422, :1472).  The reference's own
+    sorts are unstable (pandas quicksort), so the order among EQUAL final scores is not defined by it; here the
+    thresholded-away rows (score exactly 0, the bulk of the table) keep melt order and only the rows with a positive
+    score go through the two stable sorts.  Host mirror of ``laris_result_row_order`` (T6a), used for scores the device
+    pass does not order (negative / NaN) and as its test oracle."""
+    L = C * C
+    melt = np.arange(npair * L).reshape(npair, C, C).transpose(0, 2, 1).reshape(-1)     # [pair, r, s] -> flat [pair, s, r]
+    fm = host_flat.reshape(-1)[melt]
+    if (fm < 0).any() or np.isnan(fm).any():             # negative / NaN scores can only occur with exotic thresholds
+        o1 = melt[np.argsort(-host_inter.reshape(-1)[melt], kind="stable")]
+        return o1[np.argsort(-host_flat.reshape(-1)[o1], kind="stable")]
+    pos = melt[fm > 0]
+    o1 = pos[np.argsort(-host_inter.reshape(-1)[pos], kind="stable")]
+    o2 = o1[np.argsort(-host_flat.reshape(-1)[o1], kind="stable")]
+    return np.concatenate([o2, melt[fm == 0]])
+
+
 def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str = "CellTypes",
                                        use_rep_spatial: str = "X_spatial", number_nearest_neighbors: int = 10,
                                        mu: float = 100, expressed_pct: float = 0.1, remove_lowly_expressed: bool = True,
@@ -849,24 +883,22 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
     raw_d, pair_names = raw_d0, pair_names0
     ctc_names = lr_names
     if output == "frames":
-        _store_neighborhood_uns(lr_adata, "cosg_lr", groupby, mu, raw_d.cpu().numpy(), ctc_names, pair_names, True, "@@")
+        # uns['cosg_lr'] is ranked lazily; its table comes down through a copy queued now and is only awaited on access
+        _store_neighborhood_uns(lr_adata, "cosg_lr", groupby, mu, K.to_host_async(raw_d), ctc_names, pair_names, True, "@@")
     flat_d, table_d, active_d = K.finalize_scores(inter_d, rescale_d, ctc_d, pair_id_d, P, score_threshold)
+    # T6a: the reference's row order, sorted on the device while the p-values are computed (the long table and the
+    # reference-stream draws need it)
+    order_d = exotic_d = None
+    if npair * L < 2 ** 31 - 1 and (output == "frames" or (calculate_pvalues and rng == "numpy")):
+        order_d, exotic_d = K.result_row_order(inter_d, flat_d, C)
 
-    def rows_in_table_order(host_inter, host_flat):
-        """Row order of the reference's result: melt order (pair-major, receiver-major, sender fastest), stably
-        sorted by the pre-weight score and then by the final score, both descending (:1422, :1472).  The reference's own
-        sorts are unstable (pandas quicksort), so the order among EQUAL final scores is not defined by it; here the
-        thresholded-away rows (score exactly 0, the bulk of the table) keep melt order and only the rows with a positive
-        score go through the two stable sorts."""
-        melt = np.arange(npair * L).reshape(npair, C, C).transpose(0, 2, 1).reshape(-1)     # [pair, r, s] -> flat [pair, s, r]
-        fm = host_flat.reshape(-1)[melt]
-        if (fm < 0).any() or np.isnan(fm).any():             # negative / NaN scores can only occur with exotic thresholds
-            o1 = melt[np.argsort(-host_inter.reshape(-1)[melt], kind="stable")]
-            return o1[np.argsort(-host_flat.reshape(-1)[o1], kind="stable")]
-        pos = melt[fm > 0]
-        o1 = pos[np.argsort(-host_inter.reshape(-1)[pos], kind="stable")]
-        o2 = o1[np.argsort(-host_flat.reshape(-1)[o1], kind="stable")]
-        return np.concatenate([o2, melt[fm == 0]])
+    def host_order():
+        """The row order on the host: the device's (T6a), or the numpy mirror above for scores it does not order."""
+        if order_d is not None:
+            got, exotic = K.to_host(order_d, exotic_d)
+            if not exotic[0]:
+                return got.astype(np.int64)
+        return _rows_in_table_order(inter_d.cpu().numpy(), flat_d.cpu().numpy(), npair, C)
 
     result = {"pair_id": pair_id, "C": C, "cats": cats_arr, "ligand": lig, "receptor": rec, "interaction_name": inter_names,
               "interaction_score": flat_d, "ctc_raw": raw_d}
@@ -894,7 +926,7 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
             if nb > 256:
                 raise ValueError(f"rng='numpy' stores draws as uint8: n_neighbors_permutation must be <= 256 (got {nb})")
             rs = rng_state if rng_state is not None else np.random.RandomState(random_seed)
-            order_rows = rows_in_table_order(inter_d.cpu().numpy(), flat_d.cpu().numpy())
+            order_rows = host_order()
             group_of = np.tile(np.arange(L), npair)
             pair_of = np.repeat(pair_id, L)
             ge, nz, both = _numpy_mode_counts(table_d, bg_d, active_d, order_rows, group_of, pair_of, cats, C, P,
@@ -933,29 +965,38 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
         return result
 
     # ---- the reference's long table, rows by descending score ----
-    flat = flat_d.cpu().numpy()
-    if order_rows is None:
-        order_rows = rows_in_table_order(inter_d.cpu().numpy(), flat)
-    row_pair, rem = np.divmod(order_rows, L)
-    row_send, row_recv = np.divmod(rem, C)
+    host = None
+    if order_d is not None:
+        # T6b: numeric columns and (pair, sender, receiver) codes gathered in table order on the device, one download
+        cols_d = K.result_rows_gather(order_d, C, flat_d, p_rows, fdr_rows, nlog_rows, label_rows)
+        present = [c is not None for c in cols_d]
+        got = iter(K.to_host(exotic_d, *[c for c in cols_d if c is not None]))
+        if not next(got)[0]:
+            host = [next(got) if here else None for here in present]
+    if host is None:                            # scores the device pass does not order (negative / NaN), or > 2^31 rows
+        flat = flat_d.cpu().numpy()
+        if order_rows is None:
+            order_rows = _rows_in_table_order(inter_d.cpu().numpy(), flat, npair, C)
+        row_pair, rem = np.divmod(order_rows, L)
+        row_send, row_recv = np.divmod(rem, C)
+        take = lambda t: None if t is None else t.cpu().numpy().reshape(-1)[order_rows]          # noqa: E731
+        host = [flat.reshape(-1)[order_rows], take(p_rows), take(fdr_rows), take(nlog_rows), take(label_rows),
+                row_pair, row_send, row_recv]
+    score, p_col, fdr_col, nlog_col, label_col, row_pair, row_send, row_recv = host
     cat_taker = cosg_compat.StringTaker(cats_arr)
-    res = pd.DataFrame({
-        "sender": cat_taker.take(row_send), "receiver": cat_taker.take(row_recv),
-        "interaction_score": flat.reshape(-1)[order_rows],
-        "ligand": _take_strings(lig, row_pair), "receptor": _take_strings(rec, row_pair),
-        "interaction_name": _take_strings(inter_names, row_pair)})
-    if not calculate_pvalues:
-        res["p_value"] = np.nan
-        res["p_value_fdr"] = np.nan
-        res["nlog10_p_value_fdr"] = np.nan
-    else:
-        host = K.to_host(p_rows, fdr_rows, nlog_rows)
-        res["p_value"] = host[0].reshape(-1)[order_rows]
-        res["p_value_fdr"] = host[1].reshape(-1)[order_rows]
-        res["nlog10_p_value_fdr"] = host[2].reshape(-1)[order_rows]
-    if label_rows is not None:
-        res["p_value_label_null"] = label_rows.cpu().numpy().reshape(-1)[order_rows]
-    return res
+    sender, receiver, lig_col, rec_col, name_col = cosg_compat.take_many([
+        (cat_taker, row_send), (cat_taker, row_recv), (cosg_compat.StringTaker(lig), row_pair),
+        (cosg_compat.StringTaker(rec), row_pair), (cosg_compat.StringTaker(inter_names), row_pair)])
+    nan_col = None if calculate_pvalues else np.full(len(score), np.nan)
+    data = {"sender": sender, "receiver": receiver, "interaction_score": score, "ligand": lig_col, "receptor": rec_col,
+            "interaction_name": name_col,
+            "p_value": p_col if calculate_pvalues else nan_col,
+            "p_value_fdr": fdr_col if calculate_pvalues else nan_col.copy(),
+            "nlog10_p_value_fdr": nlog_col if calculate_pvalues else nan_col.copy()}
+    if label_col is not None:
+        data["p_value_label_null"] = label_col
+    # the columns are fresh arrays nobody else holds: no defensive copy (86 ms at 3.2 M rows)
+    return pd.DataFrame(data, copy=False)
 
 
 __all__ = [

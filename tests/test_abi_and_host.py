@@ -262,3 +262,32 @@ def test_product_stand_ins_equal_the_oracle_stand_ins():
     n1 = cosg_compat.iqr_log_normalize(t1).to_numpy()
     n2 = cosg_standin.iqr_log_normalize(t2).to_numpy()
     assert np.allclose(n1, n2, rtol=1e-14, atol=0) and n1.max() == 1.0 and n1.min() == 0.0 and (n1[:, 4] == 0).all()
+
+
+def test_pending_csr_is_a_scipy_matrix_that_joins_once():
+    """engine.PendingCSR without a GPU: the arrays are joined on first access, exactly once; copies / pickles are plain."""
+    import pickle
+    from laris_b200 import engine
+    A = sp.random(40, 17, 0.3, format="csr", dtype=np.float32, random_state=3)
+    X = engine.PendingCSR((40, 17), dtype=np.float32)
+    X.indptr, X.indices, X.data = A.indptr.copy(), A.indices.copy(), A.data.copy()
+    X.has_sorted_indices = X.has_canonical_format = True
+    joined = []
+    X.__dict__["_laris_wait"] = lambda m: joined.append(m.shape)
+    assert X._laris_pending() and X.shape == (40, 17) and sp.issparse(X) and not joined      # shape alone does not join
+    assert X.nnz == A.nnz and joined == [(40, 17)] and not X._laris_pending()
+    assert (X != A).nnz == 0 and np.allclose((X @ np.ones(17)), A @ np.ones(17)) and len(joined) == 1
+    assert type(pickle.loads(pickle.dumps(X))) is sp.csr_matrix and (X.copy() != A).nnz == 0
+    X.data *= 2.0
+    assert np.allclose(X.sum(), 2.0 * A.sum())
+
+
+def test_take_many_equals_single_takes():
+    from laris_b200 import cosg_compat
+    rng = np.random.default_rng(1)
+    names = np.array([f"n{i}" for i in range(50)], dtype=object)
+    codes = [rng.integers(0, 50, 300_000).astype(np.int32), rng.integers(0, 50, 300_000)]
+    t = cosg_compat.StringTaker(names)
+    many = cosg_compat.take_many([(t, codes[0]), (t, codes[1])])
+    for got, c in zip(many, codes):
+        assert (np.asarray(got, dtype=object) == names[c]).all()

@@ -499,3 +499,110 @@ def test_speculative_entry_array_is_validated(monkeypatch):
     for got in (first, second, third):
         assert list(got.index) == list(ref.index)
         assert np.allclose(got["score"].to_numpy(), ref["score"].to_numpy(), rtol=1e-6, atol=1e-12)
+
+
+# ------------------------------------------------- result materialisation ----
+@pytest.mark.parametrize("npair,C,frac", [(7, 3, 0.5), (60, 5, 0.3), (300, 12, 0.05), (2, 1, 1.0), (40, 9, 0.0)])
+def test_result_row_order_equals_the_host_mirror(dev, npair, C, frac):
+    """T6a/T6b: the device's table order (two stable radix sorts) is exactly the numpy mirror's - ties in both keys,
+    thresholded-away rows in melt order - and the gathered columns / codes are the host gathers of that order."""
+    from laris_b200 import _kernels as K
+    from laris_b200.tools import _utils as U
+    rng = np.random.default_rng(npair * 31 + C)
+    L = C * C
+    inter = np.round(rng.random((npair, L)), 2)                         # two decimals: plenty of ties in the first key
+    flat = np.round(inter * rng.random((npair, L)), 1) * (rng.random((npair, L)) < frac)      # ties and zeros in the second
+    cols = [rng.random((npair, L)) for _ in range(4)]
+    inter_d, flat_d = _d(inter, torch.float64), _d(flat, torch.float64)
+    order_d, exotic_d = K.result_row_order(inter_d, flat_d, C)
+    want = U._rows_in_table_order(inter, flat, npair, C)
+    assert int(exotic_d.item()) == 0
+    assert np.array_equal(order_d.cpu().numpy(), want)
+    got = K.result_rows_gather(order_d, C, flat_d, *[_d(c, torch.float64) for c in cols])
+    assert np.array_equal(got[0].cpu().numpy(), flat.reshape(-1)[want])
+    for g, c in zip(got[1:5], cols):
+        assert np.array_equal(g.cpu().numpy(), c.reshape(-1)[want])
+    pair, rem = np.divmod(want, L)
+    assert np.array_equal(got[5].cpu().numpy(), pair)
+    assert np.array_equal(got[6].cpu().numpy(), rem // C) and np.array_equal(got[7].cpu().numpy(), rem % C)
+    only = K.result_rows_gather(order_d, C, flat_d)                     # no p-value columns
+    assert only[1] is None and only[4] is None and np.array_equal(only[0].cpu().numpy(), flat.reshape(-1)[want])
+    for bad in (-0.5, np.nan):                                          # scores the device pass hands back to the host
+        f2 = flat.copy()
+        f2[npair // 2, L // 2] = bad
+        assert int(K.result_row_order(inter_d, _d(f2, torch.float64), C)[1].item()) == 1
+
+
+def test_long_table_same_through_device_and_host_order(dev, tiny, monkeypatch):
+    """The DataFrame built from the device-ordered columns equals the one assembled on the host (order, strings, values)."""
+    import laris_b200 as la
+    from laris_b200 import _kernels as K
+    a, lr, c = tiny
+    kw = dict(n_nearest_neighbors=8, n_cells_expressed_threshold=20, number_nearest_neighbors=8, n_permutations=100,
+              rng="philox", verbose=False)
+    lr_adata = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=8)
+    _, dev_tab = la.tl.runLARIS(lr_adata, a, **kw)
+    real = K.result_row_order
+
+    def flagged(inter, flat, C):
+        order, exotic = real(inter, flat, C)
+        return order, torch.ones_like(exotic)                            # pretend the scores were exotic: host path
+    monkeypatch.setattr(K, "result_row_order", flagged)
+    _, host_tab = la.tl.runLARIS(lr_adata, a, **kw)
+    assert list(dev_tab.columns) == list(host_tab.columns) and len(dev_tab) == 120 * c.C * c.C
+    for col in ("sender", "receiver", "ligand", "receptor", "interaction_name"):
+        assert dev_tab[col].dtype == host_tab[col].dtype and (dev_tab[col].to_numpy() == host_tab[col].to_numpy()).all(), col
+    assert np.allclose(dev_tab["interaction_score"], host_tab["interaction_score"], rtol=1e-12, atol=0)
+    assert np.array_equal(dev_tab["p_value"].to_numpy(), host_tab["p_value"].to_numpy())
+    assert {"n_genes_by_counts", "total_counts", "pct_counts_in_top_50_genes"} <= set(lr_adata.obs.columns)
+
+
+def test_pending_score_matrix_joins_on_first_access(dev, tiny):
+    """prepareLRInteraction hands the CSR over while its arrays are still coming down; runLARIS scores the resident copy
+    without touching them; the first reader waits and sees the oracle's matrix; copies and pickles are plain matrices."""
+    import pickle
+    import laris_b200 as la
+    from laris_b200 import engine
+    from oracle import restate as R
+    a, lr, _ = tiny
+    lr_adata = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=8)
+    X = lr_adata.X
+    assert isinstance(X, engine.PendingCSR) and sp.issparse(X) and X._laris_pending() and X.shape == (1500, 120)
+    out = la.tl.runLARIS(lr_adata, None, n_nearest_neighbors=8, by_celltype=False, n_cells_expressed_threshold=20,
+                         rng="philox", verbose=False)
+    assert X._laris_pending() and len(out) == 120                        # nothing on that path looked at the host arrays
+    ind, dist = R.knn_graph(a.obsm["X_spatial"], 8, True)
+    S = R.lr_scores(a.X, ind, R.decay_weights(dist), R.gene_index(a.var_names, lr["ligand"]),
+                    R.gene_index(a.var_names, lr["receptor"]))
+    assert X.nnz == S.nnz and not X._laris_pending()
+    assert np.array_equal(X.indptr, S.indptr) and np.array_equal(X.indices, S.indices)
+    assert np.allclose(X.data, S.data, rtol=RTOL, atol=0) and X.dtype == np.float32 and X.indptr.dtype == np.int32
+    for Y in (X.copy(), pickle.loads(pickle.dumps(X))):
+        assert (Y != X).nnz == 0
+    assert type(pickle.loads(pickle.dumps(X))) is sp.csr_matrix
+    X64 = la.tl.prepareLRInteraction(a, lr, number_nearest_neighbors=8, dtype=np.float64).X
+    assert X64.dtype == np.float64 and X64.data.dtype == np.float64 and np.array_equal(X64.data, X.data.astype(np.float64))
+
+
+def test_row_qc_reaches_into_the_negative_values(dev):
+    """Top-N sums when N exceeds the positives plus the zeros of a row (the select then runs below the key of 0.0)."""
+    from laris_b200 import _kernels as K
+    rng = np.random.default_rng(5)
+    n, P = 64, 200
+    S = np.zeros((n, K.padded_ld(P)), np.float32)
+    S[:, :P] = rng.normal(0.0, 1.0, (n, P)).astype(np.float32) * (rng.random((n, P)) < 0.8)
+    S[3, :P] = -np.abs(S[3, :P]) - 1.0                                  # no positives, no zeros
+    S[4, :P] = 0.0
+    S[4, :5] = [-1.0, -2.0, 3.0, -0.5, 7.0]
+    tops = [1, 120, 150, 199]
+    total, nnz, top = K.row_qc(torch.from_numpy(S).to(dev), P, tops)
+    ref = S[:, :P].astype(np.float64)
+    srt = -np.sort(-ref, axis=1)
+    assert np.allclose(total.cpu().numpy(), ref.sum(1), rtol=1e-12, atol=1e-12)
+    assert np.array_equal(nnz.cpu().numpy(), (ref != 0).sum(1))
+    for j, N in enumerate(tops):
+        assert np.allclose(top.cpu().numpy()[:, j], srt[:, :N].sum(1), rtol=1e-12, atol=1e-12), N
+    view = torch.from_numpy(S).to(dev)[:, 1:]                           # ld not a multiple of 4 / unaligned rows: scalar loads
+    Sv = view.contiguous()
+    t2 = K.row_qc(Sv, P - 1, [50])[2].cpu().numpy()[:, 0]
+    assert np.allclose(t2, (-np.sort(-ref[:, 1:], axis=1))[:, :50].sum(1), rtol=1e-12, atol=1e-12)
