@@ -268,6 +268,8 @@ def kernel_rooflines(stage_ms, calls, c, P_local, nnz_u, k, hbm_peak, bf16_peak,
         "instead of 4P bytes per gathered row")
     add("K4 pack scores", 4 * n * P_local + 8 * n_entries + 8 * (n + 1), "4nP + 8E + 8(n+1): S read once, packed rows written once")
     add("K5b nonzero_count", 4 * n * P_local, "4nP: S read once")
+    add("K5b nonzero_count (packed)", 8 * n_entries + 8 * (n + 1) + 8 * n,
+        "8E + 8(n+1) + 8n: the packed rows of S read once, their pointers, the type-grouped cell list written and read")
     add("K5 pair_contract", 4 * n * P_local,
         "4nP: one read of S is the floor of the key-gather contraction (the default at <= 8 cell-type pairs per cell); it reads S "
         "once per key a cell takes part in (3.0x at config 3, mostly L2 hits).  The tcgen05 variant (mixed neighbourhoods, "
@@ -456,7 +458,9 @@ def run_ours(args):
                    "call": ("laris_b200.dist.prepare_sharded + " if world > 1 else "laris_b200.tl.prepareLRInteraction + ")
                            + "laris_b200.tl.runLARIS(rng='philox'): host AnnData in, host AnnData (scipy CSR) + two DataFrames out",
                    "state": "caller's input arrays are page-locked; the LR-table plan and the pinned result buffers are warm "
-                            "(2 untimed calls); bytes are per rank"}
+                            "(3 untimed calls); bytes are per rank; the score matrix's device->host copies run on a copy stream "
+                            "behind runLARIS's kernels and are complete when the timed call ends (torch.cuda.synchronize() is "
+                            "inside the timed region)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,

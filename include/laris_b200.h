@@ -251,6 +251,11 @@ LARIS_API int laris_celltype_pair_contract(const float* S, int64_t ldS, int64_t 
  * device and counted in registers, integer atomics only where the type changes); labels outside [0,C) are skipped. */
 LARIS_API int laris_celltype_nonzero_count(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* labels,
                                  int32_t C, uint64_t* counts, void* stream);
+/* The same counts (same reference lines) from the packed rows of S that laris_scores_pack wrote (sp_ptr [n+1], entries
+ * {int32 column, fp32 bits}, zero-valued padding; entries beyond `capacity` are not read): 8 bytes per non-zero score
+ * instead of 4P bytes per cell.  P * 4 bytes of shared memory per CTA. */
+LARIS_API int laris_celltype_nonzero_count_packed(const int64_t* sp_ptr, const void* entries, int64_t capacity, int64_t n,
+                                 int32_t P, const int32_t* labels, int32_t C, uint64_t* counts, void* stream);
 /* One-hot contraction straight from a packed CSR (laris_csr_select_fill layout):
  * sum[c*G_u+g] = sum of Xu over cells of type c, cnt = non-zero count, colsq[g] =
  * sum_i Xu[i,g]^2.  These are the numerators / norms of the cosine between a

@@ -450,6 +450,17 @@ def celltype_nonzero_count(S, P, labels, C):
     return cnt
 
 
+@_staged("K5b nonzero_count (packed)")
+def celltype_nonzero_count_packed(sp_ptr, entries, P, labels, C):
+    """K5b from the packed rows of S (``scores_pack``): [C, P] int64 counts."""
+    n = sp_ptr.numel() - 1
+    cnt = torch.empty((C, P), dtype=torch.int64, device=sp_ptr.device)
+    check(lib.laris_celltype_nonzero_count_packed(_ptr(sp_ptr, torch.int64), _ptr(entries, torch.int64), entries.numel(), n, P,
+                                                  _ptr(labels, torch.int32), C, _ptr(cnt), _stream()),
+          "laris_celltype_nonzero_count_packed")
+    return cnt
+
+
 @_staged("COSG onehot_contract")
 def onehot_contract_csr(xu_indptr, xu_packed, G_u, labels, C, row_end=None):
     n = xu_indptr.numel() - 1

@@ -58,6 +58,7 @@ SIGNATURES = {
     "laris_permute_labels": [_p, _i64, _i, _u64, _p, _p],
     "laris_count_exceed": [_p, _p, _i64, _p, _p],
     "laris_celltype_nonzero_count": [_p, _i64, _i64, _i, _p, _i, _p, _p],
+    "laris_celltype_nonzero_count_packed": [_p, _p, _i64, _i64, _i, _p, _i, _p, _p],
     "laris_onehot_contract_csr": [_p, _p, _i64, _i, _p, _i, _p, _p, _p, _p],
     "laris_onehot_contract_rows": [_p, _p, _p, _i64, _i, _p, _i, _p, _p, _p, _p],
     "laris_pvalue_counts": [_p, _i64, _i, _i, _p, _i, _p, _p, _i64, _i, _i, _i, _i, _u64, _p, _p, _p, _p, _p],

@@ -88,6 +88,61 @@ celltype_nonzero_count_kernel(const float4* __restrict__ S4, int64_t ld4, int64_
     flush(cur);
 }
 
+// The same counts from the PACKED rows of S (csrc/stats_sparse.cu: entries {column, value bits}, rows padded to whole
+// 32-entry chunks with zero-valued entries): 8 bytes per non-zero instead of 4P bytes per cell.  A CTA takes a contiguous
+// range of the type-grouped cell list and walks it one type segment at a time; a warp owns a row, its lanes count the
+// row's entries into a per-CTA shared-memory table [P] (a row's columns are distinct, so the adds of a row never collide
+// inside the warp; rows of different warps do, hence atomics), flushed with global integer atomics at the end of a segment.
+constexpr int kPcThreads = 256;
+
+__global__ void __launch_bounds__(kPcThreads)
+nonzero_count_packed_kernel(const int64_t* __restrict__ sp_ptr, const int2* __restrict__ entries, int64_t capacity, int P,
+                            const int32_t* __restrict__ rows, const int32_t* __restrict__ start /*[C+1]*/, int C,
+                            unsigned long long* __restrict__ counts /*[C][P]*/) {
+    extern __shared__ uint32_t pc_cnt[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t m = start[C];                                       // validly labelled cells
+    const int64_t per = (m + gridDim.x - 1) / gridDim.x;
+    int64_t r0 = (int64_t)blockIdx.x * per;
+    const int64_t r1 = min(m, r0 + per);
+    if (r0 >= r1) return;
+    for (int i = threadIdx.x; i < P; i += kPcThreads) pc_cnt[i] = 0u;
+    int lo = 0, hi = C;                                               // type of cell r0: last c with start[c] <= r0
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)start[mid] <= r0) lo = mid; else hi = mid;
+    }
+    int c = lo;
+    __syncthreads();
+    while (r0 < r1) {
+        while (c + 1 < C && (int64_t)start[c + 1] <= r0) ++c;          // skip types without cells
+        const int64_t seg_end = min(r1, (int64_t)start[c + 1]);
+        for (int64_t r = r0 + warp; r < seg_end; r += kPcThreads / 32) {
+            const int64_t i = rows[r];
+            const int64_t rs = sp_ptr[i], re = min(sp_ptr[i + 1], capacity);
+            for (int64_t e = rs + lane; e < re; e += 128) {            // four chunks in flight per lane
+                int2 en[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    en[u] = e + 32 * u < re ? __ldg(entries + e + 32 * u) : make_int2(0, 0);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (en[u].y != 0 && en[u].x < P) atomicAdd(&pc_cnt[en[u].x], 1u);
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < P; i += kPcThreads) {
+            const uint32_t v = pc_cnt[i];
+            if (v) {
+                atomicAdd(counts + (int64_t)c * P + i, (unsigned long long)v);
+                pc_cnt[i] = 0u;
+            }
+        }
+        __syncthreads();
+        r0 = seg_end;
+    }
+}
+
 // ---- per (type, gene) sums straight from the packed CSR: warp per row
 __global__ void onehot_contract_csr_kernel(const int64_t* __restrict__ row_start, const int64_t* __restrict__ row_end,
                                            const int64_t* __restrict__ packed,
@@ -208,6 +263,23 @@ extern "C" int laris_neighborhood_composition(const int32_t* labels, const int32
     return LARIS_OK;
 }
 
+// cells grouped by type: histogram -> scan -> scatter (cells with a label outside [0,C) are skipped); start [C+1],
+// rows / row_label [n] (row_label = -1 in the unused tail)
+static int group_cells_by_type(const int32_t* labels, int64_t n, int C, int32_t* hist, int32_t* start, int32_t* cursor,
+                               int32_t* rows, int32_t* row_label, cudaStream_t st) {
+    LARIS_CUDA(cudaMemsetAsync(hist, 0, (size_t)C * sizeof(int32_t), st));
+    LARIS_CUDA(cudaMemsetAsync(cursor, 0, (size_t)C * sizeof(int32_t), st));
+    LARIS_CUDA(cudaMemsetAsync(row_label, 0xff, (size_t)n * sizeof(int32_t), st));     // -1: unused tail
+    const unsigned gn = (unsigned)ceil_div(n, 256);
+    label_histogram_kernel<<<gn, 256, 0, st>>>(labels, n, C, hist);
+    LARIS_LAUNCH_CHECK();
+    int rc = exclusive_scan<int32_t>(hist, C, start, st);
+    if (rc) return rc;
+    label_scatter_kernel<<<gn, 256, 0, st>>>(labels, n, C, start, cursor, rows, row_label);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
 extern "C" int laris_celltype_nonzero_count(const float* S, int64_t ldS, int64_t n, int32_t P, const int32_t* labels,
                                             int32_t C, uint64_t* counts, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -215,23 +287,14 @@ extern "C" int laris_celltype_nonzero_count(const float* S, int64_t ldS, int64_t
     LARIS_CHECK_ARG(ldS >= P && ldS % 4 == 0 && ((uintptr_t)S & 15) == 0, "laris_celltype_nonzero_count: S layout");
     LARIS_CHECK_ARG(n < (int64_t)INT32_MAX, "laris_celltype_nonzero_count: n must fit int32");
     LARIS_CUDA(cudaMemsetAsync(counts, 0, (size_t)C * P * sizeof(uint64_t), st));
-    // group the cells by type: histogram -> scan -> scatter (cells with a label outside [0,C) are skipped)
     Scratch<int32_t> hist(st), start(st), cursor(st), rows(st), row_label(st);
     LARIS_CUDA(hist.alloc(C));
     LARIS_CUDA(start.alloc(C + 1));
     LARIS_CUDA(cursor.alloc(C));
     LARIS_CUDA(rows.alloc(n));
     LARIS_CUDA(row_label.alloc(n));
-    LARIS_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)C * sizeof(int32_t), st));
-    LARIS_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)C * sizeof(int32_t), st));
-    LARIS_CUDA(cudaMemsetAsync(row_label.p, 0xff, (size_t)n * sizeof(int32_t), st));     // -1: unused tail
-    const unsigned gn = (unsigned)ceil_div(n, 256);
-    label_histogram_kernel<<<gn, 256, 0, st>>>(labels, n, C, hist.p);
-    LARIS_LAUNCH_CHECK();
-    int rc = exclusive_scan<int32_t>(hist.p, C, start.p, st);
+    int rc = group_cells_by_type(labels, n, C, hist.p, start.p, cursor.p, rows.p, row_label.p, st);
     if (rc) return rc;
-    label_scatter_kernel<<<gn, 256, 0, st>>>(labels, n, C, start.p, cursor.p, rows.p, row_label.p);
-    LARIS_LAUNCH_CHECK();
     const int64_t ld4 = ldS / 4;
     const int slabs = (int)ceil_div(ld4, kCcThreads);
     int64_t nchunks = ceil_div((int64_t)kNumSMs * 16, slabs);          // ~16 resident 128-thread CTAs per SM
@@ -241,6 +304,34 @@ extern "C" int laris_celltype_nonzero_count(const float* S, int64_t ldS, int64_t
     // rows beyond the number of validly labelled cells carry label -1 and end the chunk loops
     celltype_nonzero_count_kernel<<<grid, kCcThreads, 0, st>>>((const float4*)S, ld4, n, P, rows.p, row_label.p, (int)nchunks,
                                                                (unsigned long long*)counts);
+    LARIS_LAUNCH_CHECK();
+    return LARIS_OK;
+}
+
+extern "C" int laris_celltype_nonzero_count_packed(const int64_t* sp_ptr, const void* entries, int64_t capacity, int64_t n,
+                                                   int32_t P, const int32_t* labels, int32_t C, uint64_t* counts,
+                                                   void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    LARIS_CHECK_ARG(sp_ptr && entries && labels && counts && n > 0 && P >= 1 && C >= 1 && capacity >= 0,
+                    "laris_celltype_nonzero_count_packed: bad arguments");
+    LARIS_CHECK_ARG(n < (int64_t)INT32_MAX, "laris_celltype_nonzero_count_packed: n must fit int32");
+    LARIS_CHECK_ARG((size_t)P * sizeof(uint32_t) <= (size_t)200 * 1024,
+                    "laris_celltype_nonzero_count_packed: P=%d does not fit shared memory", P);
+    LARIS_CUDA(cudaMemsetAsync(counts, 0, (size_t)C * P * sizeof(uint64_t), st));
+    Scratch<int32_t> hist(st), start(st), cursor(st), rows(st), row_label(st);
+    LARIS_CUDA(hist.alloc(C));
+    LARIS_CUDA(start.alloc(C + 1));
+    LARIS_CUDA(cursor.alloc(C));
+    LARIS_CUDA(rows.alloc(n));
+    LARIS_CUDA(row_label.alloc(n));
+    int rc = group_cells_by_type(labels, n, C, hist.p, start.p, cursor.p, rows.p, row_label.p, st);
+    if (rc) return rc;
+    const size_t smem = (size_t)P * sizeof(uint32_t);
+    LARIS_CUDA(cudaFuncSetAttribute(nonzero_count_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t grid = (int64_t)kNumSMs * 8;                               // 8 x 256 threads per SM when the table is small
+    if (grid > ceil_div(n, 64)) grid = ceil_div(n, 64);
+    nonzero_count_packed_kernel<<<(unsigned)grid, kPcThreads, smem, st>>>(sp_ptr, (const int2*)entries, capacity, P, rows.p,
+                                                                         start.p, C, (unsigned long long*)counts);
     LARIS_LAUNCH_CHECK();
     return LARIS_OK;
 }

@@ -457,7 +457,7 @@ class CapturedScoring:
         return self.scores
 
 
-FP_SAMPLES = 1 << 20
+FP_SAMPLES = 1 << 18          # strided sample of the stored values a content fingerprint covers (every value below that)
 
 
 def device_fingerprint_async(data_d):

@@ -163,7 +163,8 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     else:
         graph = engine.build_radius_graph(_utils._coords(lr_adata, use_rep), radius, False, sigma)
     # observed statistics + all null repeats: one device tensor [1+R, 5, P_local], one gather, one download
-    st_d, rng_state = engine.spatial_stats_all(sm, graph, n_repeats, random_seed, rng, speculative=True)
+    # (speculative sizing of the packed rows only without sharding: a redo on some ranks would unbalance the collectives)
+    st_d, rng_state = engine.spatial_stats_all(sm, graph, n_repeats, random_seed, rng, speculative=shard is None)
     sm.cache["stats_d"] = st_d[0]
     sm.cache["graph"] = graph                 # the cell-type step re-uses the neighbour search when it can
     # the statistics come down through a copy queued NOW (K.to_host_async), so that waiting for them below does not also
@@ -188,6 +189,8 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
         # (the random graphs are regenerated from random_seed: same graphs, same continued rng state)
         st_d, rng_state = engine.spatial_stats_all(sm, graph, n_repeats, random_seed, rng)
         sm.cache["stats_d"] = st_d[0]
+        if pre is not None and pre.get("cnt_from_packed"):             # K5b counted the truncated rows too
+            pre["cnt_d"] = K.celltype_nonzero_count(sm.S, sm.P, pre["labels"][3], len(pre["labels"][1]))
         if shard is not None:
             stats_get = K.to_host_async(_dist.all_gather_pairs_dev(st_d, shard, axis=-1), st_d[0].contiguous())
         else:

@@ -23,7 +23,7 @@ from .. import dist as _dist
 # runLARIS neither re-uploads lr_adata.X nor re-selects adata.X.  A hit needs the SAME matrix
 # object with the SAME contents: entries are keyed by id() (weakly referenced) and validated against a content
 # fingerprint - nnz plus an exact integer checksum of the float32 bit patterns of a strided sample of ``.data``
-# (every element for matrices below 2^20 stored entries) - so in-place edits such as ``X.data *= c`` or a scanpy
+# (every element for matrices below 2^18 stored entries) - so in-place edits such as ``X.data *= c`` or a scanpy
 # ``log1p`` / ``scale`` between the two calls invalidate the entry instead of being silently ignored.
 # ---------------------------------------------------------------------------
 _SCORE_CACHE: dict = {}
@@ -136,7 +136,7 @@ def _write_obs_qc_async(lr_adata, sm, shard=None, percent_top=(50, 100, 200, 500
     tops = [] if shard is not None else [N for N in percent_top if N < P]
     get = K.to_host_async(*K.row_qc(sm.S, P, tops))
 
-    def finish():
+    def columns():
         total, nnz, top = get()
         if shard is not None:
             both = _dist.all_reduce_sum(np.stack([total, nnz.astype(np.float64)]))
@@ -146,6 +146,15 @@ def _write_obs_qc_async(lr_adata, sm, shard=None, percent_top=(50, 100, 200, 500
                     "total_counts": total.astype(np.float32), "log1p_total_counts": np.log1p(total).astype(np.float32)}
             for j, N in enumerate(tops):
                 cols[f"pct_counts_in_top_{N}_genes"] = 100.0 * top[:, j] / total
+        return cols
+
+    # single-GPU runs: a worker thread waits for the download and does the column arithmetic (numpy releases the GIL);
+    # a sharded run keeps its all-reduce on the calling thread, in program order
+    pool = cosg_compat._pool() if shard is None else None
+    fut = pool.submit(columns) if pool is not None else None
+
+    def finish():
+        cols = fut.result() if fut is not None else columns()
         obs = lr_adata.obs
         for name, col in cols.items():
             obs[name] = col
@@ -423,13 +432,18 @@ def _celltype_prefetch(adata, lr_adata, groupby, use_rep_spatial, number_nearest
     rec_g = gene_pos.get_indexer([h[-1] for h in halves])
     cosg_finish = _gene_cosg_scores_async(adata, genes_all, groupby, mu, expressed_pct, remove_lowly_expressed, shard, labels)
     sm = _scores_of(lr_adata)
-    cnt_d = K.celltype_nonzero_count(sm.S, sm.P, labels_d, C)                                   # [C, P_local] int64
+    # K5b: from the packed rows when the statistics pass built them (8 bytes per non-zero instead of 4P bytes per cell)
+    packed = sm.cache.get("packed")
+    if packed is not None:
+        cnt_d = K.celltype_nonzero_count_packed(packed[0], packed[1], sm.P, labels_d, C)        # [C, P_local] int64
+    else:
+        cnt_d = K.celltype_nonzero_count(sm.S, sm.P, labels_d, C)
     if shard is not None:
         cnt_d = _dist.all_gather_pairs_dev(cnt_d, shard, axis=1)
     raw_finish = _neighborhood_raw_async(adata, sm, labels, use_rep_spatial, number_nearest_neighbors, mu, contract_impl,
                                          shard, radius)
     return dict(labels=labels, lr_names=lr_names, genes_all=genes_all, lig_g=lig_g, rec_g=rec_g, cosg_finish=cosg_finish,
-                cnt_d=cnt_d, raw_finish=raw_finish)
+                cnt_d=cnt_d, cnt_from_packed=packed is not None, raw_finish=raw_finish)
 
 
 def _calculate_diffused_lr_specificity(lr_adata, groupby: str = "CellTypes", mu: float = 100, expressed_pct: float = 0.05,
@@ -889,8 +903,14 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
     # T6a: the reference's row order, sorted on the device while the p-values are computed (the long table and the
     # reference-stream draws need it)
     order_d = exotic_d = None
+    early_get = None
     if npair * L < 2 ** 31 - 1 and (output == "frames" or (calculate_pvalues and rng == "numpy")):
         order_d, exotic_d = K.result_row_order(inter_d, flat_d, C)
+        if output == "frames":
+            # T6b, first call: the score column and the (pair, sender, receiver) codes of every row start their way to the
+            # host now - the string columns are decoded from them on worker threads while the device does the p-values
+            early = K.result_rows_gather(order_d, C, flat_d)
+            early_get = K.to_host_async(exotic_d, early[0], early[5], early[6], early[7])
 
     def host_order():
         """The row order on the host: the device's (T6a), or the numpy mirror above for scores it does not order."""
@@ -965,14 +985,23 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
         return result
 
     # ---- the reference's long table, rows by descending score ----
-    host = None
-    if order_d is not None:
-        # T6b: numeric columns and (pair, sender, receiver) codes gathered in table order on the device, one download
-        cols_d = K.result_rows_gather(order_d, C, flat_d, p_rows, fdr_rows, nlog_rows, label_rows)
-        present = [c is not None for c in cols_d]
-        got = iter(K.to_host(exotic_d, *[c for c in cols_d if c is not None]))
-        if not next(got)[0]:
-            host = [next(got) if here else None for here in present]
+    host = strings = None
+    cat_taker = cosg_compat.StringTaker(cats_arr)
+
+    def string_jobs(row_pair, row_send, row_recv):
+        return [(cat_taker, row_send), (cat_taker, row_recv), (cosg_compat.StringTaker(lig), row_pair),
+                (cosg_compat.StringTaker(rec), row_pair), (cosg_compat.StringTaker(inter_names), row_pair)]
+
+    if early_get is not None:
+        # T6b, second call: the p-value columns in table order (queued behind K6 / K7); meanwhile the codes have arrived
+        late_d = [c for c in K.result_rows_gather(order_d, C, flat_d, p_rows, fdr_rows, nlog_rows, label_rows)[1:5]]
+        late_get = K.to_host_async(*[c for c in late_d if c is not None]) if any(c is not None for c in late_d) else (lambda: ())
+        exotic, score, row_pair, row_send, row_recv = early_get()
+        if not exotic[0]:
+            strings = cosg_compat.take_many_async(string_jobs(row_pair, row_send, row_recv))
+            late = late_get()
+            late = iter(late if isinstance(late, tuple) else (late,))
+            host = [score] + [next(late) if c is not None else None for c in late_d]
     if host is None:                            # scores the device pass does not order (negative / NaN), or > 2^31 rows
         flat = flat_d.cpu().numpy()
         if order_rows is None:
@@ -980,13 +1009,10 @@ def _calculate_laris_score_by_celltype(adata, lr_adata, laris_lr, groupby: str =
         row_pair, rem = np.divmod(order_rows, L)
         row_send, row_recv = np.divmod(rem, C)
         take = lambda t: None if t is None else t.cpu().numpy().reshape(-1)[order_rows]          # noqa: E731
-        host = [flat.reshape(-1)[order_rows], take(p_rows), take(fdr_rows), take(nlog_rows), take(label_rows),
-                row_pair, row_send, row_recv]
-    score, p_col, fdr_col, nlog_col, label_col, row_pair, row_send, row_recv = host
-    cat_taker = cosg_compat.StringTaker(cats_arr)
-    sender, receiver, lig_col, rec_col, name_col = cosg_compat.take_many([
-        (cat_taker, row_send), (cat_taker, row_recv), (cosg_compat.StringTaker(lig), row_pair),
-        (cosg_compat.StringTaker(rec), row_pair), (cosg_compat.StringTaker(inter_names), row_pair)])
+        host = [flat.reshape(-1)[order_rows], take(p_rows), take(fdr_rows), take(nlog_rows), take(label_rows)]
+        strings = cosg_compat.take_many_async(string_jobs(row_pair, row_send, row_recv))
+    score, p_col, fdr_col, nlog_col, label_col = host
+    sender, receiver, lig_col, rec_col, name_col = strings()
     nan_col = None if calculate_pvalues else np.full(len(score), np.nan)
     data = {"sender": sender, "receiver": receiver, "interaction_score": score, "ligand": lig_col, "receptor": rec_col,
             "interaction_name": name_col,

@@ -606,3 +606,34 @@ def test_row_qc_reaches_into_the_negative_values(dev):
     Sv = view.contiguous()
     t2 = K.row_qc(Sv, P - 1, [50])[2].cpu().numpy()[:, 0]
     assert np.allclose(t2, (-np.sort(-ref[:, 1:], axis=1))[:, :50].sum(1), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("n,P,k,C,density", [(5000, 37, 3, 4, 0.3), (30000, 700, 10, 40, 0.1), (6000, 2500, 5, 150, 0.04),
+                                             (777, 3, 2, 1, 0.5)])
+def test_packed_row_celltype_counts_equal_the_dense_pass(n, P, k, C, density):
+    """K5b from the packed rows of S: the integer table of the dense pass, exactly - types without cells, labels outside
+    [0, C) (skipped by both), a dense and an empty row; rows beyond an under-sized entry array are left out, not misread."""
+    from laris_b200 import _kernels as K, engine
+    S, _, _, _ = _sparse_case(n, P, k, 0, density)
+    sm = engine.ScoreMatrix(S, P)
+    engine.queue_row_pointers(sm)
+    n_entries = int(sm.cache["nnz_get"]()[0])
+    sp_ptr = sm.cache["sp_ptr"]
+    entries = K.scores_pack(S, P, sp_ptr, n_entries)
+    rng = np.random.default_rng(n + C)
+    labels = rng.integers(0, C, n).astype(np.int32)
+    if C > 3:
+        labels[labels == 2] = 3                                        # a type without cells
+        labels[:7] = -1                                                # unlabelled cells
+        labels[7:9] = C
+    lab_d = torch.from_numpy(labels).cuda()
+    dense = K.celltype_nonzero_count(S, P, lab_d, C)
+    packed = K.celltype_nonzero_count_packed(sp_ptr, entries, P, lab_d, C)
+    assert torch.equal(dense, packed)
+    Sh = S.cpu().numpy()[:, :P] != 0
+    ok = (labels >= 0) & (labels < C)
+    ref = np.zeros((C, P), np.int64)
+    np.add.at(ref, labels[ok], Sh[ok].astype(np.int64))
+    assert np.array_equal(packed.cpu().numpy(), ref)
+    short = K.celltype_nonzero_count_packed(sp_ptr, entries[: n_entries // 2 // 32 * 32].contiguous(), P, lab_d, C)
+    assert (short <= packed).all() and (n_entries < 64 or short.sum() < packed.sum())
