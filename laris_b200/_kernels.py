@@ -77,13 +77,58 @@ def require_cuda():
 
 
 PIN_STAGE_MAX_BYTES = 64 << 20
+PAGEABLE_PIPELINE = True            # large pageable arrays go up through a ring of page-locked buffers (below)
+_RING_SLOTS, _RING_BYTES = 6, 32 << 20
+_RING: dict = {}
+
+
+def _upload_pageable(t, dev):
+    """A large PAGEABLE host tensor -> device tensor of the same dtype through a ring of page-locked staging buffers:
+    worker threads copy 32 MB pieces into the ring (a plain memcpy, the GIL is released) while the pieces already staged
+    go up as asynchronous copies on the current stream.  ``cudaMemcpy`` from pageable memory stages through the driver's
+    own bounce buffer on ONE thread (~6-10 GB/s); several staging threads keep the PCIe link (55 GB/s) far busier.
+    Returns None when no worker threads are available (the caller then takes the plain path)."""
+    from . import _threads
+    pool = _threads.pool()
+    if pool is None:
+        return None
+    ring = _RING.get(dev.index)
+    if ring is None:
+        ring = _RING[dev.index] = [torch.empty(_RING_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(_RING_SLOTS)]
+    src = t.reshape(-1).view(torch.uint8)
+    out = torch.empty(src.shape, dtype=torch.uint8, device=dev)
+    total = src.numel()
+    pieces = [(lo, min(total, lo + _RING_BYTES)) for lo in range(0, total, _RING_BYTES)]
+    freed = [None] * _RING_SLOTS                              # event after the upload that last used the slot
+
+    def stage(c):
+        slot, (lo, hi) = c % _RING_SLOTS, pieces[c]
+        if freed[slot] is not None:
+            freed[slot].synchronize()                         # the staging buffer is free again
+        ring[slot][: hi - lo].copy_(src[lo:hi])
+        return slot
+
+    pending = [pool.submit(stage, c) for c in range(min(_RING_SLOTS, len(pieces)))]
+    for c, (lo, hi) in enumerate(pieces):
+        slot = pending[c].result()
+        out[lo:hi].copy_(ring[slot][: hi - lo], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        freed[slot] = ev
+        if c + _RING_SLOTS < len(pieces):
+            pending.append(pool.submit(stage, c + _RING_SLOTS))
+    # the ring is reused by the next call: its last uploads must have left the buffers before anyone refills them
+    for ev in freed:
+        if ev is not None:
+            ev.synchronize()
+    return out.view(t.dtype).view(t.shape)
 
 
 def to_device(a, dtype):
     """numpy -> device tensor of ``dtype``, without blocking the host: a pageable source is first copied into a page-locked
     staging buffer (torch's caching pinned allocator) so that the upload is an asynchronous copy on the current stream -
-    a synchronous ``cudaMemcpy`` would make the host wait for every kernel queued before it (arrays above 64 MB go the
-    plain way; the expression matrix has its own copy stream)."""
+    a synchronous ``cudaMemcpy`` would make the host wait for every kernel queued before it.  Arrays above 64 MB (the
+    expression matrix, which has its own copy stream) go through ``_upload_pageable``'s staging ring."""
     a = np.ascontiguousarray(a)
     t = torch.from_numpy(a) if a.dtype != np.dtype(object) else None
     if t is None:
@@ -94,6 +139,10 @@ def to_device(a, dtype):
     if t.is_pinned():
         out = t.to(dev, non_blocking=True)
         return out if out.dtype == dtype else out.to(dtype)
+    if PAGEABLE_PIPELINE and t.numel() > 0:
+        out = _upload_pageable(t, dev)
+        if out is not None:
+            return out if out.dtype == dtype else out.to(dtype)
     return t.to(dev, dtype=dtype)
 
 

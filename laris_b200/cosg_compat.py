@@ -70,23 +70,13 @@ def take_strings(values, codes):
     return StringTaker(values).take(codes)
 
 
-_POOL = []
 _TAKE_CHUNK = 1 << 19
 
 
 def _pool():
     """Worker threads for the string columns, or None on a single-core host."""
-    import os
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        cores = os.cpu_count() or 1
-    if cores < 2:
-        return None
-    if not _POOL:
-        from concurrent.futures import ThreadPoolExecutor
-        _POOL.append(ThreadPoolExecutor(max_workers=min(12, cores), thread_name_prefix="laris-take"))
-    return _POOL[0]
+    from . import _threads
+    return _threads.pool()
 
 
 def take_many_async(jobs):

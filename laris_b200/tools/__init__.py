@@ -70,6 +70,12 @@ def prepareLRInteraction(adata, lr_df, number_nearest_neighbors: int = 10, use_r
     tensors (e.g. from ``laris_b200.dist.upload_csr_replicated``) - nothing is uploaded.  ``to_host=False``
     (extension): skip the CSR compaction and download; ``.X`` of the returned (AnnDataLite) object is then a
     ``ResidentScores`` handle that ``runLARIS`` consumes directly and ``.X.tocsr()`` materialises on demand.
+
+    With ``to_host=True`` (default) ``.X`` is a ``scipy.sparse.csr_matrix`` (subclass ``engine.PendingCSR``) that is
+    returned while its arrays are still being copied from the device: the first access to them waits for the copy.
+    Limits of the compiled kernels (a ``LarisError`` names the limit when one is exceeded): at most 64 neighbours per
+    cell (``number_nearest_neighbors`` or the maximum degree of a radius graph) and at most 65533 distinct LR-gene /
+    complex columns.
     """
     xy = _utils._coords(adata, use_rep_spatial)
     # schedule: the expression matrix goes up on the copy stream while the host resolves the LR table and the graph is
@@ -139,6 +145,11 @@ def runLARIS(lr_adata, adata=None, use_rep: str = "X_spatial", n_nearest_neighbo
     ``label_permutations=T`` (extension, default 0 = the reference's behaviour): additionally relabel the cells T times
     and add ``p_value_label_null`` - the label-permutation p-value of the row's co-localisation cosine
     (``labelPermutationNull``).
+
+    Limits of the compiled kernels (a ``LarisError`` / ``ValueError`` names the limit when one is exceeded):
+    ``n_nearest_neighbors`` / ``number_nearest_neighbors`` (or the maximum radius-graph degree) <= 64;
+    ``n_neighbors_permutation`` <= 256; at most 16384 LR pairs per sender-receiver group in the BH-FDR step; the default
+    cell-type contraction takes <= 64 cell types (more fall back to the fp32 tile kernel automatically).
     """
     if by_celltype and adata is None:
         raise ValueError("Parameter 'adata' must be provided when by_celltype=True. "

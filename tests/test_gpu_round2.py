@@ -637,3 +637,22 @@ def test_packed_row_celltype_counts_equal_the_dense_pass(n, P, k, C, density):
     assert np.array_equal(packed.cpu().numpy(), ref)
     short = K.celltype_nonzero_count_packed(sp_ptr, entries[: n_entries // 2 // 32 * 32].contiguous(), P, lab_d, C)
     assert (short <= packed).all() and (n_entries < 64 or short.sum() < packed.sum())
+
+
+def test_large_pageable_arrays_go_up_through_the_staging_ring(dev):
+    """K.to_device of a pageable array above the 64 MB staging limit (the expression matrix of an ordinary AnnData): the ring
+    of page-locked buffers is refilled more than once, the last piece is ragged, dtype conversions happen on the device."""
+    from laris_b200 import _kernels as K
+    rng = np.random.default_rng(0)
+    a = rng.random((230 << 20) // 4 + 12345, dtype=np.float32)          # 8 pieces of 32 MB and a bit
+    assert K.PAGEABLE_PIPELINE and not torch.from_numpy(a).is_pinned()
+    d = K.to_device(a, torch.float32)
+    assert d.dtype == torch.float32 and d.shape == a.shape and np.array_equal(d.cpu().numpy(), a)
+    again = K.to_device(a[::-1].copy(), torch.float32)                  # the ring is reused by the next call
+    assert np.array_equal(again.cpu().numpy(), a[::-1])
+    i = (a[: (70 << 20) // 4] * 1e6).astype(np.int32)
+    d64 = K.to_device(i, torch.int64)
+    assert d64.dtype == torch.int64 and np.array_equal(d64.cpu().numpy(), i.astype(np.int64))
+    m = a[: 3 * 7_000_000].reshape(-1, 3).astype(np.float64)            # 2-D, 168 MB
+    dm = K.to_device(m, torch.float64)
+    assert dm.shape == m.shape and np.array_equal(dm.cpu().numpy(), m)
