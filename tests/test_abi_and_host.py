@@ -291,3 +291,33 @@ def test_take_many_equals_single_takes():
     many = cosg_compat.take_many([(t, codes[0]), (t, codes[1])])
     for got, c in zip(many, codes):
         assert (np.asarray(got, dtype=object) == names[c]).all()
+
+
+def test_table_row_order_mirror_equals_the_oracle_sorts():
+    """``_rows_in_table_order`` (the host mirror and test oracle of the device ordering, T6a) against the oracle's own
+    restatement of reference _utils.py:1408-1422, :1472: melt order, stable sort by the pre-weight score, stable sort by
+    the final score.  The rows that keep a positive score come out in exactly the oracle's order (ties included); the
+    thresholded-away rows follow in melt order."""
+    from laris_b200.tools import _utils as U
+    rng = np.random.default_rng(11)
+    for npair, C in ((5, 3), (40, 6), (3, 1)):
+        L = C * C
+        inter = np.round(rng.random((npair, C, C)), 1)                        # [pair, sender, receiver], many ties
+        weight = np.round(rng.random((npair, C, C)), 1)
+        final = inter * weight
+        final[final < 0.2] = 0.0                                              # the threshold of :1480-1489
+        # oracle/restate.py run_step2: melt [pair, receiver, sender], o1 by -inter, o2 by -(inter * weight)
+        melt_inter = inter.transpose(0, 2, 1).reshape(-1)
+        elem = np.arange(npair * L).reshape(npair, C, C).transpose(0, 2, 1).reshape(-1)
+        o1 = np.argsort(-melt_inter, kind="stable")
+        prod = (inter * weight).reshape(-1)[elem[o1]]
+        o2 = np.argsort(-prod, kind="stable")
+        oracle_rows = elem[o1][o2]
+        oracle_rows = oracle_rows[final.reshape(-1)[oracle_rows] > 0]
+        got = U._rows_in_table_order(inter.reshape(npair, L), final.reshape(npair, L), npair, C)
+        npos = int((final > 0).sum())
+        assert sorted(got.tolist()) == list(range(npair * L))
+        assert np.array_equal(got[:npos], oracle_rows)
+        rest = got[npos:]
+        assert (final.reshape(-1)[rest] == 0).all()
+        assert np.array_equal(rest, elem[final.reshape(-1)[elem] == 0])
