@@ -143,6 +143,7 @@ def main():
         tbl_key=key_ref[o_ref], tbl_score=res["interaction_score"].to_numpy()[o_ref],
         tbl_p=res["p_value"].to_numpy()[o_ref], tbl_fdr=res["p_value_fdr"].to_numpy()[o_ref],
         tbl_nlog=res["nlog10_p_value_fdr"].to_numpy()[o_ref],
+        tbl_pos=o_ref,                     # row of the reference's table that holds the j-th key: its row ORDER
     )
     # docstring known answers (laris/tools/_utils.py:133-135, :188-197)
     m = sp.csr_matrix(np.array([[1., 0, 2, 0, 1], [0, 1, 1, 0, 2], [2, 0, 0, 1, 1]]))

@@ -88,6 +88,14 @@ def test_step2_matches_reference(golden):
     assert np.allclose(s2["p_value"][o], golden["tbl_p"], rtol=1e-12)            # permutation counts: exact
     assert np.allclose(s2["p_value_fdr"][o], golden["tbl_fdr"], rtol=1e-9)
     assert np.allclose(s2["nlog10_p_value_fdr"][o], golden["tbl_nlog"], rtol=1e-9, atol=1e-12)
+    # row ORDER of the reference's table (melt, sort by the pre-weight score, sort by the final score - unstable sorts, so
+    # only rows with a distinct positive score are comparable): the restatement's stable sorts put them in the same rows
+    pos = golden["tbl_score"] > 0
+    distinct = pos & (np.unique(golden["tbl_score"], return_counts=True)[1][np.searchsorted(np.unique(golden["tbl_score"]),
+                                                                                             golden["tbl_score"])] == 1)
+    assert distinct.sum() > 400
+    assert golden["tbl_pos"][pos].max() == pos.sum() - 1 and o[pos].max() == pos.sum() - 1      # positive rows come first
+    assert np.array_equal(golden["tbl_pos"][distinct], o[distinct])
 
 
 def test_docstring_known_answers():
