@@ -125,6 +125,15 @@ def main():
         assert np.allclose(r, m, rtol=1e-9, atol=1e-15), (col, np.abs(r - m).max())
     print("restatement == reference on the tiny case: prepare, step 1, step 2 (table, p-values, FDR)")
 
+    # ---- reference: _compute_avg_expression (laris/tools/_utils.py:248-340, unmodified; all groups / a gene subset -
+    # the `groups=` form depends on real AnnData views dropping unused categories, which the duck-typed carrier does not) ----
+    avg_gene_names = ["g00003", "g00150", "g00007"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        avg_all_ref = U._compute_avg_expression(a, groupby="CellTypes")
+        avg_genes_ref = U._compute_avg_expression(a, groupby="CellTypes", genes=avg_gene_names)
+    assert list(avg_all_ref.index) == list(a.obs["CellTypes"].cat.categories) and list(avg_all_ref.columns) == list(a.var_names)
+
     # ---- fixtures -------------------------------------------------------
     os.makedirs(OUT, exist_ok=True)
     X = sp.csr_matrix(a.X)
@@ -144,6 +153,8 @@ def main():
         tbl_p=res["p_value"].to_numpy()[o_ref], tbl_fdr=res["p_value_fdr"].to_numpy()[o_ref],
         tbl_nlog=res["nlog10_p_value_fdr"].to_numpy()[o_ref],
         tbl_pos=o_ref,                     # row of the reference's table that holds the j-th key: its row ORDER
+        avg_all=avg_all_ref.to_numpy(dtype=np.float64), avg_genes=avg_genes_ref.to_numpy(dtype=np.float64),
+        avg_gene_query=np.array(avg_gene_names, dtype=str), avg_gene_columns=np.array(list(avg_genes_ref.columns), dtype=str),
     )
     # docstring known answers (laris/tools/_utils.py:133-135, :188-197)
     m = sp.csr_matrix(np.array([[1., 0, 2, 0, 1], [0, 1, 1, 0, 2], [2, 0, 0, 1, 1]]))

@@ -321,3 +321,25 @@ def test_table_row_order_mirror_equals_the_oracle_sorts():
         rest = got[npos:]
         assert (final.reshape(-1)[rest] == 0).all()
         assert np.array_equal(rest, elem[final.reshape(-1)[elem] == 0])
+
+
+def test_compute_avg_expression_matches_the_reference(golden, tiny):
+    """Host helper laris/tools/_utils.py:248-340 against outputs of the unmodified reference (oracle/make_golden.py): per-category
+    column means, categories x genes, gene subsets in var order; same ValueErrors.  (The reference averages float32 sparse rows
+    in float32; here the sums are float64 - hence the 1e-5 tolerance.)"""
+    import warnings
+    from laris_b200.tools import _utils as U
+    a, _, _ = tiny
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        full = U._compute_avg_expression(a, groupby="CellTypes")
+        sub = U._compute_avg_expression(a, groupby="CellTypes", genes=list(golden["avg_gene_query"]))
+        one = U._compute_avg_expression(a, groupby="CellTypes", groups=["ct03", "ct01"])
+    assert list(full.index) == list(a.obs["CellTypes"].cat.categories) and list(full.columns) == list(a.var_names)
+    assert np.allclose(full.to_numpy(dtype=np.float64), golden["avg_all"], rtol=1e-5, atol=1e-9)
+    assert list(sub.columns) == list(golden["avg_gene_columns"])
+    assert np.allclose(sub.to_numpy(dtype=np.float64), golden["avg_genes"], rtol=1e-5, atol=1e-9)
+    assert list(one.index) == ["ct01", "ct03"] and np.allclose(one.to_numpy(dtype=np.float64), golden["avg_all"][[1, 3]], rtol=1e-5)
+    for bad in (dict(groupby="nope"), dict(groupby="CellTypes", genes=["zzz"]), dict(groupby="CellTypes", groups=["zzz"])):
+        with pytest.raises(ValueError):
+            U._compute_avg_expression(a, **bad)
