@@ -11,6 +11,7 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 
 import os
+import threading
 
 import numpy as np
 import scipy.sparse as sp
@@ -488,10 +489,16 @@ class PendingCSR(sp.csr_matrix):
     ``runLARIS`` works on the device-resident scores and never touches them, so the 1.6 GB download of a 1e6-cell
     matrix overlaps its kernels instead of preceding them.  Copies, slices and pickles are ordinary matrices."""
 
+    _laris_lock = threading.RLock()          # joins are rare; one lock for all pending matrices keeps instances plain
+
     def _laris_join(self):
-        wait = self.__dict__.pop("_laris_wait", None)
-        if wait is not None:
-            wait(self)
+        if "_laris_wait" not in self.__dict__:
+            return
+        with PendingCSR._laris_lock:           # a second reader waits here until the first one has joined the copies
+            wait = self.__dict__.get("_laris_wait")
+            if wait is not None:
+                wait(self)                     # (touches the arrays through __dict__ / the setters only)
+                self.__dict__.pop("_laris_wait", None)
 
     def _laris_pending(self):
         """True while nobody has looked at the arrays (they then still equal the device copy)."""

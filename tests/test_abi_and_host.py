@@ -343,3 +343,27 @@ def test_compute_avg_expression_matches_the_reference(golden, tiny):
     for bad in (dict(groupby="nope"), dict(groupby="CellTypes", genes=["zzz"]), dict(groupby="CellTypes", groups=["zzz"])):
         with pytest.raises(ValueError):
             U._compute_avg_expression(a, **bad)
+
+
+def test_pending_csr_concurrent_readers_all_wait_for_the_join():
+    """Two threads touching a pending matrix at once: the second waits until the first has joined the copies."""
+    import threading
+    import time
+    from laris_b200 import engine
+    A = sp.random(30, 11, 0.4, format="csr", dtype=np.float32, random_state=5)
+    X = engine.PendingCSR((30, 11), dtype=np.float32)
+    X.indptr, X.indices, X.data = A.indptr.copy(), A.indices.copy(), np.zeros_like(A.data)      # "not arrived yet"
+    joins = []
+
+    def wait(m):
+        time.sleep(0.2)
+        m.__dict__["_laris_data"][:] = A.data
+        joins.append(1)
+    X.__dict__["_laris_wait"] = wait
+    seen = []
+    threads = [threading.Thread(target=lambda: seen.append(float(X.data.sum()))) for _ in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert joins == [1] and seen == [float(A.data.sum())] * 4 and not X._laris_pending()
